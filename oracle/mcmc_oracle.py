@@ -1,0 +1,417 @@
+"""CPU restatement of the reference's MCMC hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline
+legs may import this module.  ``pybitup_b200`` (the product) never imports it
+and has no CPU fallback.
+
+It restates, in plain numpy / Python floats, the arithmetic of
+
+* ``pybitup/metropolis_hastings_algorithms.py``  (RWMH :158-224, AM :397-487,
+  DR :512-567, DRAM :570-595, GradientBasedMCMC :621-777, ito_SDE :911-1040,
+  computeGradientFD :1043-1088),
+* ``pybitup/bayesian_inference.py``  (BayesianPosterior.compute_log_value
+  :44-64, Likelihood.arg_gauss_likelihood :495-542, compute_grad_log_value
+  :573-623, Model.run_model :338-371),
+* ``pybitup/distributions.py``  (Uniform.compute_value :282-289,
+  Mixture.compute_log_value :456-479),
+
+with the random draws INJECTED (a ``Streams`` object standing in for the
+stdlib ``random`` module the reference calls at :213, :314, :523, :561).
+
+Pinning: ``tests/test_oracle_golden.py`` checks every function here against
+golden vectors recorded from the UNMODIFIED reference run in the build
+container (``tests/golden/gen_golden.py``; vectors in ``tests/golden/*.npz``).
+The reference's own unit tests assert nothing about chains, so
+those recorded runs are the pin.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.linalg
+
+from . import cpu_models
+
+
+# --------------------------------------------------------------------------- problem
+@dataclass
+class Problem:
+    """Flat description of one Bayesian inverse problem (one model, n_runs data sets)."""
+    model: str                       # 'linear' | 'poly' | 'arrhenius' | 'heat'
+    theta_nom: np.ndarray            # f64[P] nominal full parameter vector (Model.param_nom)
+    unc_idx: np.ndarray              # int[d] position of each uncertain parameter in theta
+    y: np.ndarray                    # f64[n_runs, N]
+    std_y: np.ndarray                # f64[N]
+    lb: np.ndarray                   # f64[d]
+    ub: np.ndarray                   # f64[d]
+    gamma: float = 1.0
+    design: dict = field(default_factory=dict)   # model specific (Phi | x | T0,dT,n_steps,beta)
+
+    @property
+    def d(self):
+        return len(self.unc_idx)
+
+    @property
+    def n_points(self):
+        return self.y.shape[1]
+
+    def full_theta(self, X):
+        # Model.run_model: uncertain values written into the nominal vector (:361-369)
+        th = np.array(self.theta_nom, dtype=np.float64)
+        for i, idx in enumerate(self.unc_idx):
+            th[idx] = X[i]
+        return th
+
+    def model_eval(self, X):
+        th = self.full_theta(X)
+        if self.model == "linear":
+            return cpu_models.linear_design(th, self.design["Phi"])
+        if self.model == "poly":
+            return cpu_models.poly_horner(th, self.design["x"])
+        if self.model == "arrhenius":
+            dg = self.design
+            return cpu_models.arrhenius_rk4(th, dg["T0"], dg["dT"], dg["n_steps"], dg["beta"])
+        if self.model == "heat":
+            return cpu_models.heat_conduction(th, self.design["x"])
+        raise ValueError(self.model)
+
+    def model_grad(self, X):
+        """d f / d X_i for the uncertain parameters, dict i -> f64[N] (analytical)."""
+        th = self.full_theta(X)
+        if self.model == "linear":
+            g = cpu_models.linear_design_grad(th, self.design["Phi"])
+        elif self.model == "poly":
+            g = cpu_models.poly_grad(th, self.design["x"])
+        else:
+            raise ValueError("no analytical gradient for model %r" % self.model)
+        return {i: g[int(idx)] for i, idx in enumerate(self.unc_idx)}
+
+
+def log_prior(prob, X):
+    """Mixture of Uniform: sum_i log(p_i(X_i)); bounds inclusive (distributions.py:282-289, :456-479)."""
+    Y = 0.0
+    with np.errstate(divide="ignore"):
+        for i in range(prob.d):
+            if X[i] < prob.lb[i] or X[i] > prob.ub[i]:
+                p = 0
+            else:
+                p = 1 / abs(prob.ub[i] - prob.lb[i])
+            Y += np.log(p)
+    return Y
+
+
+def arg_gauss_likelihood(prob, X):
+    """J = sum_runs sum_k ((y - f)/(std_y*gamma))^2   (bayesian_inference.py:495-542)."""
+    f = prob.model_eval(X)
+    J = 0
+    for c_run in range(prob.y.shape[0]):
+        arg_exp = (prob.y[c_run] - f) / (prob.std_y * prob.gamma)
+        J = J + np.sum(arg_exp ** 2, axis=0)
+    return J
+
+
+def log_post(prob, X):
+    """BayesianPosterior.compute_log_value with the identity parametrisation (:44-64)."""
+    lp = log_prior(prob, X)
+    if lp == -np.inf:
+        return -np.inf
+    log_like = -(1 / 2) * arg_gauss_likelihood(prob, X)
+    return lp - np.log(1) + log_like
+
+
+def grad_log_post(prob, X):
+    """Analytical gradient: compute_grad_log_value (:573-623) with inv_jac = I, det_jac = 1.
+
+    Only run 0 enters (:606-608) and the prior does not (:80-82).
+    """
+    f = prob.model_eval(X)
+    mg = prob.model_grad(X)
+    ss_x = (prob.y[0] - f) / (prob.std_y ** 2 * prob.gamma ** 2)
+    grad = np.zeros(prob.d)
+    for i in range(prob.d):
+        grad[i] = grad[i] + np.matmul(ss_x, mg[i])
+    return grad
+
+
+def grad_fd(fun, X, eps=1e-10):
+    """computeGradientFD, forward scheme (:1069-1088)."""
+    n = X.size
+    g = np.zeros(n)
+    f0 = fun(X)
+    for i in range(n):
+        Xp = np.array(X)
+        delta = Xp[i] * eps
+        if delta == 0.0:
+            delta = eps
+        Xp[i] = X[i] + delta
+        g[i] = (fun(Xp) - f0) / delta
+    return g
+
+
+# --------------------------------------------------------------------------- streams
+class Streams:
+    """Stand-in for the stdlib ``random`` module: pre-generated normals and uniforms."""
+
+    def __init__(self, normals, uniforms):
+        self.normals = np.asarray(normals, dtype=np.float64)
+        self.uniforms = np.asarray(uniforms, dtype=np.float64)
+        self.i_n = 0
+        self.i_u = 0
+
+    def gauss(self, mu=0.0, sigma=1.0):
+        v = self.normals[self.i_n]
+        self.i_n += 1
+        return mu + sigma * float(v)
+
+    def random(self):
+        v = self.uniforms[self.i_u]
+        self.i_u += 1
+        return float(v)
+
+
+def py_min1(r):
+    """Python's ``min(1, r)``: returns r only when r < 1, so NaN gives 1."""
+    return r if r < 1 else 1
+
+
+def chol_upper(V):
+    """Upper Cholesky factor, V = R^T R: the reference's literal call, scipy.linalg.cholesky with
+    its default lower=False (:143, :487, :592, :703, :775)."""
+    return scipy.linalg.cholesky(np.asarray(V, dtype=np.float64))
+
+
+def inv_upper(R):
+    """scipy.linalg.inv, as the reference calls it on the Cholesky factor (:517, :594, :704)."""
+    return scipy.linalg.inv(np.asarray(R, dtype=np.float64))
+
+
+def chol_upper_plain(V):
+    """Row-by-row upper Cholesky (the order the CUDA device function uses).  Same mathematics as
+    LAPACK's potrf but a different rounding order: on the nearly singular V_i that adaptive
+    Metropolis produces in its first iterations the two differ by cond(V)*eps, which feeds back
+    into the chain (tests/test_oracle_golden.py::test_cholesky_order_sensitivity)."""
+    V = np.asarray(V, dtype=np.float64)
+    n = V.shape[0]
+    R = np.zeros((n, n))
+    for i in range(n):
+        s = V[i, i]
+        for k in range(i):
+            s -= R[k, i] * R[k, i]
+        if not s > 0.0:
+            raise np.linalg.LinAlgError("matrix not positive definite")
+        R[i, i] = np.sqrt(s)
+        for j in range(i + 1, n):
+            t = V[i, j]
+            for k in range(i):
+                t -= R[k, i] * R[k, j]
+            R[i, j] = t / R[i, i]
+    return R
+
+
+def inv_upper_plain(R):
+    """Inverse of an upper-triangular matrix by back substitution."""
+    n = R.shape[0]
+    X = np.zeros((n, n))
+    for j in range(n):
+        X[j, j] = 1.0 / R[j, j]
+        for i in range(j - 1, -1, -1):
+            s = 0.0
+            for k in range(i + 1, j + 1):
+                s += R[i, k] * X[k, j]
+            X[i, j] = -s / R[i, i]
+    return X
+
+
+# --------------------------------------------------------------------------- MH family
+def run_mh(prob, x0, V, n_it, streams, adaptive=False, delayed=False,
+           updating_it=10, eps_v=0.0, gamma_dr=0.2):
+    """RWMH / AM / DR / DRAM for ONE chain, literal reference semantics.
+
+    Returns a dict with chain[T+1,d], lp[T+1] (log-posterior of the current state after
+    each iteration), acc[T] (0 rejected, 1 accepted at stage 1, 2 at stage 2),
+    eval_x / eval_lp (every posterior evaluation in call order), R, V_i, X_av, n_rejected,
+    mean_r and n_eval.
+    """
+    d = prob.d
+    cur = np.array(x0, dtype=np.float64)
+    evals_x, evals_lp = [], []
+
+    def post(X):
+        v = log_post(prob, X)
+        evals_x.append(np.array(X))
+        evals_lp.append(v)
+        return v
+
+    lp_cur = post(cur)
+    if adaptive and delayed:
+        lp_cur = post(cur)          # DRAM runs MetropolisHastings.__init__ twice (:588-589)
+    R = chol_upper(V)
+    S_d = 2.38 ** 2 / d
+    eps_Id = eps_v * np.eye(d)
+    V_i = np.array(V, dtype=np.float64)
+    X_av = None                      # aliases the state until the first adaptation (Q3)
+    inv_V = None
+    if delayed:
+        inv_R = inv_upper(R)
+        inv_V = inv_R * np.transpose(inv_R)      # elementwise (:517-518) -> diag(1/R_ii^2)
+    chain = np.zeros((n_it + 1, d))
+    lps = np.zeros(n_it + 1)
+    acc = np.zeros(n_it, dtype=np.int32)
+    chain[0] = cur
+    lps[0] = lp_cur
+    n_rejected = 0
+    mean_r = 0.0
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        for it in range(1, n_it + 1):
+            z = np.array([streams.gauss(0, 1) for _ in range(d)])
+            new = cur + np.matmul(R, z)                      # :193
+            lp_new = post(new)
+            if lp_new == -np.inf:
+                r = 0
+            else:
+                r = np.exp(lp_new - lp_cur)                  # :205
+            alpha = py_min1(r)
+            u = streams.random()
+            if u < alpha:
+                cur = np.array(new)
+                lp_cur = lp_new
+                acc[it - 1] = 1
+            elif delayed:
+                z2 = np.array([streams.gauss(0, 1) for _ in range(d)])
+                new2 = cur + gamma_dr * np.matmul(R, z2)     # :543
+                lp2 = post(new2)
+                r_12 = np.exp(lp_new - lp2)
+                alpha_12 = py_min1(r_12)
+                diff1 = new - new2
+                diff2 = new - cur
+                M2 = np.matmul(np.matmul(diff1, inv_V), diff1)
+                M4 = np.matmul(np.matmul(diff2, inv_V), diff2)
+                r_2 = np.exp(lp2 - lp_cur) * (np.exp(-1 / 2 * M2) / np.exp(-1 / 2 * M4)) \
+                    * (1 - alpha_12) / (1 - alpha)           # :555-556
+                alpha_2 = py_min1(r_2)
+                u2 = streams.random()
+                if u2 < alpha_2:
+                    cur = np.array(new2)
+                    lp_cur = lp2
+                    acc[it - 1] = 2
+                else:
+                    n_rejected += 1
+            else:
+                n_rejected += 1
+
+            if adaptive:
+                i = it
+                X_i = cur
+                X_av_prev = cur if X_av is None else X_av    # aliasing at i == 1 (Q3)
+                X_av_ip = X_i + (i) / (i + 1) * (X_av_prev - X_i)          # :455
+                V_ip = (i - 1) / i * V_i + S_d / i * (
+                    i * np.tensordot(X_av_prev, X_av_prev, axes=0)
+                    - (i + 1) * np.tensordot(X_av_ip, X_av_ip, axes=0)
+                    + np.tensordot(X_i, X_i, axes=0) + eps_Id)             # :463
+                V_i = V_ip
+                X_av = X_av_ip
+                if i % updating_it == 0:
+                    R = chol_upper(V_i)                      # :487 / :592
+                    if delayed:
+                        inv_R = inv_upper(R)
+                        inv_V = np.transpose(inv_R) * inv_R  # :595
+                mean_r += r                                  # :419 (unclipped, Q9)
+            else:
+                mean_r += alpha                              # :170
+            chain[it] = cur
+            lps[it] = lp_cur
+    return dict(chain=chain, lp=lps, acc=acc, eval_x=np.array(evals_x), eval_lp=np.array(evals_lp),
+                R=R, V_i=V_i, X_av=(cur if X_av is None else X_av), n_rejected=n_rejected,
+                mean_r=mean_r, n_eval=len(evals_lp))
+
+
+# --------------------------------------------------------------------------- Ito-SDE
+def _csv_quantise(v):
+    """What survives np.savetxt(fmt='%f') + pandas.read_csv (bayesian_inference.py:134; Q11/Q18)."""
+    return np.array([float("%f" % t) for t in v])
+
+
+def run_isde(prob, x0, n_it, streams, h, f0, gradient="Analytical", C0=None,
+             starting_it=None, update_it=1, end_it=None, csv_quantise=False):
+    """ito_SDE.run_algorithm (:932-1040) for ONE chain.
+
+    C0: initial preconditioner (identity when None, the 'Identity' branch :661-664).
+    Adaptation window as GradientBasedMCMC.adapt_covariance (:736-777).  The reference
+    initialises the window from the chain CSV re-read from disk (6-decimal text, Q11);
+    ``csv_quantise=True`` reproduces that, ``False`` uses the exact states (what the
+    CUDA engine does, a documented deviation).
+    Returns chain[T+1,d], P[T+1,d], final C, X_av, V_i.
+    """
+    d = prob.d
+    xi = np.array(x0, dtype=np.float64)
+    P = np.zeros(d)
+    C = np.eye(d) if C0 is None else np.array(C0, dtype=np.float64)
+    L_c = chol_upper(C)
+    inv_L_c = inv_upper(L_c)
+    if starting_it is None:
+        starting_it = n_it + 10
+    if end_it is None:
+        end_it = n_it + 1
+    S_d = 1.0
+    eps_Id = 1e-10 * np.eye(d)
+    X_av = np.array(x0, dtype=np.float64)
+    V_i = None
+    hfm = 1 - h * f0 / 4
+    hfp = 1 + h * f0 / 4
+    if gradient == "Analytical":
+        def grad(X):
+            return grad_log_post(prob, X)
+    else:
+        def grad(X):
+            return grad_fd(lambda Z: log_post(prob, Z), X, eps=0.0000000001)
+    chain = np.zeros((n_it + 1, d))
+    Ps = np.zeros((n_it + 1, d))
+    chain[0] = xi
+    rows = [_csv_quantise(xi) if csv_quantise else np.array(xi)]
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        for it in range(1, n_it + 1):
+            cur = xi
+            if starting_it <= it <= end_it + 1:
+                if it == starting_it:
+                    vals = np.array(rows)
+                    X_av = np.mean(vals, axis=0)
+                    V_i = S_d * (np.atleast_2d(np.cov(vals, rowvar=False)) + eps_Id)
+                elif it <= end_it:
+                    X_i = cur
+                    X_av_ip = X_i + (it) / (it + 1) * (X_av - X_i)
+                    V_ip = (it - 1) / it * V_i + S_d / it * (
+                        it * np.tensordot(X_av, X_av, axes=0)
+                        - (it + 1) * np.tensordot(X_av_ip, X_av_ip, axes=0)
+                        + np.tensordot(X_i, X_i, axes=0) + eps_Id)
+                    V_i = V_ip
+                    X_av = X_av_ip
+                if it % update_it == 0:
+                    C = V_i
+                    L_c = chol_upper(C)
+                    inv_L_c = inv_upper(L_c)
+            WP = np.sqrt(h) * np.array([streams.gauss(0, 1) for _ in range(d)])    # :990
+            xi_n = xi + h / 2 * np.matmul(C, P)                                      # :991
+            grad_phi = -grad(xi_n)                                                   # :994
+            P_np = hfm / hfp * P + h / hfp * (-grad_phi) + np.sqrt(f0) / hfp * np.matmul(inv_L_c, WP)
+            xi_np = xi_n + h / 2 * np.matmul(C, P_np)                                # :1001
+            P = P_np
+            xi = xi_np
+            chain[it] = xi
+            Ps[it] = P
+            rows.append(_csv_quantise(xi) if csv_quantise else np.array(xi))
+    return dict(chain=chain, P=Ps, C=C, X_av=X_av, V_i=V_i)
+
+
+# --------------------------------------------------------------------------- propagation
+def propagate(prob, samples):
+    """Monte-Carlo propagation, emulator == 'None' (solve_problem.py:543-647).
+
+    Returns fun_eval[S,N] and the statistics the reference writes: mean, min, max
+    (computed as plain reductions, NOT with the reference's elif/±1e5 quirks, Q15) and the
+    2.5 / 97.5 percentiles (np.percentile, :643-645).
+    """
+    S = samples.shape[0]
+    fe = np.zeros((S, prob.n_points))
+    for s in range(S):
+        fe[s] = prob.model_eval(samples[s])
+    return dict(fun_eval=fe, mean=fe.mean(axis=0), min=fe.min(axis=0), max=fe.max(axis=0),
+                ci_lb=np.percentile(fe, 2.5, axis=0), ci_ub=np.percentile(fe, 97.5, axis=0))

@@ -1,0 +1,295 @@
+"""Generate golden vectors by running the UNMODIFIED reference (jcoheur/pybitup).
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/gen_golden.py
+
+For each case it drives ``pybitup.solve_problem.Sampling(json).sample(models)``
+(``solve_problem.py:125-348``) end to end -- JSON parsing, CSV data loading,
+prior / likelihood / posterior construction, ``Sampler`` dispatch, the sampler
+loop -- with the stdlib ``random`` module the samplers call replaced by
+pre-generated streams (``mha.random = Streams``), and records
+at FULL precision (the chain CSV is 6-decimal text):
+
+* every ``BayesianPosterior.compute_log_value`` call (input, output),
+* the state handed to ``save_sample`` after every iteration,
+* final sampler attributes (R, V_i, X_av_i, n_rejected, mean_r, P for ISDE).
+
+The forward models of the linear / polynomial / Arrhenius cases are this
+repo's (``oracle/cpu_models.py``); the heat-conduction case is the reference's
+own test case (``pybitup/test/test_pce/heat_conduction*.{py,json,csv}``).
+Outputs: ``tests/golden/<case>.npz`` (a few tens of KB each).
+"""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import pandas as pd
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim, cpu_models          # noqa: E402
+from oracle.mcmc_oracle import Streams           # noqa: E402
+from pybitup_b200 import synthetic               # noqa: E402
+
+ref_shim.install()
+import pybitup.solve_problem as sp               # noqa: E402  (the reference)
+import pybitup.bayesian_inference as bi          # noqa: E402
+import pybitup.metropolis_hastings_algorithms as mha  # noqa: E402
+
+
+# ----------------------------------------------------------------------------- reference-side models
+class LinearModel(bi.Model):
+    Phi = None
+
+    def fun_x(self):
+        return cpu_models.linear_design(self.param, self.Phi)
+
+    def d_fx_dparam(self):
+        g = cpu_models.linear_design_grad(self.param, self.Phi)
+        return {name: g[i] for i, name in enumerate(self.param_names)}
+
+    def parametrization_inv_jac(self, X=1):
+        return np.eye(len(X))
+
+    def grad_det_jac(self, X=1):
+        return np.zeros(len(X))
+
+
+class PolyModel(bi.Model):
+    def fun_x(self):
+        return cpu_models.poly_horner(self.param, self.x)
+
+    def d_fx_dparam(self):
+        g = cpu_models.poly_grad(self.param, self.x)
+        return {name: g[i] for i, name in enumerate(self.param_names)}
+
+    def parametrization_inv_jac(self, X=1):
+        return np.eye(len(X))
+
+    def grad_det_jac(self, X=1):
+        return np.zeros(len(X))
+
+
+class ArrheniusModel(bi.Model):
+    cfg = None
+
+    def fun_x(self):
+        c = self.cfg
+        return cpu_models.arrhenius_rk4(self.param, c["T0"], c["dT"], c["n_steps"], c["beta"])
+
+
+def heat_model():
+    sys.path.insert(0, os.path.join(ref_shim.REFERENCE_ROOT, "pybitup", "test", "test_pce"))
+    import heat_conduction                       # the reference's own model file
+    return heat_conduction.HeatConduction()
+
+
+# ----------------------------------------------------------------------------- recording hooks
+class Recorder:
+    def __init__(self):
+        self.eval_x, self.eval_lp, self.saved = [], [], []
+        self.sampler = None
+
+
+def run_reference(workdir, json_name, models, normals, uniforms):
+    rec = Recorder()
+    streams = Streams(normals, uniforms)
+    orig_clv = bi.BayesianPosterior.compute_log_value
+    orig_save = bi.BayesianPosterior.save_sample
+    orig_cov = mha.MetropolisHastings.compute_covariance
+    orig_term = mha.MetropolisHastings.terminate_loop
+    orig_random = mha.random
+
+    def clv(self, Y):
+        v = orig_clv(self, Y)
+        rec.eval_x.append(np.array(Y, dtype=np.float64))
+        rec.eval_lp.append(float(v))
+        return v
+
+    def save(self, IO_fileID, value):
+        rec.saved.append(np.array(value, dtype=np.float64))
+        return orig_save(self, IO_fileID, value)
+
+    def cov(self, n_iterations):
+        # harness workaround: the reference reads its own chain file while
+        # the write handle is unflushed; flush so short runs do not crash.
+        for f in self.IO_fileID.values():
+            f.flush()
+        return orig_cov(self, n_iterations)
+
+    def term(self):
+        rec.sampler = self
+        return orig_term(self)
+
+    bi.BayesianPosterior.compute_log_value = clv
+    bi.BayesianPosterior.save_sample = save
+    mha.MetropolisHastings.compute_covariance = cov
+    mha.MetropolisHastings.terminate_loop = term
+    mha.random = streams
+    cwd = os.getcwd()
+    os.chdir(workdir)
+    try:
+        with np.errstate(all="ignore"):
+            s = sp.Sampling(json_name)
+            s.sample(models)
+            s.__del__()
+    finally:
+        os.chdir(cwd)
+        bi.BayesianPosterior.compute_log_value = orig_clv
+        bi.BayesianPosterior.save_sample = orig_save
+        mha.MetropolisHastings.compute_covariance = orig_cov
+        mha.MetropolisHastings.terminate_loop = orig_term
+        mha.random = orig_random
+    rec.n_normals_used = streams.i_n
+    rec.n_uniforms_used = streams.i_u
+    return rec
+
+
+# ----------------------------------------------------------------------------- case builders
+def write_case(workdir, prob, names, algo_block, x_col):
+    """CSV + JSON exactly in the reference's input format (heat_conduction_1.json is the model)."""
+    N = prob["y"].shape[1]
+    df = pd.DataFrame({"x": x_col, "y": prob["y"][0], "std_y": prob["std_y"]})
+    df.to_csv(os.path.join(workdir, "data.csv"))
+    unc = [int(i) for i in prob["unc_idx"]]
+    prior = {}
+    for k, idx in enumerate(unc):
+        prior[names[idx]] = {"initial_val": float(prob["x0"][k]), "prior_name": "Uniform",
+                             "prior_param": [float(prob["lb"][k]), float(prob["ub"][k])]}
+    js = {"Sampling": {
+        "BayesianPosterior": {
+            "Data": [{"Type": "ReadFromFile", "FileName": "data", "xField": ["x"],
+                      "yField": ["y"], "sigmaField": ["std_y"]}],
+            "Model": [{"param_names": names, "param_values": [float(v) for v in prob["theta_nom"]],
+                       "parametrization": "no"}],
+            "Prior": {"Distribution": "Mixture", "Param": prior},
+            "Likelihood": {"function": "Gaussian", "distance": "L2"}},
+        "Algorithm": algo_block}}
+    with open(os.path.join(workdir, "case.json"), "w") as f:
+        f.write("/* generated by tests/golden/gen_golden.py */\n")
+        json.dump(js, f, indent=1)
+    return N
+
+
+def mh_algo(name, n_it, cov, **kw):
+    blk = {"name": name, "n_iterations": n_it, "save_eval_freq": 10 ** 9,
+           "proposal": {"name": "Gaussian", "covariance": {"type": "full", "value": np.asarray(cov).tolist()}}}
+    if name == "AMH":
+        blk["AMH"] = {"starting_it": 100, "updating_it": kw["updating_it"], "eps_v": kw["eps_v"]}
+    if name == "DR":
+        blk["DR"] = {"gamma": kw["gamma"]}
+    if name == "DRAM":
+        blk["DRAM"] = {"starting_it": 100, "updating_it": kw["updating_it"], "eps_v": kw["eps_v"],
+                       "gamma": kw["gamma"]}
+    return blk
+
+
+def isde_algo(n_it, h, f0, gradient, starting_it, update_it, end_it=None):
+    cov = {"value": "Identity", "starting_it": starting_it, "update_it": update_it}
+    if end_it is not None:
+        cov["end_it"] = end_it
+    return {"name": "ISDE", "n_iterations": n_it, "save_eval_freq": 10 ** 9,
+            "covariance": cov, "gradient": gradient, "ISDE": {"h": h, "f0": f0}}
+
+
+def build_model(prob, names):
+    if prob["model"] == "linear":
+        m = LinearModel()
+        m.Phi = prob["design"]["Phi"]
+    elif prob["model"] == "poly":
+        m = PolyModel()
+    elif prob["model"] == "arrhenius":
+        m = ArrheniusModel()
+        m.cfg = prob["design"]
+    else:
+        m = heat_model()
+    return m
+
+
+def pack_problem(prob):
+    out = {"model": prob["model"], "theta_nom": prob["theta_nom"], "unc_idx": prob["unc_idx"],
+           "y": prob["y"], "std_y": prob["std_y"], "lb": prob["lb"], "ub": prob["ub"],
+           "gamma": prob["gamma"], "x0": prob["x0"], "prop_cov": prob["prop_cov"]}
+    for k, v in prob["design"].items():
+        out["design_" + k] = v
+    return out
+
+
+def run_case(case, prob, names, algo, seed, stream_len):
+    rng = np.random.default_rng(seed)
+    normals = rng.standard_normal(stream_len)
+    uniforms = rng.random(stream_len)
+    with tempfile.TemporaryDirectory() as wd:
+        write_case(wd, prob, names, algo, prob["design"].get("x", np.arange(prob["y"].shape[1], dtype=float)))
+        model = build_model(prob, names)
+        rec = run_reference(wd, "case.json", {"case": model}, normals, uniforms)
+    s = rec.sampler
+    out = pack_problem(prob)
+    out.update(algo_json=json.dumps(algo), normals=normals[:rec.n_normals_used],
+               uniforms=uniforms[:rec.n_uniforms_used],
+               eval_x=np.array(rec.eval_x), eval_lp=np.array(rec.eval_lp), chain=np.array(rec.saved),
+               n_rejected=s.n_rejected, mean_r=float(s.mean_r))
+    for attr in ("R", "V_i", "X_av_i", "inv_V", "C_approx", "P_nm", "xi_nm", "L_c", "inv_L_c"):
+        if hasattr(s, attr):
+            out["final_" + attr] = np.array(getattr(s, attr), dtype=np.float64)
+    path = os.path.join(HERE, case + ".npz")
+    np.savez_compressed(path, **out)
+    print("%-22s evals=%d chain=%s n_rej=%d -> %s (%d B)" % (
+        case, len(rec.eval_lp), np.array(rec.saved).shape, s.n_rejected, os.path.basename(path),
+        os.path.getsize(path)))
+
+
+def main():
+    lin = synthetic.linear_problem()
+    lin_names = ["th0", "th1", "th2"]
+    T = 300
+    run_case("linear_rwmh", lin, lin_names, mh_algo("RWMH", T, lin["prop_cov"]), 11, 4 * T * 4)
+    full_cov = np.array([[1e-3, 2e-3, -1e-3], [2e-3, 1e-2, 1e-3], [-1e-3, 1e-3, 1e-2]])
+    lin2 = dict(lin, prop_cov=full_cov)
+    run_case("linear_rwmh_fullcov", lin2, lin_names, mh_algo("RWMH", T, full_cov), 12, 4 * T * 4)
+    run_case("linear_am", lin, lin_names, mh_algo("AMH", T, lin["prop_cov"], updating_it=10, eps_v=1e-10),
+             13, 4 * T * 4)
+    run_case("linear_dr", lin2, lin_names, mh_algo("DR", T, full_cov, gamma=0.2), 14, 8 * T * 4)
+    run_case("linear_dram", lin, lin_names,
+             mh_algo("DRAM", T, lin["prop_cov"], updating_it=10, eps_v=1e-10, gamma=0.2), 15, 8 * T * 4)
+
+    # prior-box rejection path: tight box so that proposals leave it often
+    lin3 = dict(lin, lb=np.array([0.95, 1.9, 2.9]), ub=np.array([1.05, 2.1, 3.1]), prop_cov=lin["prop_cov"] * 4)
+    run_case("linear_dr_tightbox", lin3, lin_names, mh_algo("DR", T, lin3["prop_cov"], gamma=0.2), 16, 8 * T * 4)
+
+    cub = synthetic.cubic_problem(n_points=100)
+    cub = dict(cub, prop_cov=cub["prop_cov"] * 10)
+    cub_names = ["c0", "c1", "c2", "c3"]
+    run_case("cubic_am", cub, cub_names, mh_algo("AMH", T, cub["prop_cov"], updating_it=10, eps_v=1e-10),
+             21, 5 * T * 4)
+
+    # 60 RK4 steps of 10 K (300 -> 900 K) so that the reaction (~650 K) is inside the ramp
+    arr = synthetic.arrhenius_problem(n_steps=60, dT=10.0)
+    arr_names = ["log10A", "E", "n", "F"]
+    run_case("arrhenius_rwmh", arr, arr_names, mh_algo("RWMH", 200, arr["prop_cov"]), 30, 10 * 200 * 4)
+    run_case("arrhenius_dr", arr, arr_names, mh_algo("DR", 200, arr["prop_cov"] , gamma=0.2), 32, 10 * 200 * 4)
+    run_case("arrhenius_dram", arr, arr_names,
+             mh_algo("DRAM", 200, arr["prop_cov"], updating_it=10, eps_v=1e-10, gamma=0.2), 31, 10 * 200 * 4)
+
+    # the reference's own case: heat conduction, DRAM, eps_v = 0 as in heat_conduction_1.json:33-51
+    heat = synthetic.heat_problem()
+    heat_names = ["a", "b", "k", "T_amb", "phi", "h"]
+    run_case("heat_dram", heat, heat_names,
+             mh_algo("DRAM", 500, heat["prop_cov"], updating_it=10, eps_v=0.0, gamma=0.2), 41, 6 * 500 * 2)
+    run_case("heat_rwmh", heat, heat_names, mh_algo("RWMH", 300, heat["prop_cov"]), 42, 6 * 300 * 2)
+
+    reg = synthetic.regression_problem(n_points=200, d=5)
+    reg_names = ["b%d" % i for i in range(5)]
+    run_case("regression_isde", reg, reg_names, isde_algo(200, 0.02, 4.0, "Analytical", 10 ** 6, 10), 51, 200 * 5)
+    run_case("regression_isde_adapt", reg, reg_names, isde_algo(300, 0.02, 4.0, "Analytical", 100, 10, 250),
+             52, 300 * 5)
+    run_case("linear_isde_fd", lin, lin_names, isde_algo(100, 0.002, 4.0, "Numerical", 10 ** 6, 10), 53, 100 * 3)
+
+
+if __name__ == "__main__":
+    main()
