@@ -1,0 +1,177 @@
+/*
+ * pybitup_b200 -- C ABI of the B200-native batched-chain MCMC engine.
+ *
+ * This is the drop-in boundary for the MCMC hot path of jcoheur/pybitup.  The reference is pure
+ * Python and has no FFI of its own; the entry points below are what a ctypes binding inside the
+ * reference's `pybitup/inference_problem.py` (Sampler.sample, :75-109) and
+ * `pybitup/solve_problem.py` (Propagation.propagate, :543-576) would bind -- see INTEGRATION.md.
+ * Every function cites the reference interface it replaces (file:line relative to the reference
+ * repository root).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types; all floating point data is float64;
+ *   - every function returns PBU_OK (0) or a negative pbu_status; pbu_last_error() gives the
+ *     message of the last failure on the calling thread; no exceptions cross the ABI;
+ *   - "host" pointers are ordinary host memory (pinned or pageable), "dev" pointers are CUDA
+ *     device pointers on the engine's device (e.g. torch.Tensor.data_ptr());
+ *   - one engine belongs to one CUDA device and is used from one host thread at a time
+ *     (the reference's samplers are single threaded and not re-entrant either);
+ *   - chains are independent units: engine g of G owns chains [chain_offset, chain_offset+n_chains)
+ *     of the global chain index space, which also keys the Philox streams, so results do not
+ *     depend on how chains are sharded over GPUs.
+ */
+#ifndef PYBITUP_B200_H
+#define PYBITUP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBU_ABI_VERSION 1
+#define PBU_MAX_PARAM 16 /* max length of the full model parameter vector (P)   */
+#define PBU_MAX_DIM 16   /* max number of uncertain parameters (d)              */
+
+typedef enum {
+    PBU_OK = 0,
+    PBU_ERR_INVALID = -1,     /* bad argument                                    */
+    PBU_ERR_UNSUPPORTED = -2, /* (model, P, d, ...) combination has no kernel     */
+    PBU_ERR_CUDA = -3,        /* CUDA runtime error (message has the detail)     */
+    PBU_ERR_NOT_PD = -4,      /* a covariance was not positive definite (scipy LinAlgError in the
+                                 reference: metropolis_hastings_algorithms.py:143, :487)          */
+    PBU_ERR_STREAM_EXHAUSTED = -5 /* injected random streams too short for the run               */
+} pbu_status;
+
+/* Registered device forward models (the reference ships none: documentation/pybitup_doc.tex:280;
+ * these replace user `bi.Model.fun_x`, bayesian_inference.py:306-308, :371). */
+typedef enum {
+    PBU_MODEL_LINEAR = 0,    /* f_k = sum_j Phi[k][j]*theta[j]; design = Phi (N x P)              */
+    PBU_MODEL_POLY = 1,      /* Horner polynomial in x, theta = coefficients; design = x (N x 1) */
+    PBU_MODEL_ARRHENIUS = 2, /* one-reaction pyrolysis ODE, RK4 over a temperature ramp;
+                                theta = (log10 A, E, n, F); consts = {T0, dT, beta}; no design    */
+    PBU_MODEL_HEAT = 3       /* the reference's test model (test/test_pce/heat_conduction.py:27-41);
+                                theta = (a,b,k,T_amb,phi,h); design = x; consts = {L}             */
+} pbu_model_id;
+
+/* Samplers (inference_problem.py:23-33, :79-107). */
+typedef enum {
+    PBU_ALGO_RWMH = 0, /* MetropolisHastings                         mha.py:26-368   */
+    PBU_ALGO_AM = 1,   /* AdaptiveMetropolisHastings                 mha.py:370-487  */
+    PBU_ALGO_DR = 2,   /* DelayedRejectionMetropolisHastings         mha.py:490-567  */
+    PBU_ALGO_DRAM = 3, /* DelayedRejectionAdaptiveMetropolisHastings mha.py:570-595  */
+    PBU_ALGO_ISDE = 4  /* ito_SDE                                    mha.py:886-1040 */
+} pbu_algo_id;
+
+/* One Bayesian inverse problem: what Sampling.sample builds at solve_problem.py:184-337
+ * (Data :271, Model parameters :200-202, Mixture-of-Uniform prior :322-324, Likelihood :332). */
+typedef struct {
+    int32_t model;            /* pbu_model_id                                                     */
+    int32_t n_param;          /* P: length of theta_nom (Model.param_nom)                         */
+    int32_t n_unc;            /* d: number of uncertain parameters                                */
+    int32_t n_points;         /* N: data points                                                   */
+    int32_t n_runs;           /* Data.n_runs (bayesian_inference.py:160)                          */
+    int32_t n_design_cols;    /* columns of `design` (P for LINEAR, 1 for POLY/HEAT, 0 ARRHENIUS) */
+    const double *theta_nom;  /* host [P]                                                         */
+    const int32_t *unc_idx;   /* host [d]: position of uncertain parameter i inside theta         */
+    const double *design;     /* host [N][n_design_cols] row major, may be NULL when 0 columns    */
+    const double *y;          /* host [n_runs][N]    Data.y[run]                                   */
+    const double *std_y;      /* host [N]            Data.std_y                                    */
+    const double *lb;         /* host [d] Uniform.lb (distributions.py:276)                       */
+    const double *ub;         /* host [d] Uniform.ub (distributions.py:277)                       */
+    double gamma;             /* Likelihood.gamma (bayesian_inference.py:407)                     */
+    double consts[8];         /* model constants, see pbu_model_id                                */
+} pbu_problem;
+
+/* Algorithm block: inference_problem.py:37-107 (JSON keys in SURVEY.md 9.2). */
+typedef struct {
+    int32_t algo;             /* pbu_algo_id                                                      */
+    int32_t updating_it;      /* AMH/DRAM.updating_it          (mha.py:470)                       */
+    double eps_v;             /* AMH/DRAM.eps_v                (mha.py:403)                       */
+    double gamma_dr;          /* DR/DRAM.gamma                 (mha.py:514, :543)                 */
+    double isde_h;            /* ISDE.h                        (mha.py:926)                       */
+    double isde_f0;           /* ISDE.f0                       (mha.py:927)                       */
+    int32_t isde_gradient;    /* 0 Analytical (mha.py:727-729), 1 Numerical forward FD (:724-726)  */
+    int32_t adapt_start;      /* covariance.starting_it        (mha.py:632)  (ISDE)               */
+    int32_t adapt_update;     /* covariance.update_it          (mha.py:633)  (ISDE)               */
+    int32_t adapt_end;        /* covariance.end_it, <=0: n_iterations+1 (mha.py:635-638) (ISDE)   */
+    int32_t am_welford;       /* 0: literal Haario recursion of the reference (mha.py:455,:463);
+                                 1: Welford accumulation (cancellation free, same estimator)      */
+    int32_t nan_rejects;      /* 0: reference semantics, min(1,nan)==1 accepts;
+                                 1: a NaN acceptance ratio rejects                                */
+    int32_t lanes_per_chain;  /* 0 auto; 1,2,4,8: lanes of a warp that share one chain's data sum */
+    int32_t block_threads;    /* 0 auto                                                           */
+    uint64_t seed;            /* Philox key                                                       */
+    uint64_t chain_offset;    /* global index of this engine's first chain (multi-GPU sharding)   */
+} pbu_sampler_cfg;
+
+/* Per-run outputs that live on the device; any pointer may be NULL (= not recorded).
+ * Layouts are chain-minor so that one thread per chain writes coalesced. */
+typedef struct {
+    double *samples;     /* dev [n_keep][d][C]   state after every `thin`-th iteration (chain rows,
+                            bayesian_inference.py:131-138)                                        */
+    double *lp_kept;     /* dev [n_keep][C]      log-posterior of the kept states                 */
+    double *trace_lp1;   /* dev [n_steps][C]     log-posterior of the stage-1 proposal (parity)   */
+    double *trace_lp2;   /* dev [n_steps][C]     ... of the stage-2 proposal, NaN if none         */
+    uint8_t *trace_acc;  /* dev [n_steps][C]     0 rejected, 1 accepted stage 1, 2 stage 2        */
+} pbu_run_outputs;
+
+typedef struct pbu_engine pbu_engine;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int pbu_abi_version(void);
+const char *pbu_last_error(void);
+/* number of (model,P,d) kernel variants compiled in; fills `buf` with a human readable list */
+int pbu_list_kernels(char *buf, int buf_len);
+
+/* ---- engine life cycle: replaces Sampler.__init__ + sampler class __init__
+ *      (inference_problem.py:15-73, metropolis_hastings_algorithms.py:74-155) ------------------- */
+int pbu_engine_create(const pbu_problem *prob, const pbu_sampler_cfg *cfg, int64_t n_chains,
+                      int device, pbu_engine **out);
+int pbu_engine_destroy(pbu_engine *e);
+/* CUDA stream all later work is issued on (a cudaStream_t, e.g. torch's current stream); NULL =
+ * the legacy default stream. */
+int pbu_engine_set_stream(pbu_engine *e, void *cuda_stream);
+
+/* Initial state: x0 host [C][d] (MetropolisHastings.__init__: current_val = param_init, :95-99),
+ * proposal covariance V0 host [d][d] shared by all chains (:80, :142-143; R = upper Cholesky).
+ * Evaluates the initial log-posterior on the device (:102). For ISDE V0 is the preconditioner
+ * C_approx (:653-711) and may be NULL for identity. */
+int pbu_engine_init_chains(pbu_engine *e, const double *x0_host, const double *V0_host);
+
+/* Parity mode: replace Philox by pre-generated streams (what `mha.random = obj` does to the
+ * reference). normals host [C][n_normals], uniforms host [C][n_uniforms]; each chain
+ * consumes its own rows sequentially (d normals then one uniform per stage). n == 0 restores Philox. */
+int pbu_engine_set_streams(pbu_engine *e, const double *normals_host, int64_t n_normals,
+                           const double *uniforms_host, int64_t n_uniforms);
+
+/* ---- the hot loop: replaces run_algorithm (mha.py:158-182, :407-430, :932-1040) -------------- */
+/* Advance every chain by n_steps iterations in ONE kernel launch (asynchronous on the engine's
+ * stream). thin >= 1. Iteration numbering continues across calls. */
+int pbu_engine_run(pbu_engine *e, int64_t n_steps, int64_t thin, const pbu_run_outputs *out);
+/* number of rows `samples` needs for a run of n_steps starting at the engine's current iteration */
+int64_t pbu_engine_n_keep(const pbu_engine *e, int64_t n_steps, int64_t thin);
+int pbu_engine_synchronize(pbu_engine *e);
+
+/* ---- state access (device -> host copies; synchronise the engine's stream) ------------------- */
+int pbu_engine_get_state(pbu_engine *e, double *x_host /*[C][d]*/, double *lp_host /*[C]*/);
+int pbu_engine_get_counters(pbu_engine *e, int64_t *n_rejected /*[C]*/, double *mean_r /*[C]*/,
+                            int64_t *n_eval /*[C]*/, int32_t *status /*[C]*/);
+/* per-chain proposal factor R (upper, V = R^T R; mha.py:143,:487), adaptive covariance V_i
+ * (:463-466) and running mean X_av_i (:455,:467); any pointer may be NULL. Row-major [C][d][d]. */
+int pbu_engine_get_proposal(pbu_engine *e, double *R_host, double *V_host, double *xav_host);
+int64_t pbu_engine_iteration(const pbu_engine *e);
+
+/* ---- evaluation only: BayesianPosterior.compute_log_value (bayesian_inference.py:44-64) and
+ *      Model.run_model (:338-371) for S parameter vectors -------------------------------------- */
+int pbu_eval_logpost(pbu_engine *e, const double *X_host /*[S][d]*/, int64_t S, double *lp_host /*[S]*/);
+int pbu_eval_model(pbu_engine *e, const double *X_host /*[S][d]*/, int64_t S, double *f_host /*[S][N]*/);
+
+/* ---- measurement helper: achieved FP64 FMA throughput of the device (TFLOP/s, FMA = 2 flops) from a
+ *      register-resident DFMA loop; the denominator of the FP64 roofline in bench.py ------------- */
+int pbu_measure_fp64_peak(int device, int iters, int reps, double *tflops, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYBITUP_B200_H */

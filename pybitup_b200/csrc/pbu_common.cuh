@@ -1,0 +1,196 @@
+// Shared device-side definitions of the pybitup_b200 engine (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/pybitup_b200.h"
+
+namespace pbu {
+
+// ------------------------------------------------------------------------------------------------
+// Problem as the kernels see it.  Passed by value as a __grid_constant__ kernel parameter, so the
+// small per-problem vectors live in the constant bank and indexing them with unrolled loop
+// counters costs nothing.
+// ------------------------------------------------------------------------------------------------
+struct ProblemDev {
+    const double *records;   // dev [N][ncol] point records: [design cols | w = 1/(std_y*gamma) | y_run0 | pad | y_run1.. ]
+    int32_t n_points;
+    int32_t n_runs;
+    int32_t ncol;            // doubles per record (even)
+    int32_t ncol0;           // doubles of the vector-loaded head of a record (even): design, w, y_run0
+    int32_t n_param;
+    int32_t n_unc;
+    int32_t unc_idx[PBU_MAX_DIM];
+    double theta_nom[PBU_MAX_PARAM];
+    double lb[PBU_MAX_DIM];
+    double ub[PBU_MAX_DIM];
+    double log_prior_const;  // sum_i log(1/|ub_i-lb_i|)  (Mixture.compute_log_value, distributions.py:456-479)
+    double consts[8];
+};
+
+// Chain state, structure-of-arrays with stride = n_chains (coalesced for one thread per chain).
+struct ChainState {
+    int64_t n_chains;
+    double *x;        // [d][C]      current_val                      (mha.py:99)
+    double *lp;       // [C]         distr_fun_current_val            (mha.py:102)
+    double *R;        // [d(d+1)/2][C] packed upper Cholesky factor   (mha.py:143)
+    double *xav;      // [d][C]      X_av_i                           (mha.py:405)
+    double *V;        // [d(d+1)/2][C] packed upper V_i               (mha.py:404)
+    double *mean_r;   // [C]                                          (mha.py:154,:170,:419)
+    int64_t *n_rej;   // [C]         n_rejected                       (mha.py:146)
+    int64_t *n_eval;  // [C]         posterior evaluations
+    int32_t *status;  // [C]         bit0: Cholesky failed (not PD), bit1: stream exhausted, bit2: NaN ratio seen
+    // Welford moments of the visited states (for pooled covariance / R-hat; K4 input)
+    double *wmean;    // [d][C]
+    double *wM2;      // [d(d+1)/2][C]
+    int64_t *wcount;  // [C]
+    // ISDE
+    double *P;        // [d][C]      momentum P_nm                    (mha.py:920)
+};
+
+struct StreamsDev {
+    const double *normals;   // [C][n_normals]  (row per chain)
+    const double *uniforms;  // [C][n_uniforms]
+    int64_t n_normals;
+    int64_t n_uniforms;
+    int64_t *cur_n;          // [C] cursors
+    int64_t *cur_u;          // [C]
+};
+
+struct MhParams {
+    ProblemDev prob;
+    ChainState st;
+    StreamsDev streams;       // normals == nullptr -> Philox
+    pbu_run_outputs out;
+    int64_t it0;              // iterations already done (global counter, 0 at start)
+    int64_t n_steps;
+    int64_t thin;
+    int64_t keep0;            // number of kept rows before this launch (for absolute thinning phase)
+    uint64_t seed;
+    uint64_t chain_offset;
+    double eps_v;
+    double gamma_dr;
+    double S_d;               // 2.38^2/d (mha.py:402)
+    int32_t updating_it;
+    int32_t delayed;          // DR / DRAM
+    int32_t am_welford;
+    int32_t nan_rejects;
+    int32_t resident;         // 1: all records fit in shared memory
+    int32_t tile_points;      // streaming mode: points per shared-memory tile
+};
+
+// status bits
+enum { ST_NOT_PD = 1, ST_STREAM_EXHAUSTED = 2, ST_NAN_RATIO = 4 };
+
+__host__ __device__ constexpr int tri_size(int d) { return d * (d + 1) / 2; }
+// packed row-major upper triangle: (i, j>=i)
+__host__ __device__ constexpr int tri_idx(int d, int i, int j) { return i * d - (i * (i - 1)) / 2 + (j - i); }
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), counter based: counter = (chain, iteration lo, iteration
+// hi | stage<<28, block), key = seed.
+// ------------------------------------------------------------------------------------------------
+struct Philox {
+    static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    __device__ __forceinline__ static uint4 round10(uint4 c, uint2 k) {
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+            uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+            c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+            k.x += W0;
+            k.y += W1;
+        }
+        return c;
+    }
+};
+
+// two standard normals from two 32-bit words: Box-Muller in fp32 (as curand_normal does), widened.
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, double &z0, double &z1) {
+    float u = (float)a * 2.3283064365386963e-10f + 1.1641532182693481e-10f;   // (0,1]
+    float v = (float)b * 2.3283064365386963e-10f + 1.1641532182693481e-10f;
+    float s = sqrtf(-2.0f * logf(u));
+    float sn, cs;
+    sincospif(2.0f * v, &sn, &cs);
+    z0 = (double)(s * cs);
+    z1 = (double)(s * sn);
+}
+
+// uniform in (0,1) with 53 random bits
+__device__ __forceinline__ double uniform53(uint32_t a, uint32_t b) {
+    uint64_t bits = ((uint64_t)a << 21) ^ (uint64_t)(b >> 11);   // 53 bits
+    return ((double)bits + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1-D bulk TMA copy global -> shared with mbarrier completion (cp.async.bulk, SASS UBLKCP).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// bytes must be a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small dense helpers on packed upper triangles, fully unrolled (D compile time).
+// ------------------------------------------------------------------------------------------------
+// Upper Cholesky V = R^T R, row by row (the order scipy's potrf result is compared against in
+// tests/test_oracle_golden.py::test_cholesky_order_sensitivity). Returns false if not PD.
+template <int D>
+__device__ __forceinline__ bool chol_upper_packed(const double (&V)[tri_size(D)], double (&R)[tri_size(D)]) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double s = V[tri_idx(D, i, i)];
+#pragma unroll
+        for (int k = 0; k < i; ++k) s -= R[tri_idx(D, k, i)] * R[tri_idx(D, k, i)];
+        if (!(s > 0.0)) ok = false;
+        double rii = sqrt(s);
+        R[tri_idx(D, i, i)] = rii;
+#pragma unroll
+        for (int j = i + 1; j < D; ++j) {
+            double t = V[tri_idx(D, i, j)];
+#pragma unroll
+            for (int k = 0; k < i; ++k) t -= R[tri_idx(D, k, i)] * R[tri_idx(D, k, j)];
+            R[tri_idx(D, i, j)] = t / rii;
+        }
+    }
+    return ok;
+}
+
+// Python's min(1, r): r only when r < 1, so NaN -> 1
+__device__ __forceinline__ double py_min1(double r) { return (r < 1.0) ? r : 1.0; }
+
+}  // namespace pbu

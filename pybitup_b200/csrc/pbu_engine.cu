@@ -1,0 +1,562 @@
+// Host side of the C ABI (include/pybitup_b200.h): engine life cycle, problem lowering to device
+// records, kernel selection and launches.  No torch, no exceptions across the ABI.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pbu_mh_kernel.cuh"
+#include "pbu_registry.h"
+
+using namespace pbu;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(PBU_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+struct pbu_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    pbu_sampler_cfg cfg{};
+    ProblemDev prob{};
+    int d = 0, P = 0, nt = 0;
+    int64_t C = 0;
+    int64_t iteration = 0;
+    bool initialised = false;
+    const MhKernelEntry *mh = nullptr;
+    const EvalKernelEntry *ev = nullptr;
+    int lanes = 1;
+    int block = 128;
+    size_t smem_bytes = 0;
+    // device allocations
+    double *d_records = nullptr;
+    ChainState st{};
+    StreamsDev streams{};
+    double *d_normals = nullptr, *d_uniforms = nullptr;
+    std::vector<void *> allocs;
+};
+
+template <class T>
+static int dev_alloc(pbu_engine *e, T **p, size_t n) {
+    void *q = nullptr;
+    CUDA_TRY(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+    CUDA_TRY(cudaMemsetAsync(q, 0, std::max<size_t>(n, 1) * sizeof(T), e->stream));
+    e->allocs.push_back(q);
+    *p = static_cast<T *>(q);
+    return PBU_OK;
+}
+
+// host [C][d] -> host [d][C]
+static void transpose_to_soa(const double *src, int64_t C, int d, std::vector<double> &dst) {
+    dst.resize((size_t)C * d);
+    for (int64_t c = 0; c < C; ++c)
+        for (int i = 0; i < d; ++i) dst[(size_t)i * C + c] = src[(size_t)c * d + i];
+}
+static void transpose_from_soa(const std::vector<double> &src, int64_t C, int d, double *dst) {
+    for (int64_t c = 0; c < C; ++c)
+        for (int i = 0; i < d; ++i) dst[(size_t)c * d + i] = src[(size_t)i * C + c];
+}
+
+static bool chol_upper_host(const double *V, int d, std::vector<double> &Rp) {
+    // same row-by-row order as pbu::chol_upper_packed
+    Rp.assign(tri_size(d), 0.0);
+    for (int i = 0; i < d; ++i) {
+        double s = V[i * d + i];
+        for (int k = 0; k < i; ++k) s -= Rp[tri_idx(d, k, i)] * Rp[tri_idx(d, k, i)];
+        if (!(s > 0.0)) return false;
+        double rii = std::sqrt(s);
+        Rp[tri_idx(d, i, i)] = rii;
+        for (int j = i + 1; j < d; ++j) {
+            double t = V[i * d + j];
+            for (int k = 0; k < i; ++k) t -= Rp[tri_idx(d, k, i)] * Rp[tri_idx(d, k, j)];
+            Rp[tri_idx(d, i, j)] = t / rii;
+        }
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" __attribute__((visibility("default"))) int pbu_abi_version(void) { return PBU_ABI_VERSION; }
+extern "C" __attribute__((visibility("default"))) const char *pbu_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" __attribute__((visibility("default"))) int pbu_list_kernels(char *buf, int buf_len) {
+    std::string s;
+    int n = 0;
+    for (const MhKernelEntry *t = pbu_mh_kernels(&n); t && s.size() < 1u << 20 && n > 0; --n, ++t) {
+        char line[128];
+        snprintf(line, sizeof line, "mh model=%d P=%d d=%d lanes=%d adapt=%d\n", t->model, t->n_param, t->n_unc, t->lanes, t->adapt);
+        s += line;
+    }
+    int total = 0;
+    pbu_mh_kernels(&total);
+    if (buf && buf_len > 0) {
+        strncpy(buf, s.c_str(), buf_len - 1);
+        buf[buf_len - 1] = 0;
+    }
+    return total;
+}
+
+static const MhKernelEntry *find_mh(int model, int P, int d, int lanes, int adapt) {
+    int n = 0;
+    const MhKernelEntry *t = pbu_mh_kernels(&n);
+    for (int i = 0; i < n; ++i)
+        if (t[i].model == model && t[i].n_param == P && t[i].n_unc == d && t[i].lanes == lanes && t[i].adapt == adapt) return &t[i];
+    return nullptr;
+}
+static const EvalKernelEntry *find_eval(int model, int P, int d) {
+    int n = 0;
+    const EvalKernelEntry *t = pbu_eval_kernels(&n);
+    for (int i = 0; i < n; ++i)
+        if (t[i].model == model && t[i].n_param == P && t[i].n_unc == d) return &t[i];
+    return nullptr;
+}
+
+// Lower the problem to point records [N][ncol]: [design | w | y0 | pad | y1..]
+static int build_records(const pbu_problem *pr, int nd, std::vector<double> &rec, int &ncol, int &ncol0) {
+    const int N = pr->n_points, nr = pr->n_runs;
+    ncol0 = even_up(nd + 2);
+    ncol = ncol0 + even_up(nr - 1);
+    rec.assign((size_t)N * ncol, 0.0);
+    for (int k = 0; k < N; ++k) {
+        double *r = &rec[(size_t)k * ncol];
+        if (pr->model == PBU_MODEL_ARRHENIUS) {
+            const double T0 = pr->consts[0], dT = pr->consts[1];
+            r[0] = 1.0 / (T0 + ((double)k + 0.5) * dT);
+            r[1] = 1.0 / (T0 + ((double)k + 1.0) * dT);
+        } else {
+            for (int j = 0; j < nd; ++j) r[j] = pr->design[(size_t)k * pr->n_design_cols + j];
+        }
+        r[nd] = 1.0 / (pr->std_y[k] * pr->gamma);
+        r[nd + 1] = pr->y[k];
+        for (int q = 1; q < nr; ++q) r[ncol0 + q - 1] = pr->y[(size_t)q * N + k];
+    }
+    return PBU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pbu_problem *pr, const pbu_sampler_cfg *cfg, int64_t n_chains, int device, pbu_engine **out) {
+    if (!pr || !cfg || !out) return fail(PBU_ERR_INVALID, "null argument");
+    if (n_chains < 1) return fail(PBU_ERR_INVALID, "n_chains must be >= 1");
+    if (pr->n_unc < 1 || pr->n_unc > PBU_MAX_DIM || pr->n_param < pr->n_unc || pr->n_param > PBU_MAX_PARAM)
+        return fail(PBU_ERR_INVALID, "bad parameter counts P=%d d=%d", pr->n_param, pr->n_unc);
+    if (pr->n_points < 1 || pr->n_runs < 1) return fail(PBU_ERR_INVALID, "need n_points >= 1 and n_runs >= 1");
+    if (!pr->theta_nom || !pr->unc_idx || !pr->y || !pr->std_y || !pr->lb || !pr->ub) return fail(PBU_ERR_INVALID, "null problem array");
+    int nd;
+    switch (pr->model) {
+        case PBU_MODEL_LINEAR: nd = pr->n_param; break;
+        case PBU_MODEL_POLY: nd = 1; break;
+        case PBU_MODEL_ARRHENIUS: nd = 2; break;
+        case PBU_MODEL_HEAT: nd = 1; break;
+        default: return fail(PBU_ERR_INVALID, "unknown model id %d", pr->model);
+    }
+    if (pr->model != PBU_MODEL_ARRHENIUS && (pr->n_design_cols != nd || !pr->design))
+        return fail(PBU_ERR_INVALID, "model %d needs %d design column(s), got %d", pr->model, nd, pr->n_design_cols);
+    for (int i = 0; i < pr->n_unc; ++i)
+        if (pr->unc_idx[i] < 0 || pr->unc_idx[i] >= pr->n_param) return fail(PBU_ERR_INVALID, "unc_idx[%d] out of range", i);
+    const bool adapt = cfg->algo == PBU_ALGO_AM || cfg->algo == PBU_ALGO_DRAM;
+    if (adapt && cfg->updating_it < 1) return fail(PBU_ERR_INVALID, "updating_it must be >= 1");
+
+    const EvalKernelEntry *ev = find_eval(pr->model, pr->n_param, pr->n_unc);
+    if (!ev)
+        return fail(PBU_ERR_UNSUPPORTED, "no device kernel for model=%d with P=%d parameters, d=%d uncertain (see pbu_list_kernels)",
+                    pr->model, pr->n_param, pr->n_unc);
+
+    CUDA_TRY(cudaSetDevice(device));
+    pbu_engine *e = new pbu_engine();
+    e->device = device;
+    e->cfg = *cfg;
+    e->C = n_chains;
+    e->d = pr->n_unc;
+    e->P = pr->n_param;
+    e->nt = tri_size(e->d);
+    e->ev = ev;
+
+    // ---- lanes per chain
+    int lanes = cfg->lanes_per_chain;
+    if (ev->sequential) lanes = 1;
+    if (lanes == 0) {
+        // minimise ceil(blocks/148)/G over the compiled lane counts; ties -> fewer lanes
+        const int cand[3] = {1, 2, 8};
+        double best = 1e300;
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+        for (int g : cand) {
+            double blocks = std::ceil((double)n_chains * g / 128.0);
+            double t = std::ceil(blocks / nsm) / g;
+            if (t < best * (1.0 - 1e-9)) {
+                best = t;
+                lanes = g;
+            }
+        }
+    }
+    e->lanes = lanes;
+    e->block = cfg->block_threads > 0 ? cfg->block_threads : 128;
+    if (e->block % 32 != 0 || e->block > 1024) {
+        delete e;
+        return fail(PBU_ERR_INVALID, "block_threads must be a multiple of 32 and <= 1024");
+    }
+    if (cfg->algo != PBU_ALGO_ISDE) {
+        e->mh = find_mh(pr->model, pr->n_param, pr->n_unc, lanes, adapt ? 1 : 0);
+        if (!e->mh) {
+            delete e;
+            return fail(PBU_ERR_UNSUPPORTED, "no MH kernel for model=%d P=%d d=%d lanes=%d adapt=%d", pr->model, pr->n_param, pr->n_unc,
+                        lanes, (int)adapt);
+        }
+    } else {
+        delete e;
+        return fail(PBU_ERR_UNSUPPORTED, "ISDE kernel not built in this library version");
+    }
+
+    // ---- problem records
+    std::vector<double> rec;
+    int ncol, ncol0;
+    build_records(pr, nd, rec, ncol, ncol0);
+    ProblemDev &pd = e->prob;
+    memset(&pd, 0, sizeof pd);
+    pd.n_points = pr->n_points;
+    pd.n_runs = pr->n_runs;
+    pd.ncol = ncol;
+    pd.ncol0 = ncol0;
+    pd.n_param = pr->n_param;
+    pd.n_unc = pr->n_unc;
+    for (int i = 0; i < PBU_MAX_DIM; ++i) pd.unc_idx[i] = -1;
+    double lpc = 0.0;
+    for (int i = 0; i < pr->n_unc; ++i) {
+        pd.unc_idx[i] = pr->unc_idx[i];
+        pd.lb[i] = pr->lb[i];
+        pd.ub[i] = pr->ub[i];
+        lpc += std::log(1.0 / std::fabs(pr->ub[i] - pr->lb[i]));      // distributions.py:278, :475
+    }
+    pd.log_prior_const = lpc;
+    for (int i = 0; i < pr->n_param; ++i) pd.theta_nom[i] = pr->theta_nom[i];
+    for (int i = 0; i < 8; ++i) pd.consts[i] = pr->consts[i];
+
+    e->smem_bytes = 128 + rec.size() * sizeof(double);
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if ((int64_t)e->smem_bytes > (int64_t)max_smem) {
+        delete e;
+        return fail(PBU_ERR_UNSUPPORTED, "point records need %zu B of shared memory, device allows %d B (streaming mode not built)",
+                    e->smem_bytes, max_smem);
+    }
+    int rc;
+    if ((rc = dev_alloc(e, &e->d_records, rec.size())) != PBU_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(e->d_records, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    pd.records = e->d_records;
+
+    // ---- chain state
+    const int64_t C = n_chains;
+    ChainState &st = e->st;
+    st.n_chains = C;
+    if ((rc = dev_alloc(e, &st.x, (size_t)e->d * C)) || (rc = dev_alloc(e, &st.lp, (size_t)C)) ||
+        (rc = dev_alloc(e, &st.R, (size_t)e->nt * C)) || (rc = dev_alloc(e, &st.xav, (size_t)e->d * C)) ||
+        (rc = dev_alloc(e, &st.V, (size_t)e->nt * C)) || (rc = dev_alloc(e, &st.mean_r, (size_t)C)) ||
+        (rc = dev_alloc(e, &st.n_rej, (size_t)C)) || (rc = dev_alloc(e, &st.n_eval, (size_t)C)) ||
+        (rc = dev_alloc(e, &st.status, (size_t)C)) || (rc = dev_alloc(e, &st.wmean, (size_t)e->d * C)) ||
+        (rc = dev_alloc(e, &st.wM2, (size_t)e->nt * C)) || (rc = dev_alloc(e, &st.wcount, (size_t)C)) ||
+        (rc = dev_alloc(e, &st.P, (size_t)e->d * C)) || (rc = dev_alloc(e, &e->streams.cur_n, (size_t)C)) ||
+        (rc = dev_alloc(e, &e->streams.cur_u, (size_t)C)))
+        return rc;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    *out = e;
+    return PBU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pbu_engine_destroy(pbu_engine *e) {
+    if (!e) return PBU_OK;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (void *p : e->allocs) cudaFree(p);
+    if (e->d_normals) cudaFree(e->d_normals);
+    if (e->d_uniforms) cudaFree(e->d_uniforms);
+    delete e;
+    return PBU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pbu_engine_set_stream(pbu_engine *e, void *cuda_stream) {
+    if (!e) return fail(PBU_ERR_INVALID, "null engine");
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->stream = static_cast<cudaStream_t>(cuda_stream);
+    return PBU_OK;
+}
+
+static int launch_eval_lp(pbu_engine *e, const double *X_soa_dev, int64_t S, double *lp_dev) {
+    CUDA_TRY(cudaFuncSetAttribute(e->ev->eval_lp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    const int block = 128;
+    const unsigned grid = (unsigned)((S + block - 1) / block);
+    void *args[] = {(void *)&e->prob, (void *)&X_soa_dev, (void *)&S, (void *)&lp_dev};
+    CUDA_TRY(cudaLaunchKernel(e->ev->eval_lp, dim3(grid), dim3(block), args, e->smem_bytes, e->stream));
+    return PBU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pbu_engine_init_chains(pbu_engine *e, const double *x0_host, const double *V0_host) {
+    if (!e || !x0_host) return fail(PBU_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int d = e->d, nt = e->nt;
+    const int64_t C = e->C;
+    std::vector<double> soa;
+    transpose_to_soa(x0_host, C, d, soa);
+    CUDA_TRY(cudaMemcpyAsync(e->st.x, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    const bool adapt = e->cfg.algo == PBU_ALGO_AM || e->cfg.algo == PBU_ALGO_DRAM;
+    std::vector<double> Vid;
+    if (!V0_host) {
+        Vid.assign((size_t)d * d, 0.0);
+        for (int i = 0; i < d; ++i) Vid[i * d + i] = 1.0;
+        V0_host = Vid.data();
+    }
+    std::vector<double> Rp;
+    if (!chol_upper_host(V0_host, d, Rp))
+        return fail(PBU_ERR_NOT_PD, "proposal covariance is not positive definite (scipy.linalg.cholesky would raise LinAlgError)");
+    std::vector<double> buf((size_t)nt * C);
+    for (int i = 0; i < nt; ++i) std::fill(buf.begin() + (size_t)i * C, buf.begin() + (size_t)(i + 1) * C, Rp[i]);
+    CUDA_TRY(cudaMemcpyAsync(e->st.R, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));   // buf reused below
+    if (adapt) {
+        // V_i = V_0 (mha.py:404), X_av_i = param_init (:405); Welford mode starts from M2 = 0
+        for (int i = 0; i < d; ++i)
+            for (int j = i; j < d; ++j) {
+                const double v = e->cfg.am_welford ? 0.0 : V0_host[i * d + j];
+                std::fill(buf.begin() + (size_t)tri_idx(d, i, j) * C, buf.begin() + (size_t)(tri_idx(d, i, j) + 1) * C, v);
+            }
+        CUDA_TRY(cudaMemcpyAsync(e->st.V, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        CUDA_TRY(cudaMemcpyAsync(e->st.xav, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    }
+    CUDA_TRY(cudaMemsetAsync(e->st.mean_r, 0, C * sizeof(double), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->st.n_rej, 0, C * sizeof(int64_t), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->st.status, 0, C * sizeof(int32_t), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->st.wmean, 0, (size_t)d * C * sizeof(double), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->st.wM2, 0, (size_t)nt * C * sizeof(double), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->st.wcount, 0, C * sizeof(int64_t), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->st.P, 0, (size_t)d * C * sizeof(double), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->streams.cur_n, 0, C * sizeof(int64_t), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->streams.cur_u, 0, C * sizeof(int64_t), e->stream));
+    // initial posterior evaluation(s): once, twice for DRAM (double __init__, mha.py:588-589)
+    std::vector<int64_t> ne((size_t)C, e->cfg.algo == PBU_ALGO_DRAM ? 2 : 1);
+    CUDA_TRY(cudaMemcpyAsync(e->st.n_eval, ne.data(), C * sizeof(int64_t), cudaMemcpyHostToDevice, e->stream));
+    int rc = launch_eval_lp(e, e->st.x, C, e->st.lp);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->iteration = 0;
+    e->initialised = true;
+    return PBU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pbu_engine_set_streams(pbu_engine *e, const double *normals_host, int64_t n_normals, const double *uniforms_host,
+                                      int64_t n_uniforms) {
+    if (!e) return fail(PBU_ERR_INVALID, "null engine");
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (e->d_normals) cudaFree(e->d_normals);
+    if (e->d_uniforms) cudaFree(e->d_uniforms);
+    e->d_normals = e->d_uniforms = nullptr;
+    e->streams.normals = e->streams.uniforms = nullptr;
+    e->streams.n_normals = e->streams.n_uniforms = 0;
+    if (n_normals <= 0 || !normals_host) return PBU_OK;
+    if (!uniforms_host || n_uniforms <= 0) return fail(PBU_ERR_INVALID, "uniform stream missing");
+    CUDA_TRY(cudaMalloc(&e->d_normals, (size_t)e->C * n_normals * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&e->d_uniforms, (size_t)e->C * n_uniforms * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(e->d_normals, normals_host, (size_t)e->C * n_normals * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(e->d_uniforms, uniforms_host, (size_t)e->C * n_uniforms * sizeof(double), cudaMemcpyHostToDevice));
+    e->streams.normals = e->d_normals;
+    e->streams.uniforms = e->d_uniforms;
+    e->streams.n_normals = n_normals;
+    e->streams.n_uniforms = n_uniforms;
+    CUDA_TRY(cudaMemsetAsync(e->streams.cur_n, 0, e->C * sizeof(int64_t), e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->streams.cur_u, 0, e->C * sizeof(int64_t), e->stream));
+    return PBU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t pbu_engine_n_keep(const pbu_engine *e, int64_t n_steps, int64_t thin) {
+    if (!e || thin < 1 || n_steps < 0) return -1;
+    return (e->iteration + n_steps) / thin - e->iteration / thin;
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t pbu_engine_iteration(const pbu_engine *e) { return e ? e->iteration : -1; }
+
+extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine *e, int64_t n_steps, int64_t thin, const pbu_run_outputs *out) {
+    if (!e) return fail(PBU_ERR_INVALID, "null engine");
+    if (!e->initialised) return fail(PBU_ERR_INVALID, "pbu_engine_init_chains has not been called");
+    if (n_steps < 0 || thin < 1) return fail(PBU_ERR_INVALID, "need n_steps >= 0 and thin >= 1");
+    if (n_steps == 0) return PBU_OK;
+    CUDA_TRY(cudaSetDevice(e->device));
+    MhParams p;
+    memset(&p, 0, sizeof p);
+    p.prob = e->prob;
+    p.st = e->st;
+    p.streams = e->streams;
+    if (out) p.out = *out;
+    p.it0 = e->iteration;
+    p.n_steps = n_steps;
+    p.thin = thin;
+    p.seed = e->cfg.seed;
+    p.chain_offset = e->cfg.chain_offset;
+    p.eps_v = e->cfg.eps_v;
+    p.gamma_dr = e->cfg.gamma_dr;
+    p.S_d = 2.38 * 2.38 / (double)e->d;     // mha.py:402
+    p.updating_it = e->cfg.updating_it > 0 ? e->cfg.updating_it : 1;
+    p.delayed = (e->cfg.algo == PBU_ALGO_DR || e->cfg.algo == PBU_ALGO_DRAM) ? 1 : 0;
+    p.am_welford = e->cfg.am_welford;
+    p.nan_rejects = e->cfg.nan_rejects;
+    p.resident = 1;
+    CUDA_TRY(cudaFuncSetAttribute(e->mh->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    const int64_t threads = e->C * e->lanes;
+    const unsigned grid = (unsigned)((threads + e->block - 1) / e->block);
+    void *args[] = {(void *)&p};
+    CUDA_TRY(cudaLaunchKernel(e->mh->fn, dim3(grid), dim3(e->block), args, e->smem_bytes, e->stream));
+    e->iteration += n_steps;
+    return PBU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pbu_engine_synchronize(pbu_engine *e) {
+    if (!e) return fail(PBU_ERR_INVALID, "null engine");
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PBU_OK;
+}
+
+template <class T>
+static int d2h(pbu_engine *e, const T *dev, size_t n, std::vector<T> &host) {
+    host.resize(n);
+    CUDA_TRY(cudaMemcpyAsync(host.data(), dev, n * sizeof(T), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PBU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pbu_engine_get_state(pbu_engine *e, double *x_host, double *lp_host) {
+    if (!e) return fail(PBU_ERR_INVALID, "null engine");
+    CUDA_TRY(cudaSetDevice(e->device));
+    int rc;
+    if (x_host) {
+        std::vector<double> soa;
+        if ((rc = d2h(e, e->st.x, (size_t)e->d * e->C, soa))) return rc;
+        transpose_from_soa(soa, e->C, e->d, x_host);
+    }
+    if (lp_host) {
+        CUDA_TRY(cudaMemcpyAsync(lp_host, e->st.lp, e->C * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    }
+    return PBU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pbu_engine_get_counters(pbu_engine *e, int64_t *n_rejected, double *mean_r, int64_t *n_eval, int32_t *status) {
+    if (!e) return fail(PBU_ERR_INVALID, "null engine");
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (n_rejected) CUDA_TRY(cudaMemcpyAsync(n_rejected, e->st.n_rej, e->C * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
+    if (mean_r) CUDA_TRY(cudaMemcpyAsync(mean_r, e->st.mean_r, e->C * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (n_eval) CUDA_TRY(cudaMemcpyAsync(n_eval, e->st.n_eval, e->C * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
+    if (status) CUDA_TRY(cudaMemcpyAsync(status, e->st.status, e->C * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PBU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pbu_engine_get_proposal(pbu_engine *e, double *R_host, double *V_host, double *xav_host) {
+    if (!e) return fail(PBU_ERR_INVALID, "null engine");
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int d = e->d;
+    const int64_t C = e->C;
+    int rc;
+    std::vector<double> tri;
+    auto unpack = [&](double *dst, bool symmetric, double scale, double diag_add) {
+        for (int64_t c = 0; c < C; ++c)
+            for (int i = 0; i < d; ++i)
+                for (int j = 0; j < d; ++j) {
+                    double v = 0.0;
+                    if (j >= i)
+                        v = tri[(size_t)tri_idx(d, i, j) * C + c] * scale + (i == j ? diag_add : 0.0);
+                    else if (symmetric)
+                        v = tri[(size_t)tri_idx(d, j, i) * C + c] * scale;
+                    dst[((size_t)c * d + i) * d + j] = v;
+                }
+    };
+    if (R_host) {
+        if ((rc = d2h(e, e->st.R, (size_t)e->nt * C, tri))) return rc;
+        unpack(R_host, false, 1.0, 0.0);
+    }
+    if (V_host) {
+        if ((rc = d2h(e, e->st.V, (size_t)e->nt * C, tri))) return rc;
+        if (e->cfg.am_welford && e->iteration > 0) {
+            const double S_d = 2.38 * 2.38 / (double)d;
+            unpack(V_host, true, S_d / (double)e->iteration, S_d * e->cfg.eps_v);
+        } else {
+            unpack(V_host, true, 1.0, 0.0);
+        }
+    }
+    if (xav_host) {
+        std::vector<double> soa;
+        if ((rc = d2h(e, e->st.xav, (size_t)d * C, soa))) return rc;
+        transpose_from_soa(soa, C, d, xav_host);
+    }
+    return PBU_OK;
+}
+
+static int upload_soa(pbu_engine *e, const double *X_host, int64_t S, double **X_dev) {
+    std::vector<double> soa;
+    transpose_to_soa(X_host, S, e->d, soa);
+    CUDA_TRY(cudaMalloc((void **)X_dev, soa.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(*X_dev, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return PBU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pbu_eval_logpost(pbu_engine *e, const double *X_host, int64_t S, double *lp_host) {
+    if (!e || !X_host || !lp_host || S < 1) return fail(PBU_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    double *X_dev = nullptr, *lp_dev = nullptr;
+    int rc = upload_soa(e, X_host, S, &X_dev);
+    if (rc) return rc;
+    CUDA_TRY(cudaMalloc((void **)&lp_dev, S * sizeof(double)));
+    rc = launch_eval_lp(e, X_dev, S, lp_dev);
+    if (!rc) {
+        cudaError_t ce = cudaMemcpyAsync(lp_host, lp_dev, S * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        if (ce != cudaSuccess) rc = fail(PBU_ERR_CUDA, "eval_logpost: %s", cudaGetErrorString(ce));
+    }
+    cudaFree(X_dev);
+    cudaFree(lp_dev);
+    return rc;
+}
+
+extern "C" __attribute__((visibility("default"))) int pbu_eval_model(pbu_engine *e, const double *X_host, int64_t S, double *f_host) {
+    if (!e || !X_host || !f_host || S < 1) return fail(PBU_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int N = e->prob.n_points;
+    double *X_dev = nullptr, *f_dev = nullptr;
+    int rc = upload_soa(e, X_host, S, &X_dev);
+    if (rc) return rc;
+    CUDA_TRY(cudaMalloc((void **)&f_dev, (size_t)S * N * sizeof(double)));
+    CUDA_TRY(cudaFuncSetAttribute(e->ev->eval_model, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    const int block = 128;
+    const unsigned grid = (unsigned)((S + block - 1) / block);
+    void *args[] = {(void *)&e->prob, (void *)&X_dev, (void *)&S, (void *)&f_dev};
+    cudaError_t ce = cudaLaunchKernel(e->ev->eval_model, dim3(grid), dim3(block), args, e->smem_bytes, e->stream);
+    std::vector<double> pm;
+    if (ce == cudaSuccess) {
+        pm.resize((size_t)S * N);
+        ce = cudaMemcpyAsync(pm.data(), f_dev, pm.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    cudaFree(X_dev);
+    cudaFree(f_dev);
+    if (ce != cudaSuccess) return fail(PBU_ERR_CUDA, "eval_model: %s", cudaGetErrorString(ce));
+    for (int64_t s = 0; s < S; ++s)
+        for (int k = 0; k < N; ++k) f_host[(size_t)s * N + k] = pm[(size_t)k * S + s];
+    return PBU_OK;
+}

@@ -1,0 +1,5 @@
+#include "pbu_inst.cuh"
+using namespace pbu;
+#define MH_LIST PBU_MH_SEQ(ArrheniusModel, 4, 1), PBU_MH_SEQ(ArrheniusModel, 4, 2), PBU_MH_SEQ(ArrheniusModel, 4, 3), PBU_MH_SEQ(ArrheniusModel, 4, 4)
+#define EV_LIST PBU_EVAL(ArrheniusModel, 4, 1), PBU_EVAL(ArrheniusModel, 4, 2), PBU_EVAL(ArrheniusModel, 4, 3), PBU_EVAL(ArrheniusModel, 4, 4)
+PBU_DEFINE_SLICE(arrhenius, MH_LIST, EV_LIST)

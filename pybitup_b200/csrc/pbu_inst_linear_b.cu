@@ -1,0 +1,5 @@
+#include "pbu_inst.cuh"
+using namespace pbu;
+#define MH_LIST PBU_MH_ALL(LinearModel<4>, 4, 4), PBU_MH_ALL(LinearModel<5>, 5, 5), PBU_MH_ALL(LinearModel<6>, 6, 6)
+#define EV_LIST PBU_EVAL(LinearModel<4>, 4, 4), PBU_EVAL(LinearModel<5>, 5, 5), PBU_EVAL(LinearModel<6>, 6, 6)
+PBU_DEFINE_SLICE(linear_b, MH_LIST, EV_LIST)

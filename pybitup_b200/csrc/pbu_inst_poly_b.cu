@@ -1,0 +1,5 @@
+#include "pbu_inst.cuh"
+using namespace pbu;
+#define MH_LIST PBU_MH_ALL(PolyModel<5>, 5, 5), PBU_MH_ALL(PolyModel<6>, 6, 6)
+#define EV_LIST PBU_EVAL(PolyModel<5>, 5, 5), PBU_EVAL(PolyModel<6>, 6, 6)
+PBU_DEFINE_SLICE(poly_b, MH_LIST, EV_LIST)

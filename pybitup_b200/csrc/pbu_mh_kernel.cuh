@@ -1,0 +1,489 @@
+// K1: fused Metropolis-Hastings step kernel (RWMH / AM / DR / DRAM), many iterations per launch.
+//
+// Replaces, per chain and per iteration, the reference's Python loop
+//   run_algorithm             metropolis_hastings_algorithms.py:158-182, :407-430
+//   compute_new_val           :184-193   (d normals, new = cur + R @ z with R upper)
+//   compute_acceptance_ratio  :195-207   (-> BayesianPosterior.compute_log_value,
+//                                         bayesian_inference.py:44-64; Mixture prior,
+//                                         distributions.py:456-479; Gaussian sum of squares,
+//                                         bayesian_inference.py:495-542; Model.run_model :338-371)
+//   accept_reject             :210-224, :520-567 (delayed rejection)
+//   adapt_covariance          :432-487, :591-595
+// with no host round trip per iteration.
+//
+// Mapping: G lanes of a warp own one chain (G = 1, 2, 4, 8).  All G lanes carry the chain state
+// redundantly in registers and execute the scalar part of the step identically; the sum over the
+// N data points is strided over the G lanes and combined with an xor-butterfly of warp shuffles, so
+// every lane ends with the bit-identical sum.  The point records (design columns, weight, data) are
+// staged once per launch into shared memory with a bulk TMA copy and read by all chains of the
+// block: with G = 1 every shared-memory read is a warp broadcast.
+#pragma once
+#include "pbu_common.cuh"
+#include "pbu_models.cuh"
+
+namespace pbu {
+
+__host__ __device__ constexpr int even_up(int n) { return (n + 1) & ~1; }
+
+// ------------------------------------------------------------------------------------------------
+// Stage all point records into shared memory (resident mode).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_records(double *smem_rec, uint64_t *bar, const ProblemDev &prob) {
+    const uint32_t total = (uint32_t)prob.n_points * (uint32_t)prob.ncol * 8u;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, total);
+        const uint32_t CH = 32768u;
+        for (uint32_t off = 0; off < total; off += CH) {
+            uint32_t n = (total - off < CH) ? (total - off) : CH;
+            tma_load_1d(reinterpret_cast<char *>(smem_rec) + off, reinterpret_cast<const char *>(prob.records) + off, n, bar);
+        }
+    }
+    mbar_wait(bar, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gaussian sum of squares J(theta) = sum_runs sum_k ((y_k - f_k) * w_k)^2 over the staged records
+// (Likelihood.arg_gauss_likelihood, bayesian_inference.py:495-542).
+// ------------------------------------------------------------------------------------------------
+template <class M, int G>
+__device__ __forceinline__ double sum_of_squares(const typename M::Ctx &ctx, const ProblemDev &prob, const double *smem_rec,
+                                                 int sub, unsigned group_mask) {
+    constexpr int NC0 = even_up(M::ND + 2);
+    const int N = prob.n_points;
+    const int ncol = prob.ncol;
+    const int n_runs = prob.n_runs;
+    typename M::Seq seq;
+    M::seq_init(ctx, seq, prob);
+    double J0 = 0.0, J1 = 0.0;
+    auto point = [&](int k, double &J) {
+        const double2 *r2 = reinterpret_cast<const double2 *>(smem_rec + (size_t)k * ncol);
+        double rec[NC0];
+#pragma unroll
+        for (int j = 0; j < NC0 / 2; ++j) {
+            double2 v = r2[j];
+            rec[2 * j] = v.x;
+            rec[2 * j + 1] = v.y;
+        }
+        const double f = M::eval(ctx, seq, rec);
+        const double w = rec[M::ND];
+        const double t = (rec[M::ND + 1] - f) * w;
+        J = fma(t, t, J);
+        if (n_runs > 1) {
+            const double *extra = smem_rec + (size_t)k * ncol + NC0;
+            for (int r = 1; r < n_runs; ++r) {
+                const double tr = (extra[r - 1] - f) * w;
+                J = fma(tr, tr, J);
+            }
+        }
+    };
+    if (M::SEQUENTIAL) {
+        for (int k = 0; k < N; ++k) point(k, J0);
+    } else {
+        int k = sub;
+#pragma unroll 2
+        for (; k + G < N; k += 2 * G) {
+            point(k, J0);
+            point(k + G, J1);
+        }
+        if (k < N) point(k, J0);
+    }
+    double J = J0 + J1;
+    if (G > 1) {
+#pragma unroll
+        for (int s = 1; s < G; s <<= 1) J += __shfl_xor_sync(group_mask, J, s);
+    }
+    return J;
+}
+
+// BayesianPosterior.compute_log_value (bayesian_inference.py:44-64) with the identity
+// parametrisation: -inf outside the prior box WITHOUT evaluating the model (:53-55), otherwise
+// log_prior - log(1) + (-(1/2) J).
+template <class M, int D, int G>
+__device__ __forceinline__ double log_posterior(const double (&x)[D], const ProblemDev &prob, const double *smem_rec, int sub,
+                                                unsigned group_mask) {
+    bool inside = true;
+#pragma unroll
+    for (int i = 0; i < D; ++i) inside = inside && !(x[i] < prob.lb[i] || x[i] > prob.ub[i]);
+    if (!inside) return -INFINITY;
+    double theta[M::NPARAM];
+#pragma unroll
+    for (int p = 0; p < M::NPARAM; ++p) {
+        double v = prob.theta_nom[p];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+            if (prob.unc_idx[i] == p) v = x[i];        // Model.run_model :361-369
+        theta[p] = v;
+    }
+    typename M::Ctx ctx;
+    M::begin(ctx, theta, prob);
+    const double J = sum_of_squares<M, G>(ctx, prob, smem_rec, sub, group_mask);
+    return (prob.log_prior_const - 0.0) + (-0.5 * J);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Random draws for one proposal stage: D standard normals and one uniform.
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ void draw_philox(uint64_t seed, uint64_t chain, uint64_t it, uint32_t stage, double (&z)[D], double &u) {
+    constexpr int NPAIR = (D + 1) / 2;
+    constexpr int NW = 2 * NPAIR + 2;
+    constexpr int NB = (NW + 3) / 4;
+    uint32_t w[NB * 4];
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        uint4 ctr = make_uint4((uint32_t)chain, (uint32_t)it, (uint32_t)(it >> 32) ^ ((uint32_t)(chain >> 32) << 8) ^ (stage << 30),
+                               (uint32_t)b);
+        uint4 r = Philox::round10(ctr, key);
+        w[4 * b] = r.x;
+        w[4 * b + 1] = r.y;
+        w[4 * b + 2] = r.z;
+        w[4 * b + 3] = r.w;
+    }
+#pragma unroll
+    for (int p = 0; p < NPAIR; ++p) {
+        double a, b;
+        box_muller(w[2 * p], w[2 * p + 1], a, b);
+        z[2 * p] = a;
+        if (2 * p + 1 < D) z[2 * p + 1] = b;
+    }
+    u = uniform53(w[2 * NPAIR], w[2 * NPAIR + 1]);
+}
+
+template <int D>
+__device__ __forceinline__ bool draw_injected(const StreamsDev &s, int64_t c, int64_t &cn, int64_t &cu, double (&z)[D], double &u) {
+    if (cn + D > s.n_normals || cu + 1 > s.n_uniforms) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) z[i] = 0.0;
+        u = 1.0;
+        return false;
+    }
+    const double *zn = s.normals + c * s.n_normals + cn;
+#pragma unroll
+    for (int i = 0; i < D; ++i) z[i] = zn[i];
+    u = s.uniforms[c * s.n_uniforms + cu];
+    cn += D;
+    cu += 1;
+    return true;
+}
+
+// new = cur + scale * R @ z with R UPPER triangular (mha.py:193, :543)
+template <int D>
+__device__ __forceinline__ void propose(const double (&x)[D], const double (&R)[tri_size(D)], const double (&z)[D], double scale,
+                                        double (&y)[D]) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = i; j < D; ++j) s = fma(R[tri_idx(D, i, j)], z[j], s);
+        y[i] = x[i] + scale * s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The kernel.
+// ------------------------------------------------------------------------------------------------
+template <class M, int D, int G, bool ADAPT>
+__global__ void mh_step_kernel(const __grid_constant__ MhParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *smem_rec = reinterpret_cast<double *>(smem_raw + 128);
+    constexpr int NT = tri_size(D);
+
+    stage_records(smem_rec, bar, p.prob);
+
+    const int64_t C = p.st.n_chains;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t c = gtid / G;
+    const int sub = (int)(gtid % G);
+    const bool live = c < C;
+    if (!live) c = C - 1;                       // padding lanes shadow the last chain, never write
+    const bool writer = live && (sub == 0);
+    const int lane = threadIdx.x & 31;
+    const unsigned group_mask = (G == 1) ? (1u << lane) : (((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(G - 1)));
+
+    // ---- load state
+    double x[D], R[NT], lp;
+    double xav[ADAPT ? D : 1], V[ADAPT ? NT : 1];
+    double wmean[D], wM2[NT];
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[i] = p.st.x[i * C + c];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) R[i] = p.st.R[i * C + c];
+    lp = p.st.lp[c];
+    if (ADAPT) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) xav[i] = p.st.xav[i * C + c];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) V[i] = p.st.V[i * C + c];
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) wmean[i] = p.st.wmean[i * C + c];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) wM2[i] = p.st.wM2[i * C + c];
+    int64_t wcount = p.st.wcount[c];
+    double mean_r = p.st.mean_r[c];
+    int64_t n_rej = p.st.n_rej[c];
+    int64_t n_eval = p.st.n_eval[c];
+    int32_t status = p.st.status[c];
+    const bool injected = p.streams.normals != nullptr;
+    int64_t cn = 0, cu = 0;
+    if (injected) {
+        cn = p.streams.cur_n[c];
+        cu = p.streams.cur_u[c];
+    }
+    const uint64_t gchain = p.chain_offset + (uint64_t)c;
+
+    for (int64_t s = 0; s < p.n_steps; ++s) {
+        const int64_t it = p.it0 + s + 1;
+        // ---- stage 1 proposal (mha.py:184-193)
+        double z[D], u;
+        if (injected) {
+            if (!draw_injected<D>(p.streams, c, cn, cu, z, u)) status |= ST_STREAM_EXHAUSTED;
+        } else {
+            draw_philox<D>(p.seed, gchain, (uint64_t)it, 0u, z, u);
+        }
+        double y1[D];
+        propose<D>(x, R, z, 1.0, y1);
+        const double lp1 = log_posterior<M, D, G>(y1, p.prob, smem_rec, sub, group_mask);
+        n_eval += 1;
+        // ---- acceptance ratio (mha.py:195-207)
+        double r = (lp1 == -INFINITY) ? 0.0 : exp(lp1 - lp);
+        if (r != r) {
+            status |= ST_NAN_RATIO;
+            if (p.nan_rejects) r = 0.0;
+        }
+        const double alpha = py_min1(r);
+        int acc = 0;
+        double lp2 = nan("");
+        if (u < alpha) {                                   // mha.py:214-222
+#pragma unroll
+            for (int i = 0; i < D; ++i) x[i] = y1[i];
+            lp = lp1;
+            acc = 1;
+        } else if (p.delayed) {                            // mha.py:535-567
+            double z2[D], u2;
+            if (injected) {
+                if (!draw_injected<D>(p.streams, c, cn, cu, z2, u2)) status |= ST_STREAM_EXHAUSTED;
+            } else {
+                draw_philox<D>(p.seed, gchain, (uint64_t)it, 1u, z2, u2);
+            }
+            double y2[D];
+            propose<D>(x, R, z2, p.gamma_dr, y2);
+            lp2 = log_posterior<M, D, G>(y2, p.prob, smem_rec, sub, group_mask);
+            n_eval += 1;
+            const double r12 = exp(lp1 - lp2);
+            const double a12 = py_min1(r12);
+            // inv_V = inv_R * inv_R^T ELEMENTWISE = diag(1/R_ii^2)  (mha.py:517-518, :594-595)
+            double M2 = 0.0, M4 = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                const double ir = 1.0 / R[tri_idx(D, i, i)];
+                const double iv = ir * ir;
+                const double d1 = y1[i] - y2[i];
+                const double d2 = y1[i] - x[i];
+                M2 += (d1 * iv) * d1;
+                M4 += (d2 * iv) * d2;
+            }
+            double r2 = exp(lp2 - lp) * (exp(-0.5 * M2) / exp(-0.5 * M4)) * (1.0 - a12) / (1.0 - alpha);   // mha.py:555-556
+            if (r2 != r2) {
+                status |= ST_NAN_RATIO;
+                if (p.nan_rejects) r2 = 0.0;
+            }
+            const double a2 = py_min1(r2);
+            if (u2 < a2) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) x[i] = y2[i];
+                lp = lp2;
+                acc = 2;
+            } else {
+                n_rej += 1;
+            }
+        } else {
+            n_rej += 1;
+        }
+
+        // ---- covariance adaptation (mha.py:432-487)
+        if (ADAPT) {
+            const double fi = (double)it;
+            if (!p.am_welford) {
+                // literal Haario/Smith recursion, evaluated in the reference's operation order
+                // without FMA contraction; at it == 1 X_av_i aliases the state.
+                double xa[D], xb[D];
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    xa[i] = (it == 1) ? x[i] : xav[i];
+                    xb[i] = __dadd_rn(x[i], __dmul_rn(fi / (fi + 1.0), __dadd_rn(xa[i], -x[i])));       // :455
+                }
+                const double c1 = (fi - 1.0) / fi, c2 = p.S_d / fi;
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = i; j < D; ++j) {
+                        double t = __dadd_rn(__dmul_rn(fi, __dmul_rn(xa[i], xa[j])), -__dmul_rn(fi + 1.0, __dmul_rn(xb[i], xb[j])));
+                        t = __dadd_rn(t, __dmul_rn(x[i], x[j]));
+                        t = __dadd_rn(t, (i == j) ? p.eps_v : 0.0);
+                        V[tri_idx(D, i, j)] = __dadd_rn(__dmul_rn(c1, V[tri_idx(D, i, j)]), __dmul_rn(c2, t));  // :463
+                    }
+#pragma unroll
+                for (int i = 0; i < D; ++i) xav[i] = xb[i];
+            } else {
+                // Welford over x_0..x_it: xav = running mean, V = sum of outer products of deviations
+                const double inv_n = 1.0 / (fi + 1.0);
+                double dl[D];
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    dl[i] = x[i] - xav[i];
+                    xav[i] = fma(dl[i], inv_n, xav[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = i; j < D; ++j) V[tri_idx(D, i, j)] = fma(dl[i], x[j] - xav[j], V[tri_idx(D, i, j)]);
+            }
+            if (it % p.updating_it == 0) {                  // :470, :486-487, :591-595
+                double Vc[NT], Rn[NT];
+                if (!p.am_welford) {
+#pragma unroll
+                    for (int i = 0; i < NT; ++i) Vc[i] = V[i];
+                } else {
+                    const double sc = p.S_d / fi;           // S_d * M2/(n-1), n = it+1
+#pragma unroll
+                    for (int i = 0; i < D; ++i)
+#pragma unroll
+                        for (int j = i; j < D; ++j)
+                            Vc[tri_idx(D, i, j)] = sc * V[tri_idx(D, i, j)] + ((i == j) ? p.S_d * p.eps_v : 0.0);
+                }
+                if (chol_upper_packed<D>(Vc, Rn)) {
+#pragma unroll
+                    for (int i = 0; i < NT; ++i) R[i] = Rn[i];
+                } else {
+                    status |= ST_NOT_PD;                    // scipy raises LinAlgError here (:487)
+                }
+            }
+            mean_r += r;                                    // :419 (unclipped)
+        } else {
+            mean_r += alpha;                                // :170
+        }
+
+        // ---- running moments of the visited states (input of the moment reduction, K4)
+        {
+            wcount += 1;
+            const double inv_n = 1.0 / (double)wcount;
+            double dl[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                dl[i] = x[i] - wmean[i];
+                wmean[i] = fma(dl[i], inv_n, wmean[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = i; j < D; ++j) wM2[tri_idx(D, i, j)] = fma(dl[i], x[j] - wmean[j], wM2[tri_idx(D, i, j)]);
+        }
+
+        // ---- outputs
+        if (writer) {
+            if (p.out.trace_lp1) p.out.trace_lp1[s * C + c] = lp1;
+            if (p.out.trace_lp2) p.out.trace_lp2[s * C + c] = lp2;
+            if (p.out.trace_acc) p.out.trace_acc[s * C + c] = (uint8_t)acc;
+            if (it % p.thin == 0) {
+                const int64_t row = it / p.thin - p.it0 / p.thin - 1;
+                if (p.out.samples) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) p.out.samples[(row * D + i) * C + c] = x[i];
+                }
+                if (p.out.lp_kept) p.out.lp_kept[row * C + c] = lp;
+            }
+        }
+    }
+
+    // ---- store state
+    if (writer) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) p.st.x[i * C + c] = x[i];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) p.st.R[i * C + c] = R[i];
+        p.st.lp[c] = lp;
+        if (ADAPT) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) p.st.xav[i * C + c] = xav[i];
+#pragma unroll
+            for (int i = 0; i < NT; ++i) p.st.V[i * C + c] = V[i];
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) p.st.wmean[i * C + c] = wmean[i];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) p.st.wM2[i * C + c] = wM2[i];
+        p.st.wcount[c] = wcount;
+        p.st.mean_r[c] = mean_r;
+        p.st.n_rej[c] = n_rej;
+        p.st.n_eval[c] = n_eval;
+        p.st.status[c] = status;
+        if (injected) {
+            p.streams.cur_n[c] = cn;
+            p.streams.cur_u[c] = cu;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Initial state: log-posterior of x0 (mha.py:102) and R = upper Cholesky of V0 (:143).
+// Also used for plain evaluation of S parameter vectors (one thread per vector, G = 1).
+// ------------------------------------------------------------------------------------------------
+template <class M, int D>
+__global__ void eval_logpost_kernel(const __grid_constant__ ProblemDev prob, const double *X /*[d][S]*/, int64_t S, double *lp_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *smem_rec = reinterpret_cast<double *>(smem_raw + 128);
+    stage_records(smem_rec, bar, prob);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S) return;
+    double x[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[i] = X[i * S + t];
+    lp_out[t] = log_posterior<M, D, 1>(x, prob, smem_rec, 0, 1u << (threadIdx.x & 31));
+}
+
+// Model.run_model for S parameter vectors: f_out[k][s] (point-major, coalesced over samples).
+template <class M, int D>
+__global__ void eval_model_kernel(const __grid_constant__ ProblemDev prob, const double *X /*[d][S]*/, int64_t S, double *f_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    double *smem_rec = reinterpret_cast<double *>(smem_raw + 128);
+    stage_records(smem_rec, bar, prob);
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S) return;
+    double theta[M::NPARAM];
+#pragma unroll
+    for (int q = 0; q < M::NPARAM; ++q) {
+        double v = prob.theta_nom[q];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+            if (prob.unc_idx[i] == q) v = X[i * S + t];
+        theta[q] = v;
+    }
+    typename M::Ctx ctx;
+    M::begin(ctx, theta, prob);
+    typename M::Seq seq;
+    M::seq_init(ctx, seq, prob);
+    constexpr int NC0 = even_up(M::ND + 2);
+    for (int k = 0; k < prob.n_points; ++k) {
+        const double2 *r2 = reinterpret_cast<const double2 *>(smem_rec + (size_t)k * prob.ncol);
+        double rec[NC0];
+#pragma unroll
+        for (int j = 0; j < NC0 / 2; ++j) {
+            double2 v = r2[j];
+            rec[2 * j] = v.x;
+            rec[2 * j + 1] = v.y;
+        }
+        f_out[(int64_t)k * S + t] = M::eval(ctx, seq, rec);
+    }
+}
+
+}  // namespace pbu

@@ -1,0 +1,154 @@
+// Registered device forward models (replace user bi.Model.fun_x, bayesian_inference.py:306-308,:371).
+//
+// A model is a struct with
+//   NPARAM      length of the full parameter vector theta
+//   ND          design columns at the head of each point record
+//   SEQUENTIAL  true if point k depends on point k-1 (ODE): no splitting of the sum over lanes
+//   Ctx         per-evaluation constants derived from theta        (begin)
+//   Seq         running state across points                         (seq_init)
+//   eval(ctx, seq, rec) -> f_k   with rec = the point record in registers
+// and, when HAS_GRAD, grad(ctx, rec, j) = d f_k / d theta_j.
+//
+// Record layout: [design (ND) | w = 1/(std_y*gamma) | y_run0 | pad to even | y_run1 ...].
+#pragma once
+#include "pbu_common.cuh"
+
+namespace pbu {
+
+// ------------------------------------------------------------------------------------------------
+// LINEAR: f_k = sum_j Phi[k][j] * theta[j], accumulated j = 0..P-1 (oracle/cpu_models.py::linear_design)
+template <int P>
+struct LinearModel {
+    static constexpr int NPARAM = P;
+    static constexpr int ND = P;
+    static constexpr bool SEQUENTIAL = false;
+    static constexpr bool HAS_GRAD = true;
+    static constexpr int ID = PBU_MODEL_LINEAR;
+    struct Ctx {
+        double th[P];
+    };
+    struct Seq {};
+    __device__ __forceinline__ static void begin(Ctx &c, const double (&theta)[P], const ProblemDev &) {
+#pragma unroll
+        for (int j = 0; j < P; ++j) c.th[j] = theta[j];
+    }
+    __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const ProblemDev &) {}
+    __device__ __forceinline__ static double eval(const Ctx &c, Seq &, const double *rec) {
+        double f = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) f = fma(rec[j], c.th[j], f);
+        return f;
+    }
+    __device__ __forceinline__ static double grad(const Ctx &, const double *rec, int j) { return rec[j]; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// POLY: Horner from the top coefficient (oracle/cpu_models.py::poly_horner)
+template <int P>
+struct PolyModel {
+    static constexpr int NPARAM = P;
+    static constexpr int ND = 1;
+    static constexpr bool SEQUENTIAL = false;
+    static constexpr bool HAS_GRAD = true;
+    static constexpr int ID = PBU_MODEL_POLY;
+    struct Ctx {
+        double th[P];
+    };
+    struct Seq {};
+    __device__ __forceinline__ static void begin(Ctx &c, const double (&theta)[P], const ProblemDev &) {
+#pragma unroll
+        for (int j = 0; j < P; ++j) c.th[j] = theta[j];
+    }
+    __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const ProblemDev &) {}
+    __device__ __forceinline__ static double eval(const Ctx &c, Seq &, const double *rec) {
+        const double x = rec[0];
+        double f = c.th[P - 1];
+#pragma unroll
+        for (int j = P - 2; j >= 0; --j) f = fma(f, x, c.th[j]);
+        return f;
+    }
+    __device__ __forceinline__ static double grad(const Ctx &, const double *rec, int j) {
+        double p = 1.0;
+        for (int i = 0; i < j; ++i) p *= rec[0];
+        return p;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// ARRHENIUS: d(alpha)/dT = (A/beta) exp(-E/(R T)) (1-alpha)^n, RK4 with step dT, output 1 - F*alpha
+// at the end of every step (oracle/cpu_models.py::arrhenius_rk4).  Record design columns:
+// [1/T_mid, 1/T_end] of the step; consts = {T0, dT, beta}.  The rate at the start of a step is the
+// rate at the end of the previous one, so each step costs two exp and four pow.
+struct ArrheniusModel {
+    static constexpr int NPARAM = 4;
+    static constexpr int ND = 2;
+    static constexpr bool SEQUENTIAL = true;
+    static constexpr bool HAS_GRAD = false;
+    static constexpr int ID = PBU_MODEL_ARRHENIUS;
+    static constexpr double R_GAS = 8.314462618;
+    struct Ctx {
+        double c0, ER, n, F, h, g_start;
+    };
+    struct Seq {
+        double alpha, g0;
+    };
+    __device__ __forceinline__ static void begin(Ctx &c, const double (&theta)[4], const ProblemDev &p) {
+        c.c0 = 2.302585092994046 * theta[0] - log(p.consts[2]);   // ln(10)*log10A - ln(beta)
+        c.ER = theta[1] / R_GAS;
+        c.n = theta[2];
+        c.F = theta[3];
+        c.h = p.consts[1];
+        c.g_start = exp(c.c0 - c.ER * (1.0 / p.consts[0]));
+    }
+    __device__ __forceinline__ static void seq_init(const Ctx &c, Seq &s, const ProblemDev &) {
+        s.alpha = 0.0;
+        s.g0 = c.g_start;
+    }
+    __device__ __forceinline__ static double pw(double u, double n) { return (u > 0.0) ? pow(u, n) : 0.0; }
+    __device__ __forceinline__ static double eval(const Ctx &c, Seq &s, const double *rec) {
+        const double gm = exp(c.c0 - c.ER * rec[0]);
+        const double g1 = exp(c.c0 - c.ER * rec[1]);
+        const double a = s.alpha;
+        const double k1 = c.h * s.g0 * pw(1.0 - a, c.n);
+        const double k2 = c.h * gm * pw(1.0 - (a + 0.5 * k1), c.n);
+        const double k3 = c.h * gm * pw(1.0 - (a + 0.5 * k2), c.n);
+        const double k4 = c.h * g1 * pw(1.0 - (a + k3), c.n);
+        s.alpha = a + (k1 + 2.0 * k2 + 2.0 * k3 + k4) / 6.0;
+        s.g0 = g1;
+        return 1.0 - c.F * s.alpha;
+    }
+    __device__ __forceinline__ static double grad(const Ctx &, const double *, int) { return 0.0; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// HEAT: steady fin temperature, the reference's own test model
+// (pybitup/test/test_pce/heat_conduction.py:27-41); theta = (a,b,k,T_amb,phi,h), consts = {L}.
+struct HeatModel {
+    static constexpr int NPARAM = 6;
+    static constexpr int ND = 1;
+    static constexpr bool SEQUENTIAL = false;
+    static constexpr bool HAS_GRAD = false;
+    static constexpr int ID = PBU_MODEL_HEAT;
+    struct Ctx {
+        double gamma, c1, c2, T_amb;
+    };
+    struct Seq {};
+    __device__ __forceinline__ static void begin(Ctx &c, const double (&th)[6], const ProblemDev &p) {
+        const double a = th[0], b = th[1], k = th[2], phi = th[4], h = th[5], L = p.consts[0];
+        const double gamma = sqrt(2.0 * (a + b) * h / (a * b * k));
+        const double ep = exp(gamma * L), em = exp(-gamma * L);
+        const double c1 = -phi / (k * gamma) * (ep * (h + k * gamma) / (em * (h - k * gamma) + ep * (h + k * gamma)));
+        c.gamma = gamma;
+        c.c1 = c1;
+        c.c2 = phi / (k * gamma) + c1;
+        c.T_amb = th[3];
+    }
+    __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const ProblemDev &) {}
+    __device__ __forceinline__ static double eval(const Ctx &c, Seq &, const double *rec) {
+        const double x = rec[0];
+        return c.c1 * exp(-c.gamma * x) + c.c2 * exp(c.gamma * x) + c.T_amb;
+    }
+    __device__ __forceinline__ static double grad(const Ctx &, const double *, int) { return 0.0; }
+};
+
+}  // namespace pbu

@@ -1,0 +1,42 @@
+// Concatenates the per-file kernel table slices.
+#include <vector>
+#include "pbu_registry.h"
+
+template <class E, class F>
+static void append(std::vector<E> &v, F slice) {
+    int n = 0;
+    const E *t = slice(&n);
+    v.insert(v.end(), t, t + n);
+}
+
+const pbu::MhKernelEntry *pbu_mh_kernels(int *n) {
+    static const std::vector<pbu::MhKernelEntry> all = [] {
+        std::vector<pbu::MhKernelEntry> v;
+        append(v, pbu_mh_slice_linear_a);
+        append(v, pbu_mh_slice_linear_b);
+        append(v, pbu_mh_slice_linear_c);
+        append(v, pbu_mh_slice_poly_a);
+        append(v, pbu_mh_slice_poly_b);
+        append(v, pbu_mh_slice_arrhenius);
+        append(v, pbu_mh_slice_heat);
+        return v;
+    }();
+    *n = (int)all.size();
+    return all.data();
+}
+
+const pbu::EvalKernelEntry *pbu_eval_kernels(int *n) {
+    static const std::vector<pbu::EvalKernelEntry> all = [] {
+        std::vector<pbu::EvalKernelEntry> v;
+        append(v, pbu_eval_slice_linear_a);
+        append(v, pbu_eval_slice_linear_b);
+        append(v, pbu_eval_slice_linear_c);
+        append(v, pbu_eval_slice_poly_a);
+        append(v, pbu_eval_slice_poly_b);
+        append(v, pbu_eval_slice_arrhenius);
+        append(v, pbu_eval_slice_heat);
+        return v;
+    }();
+    *n = (int)all.size();
+    return all.data();
+}

@@ -1,0 +1,32 @@
+// Table of compiled kernel variants; each pbu_inst_*.cu contributes a slice.
+#pragma once
+#include "pbu_common.cuh"
+
+namespace pbu {
+
+struct MhKernelEntry {
+    int model, n_param, n_unc, lanes, adapt;
+    const void *fn;   // __global__ void (*)(const MhParams)
+};
+struct EvalKernelEntry {
+    int model, n_param, n_unc, sequential;
+    const void *eval_lp;      // __global__ void (*)(const ProblemDev, const double*, int64_t, double*)
+    const void *eval_model;   // same signature
+};
+
+}  // namespace pbu
+
+const pbu::MhKernelEntry *pbu_mh_kernels(int *n);
+const pbu::EvalKernelEntry *pbu_eval_kernels(int *n);
+
+// slices
+#define PBU_DECLARE_SLICE(name)                                     \
+    const pbu::MhKernelEntry *pbu_mh_slice_##name(int *n);          \
+    const pbu::EvalKernelEntry *pbu_eval_slice_##name(int *n);
+PBU_DECLARE_SLICE(linear_a)
+PBU_DECLARE_SLICE(linear_b)
+PBU_DECLARE_SLICE(linear_c)
+PBU_DECLARE_SLICE(poly_a)
+PBU_DECLARE_SLICE(poly_b)
+PBU_DECLARE_SLICE(arrhenius)
+PBU_DECLARE_SLICE(heat)

@@ -1,0 +1,280 @@
+"""Host-side handle on the CUDA chain engine (thin wrapper over the C ABI).
+
+``ProblemSpec`` is the flat problem descriptor the reference's objects are lowered to
+(SURVEY.md §8b "what the engine must extract"); ``ChainEngine`` owns one ``pbu_engine``.
+PyTorch is used only to allocate the device output buffers and to hand over the CUDA stream.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _capi as capi
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+@dataclass
+class ProblemSpec:
+    """One Bayesian inverse problem with a registered device forward model."""
+    model: str                       # 'linear' | 'poly' | 'arrhenius' | 'heat'
+    theta_nom: np.ndarray            # f64[P]   Model.param_nom
+    unc_idx: np.ndarray              # int[d]   position of each uncertain parameter in theta
+    y: np.ndarray                    # f64[n_runs, N]
+    std_y: np.ndarray                # f64[N]
+    lb: np.ndarray                   # f64[d]
+    ub: np.ndarray                   # f64[d]
+    gamma: float = 1.0
+    design: dict = field(default_factory=dict)
+
+    @classmethod
+    def from_dict(cls, p):
+        return cls(model=str(p["model"]), theta_nom=_f64(p["theta_nom"]),
+                   unc_idx=np.ascontiguousarray(np.asarray(p["unc_idx"], dtype=np.int32)),
+                   y=_f64(np.atleast_2d(p["y"])), std_y=_f64(p["std_y"]), lb=_f64(p["lb"]), ub=_f64(p["ub"]),
+                   gamma=float(p.get("gamma", 1.0)), design=dict(p.get("design", {})))
+
+    @property
+    def d(self):
+        return int(len(self.unc_idx))
+
+    @property
+    def n_points(self):
+        return int(self.y.shape[1])
+
+    def _c_struct(self):
+        """Build the pbu_problem struct; returns (struct, keepalive list)."""
+        if self.model not in capi.MODEL_IDS:
+            raise capi.UnsupportedProblem(capi.PBU_ERR_UNSUPPORTED,
+                                          "model %r is not a registered device model %s"
+                                          % (self.model, sorted(capi.MODEL_IDS)))
+        keep = []
+        theta = _f64(self.theta_nom)
+        unc = np.ascontiguousarray(np.asarray(self.unc_idx, dtype=np.int32))
+        y = _f64(np.atleast_2d(self.y))
+        std = _f64(self.std_y)
+        lb, ub = _f64(self.lb), _f64(self.ub)
+        N = y.shape[1]
+        consts = [0.0] * 8
+        design = None
+        ncols = 0
+        if self.model == "linear":
+            design = _f64(self.design["Phi"])
+            if design.shape != (N, len(theta)):
+                raise ValueError("linear model: Phi must be [N, P] = [%d, %d], got %s" % (N, len(theta), design.shape))
+            ncols = design.shape[1]
+        elif self.model in ("poly", "heat"):
+            design = _f64(self.design["x"]).reshape(N, 1)
+            ncols = 1
+            if self.model == "heat":
+                consts[0] = float(self.design.get("L", 70.0))
+        elif self.model == "arrhenius":
+            dg = self.design
+            if int(dg["n_steps"]) != N:
+                raise ValueError("arrhenius model: n_steps (%d) must equal the number of data points (%d)"
+                                 % (int(dg["n_steps"]), N))
+            consts[0], consts[1], consts[2] = float(dg["T0"]), float(dg["dT"]), float(dg["beta"])
+        if std.shape != (N,) or lb.shape != unc.shape or ub.shape != unc.shape:
+            raise ValueError("inconsistent problem array shapes")
+        keep += [theta, unc, y, std, lb, ub, design]
+        s = capi.pbu_problem()
+        s.model = capi.MODEL_IDS[self.model]
+        s.n_param, s.n_unc, s.n_points, s.n_runs, s.n_design_cols = len(theta), len(unc), N, y.shape[0], ncols
+        s.theta_nom = capi.dptr(theta)
+        s.unc_idx = unc.ctypes.data_as(C.POINTER(C.c_int32))
+        s.design = capi.dptr(design) if design is not None else None
+        s.y, s.std_y, s.lb, s.ub = capi.dptr(y), capi.dptr(std), capi.dptr(lb), capi.dptr(ub)
+        s.gamma = float(self.gamma)
+        s.consts = (C.c_double * 8)(*consts)
+        return s, keep
+
+
+@dataclass
+class SamplerConfig:
+    """Algorithm block (inference_problem.py:37-107) plus engine-only knobs."""
+    algo: str = "RWMH"               # RWMH | AMH | DR | DRAM | ISDE
+    updating_it: int = 1
+    eps_v: float = 0.0
+    gamma_dr: float = 1.0
+    isde_h: float = 0.0
+    isde_f0: float = 0.0
+    isde_gradient: str = "Analytical"
+    adapt_start: int = 0
+    adapt_update: int = 1
+    adapt_end: int = 0
+    am_welford: bool = False         # False = the reference's literal recursion (mha.py:455,:463)
+    nan_rejects: bool = False        # False = reference semantics, min(1, nan) == 1 accepts
+    lanes_per_chain: int = 0
+    block_threads: int = 0
+    seed: int = 0
+    chain_offset: int = 0
+
+    def _c_struct(self):
+        s = capi.pbu_sampler_cfg()
+        if self.algo not in capi.ALGO_IDS:
+            raise ValueError('Algorithm "{}" unknown.'.format(self.algo))     # inference_problem.py:32-33
+        s.algo = capi.ALGO_IDS[self.algo]
+        s.updating_it, s.eps_v, s.gamma_dr = int(self.updating_it), float(self.eps_v), float(self.gamma_dr)
+        s.isde_h, s.isde_f0 = float(self.isde_h), float(self.isde_f0)
+        s.isde_gradient = 0 if self.isde_gradient == "Analytical" else 1
+        s.adapt_start, s.adapt_update, s.adapt_end = int(self.adapt_start), int(self.adapt_update), int(self.adapt_end)
+        s.am_welford, s.nan_rejects = int(self.am_welford), int(self.nan_rejects)
+        s.lanes_per_chain, s.block_threads = int(self.lanes_per_chain), int(self.block_threads)
+        s.seed, s.chain_offset = int(self.seed) & (2 ** 64 - 1), int(self.chain_offset)
+        return s
+
+
+@dataclass
+class RunResult:
+    """Device-resident outputs of one ``ChainEngine.run`` (torch tensors, chain-minor layout)."""
+    n_steps: int
+    thin: int
+    samples: object = None      # [n_keep, d, C]
+    lp_kept: object = None      # [n_keep, C]
+    trace_lp1: object = None    # [n_steps, C]
+    trace_lp2: object = None    # [n_steps, C]
+    trace_acc: object = None    # [n_steps, C] uint8
+
+
+class ChainEngine:
+    """C chains of one problem on one GPU."""
+
+    def __init__(self, problem, config, n_chains, device=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("pybitup_b200 needs a CUDA device; there is no CPU fallback")
+        self._torch = torch
+        self.problem = problem if isinstance(problem, ProblemSpec) else ProblemSpec.from_dict(problem)
+        self.config = config
+        self.n_chains = int(n_chains)
+        self.device = int(device)
+        self.d = self.problem.d
+        ps, keep = self.problem._c_struct()
+        cs = config._c_struct()
+        h = C.c_void_p()
+        capi.check(capi.lib.pbu_engine_create(C.byref(ps), C.byref(cs), self.n_chains, self.device, C.byref(h)))
+        self._h = h
+        del keep
+        self.use_torch_stream()
+
+    # -- life cycle ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib.pbu_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def use_torch_stream(self):
+        s = self._torch.cuda.current_stream(self.device)
+        capi.check(capi.lib.pbu_engine_set_stream(self._h, C.c_void_p(s.cuda_stream)))
+
+    # -- state --------------------------------------------------------------------------------
+    def init_chains(self, x0, V0=None):
+        x0 = _f64(x0)
+        if x0.ndim == 1:
+            x0 = np.ascontiguousarray(np.broadcast_to(x0, (self.n_chains, self.d)))
+        if x0.shape != (self.n_chains, self.d):
+            raise ValueError("x0 must be [n_chains, d] = [%d, %d], got %s" % (self.n_chains, self.d, x0.shape))
+        V = None
+        if V0 is not None:
+            V = _f64(V0)
+            if V.shape != (self.d, self.d):
+                raise ValueError("V0 must be [d, d]")
+        capi.check(capi.lib.pbu_engine_init_chains(self._h, capi.dptr(x0), capi.dptr(V) if V is not None else None))
+
+    def set_streams(self, normals, uniforms):
+        """Parity mode: per-chain pre-generated draws, normals [C, n], uniforms [C, m]."""
+        if normals is None:
+            capi.check(capi.lib.pbu_engine_set_streams(self._h, None, 0, None, 0))
+            return
+        nz, un = _f64(normals), _f64(uniforms)
+        if nz.ndim == 1:
+            nz = nz[None, :]
+        if un.ndim == 1:
+            un = un[None, :]
+        if nz.shape[0] != self.n_chains or un.shape[0] != self.n_chains:
+            raise ValueError("streams need one row per chain")
+        nz, un = np.ascontiguousarray(nz), np.ascontiguousarray(un)
+        capi.check(capi.lib.pbu_engine_set_streams(self._h, capi.dptr(nz), nz.shape[1], capi.dptr(un), un.shape[1]))
+
+    @property
+    def iteration(self):
+        return int(capi.lib.pbu_engine_iteration(self._h))
+
+    # -- the hot loop -------------------------------------------------------------------------
+    def run(self, n_steps, thin=1, keep_samples=True, keep_lp=False, trace=False, out=None):
+        """Advance all chains by n_steps iterations in one kernel launch (asynchronous)."""
+        torch = self._torch
+        n_steps, thin = int(n_steps), int(thin)
+        dev = torch.device("cuda", self.device)
+        res = out if out is not None else RunResult(n_steps=n_steps, thin=thin)
+        n_keep = int(capi.lib.pbu_engine_n_keep(self._h, n_steps, thin))
+        Cn, d = self.n_chains, self.d
+        if out is None:
+            if keep_samples:
+                res.samples = torch.empty((n_keep, d, Cn), dtype=torch.float64, device=dev)
+            if keep_lp:
+                res.lp_kept = torch.empty((n_keep, Cn), dtype=torch.float64, device=dev)
+            if trace:
+                res.trace_lp1 = torch.empty((n_steps, Cn), dtype=torch.float64, device=dev)
+                res.trace_lp2 = torch.empty((n_steps, Cn), dtype=torch.float64, device=dev)
+                res.trace_acc = torch.empty((n_steps, Cn), dtype=torch.uint8, device=dev)
+        o = capi.pbu_run_outputs()
+        for name in ("samples", "lp_kept", "trace_lp1", "trace_lp2", "trace_acc"):
+            t = getattr(res, name)
+            setattr(o, name, C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else None)
+        capi.check(capi.lib.pbu_engine_run(self._h, n_steps, thin, C.byref(o)))
+        return res
+
+    def synchronize(self):
+        capi.check(capi.lib.pbu_engine_synchronize(self._h))
+
+    # -- read back ----------------------------------------------------------------------------
+    def state(self):
+        x = np.empty((self.n_chains, self.d))
+        lp = np.empty(self.n_chains)
+        capi.check(capi.lib.pbu_engine_get_state(self._h, capi.dptr(x), capi.dptr(lp)))
+        return x, lp
+
+    def counters(self):
+        n_rej = np.empty(self.n_chains, dtype=np.int64)
+        mean_r = np.empty(self.n_chains)
+        n_eval = np.empty(self.n_chains, dtype=np.int64)
+        status = np.empty(self.n_chains, dtype=np.int32)
+        capi.check(capi.lib.pbu_engine_get_counters(
+            self._h, n_rej.ctypes.data_as(C.POINTER(C.c_int64)), capi.dptr(mean_r),
+            n_eval.ctypes.data_as(C.POINTER(C.c_int64)), status.ctypes.data_as(C.POINTER(C.c_int32))))
+        return dict(n_rejected=n_rej, mean_r=mean_r, n_eval=n_eval, status=status)
+
+    def proposal(self):
+        R = np.empty((self.n_chains, self.d, self.d))
+        V = np.empty((self.n_chains, self.d, self.d))
+        xav = np.empty((self.n_chains, self.d))
+        capi.check(capi.lib.pbu_engine_get_proposal(self._h, capi.dptr(R), capi.dptr(V), capi.dptr(xav)))
+        return dict(R=R, V=V, X_av=xav)
+
+    # -- evaluation only ----------------------------------------------------------------------
+    def log_posterior(self, X):
+        X = _f64(np.atleast_2d(X))
+        out = np.empty(X.shape[0])
+        capi.check(capi.lib.pbu_eval_logpost(self._h, capi.dptr(X), X.shape[0], capi.dptr(out)))
+        return out
+
+    def model_eval(self, X):
+        X = _f64(np.atleast_2d(X))
+        out = np.empty((X.shape[0], self.problem.n_points))
+        capi.check(capi.lib.pbu_eval_model(self._h, capi.dptr(X), X.shape[0], capi.dptr(out)))
+        return out
