@@ -14,11 +14,12 @@ namespace pbu {
 // counters costs nothing.
 // ------------------------------------------------------------------------------------------------
 struct ProblemDev {
-    const double *records;   // dev [N][ncol] point records: [design cols | w = 1/(std_y*gamma) | y_run0 | pad | y_run1.. ]
+    const double *records;   // dev [N][ncol] point records: [design cols | w = sqrt(n_runs)/(std_y*gamma) | ybar | pad]
     int32_t n_points;
     int32_t n_runs;
-    int32_t ncol;            // doubles per record (even)
-    int32_t ncol0;           // doubles of the vector-loaded head of a record (even): design, w, y_run0
+    int32_t ncol;            // doubles per record (even) = even_up(ND + 2)
+    int32_t pad0;
+    double J_const;          // sum_k sum_runs ((y_run,k - ybar_k)/(std_y,k*gamma))^2, 0 for a single run
     int32_t n_param;
     int32_t n_unc;
     int32_t unc_idx[PBU_MAX_DIM];

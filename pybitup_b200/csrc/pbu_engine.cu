@@ -131,12 +131,13 @@ static const EvalKernelEntry *find_eval(int model, int P, int d) {
     return nullptr;
 }
 
-// Lower the problem to point records [N][ncol]: [design | w | y0 | pad | y1..]
-static int build_records(const pbu_problem *pr, int nd, std::vector<double> &rec, int &ncol, int &ncol0) {
+// Lower the problem to point records [N][ncol]: [design | w*sqrt(n_runs) | ybar | pad]; several runs are
+// folded exactly: sum_r (y_r - f)^2 = n_r (ybar - f)^2 + sum_r (y_r - ybar)^2 (second term -> J_const).
+static int build_records(const pbu_problem *pr, int nd, std::vector<double> &rec, int &ncol, double &J_const) {
     const int N = pr->n_points, nr = pr->n_runs;
-    ncol0 = even_up(nd + 2);
-    ncol = ncol0 + even_up(nr - 1);
+    ncol = even_up(nd + 2);
     rec.assign((size_t)N * ncol, 0.0);
+    J_const = 0.0;
     for (int k = 0; k < N; ++k) {
         double *r = &rec[(size_t)k * ncol];
         if (pr->model == PBU_MODEL_ARRHENIUS) {
@@ -146,9 +147,21 @@ static int build_records(const pbu_problem *pr, int nd, std::vector<double> &rec
         } else {
             for (int j = 0; j < nd; ++j) r[j] = pr->design[(size_t)k * pr->n_design_cols + j];
         }
-        r[nd] = 1.0 / (pr->std_y[k] * pr->gamma);
-        r[nd + 1] = pr->y[k];
-        for (int q = 1; q < nr; ++q) r[ncol0 + q - 1] = pr->y[(size_t)q * N + k];
+        const double w = 1.0 / (pr->std_y[k] * pr->gamma);
+        if (nr == 1) {
+            r[nd] = w;
+            r[nd + 1] = pr->y[k];
+        } else {
+            double ybar = 0.0;
+            for (int q = 0; q < nr; ++q) ybar += pr->y[(size_t)q * N + k];
+            ybar /= (double)nr;
+            for (int q = 0; q < nr; ++q) {
+                const double t = (pr->y[(size_t)q * N + k] - ybar) * w;
+                J_const += t * t;
+            }
+            r[nd] = w * std::sqrt((double)nr);
+            r[nd + 1] = ybar;
+        }
     }
     return PBU_OK;
 }
@@ -209,10 +222,10 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
         }
     }
     e->lanes = lanes;
-    e->block = cfg->block_threads > 0 ? cfg->block_threads : 128;
-    if (e->block % 32 != 0 || e->block > 1024) {
+    e->block = cfg->block_threads > 0 ? cfg->block_threads : MH_BLOCK;
+    if (e->block % 32 != 0 || e->block > MH_BLOCK) {
         delete e;
-        return fail(PBU_ERR_INVALID, "block_threads must be a multiple of 32 and <= 1024");
+        return fail(PBU_ERR_INVALID, "block_threads must be a multiple of 32 and <= %d", MH_BLOCK);
     }
     if (cfg->algo != PBU_ALGO_ISDE) {
         e->mh = find_mh(pr->model, pr->n_param, pr->n_unc, lanes, adapt ? 1 : 0);
@@ -228,14 +241,15 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
 
     // ---- problem records
     std::vector<double> rec;
-    int ncol, ncol0;
-    build_records(pr, nd, rec, ncol, ncol0);
+    int ncol;
+    double J_const;
+    build_records(pr, nd, rec, ncol, J_const);
     ProblemDev &pd = e->prob;
     memset(&pd, 0, sizeof pd);
     pd.n_points = pr->n_points;
     pd.n_runs = pr->n_runs;
     pd.ncol = ncol;
-    pd.ncol0 = ncol0;
+    pd.J_const = J_const;
     pd.n_param = pr->n_param;
     pd.n_unc = pr->n_unc;
     for (int i = 0; i < PBU_MAX_DIM; ++i) pd.unc_idx[i] = -1;

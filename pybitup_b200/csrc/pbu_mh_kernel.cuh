@@ -29,7 +29,7 @@ __host__ __device__ constexpr int even_up(int n) { return (n + 1) & ~1; }
 // Stage all point records into shared memory (resident mode).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void stage_records(double *smem_rec, uint64_t *bar, const ProblemDev &prob) {
-    const uint32_t total = (uint32_t)prob.n_points * (uint32_t)prob.ncol * 8u;
+    const uint32_t total = (uint32_t)prob.n_points * (uint32_t)prob.ncol * 8u;   // multiple of 16
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
@@ -47,57 +47,74 @@ __device__ __forceinline__ void stage_records(double *smem_rec, uint64_t *bar, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// Gaussian sum of squares J(theta) = sum_runs sum_k ((y_k - f_k) * w_k)^2 over the staged records
-// (Likelihood.arg_gauss_likelihood, bayesian_inference.py:495-542).
+// Gaussian sum of squares J(theta) = sum_runs sum_k ((y_run,k - f_k) * w_k)^2 over the staged records
+// (Likelihood.arg_gauss_likelihood, bayesian_inference.py:495-542).  Several experimental runs are
+// folded on the host with the exact identity
+//   sum_r (y_r - f)^2 = n_r (ybar - f)^2 + sum_r (y_r - ybar)^2
+// so a record holds ybar and w*sqrt(n_r) and the second term is the constant prob.J_const: the
+// device loop reads one (w, y) pair per point whatever n_runs is.
 // ------------------------------------------------------------------------------------------------
 template <class M, int G>
 __device__ __forceinline__ double sum_of_squares(const typename M::Ctx &ctx, const ProblemDev &prob, const double *smem_rec,
                                                  int sub, unsigned group_mask) {
-    constexpr int NC0 = even_up(M::ND + 2);
+    constexpr int NC = even_up(M::ND + 2);     // doubles per record: [design | w | y] (+ pad)
+    constexpr int U = M::UNROLL;               // points in flight per thread (independent DFMA chains)
     const int N = prob.n_points;
-    const int ncol = prob.ncol;
-    const int n_runs = prob.n_runs;
     typename M::Seq seq;
     M::seq_init(ctx, seq, prob);
-    double J0 = 0.0, J1 = 0.0;
-    auto point = [&](int k, double &J) {
-        const double2 *r2 = reinterpret_cast<const double2 *>(smem_rec + (size_t)k * ncol);
-        double rec[NC0];
+    auto load = [&](int k, double (&rec)[NC]) {
+        const double2 *r2 = reinterpret_cast<const double2 *>(smem_rec + (size_t)k * NC);
 #pragma unroll
-        for (int j = 0; j < NC0 / 2; ++j) {
-            double2 v = r2[j];
+        for (int j = 0; j < NC / 2; ++j) {
+            const double2 v = r2[j];
             rec[2 * j] = v.x;
             rec[2 * j + 1] = v.y;
         }
-        const double f = M::eval(ctx, seq, rec);
-        const double w = rec[M::ND];
-        const double t = (rec[M::ND + 1] - f) * w;
-        J = fma(t, t, J);
-        if (n_runs > 1) {
-            const double *extra = smem_rec + (size_t)k * ncol + NC0;
-            for (int r = 1; r < n_runs; ++r) {
-                const double tr = (extra[r - 1] - f) * w;
-                J = fma(tr, tr, J);
-            }
-        }
     };
+    double J = 0.0;
     if (M::SEQUENTIAL) {
-        for (int k = 0; k < N; ++k) point(k, J0);
-    } else {
-        int k = sub;
-#pragma unroll 2
-        for (; k + G < N; k += 2 * G) {
-            point(k, J0);
-            point(k + G, J1);
+        for (int k = 0; k < N; ++k) {
+            double rec[NC];
+            load(k, rec);
+            const double f = M::eval(ctx, seq, rec);
+            const double t = (rec[M::ND + 1] - f) * rec[M::ND];
+            J = fma(t, t, J);
         }
-        if (k < N) point(k, J0);
+    } else {
+        double Ju[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) Ju[u] = 0.0;
+        int k = sub;
+#pragma unroll 1
+        for (; k + (U - 1) * G < N; k += U * G) {
+            double rec[U][NC];
+#pragma unroll
+            for (int u = 0; u < U; ++u) load(k + u * G, rec[u]);
+            double f[U], t[U];
+            M::template eval_batch<U, NC>(ctx, seq, rec, f);
+#pragma unroll
+            for (int u = 0; u < U; ++u) t[u] = rec[u][M::ND + 1] - f[u];
+#pragma unroll
+            for (int u = 0; u < U; ++u) t[u] *= rec[u][M::ND];
+#pragma unroll
+            for (int u = 0; u < U; ++u) Ju[u] = fma(t[u], t[u], Ju[u]);
+        }
+#pragma unroll 1
+        for (; k < N; k += G) {
+            double rec[NC];
+            load(k, rec);
+            const double f = M::eval(ctx, seq, rec);
+            const double t = (rec[M::ND + 1] - f) * rec[M::ND];
+            Ju[0] = fma(t, t, Ju[0]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) J += Ju[u];
     }
-    double J = J0 + J1;
     if (G > 1) {
 #pragma unroll
         for (int s = 1; s < G; s <<= 1) J += __shfl_xor_sync(group_mask, J, s);
     }
-    return J;
+    return J + prob.J_const;
 }
 
 // BayesianPosterior.compute_log_value (bayesian_inference.py:44-64) with the identity
@@ -188,8 +205,15 @@ __device__ __forceinline__ void propose(const double (&x)[D], const double (&R)[
 // ------------------------------------------------------------------------------------------------
 // The kernel.
 // ------------------------------------------------------------------------------------------------
+constexpr int MH_BLOCK = 128;
+// registers: cap at 65536/(128*MINB) so that MINB blocks (4*MINB warps) are resident per SM
+template <int D, bool ADAPT>
+__host__ __device__ constexpr int mh_min_blocks() {
+    return (D <= 4) ? 3 : 2;
+}
+
 template <class M, int D, int G, bool ADAPT>
-__global__ void mh_step_kernel(const __grid_constant__ MhParams p) {
+__global__ void __launch_bounds__(MH_BLOCK, mh_min_blocks<D, ADAPT>()) mh_step_kernel(const __grid_constant__ MhParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     double *smem_rec = reinterpret_cast<double *>(smem_raw + 128);
@@ -210,7 +234,6 @@ __global__ void mh_step_kernel(const __grid_constant__ MhParams p) {
     // ---- load state
     double x[D], R[NT], lp;
     double xav[ADAPT ? D : 1], V[ADAPT ? NT : 1];
-    double wmean[D], wM2[NT];
 #pragma unroll
     for (int i = 0; i < D; ++i) x[i] = p.st.x[i * C + c];
 #pragma unroll
@@ -222,11 +245,6 @@ __global__ void mh_step_kernel(const __grid_constant__ MhParams p) {
 #pragma unroll
         for (int i = 0; i < NT; ++i) V[i] = p.st.V[i * C + c];
     }
-#pragma unroll
-    for (int i = 0; i < D; ++i) wmean[i] = p.st.wmean[i * C + c];
-#pragma unroll
-    for (int i = 0; i < NT; ++i) wM2[i] = p.st.wM2[i * C + c];
-    int64_t wcount = p.st.wcount[c];
     double mean_r = p.st.mean_r[c];
     int64_t n_rej = p.st.n_rej[c];
     int64_t n_eval = p.st.n_eval[c];
@@ -241,71 +259,68 @@ __global__ void mh_step_kernel(const __grid_constant__ MhParams p) {
 
     for (int64_t s = 0; s < p.n_steps; ++s) {
         const int64_t it = p.it0 + s + 1;
-        // ---- stage 1 proposal (mha.py:184-193)
-        double z[D], u;
-        if (injected) {
-            if (!draw_injected<D>(p.streams, c, cn, cu, z, u)) status |= ST_STREAM_EXHAUSTED;
-        } else {
-            draw_philox<D>(p.seed, gchain, (uint64_t)it, 0u, z, u);
-        }
-        double y1[D];
-        propose<D>(x, R, z, 1.0, y1);
-        const double lp1 = log_posterior<M, D, G>(y1, p.prob, smem_rec, sub, group_mask);
-        n_eval += 1;
-        // ---- acceptance ratio (mha.py:195-207)
-        double r = (lp1 == -INFINITY) ? 0.0 : exp(lp1 - lp);
-        if (r != r) {
-            status |= ST_NAN_RATIO;
-            if (p.nan_rejects) r = 0.0;
-        }
-        const double alpha = py_min1(r);
+        // Up to two proposal stages share ONE inlined copy of the posterior evaluation (code size):
+        // stage 0 = the Metropolis proposal (mha.py:184-224), stage 1 = the delayed-rejection
+        // proposal (mha.py:535-567), entered only by chains whose first proposal was rejected.
+        double y1[D], lp1 = 0.0, lp2 = nan(""), r = 0.0, alpha = 0.0;
         int acc = 0;
-        double lp2 = nan("");
-        if (u < alpha) {                                   // mha.py:214-222
-#pragma unroll
-            for (int i = 0; i < D; ++i) x[i] = y1[i];
-            lp = lp1;
-            acc = 1;
-        } else if (p.delayed) {                            // mha.py:535-567
-            double z2[D], u2;
+#pragma unroll 1
+        for (int stage = 0; stage < 2; ++stage) {
+            double z[D], u;
             if (injected) {
-                if (!draw_injected<D>(p.streams, c, cn, cu, z2, u2)) status |= ST_STREAM_EXHAUSTED;
+                if (!draw_injected<D>(p.streams, c, cn, cu, z, u)) status |= ST_STREAM_EXHAUSTED;
             } else {
-                draw_philox<D>(p.seed, gchain, (uint64_t)it, 1u, z2, u2);
+                draw_philox<D>(p.seed, gchain, (uint64_t)it, (uint32_t)stage, z, u);
             }
-            double y2[D];
-            propose<D>(x, R, z2, p.gamma_dr, y2);
-            lp2 = log_posterior<M, D, G>(y2, p.prob, smem_rec, sub, group_mask);
+            double y[D];
+            propose<D>(x, R, z, stage == 0 ? 1.0 : p.gamma_dr, y);          // :193, :543
+            const double lpy = log_posterior<M, D, G>(y, p.prob, smem_rec, sub, group_mask);
             n_eval += 1;
-            const double r12 = exp(lp1 - lp2);
-            const double a12 = py_min1(r12);
-            // inv_V = inv_R * inv_R^T ELEMENTWISE = diag(1/R_ii^2)  (mha.py:517-518, :594-595)
-            double M2 = 0.0, M4 = 0.0;
+            bool accept;
+            if (stage == 0) {
 #pragma unroll
-            for (int i = 0; i < D; ++i) {
-                const double ir = 1.0 / R[tri_idx(D, i, i)];
-                const double iv = ir * ir;
-                const double d1 = y1[i] - y2[i];
-                const double d2 = y1[i] - x[i];
-                M2 += (d1 * iv) * d1;
-                M4 += (d2 * iv) * d2;
-            }
-            double r2 = exp(lp2 - lp) * (exp(-0.5 * M2) / exp(-0.5 * M4)) * (1.0 - a12) / (1.0 - alpha);   // mha.py:555-556
-            if (r2 != r2) {
-                status |= ST_NAN_RATIO;
-                if (p.nan_rejects) r2 = 0.0;
-            }
-            const double a2 = py_min1(r2);
-            if (u2 < a2) {
-#pragma unroll
-                for (int i = 0; i < D; ++i) x[i] = y2[i];
-                lp = lp2;
-                acc = 2;
+                for (int i = 0; i < D; ++i) y1[i] = y[i];
+                lp1 = lpy;
+                r = (lp1 == -INFINITY) ? 0.0 : exp(lp1 - lp);              // :200-205
+                if (r != r) {
+                    status |= ST_NAN_RATIO;
+                    if (p.nan_rejects) r = 0.0;
+                }
+                alpha = py_min1(r);                                         // :207
+                accept = u < alpha;                                         // :214
             } else {
-                n_rej += 1;
+                lp2 = lpy;
+                const double r12 = exp(lp1 - lp2);                          // :547
+                const double a12 = py_min1(r12);
+                // inv_V = inv_R * inv_R^T ELEMENTWISE = diag(1/R_ii^2)  (:517-518, :594-595)
+                double M2 = 0.0, M4 = 0.0;
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    const double ir = 1.0 / R[tri_idx(D, i, i)];
+                    const double iv = ir * ir;
+                    const double d1 = y1[i] - y[i];
+                    const double d2 = y1[i] - x[i];
+                    M2 += (d1 * iv) * d1;
+                    M4 += (d2 * iv) * d2;
+                }
+                double r2 = exp(lp2 - lp) * (exp(-0.5 * M2) / exp(-0.5 * M4)) * (1.0 - a12) / (1.0 - alpha);   // :555-556
+                if (r2 != r2) {
+                    status |= ST_NAN_RATIO;
+                    if (p.nan_rejects) r2 = 0.0;
+                }
+                accept = u < py_min1(r2);                                   // :558-562
             }
-        } else {
-            n_rej += 1;
+            if (accept) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) x[i] = y[i];
+                lp = lpy;
+                acc = stage + 1;
+                break;
+            }
+            if (stage == 1 || !p.delayed) {
+                n_rej += 1;                                                 // :224, :567
+                break;
+            }
         }
 
         // ---- covariance adaptation (mha.py:432-487)
@@ -371,28 +386,34 @@ __global__ void mh_step_kernel(const __grid_constant__ MhParams p) {
             mean_r += alpha;                                // :170
         }
 
-        // ---- running moments of the visited states (input of the moment reduction, K4)
-        {
-            wcount += 1;
-            const double inv_n = 1.0 / (double)wcount;
-            double dl[D];
-#pragma unroll
-            for (int i = 0; i < D; ++i) {
-                dl[i] = x[i] - wmean[i];
-                wmean[i] = fma(dl[i], inv_n, wmean[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-#pragma unroll
-                for (int j = i; j < D; ++j) wM2[tri_idx(D, i, j)] = fma(dl[i], x[j] - wmean[j], wM2[tri_idx(D, i, j)]);
-        }
-
         // ---- outputs
         if (writer) {
             if (p.out.trace_lp1) p.out.trace_lp1[s * C + c] = lp1;
             if (p.out.trace_lp2) p.out.trace_lp2[s * C + c] = lp2;
             if (p.out.trace_acc) p.out.trace_acc[s * C + c] = (uint8_t)acc;
             if (it % p.thin == 0) {
+                // running (Welford) moments of the KEPT states, held in global memory so that they cost
+                // no registers in the data loop; input of the moment reduction (K4: pooled covariance, R-hat)
+                {
+                    const int64_t wc = p.st.wcount[c] + 1;
+                    p.st.wcount[c] = wc;
+                    const double inv_n = 1.0 / (double)wc;
+                    double dl[D], mu[D];
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+                        const double m = p.st.wmean[i * C + c];
+                        dl[i] = x[i] - m;
+                        mu[i] = fma(dl[i], inv_n, m);
+                        p.st.wmean[i * C + c] = mu[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < D; ++i)
+#pragma unroll
+                        for (int j = i; j < D; ++j) {
+                            double *q = &p.st.wM2[tri_idx(D, i, j) * C + c];
+                            *q = fma(dl[i], x[j] - mu[j], *q);
+                        }
+                }
                 const int64_t row = it / p.thin - p.it0 / p.thin - 1;
                 if (p.out.samples) {
 #pragma unroll
@@ -416,11 +437,6 @@ __global__ void mh_step_kernel(const __grid_constant__ MhParams p) {
 #pragma unroll
             for (int i = 0; i < NT; ++i) p.st.V[i * C + c] = V[i];
         }
-#pragma unroll
-        for (int i = 0; i < D; ++i) p.st.wmean[i * C + c] = wmean[i];
-#pragma unroll
-        for (int i = 0; i < NT; ++i) p.st.wM2[i * C + c] = wM2[i];
-        p.st.wcount[c] = wcount;
         p.st.mean_r[c] = mean_r;
         p.st.n_rej[c] = n_rej;
         p.st.n_eval[c] = n_eval;
@@ -474,7 +490,7 @@ __global__ void eval_model_kernel(const __grid_constant__ ProblemDev prob, const
     M::seq_init(ctx, seq, prob);
     constexpr int NC0 = even_up(M::ND + 2);
     for (int k = 0; k < prob.n_points; ++k) {
-        const double2 *r2 = reinterpret_cast<const double2 *>(smem_rec + (size_t)k * prob.ncol);
+        const double2 *r2 = reinterpret_cast<const double2 *>(smem_rec + (size_t)k * NC0);
         double rec[NC0];
 #pragma unroll
         for (int j = 0; j < NC0 / 2; ++j) {

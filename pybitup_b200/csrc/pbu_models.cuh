@@ -9,7 +9,8 @@
 //   eval(ctx, seq, rec) -> f_k   with rec = the point record in registers
 // and, when HAS_GRAD, grad(ctx, rec, j) = d f_k / d theta_j.
 //
-// Record layout: [design (ND) | w = 1/(std_y*gamma) | y_run0 | pad to even | y_run1 ...].
+//   UNROLL      points a thread keeps in flight (independent FP64 dependency chains)
+// Record layout: [design (ND) | w = sqrt(n_runs)/(std_y*gamma) | ybar | pad to even].
 #pragma once
 #include "pbu_common.cuh"
 
@@ -24,6 +25,7 @@ struct LinearModel {
     static constexpr bool SEQUENTIAL = false;
     static constexpr bool HAS_GRAD = true;
     static constexpr int ID = PBU_MODEL_LINEAR;
+    static constexpr int UNROLL = (P <= 4) ? 4 : ((P <= 6) ? 3 : 2);
     struct Ctx {
         double th[P];
     };
@@ -34,10 +36,21 @@ struct LinearModel {
     }
     __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const ProblemDev &) {}
     __device__ __forceinline__ static double eval(const Ctx &c, Seq &, const double *rec) {
-        double f = 0.0;
+        double f = rec[0] * c.th[0];
 #pragma unroll
-        for (int j = 0; j < P; ++j) f = fma(rec[j], c.th[j], f);
+        for (int j = 1; j < P; ++j) f = fma(rec[j], c.th[j], f);
         return f;
+    }
+    // U points at once, written stage-by-stage across the points so that the U dependency chains are
+    // interleaved in program order (ptxas keeps that order; written point-by-point it serialises them)
+    template <int U, int NC>
+    __device__ __forceinline__ static void eval_batch(const Ctx &c, Seq &, const double (&rec)[U][NC], double (&f)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) f[u] = rec[u][0] * c.th[0];
+#pragma unroll
+        for (int j = 1; j < P; ++j)
+#pragma unroll
+            for (int u = 0; u < U; ++u) f[u] = fma(rec[u][j], c.th[j], f[u]);
     }
     __device__ __forceinline__ static double grad(const Ctx &, const double *rec, int j) { return rec[j]; }
 };
@@ -51,6 +64,7 @@ struct PolyModel {
     static constexpr bool SEQUENTIAL = false;
     static constexpr bool HAS_GRAD = true;
     static constexpr int ID = PBU_MODEL_POLY;
+    static constexpr int UNROLL = 4;
     struct Ctx {
         double th[P];
     };
@@ -66,6 +80,15 @@ struct PolyModel {
 #pragma unroll
         for (int j = P - 2; j >= 0; --j) f = fma(f, x, c.th[j]);
         return f;
+    }
+    template <int U, int NC>
+    __device__ __forceinline__ static void eval_batch(const Ctx &c, Seq &, const double (&rec)[U][NC], double (&f)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) f[u] = c.th[P - 1];
+#pragma unroll
+        for (int j = P - 2; j >= 0; --j)
+#pragma unroll
+            for (int u = 0; u < U; ++u) f[u] = fma(f[u], rec[u][0], c.th[j]);
     }
     __device__ __forceinline__ static double grad(const Ctx &, const double *rec, int j) {
         double p = 1.0;
@@ -85,6 +108,7 @@ struct ArrheniusModel {
     static constexpr bool SEQUENTIAL = true;
     static constexpr bool HAS_GRAD = false;
     static constexpr int ID = PBU_MODEL_ARRHENIUS;
+    static constexpr int UNROLL = 1;
     static constexpr double R_GAS = 8.314462618;
     struct Ctx {
         double c0, ER, n, F, h, g_start;
@@ -117,6 +141,11 @@ struct ArrheniusModel {
         s.g0 = g1;
         return 1.0 - c.F * s.alpha;
     }
+    template <int U, int NC>
+    __device__ __forceinline__ static void eval_batch(const Ctx &c, Seq &s, const double (&rec)[U][NC], double (&f)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) f[u] = eval(c, s, rec[u]);
+    }
     __device__ __forceinline__ static double grad(const Ctx &, const double *, int) { return 0.0; }
 };
 
@@ -129,6 +158,7 @@ struct HeatModel {
     static constexpr bool SEQUENTIAL = false;
     static constexpr bool HAS_GRAD = false;
     static constexpr int ID = PBU_MODEL_HEAT;
+    static constexpr int UNROLL = 2;
     struct Ctx {
         double gamma, c1, c2, T_amb;
     };
@@ -147,6 +177,11 @@ struct HeatModel {
     __device__ __forceinline__ static double eval(const Ctx &c, Seq &, const double *rec) {
         const double x = rec[0];
         return c.c1 * exp(-c.gamma * x) + c.c2 * exp(c.gamma * x) + c.T_amb;
+    }
+    template <int U, int NC>
+    __device__ __forceinline__ static void eval_batch(const Ctx &c, Seq &s, const double (&rec)[U][NC], double (&f)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) f[u] = eval(c, s, rec[u]);
     }
     __device__ __forceinline__ static double grad(const Ctx &, const double *, int) { return 0.0; }
 };
