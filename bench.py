@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Headline benchmark of the batched-chain MCMC hot path (BASELINE.json metric: chain-steps/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on for one GPU):
+cubic polynomial model, d = 4 parameters, N = 1000 data points, adaptive Metropolis,
+65,536 chains per B200 (weak scaling: every rank owns its own 65,536 chains, no data-path collective).
+One bench "step" = ITERS_PER_STEP sampler iterations of all chains = one launch of the fused step kernel.
+
+What is timed
+  value    chain states resident in HBM, CUDA events around each kernel launch on the launching stream,
+           L2 flushed between timed launches, max over ranks (barrier + synchronize on both sides).
+  e2e      the same through the public host API with HOST buffers: every step uploads the chains' starting
+           points from pinned host memory, initialises the chains, runs ITERS_PER_STEP iterations and reads
+           the final states, log-posteriors and counters back to the host.
+  roofline the step kernel is FP64-pipe bound (the data shared by all chains stays in shared
+           memory, so HBM does not bind); achieved = algorithmic flops per launch / mean launch duration,
+           peak = a DFMA micro-benchmark run live on the same GPU (MEASURED_PEAKS.json has no FP64 entry).
+           The HBM view (algorithmic bytes / duration vs MEASURED_PEAKS.json hbm_gbs) is reported beside it.
+  cpu_baseline  the CPU oracle port of the reference's loop (oracle/mcmc_oracle.py), one chain on one core,
+           on a bounded sample of the same workload (rank 0, N = 1 only).
+
+--impl reference times the reference's CPU implementation of the path (the oracle port: the reference is
+pure Python and /root/reference does not exist on the GPU box) on all host cores, one chain per process.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "chain-steps/sec"
+UNIT = "chain-steps/s"
+CHAINS_PER_GPU = 65536
+ITERS_PER_STEP = 100
+N_POINTS = 1000
+D = 4
+WORKLOAD = "cubic polynomial (Horner), d=4, N=1000, adaptive Metropolis (updating_it=10, eps_v=1e-10), " \
+           "65536 chains per GPU, %d iterations per step" % ITERS_PER_STEP
+AM = dict(updating_it=10, eps_v=1e-10)
+# SURVEY.md 8(d), lower-bound convention (FMA = 2): N*(2p+4) + proposal d(d+1) + accept 3 + AM 8d^2+3d
+FLOPS_PER_CHAIN_STEP = N_POINTS * (2 * 3 + 4) + D * (D + 1) + 3 + (8 * D * D + 3 * D)
+# per launch and chain: state in + out (x, lp, R, xav, V, counters) ; shared data once per block
+STATE_BYTES_PER_CHAIN = 2 * 8 * (D + 1 + 10 + D + 10 + 4)
+DATA_BYTES = N_POINTS * 4 * 8
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        self.f.close()
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs
+def _cpu_chain_worker(args):
+    """One chain of the workload through the oracle port; returns (iterations, seconds)."""
+    seed, n_it = args
+    from oracle import mcmc_oracle as orc
+    from pybitup_b200 import synthetic
+    p = synthetic.cubic_problem(n_points=N_POINTS)
+    prob = orc.Problem(model=p["model"], theta_nom=p["theta_nom"], unc_idx=p["unc_idx"], y=p["y"], std_y=p["std_y"],
+                       lb=p["lb"], ub=p["ub"], gamma=p["gamma"], design=p["design"])
+    rng = np.random.default_rng(seed)
+    st = orc.Streams(rng.standard_normal(n_it * D), rng.random(n_it))
+    x0 = synthetic.chain_starts(p["x0"], 1, jitter=0.01, seed=seed)[0]
+    t0 = time.perf_counter()
+    orc.run_mh(prob, x0, p["prop_cov"], n_it, st, adaptive=True, delayed=False, **AM)
+    return n_it, time.perf_counter() - t0
+
+
+def cpu_port_rate(n_procs, n_it, pool=None):
+    """chain-steps/s of the oracle port with n_procs independent single-chain processes."""
+    if n_procs == 1 or pool is None:
+        it, dt = _cpu_chain_worker((0, n_it))
+        return it / dt, dt
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_chain_worker, [(s, n_it) for s in range(n_procs)], chunksize=1)
+    wall = time.perf_counter() - t0
+    # the processes run their chains concurrently: rate = all iterations / wall time of the slowest
+    return sum(it for it, _ in res) / max(dt for _, dt in res), wall
+
+
+def run_reference_arm(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    n_it = 20000
+    import multiprocessing as mp
+    pool = mp.get_context("spawn").Pool(cores) if cores > 1 else None
+    try:
+        for _ in range(min(args.warmup, 1)):
+            cpu_port_rate(cores, 500, pool)
+        rates, t_all = [], 0.0
+        for _ in range(args.steps):
+            r, wall = cpu_port_rate(cores, n_it, pool)
+            rates.append(r)
+            t_all += wall
+    finally:
+        if pool is not None:
+            pool.close()
+            pool.join()
+    value = float(np.mean(rates))
+    sample = "%d independent chains (one process per core) x %d AM iterations per bench step" % (cores, n_it)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU port of the reference loop (oracle/mcmc_oracle.py); the reference is "
+                   "pure Python and is not present on the GPU box"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from pybitup_b200 import _capi, synthetic
+    from pybitup_b200.engine import ChainEngine, ProblemSpec, SamplerConfig
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    C, T = args.chains, args.iters
+    K, W = args.steps, args.warmup
+    p = synthetic.cubic_problem(n_points=N_POINTS)
+    spec = ProblemSpec.from_dict(p)
+    cfg = SamplerConfig(algo="AMH", seed=2026, chain_offset=rank * C, **AM)
+    x0 = synthetic.chain_starts(p["x0"], C, jitter=0.01, seed=1000 + rank)
+
+    fp64_peak, _ = _capi.measure_fp64_peak(local_rank, 4096, 5)
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    # ---- device-resident timing -----------------------------------------------------------------
+    eng = ChainEngine(spec, cfg, C, device=local_rank)
+    eng.init_chains(x0, p["prop_cov"])
+    out = None
+    for _ in range(W):
+        out = eng.run(T, thin=T, keep_samples=True, out=None)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    for k in range(K):
+        flush_buf.fill_(k & 0xff)                                          # L2 flush between timed launches
+        ev[k][0].record()
+        out = eng.run(T, thin=T, keep_samples=True)
+        ev[k][1].record()
+    barrier()
+    clk = clocks.stop()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    t_dev = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    total_ms = float(t_dev.item())
+    ctr = eng.counters()
+    acc_rate = 1.0 - float(ctr["n_rejected"].mean()) / max(eng.iteration, 1)
+    bad = int(np.count_nonzero(ctr["status"]))
+    eng.close()
+    value = world * C * T * K / (total_ms * 1e-3)
+
+    # ---- end to end through the host API --------------------------------------------------------
+    x0_pin = torch.from_numpy(x0).pin_memory()
+    x0_host = x0_pin.numpy()
+    eng = ChainEngine(spec, cfg, C, device=local_rank)
+    h2d = C * 8 * (2 * D + 2 * 10 + 1)            # x0, xav, packed R and V, evaluation counters
+    d2h = C * 8 * (D + 1) + C * (8 + 8 + 8 + 4)
+    for _ in range(min(W, 3)):
+        eng.init_chains(x0_host, p["prop_cov"])
+        eng.run(T, thin=T, keep_samples=False)
+        eng.state()
+        eng.counters()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for k in range(K):
+        eng.init_chains(x0_host, p["prop_cov"])
+        eng.run(T, thin=T, keep_samples=False)
+        xs, lps = eng.state()
+        eng.counters()
+    e1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    t_e2e = torch.tensor([max(e0.elapsed_time(e1), 1e3 * t_wall)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * C * T * K / (float(t_e2e.item()) * 1e-3)
+    eng.close()
+
+    # ---- CPU baseline (rank 0, single GPU runs only) ----------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        n_it = 100000
+        rate, dt = cpu_port_rate(1, n_it)
+        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "1 chain x %d AM iterations of the same cubic problem through oracle/mcmc_oracle.py (%.1f s)" % (n_it, dt)}
+
+    if rank == 0:
+        ms_launch = total_ms / K
+        flops_launch = float(FLOPS_PER_CHAIN_STEP) * C * T
+        achieved = flops_launch / (ms_launch * 1e-3) / 1e12
+        bytes_launch = float(STATE_BYTES_PER_CHAIN) * C + DATA_BYTES * ((C + 127) // 128)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "chains_per_gpu": C, "iterations_per_step": T, "rng": "Philox4x32-10",
+                       "l2": "flushed between timed launches (256 MiB fill)", "acceptance_rate": acc_rate,
+                       "chains_with_status_flags": bad},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": K,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak, "traffic": None,
+                         "kernel": "mh_step_kernel<PolyModel<4>,4,G,adapt>",
+                         "flops_per_chain_step": FLOPS_PER_CHAIN_STEP,
+                         "peak_source": "live DFMA micro-benchmark on this GPU (pbu_measure_fp64_peak); "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "hbm": {"achieved": bytes_launch / (ms_launch * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": bytes_launch / (ms_launch * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src}},
+            "cpu_baseline": cpu,
+        }
+        prof = os.path.join(ROOT, "profiles", "traffic_r1.json")
+        if os.path.exists(prof):
+            try:
+                with open(prof) as f:
+                    line["roofline"]["traffic"] = json.load(f).get("dram_bytes_per_launch")
+            except (OSError, ValueError):
+                pass
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
+    ap.add_argument("--iters", type=int, default=ITERS_PER_STEP, help="sampler iterations per bench step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

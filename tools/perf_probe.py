@@ -41,7 +41,7 @@ def main():
         p = synthetic.cubic_problem()
         flops = 1000 * 10 + 20 + 140
         for lanes in (1, 2, 8):
-            for block in (64, 128, 256):
+            for block in (64, 128):
                 ms, acc, ev = time_run(p, "AMH", 65536, 100, lanes, block, updating_it=10, eps_v=1e-10)
                 rate = 65536 * 100 / (ms * 1e-3)
                 print(json.dumps({"cfg": "cubic_am_65536", "lanes": lanes, "block": block, "ms": ms, "steps_per_s": rate,
