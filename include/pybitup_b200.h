@@ -161,6 +161,9 @@ int pbu_engine_get_counters(pbu_engine *e, int64_t *n_rejected /*[C]*/, double *
  * (:463-466) and running mean X_av_i (:455,:467); any pointer may be NULL. Row-major [C][d][d]. */
 int pbu_engine_get_proposal(pbu_engine *e, double *R_host, double *V_host, double *xav_host);
 int64_t pbu_engine_iteration(const pbu_engine *e);
+/* launch geometry the engine planned for the step kernel: lanes of a warp per chain, threads per block,
+ * blocks, dynamic shared memory bytes per block (diagnostics; no reference counterpart). */
+int pbu_engine_get_launch(const pbu_engine *e, int32_t *lanes, int32_t *block, int32_t *grid, int64_t *smem_bytes);
 
 /* ---- evaluation only: BayesianPosterior.compute_log_value (bayesian_inference.py:44-64) and
  *      Model.run_model (:338-371) for S parameter vectors -------------------------------------- */

@@ -86,6 +86,7 @@ def _load():
         "pbu_engine_get_counters": (C.c_int, [E, _lp, _dp, _lp, _ip]),
         "pbu_engine_get_proposal": (C.c_int, [E, _dp, _dp, _dp]),
         "pbu_engine_iteration": (C.c_int64, [E]),
+        "pbu_engine_get_launch": (C.c_int, [E, _ip, _ip, _ip, _lp]),
         "pbu_eval_logpost": (C.c_int, [E, _dp, C.c_int64, _dp]),
         "pbu_eval_model": (C.c_int, [E, _dp, C.c_int64, _dp]),
         "pbu_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp]),

@@ -14,11 +14,12 @@ namespace pbu {
 // counters costs nothing.
 // ------------------------------------------------------------------------------------------------
 struct ProblemDev {
-    const double *records;   // dev [N][ncol] point records: [design cols | w = sqrt(n_runs)/(std_y*gamma) | ybar | pad]
+    const double *records;   // dev [N][NC]  likelihood records, pre-scaled by w = sqrt(n_runs)/(std_y*gamma) (pbu_models.cuh)
+    const double *raw;       // dev [N][NCR] raw design records (Model.run_model / propagation)
     int32_t n_points;
     int32_t n_runs;
-    int32_t ncol;            // doubles per record (even) = even_up(ND + 2)
-    int32_t pad0;
+    int32_t ncol;            // doubles per likelihood record (even) = Model::NC
+    int32_t ncol_raw;        // doubles per raw record (even)        = Model::NCR
     double J_const;          // sum_k sum_runs ((y_run,k - ybar_k)/(std_y,k*gamma))^2, 0 for a single run
     int32_t n_param;
     int32_t n_unc;
@@ -79,6 +80,7 @@ struct MhParams {
     int32_t nan_rejects;
     int32_t resident;         // 1: all records fit in shared memory
     int32_t tile_points;      // streaming mode: points per shared-memory tile
+    double R0[PBU_MAX_DIM * (PBU_MAX_DIM + 1) / 2];   // packed upper Cholesky factor shared by all chains (non-adaptive samplers)
 };
 
 // status bits

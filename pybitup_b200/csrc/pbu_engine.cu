@@ -47,9 +47,13 @@ struct pbu_engine {
     const EvalKernelEntry *ev = nullptr;
     int lanes = 1;
     int block = 128;
-    size_t smem_bytes = 0;
+    int grid = 1;
+    size_t smem_bytes = 0;        // step / log-posterior kernels: barrier + likelihood records
+    size_t smem_raw_bytes = 0;    // model-evaluation kernel: barrier + raw records
+    std::vector<double> R0;       // packed upper Cholesky factor of the shared proposal covariance
     // device allocations
     double *d_records = nullptr;
+    double *d_raw = nullptr;
     ChainState st{};
     StreamsDev streams{};
     double *d_normals = nullptr, *d_uniforms = nullptr;
@@ -131,38 +135,103 @@ static const EvalKernelEntry *find_eval(int model, int P, int d) {
     return nullptr;
 }
 
-// Lower the problem to point records [N][ncol]: [design | w*sqrt(n_runs) | ybar | pad]; several runs are
-// folded exactly: sum_r (y_r - f)^2 = n_r (ybar - f)^2 + sum_r (y_r - ybar)^2 (second term -> J_const).
-static int build_records(const pbu_problem *pr, int nd, std::vector<double> &rec, int &ncol, double &J_const) {
-    const int N = pr->n_points, nr = pr->n_runs;
-    ncol = even_up(nd + 2);
-    rec.assign((size_t)N * ncol, 0.0);
+// Lower the problem to the two record streams of pbu_models.cuh.  Several runs are folded exactly:
+// sum_r (y_r - f)^2 = n_r (ybar - f)^2 + sum_r (y_r - ybar)^2  (second term -> J_const).
+static void build_records(const pbu_problem *pr, int nc, int ncr, std::vector<double> &rec, std::vector<double> &raw, double &J_const) {
+    const int N = pr->n_points, nr = pr->n_runs, P = pr->n_param;
+    rec.assign((size_t)N * nc, 0.0);
+    raw.assign((size_t)N * ncr, 0.0);
     J_const = 0.0;
     for (int k = 0; k < N; ++k) {
-        double *r = &rec[(size_t)k * ncol];
-        if (pr->model == PBU_MODEL_ARRHENIUS) {
-            const double T0 = pr->consts[0], dT = pr->consts[1];
-            r[0] = 1.0 / (T0 + ((double)k + 0.5) * dT);
-            r[1] = 1.0 / (T0 + ((double)k + 1.0) * dT);
-        } else {
-            for (int j = 0; j < nd; ++j) r[j] = pr->design[(size_t)k * pr->n_design_cols + j];
-        }
-        const double w = 1.0 / (pr->std_y[k] * pr->gamma);
-        if (nr == 1) {
-            r[nd] = w;
-            r[nd + 1] = pr->y[k];
-        } else {
-            double ybar = 0.0;
-            for (int q = 0; q < nr; ++q) ybar += pr->y[(size_t)q * N + k];
+        double *r = &rec[(size_t)k * nc];
+        double *q = &raw[(size_t)k * ncr];
+        double w = 1.0 / (pr->std_y[k] * pr->gamma);
+        double ybar = pr->y[k];
+        if (nr > 1) {
+            ybar = 0.0;
+            for (int i = 0; i < nr; ++i) ybar += pr->y[(size_t)i * N + k];
             ybar /= (double)nr;
-            for (int q = 0; q < nr; ++q) {
-                const double t = (pr->y[(size_t)q * N + k] - ybar) * w;
+            for (int i = 0; i < nr; ++i) {
+                const double t = (pr->y[(size_t)i * N + k] - ybar) * w;
                 J_const += t * t;
             }
-            r[nd] = w * std::sqrt((double)nr);
-            r[nd + 1] = ybar;
+            w *= std::sqrt((double)nr);
+        }
+        const double wy = w * ybar;
+        switch (pr->model) {
+            case PBU_MODEL_LINEAR:
+                for (int j = 0; j < P; ++j) {
+                    q[j] = pr->design[(size_t)k * P + j];
+                    r[j] = w * q[j];
+                }
+                r[P] = wy;
+                break;
+            case PBU_MODEL_ARRHENIUS: {
+                const double T0 = pr->consts[0], dT = pr->consts[1];
+                q[0] = r[0] = 1.0 / (T0 + ((double)k + 0.5) * dT);
+                q[1] = r[1] = 1.0 / (T0 + ((double)k + 1.0) * dT);
+                r[2] = w;
+                r[3] = wy;
+                break;
+            }
+            default:   // POLY, HEAT: one design column x
+                q[0] = r[0] = pr->design[k];
+                r[1] = w;
+                r[2] = wy;
+                break;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Launch geometry.  One block is resident per SM slot; the chains' G-lane groups are spread so that
+// the busiest SM has as little work as possible: block sizes in steps of one warp up to 512 threads
+// are tried for every compiled lane count, with the occupancy the runtime reports for that kernel.
+// Cost model (arbitrary units): the busiest SM runs ceil(blocks/n_sm) blocks, `occ` at a time; a
+// thread costs N/G point evaluations plus a fixed per-iteration part; with fewer than WSAT resident
+// warps the FP64 pipe is latency- rather than throughput-bound.
+// ------------------------------------------------------------------------------------------------
+static int plan_launch(pbu_engine *e, int model, bool sequential, bool adapt, int want_lanes, int want_block) {
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, e->device);
+    const double WSAT = 8.0;
+    const double N = (double)e->prob.n_points;
+    const double S0 = 30.0 + 6.0 * e->d;
+    const int lane_cand[3] = {1, 2, 8};
+    double best = 1e300;
+    bool found = false;
+    for (int g : lane_cand) {
+        if (want_lanes > 0 && g != want_lanes) continue;
+        if (sequential && g != 1) continue;
+        const MhKernelEntry *k = find_mh(model, e->P, e->d, g, adapt ? 1 : 0);
+        if (!k) continue;
+        CUDA_TRY(cudaFuncSetAttribute(k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+        for (int B = MH_MAX_BLOCK; B >= 32; B -= 32) {
+            if (want_block > 0 && B != want_block) continue;
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k->fn, B, e->smem_bytes) != cudaSuccess || occ < 1) {
+                cudaGetLastError();
+                continue;
+            }
+            const double blocks = std::ceil((double)e->C * g / B);
+            const double per_sm = std::ceil(blocks / nsm);
+            const double conc = std::min(per_sm, (double)occ);
+            const double warps = conc * B / 32.0;
+            const double work = (sequential ? N : std::ceil(N / g)) + S0;
+            const double t = per_sm * B * work * std::max(1.0, WSAT / warps);
+            if (t < best * (1.0 - 1e-3)) {
+                best = t;
+                e->mh = k;
+                e->lanes = g;
+                e->block = B;
+                e->grid = (int)blocks;
+                found = true;
+            }
+        }
+    }
+    if (!found)
+        return fail(PBU_ERR_UNSUPPORTED, "no MH kernel variant fits model=%d P=%d d=%d lanes=%d block=%d adapt=%d (smem %zu B)", model, e->P,
+                    e->d, want_lanes, want_block, (int)adapt, e->smem_bytes);
     return PBU_OK;
 }
 
@@ -203,52 +272,25 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
     e->nt = tri_size(e->d);
     e->ev = ev;
 
-    // ---- lanes per chain
-    int lanes = cfg->lanes_per_chain;
-    if (ev->sequential) lanes = 1;
-    if (lanes == 0) {
-        // minimise ceil(blocks/148)/G over the compiled lane counts; ties -> fewer lanes
-        const int cand[3] = {1, 2, 8};
-        double best = 1e300;
-        int nsm = 148;
-        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
-        for (int g : cand) {
-            double blocks = std::ceil((double)n_chains * g / 128.0);
-            double t = std::ceil(blocks / nsm) / g;
-            if (t < best * (1.0 - 1e-9)) {
-                best = t;
-                lanes = g;
-            }
-        }
-    }
-    e->lanes = lanes;
-    e->block = cfg->block_threads > 0 ? cfg->block_threads : MH_BLOCK;
-    if (e->block % 32 != 0 || e->block > MH_BLOCK) {
+    if (cfg->block_threads != 0 && (cfg->block_threads % 32 != 0 || cfg->block_threads < 32 || cfg->block_threads > MH_MAX_BLOCK)) {
         delete e;
-        return fail(PBU_ERR_INVALID, "block_threads must be a multiple of 32 and <= %d", MH_BLOCK);
+        return fail(PBU_ERR_INVALID, "block_threads must be a multiple of 32 in [32, %d]", MH_MAX_BLOCK);
     }
-    if (cfg->algo != PBU_ALGO_ISDE) {
-        e->mh = find_mh(pr->model, pr->n_param, pr->n_unc, lanes, adapt ? 1 : 0);
-        if (!e->mh) {
-            delete e;
-            return fail(PBU_ERR_UNSUPPORTED, "no MH kernel for model=%d P=%d d=%d lanes=%d adapt=%d", pr->model, pr->n_param, pr->n_unc,
-                        lanes, (int)adapt);
-        }
-    } else {
+    if (cfg->algo == PBU_ALGO_ISDE) {
         delete e;
         return fail(PBU_ERR_UNSUPPORTED, "ISDE kernel not built in this library version");
     }
 
     // ---- problem records
-    std::vector<double> rec;
-    int ncol;
+    std::vector<double> rec, raw;
     double J_const;
-    build_records(pr, nd, rec, ncol, J_const);
+    build_records(pr, ev->nc, ev->ncr, rec, raw, J_const);
     ProblemDev &pd = e->prob;
     memset(&pd, 0, sizeof pd);
     pd.n_points = pr->n_points;
     pd.n_runs = pr->n_runs;
-    pd.ncol = ncol;
+    pd.ncol = ev->nc;
+    pd.ncol_raw = ev->ncr;
     pd.J_const = J_const;
     pd.n_param = pr->n_param;
     pd.n_unc = pr->n_unc;
@@ -265,6 +307,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
     for (int i = 0; i < 8; ++i) pd.consts[i] = pr->consts[i];
 
     e->smem_bytes = 128 + rec.size() * sizeof(double);
+    e->smem_raw_bytes = 128 + raw.size() * sizeof(double);
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if ((int64_t)e->smem_bytes > (int64_t)max_smem) {
@@ -273,9 +316,17 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
                     e->smem_bytes, max_smem);
     }
     int rc;
-    if ((rc = dev_alloc(e, &e->d_records, rec.size())) != PBU_OK) return rc;
+    if ((rc = dev_alloc(e, &e->d_records, rec.size())) != PBU_OK || (rc = dev_alloc(e, &e->d_raw, raw.size())) != PBU_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(e->d_records, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(e->d_raw, raw.data(), raw.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     pd.records = e->d_records;
+    pd.raw = e->d_raw;
+
+    // ---- launch geometry
+    if ((rc = plan_launch(e, pr->model, ev->sequential != 0, adapt, cfg->lanes_per_chain, cfg->block_threads)) != PBU_OK) {
+        pbu_engine_destroy(e);
+        return rc;
+    }
 
     // ---- chain state
     const int64_t C = n_chains;
@@ -340,6 +391,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_init_chains(pbu
     std::vector<double> Rp;
     if (!chol_upper_host(V0_host, d, Rp))
         return fail(PBU_ERR_NOT_PD, "proposal covariance is not positive definite (scipy.linalg.cholesky would raise LinAlgError)");
+    e->R0 = Rp;
     std::vector<double> buf((size_t)nt * C);
     for (int i = 0; i < nt; ++i) std::fill(buf.begin() + (size_t)i * C, buf.begin() + (size_t)(i + 1) * C, Rp[i]);
     CUDA_TRY(cudaMemcpyAsync(e->st.R, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
@@ -406,6 +458,15 @@ extern "C" __attribute__((visibility("default"))) int64_t pbu_engine_n_keep(cons
 
 extern "C" __attribute__((visibility("default"))) int64_t pbu_engine_iteration(const pbu_engine *e) { return e ? e->iteration : -1; }
 
+extern "C" __attribute__((visibility("default"))) int pbu_engine_get_launch(const pbu_engine *e, int32_t *lanes, int32_t *block, int32_t *grid, int64_t *smem_bytes) {
+    if (!e) return fail(PBU_ERR_INVALID, "null engine");
+    if (lanes) *lanes = e->lanes;
+    if (block) *block = e->block;
+    if (grid) *grid = e->grid;
+    if (smem_bytes) *smem_bytes = (int64_t)e->smem_bytes;
+    return PBU_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine *e, int64_t n_steps, int64_t thin, const pbu_run_outputs *out) {
     if (!e) return fail(PBU_ERR_INVALID, "null engine");
     if (!e->initialised) return fail(PBU_ERR_INVALID, "pbu_engine_init_chains has not been called");
@@ -431,11 +492,9 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine 
     p.am_welford = e->cfg.am_welford;
     p.nan_rejects = e->cfg.nan_rejects;
     p.resident = 1;
-    CUDA_TRY(cudaFuncSetAttribute(e->mh->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
-    const int64_t threads = e->C * e->lanes;
-    const unsigned grid = (unsigned)((threads + e->block - 1) / e->block);
+    for (size_t i = 0; i < e->R0.size(); ++i) p.R0[i] = e->R0[i];
     void *args[] = {(void *)&p};
-    CUDA_TRY(cudaLaunchKernel(e->mh->fn, dim3(grid), dim3(e->block), args, e->smem_bytes, e->stream));
+    CUDA_TRY(cudaLaunchKernel(e->mh->fn, dim3((unsigned)e->grid), dim3(e->block), args, e->smem_bytes, e->stream));
     e->iteration += n_steps;
     return PBU_OK;
 }
@@ -556,11 +615,11 @@ extern "C" __attribute__((visibility("default"))) int pbu_eval_model(pbu_engine 
     int rc = upload_soa(e, X_host, S, &X_dev);
     if (rc) return rc;
     CUDA_TRY(cudaMalloc((void **)&f_dev, (size_t)S * N * sizeof(double)));
-    CUDA_TRY(cudaFuncSetAttribute(e->ev->eval_model, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    CUDA_TRY(cudaFuncSetAttribute(e->ev->eval_model, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_raw_bytes));
     const int block = 128;
     const unsigned grid = (unsigned)((S + block - 1) / block);
     void *args[] = {(void *)&e->prob, (void *)&X_dev, (void *)&S, (void *)&f_dev};
-    cudaError_t ce = cudaLaunchKernel(e->ev->eval_model, dim3(grid), dim3(block), args, e->smem_bytes, e->stream);
+    cudaError_t ce = cudaLaunchKernel(e->ev->eval_model, dim3(grid), dim3(block), args, e->smem_raw_bytes, e->stream);
     std::vector<double> pm;
     if (ce == cudaSuccess) {
         pm.resize((size_t)S * N);

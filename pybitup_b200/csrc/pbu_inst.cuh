@@ -11,7 +11,7 @@
         PBU_MH(MODEL, P, D, 8, 0), PBU_MH(MODEL, P, D, 8, 1)
 #define PBU_MH_SEQ(MODEL, P, D) PBU_MH(MODEL, P, D, 1, 0), PBU_MH(MODEL, P, D, 1, 1)
 #define PBU_EVAL(MODEL, P, D)                                                                 \
-    { MODEL::ID, P, D, MODEL::SEQUENTIAL ? 1 : 0, (const void *)&pbu::eval_logpost_kernel<MODEL, D>, \
+    { MODEL::ID, P, D, MODEL::SEQUENTIAL ? 1 : 0, MODEL::NC, MODEL::NCR, (const void *)&pbu::eval_logpost_kernel<MODEL, D>, \
       (const void *)&pbu::eval_model_kernel<MODEL, D> }
 
 #define PBU_DEFINE_SLICE(name, MH_LIST, EVAL_LIST)                                   \

@@ -11,134 +11,153 @@
 //   adapt_covariance          :432-487, :591-595
 // with no host round trip per iteration.
 //
-// Mapping: G lanes of a warp own one chain (G = 1, 2, 4, 8).  All G lanes carry the chain state
-// redundantly in registers and execute the scalar part of the step identically; the sum over the
-// N data points is strided over the G lanes and combined with an xor-butterfly of warp shuffles, so
-// every lane ends with the bit-identical sum.  The point records (design columns, weight, data) are
-// staged once per launch into shared memory with a bulk TMA copy and read by all chains of the
-// block: with G = 1 every shared-memory read is a warp broadcast.
+// Mapping: G lanes of a warp own one chain (G = 1, 2, 8).  All G lanes carry the chain state
+// redundantly and execute the scalar part of the step identically; the sum over the N data points
+// is strided over the G lanes and combined with an xor-butterfly of warp shuffles, so every lane
+// ends with the bit-identical sum.  The likelihood records are staged into shared memory with bulk
+// TMA copies and read by all chains of the block: with G = 1 every shared-memory read is a warp
+// broadcast.  Registers hold only what the data loop needs (state x, proposal, model constants,
+// U records in flight); the adaptive-Metropolis state (X_av, V_i, R) is touched once per iteration
+// and lives in global memory, chain-minor, where it stays L1/L2 resident.  That keeps the kernel
+// under 128 registers so that one block of up to 512 threads (16 warps) fills an SM, and lets the
+// host pick a block size that spreads the chains evenly over the 148 SMs (pbu_engine.cu::plan_launch).
 #pragma once
 #include "pbu_common.cuh"
 #include "pbu_models.cuh"
 
 namespace pbu {
 
-__host__ __device__ constexpr int even_up(int n) { return (n + 1) & ~1; }
+constexpr int MH_MAX_BLOCK = 512;
 
 // ------------------------------------------------------------------------------------------------
-// Stage all point records into shared memory (resident mode).
+// Stage `bytes` (multiple of 16) from global into shared memory with bulk TMA copies; all threads
+// of the block return once the data has landed.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_records(double *smem_rec, uint64_t *bar, const ProblemDev &prob) {
-    const uint32_t total = (uint32_t)prob.n_points * (uint32_t)prob.ncol * 8u;   // multiple of 16
+__device__ __forceinline__ void stage_records(double *smem_rec, uint64_t *bar, const double *gsrc, uint32_t bytes) {
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        mbar_expect_tx(bar, total);
+        mbar_expect_tx(bar, bytes);
         const uint32_t CH = 32768u;
-        for (uint32_t off = 0; off < total; off += CH) {
-            uint32_t n = (total - off < CH) ? (total - off) : CH;
-            tma_load_1d(reinterpret_cast<char *>(smem_rec) + off, reinterpret_cast<const char *>(prob.records) + off, n, bar);
+        for (uint32_t off = 0; off < bytes; off += CH) {
+            const uint32_t n = (bytes - off < CH) ? (bytes - off) : CH;
+            tma_load_1d(reinterpret_cast<char *>(smem_rec) + off, reinterpret_cast<const char *>(gsrc) + off, n, bar);
         }
     }
     mbar_wait(bar, 0);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Gaussian sum of squares J(theta) = sum_runs sum_k ((y_run,k - f_k) * w_k)^2 over the staged records
-// (Likelihood.arg_gauss_likelihood, bayesian_inference.py:495-542).  Several experimental runs are
-// folded on the host with the exact identity
-//   sum_r (y_r - f)^2 = n_r (ybar - f)^2 + sum_r (y_r - ybar)^2
-// so a record holds ybar and w*sqrt(n_r) and the second term is the constant prob.J_const: the
-// device loop reads one (w, y) pair per point whatever n_runs is.
-// ------------------------------------------------------------------------------------------------
-template <class M, int G>
-__device__ __forceinline__ double sum_of_squares(const typename M::Ctx &ctx, const ProblemDev &prob, const double *smem_rec,
-                                                 int sub, unsigned group_mask) {
-    constexpr int NC = even_up(M::ND + 2);     // doubles per record: [design | w | y] (+ pad)
-    constexpr int U = M::UNROLL;               // points in flight per thread (independent DFMA chains)
-    const int N = prob.n_points;
-    typename M::Seq seq;
-    M::seq_init(ctx, seq, prob);
-    auto load = [&](int k, double (&rec)[NC]) {
-        const double2 *r2 = reinterpret_cast<const double2 *>(smem_rec + (size_t)k * NC);
+template <int NC>
+__device__ __forceinline__ void load_record(const double *smem_rec, int k, double (&rec)[NC]) {
+    const double2 *r2 = reinterpret_cast<const double2 *>(smem_rec + (size_t)k * NC);
 #pragma unroll
-        for (int j = 0; j < NC / 2; ++j) {
-            const double2 v = r2[j];
-            rec[2 * j] = v.x;
-            rec[2 * j + 1] = v.y;
-        }
-    };
-    double J = 0.0;
+    for (int j = 0; j < NC / 2; ++j) {
+        const double2 v = r2[j];
+        rec[2 * j] = v.x;
+        rec[2 * j + 1] = v.y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gaussian sum of squares J(theta) = sum_runs sum_k ((y_run,k - f_k)/(std_y,k gamma))^2 over the records of
+// one shared-memory tile (Likelihood.arg_gauss_likelihood, bayesian_inference.py:495-542), and, when
+// GRAD, the gradient sum of Likelihood.compute_grad_log_value (:573-623).  Several experimental runs
+// are folded on the host with the exact identity
+//   sum_r (y_r - f)^2 = n_r (ybar - f)^2 + sum_r (y_r - ybar)^2
+// so a record carries w = sqrt(n_r)/(std_y gamma) and w*ybar, and the second term is the constant
+// prob.J_const: the device loop costs the same whatever n_runs is.
+// Ju[U] are U independent partial sums (one per point in flight).
+// ------------------------------------------------------------------------------------------------
+template <class M, int G, bool GRAD>
+__device__ __forceinline__ void tile_accumulate(const typename M::Ctx &ctx, typename M::Seq &seq, const double *tile, int n, int sub,
+                                                double (&Ju)[M::UNROLL], double (&g)[GRAD ? M::NPARAM : 1]) {
+    constexpr int NC = M::NC;
+    constexpr int U = M::UNROLL;
     if (M::SEQUENTIAL) {
-        for (int k = 0; k < N; ++k) {
-            double rec[NC];
-            load(k, rec);
-            const double f = M::eval(ctx, seq, rec);
-            const double t = (rec[M::ND + 1] - f) * rec[M::ND];
-            J = fma(t, t, J);
+        for (int k = 0; k < n; ++k) {
+            double rec[1][NC], t[1];
+            load_record<NC>(tile, k, rec[0]);
+            M::template resid_batch<1>(ctx, seq, rec, t);
+            Ju[0] = fma(t[0], t[0], Ju[0]);
         }
     } else {
-        double Ju[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) Ju[u] = 0.0;
         int k = sub;
 #pragma unroll 1
-        for (; k + (U - 1) * G < N; k += U * G) {
-            double rec[U][NC];
+        for (; k + (U - 1) * G < n; k += U * G) {
+            double rec[U][NC], t[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) load(k + u * G, rec[u]);
-            double f[U], t[U];
-            M::template eval_batch<U, NC>(ctx, seq, rec, f);
-#pragma unroll
-            for (int u = 0; u < U; ++u) t[u] = rec[u][M::ND + 1] - f[u];
-#pragma unroll
-            for (int u = 0; u < U; ++u) t[u] *= rec[u][M::ND];
+            for (int u = 0; u < U; ++u) load_record<NC>(tile, k + u * G, rec[u]);
+            M::template resid_batch<U>(ctx, seq, rec, t);
 #pragma unroll
             for (int u = 0; u < U; ++u) Ju[u] = fma(t[u], t[u], Ju[u]);
+            if constexpr (GRAD) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) M::grad_acc(ctx, rec[u], t[u], g);
+            }
         }
 #pragma unroll 1
-        for (; k < N; k += G) {
-            double rec[NC];
-            load(k, rec);
-            const double f = M::eval(ctx, seq, rec);
-            const double t = (rec[M::ND + 1] - f) * rec[M::ND];
-            Ju[0] = fma(t, t, Ju[0]);
+        for (; k < n; k += G) {
+            double rec[1][NC], t[1];
+            load_record<NC>(tile, k, rec[0]);
+            M::template resid_batch<1>(ctx, seq, rec, t);
+            Ju[0] = fma(t[0], t[0], Ju[0]);
+            if constexpr (GRAD) M::grad_acc(ctx, rec[0], t[0], g);
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) J += Ju[u];
     }
-    if (G > 1) {
+}
+
+template <int G>
+__device__ __forceinline__ double group_sum(double v, unsigned group_mask) {
 #pragma unroll
-        for (int s = 1; s < G; s <<= 1) J += __shfl_xor_sync(group_mask, J, s);
+    for (int s = 1; s < G; s <<= 1) v += __shfl_xor_sync(group_mask, v, s);
+    return v;
+}
+
+// Full parameter vector from the uncertain ones (Model.run_model, bayesian_inference.py:361-369).
+template <class M, int D>
+__device__ __forceinline__ void full_theta(const double (&x)[D], const ProblemDev &prob, double (&theta)[M::NPARAM]) {
+#pragma unroll
+    for (int q = 0; q < M::NPARAM; ++q) {
+        double v = prob.theta_nom[q];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+            if (prob.unc_idx[i] == q) v = x[i];
+        theta[q] = v;
     }
-    return J + prob.J_const;
+}
+
+template <int D>
+__device__ __forceinline__ bool inside_box(const double (&x)[D], const ProblemDev &prob) {
+    bool inside = true;
+#pragma unroll
+    for (int i = 0; i < D; ++i) inside = inside && !(x[i] < prob.lb[i] || x[i] > prob.ub[i]);   // bounds inclusive, distributions.py:284
+    return inside;
 }
 
 // BayesianPosterior.compute_log_value (bayesian_inference.py:44-64) with the identity
 // parametrisation: -inf outside the prior box WITHOUT evaluating the model (:53-55), otherwise
-// log_prior - log(1) + (-(1/2) J).
+// log_prior - log(1) + (-(1/2) J).   Resident mode: all records are in shared memory.
 template <class M, int D, int G>
 __device__ __forceinline__ double log_posterior(const double (&x)[D], const ProblemDev &prob, const double *smem_rec, int sub,
                                                 unsigned group_mask) {
-    bool inside = true;
-#pragma unroll
-    for (int i = 0; i < D; ++i) inside = inside && !(x[i] < prob.lb[i] || x[i] > prob.ub[i]);
-    if (!inside) return -INFINITY;
+    if (!inside_box<D>(x, prob)) return -INFINITY;
     double theta[M::NPARAM];
-#pragma unroll
-    for (int p = 0; p < M::NPARAM; ++p) {
-        double v = prob.theta_nom[p];
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-            if (prob.unc_idx[i] == p) v = x[i];        // Model.run_model :361-369
-        theta[p] = v;
-    }
+    full_theta<M, D>(x, prob, theta);
     typename M::Ctx ctx;
     M::begin(ctx, theta, prob);
-    const double J = sum_of_squares<M, G>(ctx, prob, smem_rec, sub, group_mask);
+    typename M::Seq seq;
+    M::seq_init(ctx, seq, prob);
+    double Ju[M::UNROLL], gdummy[1];
+#pragma unroll
+    for (int u = 0; u < M::UNROLL; ++u) Ju[u] = 0.0;
+    tile_accumulate<M, G, false>(ctx, seq, smem_rec, prob.n_points, sub, Ju, gdummy);
+    double J = 0.0;
+#pragma unroll
+    for (int u = 0; u < M::UNROLL; ++u) J += Ju[u];
+    J = group_sum<G>(J, group_mask) + prob.J_const;
     return (prob.log_prior_const - 0.0) + (-0.5 * J);
 }
 
@@ -173,8 +192,9 @@ __device__ __forceinline__ void draw_philox(uint64_t seed, uint64_t chain, uint6
 }
 
 template <int D>
-__device__ __forceinline__ bool draw_injected(const StreamsDev &s, int64_t c, int64_t &cn, int64_t &cu, double (&z)[D], double &u) {
-    if (cn + D > s.n_normals || cu + 1 > s.n_uniforms) {
+__device__ __forceinline__ bool draw_injected(const StreamsDev &s, int64_t c, int64_t &cn, int64_t &cu, bool want_uniform, double (&z)[D],
+                                              double &u) {
+    if (cn + D > s.n_normals || (want_uniform && cu + 1 > s.n_uniforms)) {
 #pragma unroll
         for (int i = 0; i < D; ++i) z[i] = 0.0;
         u = 1.0;
@@ -183,43 +203,25 @@ __device__ __forceinline__ bool draw_injected(const StreamsDev &s, int64_t c, in
     const double *zn = s.normals + c * s.n_normals + cn;
 #pragma unroll
     for (int i = 0; i < D; ++i) z[i] = zn[i];
-    u = s.uniforms[c * s.n_uniforms + cu];
     cn += D;
-    cu += 1;
-    return true;
-}
-
-// new = cur + scale * R @ z with R UPPER triangular (mha.py:193, :543)
-template <int D>
-__device__ __forceinline__ void propose(const double (&x)[D], const double (&R)[tri_size(D)], const double (&z)[D], double scale,
-                                        double (&y)[D]) {
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-        double s = 0.0;
-#pragma unroll
-        for (int j = i; j < D; ++j) s = fma(R[tri_idx(D, i, j)], z[j], s);
-        y[i] = x[i] + scale * s;
+    if (want_uniform) {
+        u = s.uniforms[c * s.n_uniforms + cu];
+        cu += 1;
     }
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
 // The kernel.
 // ------------------------------------------------------------------------------------------------
-constexpr int MH_BLOCK = 128;
-// registers: cap at 65536/(128*MINB) so that MINB blocks (4*MINB warps) are resident per SM
-template <int D, bool ADAPT>
-__host__ __device__ constexpr int mh_min_blocks() {
-    return (D <= 4) ? 3 : 2;
-}
-
 template <class M, int D, int G, bool ADAPT>
-__global__ void __launch_bounds__(MH_BLOCK, mh_min_blocks<D, ADAPT>()) mh_step_kernel(const __grid_constant__ MhParams p) {
+__global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_constant__ MhParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     double *smem_rec = reinterpret_cast<double *>(smem_raw + 128);
     constexpr int NT = tri_size(D);
 
-    stage_records(smem_rec, bar, p.prob);
+    stage_records(smem_rec, bar, p.prob.records, (uint32_t)p.prob.n_points * (uint32_t)(M::NC * 8));
 
     const int64_t C = p.st.n_chains;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -231,23 +233,13 @@ __global__ void __launch_bounds__(MH_BLOCK, mh_min_blocks<D, ADAPT>()) mh_step_k
     const int lane = threadIdx.x & 31;
     const unsigned group_mask = (G == 1) ? (1u << lane) : (((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(G - 1)));
 
-    // ---- load state
-    double x[D], R[NT], lp;
-    double xav[ADAPT ? D : 1], V[ADAPT ? NT : 1];
+    // ---- chain state kept in registers across the launch
+    double x[D], lp;
 #pragma unroll
     for (int i = 0; i < D; ++i) x[i] = p.st.x[i * C + c];
-#pragma unroll
-    for (int i = 0; i < NT; ++i) R[i] = p.st.R[i * C + c];
     lp = p.st.lp[c];
-    if (ADAPT) {
-#pragma unroll
-        for (int i = 0; i < D; ++i) xav[i] = p.st.xav[i * C + c];
-#pragma unroll
-        for (int i = 0; i < NT; ++i) V[i] = p.st.V[i * C + c];
-    }
     double mean_r = p.st.mean_r[c];
-    int64_t n_rej = p.st.n_rej[c];
-    int64_t n_eval = p.st.n_eval[c];
+    int32_t n_rej = 0, n_eval = 0;              // per-launch increments of the int64 counters
     int32_t status = p.st.status[c];
     const bool injected = p.streams.normals != nullptr;
     int64_t cn = 0, cu = 0;
@@ -256,6 +248,11 @@ __global__ void __launch_bounds__(MH_BLOCK, mh_min_blocks<D, ADAPT>()) mh_step_k
         cu = p.streams.cur_u[c];
     }
     const uint64_t gchain = p.chain_offset + (uint64_t)c;
+    // per-chain adaptive state in global memory (chain-minor): every lane of a group reads and, if live,
+    // writes the same values, so each thread only ever reads back its own stores.
+    double *const gR = p.st.R + c;
+    double *const gV = p.st.V + c;
+    double *const gxav = p.st.xav + c;
 
     for (int64_t s = 0; s < p.n_steps; ++s) {
         const int64_t it = p.it0 + s + 1;
@@ -268,12 +265,23 @@ __global__ void __launch_bounds__(MH_BLOCK, mh_min_blocks<D, ADAPT>()) mh_step_k
         for (int stage = 0; stage < 2; ++stage) {
             double z[D], u;
             if (injected) {
-                if (!draw_injected<D>(p.streams, c, cn, cu, z, u)) status |= ST_STREAM_EXHAUSTED;
+                if (!draw_injected<D>(p.streams, c, cn, cu, true, z, u)) status |= ST_STREAM_EXHAUSTED;
             } else {
                 draw_philox<D>(p.seed, gchain, (uint64_t)it, (uint32_t)stage, z, u);
             }
+            // new = cur + scale * R @ z with R UPPER triangular (mha.py:193, :543)
             double y[D];
-            propose<D>(x, R, z, stage == 0 ? 1.0 : p.gamma_dr, y);          // :193, :543
+            const double scale = (stage == 0) ? 1.0 : p.gamma_dr;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                double sj = 0.0;
+#pragma unroll
+                for (int j = i; j < D; ++j) {
+                    const double rij = ADAPT ? gR[(int64_t)tri_idx(D, i, j) * C] : p.R0[tri_idx(D, i, j)];
+                    sj = fma(rij, z[j], sj);
+                }
+                y[i] = x[i] + scale * sj;
+            }
             const double lpy = log_posterior<M, D, G>(y, p.prob, smem_rec, sub, group_mask);
             n_eval += 1;
             bool accept;
@@ -296,7 +304,8 @@ __global__ void __launch_bounds__(MH_BLOCK, mh_min_blocks<D, ADAPT>()) mh_step_k
                 double M2 = 0.0, M4 = 0.0;
 #pragma unroll
                 for (int i = 0; i < D; ++i) {
-                    const double ir = 1.0 / R[tri_idx(D, i, i)];
+                    const double rii = ADAPT ? gR[(int64_t)tri_idx(D, i, i) * C] : p.R0[tri_idx(D, i, i)];
+                    const double ir = 1.0 / rii;
                     const double iv = ir * ir;
                     const double d1 = y1[i] - y[i];
                     const double d2 = y1[i] - x[i];
@@ -326,13 +335,15 @@ __global__ void __launch_bounds__(MH_BLOCK, mh_min_blocks<D, ADAPT>()) mh_step_k
         // ---- covariance adaptation (mha.py:432-487)
         if (ADAPT) {
             const double fi = (double)it;
+            const bool refresh = (it % p.updating_it == 0);                 // :470
+            double Vc[NT];
             if (!p.am_welford) {
                 // literal Haario/Smith recursion, evaluated in the reference's operation order
                 // without FMA contraction; at it == 1 X_av_i aliases the state.
                 double xa[D], xb[D];
 #pragma unroll
                 for (int i = 0; i < D; ++i) {
-                    xa[i] = (it == 1) ? x[i] : xav[i];
+                    xa[i] = (it == 1) ? x[i] : gxav[(int64_t)i * C];
                     xb[i] = __dadd_rn(x[i], __dmul_rn(fi / (fi + 1.0), __dadd_rn(xa[i], -x[i])));       // :455
                 }
                 const double c1 = (fi - 1.0) / fi, c2 = p.S_d / fi;
@@ -343,40 +354,47 @@ __global__ void __launch_bounds__(MH_BLOCK, mh_min_blocks<D, ADAPT>()) mh_step_k
                         double t = __dadd_rn(__dmul_rn(fi, __dmul_rn(xa[i], xa[j])), -__dmul_rn(fi + 1.0, __dmul_rn(xb[i], xb[j])));
                         t = __dadd_rn(t, __dmul_rn(x[i], x[j]));
                         t = __dadd_rn(t, (i == j) ? p.eps_v : 0.0);
-                        V[tri_idx(D, i, j)] = __dadd_rn(__dmul_rn(c1, V[tri_idx(D, i, j)]), __dmul_rn(c2, t));  // :463
+                        const int64_t o = (int64_t)tri_idx(D, i, j) * C;
+                        const double v = __dadd_rn(__dmul_rn(c1, gV[o]), __dmul_rn(c2, t));             // :463
+                        Vc[tri_idx(D, i, j)] = v;
+                        if (live) gV[o] = v;
                     }
+                if (live) {
 #pragma unroll
-                for (int i = 0; i < D; ++i) xav[i] = xb[i];
+                    for (int i = 0; i < D; ++i) gxav[(int64_t)i * C] = xb[i];
+                }
             } else {
                 // Welford over x_0..x_it: xav = running mean, V = sum of outer products of deviations
                 const double inv_n = 1.0 / (fi + 1.0);
-                double dl[D];
+                const double sc = p.S_d / fi;                               // S_d * M2/(n-1), n = it+1
+                double dl[D], mu[D];
 #pragma unroll
                 for (int i = 0; i < D; ++i) {
-                    dl[i] = x[i] - xav[i];
-                    xav[i] = fma(dl[i], inv_n, xav[i]);
+                    const double m = gxav[(int64_t)i * C];
+                    dl[i] = x[i] - m;
+                    mu[i] = fma(dl[i], inv_n, m);
                 }
 #pragma unroll
                 for (int i = 0; i < D; ++i)
 #pragma unroll
-                    for (int j = i; j < D; ++j) V[tri_idx(D, i, j)] = fma(dl[i], x[j] - xav[j], V[tri_idx(D, i, j)]);
-            }
-            if (it % p.updating_it == 0) {                  // :470, :486-487, :591-595
-                double Vc[NT], Rn[NT];
-                if (!p.am_welford) {
+                    for (int j = i; j < D; ++j) {
+                        const int64_t o = (int64_t)tri_idx(D, i, j) * C;
+                        const double v = fma(dl[i], x[j] - mu[j], gV[o]);
+                        Vc[tri_idx(D, i, j)] = sc * v + ((i == j) ? p.S_d * p.eps_v : 0.0);
+                        if (live) gV[o] = v;
+                    }
+                if (live) {
 #pragma unroll
-                    for (int i = 0; i < NT; ++i) Vc[i] = V[i];
-                } else {
-                    const double sc = p.S_d / fi;           // S_d * M2/(n-1), n = it+1
-#pragma unroll
-                    for (int i = 0; i < D; ++i)
-#pragma unroll
-                        for (int j = i; j < D; ++j)
-                            Vc[tri_idx(D, i, j)] = sc * V[tri_idx(D, i, j)] + ((i == j) ? p.S_d * p.eps_v : 0.0);
+                    for (int i = 0; i < D; ++i) gxav[(int64_t)i * C] = mu[i];
                 }
+            }
+            if (refresh) {                                  // :486-487, :591-595
+                double Rn[NT];
                 if (chol_upper_packed<D>(Vc, Rn)) {
+                    if (live) {
 #pragma unroll
-                    for (int i = 0; i < NT; ++i) R[i] = Rn[i];
+                        for (int i = 0; i < NT; ++i) gR[(int64_t)i * C] = Rn[i];
+                    }
                 } else {
                     status |= ST_NOT_PD;                    // scipy raises LinAlgError here (:487)
                 }
@@ -428,18 +446,10 @@ __global__ void __launch_bounds__(MH_BLOCK, mh_min_blocks<D, ADAPT>()) mh_step_k
     if (writer) {
 #pragma unroll
         for (int i = 0; i < D; ++i) p.st.x[i * C + c] = x[i];
-#pragma unroll
-        for (int i = 0; i < NT; ++i) p.st.R[i * C + c] = R[i];
         p.st.lp[c] = lp;
-        if (ADAPT) {
-#pragma unroll
-            for (int i = 0; i < D; ++i) p.st.xav[i * C + c] = xav[i];
-#pragma unroll
-            for (int i = 0; i < NT; ++i) p.st.V[i * C + c] = V[i];
-        }
         p.st.mean_r[c] = mean_r;
-        p.st.n_rej[c] = n_rej;
-        p.st.n_eval[c] = n_eval;
+        p.st.n_rej[c] += n_rej;
+        p.st.n_eval[c] += n_eval;
         p.st.status[c] = status;
         if (injected) {
             p.streams.cur_n[c] = cn;
@@ -449,15 +459,16 @@ __global__ void __launch_bounds__(MH_BLOCK, mh_min_blocks<D, ADAPT>()) mh_step_k
 }
 
 // ------------------------------------------------------------------------------------------------
-// Initial state: log-posterior of x0 (mha.py:102) and R = upper Cholesky of V0 (:143).
-// Also used for plain evaluation of S parameter vectors (one thread per vector, G = 1).
+// Initial state: log-posterior of x0 (mha.py:102).  Also used for plain evaluation of S parameter
+// vectors (one thread per vector, G = 1).
 // ------------------------------------------------------------------------------------------------
 template <class M, int D>
-__global__ void eval_logpost_kernel(const __grid_constant__ ProblemDev prob, const double *X /*[d][S]*/, int64_t S, double *lp_out) {
+__global__ void __launch_bounds__(256) eval_logpost_kernel(const __grid_constant__ ProblemDev prob, const double *X /*[d][S]*/, int64_t S,
+                                                           double *lp_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     double *smem_rec = reinterpret_cast<double *>(smem_raw + 128);
-    stage_records(smem_rec, bar, prob);
+    stage_records(smem_rec, bar, prob.records, (uint32_t)prob.n_points * (uint32_t)(M::NC * 8));
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= S) return;
     double x[D];
@@ -468,37 +479,26 @@ __global__ void eval_logpost_kernel(const __grid_constant__ ProblemDev prob, con
 
 // Model.run_model for S parameter vectors: f_out[k][s] (point-major, coalesced over samples).
 template <class M, int D>
-__global__ void eval_model_kernel(const __grid_constant__ ProblemDev prob, const double *X /*[d][S]*/, int64_t S, double *f_out) {
+__global__ void __launch_bounds__(256) eval_model_kernel(const __grid_constant__ ProblemDev prob, const double *X /*[d][S]*/, int64_t S,
+                                                         double *f_out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    double *smem_rec = reinterpret_cast<double *>(smem_raw + 128);
-    stage_records(smem_rec, bar, prob);
+    double *smem_raw_rec = reinterpret_cast<double *>(smem_raw + 128);
+    stage_records(smem_raw_rec, bar, prob.raw, (uint32_t)prob.n_points * (uint32_t)(M::NCR * 8));
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= S) return;
-    double theta[M::NPARAM];
+    double x[D], theta[M::NPARAM];
 #pragma unroll
-    for (int q = 0; q < M::NPARAM; ++q) {
-        double v = prob.theta_nom[q];
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-            if (prob.unc_idx[i] == q) v = X[i * S + t];
-        theta[q] = v;
-    }
+    for (int i = 0; i < D; ++i) x[i] = X[i * S + t];
+    full_theta<M, D>(x, prob, theta);
     typename M::Ctx ctx;
     M::begin(ctx, theta, prob);
     typename M::Seq seq;
     M::seq_init(ctx, seq, prob);
-    constexpr int NC0 = even_up(M::ND + 2);
     for (int k = 0; k < prob.n_points; ++k) {
-        const double2 *r2 = reinterpret_cast<const double2 *>(smem_rec + (size_t)k * NC0);
-        double rec[NC0];
-#pragma unroll
-        for (int j = 0; j < NC0 / 2; ++j) {
-            double2 v = r2[j];
-            rec[2 * j] = v.x;
-            rec[2 * j + 1] = v.y;
-        }
-        f_out[(int64_t)k * S + t] = M::eval(ctx, seq, rec);
+        double raw[M::NCR];
+        load_record<M::NCR>(smem_raw_rec, k, raw);
+        f_out[(int64_t)k * S + t] = M::value(ctx, seq, raw);
     }
 }
 

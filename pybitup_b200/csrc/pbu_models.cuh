@@ -1,27 +1,37 @@
 // Registered device forward models (replace user bi.Model.fun_x, bayesian_inference.py:306-308,:371).
 //
+// Two record streams describe the experimental design (built on the host, pbu_engine.cu::build_records):
+//   likelihood records  [N][NC]   what the Gaussian sum of squares needs per point, pre-scaled by the
+//                                 weight w_k = sqrt(n_runs)/(std_y,k*gamma) so that the weighted residual
+//                                 t_k = w_k (ybar_k - f_k) costs ONE fused multiply-add after the model value;
+//   raw records         [N][NCR]  the unscaled design, for Model.run_model / propagation.
+//
 // A model is a struct with
 //   NPARAM      length of the full parameter vector theta
-//   ND          design columns at the head of each point record
-//   SEQUENTIAL  true if point k depends on point k-1 (ODE): no splitting of the sum over lanes
+//   NC, NCR     doubles per likelihood / raw record (even, records are read as double2)
+//   SEQUENTIAL  true if point k depends on point k-1 (ODE): the sum over points is not split over lanes
+//   UNROLL      points a thread keeps in flight (independent FP64 dependency chains)
 //   Ctx         per-evaluation constants derived from theta        (begin)
 //   Seq         running state across points                         (seq_init)
-//   eval(ctx, seq, rec) -> f_k   with rec = the point record in registers
-// and, when HAS_GRAD, grad(ctx, rec, j) = d f_k / d theta_j.
-//
-//   UNROLL      points a thread keeps in flight (independent FP64 dependency chains)
-// Record layout: [design (ND) | w = sqrt(n_runs)/(std_y*gamma) | ybar | pad to even].
+//   resid_batch<U>(ctx, seq, rec[U][NC], t[U])   weighted residuals of U consecutive points
+//   value(ctx, seq, raw)                         f_k from a raw record
+// and, when HAS_GRAD,
+//   grad_acc(ctx, rec, t, g[NPARAM])             g_j += t_k * w_k * d f_k / d theta_j
+// which is the summand of Likelihood.compute_grad_log_value (bayesian_inference.py:573-623).
 #pragma once
 #include "pbu_common.cuh"
 
 namespace pbu {
 
 // ------------------------------------------------------------------------------------------------
-// LINEAR: f_k = sum_j Phi[k][j] * theta[j], accumulated j = 0..P-1 (oracle/cpu_models.py::linear_design)
+// LINEAR: f_k = sum_j Phi[k][j] * theta[j]  (oracle/cpu_models.py::linear_design)
+//   likelihood record [w*Phi_0 .. w*Phi_{P-1} | w*y | pad]:  t = w*y - sum_j (w*Phi_j) theta_j, P FMAs
+//   raw record        [Phi_0 .. Phi_{P-1} | pad]
 template <int P>
 struct LinearModel {
     static constexpr int NPARAM = P;
-    static constexpr int ND = P;
+    static constexpr int NC = (P + 2) & ~1;
+    static constexpr int NCR = (P + 1) & ~1;
     static constexpr bool SEQUENTIAL = false;
     static constexpr bool HAS_GRAD = true;
     static constexpr int ID = PBU_MODEL_LINEAR;
@@ -35,32 +45,36 @@ struct LinearModel {
         for (int j = 0; j < P; ++j) c.th[j] = theta[j];
     }
     __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const ProblemDev &) {}
-    __device__ __forceinline__ static double eval(const Ctx &c, Seq &, const double *rec) {
-        double f = rec[0] * c.th[0];
+    // written stage-by-stage across the U points so that the U dependency chains interleave in program order
+    template <int U>
+    __device__ __forceinline__ static void resid_batch(const Ctx &c, Seq &, const double (&rec)[U][NC], double (&t)[U]) {
 #pragma unroll
-        for (int j = 1; j < P; ++j) f = fma(rec[j], c.th[j], f);
+        for (int u = 0; u < U; ++u) t[u] = rec[u][P];
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+#pragma unroll
+            for (int u = 0; u < U; ++u) t[u] = fma(-rec[u][j], c.th[j], t[u]);
+    }
+    __device__ __forceinline__ static double value(const Ctx &c, Seq &, const double *raw) {
+        double f = raw[0] * c.th[0];
+#pragma unroll
+        for (int j = 1; j < P; ++j) f = fma(raw[j], c.th[j], f);
         return f;
     }
-    // U points at once, written stage-by-stage across the points so that the U dependency chains are
-    // interleaved in program order (ptxas keeps that order; written point-by-point it serialises them)
-    template <int U, int NC>
-    __device__ __forceinline__ static void eval_batch(const Ctx &c, Seq &, const double (&rec)[U][NC], double (&f)[U]) {
+    __device__ __forceinline__ static void grad_acc(const Ctx &, const double (&rec)[NC], double t, double (&g)[P]) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) f[u] = rec[u][0] * c.th[0];
-#pragma unroll
-        for (int j = 1; j < P; ++j)
-#pragma unroll
-            for (int u = 0; u < U; ++u) f[u] = fma(rec[u][j], c.th[j], f[u]);
+        for (int j = 0; j < P; ++j) g[j] = fma(t, rec[j], g[j]);
     }
-    __device__ __forceinline__ static double grad(const Ctx &, const double *rec, int j) { return rec[j]; }
 };
 
 // ------------------------------------------------------------------------------------------------
 // POLY: Horner from the top coefficient (oracle/cpu_models.py::poly_horner)
+//   likelihood record [x | w | w*y | pad];  raw record [x | pad]
 template <int P>
 struct PolyModel {
     static constexpr int NPARAM = P;
-    static constexpr int ND = 1;
+    static constexpr int NC = 4;
+    static constexpr int NCR = 2;
     static constexpr bool SEQUENTIAL = false;
     static constexpr bool HAS_GRAD = true;
     static constexpr int ID = PBU_MODEL_POLY;
@@ -74,37 +88,45 @@ struct PolyModel {
         for (int j = 0; j < P; ++j) c.th[j] = theta[j];
     }
     __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const ProblemDev &) {}
-    __device__ __forceinline__ static double eval(const Ctx &c, Seq &, const double *rec) {
-        const double x = rec[0];
-        double f = c.th[P - 1];
-#pragma unroll
-        for (int j = P - 2; j >= 0; --j) f = fma(f, x, c.th[j]);
-        return f;
-    }
-    template <int U, int NC>
-    __device__ __forceinline__ static void eval_batch(const Ctx &c, Seq &, const double (&rec)[U][NC], double (&f)[U]) {
+    template <int U>
+    __device__ __forceinline__ static void resid_batch(const Ctx &c, Seq &, const double (&rec)[U][NC], double (&t)[U]) {
+        double f[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) f[u] = c.th[P - 1];
 #pragma unroll
         for (int j = P - 2; j >= 0; --j)
 #pragma unroll
             for (int u = 0; u < U; ++u) f[u] = fma(f[u], rec[u][0], c.th[j]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) t[u] = fma(-f[u], rec[u][1], rec[u][2]);
     }
-    __device__ __forceinline__ static double grad(const Ctx &, const double *rec, int j) {
-        double p = 1.0;
-        for (int i = 0; i < j; ++i) p *= rec[0];
-        return p;
+    __device__ __forceinline__ static double value(const Ctx &c, Seq &, const double *raw) {
+        const double x = raw[0];
+        double f = c.th[P - 1];
+#pragma unroll
+        for (int j = P - 2; j >= 0; --j) f = fma(f, x, c.th[j]);
+        return f;
+    }
+    __device__ __forceinline__ static void grad_acc(const Ctx &, const double (&rec)[NC], double t, double (&g)[P]) {
+        double s = t * rec[1];          // t_k w_k x^j
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            g[j] += s;
+            s *= rec[0];
+        }
     }
 };
 
 // ------------------------------------------------------------------------------------------------
 // ARRHENIUS: d(alpha)/dT = (A/beta) exp(-E/(R T)) (1-alpha)^n, RK4 with step dT, output 1 - F*alpha
-// at the end of every step (oracle/cpu_models.py::arrhenius_rk4).  Record design columns:
-// [1/T_mid, 1/T_end] of the step; consts = {T0, dT, beta}.  The rate at the start of a step is the
-// rate at the end of the previous one, so each step costs two exp and four pow.
+// at the end of every step (oracle/cpu_models.py::arrhenius_rk4).  consts = {T0, dT, beta}.
+//   likelihood record [1/T_mid | 1/T_end | w | w*y];  raw record [1/T_mid | 1/T_end]
+// The rate at the start of a step is the rate at the end of the previous one, so each step costs two
+// exp and four pow.
 struct ArrheniusModel {
     static constexpr int NPARAM = 4;
-    static constexpr int ND = 2;
+    static constexpr int NC = 4;
+    static constexpr int NCR = 2;
     static constexpr bool SEQUENTIAL = true;
     static constexpr bool HAS_GRAD = false;
     static constexpr int ID = PBU_MODEL_ARRHENIUS;
@@ -129,9 +151,9 @@ struct ArrheniusModel {
         s.g0 = c.g_start;
     }
     __device__ __forceinline__ static double pw(double u, double n) { return (u > 0.0) ? pow(u, n) : 0.0; }
-    __device__ __forceinline__ static double eval(const Ctx &c, Seq &s, const double *rec) {
-        const double gm = exp(c.c0 - c.ER * rec[0]);
-        const double g1 = exp(c.c0 - c.ER * rec[1]);
+    __device__ __forceinline__ static double step(const Ctx &c, Seq &s, double inv_mid, double inv_end) {
+        const double gm = exp(c.c0 - c.ER * inv_mid);
+        const double g1 = exp(c.c0 - c.ER * inv_end);
         const double a = s.alpha;
         const double k1 = c.h * s.g0 * pw(1.0 - a, c.n);
         const double k2 = c.h * gm * pw(1.0 - (a + 0.5 * k1), c.n);
@@ -141,20 +163,23 @@ struct ArrheniusModel {
         s.g0 = g1;
         return 1.0 - c.F * s.alpha;
     }
-    template <int U, int NC>
-    __device__ __forceinline__ static void eval_batch(const Ctx &c, Seq &s, const double (&rec)[U][NC], double (&f)[U]) {
+    template <int U>
+    __device__ __forceinline__ static void resid_batch(const Ctx &c, Seq &s, const double (&rec)[U][NC], double (&t)[U]) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) f[u] = eval(c, s, rec[u]);
+        for (int u = 0; u < U; ++u) t[u] = fma(-step(c, s, rec[u][0], rec[u][1]), rec[u][2], rec[u][3]);
     }
-    __device__ __forceinline__ static double grad(const Ctx &, const double *, int) { return 0.0; }
+    __device__ __forceinline__ static double value(const Ctx &c, Seq &s, const double *raw) { return step(c, s, raw[0], raw[1]); }
+    __device__ __forceinline__ static void grad_acc(const Ctx &, const double (&)[NC], double, double (&)[4]) {}
 };
 
 // ------------------------------------------------------------------------------------------------
 // HEAT: steady fin temperature, the reference's own test model
 // (pybitup/test/test_pce/heat_conduction.py:27-41); theta = (a,b,k,T_amb,phi,h), consts = {L}.
+//   likelihood record [x | w | w*y | pad];  raw record [x | pad]
 struct HeatModel {
     static constexpr int NPARAM = 6;
-    static constexpr int ND = 1;
+    static constexpr int NC = 4;
+    static constexpr int NCR = 2;
     static constexpr bool SEQUENTIAL = false;
     static constexpr bool HAS_GRAD = false;
     static constexpr int ID = PBU_MODEL_HEAT;
@@ -174,16 +199,16 @@ struct HeatModel {
         c.T_amb = th[3];
     }
     __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const ProblemDev &) {}
-    __device__ __forceinline__ static double eval(const Ctx &c, Seq &, const double *rec) {
-        const double x = rec[0];
+    __device__ __forceinline__ static double value(const Ctx &c, Seq &, const double *raw) {
+        const double x = raw[0];
         return c.c1 * exp(-c.gamma * x) + c.c2 * exp(c.gamma * x) + c.T_amb;
     }
-    template <int U, int NC>
-    __device__ __forceinline__ static void eval_batch(const Ctx &c, Seq &s, const double (&rec)[U][NC], double (&f)[U]) {
+    template <int U>
+    __device__ __forceinline__ static void resid_batch(const Ctx &c, Seq &s, const double (&rec)[U][NC], double (&t)[U]) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) f[u] = eval(c, s, rec[u]);
+        for (int u = 0; u < U; ++u) t[u] = fma(-value(c, s, rec[u]), rec[u][1], rec[u][2]);
     }
-    __device__ __forceinline__ static double grad(const Ctx &, const double *, int) { return 0.0; }
+    __device__ __forceinline__ static void grad_acc(const Ctx &, const double (&)[NC], double, double (&)[6]) {}
 };
 
 }  // namespace pbu

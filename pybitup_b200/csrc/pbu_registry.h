@@ -10,6 +10,7 @@ struct MhKernelEntry {
 };
 struct EvalKernelEntry {
     int model, n_param, n_unc, sequential;
+    int nc, ncr;              // doubles per likelihood / raw record (Model::NC, Model::NCR)
     const void *eval_lp;      // __global__ void (*)(const ProblemDev, const double*, int64_t, double*)
     const void *eval_model;   // same signature
 };

@@ -214,6 +214,12 @@ class ChainEngine:
     def iteration(self):
         return int(capi.lib.pbu_engine_iteration(self._h))
 
+    def launch_geometry(self):
+        """(lanes per chain, threads per block, blocks, dynamic shared memory bytes) of the step kernel."""
+        a, b, g, m = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+        capi.check(capi.lib.pbu_engine_get_launch(self._h, C.byref(a), C.byref(b), C.byref(g), C.byref(m)))
+        return dict(lanes=a.value, block=b.value, grid=g.value, smem_bytes=m.value)
+
     # -- the hot loop -------------------------------------------------------------------------
     def run(self, n_steps, thin=1, keep_samples=True, keep_lp=False, trace=False, out=None):
         """Advance all chains by n_steps iterations in one kernel launch (asynchronous)."""

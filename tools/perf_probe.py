@@ -4,6 +4,8 @@ import sys
 import os
 import time
 
+LAST_GEOM = None
+
 import numpy as np
 import torch
 
@@ -26,6 +28,8 @@ def time_run(p, algo, C, steps, lanes=0, block=0, reps=3, **kw):
         e1.record()
         e1.synchronize()
         best = min(best, e0.elapsed_time(e1))
+    global LAST_GEOM
+    LAST_GEOM = eng.launch_geometry()
     ctr = eng.counters()
     acc = 1.0 - ctr["n_rejected"].mean() / eng.iteration
     evals = ctr["n_eval"].mean() / eng.iteration
@@ -40,12 +44,11 @@ def main():
     if "cubic" in which:
         p = synthetic.cubic_problem()
         flops = 1000 * 10 + 20 + 140
-        for lanes in (1, 2, 8):
-            for block in (64, 128):
-                ms, acc, ev = time_run(p, "AMH", 65536, 100, lanes, block, updating_it=10, eps_v=1e-10)
-                rate = 65536 * 100 / (ms * 1e-3)
-                print(json.dumps({"cfg": "cubic_am_65536", "lanes": lanes, "block": block, "ms": ms, "steps_per_s": rate,
-                                  "tflops_alg": rate * flops / 1e12, "frac": rate * flops / 1e12 / tf, "acc": acc}))
+        for lanes, block in ((0, 0), (1, 448), (1, 224), (1, 128), (1, 512), (1, 384), (2, 448), (2, 512), (2, 128), (8, 512)):
+            ms, acc, ev = time_run(p, "AMH", 65536, 100, lanes, block, updating_it=10, eps_v=1e-10)
+            rate = 65536 * 100 / (ms * 1e-3)
+            print(json.dumps({"cfg": "cubic_am_65536", "lanes": lanes, "block": block, "geom": LAST_GEOM, "ms": ms, "steps_per_s": rate,
+                              "tflops_alg": rate * flops / 1e12, "frac": rate * flops / 1e12 / tf, "acc": acc}))
         for algo in ("RWMH", "DR", "DRAM"):
             ms, acc, ev = time_run(p, algo, 65536, 100, 0, 0, updating_it=10, eps_v=1e-10, gamma_dr=0.2)
             rate = 65536 * 100 / (ms * 1e-3)
@@ -54,15 +57,15 @@ def main():
     if "linear" in which:
         p = synthetic.linear_problem()
         for C in (1, 148 * 128, 1 << 20):
-            for lanes in ((1, 8) if C == 1 else (1, 2)):
+            for lanes in ((0, 1, 8) if C == 1 else (0, 1, 2)):
                 steps = 20000 if C == 1 else 200
                 ms, acc, ev = time_run(p, "RWMH", C, steps, lanes, 0)
                 rate = C * steps / (ms * 1e-3)
-                print(json.dumps({"cfg": "linear_rwmh", "C": C, "lanes": lanes, "ms": ms, "steps_per_s": rate,
+                print(json.dumps({"cfg": "linear_rwmh", "C": C, "lanes": lanes, "geom": LAST_GEOM, "ms": ms, "steps_per_s": rate,
                                   "ns_per_step": ms * 1e6 / steps, "tflops_alg": rate * 512 / 1e12, "acc": acc}))
     if "arrhenius" in which:
         p = synthetic.arrhenius_problem()
-        for block in (64, 128):
+        for block in (0, 128, 256, 512):
             ms, acc, ev = time_run(p, "DRAM", 262144, 4, 1, block, updating_it=10, eps_v=1e-10, gamma_dr=0.2, reps=2)
             rate = 262144 * 4 / (ms * 1e-3)
             print(json.dumps({"cfg": "arrhenius_dram_262144", "block": block, "ms": ms, "steps_per_s": rate,
