@@ -101,6 +101,8 @@ typedef struct {
                                  1: a NaN acceptance ratio rejects                                */
     int32_t lanes_per_chain;  /* 0 auto; 1,2,4,8: lanes of a warp that share one chain's data sum */
     int32_t block_threads;    /* 0 auto                                                           */
+    int32_t chains_per_thread;/* 0 auto; 1,2: chains that share every record a thread reads       */
+    int32_t pad0;
     uint64_t seed;            /* Philox key                                                       */
     uint64_t chain_offset;    /* global index of this engine's first chain (multi-GPU sharding)   */
 } pbu_sampler_cfg;
@@ -162,8 +164,9 @@ int pbu_engine_get_counters(pbu_engine *e, int64_t *n_rejected /*[C]*/, double *
 int pbu_engine_get_proposal(pbu_engine *e, double *R_host, double *V_host, double *xav_host);
 int64_t pbu_engine_iteration(const pbu_engine *e);
 /* launch geometry the engine planned for the step kernel: lanes of a warp per chain, threads per block,
- * blocks, dynamic shared memory bytes per block (diagnostics; no reference counterpart). */
-int pbu_engine_get_launch(const pbu_engine *e, int32_t *lanes, int32_t *block, int32_t *grid, int64_t *smem_bytes);
+ * chains per thread, blocks, dynamic shared memory bytes per block (diagnostics; no reference counterpart). */
+int pbu_engine_get_launch(const pbu_engine *e, int32_t *lanes, int32_t *chains_per_thread, int32_t *block, int32_t *grid,
+                          int64_t *smem_bytes);
 
 /* ---- evaluation only: BayesianPosterior.compute_log_value (bayesian_inference.py:44-64) and
  *      Model.run_model (:338-371) for S parameter vectors -------------------------------------- */

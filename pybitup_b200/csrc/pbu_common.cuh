@@ -68,7 +68,7 @@ struct MhParams {
     int64_t it0;              // iterations already done (global counter, 0 at start)
     int64_t n_steps;
     int64_t thin;
-    int64_t keep0;            // number of kept rows before this launch (for absolute thinning phase)
+    int64_t n_groups;         // thread groups in the grid; group g owns chains g, g + n_groups, ... (Q per group)
     uint64_t seed;
     uint64_t chain_offset;
     double eps_v;

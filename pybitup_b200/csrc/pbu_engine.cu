@@ -46,6 +46,7 @@ struct pbu_engine {
     const MhKernelEntry *mh = nullptr;
     const EvalKernelEntry *ev = nullptr;
     int lanes = 1;
+    int q = 1;                    // chains per thread
     int block = 128;
     int grid = 1;
     size_t smem_bytes = 0;        // step / log-posterior kernels: barrier + likelihood records
@@ -108,7 +109,8 @@ extern "C" __attribute__((visibility("default"))) int pbu_list_kernels(char *buf
     int n = 0;
     for (const MhKernelEntry *t = pbu_mh_kernels(&n); t && s.size() < 1u << 20 && n > 0; --n, ++t) {
         char line[128];
-        snprintf(line, sizeof line, "mh model=%d P=%d d=%d lanes=%d adapt=%d\n", t->model, t->n_param, t->n_unc, t->lanes, t->adapt);
+        snprintf(line, sizeof line, "mh model=%d P=%d d=%d lanes=%d chains_per_thread=%d algo=%d\n", t->model, t->n_param, t->n_unc,
+                 t->lanes, t->chains_per_thread, t->algo);
         s += line;
     }
     int total = 0;
@@ -120,11 +122,13 @@ extern "C" __attribute__((visibility("default"))) int pbu_list_kernels(char *buf
     return total;
 }
 
-static const MhKernelEntry *find_mh(int model, int P, int d, int lanes, int adapt) {
+static const MhKernelEntry *find_mh(int model, int P, int d, int lanes, int q, int algo) {
     int n = 0;
     const MhKernelEntry *t = pbu_mh_kernels(&n);
     for (int i = 0; i < n; ++i)
-        if (t[i].model == model && t[i].n_param == P && t[i].n_unc == d && t[i].lanes == lanes && t[i].adapt == adapt) return &t[i];
+        if (t[i].model == model && t[i].n_param == P && t[i].n_unc == d && t[i].lanes == lanes && t[i].chains_per_thread == q &&
+            t[i].algo == algo)
+            return &t[i];
     return nullptr;
 }
 static const EvalKernelEntry *find_eval(int model, int P, int d) {
@@ -191,21 +195,39 @@ static void build_records(const pbu_problem *pr, int nc, int ncr, std::vector<do
 // thread costs N/G point evaluations plus a fixed per-iteration part; with fewer than WSAT resident
 // warps the FP64 pipe is latency- rather than throughput-bound.
 // ------------------------------------------------------------------------------------------------
-static int plan_launch(pbu_engine *e, int model, bool sequential, bool adapt, int want_lanes, int want_block) {
+// Relative FP64 throughput of the data loop against resident warps per SM, measured with tools/ubench
+// (cubic Horner loop fed by broadcast shared-memory loads, U = 4 points in flight) for one and two chains
+// per thread: two chains per thread reuse every loaded record and every operand-cache entry twice.
+static double loop_efficiency(int q, double warps) {
+    static const double w1[] = {0, 4, 8, 12, 16, 24, 32}, e1[] = {0.0, 0.19, 0.38, 0.54, 0.67, 0.83, 0.86};
+    static const double w2[] = {0, 4, 8, 12, 16, 24, 32}, e2[] = {0.0, 0.74, 0.90, 0.99, 1.0, 1.0, 1.0};
+    const double *w = (q >= 2) ? w2 : w1, *e = (q >= 2) ? e2 : e1;
+    if (warps >= 32) return e[6];
+    for (int i = 1; i < 7; ++i)
+        if (warps <= w[i]) return e[i - 1] + (e[i] - e[i - 1]) * (warps - w[i - 1]) / (w[i] - w[i - 1]);
+    return e[6];
+}
+
+static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int want_lanes, int want_q, int want_block) {
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, e->device);
-    const double WSAT = 8.0;
     const double N = (double)e->prob.n_points;
-    const double S0 = 30.0 + 6.0 * e->d;
-    const int lane_cand[3] = {1, 2, 8};
+    const double S0 = 60.0 + 15.0 * e->d;           // per-iteration scalar part (RNG, proposal, accept, adaptation), in DFMA-equivalents
+    const int cand[5][2] = {{1, 1}, {1, 2}, {2, 2}, {4, 2}, {8, 1}};     // (lanes per chain, chains per thread)
     double best = 1e300;
     bool found = false;
-    for (int g : lane_cand) {
+    for (const auto &gq : cand) {
+        const int g = gq[0], q = gq[1];
         if (want_lanes > 0 && g != want_lanes) continue;
+        if (want_q > 0 && q != want_q) continue;
         if (sequential && g != 1) continue;
-        const MhKernelEntry *k = find_mh(model, e->P, e->d, g, adapt ? 1 : 0);
+        // delayed rejection: the second stage runs for a thread when ANY of its chains was rejected, so pairing
+        // chains wastes evaluations; one chain per thread unless asked otherwise
+        if ((algo == PBU_ALGO_DR || algo == PBU_ALGO_DRAM) && q != 1 && want_q <= 0) continue;
+        const MhKernelEntry *k = find_mh(model, e->P, e->d, g, q, algo);
         if (!k) continue;
         CUDA_TRY(cudaFuncSetAttribute(k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+        const int64_t groups_needed = (e->C + q - 1) / q;
         for (int B = MH_MAX_BLOCK; B >= 32; B -= 32) {
             if (want_block > 0 && B != want_block) continue;
             int occ = 0;
@@ -213,16 +235,16 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, bool adapt, in
                 cudaGetLastError();
                 continue;
             }
-            const double blocks = std::ceil((double)e->C * g / B);
-            const double per_sm = std::ceil(blocks / nsm);
-            const double conc = std::min(per_sm, (double)occ);
-            const double warps = conc * B / 32.0;
-            const double work = (sequential ? N : std::ceil(N / g)) + S0;
-            const double t = per_sm * B * work * std::max(1.0, WSAT / warps);
+            const double blocks = std::ceil((double)groups_needed * g / B);
+            const double per_sm = std::ceil(blocks / nsm);          // blocks the busiest SM runs, `occ` at a time
+            const double warps = std::min(per_sm, (double)occ) * B / 32.0;
+            const double work = q * ((sequential ? N : std::ceil(N / g)) * e->ev->ops + S0);
+            const double t = per_sm * B * work / loop_efficiency(q, warps);
             if (t < best * (1.0 - 1e-3)) {
                 best = t;
                 e->mh = k;
                 e->lanes = g;
+                e->q = q;
                 e->block = B;
                 e->grid = (int)blocks;
                 found = true;
@@ -230,8 +252,8 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, bool adapt, in
         }
     }
     if (!found)
-        return fail(PBU_ERR_UNSUPPORTED, "no MH kernel variant fits model=%d P=%d d=%d lanes=%d block=%d adapt=%d (smem %zu B)", model, e->P,
-                    e->d, want_lanes, want_block, (int)adapt, e->smem_bytes);
+        return fail(PBU_ERR_UNSUPPORTED, "no MH kernel variant fits model=%d P=%d d=%d lanes=%d chains_per_thread=%d block=%d algo=%d (smem %zu B)",
+                    model, e->P, e->d, want_lanes, want_q, want_block, algo, e->smem_bytes);
     return PBU_OK;
 }
 
@@ -254,6 +276,10 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
         return fail(PBU_ERR_INVALID, "model %d needs %d design column(s), got %d", pr->model, nd, pr->n_design_cols);
     for (int i = 0; i < pr->n_unc; ++i)
         if (pr->unc_idx[i] < 0 || pr->unc_idx[i] >= pr->n_param) return fail(PBU_ERR_INVALID, "unc_idx[%d] out of range", i);
+    if (pr->n_unc == pr->n_param)
+        // all parameters uncertain: the reference aliases param = var_param (bayesian_inference.py:368-369), i.e. identity order
+        for (int i = 0; i < pr->n_unc; ++i)
+            if (pr->unc_idx[i] != i) return fail(PBU_ERR_INVALID, "with every parameter uncertain unc_idx must be 0..d-1 (Model.run_model aliases param = var_param)");
     const bool adapt = cfg->algo == PBU_ALGO_AM || cfg->algo == PBU_ALGO_DRAM;
     if (adapt && cfg->updating_it < 1) return fail(PBU_ERR_INVALID, "updating_it must be >= 1");
 
@@ -323,7 +349,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
     pd.raw = e->d_raw;
 
     // ---- launch geometry
-    if ((rc = plan_launch(e, pr->model, ev->sequential != 0, adapt, cfg->lanes_per_chain, cfg->block_threads)) != PBU_OK) {
+    if ((rc = plan_launch(e, pr->model, ev->sequential != 0, cfg->algo, cfg->lanes_per_chain, cfg->chains_per_thread, cfg->block_threads)) != PBU_OK) {
         pbu_engine_destroy(e);
         return rc;
     }
@@ -458,9 +484,11 @@ extern "C" __attribute__((visibility("default"))) int64_t pbu_engine_n_keep(cons
 
 extern "C" __attribute__((visibility("default"))) int64_t pbu_engine_iteration(const pbu_engine *e) { return e ? e->iteration : -1; }
 
-extern "C" __attribute__((visibility("default"))) int pbu_engine_get_launch(const pbu_engine *e, int32_t *lanes, int32_t *block, int32_t *grid, int64_t *smem_bytes) {
+extern "C" __attribute__((visibility("default"))) int pbu_engine_get_launch(const pbu_engine *e, int32_t *lanes, int32_t *chains_per_thread, int32_t *block, int32_t *grid,
+                                                                                  int64_t *smem_bytes) {
     if (!e) return fail(PBU_ERR_INVALID, "null engine");
     if (lanes) *lanes = e->lanes;
+    if (chains_per_thread) *chains_per_thread = e->q;
     if (block) *block = e->block;
     if (grid) *grid = e->grid;
     if (smem_bytes) *smem_bytes = (int64_t)e->smem_bytes;
@@ -492,6 +520,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine 
     p.am_welford = e->cfg.am_welford;
     p.nan_rejects = e->cfg.nan_rejects;
     p.resident = 1;
+    p.n_groups = (int64_t)e->grid * e->block / e->lanes;
     for (size_t i = 0; i < e->R0.size(); ++i) p.R0[i] = e->R0[i];
     void *args[] = {(void *)&p};
     CUDA_TRY(cudaLaunchKernel(e->mh->fn, dim3((unsigned)e->grid), dim3(e->block), args, e->smem_bytes, e->stream));

@@ -3,15 +3,17 @@
 #include "pbu_mh_kernel.cuh"
 #include "pbu_registry.h"
 
-#define PBU_MH(MODEL, P, D, G, A) \
-    { MODEL::ID, P, D, G, A, (const void *)&pbu::mh_step_kernel<MODEL, D, G, (A != 0)> }
-// all lane counts x {fixed, adaptive}
+#define PBU_MH(MODEL, P, D, G, Q, A) \
+    { MODEL::ID, P, D, G, Q, A, (const void *)&pbu::mh_step_kernel<MODEL, D, G, A, Q> }
+#define PBU_MH_ALGOS(MODEL, P, D, G, Q) \
+    PBU_MH(MODEL, P, D, G, Q, 0), PBU_MH(MODEL, P, D, G, Q, 1), PBU_MH(MODEL, P, D, G, Q, 2), PBU_MH(MODEL, P, D, G, Q, 3)
+// data-parallel models, (lanes per chain, chains per thread): (1,1) (1,2) (2,2) (4,2) and (8,1) for very few chains
 #define PBU_MH_ALL(MODEL, P, D)                                                                                  \
-    PBU_MH(MODEL, P, D, 1, 0), PBU_MH(MODEL, P, D, 1, 1), PBU_MH(MODEL, P, D, 2, 0), PBU_MH(MODEL, P, D, 2, 1),  \
-        PBU_MH(MODEL, P, D, 8, 0), PBU_MH(MODEL, P, D, 8, 1)
-#define PBU_MH_SEQ(MODEL, P, D) PBU_MH(MODEL, P, D, 1, 0), PBU_MH(MODEL, P, D, 1, 1)
+    PBU_MH_ALGOS(MODEL, P, D, 1, 1), PBU_MH_ALGOS(MODEL, P, D, 1, 2), PBU_MH_ALGOS(MODEL, P, D, 2, 2),           \
+        PBU_MH_ALGOS(MODEL, P, D, 4, 2), PBU_MH_ALGOS(MODEL, P, D, 8, 1)
+#define PBU_MH_SEQ(MODEL, P, D) PBU_MH_ALGOS(MODEL, P, D, 1, 1)
 #define PBU_EVAL(MODEL, P, D)                                                                 \
-    { MODEL::ID, P, D, MODEL::SEQUENTIAL ? 1 : 0, MODEL::NC, MODEL::NCR, (const void *)&pbu::eval_logpost_kernel<MODEL, D>, \
+    { MODEL::ID, P, D, MODEL::SEQUENTIAL ? 1 : 0, MODEL::NC, MODEL::NCR, MODEL::OPS, MODEL::WF, (const void *)&pbu::eval_logpost_kernel<MODEL, D>, \
       (const void *)&pbu::eval_model_kernel<MODEL, D> }
 
 #define PBU_DEFINE_SLICE(name, MH_LIST, EVAL_LIST)                                   \

@@ -64,47 +64,61 @@ __device__ __forceinline__ void load_record(const double *smem_rec, int k, doubl
 // ------------------------------------------------------------------------------------------------
 // Gaussian sum of squares J(theta) = sum_runs sum_k ((y_run,k - f_k)/(std_y,k gamma))^2 over the records of
 // one shared-memory tile (Likelihood.arg_gauss_likelihood, bayesian_inference.py:495-542), and, when
-// GRAD, the gradient sum of Likelihood.compute_grad_log_value (:573-623).  Several experimental runs
-// are folded on the host with the exact identity
+// GRAD, the gradient sum of Likelihood.compute_grad_log_value (:573-623), for the Q chains a thread
+// owns: every record read from shared memory feeds Q chains, which divides the shared-memory
+// wavefronts per FP64 operation by Q (a broadcast LDS still costs one wavefront per 8 bytes per
+// lane, and that, not the bank bandwidth, is what binds a one-chain-per-thread loop).
+// Several experimental runs are folded on the host with the exact identity
 //   sum_r (y_r - f)^2 = n_r (ybar - f)^2 + sum_r (y_r - ybar)^2
 // so a record carries w = sqrt(n_r)/(std_y gamma) and w*ybar, and the second term is the constant
 // prob.J_const: the device loop costs the same whatever n_runs is.
-// Ju[U] are U independent partial sums (one per point in flight).
+// J[Q][U] are independent partial sums (one per chain and point in flight).
 // ------------------------------------------------------------------------------------------------
-template <class M, int G, bool GRAD>
-__device__ __forceinline__ void tile_accumulate(const typename M::Ctx &ctx, typename M::Seq &seq, const double *tile, int n, int sub,
-                                                double (&Ju)[M::UNROLL], double (&g)[GRAD ? M::NPARAM : 1]) {
+template <class M, int G, int Q, int U, bool GRAD>
+__device__ __forceinline__ void tile_accumulate(const typename M::Ctx (&ctx)[Q], typename M::Seq (&seq)[Q], const double *tile, int n,
+                                                int sub, double (&J)[Q][U], double (&g)[Q][GRAD ? M::NPARAM : 1]) {
     constexpr int NC = M::NC;
-    constexpr int U = M::UNROLL;
     if (M::SEQUENTIAL) {
         for (int k = 0; k < n; ++k) {
-            double rec[1][NC], t[1];
+            double rec[1][NC];
             load_record<NC>(tile, k, rec[0]);
-            M::template resid_batch<1>(ctx, seq, rec, t);
-            Ju[0] = fma(t[0], t[0], Ju[0]);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                double t[1];
+                M::template resid_batch<1>(ctx[q], seq[q], rec, t);
+                J[q][0] = fma(t[0], t[0], J[q][0]);
+            }
         }
     } else {
         int k = sub;
 #pragma unroll 1
         for (; k + (U - 1) * G < n; k += U * G) {
-            double rec[U][NC], t[U];
+            double rec[U][NC];
 #pragma unroll
             for (int u = 0; u < U; ++u) load_record<NC>(tile, k + u * G, rec[u]);
-            M::template resid_batch<U>(ctx, seq, rec, t);
 #pragma unroll
-            for (int u = 0; u < U; ++u) Ju[u] = fma(t[u], t[u], Ju[u]);
-            if constexpr (GRAD) {
+            for (int q = 0; q < Q; ++q) {
+                double t[U];
+                M::template resid_batch<U>(ctx[q], seq[q], rec, t);
 #pragma unroll
-                for (int u = 0; u < U; ++u) M::grad_acc(ctx, rec[u], t[u], g);
+                for (int u = 0; u < U; ++u) J[q][u] = fma(t[u], t[u], J[q][u]);
+                if constexpr (GRAD) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) M::grad_acc(ctx[q], rec[u], t[u], g[q]);
+                }
             }
         }
 #pragma unroll 1
         for (; k < n; k += G) {
-            double rec[1][NC], t[1];
+            double rec[1][NC];
             load_record<NC>(tile, k, rec[0]);
-            M::template resid_batch<1>(ctx, seq, rec, t);
-            Ju[0] = fma(t[0], t[0], Ju[0]);
-            if constexpr (GRAD) M::grad_acc(ctx, rec[0], t[0], g);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                double t[1];
+                M::template resid_batch<1>(ctx[q], seq[q], rec, t);
+                J[q][0] = fma(t[0], t[0], J[q][0]);
+                if constexpr (GRAD) M::grad_acc(ctx[q], rec[0], t[0], g[q]);
+            }
         }
     }
 }
@@ -137,28 +151,54 @@ __device__ __forceinline__ bool inside_box(const double (&x)[D], const ProblemDe
     return inside;
 }
 
-// BayesianPosterior.compute_log_value (bayesian_inference.py:44-64) with the identity
-// parametrisation: -inf outside the prior box WITHOUT evaluating the model (:53-55), otherwise
-// log_prior - log(1) + (-(1/2) J).   Resident mode: all records are in shared memory.
-template <class M, int D, int G>
-__device__ __forceinline__ double log_posterior(const double (&x)[D], const ProblemDev &prob, const double *smem_rec, int sub,
-                                                unsigned group_mask) {
-    if (!inside_box<D>(x, prob)) return -INFINITY;
-    double theta[M::NPARAM];
-    full_theta<M, D>(x, prob, theta);
-    typename M::Ctx ctx;
-    M::begin(ctx, theta, prob);
-    typename M::Seq seq;
+// Model constants of one chain from its uncertain parameters.  When every parameter is uncertain
+// (D == NPARAM) the reference aliases param = var_param (bayesian_inference.py:368-369): theta IS x.
+template <class M, int D>
+__device__ __forceinline__ void begin_chain(const double (&x)[D], const ProblemDev &prob, typename M::Ctx &ctx, typename M::Seq &seq) {
+    if constexpr (D == M::NPARAM) {
+        M::begin(ctx, x, prob);
+    } else {
+        double theta[M::NPARAM];
+        full_theta<M, D>(x, prob, theta);
+        M::begin(ctx, theta, prob);
+    }
     M::seq_init(ctx, seq, prob);
-    double Ju[M::UNROLL], gdummy[1];
+}
+
+// BayesianPosterior.compute_log_value (bayesian_inference.py:44-64) with the identity
+// parametrisation, for the Q chains of a thread: -inf outside the prior box WITHOUT evaluating the
+// model (:53-55), otherwise log_prior - log(1) + (-(1/2) J).  Resident mode: all records are in
+// shared memory.  The data pass is skipped when no chain of the thread needs it.
+template <class M, int D, int G, int Q>
+__device__ __forceinline__ void log_posterior(const double (&x)[Q][D], const bool (&want)[Q], const ProblemDev &prob, const double *smem_rec,
+                                              int sub, unsigned group_mask, double (&lp)[Q]) {
+    constexpr int U = M::UNROLL;   // tools/ubench: U = 4 points x Q = 2 chains in flight reaches 83% of the DFMA peak at 12 warps/SM
+    bool inb[Q], any = false;
 #pragma unroll
-    for (int u = 0; u < M::UNROLL; ++u) Ju[u] = 0.0;
-    tile_accumulate<M, G, false>(ctx, seq, smem_rec, prob.n_points, sub, Ju, gdummy);
-    double J = 0.0;
+    for (int q = 0; q < Q; ++q) {
+        inb[q] = want[q] && inside_box<D>(x[q], prob);
+        any = any || inb[q];
+        lp[q] = -INFINITY;
+    }
+    if (!any) return;
+    typename M::Ctx ctx[Q];
+    typename M::Seq seq[Q];
+    double J[Q][U], gdummy[Q][1];
 #pragma unroll
-    for (int u = 0; u < M::UNROLL; ++u) J += Ju[u];
-    J = group_sum<G>(J, group_mask) + prob.J_const;
-    return (prob.log_prior_const - 0.0) + (-0.5 * J);
+    for (int q = 0; q < Q; ++q) {
+        begin_chain<M, D>(x[q], prob, ctx[q], seq[q]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) J[q][u] = 0.0;
+    }
+    tile_accumulate<M, G, Q, U, false>(ctx, seq, smem_rec, prob.n_points, sub, J, gdummy);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        double Jq = 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) Jq += J[q][u];
+        Jq = group_sum<G>(Jq, group_mask) + prob.J_const;
+        if (inb[q]) lp[q] = (prob.log_prior_const - 0.0) + (-0.5 * Jq);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -191,269 +231,299 @@ __device__ __forceinline__ void draw_philox(uint64_t seed, uint64_t chain, uint6
     u = uniform53(w[2 * NPAIR], w[2 * NPAIR + 1]);
 }
 
+// Parity mode: the chain's next D normals and one uniform from the injected streams; the cursors live
+// in global memory (every lane of a group reads them, the writer lane advances them after the draw).
 template <int D>
-__device__ __forceinline__ bool draw_injected(const StreamsDev &s, int64_t c, int64_t &cn, int64_t &cu, bool want_uniform, double (&z)[D],
-                                              double &u) {
-    if (cn + D > s.n_normals || (want_uniform && cu + 1 > s.n_uniforms)) {
+__device__ __forceinline__ bool draw_injected(const StreamsDev &s, int64_t c, bool advance, unsigned group_mask, double (&z)[D], double &u) {
+    const int64_t cn = s.cur_n[c], cu = s.cur_u[c];
+    __syncwarp(group_mask);
+    const bool ok = !(cn + D > s.n_normals || cu + 1 > s.n_uniforms);
+    if (ok) {
+        const double *zn = s.normals + c * s.n_normals + cn;
+#pragma unroll
+        for (int i = 0; i < D; ++i) z[i] = zn[i];
+        u = s.uniforms[c * s.n_uniforms + cu];
+        if (advance) {
+            s.cur_n[c] = cn + D;
+            s.cur_u[c] = cu + 1;
+        }
+    } else {
 #pragma unroll
         for (int i = 0; i < D; ++i) z[i] = 0.0;
         u = 1.0;
-        return false;
     }
-    const double *zn = s.normals + c * s.n_normals + cn;
-#pragma unroll
-    for (int i = 0; i < D; ++i) z[i] = zn[i];
-    cn += D;
-    if (want_uniform) {
-        u = s.uniforms[c * s.n_uniforms + cu];
-        cu += 1;
-    }
-    return true;
+    __syncwarp(group_mask);
+    return ok;
 }
 
 // ------------------------------------------------------------------------------------------------
-// The kernel.
+// The kernel.  ALGO = pbu_algo_id of the MH family: bit 0 adaptive (AM, DRAM), bit 1 delayed
+// rejection (DR, DRAM).  Q = chains per thread; thread group g owns chains g, g + n_groups, ...
 // ------------------------------------------------------------------------------------------------
-template <class M, int D, int G, bool ADAPT>
+template <class M, int D, int G, int ALGO, int Q>
 __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_constant__ MhParams p) {
+    constexpr bool ADAPT = (ALGO & 1) != 0;
+    constexpr bool DELAYED = (ALGO & 2) != 0;
+    constexpr int NT = tri_size(D);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     double *smem_rec = reinterpret_cast<double *>(smem_raw + 128);
-    constexpr int NT = tri_size(D);
 
     stage_records(smem_rec, bar, p.prob.records, (uint32_t)p.prob.n_points * (uint32_t)(M::NC * 8));
 
     const int64_t C = p.st.n_chains;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t c = gtid / G;
     const int sub = (int)(gtid % G);
-    const bool live = c < C;
-    if (!live) c = C - 1;                       // padding lanes shadow the last chain, never write
-    const bool writer = live && (sub == 0);
     const int lane = threadIdx.x & 31;
     const unsigned group_mask = (G == 1) ? (1u << lane) : (((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(G - 1)));
+    const bool injected = p.streams.normals != nullptr;
 
     // ---- chain state kept in registers across the launch
-    double x[D], lp;
+    int64_t c[Q];
+    bool live[Q];
+    double x[Q][D], lp[Q], mean_r[Q];
+    int32_t n_rej[Q], n_eval[Q], status[Q];     // n_rej / n_eval: per-launch increments of the int64 counters
 #pragma unroll
-    for (int i = 0; i < D; ++i) x[i] = p.st.x[i * C + c];
-    lp = p.st.lp[c];
-    double mean_r = p.st.mean_r[c];
-    int32_t n_rej = 0, n_eval = 0;              // per-launch increments of the int64 counters
-    int32_t status = p.st.status[c];
-    const bool injected = p.streams.normals != nullptr;
-    int64_t cn = 0, cu = 0;
-    if (injected) {
-        cn = p.streams.cur_n[c];
-        cu = p.streams.cur_u[c];
+    for (int q = 0; q < Q; ++q) {
+        c[q] = gtid / G + (int64_t)q * p.n_groups;
+        live[q] = c[q] < C;
+        if (!live[q]) c[q] = C - 1;             // padding slots shadow the last chain, never write
+#pragma unroll
+        for (int i = 0; i < D; ++i) x[q][i] = p.st.x[i * C + c[q]];
+        lp[q] = p.st.lp[c[q]];
+        mean_r[q] = p.st.mean_r[c[q]];
+        n_rej[q] = 0;
+        n_eval[q] = 0;
+        status[q] = p.st.status[c[q]];
     }
-    const uint64_t gchain = p.chain_offset + (uint64_t)c;
-    // per-chain adaptive state in global memory (chain-minor): every lane of a group reads and, if live,
-    // writes the same values, so each thread only ever reads back its own stores.
-    double *const gR = p.st.R + c;
-    double *const gV = p.st.V + c;
-    double *const gxav = p.st.xav + c;
+    // The per-chain adaptive state (X_av, V_i, R) lives in global memory, chain-minor: every lane of a group
+    // reads and, if live, writes the same values, so each thread only ever reads back its own stores.
 
     for (int64_t s = 0; s < p.n_steps; ++s) {
         const int64_t it = p.it0 + s + 1;
         // Up to two proposal stages share ONE inlined copy of the posterior evaluation (code size):
         // stage 0 = the Metropolis proposal (mha.py:184-224), stage 1 = the delayed-rejection
         // proposal (mha.py:535-567), entered only by chains whose first proposal was rejected.
-        double y1[D], lp1 = 0.0, lp2 = nan(""), r = 0.0, alpha = 0.0;
-        int acc = 0;
+        double y[Q][D], y1[DELAYED ? Q : 1][DELAYED ? D : 1], u[Q], lpy[Q];
+        double lp1[Q], lp2[Q], r[Q], alpha[Q];
+        int acc[Q];
+        bool want[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            want[q] = true;
+            acc[q] = 0;
+            lp2[q] = nan("");
+        }
 #pragma unroll 1
-        for (int stage = 0; stage < 2; ++stage) {
-            double z[D], u;
-            if (injected) {
-                if (!draw_injected<D>(p.streams, c, cn, cu, true, z, u)) status |= ST_STREAM_EXHAUSTED;
-            } else {
-                draw_philox<D>(p.seed, gchain, (uint64_t)it, (uint32_t)stage, z, u);
-            }
-            // new = cur + scale * R @ z with R UPPER triangular (mha.py:193, :543)
-            double y[D];
+        for (int stage = 0; stage < (DELAYED ? 2 : 1); ++stage) {
             const double scale = (stage == 0) ? 1.0 : p.gamma_dr;
 #pragma unroll
-            for (int i = 0; i < D; ++i) {
-                double sj = 0.0;
-#pragma unroll
-                for (int j = i; j < D; ++j) {
-                    const double rij = ADAPT ? gR[(int64_t)tri_idx(D, i, j) * C] : p.R0[tri_idx(D, i, j)];
-                    sj = fma(rij, z[j], sj);
+            for (int q = 0; q < Q; ++q) {
+                if (!want[q]) continue;
+                double z[D];
+                if (injected) {
+                    if (!draw_injected<D>(p.streams, c[q], live[q] && sub == 0, group_mask, z, u[q])) status[q] |= ST_STREAM_EXHAUSTED;
+                } else {
+                    draw_philox<D>(p.seed, p.chain_offset + (uint64_t)c[q], (uint64_t)it, (uint32_t)stage, z, u[q]);
                 }
-                y[i] = x[i] + scale * sj;
-            }
-            const double lpy = log_posterior<M, D, G>(y, p.prob, smem_rec, sub, group_mask);
-            n_eval += 1;
-            bool accept;
-            if (stage == 0) {
-#pragma unroll
-                for (int i = 0; i < D; ++i) y1[i] = y[i];
-                lp1 = lpy;
-                r = (lp1 == -INFINITY) ? 0.0 : exp(lp1 - lp);              // :200-205
-                if (r != r) {
-                    status |= ST_NAN_RATIO;
-                    if (p.nan_rejects) r = 0.0;
-                }
-                alpha = py_min1(r);                                         // :207
-                accept = u < alpha;                                         // :214
-            } else {
-                lp2 = lpy;
-                const double r12 = exp(lp1 - lp2);                          // :547
-                const double a12 = py_min1(r12);
-                // inv_V = inv_R * inv_R^T ELEMENTWISE = diag(1/R_ii^2)  (:517-518, :594-595)
-                double M2 = 0.0, M4 = 0.0;
+                // new = cur + scale * R @ z with R UPPER triangular (mha.py:193, :543)
 #pragma unroll
                 for (int i = 0; i < D; ++i) {
-                    const double rii = ADAPT ? gR[(int64_t)tri_idx(D, i, i) * C] : p.R0[tri_idx(D, i, i)];
-                    const double ir = 1.0 / rii;
-                    const double iv = ir * ir;
-                    const double d1 = y1[i] - y[i];
-                    const double d2 = y1[i] - x[i];
-                    M2 += (d1 * iv) * d1;
-                    M4 += (d2 * iv) * d2;
-                }
-                double r2 = exp(lp2 - lp) * (exp(-0.5 * M2) / exp(-0.5 * M4)) * (1.0 - a12) / (1.0 - alpha);   // :555-556
-                if (r2 != r2) {
-                    status |= ST_NAN_RATIO;
-                    if (p.nan_rejects) r2 = 0.0;
-                }
-                accept = u < py_min1(r2);                                   // :558-562
-            }
-            if (accept) {
+                    double sj = 0.0;
 #pragma unroll
-                for (int i = 0; i < D; ++i) x[i] = y[i];
-                lp = lpy;
-                acc = stage + 1;
-                break;
+                    for (int j = i; j < D; ++j) {
+                        const double rij = ADAPT ? p.st.R[(int64_t)tri_idx(D, i, j) * C + c[q]] : p.R0[tri_idx(D, i, j)];
+                        sj = fma(rij, z[j], sj);
+                    }
+                    y[q][i] = x[q][i] + scale * sj;
+                }
+                n_eval[q] += 1;
             }
-            if (stage == 1 || !p.delayed) {
-                n_rej += 1;                                                 // :224, :567
-                break;
+            log_posterior<M, D, G, Q>(y, want, p.prob, smem_rec, sub, group_mask, lpy);
+            bool again = false;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                if (!want[q]) continue;
+                bool accept;
+                if (stage == 0) {
+                    lp1[q] = lpy[q];
+                    r[q] = (lp1[q] == -INFINITY) ? 0.0 : exp(lp1[q] - lp[q]);         // :200-205
+                    if (r[q] != r[q]) {
+                        status[q] |= ST_NAN_RATIO;
+                        if (p.nan_rejects) r[q] = 0.0;
+                    }
+                    alpha[q] = py_min1(r[q]);                                           // :207
+                    accept = u[q] < alpha[q];                                           // :214
+                } else {
+                    lp2[q] = lpy[q];
+                    const double r12 = exp(lp1[q] - lp2[q]);                            // :547
+                    const double a12 = py_min1(r12);
+                    // inv_V = inv_R * inv_R^T ELEMENTWISE = diag(1/R_ii^2)  (:517-518, :594-595)
+                    double M2 = 0.0, M4 = 0.0;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+                        const double rii = ADAPT ? p.st.R[(int64_t)tri_idx(D, i, i) * C + c[q]] : p.R0[tri_idx(D, i, i)];
+                        const double ir = 1.0 / rii;
+                        const double iv = ir * ir;
+                        const double d1 = y1[DELAYED ? q : 0][DELAYED ? i : 0] - y[q][i];
+                        const double d2 = y1[DELAYED ? q : 0][DELAYED ? i : 0] - x[q][i];
+                        M2 += (d1 * iv) * d1;
+                        M4 += (d2 * iv) * d2;
+                    }
+                    double r2 = exp(lp2[q] - lp[q]) * (exp(-0.5 * M2) / exp(-0.5 * M4)) * (1.0 - a12) / (1.0 - alpha[q]);   // :555-556
+                    if (r2 != r2) {
+                        status[q] |= ST_NAN_RATIO;
+                        if (p.nan_rejects) r2 = 0.0;
+                    }
+                    accept = u[q] < py_min1(r2);                                        // :558-562
+                }
+                if (accept) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) x[q][i] = y[q][i];
+                    lp[q] = lpy[q];
+                    acc[q] = stage + 1;
+                    want[q] = false;
+                } else if (DELAYED && stage == 0) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) y1[DELAYED ? q : 0][DELAYED ? i : 0] = y[q][i];
+                    again = true;                                                       // :535
+                } else {
+                    n_rej[q] += 1;                                                      // :224, :567
+                    want[q] = false;
+                }
             }
+            if (!again) break;
         }
 
-        // ---- covariance adaptation (mha.py:432-487)
-        if (ADAPT) {
-            const double fi = (double)it;
-            const bool refresh = (it % p.updating_it == 0);                 // :470
-            double Vc[NT];
-            if (!p.am_welford) {
-                // literal Haario/Smith recursion, evaluated in the reference's operation order
-                // without FMA contraction; at it == 1 X_av_i aliases the state.
-                double xa[D], xb[D];
 #pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    xa[i] = (it == 1) ? x[i] : gxav[(int64_t)i * C];
-                    xb[i] = __dadd_rn(x[i], __dmul_rn(fi / (fi + 1.0), __dadd_rn(xa[i], -x[i])));       // :455
-                }
-                const double c1 = (fi - 1.0) / fi, c2 = p.S_d / fi;
+        for (int q = 0; q < Q; ++q) {
+            const int64_t cq = c[q];
+            // ---- covariance adaptation (mha.py:432-487)
+            if (ADAPT) {
+                double *const gR = p.st.R + cq;
+                double *const gV = p.st.V + cq;
+                double *const gxav = p.st.xav + cq;
+                const double fi = (double)it;
+                const bool refresh = (it % p.updating_it == 0);                 // :470
+                double Vc[NT];
+                if (!p.am_welford) {
+                    // literal Haario/Smith recursion, evaluated in the reference's operation order
+                    // without FMA contraction; at it == 1 X_av_i aliases the state.
+                    double xa[D], xb[D];
 #pragma unroll
-                for (int i = 0; i < D; ++i)
-#pragma unroll
-                    for (int j = i; j < D; ++j) {
-                        double t = __dadd_rn(__dmul_rn(fi, __dmul_rn(xa[i], xa[j])), -__dmul_rn(fi + 1.0, __dmul_rn(xb[i], xb[j])));
-                        t = __dadd_rn(t, __dmul_rn(x[i], x[j]));
-                        t = __dadd_rn(t, (i == j) ? p.eps_v : 0.0);
-                        const int64_t o = (int64_t)tri_idx(D, i, j) * C;
-                        const double v = __dadd_rn(__dmul_rn(c1, gV[o]), __dmul_rn(c2, t));             // :463
-                        Vc[tri_idx(D, i, j)] = v;
-                        if (live) gV[o] = v;
+                    for (int i = 0; i < D; ++i) {
+                        xa[i] = (it == 1) ? x[q][i] : gxav[(int64_t)i * C];
+                        xb[i] = __dadd_rn(x[q][i], __dmul_rn(fi / (fi + 1.0), __dadd_rn(xa[i], -x[q][i])));       // :455
                     }
-                if (live) {
+                    const double c1 = (fi - 1.0) / fi, c2 = p.S_d / fi;
 #pragma unroll
-                    for (int i = 0; i < D; ++i) gxav[(int64_t)i * C] = xb[i];
-                }
-            } else {
-                // Welford over x_0..x_it: xav = running mean, V = sum of outer products of deviations
-                const double inv_n = 1.0 / (fi + 1.0);
-                const double sc = p.S_d / fi;                               // S_d * M2/(n-1), n = it+1
-                double dl[D], mu[D];
+                    for (int i = 0; i < D; ++i)
 #pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    const double m = gxav[(int64_t)i * C];
-                    dl[i] = x[i] - m;
-                    mu[i] = fma(dl[i], inv_n, m);
-                }
+                        for (int j = i; j < D; ++j) {
+                            double t = __dadd_rn(__dmul_rn(fi, __dmul_rn(xa[i], xa[j])), -__dmul_rn(fi + 1.0, __dmul_rn(xb[i], xb[j])));
+                            t = __dadd_rn(t, __dmul_rn(x[q][i], x[q][j]));
+                            t = __dadd_rn(t, (i == j) ? p.eps_v : 0.0);
+                            const int64_t o = (int64_t)tri_idx(D, i, j) * C;
+                            const double v = __dadd_rn(__dmul_rn(c1, gV[o]), __dmul_rn(c2, t));             // :463
+                            Vc[tri_idx(D, i, j)] = v;
+                            if (live[q]) gV[o] = v;
+                        }
+                    if (live[q]) {
 #pragma unroll
-                for (int i = 0; i < D; ++i)
-#pragma unroll
-                    for (int j = i; j < D; ++j) {
-                        const int64_t o = (int64_t)tri_idx(D, i, j) * C;
-                        const double v = fma(dl[i], x[j] - mu[j], gV[o]);
-                        Vc[tri_idx(D, i, j)] = sc * v + ((i == j) ? p.S_d * p.eps_v : 0.0);
-                        if (live) gV[o] = v;
-                    }
-                if (live) {
-#pragma unroll
-                    for (int i = 0; i < D; ++i) gxav[(int64_t)i * C] = mu[i];
-                }
-            }
-            if (refresh) {                                  // :486-487, :591-595
-                double Rn[NT];
-                if (chol_upper_packed<D>(Vc, Rn)) {
-                    if (live) {
-#pragma unroll
-                        for (int i = 0; i < NT; ++i) gR[(int64_t)i * C] = Rn[i];
+                        for (int i = 0; i < D; ++i) gxav[(int64_t)i * C] = xb[i];
                     }
                 } else {
-                    status |= ST_NOT_PD;                    // scipy raises LinAlgError here (:487)
-                }
-            }
-            mean_r += r;                                    // :419 (unclipped)
-        } else {
-            mean_r += alpha;                                // :170
-        }
-
-        // ---- outputs
-        if (writer) {
-            if (p.out.trace_lp1) p.out.trace_lp1[s * C + c] = lp1;
-            if (p.out.trace_lp2) p.out.trace_lp2[s * C + c] = lp2;
-            if (p.out.trace_acc) p.out.trace_acc[s * C + c] = (uint8_t)acc;
-            if (it % p.thin == 0) {
-                // running (Welford) moments of the KEPT states, held in global memory so that they cost
-                // no registers in the data loop; input of the moment reduction (K4: pooled covariance, R-hat)
-                {
-                    const int64_t wc = p.st.wcount[c] + 1;
-                    p.st.wcount[c] = wc;
-                    const double inv_n = 1.0 / (double)wc;
+                    // Welford over x_0..x_it: xav = running mean, V = sum of outer products of deviations
+                    const double inv_n = 1.0 / (fi + 1.0);
+                    const double sc = p.S_d / fi;                               // S_d * M2/(n-1), n = it+1
                     double dl[D], mu[D];
 #pragma unroll
                     for (int i = 0; i < D; ++i) {
-                        const double m = p.st.wmean[i * C + c];
-                        dl[i] = x[i] - m;
+                        const double m = gxav[(int64_t)i * C];
+                        dl[i] = x[q][i] - m;
                         mu[i] = fma(dl[i], inv_n, m);
-                        p.st.wmean[i * C + c] = mu[i];
                     }
 #pragma unroll
                     for (int i = 0; i < D; ++i)
 #pragma unroll
                         for (int j = i; j < D; ++j) {
-                            double *q = &p.st.wM2[tri_idx(D, i, j) * C + c];
-                            *q = fma(dl[i], x[j] - mu[j], *q);
+                            const int64_t o = (int64_t)tri_idx(D, i, j) * C;
+                            const double v = fma(dl[i], x[q][j] - mu[j], gV[o]);
+                            Vc[tri_idx(D, i, j)] = sc * v + ((i == j) ? p.S_d * p.eps_v : 0.0);
+                            if (live[q]) gV[o] = v;
                         }
-                }
-                const int64_t row = it / p.thin - p.it0 / p.thin - 1;
-                if (p.out.samples) {
+                    if (live[q]) {
 #pragma unroll
-                    for (int i = 0; i < D; ++i) p.out.samples[(row * D + i) * C + c] = x[i];
+                        for (int i = 0; i < D; ++i) gxav[(int64_t)i * C] = mu[i];
+                    }
                 }
-                if (p.out.lp_kept) p.out.lp_kept[row * C + c] = lp;
+                if (refresh) {                                  // :486-487, :591-595
+                    double Rn[NT];
+                    if (chol_upper_packed<D>(Vc, Rn)) {
+                        if (live[q]) {
+#pragma unroll
+                            for (int i = 0; i < NT; ++i) gR[(int64_t)i * C] = Rn[i];
+                        }
+                    } else {
+                        status[q] |= ST_NOT_PD;                 // scipy raises LinAlgError here (:487)
+                    }
+                }
+                mean_r[q] += r[q];                              // :419 (unclipped)
+            } else {
+                mean_r[q] += alpha[q];                          // :170
+            }
+
+            // ---- outputs
+            if (live[q] && sub == 0) {
+                if (p.out.trace_lp1) p.out.trace_lp1[s * C + cq] = lp1[q];
+                if (p.out.trace_lp2) p.out.trace_lp2[s * C + cq] = lp2[q];
+                if (p.out.trace_acc) p.out.trace_acc[s * C + cq] = (uint8_t)acc[q];
+                if (it % p.thin == 0) {
+                    // running (Welford) moments of the KEPT states, held in global memory so that they cost
+                    // no registers in the data loop; input of the moment reduction (K4: pooled covariance, R-hat)
+                    {
+                        const int64_t wc = p.st.wcount[cq] + 1;
+                        p.st.wcount[cq] = wc;
+                        const double inv_n = 1.0 / (double)wc;
+                        double dl[D], mu[D];
+#pragma unroll
+                        for (int i = 0; i < D; ++i) {
+                            const double m = p.st.wmean[i * C + cq];
+                            dl[i] = x[q][i] - m;
+                            mu[i] = fma(dl[i], inv_n, m);
+                            p.st.wmean[i * C + cq] = mu[i];
+                        }
+#pragma unroll
+                        for (int i = 0; i < D; ++i)
+#pragma unroll
+                            for (int j = i; j < D; ++j) {
+                                double *w2 = &p.st.wM2[tri_idx(D, i, j) * C + cq];
+                                *w2 = fma(dl[i], x[q][j] - mu[j], *w2);
+                            }
+                    }
+                    const int64_t row = it / p.thin - p.it0 / p.thin - 1;
+                    if (p.out.samples) {
+#pragma unroll
+                        for (int i = 0; i < D; ++i) p.out.samples[(row * D + i) * C + cq] = x[q][i];
+                    }
+                    if (p.out.lp_kept) p.out.lp_kept[row * C + cq] = lp[q];
+                }
             }
         }
     }
 
     // ---- store state
-    if (writer) {
 #pragma unroll
-        for (int i = 0; i < D; ++i) p.st.x[i * C + c] = x[i];
-        p.st.lp[c] = lp;
-        p.st.mean_r[c] = mean_r;
-        p.st.n_rej[c] += n_rej;
-        p.st.n_eval[c] += n_eval;
-        p.st.status[c] = status;
-        if (injected) {
-            p.streams.cur_n[c] = cn;
-            p.streams.cur_u[c] = cu;
+    for (int q = 0; q < Q; ++q) {
+        if (live[q] && sub == 0) {
+            const int64_t cq = c[q];
+#pragma unroll
+            for (int i = 0; i < D; ++i) p.st.x[i * C + cq] = x[q][i];
+            p.st.lp[cq] = lp[q];
+            p.st.mean_r[cq] = mean_r[q];
+            p.st.n_rej[cq] += n_rej[q];
+            p.st.n_eval[cq] += n_eval[q];
+            p.st.status[cq] = status[q];
         }
     }
 }
@@ -471,10 +541,12 @@ __global__ void __launch_bounds__(256) eval_logpost_kernel(const __grid_constant
     stage_records(smem_rec, bar, prob.records, (uint32_t)prob.n_points * (uint32_t)(M::NC * 8));
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= S) return;
-    double x[D];
+    double x[1][D], lp[1];
+    const bool want[1] = {true};
 #pragma unroll
-    for (int i = 0; i < D; ++i) x[i] = X[i * S + t];
-    lp_out[t] = log_posterior<M, D, 1>(x, prob, smem_rec, 0, 1u << (threadIdx.x & 31));
+    for (int i = 0; i < D; ++i) x[0][i] = X[i * S + t];
+    log_posterior<M, D, 1, 1>(x, want, prob, smem_rec, 0, 1u << (threadIdx.x & 31), lp);
+    lp_out[t] = lp[0];
 }
 
 // Model.run_model for S parameter vectors: f_out[k][s] (point-major, coalesced over samples).

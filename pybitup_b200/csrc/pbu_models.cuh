@@ -36,6 +36,8 @@ struct LinearModel {
     static constexpr bool HAS_GRAD = true;
     static constexpr int ID = PBU_MODEL_LINEAR;
     static constexpr int UNROLL = (P <= 4) ? 4 : ((P <= 6) ? 3 : 2);
+    static constexpr int OPS = P + 1;   // FP64 instructions per point and chain
+    static constexpr int WF = P + 1;    // shared-memory wavefronts (8 B per lane) per point
     struct Ctx {
         double th[P];
     };
@@ -79,6 +81,8 @@ struct PolyModel {
     static constexpr bool HAS_GRAD = true;
     static constexpr int ID = PBU_MODEL_POLY;
     static constexpr int UNROLL = 4;
+    static constexpr int OPS = P + 1;
+    static constexpr int WF = 3;
     struct Ctx {
         double th[P];
     };
@@ -131,6 +135,8 @@ struct ArrheniusModel {
     static constexpr bool HAS_GRAD = false;
     static constexpr int ID = PBU_MODEL_ARRHENIUS;
     static constexpr int UNROLL = 1;
+    static constexpr int OPS = 400;     // two exp and four pow per RK4 step dominate
+    static constexpr int WF = 4;
     static constexpr double R_GAS = 8.314462618;
     struct Ctx {
         double c0, ER, n, F, h, g_start;
@@ -184,6 +190,8 @@ struct HeatModel {
     static constexpr bool HAS_GRAD = false;
     static constexpr int ID = PBU_MODEL_HEAT;
     static constexpr int UNROLL = 2;
+    static constexpr int OPS = 60;      // two exp per point
+    static constexpr int WF = 3;
     struct Ctx {
         double gamma, c1, c2, T_amb;
     };

@@ -5,12 +5,13 @@
 namespace pbu {
 
 struct MhKernelEntry {
-    int model, n_param, n_unc, lanes, adapt;
+    int model, n_param, n_unc, lanes, chains_per_thread, algo;   // algo = pbu_algo_id (RWMH, AM, DR, DRAM)
     const void *fn;   // __global__ void (*)(const MhParams)
 };
 struct EvalKernelEntry {
     int model, n_param, n_unc, sequential;
     int nc, ncr;              // doubles per likelihood / raw record (Model::NC, Model::NCR)
+    int ops, wf;              // FP64 instructions / shared-memory wavefronts per point (launch planning)
     const void *eval_lp;      // __global__ void (*)(const ProblemDev, const double*, int64_t, double*)
     const void *eval_model;   // same signature
 };

@@ -108,6 +108,7 @@ class SamplerConfig:
     nan_rejects: bool = False        # False = reference semantics, min(1, nan) == 1 accepts
     lanes_per_chain: int = 0
     block_threads: int = 0
+    chains_per_thread: int = 0
     seed: int = 0
     chain_offset: int = 0
 
@@ -122,6 +123,7 @@ class SamplerConfig:
         s.adapt_start, s.adapt_update, s.adapt_end = int(self.adapt_start), int(self.adapt_update), int(self.adapt_end)
         s.am_welford, s.nan_rejects = int(self.am_welford), int(self.nan_rejects)
         s.lanes_per_chain, s.block_threads = int(self.lanes_per_chain), int(self.block_threads)
+        s.chains_per_thread = int(self.chains_per_thread)
         s.seed, s.chain_offset = int(self.seed) & (2 ** 64 - 1), int(self.chain_offset)
         return s
 
@@ -216,9 +218,9 @@ class ChainEngine:
 
     def launch_geometry(self):
         """(lanes per chain, threads per block, blocks, dynamic shared memory bytes) of the step kernel."""
-        a, b, g, m = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
-        capi.check(capi.lib.pbu_engine_get_launch(self._h, C.byref(a), C.byref(b), C.byref(g), C.byref(m)))
-        return dict(lanes=a.value, block=b.value, grid=g.value, smem_bytes=m.value)
+        a, q, b, g, m = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+        capi.check(capi.lib.pbu_engine_get_launch(self._h, C.byref(a), C.byref(q), C.byref(b), C.byref(g), C.byref(m)))
+        return dict(lanes=a.value, chains_per_thread=q.value, block=b.value, grid=g.value, smem_bytes=m.value)
 
     # -- the hot loop -------------------------------------------------------------------------
     def run(self, n_steps, thin=1, keep_samples=True, keep_lp=False, trace=False, out=None):
