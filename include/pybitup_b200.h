@@ -102,7 +102,8 @@ typedef struct {
     int32_t lanes_per_chain;  /* 0 auto; 1,2,4,8: lanes of a warp that share one chain's data sum */
     int32_t block_threads;    /* 0 auto                                                           */
     int32_t chains_per_thread;/* 0 auto; 1,2: chains that share every record a thread reads       */
-    int32_t pad0;
+    int32_t tile_points;      /* 0 auto: records resident in shared memory when they fit, else streamed in
+                                 tiles; > 0 forces tiles of at most that many points (testing)            */
     uint64_t seed;            /* Philox key                                                       */
     uint64_t chain_offset;    /* global index of this engine's first chain (multi-GPU sharding)   */
 } pbu_sampler_cfg;
@@ -163,6 +164,9 @@ int pbu_engine_get_counters(pbu_engine *e, int64_t *n_rejected /*[C]*/, double *
  * (:463-466) and running mean X_av_i (:455,:467); any pointer may be NULL. Row-major [C][d][d]. */
 int pbu_engine_get_proposal(pbu_engine *e, double *R_host, double *V_host, double *xav_host);
 int64_t pbu_engine_iteration(const pbu_engine *e);
+/* Ito-SDE state: momentum P_nm (mha.py:920) host [C][d] and preconditioner C_approx (:653-697, :773) host
+ * [C][d][d]; pbu_engine_get_proposal returns inv_L_c in R_host, V_i and X_av_i as for the adaptive samplers. */
+int pbu_engine_get_isde_state(pbu_engine *e, double *P_host, double *C_host);
 /* launch geometry the engine planned for the step kernel: lanes of a warp per chain, threads per block,
  * chains per thread, blocks, dynamic shared memory bytes per block (diagnostics; no reference counterpart). */
 int pbu_engine_get_launch(const pbu_engine *e, int32_t *lanes, int32_t *chains_per_thread, int32_t *block, int32_t *grid,

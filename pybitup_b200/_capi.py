@@ -42,7 +42,7 @@ class pbu_sampler_cfg(C.Structure):
                 ("isde_h", C.c_double), ("isde_f0", C.c_double), ("isde_gradient", C.c_int32),
                 ("adapt_start", C.c_int32), ("adapt_update", C.c_int32), ("adapt_end", C.c_int32),
                 ("am_welford", C.c_int32), ("nan_rejects", C.c_int32), ("lanes_per_chain", C.c_int32),
-                ("block_threads", C.c_int32), ("chains_per_thread", C.c_int32), ("pad0", C.c_int32),
+                ("block_threads", C.c_int32), ("chains_per_thread", C.c_int32), ("tile_points", C.c_int32),
                 ("seed", C.c_uint64), ("chain_offset", C.c_uint64)]
 
 
@@ -87,6 +87,7 @@ def _load():
         "pbu_engine_get_counters": (C.c_int, [E, _lp, _dp, _lp, _ip]),
         "pbu_engine_get_proposal": (C.c_int, [E, _dp, _dp, _dp]),
         "pbu_engine_iteration": (C.c_int64, [E]),
+        "pbu_engine_get_isde_state": (C.c_int, [E, _dp, _dp]),
         "pbu_engine_get_launch": (C.c_int, [E, _ip, _ip, _ip, _ip, _lp]),
         "pbu_eval_logpost": (C.c_int, [E, _dp, C.c_int64, _dp]),
         "pbu_eval_model": (C.c_int, [E, _dp, C.c_int64, _dp]),

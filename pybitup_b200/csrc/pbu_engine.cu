@@ -8,7 +8,7 @@
 #include <string>
 #include <vector>
 
-#include "pbu_mh_kernel.cuh"
+#include "pbu_isde_kernel.cuh"
 #include "pbu_registry.h"
 
 using namespace pbu;
@@ -44,6 +44,11 @@ struct pbu_engine {
     int64_t iteration = 0;
     bool initialised = false;
     const MhKernelEntry *mh = nullptr;
+    const IsdeKernelEntry *isde = nullptr;
+    const void *step_fn = nullptr;   // the planned step kernel (mh->fn or isde->fn)
+    int tile_points = 0;          // points per shared-memory tile of the likelihood records (= n_points when resident)
+    int tile_points_raw = 0;      // same for the raw records
+    double *d_Cmat = nullptr;     // ISDE: packed symmetric preconditioner per chain
     const EvalKernelEntry *ev = nullptr;
     int lanes = 1;
     int q = 1;                    // chains per thread
@@ -131,6 +136,13 @@ static const MhKernelEntry *find_mh(int model, int P, int d, int lanes, int q, i
             return &t[i];
     return nullptr;
 }
+static const IsdeKernelEntry *find_isde(int model, int P, int d, int lanes, int q) {
+    int n = 0;
+    const IsdeKernelEntry *t = pbu_isde_kernels(&n);
+    for (int i = 0; i < n; ++i)
+        if (t[i].model == model && t[i].n_param == P && t[i].n_unc == d && t[i].lanes == lanes && t[i].chains_per_thread == q) return &t[i];
+    return nullptr;
+}
 static const EvalKernelEntry *find_eval(int model, int P, int d) {
     int n = 0;
     const EvalKernelEntry *t = pbu_eval_kernels(&n);
@@ -214,6 +226,8 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
     const double N = (double)e->prob.n_points;
     const double S0 = 60.0 + 15.0 * e->d;           // per-iteration scalar part (RNG, proposal, accept, adaptation), in DFMA-equivalents
     const int cand[5][2] = {{1, 1}, {1, 2}, {2, 2}, {4, 2}, {8, 1}};     // (lanes per chain, chains per thread)
+    const bool isde = algo == PBU_ALGO_ISDE;
+    const double ops = isde ? 2.0 * e->ev->ops : (double)e->ev->ops;     // value + gradient
     double best = 1e300;
     bool found = false;
     for (const auto &gq : cand) {
@@ -223,26 +237,39 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
         if (sequential && g != 1) continue;
         // delayed rejection: the second stage runs for a thread when ANY of its chains was rejected, so pairing
         // chains wastes evaluations; one chain per thread unless asked otherwise
-        if ((algo == PBU_ALGO_DR || algo == PBU_ALGO_DRAM) && q != 1 && want_q <= 0) continue;
-        const MhKernelEntry *k = find_mh(model, e->P, e->d, g, q, algo);
-        if (!k) continue;
-        CUDA_TRY(cudaFuncSetAttribute(k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+        if ((algo == PBU_ALGO_DR || algo == PBU_ALGO_DRAM) && q != 1 && want_q <= 0 && want_lanes <= 0) continue;
+        // wide states spill heavily with two chains per thread
+        if (e->d > 6 && q != 1 && want_q <= 0 && want_lanes <= 0) continue;
+        const void *fn = nullptr;
+        const MhKernelEntry *km = nullptr;
+        const IsdeKernelEntry *ki = nullptr;
+        if (isde) {
+            ki = find_isde(model, e->P, e->d, g, q);
+            if (ki) fn = ki->fn;
+        } else {
+            km = find_mh(model, e->P, e->d, g, q, algo);
+            if (km) fn = km->fn;
+        }
+        if (!fn) continue;
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
         const int64_t groups_needed = (e->C + q - 1) / q;
         for (int B = MH_MAX_BLOCK; B >= 32; B -= 32) {
             if (want_block > 0 && B != want_block) continue;
             int occ = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k->fn, B, e->smem_bytes) != cudaSuccess || occ < 1) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, B, e->smem_bytes) != cudaSuccess || occ < 1) {
                 cudaGetLastError();
                 continue;
             }
             const double blocks = std::ceil((double)groups_needed * g / B);
             const double per_sm = std::ceil(blocks / nsm);          // blocks the busiest SM runs, `occ` at a time
             const double warps = std::min(per_sm, (double)occ) * B / 32.0;
-            const double work = q * ((sequential ? N : std::ceil(N / g)) * e->ev->ops + S0);
+            const double work = q * ((sequential ? N : std::ceil(N / g)) * ops + S0);
             const double t = per_sm * B * work / loop_efficiency(q, warps);
             if (t < best * (1.0 - 1e-3)) {
                 best = t;
-                e->mh = k;
+                e->mh = km;
+                e->isde = ki;
+                e->step_fn = fn;
                 e->lanes = g;
                 e->q = q;
                 e->block = B;
@@ -252,7 +279,7 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
         }
     }
     if (!found)
-        return fail(PBU_ERR_UNSUPPORTED, "no MH kernel variant fits model=%d P=%d d=%d lanes=%d chains_per_thread=%d block=%d algo=%d (smem %zu B)",
+        return fail(PBU_ERR_UNSUPPORTED, "no step kernel variant fits model=%d P=%d d=%d lanes=%d chains_per_thread=%d block=%d algo=%d (smem %zu B)",
                     model, e->P, e->d, want_lanes, want_q, want_block, algo, e->smem_bytes);
     return PBU_OK;
 }
@@ -303,8 +330,25 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
         return fail(PBU_ERR_INVALID, "block_threads must be a multiple of 32 in [32, %d]", MH_MAX_BLOCK);
     }
     if (cfg->algo == PBU_ALGO_ISDE) {
-        delete e;
-        return fail(PBU_ERR_UNSUPPORTED, "ISDE kernel not built in this library version");
+        if (!(cfg->isde_h > 0.0) || !(cfg->isde_f0 >= 0.0)) {
+            delete e;
+            return fail(PBU_ERR_INVALID, "ISDE needs h > 0 and f0 >= 0");
+        }
+        if (cfg->isde_gradient == 0) {
+            const IsdeKernelEntry *k = find_isde(pr->model, pr->n_param, pr->n_unc, 1, 1);
+            if (!k || !k->has_grad) {
+                delete e;
+                return fail(PBU_ERR_UNSUPPORTED, "model %d has no analytical gradient on the device; use gradient \"Numerical\"", pr->model);
+            }
+            if (pr->n_runs != 1) {
+                delete e;
+                return fail(PBU_ERR_UNSUPPORTED, "the analytical gradient uses run 0 only (bayesian_inference.py:606-608); n_runs must be 1");
+            }
+        }
+        if (cfg->adapt_update < 1) {
+            delete e;
+            return fail(PBU_ERR_INVALID, "covariance.update_it must be >= 1");
+        }
     }
 
     // ---- problem records
@@ -332,15 +376,29 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
     for (int i = 0; i < pr->n_param; ++i) pd.theta_nom[i] = pr->theta_nom[i];
     for (int i = 0; i < 8; ++i) pd.consts[i] = pr->consts[i];
 
-    e->smem_bytes = 128 + rec.size() * sizeof(double);
-    e->smem_raw_bytes = 128 + raw.size() * sizeof(double);
+    // resident when every record fits in shared memory, otherwise streamed in tiles through a 2-slot ring
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    if ((int64_t)e->smem_bytes > (int64_t)max_smem) {
-        delete e;
-        return fail(PBU_ERR_UNSUPPORTED, "point records need %zu B of shared memory, device allows %d B (streaming mode not built)",
-                    e->smem_bytes, max_smem);
-    }
+    auto plan_tiles = [&](size_t rec_bytes, int want_tile, int &tile_points, size_t &smem) {
+        const size_t all = (size_t)pr->n_points * rec_bytes;
+        if (want_tile <= 0 && 128 + all <= (size_t)max_smem) {
+            tile_points = pr->n_points;
+            smem = 128 + all;
+            return;
+        }
+        const size_t slot = std::min<size_t>(65536, ((size_t)max_smem - 128) / TileStream::S);
+        tile_points = (int)(slot / rec_bytes);
+        if (want_tile > 0) tile_points = std::min(tile_points, want_tile);
+        tile_points = std::max(1, std::min(tile_points, pr->n_points));
+        if (tile_points >= pr->n_points) {
+            tile_points = pr->n_points;
+            smem = 128 + all;
+        } else {
+            smem = 128 + (size_t)TileStream::S * tile_points * rec_bytes;
+        }
+    };
+    plan_tiles((size_t)ev->nc * 8, cfg->tile_points, e->tile_points, e->smem_bytes);
+    plan_tiles((size_t)ev->ncr * 8, cfg->tile_points, e->tile_points_raw, e->smem_raw_bytes);
     int rc;
     if ((rc = dev_alloc(e, &e->d_records, rec.size())) != PBU_OK || (rc = dev_alloc(e, &e->d_raw, raw.size())) != PBU_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(e->d_records, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
@@ -364,7 +422,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
         (rc = dev_alloc(e, &st.n_rej, (size_t)C)) || (rc = dev_alloc(e, &st.n_eval, (size_t)C)) ||
         (rc = dev_alloc(e, &st.status, (size_t)C)) || (rc = dev_alloc(e, &st.wmean, (size_t)e->d * C)) ||
         (rc = dev_alloc(e, &st.wM2, (size_t)e->nt * C)) || (rc = dev_alloc(e, &st.wcount, (size_t)C)) ||
-        (rc = dev_alloc(e, &st.P, (size_t)e->d * C)) || (rc = dev_alloc(e, &e->streams.cur_n, (size_t)C)) ||
+        (rc = dev_alloc(e, &st.P, (size_t)e->d * C)) || (rc = dev_alloc(e, &e->d_Cmat, (size_t)(cfg->algo == PBU_ALGO_ISDE ? e->nt : 0) * C)) || (rc = dev_alloc(e, &e->streams.cur_n, (size_t)C)) ||
         (rc = dev_alloc(e, &e->streams.cur_u, (size_t)C)))
         return rc;
     CUDA_TRY(cudaStreamSynchronize(e->stream));
@@ -394,8 +452,31 @@ static int launch_eval_lp(pbu_engine *e, const double *X_soa_dev, int64_t S, dou
     CUDA_TRY(cudaFuncSetAttribute(e->ev->eval_lp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     const int block = 128;
     const unsigned grid = (unsigned)((S + block - 1) / block);
-    void *args[] = {(void *)&e->prob, (void *)&X_soa_dev, (void *)&S, (void *)&lp_dev};
+    void *args[] = {(void *)&e->prob, (void *)&X_soa_dev, (void *)&S, (void *)&lp_dev, (void *)&e->tile_points};
     CUDA_TRY(cudaLaunchKernel(e->ev->eval_lp, dim3(grid), dim3(block), args, e->smem_bytes, e->stream));
+    return PBU_OK;
+}
+
+// inverse of a packed upper-triangular matrix by back substitution (same order as pbu::inv_upper_packed)
+static void inv_upper_host(const std::vector<double> &R, int d, std::vector<double> &X) {
+    X.assign(tri_size(d), 0.0);
+    for (int j = 0; j < d; ++j) {
+        X[tri_idx(d, j, j)] = 1.0 / R[tri_idx(d, j, j)];
+        for (int i = j - 1; i >= 0; --i) {
+            double sacc = 0.0;
+            for (int k = i + 1; k <= j; ++k) sacc += R[tri_idx(d, i, k)] * X[tri_idx(d, k, j)];
+            X[tri_idx(d, i, j)] = -sacc / R[tri_idx(d, i, i)];
+        }
+    }
+}
+
+// fill rows of a chain-minor [n_rows][C] device array with one value per row
+static int broadcast_rows(pbu_engine *e, double *dev, const std::vector<double> &vals) {
+    const int64_t C = e->C;
+    std::vector<double> buf(vals.size() * (size_t)C);
+    for (size_t i = 0; i < vals.size(); ++i) std::fill(buf.begin() + i * C, buf.begin() + (i + 1) * C, vals[i]);
+    CUDA_TRY(cudaMemcpyAsync(dev, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
     return PBU_OK;
 }
 
@@ -404,33 +485,46 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_init_chains(pbu
     CUDA_TRY(cudaSetDevice(e->device));
     const int d = e->d, nt = e->nt;
     const int64_t C = e->C;
+    int rc;
     std::vector<double> soa;
     transpose_to_soa(x0_host, C, d, soa);
     CUDA_TRY(cudaMemcpyAsync(e->st.x, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     const bool adapt = e->cfg.algo == PBU_ALGO_AM || e->cfg.algo == PBU_ALGO_DRAM;
+    const bool isde = e->cfg.algo == PBU_ALGO_ISDE;
     std::vector<double> Vid;
     if (!V0_host) {
         Vid.assign((size_t)d * d, 0.0);
         for (int i = 0; i < d; ++i) Vid[i * d + i] = 1.0;
         V0_host = Vid.data();
     }
-    std::vector<double> Rp;
-    if (!chol_upper_host(V0_host, d, Rp))
+    std::vector<double> Rp, Vp((size_t)nt);
+    bool pd = chol_upper_host(V0_host, d, Rp);
+    if (!pd && !isde)
         return fail(PBU_ERR_NOT_PD, "proposal covariance is not positive definite (scipy.linalg.cholesky would raise LinAlgError)");
-    e->R0 = Rp;
-    std::vector<double> buf((size_t)nt * C);
-    for (int i = 0; i < nt; ++i) std::fill(buf.begin() + (size_t)i * C, buf.begin() + (size_t)(i + 1) * C, Rp[i]);
-    CUDA_TRY(cudaMemcpyAsync(e->st.R, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(cudaStreamSynchronize(e->stream));   // buf reused below
-    if (adapt) {
-        // V_i = V_0 (mha.py:404), X_av_i = param_init (:405); Welford mode starts from M2 = 0
-        for (int i = 0; i < d; ++i)
-            for (int j = i; j < d; ++j) {
-                const double v = e->cfg.am_welford ? 0.0 : V0_host[i * d + j];
-                std::fill(buf.begin() + (size_t)tri_idx(d, i, j) * C, buf.begin() + (size_t)(tri_idx(d, i, j) + 1) * C, v);
-            }
-        CUDA_TRY(cudaMemcpyAsync(e->st.V, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-        CUDA_TRY(cudaMemcpyAsync(e->st.xav, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    for (int i = 0; i < d; ++i)
+        for (int j = i; j < d; ++j) Vp[tri_idx(d, i, j)] = V0_host[i * d + j];
+    if (isde) {
+        // C_approx, L_c = cholesky(C) (upper), inv_L_c; a failed factorisation falls back to the identity
+        // silently, as the reference's bare except does (mha.py:702-711)
+        if (!pd) {
+            for (int i = 0; i < d; ++i)
+                for (int j = i; j < d; ++j) Vp[tri_idx(d, i, j)] = (i == j) ? 1.0 : 0.0;
+            Rp = Vp;
+        }
+        std::vector<double> IL;
+        inv_upper_host(Rp, d, IL);
+        if ((rc = broadcast_rows(e, e->d_Cmat, Vp)) || (rc = broadcast_rows(e, e->st.R, IL))) return rc;
+        CUDA_TRY(cudaMemsetAsync(e->st.V, 0, (size_t)nt * C * sizeof(double), e->stream));
+        CUDA_TRY(cudaMemsetAsync(e->st.xav, 0, (size_t)d * C * sizeof(double), e->stream));
+    } else {
+        e->R0 = Rp;
+        if ((rc = broadcast_rows(e, e->st.R, Rp))) return rc;
+        if (adapt) {
+            // V_i = V_0 (mha.py:404), X_av_i = param_init (:405); Welford mode starts from M2 = 0
+            if (e->cfg.am_welford) std::fill(Vp.begin(), Vp.end(), 0.0);
+            if ((rc = broadcast_rows(e, e->st.V, Vp))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(e->st.xav, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+        }
     }
     CUDA_TRY(cudaMemsetAsync(e->st.mean_r, 0, C * sizeof(double), e->stream));
     CUDA_TRY(cudaMemsetAsync(e->st.n_rej, 0, C * sizeof(int64_t), e->stream));
@@ -444,7 +538,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_init_chains(pbu
     // initial posterior evaluation(s): once, twice for DRAM (double __init__, mha.py:588-589)
     std::vector<int64_t> ne((size_t)C, e->cfg.algo == PBU_ALGO_DRAM ? 2 : 1);
     CUDA_TRY(cudaMemcpyAsync(e->st.n_eval, ne.data(), C * sizeof(int64_t), cudaMemcpyHostToDevice, e->stream));
-    int rc = launch_eval_lp(e, e->st.x, C, e->st.lp);
+    rc = launch_eval_lp(e, e->st.x, C, e->st.lp);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     e->iteration = 0;
@@ -463,11 +557,14 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_set_streams(pbu
     e->streams.normals = e->streams.uniforms = nullptr;
     e->streams.n_normals = e->streams.n_uniforms = 0;
     if (n_normals <= 0 || !normals_host) return PBU_OK;
-    if (!uniforms_host || n_uniforms <= 0) return fail(PBU_ERR_INVALID, "uniform stream missing");
+    const bool need_u = e->cfg.algo != PBU_ALGO_ISDE;      // the Ito-SDE step draws normals only (mha.py:990)
+    if (need_u && (!uniforms_host || n_uniforms <= 0)) return fail(PBU_ERR_INVALID, "uniform stream missing");
+    if (!uniforms_host) n_uniforms = 0;
     CUDA_TRY(cudaMalloc(&e->d_normals, (size_t)e->C * n_normals * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&e->d_uniforms, (size_t)e->C * n_uniforms * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&e->d_uniforms, std::max<size_t>(1, (size_t)e->C * n_uniforms) * sizeof(double)));
     CUDA_TRY(cudaMemcpy(e->d_normals, normals_host, (size_t)e->C * n_normals * sizeof(double), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(e->d_uniforms, uniforms_host, (size_t)e->C * n_uniforms * sizeof(double), cudaMemcpyHostToDevice));
+    if (n_uniforms > 0)
+        CUDA_TRY(cudaMemcpy(e->d_uniforms, uniforms_host, (size_t)e->C * n_uniforms * sizeof(double), cudaMemcpyHostToDevice));
     e->streams.normals = e->d_normals;
     e->streams.uniforms = e->d_uniforms;
     e->streams.n_normals = n_normals;
@@ -501,6 +598,34 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine 
     if (n_steps < 0 || thin < 1) return fail(PBU_ERR_INVALID, "need n_steps >= 0 and thin >= 1");
     if (n_steps == 0) return PBU_OK;
     CUDA_TRY(cudaSetDevice(e->device));
+    if (e->cfg.algo == PBU_ALGO_ISDE) {
+        IsdeParams q;
+        memset(&q, 0, sizeof q);
+        q.prob = e->prob;
+        q.st = e->st;
+        q.streams = e->streams;
+        if (out) q.out = *out;
+        q.Cmat = e->d_Cmat;
+        q.it0 = e->iteration;
+        q.n_steps = n_steps;
+        q.thin = thin;
+        q.n_groups = (int64_t)e->grid * e->block / e->lanes;
+        q.seed = e->cfg.seed;
+        q.chain_offset = e->cfg.chain_offset;
+        q.h = e->cfg.isde_h;
+        q.f0 = e->cfg.isde_f0;
+        q.S_d = 1.0;                 // mha.py:630
+        q.eps_id = 1e-10;            // mha.py:631
+        q.starting_it = e->cfg.adapt_start > 0 ? e->cfg.adapt_start : INT64_MAX / 4;
+        q.update_it = e->cfg.adapt_update > 0 ? e->cfg.adapt_update : 1;
+        q.end_it = e->cfg.adapt_end > 0 ? e->cfg.adapt_end : INT64_MAX / 4;
+        q.tile_points = e->tile_points;
+        q.fd_gradient = e->cfg.isde_gradient != 0;
+        void *iargs[] = {(void *)&q};
+        CUDA_TRY(cudaLaunchKernel(e->step_fn, dim3((unsigned)e->grid), dim3(e->block), iargs, e->smem_bytes, e->stream));
+        e->iteration += n_steps;
+        return PBU_OK;
+    }
     MhParams p;
     memset(&p, 0, sizeof p);
     p.prob = e->prob;
@@ -519,11 +644,12 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine 
     p.delayed = (e->cfg.algo == PBU_ALGO_DR || e->cfg.algo == PBU_ALGO_DRAM) ? 1 : 0;
     p.am_welford = e->cfg.am_welford;
     p.nan_rejects = e->cfg.nan_rejects;
-    p.resident = 1;
+    p.resident = e->tile_points >= e->prob.n_points;
+    p.tile_points = e->tile_points;
     p.n_groups = (int64_t)e->grid * e->block / e->lanes;
     for (size_t i = 0; i < e->R0.size(); ++i) p.R0[i] = e->R0[i];
     void *args[] = {(void *)&p};
-    CUDA_TRY(cudaLaunchKernel(e->mh->fn, dim3((unsigned)e->grid), dim3(e->block), args, e->smem_bytes, e->stream));
+    CUDA_TRY(cudaLaunchKernel(e->step_fn, dim3((unsigned)e->grid), dim3(e->block), args, e->smem_bytes, e->stream));
     e->iteration += n_steps;
     return PBU_OK;
 }
@@ -610,6 +736,31 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_get_proposal(pb
     return PBU_OK;
 }
 
+extern "C" __attribute__((visibility("default"))) int pbu_engine_get_isde_state(pbu_engine *e, double *P_host, double *C_host) {
+    if (!e) return fail(PBU_ERR_INVALID, "null engine");
+    if (e->cfg.algo != PBU_ALGO_ISDE) return fail(PBU_ERR_INVALID, "not an ISDE engine");
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int d = e->d;
+    const int64_t C = e->C;
+    int rc;
+    if (P_host) {
+        std::vector<double> soa;
+        if ((rc = d2h(e, e->st.P, (size_t)d * C, soa))) return rc;
+        transpose_from_soa(soa, C, d, P_host);
+    }
+    if (C_host) {
+        std::vector<double> tri;
+        if ((rc = d2h(e, e->d_Cmat, (size_t)e->nt * C, tri))) return rc;
+        for (int64_t c = 0; c < C; ++c)
+            for (int i = 0; i < d; ++i)
+                for (int j = 0; j < d; ++j) {
+                    const int a = std::min(i, j), b = std::max(i, j);
+                    C_host[((size_t)c * d + i) * d + j] = tri[(size_t)tri_idx(d, a, b) * C + c];
+                }
+    }
+    return PBU_OK;
+}
+
 static int upload_soa(pbu_engine *e, const double *X_host, int64_t S, double **X_dev) {
     std::vector<double> soa;
     transpose_to_soa(X_host, S, e->d, soa);
@@ -647,7 +798,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_eval_model(pbu_engine 
     CUDA_TRY(cudaFuncSetAttribute(e->ev->eval_model, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_raw_bytes));
     const int block = 128;
     const unsigned grid = (unsigned)((S + block - 1) / block);
-    void *args[] = {(void *)&e->prob, (void *)&X_dev, (void *)&S, (void *)&f_dev};
+    void *args[] = {(void *)&e->prob, (void *)&X_dev, (void *)&S, (void *)&f_dev, (void *)&e->tile_points_raw};
     cudaError_t ce = cudaLaunchKernel(e->ev->eval_model, dim3(grid), dim3(block), args, e->smem_raw_bytes, e->stream);
     std::vector<double> pm;
     if (ce == cudaSuccess) {

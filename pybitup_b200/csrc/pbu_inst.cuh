@@ -1,6 +1,6 @@
 // Helper macros to instantiate kernel variants and describe them in a table slice.
 #pragma once
-#include "pbu_mh_kernel.cuh"
+#include "pbu_isde_kernel.cuh"
 #include "pbu_registry.h"
 
 #define PBU_MH(MODEL, P, D, G, Q, A) \
@@ -12,13 +12,23 @@
     PBU_MH_ALGOS(MODEL, P, D, 1, 1), PBU_MH_ALGOS(MODEL, P, D, 1, 2), PBU_MH_ALGOS(MODEL, P, D, 2, 2),           \
         PBU_MH_ALGOS(MODEL, P, D, 4, 2), PBU_MH_ALGOS(MODEL, P, D, 8, 1)
 #define PBU_MH_SEQ(MODEL, P, D) PBU_MH_ALGOS(MODEL, P, D, 1, 1)
+// Ito-SDE step kernel variants (lanes per chain, chains per thread)
+#define PBU_ISDE(MODEL, P, D, G, Q) \
+    { MODEL::ID, P, D, G, Q, MODEL::HAS_GRAD ? 1 : 0, (const void *)&pbu::isde_step_kernel<MODEL, D, G, Q> }
+#define PBU_ISDE_ALL(MODEL, P, D) PBU_ISDE(MODEL, P, D, 1, 1), PBU_ISDE(MODEL, P, D, 1, 2), PBU_ISDE(MODEL, P, D, 2, 2), PBU_ISDE(MODEL, P, D, 8, 1)
+#define PBU_ISDE_SEQ(MODEL, P, D) PBU_ISDE(MODEL, P, D, 1, 1)
 #define PBU_EVAL(MODEL, P, D)                                                                 \
     { MODEL::ID, P, D, MODEL::SEQUENTIAL ? 1 : 0, MODEL::NC, MODEL::NCR, MODEL::OPS, MODEL::WF, (const void *)&pbu::eval_logpost_kernel<MODEL, D>, \
       (const void *)&pbu::eval_model_kernel<MODEL, D> }
 
-#define PBU_DEFINE_SLICE(name, MH_LIST, EVAL_LIST)                                   \
+#define PBU_DEFINE_SLICE(name, MH_LIST, EVAL_LIST, ISDE_LIST)                        \
     static const pbu::MhKernelEntry mh_tab_##name[] = {MH_LIST};                     \
     static const pbu::EvalKernelEntry ev_tab_##name[] = {EVAL_LIST};                 \
+    static const pbu::IsdeKernelEntry isde_tab_##name[] = {ISDE_LIST};               \
+    const pbu::IsdeKernelEntry *pbu_isde_slice_##name(int *n) {                      \
+        *n = (int)(sizeof(isde_tab_##name) / sizeof(isde_tab_##name[0]));            \
+        return isde_tab_##name;                                                      \
+    }                                                                                \
     const pbu::MhKernelEntry *pbu_mh_slice_##name(int *n) {                          \
         *n = (int)(sizeof(mh_tab_##name) / sizeof(mh_tab_##name[0]));                \
         return mh_tab_##name;                                                        \

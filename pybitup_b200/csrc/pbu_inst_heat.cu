@@ -1,5 +1,7 @@
+// Kernel instantiations for one slice of the (model, P, d) table; see pbu_inst.cuh.
 #include "pbu_inst.cuh"
 using namespace pbu;
 #define MH_LIST PBU_MH_ALL(HeatModel, 6, 1), PBU_MH_ALL(HeatModel, 6, 2), PBU_MH_ALL(HeatModel, 6, 3), PBU_MH_ALL(HeatModel, 6, 6)
 #define EV_LIST PBU_EVAL(HeatModel, 6, 1), PBU_EVAL(HeatModel, 6, 2), PBU_EVAL(HeatModel, 6, 3), PBU_EVAL(HeatModel, 6, 6)
-PBU_DEFINE_SLICE(heat, MH_LIST, EV_LIST)
+#define ISDE_LIST PBU_ISDE_ALL(HeatModel, 6, 1), PBU_ISDE_ALL(HeatModel, 6, 2), PBU_ISDE_ALL(HeatModel, 6, 3), PBU_ISDE_ALL(HeatModel, 6, 6)
+PBU_DEFINE_SLICE(heat, MH_LIST, EV_LIST, ISDE_LIST)

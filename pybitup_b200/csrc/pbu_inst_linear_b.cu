@@ -1,5 +1,7 @@
+// Kernel instantiations for one slice of the (model, P, d) table; see pbu_inst.cuh.
 #include "pbu_inst.cuh"
 using namespace pbu;
 #define MH_LIST PBU_MH_ALL(LinearModel<4>, 4, 4), PBU_MH_ALL(LinearModel<5>, 5, 5), PBU_MH_ALL(LinearModel<6>, 6, 6)
 #define EV_LIST PBU_EVAL(LinearModel<4>, 4, 4), PBU_EVAL(LinearModel<5>, 5, 5), PBU_EVAL(LinearModel<6>, 6, 6)
-PBU_DEFINE_SLICE(linear_b, MH_LIST, EV_LIST)
+#define ISDE_LIST PBU_ISDE_ALL(LinearModel<4>, 4, 4), PBU_ISDE_ALL(LinearModel<5>, 5, 5), PBU_ISDE_ALL(LinearModel<6>, 6, 6)
+PBU_DEFINE_SLICE(linear_b, MH_LIST, EV_LIST, ISDE_LIST)

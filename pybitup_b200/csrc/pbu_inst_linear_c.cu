@@ -1,5 +1,7 @@
+// Kernel instantiations for one slice of the (model, P, d) table; see pbu_inst.cuh.
 #include "pbu_inst.cuh"
 using namespace pbu;
-#define MH_LIST PBU_MH_ALL(LinearModel<8>, 8, 8), PBU_MH_ALL(LinearModel<10>, 10, 10)
-#define EV_LIST PBU_EVAL(LinearModel<8>, 8, 8), PBU_EVAL(LinearModel<10>, 10, 10)
-PBU_DEFINE_SLICE(linear_c, MH_LIST, EV_LIST)
+#define MH_LIST PBU_MH_ALL(LinearModel<8>, 8, 8)
+#define EV_LIST PBU_EVAL(LinearModel<8>, 8, 8)
+#define ISDE_LIST PBU_ISDE_ALL(LinearModel<8>, 8, 8)
+PBU_DEFINE_SLICE(linear_c, MH_LIST, EV_LIST, ISDE_LIST)

@@ -1,0 +1,363 @@
+// K2: fused Ito-SDE step kernel (ito_SDE.run_algorithm, metropolis_hastings_algorithms.py:932-1040,
+// with GradientBasedMCMC.adapt_covariance :736-777), many iterations per launch.
+//
+// Per chain and iteration (reference line numbers):
+//   adaptation window [starting_it, end_it+1]                              :741-777
+//     it == starting_it : X_av = mean, V_i = S_d (cov + eps I) of ALL previous states   :742-746
+//     it <= end_it      : Haario recursion on (X_av, V_i)                               :750-758
+//     it % update_it==0 : C = V_i, L_c = chol(C) (upper), inv_L_c                       :767-777
+//   WP    = sqrt(h) z                      (d normals, no uniform)         :990
+//   xi_n  = xi + h/2 C P                                                   :991
+//   g     = grad log-likelihood(xi_n)      (Analytical :573-623 | forward differences :1043-1088)
+//   P'    = hfm/hfp P + h/hfp g + sqrt(f0)/hfp inv_L_c WP                  :998-1000
+//   xi'   = xi_n + h/2 C P'                                                :1001
+// The reference initialises the window from its chain CSV re-read from disk (6-decimal text);
+// the kernel uses a Welford accumulation of the exact states instead (documented deviation).
+//
+// Mapping is the one of the MH kernel: G lanes per chain split the points, Q chains per thread share
+// every record read, records staged through shared memory (resident or streamed in tiles).  The state
+// (xi, P) stays in registers; the d x d preconditioner C, inv_L_c and the adaptation state live in global
+// memory, chain-minor, touched once per iteration.
+#pragma once
+#include "pbu_mh_kernel.cuh"
+
+namespace pbu {
+
+struct IsdeParams {
+    ProblemDev prob;
+    ChainState st;            // x = xi, P, R = packed upper inv_L_c, V = packed V_i / Welford M2, xav = X_av / Welford mean
+    StreamsDev streams;
+    pbu_run_outputs out;
+    double *Cmat;             // [d(d+1)/2][C] packed symmetric preconditioner C_approx per chain
+    int64_t it0, n_steps, thin, n_groups;
+    uint64_t seed, chain_offset;
+    double h, f0, S_d, eps_id;
+    int64_t starting_it, update_it, end_it;
+    int32_t tile_points;
+    int32_t fd_gradient;      // 1: forward differences with relative step 1e-10 (mha.py:726, :1069-1088)
+};
+
+// symmetric packed matrix (upper triangle stored) times vector, reading the matrix from global memory
+template <int D>
+__device__ __forceinline__ void symv_global(const double *gC, int64_t C, const double (&v)[D], double (&out)[D]) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const int a = (i <= j) ? i : j, b = (i <= j) ? j : i;
+            s = __dadd_rn(s, __dmul_rn(gC[(int64_t)tri_idx(D, a, b) * C], v[j]));     // np.matmul: plain dot product, no FMA
+        }
+        out[i] = s;
+    }
+}
+
+// inverse of an upper-triangular packed matrix by back substitution (oracle: inv_upper_plain)
+template <int D>
+__device__ __forceinline__ void inv_upper_packed(const double (&R)[tri_size(D)], double (&X)[tri_size(D)]) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        X[tri_idx(D, j, j)] = 1.0 / R[tri_idx(D, j, j)];
+#pragma unroll
+        for (int i = j - 1; i >= 0; --i) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = i + 1; k <= j; ++k) s += R[tri_idx(D, i, k)] * X[tri_idx(D, k, j)];
+            X[tri_idx(D, i, j)] = -s / R[tri_idx(D, i, i)];
+        }
+    }
+}
+
+// Gradient of the log-likelihood (and the log-posterior value) at x for the Q chains of a thread.
+template <class M, int D, int G, int Q>
+__device__ __forceinline__ void grad_log_like(const double (&x)[Q][D], const ProblemDev &prob, TileStream &ts, int sub, unsigned group_mask,
+                                              double (&grad)[Q][D], double (&lp)[Q]) {
+    constexpr int U = (M::UNROLL > 2) ? 2 : M::UNROLL;
+    constexpr int NP = M::NPARAM;
+    typename M::Ctx ctx[Q];
+    typename M::Seq seq[Q];
+    double J[Q][U], g[Q][M::HAS_GRAD ? NP : 1];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        begin_chain<M, D>(x[q], prob, ctx[q], seq[q]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) J[q][u] = 0.0;
+#pragma unroll
+        for (int j = 0; j < (M::HAS_GRAD ? NP : 1); ++j) g[q][j] = 0.0;
+    }
+    ts.begin_pass();
+    for (int t = 0; t < ts.n_tiles; ++t) {
+        int cnt;
+        const double *tile = ts.acquire(t, cnt);
+        tile_accumulate<M, G, Q, U, M::HAS_GRAD>(ctx, seq, tile, cnt, sub, J, g);
+        ts.release(t);
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        double Jq = 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) Jq += J[q][u];
+        Jq = group_sum<G>(Jq, group_mask) + prob.J_const;
+        lp[q] = inside_box<D>(x[q], prob) ? (prob.log_prior_const - 0.0) + (-0.5 * Jq) : -INFINITY;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            double gi = 0.0;
+            if constexpr (M::HAS_GRAD) {
+#pragma unroll
+                for (int j = 0; j < NP; ++j)
+                    if (D == NP ? (j == i) : (prob.unc_idx[i] == j)) gi = g[q][j];
+            }
+            grad[q][i] = group_sum<G>(gi, group_mask);
+        }
+    }
+}
+
+template <class M, int D, int G, int Q>
+__global__ void __launch_bounds__(MH_MAX_BLOCK, 1) isde_step_kernel(const __grid_constant__ IsdeParams p) {
+    constexpr int NT = tri_size(D);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TileStream ts;
+    ts.init(smem_raw, p.prob.records, p.prob.n_points, p.tile_points, M::NC);
+
+    const int64_t C = p.st.n_chains;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int sub = (int)(gtid % G);
+    const int lane = threadIdx.x & 31;
+    const unsigned group_mask = (G == 1) ? (1u << lane) : (((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(G - 1)));
+    const bool injected = p.streams.normals != nullptr;
+
+    int64_t c[Q];
+    bool live[Q];
+    double xi[Q][D], P[Q][D], lp[Q];
+    int32_t status[Q], n_eval[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        c[q] = gtid / G + (int64_t)q * p.n_groups;
+        live[q] = c[q] < C;
+        if (!live[q]) c[q] = C - 1;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            xi[q][i] = p.st.x[i * C + c[q]];
+            P[q][i] = p.st.P[i * C + c[q]];
+        }
+        lp[q] = p.st.lp[c[q]];
+        status[q] = p.st.status[c[q]];
+        n_eval[q] = 0;
+    }
+    const double hfm = 1.0 - p.h * p.f0 / 4.0, hfp = 1.0 + p.h * p.f0 / 4.0;      // :928-929
+    const double sqrt_h = sqrt(p.h), sqrt_f0 = sqrt(p.f0);
+
+    for (int64_t s = 0; s < p.n_steps; ++s) {
+        const int64_t it = p.it0 + s + 1;
+        double xn[Q][D], WP[Q][D];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int64_t cq = c[q];
+            double *const gC = p.Cmat + cq;
+            double *const gIL = p.st.R + cq;
+            double *const gV = p.st.V + cq;
+            double *const gxav = p.st.xav + cq;
+            // ---- adaptation of the preconditioner (:736-777); current_val = xi_nm (:958)
+            if (it <= p.starting_it) {
+                // Welford over rows 0..it-1 of the chain (the rows the reference re-reads from its CSV at :744)
+                const double inv_n = 1.0 / (double)it;
+                double dl[D], mu[D];
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    const double m = (it == 1) ? 0.0 : gxav[(int64_t)i * C];
+                    dl[i] = xi[q][i] - m;
+                    mu[i] = fma(dl[i], inv_n, m);
+                    if (live[q]) gxav[(int64_t)i * C] = mu[i];
+                }
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = i; j < D; ++j) {
+                        const int64_t o = (int64_t)tri_idx(D, i, j) * C;
+                        double v = fma(dl[i], xi[q][j] - mu[j], (it == 1) ? 0.0 : gV[o]);
+                        if (it == p.starting_it)        // V_i = S_d (cov + eps I), np.cov with ddof = 1   (:745-746)
+                            v = p.S_d * (v / (double)(it - 1) + ((i == j) ? p.eps_id : 0.0));
+                        if (live[q]) gV[o] = v;
+                    }
+            } else if (it <= p.end_it) {
+                const double fi = (double)it;
+                double xa[D], xb[D];
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    xa[i] = gxav[(int64_t)i * C];
+                    xb[i] = __dadd_rn(xi[q][i], __dmul_rn(fi / (fi + 1.0), __dadd_rn(xa[i], -xi[q][i])));      // :752
+                }
+                const double c1 = (fi - 1.0) / fi, c2 = p.S_d / fi;
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = i; j < D; ++j) {
+                        double t = __dadd_rn(__dmul_rn(fi, __dmul_rn(xa[i], xa[j])), -__dmul_rn(fi + 1.0, __dmul_rn(xb[i], xb[j])));
+                        t = __dadd_rn(t, __dmul_rn(xi[q][i], xi[q][j]));
+                        t = __dadd_rn(t, (i == j) ? p.eps_id : 0.0);
+                        const int64_t o = (int64_t)tri_idx(D, i, j) * C;
+                        const double v = __dadd_rn(__dmul_rn(c1, gV[o]), __dmul_rn(c2, t));                       // :753
+                        if (live[q]) gV[o] = v;
+                    }
+                if (live[q]) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) gxav[(int64_t)i * C] = xb[i];
+                }
+            }
+            if (it >= p.starting_it && it <= p.end_it + 1 && (it % p.update_it == 0)) {                         // :767-777
+                double Vc[NT], Lc[NT], IL[NT];
+#pragma unroll
+                for (int i = 0; i < NT; ++i) Vc[i] = gV[(int64_t)i * C];
+                if (chol_upper_packed<D>(Vc, Lc)) {
+                    inv_upper_packed<D>(Lc, IL);
+                    if (live[q]) {
+#pragma unroll
+                        for (int i = 0; i < NT; ++i) {
+                            gC[(int64_t)i * C] = Vc[i];
+                            gIL[(int64_t)i * C] = IL[i];
+                        }
+                    }
+                } else {
+                    status[q] |= ST_NOT_PD;
+                }
+            }
+
+            // ---- first half step (:990-991)
+            double z[D], udummy;
+            if (injected) {
+                if (!draw_injected<D, false>(p.streams, cq, live[q] && sub == 0, group_mask, z, udummy)) status[q] |= ST_STREAM_EXHAUSTED;
+            } else {
+                draw_philox<D>(p.seed, p.chain_offset + (uint64_t)cq, (uint64_t)it, 0u, z, udummy);
+            }
+            double CP[D];
+            symv_global<D>(gC, C, P[q], CP);
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                WP[q][i] = __dmul_rn(sqrt_h, z[i]);
+                xn[q][i] = __dadd_rn(xi[q][i], __dmul_rn(p.h / 2.0, CP[i]));
+            }
+        }
+
+        // ---- gradient at xi_n (:994)
+        double grad[Q][D], lpn[Q];
+        if (!p.fd_gradient) {
+            grad_log_like<M, D, G, Q>(xn, p.prob, ts, sub, group_mask, grad, lpn);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) n_eval[q] += 1;
+        } else {
+            // computeGradientFD, forward scheme on the log-POSTERIOR (:1069-1088): d + 1 evaluations
+            bool want[Q];
+            double f0v[Q], fp[Q], xp[Q][D];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) want[q] = true;
+            log_posterior<M, D, G, Q>(xn, want, p.prob, ts, sub, group_mask, f0v);
+#pragma unroll 1
+            for (int i = 0; i < D; ++i) {
+                double delta[Q];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) xp[q][j] = xn[q][j];
+                    double xv = 0.0;
+#pragma unroll
+                    for (int j = 0; j < D; ++j)
+                        if (j == i) xv = xn[q][j];
+                    delta[q] = __dmul_rn(xv, 1e-10);
+                    if (delta[q] == 0.0) delta[q] = 1e-10;
+#pragma unroll
+                    for (int j = 0; j < D; ++j)
+                        if (j == i) xp[q][j] = __dadd_rn(xv, delta[q]);
+                }
+                log_posterior<M, D, G, Q>(xp, want, p.prob, ts, sub, group_mask, fp);
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const double gi = (fp[q] - f0v[q]) / delta[q];
+#pragma unroll
+                    for (int j = 0; j < D; ++j)
+                        if (j == i) grad[q][j] = gi;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                lpn[q] = f0v[q];
+                n_eval[q] += D + 1;
+            }
+        }
+
+        // ---- momentum and second half step (:998-1001)
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int64_t cq = c[q];
+            const double *const gC = p.Cmat + cq;
+            const double *const gIL = p.st.R + cq;
+            double Pn[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                double lw = 0.0;                                   // (inv_L_c @ WP)_i, inv_L_c upper triangular
+#pragma unroll
+                for (int j = i; j < D; ++j) lw = __dadd_rn(lw, __dmul_rn(gIL[(int64_t)tri_idx(D, i, j) * C], WP[q][j]));
+                const double a = __dmul_rn(hfm / hfp, P[q][i]);
+                const double b = __dmul_rn(p.h / hfp, grad[q][i]);        // h/hfp * (-grad_phi), grad_phi = -grad
+                const double cc = __dmul_rn(sqrt_f0 / hfp, lw);
+                Pn[i] = __dadd_rn(__dadd_rn(a, b), cc);
+            }
+            double CP[D];
+            symv_global<D>(gC, C, Pn, CP);
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                xi[q][i] = __dadd_rn(xn[q][i], __dmul_rn(p.h / 2.0, CP[i]));
+                P[q][i] = Pn[i];
+            }
+            lp[q] = lpn[q];            // log-posterior at xi_n (the point the model was evaluated at)
+
+            if (live[q] && sub == 0) {
+                if (p.out.trace_lp1) p.out.trace_lp1[s * C + cq] = lpn[q];
+                if (it % p.thin == 0) {
+                    {
+                        const int64_t wc = p.st.wcount[cq] + 1;
+                        p.st.wcount[cq] = wc;
+                        const double inv_n = 1.0 / (double)wc;
+                        double dl[D], mu[D];
+#pragma unroll
+                        for (int i = 0; i < D; ++i) {
+                            const double m = p.st.wmean[i * C + cq];
+                            dl[i] = xi[q][i] - m;
+                            mu[i] = fma(dl[i], inv_n, m);
+                            p.st.wmean[i * C + cq] = mu[i];
+                        }
+#pragma unroll
+                        for (int i = 0; i < D; ++i)
+#pragma unroll
+                            for (int j = i; j < D; ++j) {
+                                double *w2 = &p.st.wM2[tri_idx(D, i, j) * C + cq];
+                                *w2 = fma(dl[i], xi[q][j] - mu[j], *w2);
+                            }
+                    }
+                    const int64_t row = it / p.thin - p.it0 / p.thin - 1;
+                    if (p.out.samples) {
+#pragma unroll
+                        for (int i = 0; i < D; ++i) p.out.samples[(row * D + i) * C + cq] = xi[q][i];
+                    }
+                    if (p.out.lp_kept) p.out.lp_kept[row * C + cq] = lp[q];
+                }
+            }
+        }
+    }
+
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        if (live[q] && sub == 0) {
+            const int64_t cq = c[q];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                p.st.x[i * C + cq] = xi[q][i];
+                p.st.P[i * C + cq] = P[q][i];
+            }
+            p.st.lp[cq] = lp[q];
+            p.st.n_eval[cq] += n_eval[q];
+            p.st.status[cq] = status[q];
+        }
+    }
+}
+
+}  // namespace pbu

@@ -30,25 +30,86 @@ namespace pbu {
 constexpr int MH_MAX_BLOCK = 512;
 
 // ------------------------------------------------------------------------------------------------
-// Stage `bytes` (multiple of 16) from global into shared memory with bulk TMA copies; all threads
-// of the block return once the data has landed.
+// Shared-memory staging of the point records with bulk TMA copies (cp.async.bulk + mbarrier).
+//   resident  : every record fits in shared memory; loaded once per launch, read by all chains of the
+//               block for all iterations, no synchronisation after the first wait;
+//   streaming : the records are cut into tiles that cycle through a ring of S slots once per posterior
+//               evaluation ("pass").  All threads of the block walk the tiles together: wait for the
+//               tile to land, use it, __syncthreads, then thread 0 refills the slot with the tile S
+//               ahead, so the copy of tile t+1.. overlaps the arithmetic on tile t.  Global traffic is
+//               one read of the records per block and pass, served by L2 (the record set is shared by
+//               every block of every launch).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stage_records(double *smem_rec, uint64_t *bar, const double *gsrc, uint32_t bytes) {
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+struct TileStream {
+    static constexpr int S = 2;          // ring slots
+    const char *gsrc;                    // records in global memory
+    char *buf;                           // S slots of slot_bytes each
+    uint64_t *full;                      // S mbarriers
+    uint32_t rec_bytes;                  // bytes per record
+    uint32_t slot_bytes;
+    int n_points, tile_points, n_tiles;
+    uint32_t tseq;                       // tiles consumed so far by this block (selects slot and mbarrier phase)
+    bool resident;
+
+    __device__ __forceinline__ void issue(int tile, uint32_t slot) {
+        const int first = tile * tile_points;
+        const int cnt = (n_points - first < tile_points) ? (n_points - first) : tile_points;
+        const uint32_t bytes = (uint32_t)cnt * rec_bytes;
+        uint64_t *bar = full + slot;
         mbar_expect_tx(bar, bytes);
         const uint32_t CH = 32768u;
         for (uint32_t off = 0; off < bytes; off += CH) {
             const uint32_t n = (bytes - off < CH) ? (bytes - off) : CH;
-            tma_load_1d(reinterpret_cast<char *>(smem_rec) + off, reinterpret_cast<const char *>(gsrc) + off, n, bar);
+            tma_load_1d(buf + (size_t)slot * slot_bytes + off, gsrc + (size_t)first * rec_bytes + off, n, bar);
         }
     }
-    mbar_wait(bar, 0);
-}
+    // smem layout: [S mbarriers, padded to 128 B][slot 0][slot 1]...
+    __device__ __forceinline__ void init(unsigned char *smem, const double *records, int n, int tile_pts, int ncol) {
+        full = reinterpret_cast<uint64_t *>(smem);
+        buf = reinterpret_cast<char *>(smem + 128);
+        gsrc = reinterpret_cast<const char *>(records);
+        rec_bytes = (uint32_t)ncol * 8u;
+        n_points = n;
+        tile_points = tile_pts;
+        n_tiles = (n + tile_pts - 1) / tile_pts;
+        resident = (n_tiles == 1);
+        slot_bytes = (uint32_t)tile_pts * rec_bytes;
+        tseq = 0;
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < S; ++i) mbar_init(full + i, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (resident) {
+            if (threadIdx.x == 0) issue(0, 0);
+            mbar_wait(full, 0);
+        }
+    }
+    __device__ __forceinline__ void begin_pass() {
+        if (resident) return;
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < S && i < n_tiles; ++i) issue(i, (tseq + i) % S);
+        }
+    }
+    // points of tile t of the current pass; blocks until the tile has landed
+    __device__ __forceinline__ const double *acquire(int t, int &count) {
+        if (resident) {
+            count = n_points;
+            return reinterpret_cast<const double *>(buf);
+        }
+        const uint32_t slot = tseq % S;
+        mbar_wait(full + slot, (tseq / S) & 1u);
+        const int first = t * tile_points;
+        count = (n_points - first < tile_points) ? (n_points - first) : tile_points;
+        return reinterpret_cast<const double *>(buf + (size_t)slot * slot_bytes);
+    }
+    __device__ __forceinline__ void release(int t) {
+        if (resident) return;
+        __syncthreads();                                    // every thread is done with the slot
+        if (threadIdx.x == 0 && t + S < n_tiles) issue(t + S, tseq % S);
+        tseq += 1;
+    }
+};
 
 template <int NC>
 __device__ __forceinline__ void load_record(const double *smem_rec, int k, double (&rec)[NC]) {
@@ -167,11 +228,11 @@ __device__ __forceinline__ void begin_chain(const double (&x)[D], const ProblemD
 
 // BayesianPosterior.compute_log_value (bayesian_inference.py:44-64) with the identity
 // parametrisation, for the Q chains of a thread: -inf outside the prior box WITHOUT evaluating the
-// model (:53-55), otherwise log_prior - log(1) + (-(1/2) J).  Resident mode: all records are in
-// shared memory.  The data pass is skipped when no chain of the thread needs it.
+// model (:53-55), otherwise log_prior - log(1) + (-(1/2) J).  In resident mode the data pass is skipped
+// when no chain of the thread needs it.
 template <class M, int D, int G, int Q>
-__device__ __forceinline__ void log_posterior(const double (&x)[Q][D], const bool (&want)[Q], const ProblemDev &prob, const double *smem_rec,
-                                              int sub, unsigned group_mask, double (&lp)[Q]) {
+__device__ __forceinline__ void log_posterior(const double (&x)[Q][D], const bool (&want)[Q], const ProblemDev &prob, TileStream &ts, int sub,
+                                              unsigned group_mask, double (&lp)[Q]) {
     constexpr int U = M::UNROLL;   // tools/ubench: U = 4 points x Q = 2 chains in flight reaches 83% of the DFMA peak at 12 warps/SM
     bool inb[Q], any = false;
 #pragma unroll
@@ -180,7 +241,7 @@ __device__ __forceinline__ void log_posterior(const double (&x)[Q][D], const boo
         any = any || inb[q];
         lp[q] = -INFINITY;
     }
-    if (!any) return;
+    if (ts.resident && !any) return;      // streaming: the whole block walks the tiles together
     typename M::Ctx ctx[Q];
     typename M::Seq seq[Q];
     double J[Q][U], gdummy[Q][1];
@@ -190,7 +251,13 @@ __device__ __forceinline__ void log_posterior(const double (&x)[Q][D], const boo
 #pragma unroll
         for (int u = 0; u < U; ++u) J[q][u] = 0.0;
     }
-    tile_accumulate<M, G, Q, U, false>(ctx, seq, smem_rec, prob.n_points, sub, J, gdummy);
+    ts.begin_pass();
+    for (int t = 0; t < ts.n_tiles; ++t) {
+        int cnt;
+        const double *tile = ts.acquire(t, cnt);
+        if (any) tile_accumulate<M, G, Q, U, false>(ctx, seq, tile, cnt, sub, J, gdummy);
+        ts.release(t);
+    }
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
         double Jq = 0.0;
@@ -233,19 +300,19 @@ __device__ __forceinline__ void draw_philox(uint64_t seed, uint64_t chain, uint6
 
 // Parity mode: the chain's next D normals and one uniform from the injected streams; the cursors live
 // in global memory (every lane of a group reads them, the writer lane advances them after the draw).
-template <int D>
+template <int D, bool UNIFORM = true>
 __device__ __forceinline__ bool draw_injected(const StreamsDev &s, int64_t c, bool advance, unsigned group_mask, double (&z)[D], double &u) {
     const int64_t cn = s.cur_n[c], cu = s.cur_u[c];
     __syncwarp(group_mask);
-    const bool ok = !(cn + D > s.n_normals || cu + 1 > s.n_uniforms);
+    const bool ok = !(cn + D > s.n_normals || (UNIFORM && cu + 1 > s.n_uniforms));
     if (ok) {
         const double *zn = s.normals + c * s.n_normals + cn;
 #pragma unroll
         for (int i = 0; i < D; ++i) z[i] = zn[i];
-        u = s.uniforms[c * s.n_uniforms + cu];
+        u = UNIFORM ? s.uniforms[c * s.n_uniforms + cu] : 1.0;
         if (advance) {
             s.cur_n[c] = cn + D;
-            s.cur_u[c] = cu + 1;
+            if (UNIFORM) s.cur_u[c] = cu + 1;
         }
     } else {
 #pragma unroll
@@ -266,10 +333,8 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_c
     constexpr bool DELAYED = (ALGO & 2) != 0;
     constexpr int NT = tri_size(D);
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    double *smem_rec = reinterpret_cast<double *>(smem_raw + 128);
-
-    stage_records(smem_rec, bar, p.prob.records, (uint32_t)p.prob.n_points * (uint32_t)(M::NC * 8));
+    TileStream ts;
+    ts.init(smem_raw, p.prob.records, p.prob.n_points, p.tile_points, M::NC);
 
     const int64_t C = p.st.n_chains;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -339,7 +404,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_c
                 }
                 n_eval[q] += 1;
             }
-            log_posterior<M, D, G, Q>(y, want, p.prob, smem_rec, sub, group_mask, lpy);
+            log_posterior<M, D, G, Q>(y, want, p.prob, ts, sub, group_mask, lpy);
             bool again = false;
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
@@ -392,6 +457,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_c
                     want[q] = false;
                 }
             }
+            if (!ts.resident) again = __syncthreads_or(again) != 0;     // streaming: the block walks the tiles together
             if (!again) break;
         }
 
@@ -534,43 +600,48 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_c
 // ------------------------------------------------------------------------------------------------
 template <class M, int D>
 __global__ void __launch_bounds__(256) eval_logpost_kernel(const __grid_constant__ ProblemDev prob, const double *X /*[d][S]*/, int64_t S,
-                                                           double *lp_out) {
+                                                           double *lp_out, int tile_points) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    double *smem_rec = reinterpret_cast<double *>(smem_raw + 128);
-    stage_records(smem_rec, bar, prob.records, (uint32_t)prob.n_points * (uint32_t)(M::NC * 8));
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= S) return;
+    TileStream ts;
+    ts.init(smem_raw, prob.records, prob.n_points, tile_points, M::NC);
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool livet = t < S;
+    if (!livet) t = S - 1;                  // all threads of the block walk the tiles together
     double x[1][D], lp[1];
-    const bool want[1] = {true};
+    const bool want[1] = {livet};
 #pragma unroll
     for (int i = 0; i < D; ++i) x[0][i] = X[i * S + t];
-    log_posterior<M, D, 1, 1>(x, want, prob, smem_rec, 0, 1u << (threadIdx.x & 31), lp);
-    lp_out[t] = lp[0];
+    log_posterior<M, D, 1, 1>(x, want, prob, ts, 0, 1u << (threadIdx.x & 31), lp);
+    if (livet) lp_out[t] = lp[0];
 }
 
 // Model.run_model for S parameter vectors: f_out[k][s] (point-major, coalesced over samples).
 template <class M, int D>
 __global__ void __launch_bounds__(256) eval_model_kernel(const __grid_constant__ ProblemDev prob, const double *X /*[d][S]*/, int64_t S,
-                                                         double *f_out) {
+                                                         double *f_out, int tile_points) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    double *smem_raw_rec = reinterpret_cast<double *>(smem_raw + 128);
-    stage_records(smem_raw_rec, bar, prob.raw, (uint32_t)prob.n_points * (uint32_t)(M::NCR * 8));
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= S) return;
-    double x[D], theta[M::NPARAM];
+    TileStream ts;
+    ts.init(smem_raw, prob.raw, prob.n_points, tile_points, M::NCR);
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool livet = t < S;
+    if (!livet) t = S - 1;
+    double x[D];
 #pragma unroll
     for (int i = 0; i < D; ++i) x[i] = X[i * S + t];
-    full_theta<M, D>(x, prob, theta);
     typename M::Ctx ctx;
-    M::begin(ctx, theta, prob);
     typename M::Seq seq;
-    M::seq_init(ctx, seq, prob);
-    for (int k = 0; k < prob.n_points; ++k) {
-        double raw[M::NCR];
-        load_record<M::NCR>(smem_raw_rec, k, raw);
-        f_out[(int64_t)k * S + t] = M::value(ctx, seq, raw);
+    begin_chain<M, D>(x, prob, ctx, seq);
+    ts.begin_pass();
+    for (int tl = 0; tl < ts.n_tiles; ++tl) {
+        int cnt;
+        const double *tile = ts.acquire(tl, cnt);
+        for (int k = 0; k < cnt; ++k) {
+            double raw[M::NCR];
+            load_record<M::NCR>(tile, k, raw);
+            const double f = M::value(ctx, seq, raw);
+            if (livet) f_out[(int64_t)(tl * ts.tile_points + k) * S + t] = f;
+        }
+        ts.release(tl);
     }
 }
 

@@ -15,6 +15,7 @@ const pbu::MhKernelEntry *pbu_mh_kernels(int *n) {
         append(v, pbu_mh_slice_linear_a);
         append(v, pbu_mh_slice_linear_b);
         append(v, pbu_mh_slice_linear_c);
+        append(v, pbu_mh_slice_linear_d);
         append(v, pbu_mh_slice_poly_a);
         append(v, pbu_mh_slice_poly_b);
         append(v, pbu_mh_slice_arrhenius);
@@ -31,10 +32,28 @@ const pbu::EvalKernelEntry *pbu_eval_kernels(int *n) {
         append(v, pbu_eval_slice_linear_a);
         append(v, pbu_eval_slice_linear_b);
         append(v, pbu_eval_slice_linear_c);
+        append(v, pbu_eval_slice_linear_d);
         append(v, pbu_eval_slice_poly_a);
         append(v, pbu_eval_slice_poly_b);
         append(v, pbu_eval_slice_arrhenius);
         append(v, pbu_eval_slice_heat);
+        return v;
+    }();
+    *n = (int)all.size();
+    return all.data();
+}
+
+const pbu::IsdeKernelEntry *pbu_isde_kernels(int *n) {
+    static const std::vector<pbu::IsdeKernelEntry> all = [] {
+        std::vector<pbu::IsdeKernelEntry> v;
+        append(v, pbu_isde_slice_linear_a);
+        append(v, pbu_isde_slice_linear_b);
+        append(v, pbu_isde_slice_linear_c);
+        append(v, pbu_isde_slice_linear_d);
+        append(v, pbu_isde_slice_poly_a);
+        append(v, pbu_isde_slice_poly_b);
+        append(v, pbu_isde_slice_arrhenius);
+        append(v, pbu_isde_slice_heat);
         return v;
     }();
     *n = (int)all.size();

@@ -8,6 +8,10 @@ struct MhKernelEntry {
     int model, n_param, n_unc, lanes, chains_per_thread, algo;   // algo = pbu_algo_id (RWMH, AM, DR, DRAM)
     const void *fn;   // __global__ void (*)(const MhParams)
 };
+struct IsdeKernelEntry {
+    int model, n_param, n_unc, lanes, chains_per_thread, has_grad;
+    const void *fn;   // __global__ void (*)(const IsdeParams)
+};
 struct EvalKernelEntry {
     int model, n_param, n_unc, sequential;
     int nc, ncr;              // doubles per likelihood / raw record (Model::NC, Model::NCR)
@@ -20,14 +24,17 @@ struct EvalKernelEntry {
 
 const pbu::MhKernelEntry *pbu_mh_kernels(int *n);
 const pbu::EvalKernelEntry *pbu_eval_kernels(int *n);
+const pbu::IsdeKernelEntry *pbu_isde_kernels(int *n);
 
 // slices
 #define PBU_DECLARE_SLICE(name)                                     \
     const pbu::MhKernelEntry *pbu_mh_slice_##name(int *n);          \
-    const pbu::EvalKernelEntry *pbu_eval_slice_##name(int *n);
+    const pbu::EvalKernelEntry *pbu_eval_slice_##name(int *n);      \
+    const pbu::IsdeKernelEntry *pbu_isde_slice_##name(int *n);
 PBU_DECLARE_SLICE(linear_a)
 PBU_DECLARE_SLICE(linear_b)
 PBU_DECLARE_SLICE(linear_c)
+PBU_DECLARE_SLICE(linear_d)
 PBU_DECLARE_SLICE(poly_a)
 PBU_DECLARE_SLICE(poly_b)
 PBU_DECLARE_SLICE(arrhenius)

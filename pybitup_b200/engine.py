@@ -109,6 +109,7 @@ class SamplerConfig:
     lanes_per_chain: int = 0
     block_threads: int = 0
     chains_per_thread: int = 0
+    tile_points: int = 0
     seed: int = 0
     chain_offset: int = 0
 
@@ -124,6 +125,7 @@ class SamplerConfig:
         s.am_welford, s.nan_rejects = int(self.am_welford), int(self.nan_rejects)
         s.lanes_per_chain, s.block_threads = int(self.lanes_per_chain), int(self.block_threads)
         s.chains_per_thread = int(self.chains_per_thread)
+        s.tile_points = int(self.tile_points)
         s.seed, s.chain_offset = int(self.seed) & (2 ** 64 - 1), int(self.chain_offset)
         return s
 
@@ -202,14 +204,21 @@ class ChainEngine:
         if normals is None:
             capi.check(capi.lib.pbu_engine_set_streams(self._h, None, 0, None, 0))
             return
-        nz, un = _f64(normals), _f64(uniforms)
+        nz = _f64(normals)
         if nz.ndim == 1:
             nz = nz[None, :]
+        if nz.shape[0] != self.n_chains:
+            raise ValueError("streams need one row per chain")
+        nz = np.ascontiguousarray(nz)
+        if uniforms is None:          # the Ito-SDE sampler draws normals only
+            capi.check(capi.lib.pbu_engine_set_streams(self._h, capi.dptr(nz), nz.shape[1], None, 0))
+            return
+        un = _f64(uniforms)
         if un.ndim == 1:
             un = un[None, :]
-        if nz.shape[0] != self.n_chains or un.shape[0] != self.n_chains:
+        if un.shape[0] != self.n_chains:
             raise ValueError("streams need one row per chain")
-        nz, un = np.ascontiguousarray(nz), np.ascontiguousarray(un)
+        un = np.ascontiguousarray(un)
         capi.check(capi.lib.pbu_engine_set_streams(self._h, capi.dptr(nz), nz.shape[1], capi.dptr(un), un.shape[1]))
 
     @property
@@ -273,6 +282,12 @@ class ChainEngine:
         xav = np.empty((self.n_chains, self.d))
         capi.check(capi.lib.pbu_engine_get_proposal(self._h, capi.dptr(R), capi.dptr(V), capi.dptr(xav)))
         return dict(R=R, V=V, X_av=xav)
+
+    def isde_state(self):
+        P = np.empty((self.n_chains, self.d))
+        Cm = np.empty((self.n_chains, self.d, self.d))
+        capi.check(capi.lib.pbu_engine_get_isde_state(self._h, capi.dptr(P), capi.dptr(Cm)))
+        return dict(P=P, C=Cm)
 
     # -- evaluation only ----------------------------------------------------------------------
     def log_posterior(self, X):
