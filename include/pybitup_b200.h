@@ -177,6 +177,32 @@ int pbu_engine_get_launch(const pbu_engine *e, int32_t *lanes, int32_t *chains_p
 int pbu_eval_logpost(pbu_engine *e, const double *X_host /*[S][d]*/, int64_t S, double *lp_host /*[S]*/);
 int pbu_eval_model(pbu_engine *e, const double *X_host /*[S][d]*/, int64_t S, double *f_host /*[S][N]*/);
 
+/* ---- Monte-Carlo propagation: replaces the sample loop of Propagation.propagate, emulator == "None"
+ *      (solve_problem.py:543-576) and its statistics (:596-647).  The evaluations stay in device memory,
+ *      point-major; mean / min / max and EXACT order statistics (for np.percentile, :643-645) are reduced on the
+ *      device.  With samples sharded over GPUs the caller sums the moment and histogram outputs over ranks
+ *      (one small all-reduce per call), which replaces the reference's MPI send of every evaluation (:578-592). */
+typedef struct pbu_propagation pbu_propagation;
+int pbu_propagation_create(pbu_engine *e, int64_t n_samples, pbu_propagation **out);
+int pbu_propagation_destroy(pbu_propagation *p);
+/* evaluate run_model for X host [S][d] (solve_problem.py:559-571) */
+int pbu_propagation_eval_host(pbu_propagation *p, const double *X_host);
+/* same with rows drawn on the device from N(mean, diag(std^2)); Philox keyed by (seed, sample_offset + row) */
+int pbu_propagation_eval_gaussian(pbu_propagation *p, const double *mean_host /*[d]*/, const double *std_host /*[d]*/,
+                                  uint64_t seed, uint64_t sample_offset);
+/* device pointers: samples [d][S] and evaluations [N][S] */
+int pbu_propagation_buffers(pbu_propagation *p, double **X_dev, double **f_dev);
+/* per design point sum, min, max over this engine's samples, host [N] each (:607-627) */
+int pbu_propagation_moments(pbu_propagation *p, double *sum_host, double *min_host, double *max_host);
+/* exact order statistics by radix select.  ranks host [n_ranks] (<= 4): 0-based ranks in the sorted GLOBAL sample.
+ * For pass = 0..7: select_pass -> hist_host [N][n_ranks][256] (this engine's counts); sum over GPUs; select_update. */
+int pbu_propagation_select_begin(pbu_propagation *p, const int64_t *ranks, int n_ranks);
+int pbu_propagation_select_pass(pbu_propagation *p, int pass, uint64_t *hist_host);
+int pbu_propagation_select_update(pbu_propagation *p, int pass, const uint64_t *hist_total_host);
+int pbu_propagation_select_result(pbu_propagation *p, double *values_host /*[N][n_ranks]*/);
+/* evaluations of samples [s0, s0+n) on the host, sample-major [n][N] (fun_eval, :571) */
+int pbu_propagation_get_evals(pbu_propagation *p, int64_t s0, int64_t n, double *f_host);
+
 /* ---- measurement helper: achieved FP64 FMA throughput of the device (TFLOP/s, FMA = 2 flops) from a
  *      register-resident DFMA loop; the denominator of the FP64 roofline in bench.py ------------- */
 int pbu_measure_fp64_peak(int device, int iters, int reps, double *tflops, double *ms);

@@ -91,6 +91,17 @@ def _load():
         "pbu_engine_get_launch": (C.c_int, [E, _ip, _ip, _ip, _ip, _lp]),
         "pbu_eval_logpost": (C.c_int, [E, _dp, C.c_int64, _dp]),
         "pbu_eval_model": (C.c_int, [E, _dp, C.c_int64, _dp]),
+        "pbu_propagation_create": (C.c_int, [E, C.c_int64, C.POINTER(E)]),
+        "pbu_propagation_destroy": (C.c_int, [E]),
+        "pbu_propagation_eval_host": (C.c_int, [E, _dp]),
+        "pbu_propagation_eval_gaussian": (C.c_int, [E, _dp, _dp, C.c_uint64, C.c_uint64]),
+        "pbu_propagation_buffers": (C.c_int, [E, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+        "pbu_propagation_moments": (C.c_int, [E, _dp, _dp, _dp]),
+        "pbu_propagation_select_begin": (C.c_int, [E, _lp, C.c_int]),
+        "pbu_propagation_select_pass": (C.c_int, [E, C.c_int, C.POINTER(C.c_uint64)]),
+        "pbu_propagation_select_update": (C.c_int, [E, C.c_int, C.POINTER(C.c_uint64)]),
+        "pbu_propagation_select_result": (C.c_int, [E, _dp]),
+        "pbu_propagation_get_evals": (C.c_int, [E, C.c_int64, C.c_int64, _dp]),
         "pbu_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp]),
     }
     for name, (res, args) in sig.items():

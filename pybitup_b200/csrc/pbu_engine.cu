@@ -13,10 +13,11 @@
 
 using namespace pbu;
 
-// ------------------------------------------------------------------------------------------------
+#include "pbu_engine_internal.h"
+
 static thread_local std::string g_last_error;
 
-static int fail(int code, const char *fmt, ...) {
+int pbu_fail(int code, const char *fmt, ...) {
     char buf[1024];
     va_list ap;
     va_start(ap, fmt);
@@ -25,46 +26,6 @@ static int fail(int code, const char *fmt, ...) {
     g_last_error = buf;
     return code;
 }
-
-#define CUDA_TRY(expr)                                                                                   \
-    do {                                                                                                 \
-        cudaError_t _e = (expr);                                                                         \
-        if (_e != cudaSuccess)                                                                           \
-            return fail(PBU_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
-    } while (0)
-
-// ------------------------------------------------------------------------------------------------
-struct pbu_engine {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    pbu_sampler_cfg cfg{};
-    ProblemDev prob{};
-    int d = 0, P = 0, nt = 0;
-    int64_t C = 0;
-    int64_t iteration = 0;
-    bool initialised = false;
-    const MhKernelEntry *mh = nullptr;
-    const IsdeKernelEntry *isde = nullptr;
-    const void *step_fn = nullptr;   // the planned step kernel (mh->fn or isde->fn)
-    int tile_points = 0;          // points per shared-memory tile of the likelihood records (= n_points when resident)
-    int tile_points_raw = 0;      // same for the raw records
-    double *d_Cmat = nullptr;     // ISDE: packed symmetric preconditioner per chain
-    const EvalKernelEntry *ev = nullptr;
-    int lanes = 1;
-    int q = 1;                    // chains per thread
-    int block = 128;
-    int grid = 1;
-    size_t smem_bytes = 0;        // step / log-posterior kernels: barrier + likelihood records
-    size_t smem_raw_bytes = 0;    // model-evaluation kernel: barrier + raw records
-    std::vector<double> R0;       // packed upper Cholesky factor of the shared proposal covariance
-    // device allocations
-    double *d_records = nullptr;
-    double *d_raw = nullptr;
-    ChainState st{};
-    StreamsDev streams{};
-    double *d_normals = nullptr, *d_uniforms = nullptr;
-    std::vector<void *> allocs;
-};
 
 template <class T>
 static int dev_alloc(pbu_engine *e, T **p, size_t n) {

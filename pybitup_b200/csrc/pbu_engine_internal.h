@@ -1,0 +1,53 @@
+// Internals shared by the host-side translation units of the C ABI (not installed).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "pbu_isde_kernel.cuh"
+#include "pbu_registry.h"
+
+// records the message returned by pbu_last_error() on this thread and returns `code`
+int pbu_fail(int code, const char *fmt, ...);
+#define fail pbu_fail
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return pbu_fail(PBU_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define PBU_API extern "C" __attribute__((visibility("default")))
+
+struct pbu_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    pbu_sampler_cfg cfg{};
+    pbu::ProblemDev prob{};
+    int d = 0, P = 0, nt = 0;
+    int64_t C = 0;
+    int64_t iteration = 0;
+    bool initialised = false;
+    const pbu::MhKernelEntry *mh = nullptr;
+    const pbu::IsdeKernelEntry *isde = nullptr;
+    const void *step_fn = nullptr;   // the planned step kernel (mh->fn or isde->fn)
+    int tile_points = 0;          // points per shared-memory tile of the likelihood records (= n_points when resident)
+    int tile_points_raw = 0;      // same for the raw records
+    double *d_Cmat = nullptr;     // ISDE: packed symmetric preconditioner per chain
+    const pbu::EvalKernelEntry *ev = nullptr;
+    int lanes = 1;
+    int q = 1;                    // chains per thread
+    int block = 128;
+    int grid = 1;
+    size_t smem_bytes = 0;        // step / log-posterior kernels: barrier + likelihood records
+    size_t smem_raw_bytes = 0;    // model-evaluation kernel: barrier + raw records
+    std::vector<double> R0;       // packed upper Cholesky factor of the shared proposal covariance
+    // device allocations
+    double *d_records = nullptr;
+    double *d_raw = nullptr;
+    pbu::ChainState st{};
+    pbu::StreamsDev streams{};
+    double *d_normals = nullptr, *d_uniforms = nullptr;
+    std::vector<void *> allocs;
+};
+

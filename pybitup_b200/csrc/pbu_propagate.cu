@@ -1,0 +1,337 @@
+// K3: Monte-Carlo uncertainty propagation (Propagation.propagate, emulator == "None",
+// solve_problem.py:467-647): evaluate the forward model at S parameter vectors with the same device model
+// functions the samplers use, keep the evaluations in HBM point-major, and reduce per design point
+//   mean, min, max                      (:596-627, written to <id>_interval.csv :629-637)
+//   two percentiles (2.5 / 97.5)        (np.percentile over all evaluations, :639-645, <id>_CI.csv)
+// The percentiles are EXACT order statistics found by an 8-pass most-significant-digit radix select over the
+// HBM-resident evaluations: each pass builds, per design point and per wanted rank, a 256-bin histogram of the next
+// byte of the order-preserving 64-bit key among the values that match the prefix found so far.  The histograms
+// (and the moment partials) are the only thing that has to be summed over GPUs when samples are sharded
+// (one small all-reduce per pass, done by the host layer), replacing the reference's pickled MPI send of every
+// evaluation to rank 0 (:578-592).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "pbu_engine_internal.h"
+
+using namespace pbu;
+
+struct pbu_propagation {
+    pbu_engine *e = nullptr;
+    int64_t S = 0;
+    int N = 0;
+    double *d_X = nullptr;       // [d][S] parameter vectors (structure of arrays)
+    double *d_f = nullptr;       // [N][S] model evaluations, point-major
+    double *d_part = nullptr;    // [N][NSPLIT][3] moment partials
+    // radix select state
+    int T = 0;                   // wanted ranks per design point
+    unsigned long long *d_prefix = nullptr;   // [N][T] key prefix found so far
+    long long *d_rank = nullptr;              // [N][T] remaining rank inside the prefix class
+    unsigned long long *d_hist = nullptr;     // [N][T][256]
+    bool evaluated = false;
+};
+
+static constexpr int NSPLIT = 16;
+static constexpr int MAX_T = 4;
+
+// ------------------------------------------------------------------------------------------------ kernels
+// rows of N(mean, diag(std^2)) by Philox: X[i][s] = mean_i + std_i z(seed, sample_offset + s, i)
+__global__ void gaussian_samples_kernel(double *X, int64_t S, int d, const double *mean, const double *stdv, uint64_t seed, uint64_t sample_offset) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const uint64_t g = sample_offset + (uint64_t)s;
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    for (int b = 0; b * 4 < d; ++b) {
+        const uint4 r = Philox::round10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), 0x50524f50u /* 'PROP' */, (uint32_t)b), key);
+        double z[4];
+        box_muller(r.x, r.y, z[0], z[1]);
+        box_muller(r.z, r.w, z[2], z[3]);
+        for (int j = 0; j < 4 && b * 4 + j < d; ++j) X[(int64_t)(b * 4 + j) * S + s] = mean[b * 4 + j] + stdv[b * 4 + j] * z[j];
+    }
+}
+
+// per design point (row of f) and slice: sum, min, max
+__global__ void __launch_bounds__(256) row_moments_kernel(const double *f, int64_t S, double *part) {
+    const int row = blockIdx.x, split = blockIdx.y;
+    const int64_t per = (S + gridDim.y - 1) / gridDim.y;
+    const int64_t lo = split * per, hi = (lo + per < S) ? lo + per : S;
+    const double *r = f + (int64_t)row * S;
+    double sum = 0.0, mn = INFINITY, mx = -INFINITY;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const double v = r[i];
+        sum += v;
+        mn = fmin(mn, v);
+        mx = fmax(mx, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    __shared__ double sh[3][8];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        sh[0][w] = sum;
+        sh[1][w] = mn;
+        sh[2][w] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) {
+            sum += sh[0][i];
+            mn = fmin(mn, sh[1][i]);
+            mx = fmax(mx, sh[2][i]);
+        }
+        double *o = part + ((int64_t)row * gridDim.y + split) * 3;
+        o[0] = sum;
+        o[1] = mn;
+        o[2] = mx;
+    }
+}
+
+// order-preserving map double -> uint64 (negative values reversed, sign bit flipped)
+__device__ __forceinline__ unsigned long long order_key(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ inline double key_to_double(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    double v;
+#ifdef __CUDA_ARCH__
+    v = __longlong_as_double((long long)b);
+#else
+    memcpy(&v, &b, sizeof v);
+#endif
+    return v;
+}
+
+// one pass of the MSD radix select: byte `pass` (0 = most significant) of the keys that match prefix[row][t]
+__global__ void __launch_bounds__(256) select_hist_kernel(const double *f, int64_t S, int T, int pass, const unsigned long long *prefix,
+                                                          unsigned long long *hist) {
+    __shared__ unsigned int sh[MAX_T][256];
+    const int row = blockIdx.x, split = blockIdx.y;
+    for (int i = threadIdx.x; i < MAX_T * 256; i += blockDim.x) (&sh[0][0])[i] = 0u;
+    __syncthreads();
+    const int shift = 56 - 8 * pass;
+    const unsigned long long mask = (pass == 0) ? 0ull : (~0ull << (shift + 8));
+    unsigned long long pf[MAX_T];
+    for (int t = 0; t < MAX_T; ++t) pf[t] = (t < T) ? prefix[(int64_t)row * T + t] : 0ull;
+    const int64_t per = (S + gridDim.y - 1) / gridDim.y;
+    const int64_t lo = split * per, hi = (lo + per < S) ? lo + per : S;
+    const double *r = f + (int64_t)row * S;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const unsigned long long k = order_key(r[i]);
+        const unsigned int digit = (unsigned int)(k >> shift) & 255u;
+        for (int t = 0; t < MAX_T; ++t)
+            if (t < T && ((k ^ pf[t]) & mask) == 0ull) atomicAdd(&sh[t][digit], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < T * 256; i += blockDim.x) {
+        const unsigned int v = (&sh[0][0])[i];
+        if (v) atomicAdd(&hist[(int64_t)row * T * 256 + i], (unsigned long long)v);
+    }
+}
+
+// after the (all-reduced) histogram of a pass: pick the digit that holds the wanted rank
+__global__ void select_update_kernel(int n_rows, int T, int pass, unsigned long long *prefix, long long *rank, const unsigned long long *hist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * T) return;
+    const unsigned long long *h = hist + (int64_t)i * 256;
+    long long k = rank[i];
+    int digit = 255;
+    for (int b = 0; b < 256; ++b) {
+        const long long c = (long long)h[b];
+        if (k < c) {
+            digit = b;
+            break;
+        }
+        k -= c;
+    }
+    rank[i] = k;
+    prefix[i] |= (unsigned long long)digit << (56 - 8 * pass);
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+PBU_API int pbu_propagation_create(pbu_engine *e, int64_t n_samples, pbu_propagation **out) {
+    if (!e || !out || n_samples < 1) return fail(PBU_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    pbu_propagation *p = new pbu_propagation();
+    p->e = e;
+    p->S = n_samples;
+    p->N = e->prob.n_points;
+    const size_t fbytes = (size_t)p->N * (size_t)n_samples * sizeof(double);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (fbytes + (size_t)e->d * n_samples * 8 + (64u << 20) > free_b) {
+        delete p;
+        return fail(PBU_ERR_INVALID, "propagation of %lld samples x %d points needs %.1f GB of device memory, %.1f GB free: shard the samples",
+                    (long long)n_samples, e->prob.n_points, fbytes / 1e9, free_b / 1e9);
+    }
+    cudaError_t ce = cudaMalloc(&p->d_X, (size_t)e->d * n_samples * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMalloc(&p->d_f, fbytes);
+    if (ce == cudaSuccess) ce = cudaMalloc(&p->d_part, (size_t)p->N * NSPLIT * 3 * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMalloc(&p->d_prefix, (size_t)p->N * MAX_T * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMalloc(&p->d_rank, (size_t)p->N * MAX_T * sizeof(long long));
+    if (ce == cudaSuccess) ce = cudaMalloc(&p->d_hist, (size_t)p->N * MAX_T * 256 * sizeof(unsigned long long));
+    if (ce != cudaSuccess) {
+        cudaFree(p->d_X), cudaFree(p->d_f), cudaFree(p->d_part), cudaFree(p->d_prefix), cudaFree(p->d_rank), cudaFree(p->d_hist);
+        delete p;
+        return fail(PBU_ERR_CUDA, "propagation buffers: %s", cudaGetErrorString(ce));
+    }
+    *out = p;
+    return PBU_OK;
+}
+
+PBU_API int pbu_propagation_destroy(pbu_propagation *p) {
+    if (!p) return PBU_OK;
+    cudaSetDevice(p->e->device);
+    cudaStreamSynchronize(p->e->stream);
+    cudaFree(p->d_X), cudaFree(p->d_f), cudaFree(p->d_part), cudaFree(p->d_prefix), cudaFree(p->d_rank), cudaFree(p->d_hist);
+    delete p;
+    return PBU_OK;
+}
+
+static int run_model_eval(pbu_propagation *p) {
+    pbu_engine *e = p->e;
+    CUDA_TRY(cudaFuncSetAttribute(e->ev->eval_model, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_raw_bytes));
+    const int block = 128;
+    const unsigned grid = (unsigned)((p->S + block - 1) / block);
+    void *args[] = {(void *)&e->prob, (void *)&p->d_X, (void *)&p->S, (void *)&p->d_f, (void *)&e->tile_points_raw};
+    CUDA_TRY(cudaLaunchKernel(e->ev->eval_model, dim3(grid), dim3(block), args, e->smem_raw_bytes, e->stream));
+    p->evaluated = true;
+    return PBU_OK;
+}
+
+// the loop body of solve_problem.py:553-576 for all S samples: X host [S][d] -> f = run_model(X[s]) on the device
+PBU_API int pbu_propagation_eval_host(pbu_propagation *p, const double *X_host) {
+    if (!p || !X_host) return fail(PBU_ERR_INVALID, "null argument");
+    pbu_engine *e = p->e;
+    CUDA_TRY(cudaSetDevice(e->device));
+    std::vector<double> soa((size_t)e->d * p->S);
+    for (int64_t s = 0; s < p->S; ++s)
+        for (int i = 0; i < e->d; ++i) soa[(size_t)i * p->S + s] = X_host[(size_t)s * e->d + i];
+    CUDA_TRY(cudaMemcpyAsync(p->d_X, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return run_model_eval(p);
+}
+
+// same with the samples drawn on the device: row s ~ N(mean, diag(std^2)), Philox keyed by (seed, sample_offset + s)
+PBU_API int pbu_propagation_eval_gaussian(pbu_propagation *p, const double *mean_host, const double *std_host, uint64_t seed, uint64_t sample_offset) {
+    if (!p || !mean_host || !std_host) return fail(PBU_ERR_INVALID, "null argument");
+    pbu_engine *e = p->e;
+    CUDA_TRY(cudaSetDevice(e->device));
+    double *d_ms = nullptr;
+    CUDA_TRY(cudaMalloc(&d_ms, 2 * e->d * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(d_ms, mean_host, e->d * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_ms + e->d, std_host, e->d * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    gaussian_samples_kernel<<<(unsigned)((p->S + 255) / 256), 256, 0, e->stream>>>(p->d_X, p->S, e->d, d_ms, d_ms + e->d, seed, sample_offset);
+    CUDA_TRY(cudaGetLastError());
+    int rc = run_model_eval(p);
+    cudaStreamSynchronize(e->stream);
+    cudaFree(d_ms);
+    return rc;
+}
+
+// device pointers of the sample matrix [d][S] and the evaluations [N][S] (for callers that hand over torch tensors)
+PBU_API int pbu_propagation_buffers(pbu_propagation *p, double **X_dev, double **f_dev) {
+    if (!p) return fail(PBU_ERR_INVALID, "null argument");
+    if (X_dev) *X_dev = p->d_X;
+    if (f_dev) *f_dev = p->d_f;
+    return PBU_OK;
+}
+
+// per design point: sum, min, max over this engine's samples (host [N] each); sums are added over GPUs by the caller
+PBU_API int pbu_propagation_moments(pbu_propagation *p, double *sum_host, double *min_host, double *max_host) {
+    if (!p || !p->evaluated) return fail(PBU_ERR_INVALID, "propagation has not been evaluated");
+    pbu_engine *e = p->e;
+    CUDA_TRY(cudaSetDevice(e->device));
+    row_moments_kernel<<<dim3(p->N, NSPLIT), 256, 0, e->stream>>>(p->d_f, p->S, p->d_part);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<double> part((size_t)p->N * NSPLIT * 3);
+    CUDA_TRY(cudaMemcpyAsync(part.data(), p->d_part, part.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    for (int k = 0; k < p->N; ++k) {
+        double s = 0.0, mn = INFINITY, mx = -INFINITY;
+        for (int j = 0; j < NSPLIT; ++j) {
+            const double *o = &part[((size_t)k * NSPLIT + j) * 3];
+            s += o[0];
+            mn = std::min(mn, o[1]);
+            mx = std::max(mx, o[2]);
+        }
+        if (sum_host) sum_host[k] = s;
+        if (min_host) min_host[k] = mn;
+        if (max_host) max_host[k] = mx;
+    }
+    return PBU_OK;
+}
+
+// radix select of `n_ranks` order statistics per design point.  ranks host [n_ranks]: 0-based ranks in the sorted
+// GLOBAL sample (all GPUs).  Protocol per pass 0..7: select_pass fills hist_host [N][n_ranks][256] with this engine's
+// counts; the caller sums them over GPUs and hands the total to select_update.
+PBU_API int pbu_propagation_select_begin(pbu_propagation *p, const int64_t *ranks, int n_ranks) {
+    if (!p || !ranks || n_ranks < 1 || n_ranks > MAX_T) return fail(PBU_ERR_INVALID, "need 1..%d ranks", MAX_T);
+    if (!p->evaluated) return fail(PBU_ERR_INVALID, "propagation has not been evaluated");
+    pbu_engine *e = p->e;
+    CUDA_TRY(cudaSetDevice(e->device));
+    p->T = n_ranks;
+    std::vector<long long> r((size_t)p->N * n_ranks);
+    for (int k = 0; k < p->N; ++k)
+        for (int t = 0; t < n_ranks; ++t) r[(size_t)k * n_ranks + t] = ranks[t];
+    CUDA_TRY(cudaMemcpyAsync(p->d_rank, r.data(), r.size() * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemsetAsync(p->d_prefix, 0, (size_t)p->N * n_ranks * sizeof(unsigned long long), e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PBU_OK;
+}
+
+PBU_API int pbu_propagation_select_pass(pbu_propagation *p, int pass, uint64_t *hist_host) {
+    if (!p || p->T < 1 || pass < 0 || pass > 7 || !hist_host) return fail(PBU_ERR_INVALID, "bad argument");
+    pbu_engine *e = p->e;
+    CUDA_TRY(cudaSetDevice(e->device));
+    const size_t n = (size_t)p->N * p->T * 256;
+    CUDA_TRY(cudaMemsetAsync(p->d_hist, 0, n * sizeof(unsigned long long), e->stream));
+    select_hist_kernel<<<dim3(p->N, NSPLIT), 256, 0, e->stream>>>(p->d_f, p->S, p->T, pass, p->d_prefix, p->d_hist);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(hist_host, p->d_hist, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PBU_OK;
+}
+
+PBU_API int pbu_propagation_select_update(pbu_propagation *p, int pass, const uint64_t *hist_total_host) {
+    if (!p || p->T < 1 || pass < 0 || pass > 7 || !hist_total_host) return fail(PBU_ERR_INVALID, "bad argument");
+    pbu_engine *e = p->e;
+    CUDA_TRY(cudaSetDevice(e->device));
+    const size_t n = (size_t)p->N * p->T * 256;
+    CUDA_TRY(cudaMemcpyAsync(p->d_hist, hist_total_host, n * sizeof(unsigned long long), cudaMemcpyHostToDevice, e->stream));
+    const int items = p->N * p->T;
+    select_update_kernel<<<(items + 127) / 128, 128, 0, e->stream>>>(p->N, p->T, pass, p->d_prefix, p->d_rank, p->d_hist);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PBU_OK;
+}
+
+// the order statistics after pass 7: values host [N][n_ranks]
+PBU_API int pbu_propagation_select_result(pbu_propagation *p, double *values_host) {
+    if (!p || p->T < 1 || !values_host) return fail(PBU_ERR_INVALID, "bad argument");
+    pbu_engine *e = p->e;
+    CUDA_TRY(cudaSetDevice(e->device));
+    std::vector<unsigned long long> k((size_t)p->N * p->T);
+    CUDA_TRY(cudaMemcpyAsync(k.data(), p->d_prefix, k.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    for (size_t i = 0; i < k.size(); ++i) values_host[i] = key_to_double(k[i]);
+    return PBU_OK;
+}
+
+// copy the evaluations of samples [s0, s0 + n) to the host, sample-major [n][N] (fun_eval, solve_problem.py:571)
+PBU_API int pbu_propagation_get_evals(pbu_propagation *p, int64_t s0, int64_t n, double *f_host) {
+    if (!p || !p->evaluated || s0 < 0 || n < 1 || s0 + n > p->S || !f_host) return fail(PBU_ERR_INVALID, "bad argument");
+    pbu_engine *e = p->e;
+    CUDA_TRY(cudaSetDevice(e->device));
+    std::vector<double> pm((size_t)p->N * n);
+    CUDA_TRY(cudaMemcpy2DAsync(pm.data(), (size_t)n * sizeof(double), p->d_f + s0, (size_t)p->S * sizeof(double), (size_t)n * sizeof(double), p->N,
+                               cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    for (int64_t s = 0; s < n; ++s)
+        for (int k = 0; k < p->N; ++k) f_host[(size_t)s * p->N + k] = pm[(size_t)k * n + s];
+    return PBU_OK;
+}
