@@ -177,6 +177,17 @@ int pbu_engine_get_launch(const pbu_engine *e, int32_t *lanes, int32_t *chains_p
 int pbu_eval_logpost(pbu_engine *e, const double *X_host /*[S][d]*/, int64_t S, double *lp_host /*[S]*/);
 int pbu_eval_model(pbu_engine *e, const double *X_host /*[S][d]*/, int64_t S, double *f_host /*[S][N]*/);
 
+/* ---- chain moments (K4): sums over this engine's chains of the running moments of the kept states; additive over
+ *      chains and over GPUs.  Many-chain counterpart of compute_covariance (mha.py:295-307, np.mean / np.cov over
+ *      the chain file); the host layer all-reduces them for the pooled covariance and the Gelman-Rubin R-hat.
+ *      out_host [2 + 4d + d(d+1)/2] as laid out in pbu_moments.cu; mu_host [d] reference point (NULL = 0). */
+int pbu_engine_chain_sums_len(const pbu_engine *e);
+int pbu_engine_chain_sums(pbu_engine *e, const double *mu_host, double *out_host);
+int pbu_engine_reset_moments(pbu_engine *e);
+/* Replace the proposal covariance of EVERY chain (pooled-covariance mode): R = upper Cholesky of V host [d][d]
+ * for the MH family (mha.py:486-487), C_approx / L_c / inv_L_c for ISDE (:773-777). */
+int pbu_engine_set_proposal(pbu_engine *e, const double *V_host);
+
 /* ---- Monte-Carlo propagation: replaces the sample loop of Propagation.propagate, emulator == "None"
  *      (solve_problem.py:543-576) and its statistics (:596-647).  The evaluations stay in device memory,
  *      point-major; mean / min / max and EXACT order statistics (for np.percentile, :643-645) are reduced on the

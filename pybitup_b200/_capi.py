@@ -91,6 +91,10 @@ def _load():
         "pbu_engine_get_launch": (C.c_int, [E, _ip, _ip, _ip, _ip, _lp]),
         "pbu_eval_logpost": (C.c_int, [E, _dp, C.c_int64, _dp]),
         "pbu_eval_model": (C.c_int, [E, _dp, C.c_int64, _dp]),
+        "pbu_engine_chain_sums_len": (C.c_int, [E]),
+        "pbu_engine_chain_sums": (C.c_int, [E, _dp, _dp]),
+        "pbu_engine_reset_moments": (C.c_int, [E]),
+        "pbu_engine_set_proposal": (C.c_int, [E, _dp]),
         "pbu_propagation_create": (C.c_int, [E, C.c_int64, C.POINTER(E)]),
         "pbu_propagation_destroy": (C.c_int, [E]),
         "pbu_propagation_eval_host": (C.c_int, [E, _dp]),

@@ -507,6 +507,28 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_init_chains(pbu
     return PBU_OK;
 }
 
+extern "C" __attribute__((visibility("default"))) int pbu_engine_set_proposal(pbu_engine *e, const double *V_host) {
+    if (!e || !V_host) return fail(PBU_ERR_INVALID, "null argument");
+    if (!e->initialised) return fail(PBU_ERR_INVALID, "pbu_engine_init_chains has not been called");
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int d = e->d, nt = e->nt;
+    std::vector<double> Rp, Vp((size_t)nt);
+    if (!chol_upper_host(V_host, d, Rp)) return fail(PBU_ERR_NOT_PD, "covariance is not positive definite");
+    for (int i = 0; i < d; ++i)
+        for (int j = i; j < d; ++j) Vp[tri_idx(d, i, j)] = V_host[i * d + j];
+    int rc;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (e->cfg.algo == PBU_ALGO_ISDE) {
+        std::vector<double> IL;
+        inv_upper_host(Rp, d, IL);
+        if ((rc = broadcast_rows(e, e->d_Cmat, Vp)) || (rc = broadcast_rows(e, e->st.R, IL))) return rc;
+    } else {
+        e->R0 = Rp;
+        if ((rc = broadcast_rows(e, e->st.R, Rp))) return rc;
+    }
+    return PBU_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int pbu_engine_set_streams(pbu_engine *e, const double *normals_host, int64_t n_normals, const double *uniforms_host,
                                       int64_t n_uniforms) {
     if (!e) return fail(PBU_ERR_INVALID, "null engine");

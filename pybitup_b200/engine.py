@@ -283,6 +283,30 @@ class ChainEngine:
         capi.check(capi.lib.pbu_engine_get_proposal(self._h, capi.dptr(R), capi.dptr(V), capi.dptr(xav)))
         return dict(R=R, V=V, X_av=xav)
 
+    def chain_sums(self, mu=None):
+        """Additive sums of the kept-state moments over this engine's chains (K4), about the point mu."""
+        n = int(capi.lib.pbu_engine_chain_sums_len(self._h))
+        out = np.empty(n)
+        m = None if mu is None else _f64(mu)
+        capi.check(capi.lib.pbu_engine_chain_sums(self._h, capi.dptr(m) if m is not None else None, capi.dptr(out)))
+        return out
+
+    def reset_moments(self):
+        capi.check(capi.lib.pbu_engine_reset_moments(self._h))
+
+    def set_proposal(self, V):
+        """Pooled-covariance mode: give every chain the proposal covariance / preconditioner V [d, d]."""
+        V = _f64(V)
+        if V.shape != (self.d, self.d):
+            raise ValueError("V must be [d, d]")
+        capi.check(capi.lib.pbu_engine_set_proposal(self._h, capi.dptr(V)))
+
+    def statistics(self, reducer=None):
+        """Pooled mean / covariance and R-hat of the kept states of all chains (of all ranks with a reducer)."""
+        from .distributed import global_chain_statistics
+        x, _ = self.state()
+        return global_chain_statistics(self.chain_sums, self.d, reducer, mu0=None if reducer is not None else x[0])
+
     def isde_state(self):
         P = np.empty((self.n_chains, self.d))
         Cm = np.empty((self.n_chains, self.d, self.d))

@@ -1,0 +1,104 @@
+"""Host logic of the multi-GPU path on CPU: sharding, the gloo all-reduce of chain sums (world_size 2) and the
+pooled covariance / R-hat formulas, against plain numpy over all chains."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from pybitup_b200 import diagnostics
+from pybitup_b200.distributed import shard_range
+
+
+def _chains(seed=0, C=12, T=50, d=3):
+    rng = np.random.default_rng(seed)
+    base = rng.standard_normal((C, 1, d)) * 0.3 + np.array([5.0, -2.0, 100.0])
+    return base + rng.standard_normal((C, T, d)) * np.array([1.0, 0.1, 3.0])
+
+
+def _moments(ch):
+    mean = ch.mean(axis=1)
+    dev = ch - mean[:, None, :]
+    M2 = np.einsum("cti,ctj->cij", dev, dev)
+    return np.full(ch.shape[0], ch.shape[1]), mean, M2
+
+
+def _reference(ch):
+    C, T, d = ch.shape
+    allx = ch.reshape(-1, d)
+    W = ch.var(axis=1, ddof=1).mean(axis=0)
+    B_over_n = ch.mean(axis=1).var(axis=0, ddof=1)
+    rhat = np.sqrt(((T - 1) / T * W + B_over_n) / W)
+    return allx.mean(axis=0), np.cov(allx, rowvar=False), rhat
+
+
+def test_shard_range_covers_everything():
+    for n, w in ((10, 3), (262144, 8), (7, 8), (1, 1)):
+        got = []
+        for r in range(w):
+            f, c = shard_range(n, w, r)
+            got.extend(range(f, f + c))
+        assert got == list(range(n))
+
+
+def test_finalize_single_rank_matches_numpy():
+    ch = _chains()
+    cnt, mean, M2 = _moments(ch)
+    from pybitup_b200.distributed import global_chain_statistics
+    st = global_chain_statistics(lambda mu: diagnostics.chain_sums_numpy(cnt, mean, M2, mu), 3)
+    m, cov, rhat = _reference(ch)
+    assert np.allclose(st["mean"], m, rtol=1e-13) and np.allclose(st["cov"], cov, rtol=1e-11)
+    assert np.allclose(st["rhat"], rhat, rtol=1e-11)
+    assert st["n_chains"] == 12 and st["n"] == 12 * 50
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pybitup_b200.distributed import Reducer, global_chain_statistics, shard_range
+    ch = _chains()
+    first, count = shard_range(ch.shape[0], world, rank)
+    cnt, mean, M2 = _moments(ch[first:first + count])
+    red = Reducer()
+    st = global_chain_statistics(lambda mu: diagnostics.chain_sums_numpy(cnt, mean, M2, mu), 3, red)
+    mn = red(np.array([float(rank)]), "min")
+    mx = red(np.array([float(rank)]), "max")
+    hist = red(np.arange(6, dtype=np.int64).reshape(2, 3) * (rank + 1), "sum")
+    q.put((rank, st["mean"], st["cov"], st["rhat"], st["n_chains"], mn[0], mx[0], hist))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_allreduce_matches_numpy():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    m, cov, rhat = _reference(_chains())
+    for rank, mean_r, cov_r, rhat_r, nch, mn, mx, hist in res:
+        assert np.allclose(mean_r, m, rtol=1e-13) and np.allclose(cov_r, cov, rtol=1e-11) and np.allclose(rhat_r, rhat, rtol=1e-11)
+        assert nch == 12 and mn == 0.0 and mx == 1.0
+        assert np.array_equal(hist, np.arange(6).reshape(2, 3) * 3)
+    # both ranks hold the bit-identical result
+    assert np.array_equal(res[0][2], res[1][2])
+
+
+def test_ess_batch_means_iid_and_correlated():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((20000, 2))
+    assert 0.7 * 20000 < diagnostics.ess_batch_means(x) < 1.4 * 20000
+    y = np.zeros_like(x)
+    for t in range(1, len(x)):
+        y[t] = 0.9 * y[t - 1] + x[t]
+    assert diagnostics.ess_batch_means(y) < 0.15 * 20000
