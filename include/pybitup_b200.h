@@ -111,12 +111,15 @@ typedef struct {
 /* Per-run outputs that live on the device; any pointer may be NULL (= not recorded).
  * Layouts are chain-minor so that one thread per chain writes coalesced. */
 typedef struct {
-    double *samples;     /* dev [n_keep][d][C]   state after every `thin`-th iteration (chain rows,
-                            bayesian_inference.py:131-138)                                        */
+    double *samples;     /* dev [n_keep][d][Cs]  state after every `thin`-th iteration (chain rows,
+                            bayesian_inference.py:131-138) of the first Cs = n_sample_chains chains */
     double *lp_kept;     /* dev [n_keep][C]      log-posterior of the kept states                 */
     double *trace_lp1;   /* dev [n_steps][C]     log-posterior of the stage-1 proposal (parity)   */
     double *trace_lp2;   /* dev [n_steps][C]     ... of the stage-2 proposal, NaN if none         */
     uint8_t *trace_acc;  /* dev [n_steps][C]     0 rejected, 1 accepted stage 1, 2 stage 2        */
+    double *aux;         /* dev [n_keep][d][Cs]  ISDE momentum P after the kept iterations
+                            (aux_variables.csv, mha.py:1032)                                      */
+    int64_t n_sample_chains; /* Cs: leading chains recorded in samples / aux; <= 0 means all C    */
 } pbu_run_outputs;
 
 typedef struct pbu_engine pbu_engine;

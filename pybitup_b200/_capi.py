@@ -48,7 +48,8 @@ class pbu_sampler_cfg(C.Structure):
 
 class pbu_run_outputs(C.Structure):
     _fields_ = [("samples", C.c_void_p), ("lp_kept", C.c_void_p), ("trace_lp1", C.c_void_p),
-                ("trace_lp2", C.c_void_p), ("trace_acc", C.c_void_p)]
+                ("trace_lp2", C.c_void_p), ("trace_acc", C.c_void_p), ("aux", C.c_void_p),
+                ("n_sample_chains", C.c_int64)]
 
 
 class EngineError(RuntimeError):

@@ -1,0 +1,208 @@
+"""Model / Data / Likelihood / BayesianPosterior: host-side mirror of ``pybitup/bayesian_inference.py``.
+
+The user-facing contract is the reference's (``from pybitup_b200 import bayesian_inference as bi``;
+``class MyModel(bi.Model)``): same constructor signatures, attribute names and call order as the reference's
+``Model`` (:254-389), ``Data`` (:141-210), ``Likelihood`` (:399-696) and ``BayesianPosterior`` (:15-139).  What
+changes is where the arithmetic runs: a model declares which REGISTERED DEVICE MODEL it is
+
+    class Cubic(bi.Model):
+        device_model = "poly"          # 'linear' | 'poly' | 'arrhenius' | 'heat'
+
+(and, for models whose design is not just ``x``, overrides ``device_design()``), and ``BayesianPosterior.lower()``
+turns the whole posterior into the flat ``ProblemSpec`` the CUDA engine consumes.  Anything that cannot be lowered
+raises ``UnsupportedProblem``: there is no CPU fallback.  ``fun_x`` is never called on the sampling path.
+"""
+import pathlib
+
+import numpy as np
+
+from . import _capi as capi
+from .engine import ProblemSpec
+
+
+class Data:
+    """Experimental data of one model: x, y = {run: f64[N]}, std_y (bayesian_inference.py:154-182)."""
+
+    def __init__(self, name="", x=np.array([1]), y=np.array([1]), std_y=np.array([1])):
+        self.name = list([name])
+        self.x = x
+        self.num_points = np.array([len(self.x)])
+        if not isinstance(y, dict):
+            y = {0: np.asarray(y, dtype=np.float64)}
+        self.y = y
+        self.n_runs = len(y.keys())
+        self.n_data_set = 1
+        self.std_y = std_y
+        self.index_data_set = np.array([[0, len(self.x) - 1]])
+        self.mean_y = np.mean(np.stack([np.asarray(self.y[r], dtype=np.float64) for r in range(self.n_runs)]), axis=0)
+
+    def size_x(self, i):
+        return self.num_points[i]
+
+
+class Model:
+    """Forward model contract of the reference (bayesian_inference.py:254-389) plus the device declaration."""
+
+    device_model = None      # name of the registered device model this class corresponds to
+
+    def __init__(self, x=[], param=[], scaling_factors_parametrization=1, name=""):
+        self.name = name
+        self.P = scaling_factors_parametrization
+        self._x = x
+        self._param = param
+        self.param_nom = []
+        self.param_names = []
+        self.input_file_name = []
+        self.unpar_name = {}
+        self.unpar_name_dict = {}
+        self.model_eval = 0
+        self.model_grad = 0
+
+    def size_x(self):
+        return len(self._x)
+
+    param = property(lambda self: self._param, lambda self, v: setattr(self, "_param", v))
+    x = property(lambda self: self._x, lambda self, v: setattr(self, "_x", v))
+
+    # -- user hooks (reference names) --------------------------------------------------------
+    def fun_x(self, *ext_parameters):
+        return 1
+
+    def d_fx_dparam(self, *ext_parameters):
+        return 1
+
+    def parametrization_forward(self, X=1, P=1):
+        return X
+
+    def parametrization_backward(self, Y=1, P=1):
+        return Y
+
+    def parametrization_det_jac(self, X=1):
+        return 1
+
+    def parametrization_inv_jac(self, X=1):
+        return X
+
+    # -- device declaration ----------------------------------------------------------------------
+    def device_design(self):
+        """Design data of the registered device model.  Default: the design points ``x`` (poly / heat); ``linear``
+        models return {'Phi': [N, P]}; ``arrhenius`` models return {'T0', 'dT', 'n_steps', 'beta'}."""
+        return {"x": np.asarray(self.x, dtype=np.float64)}
+
+    def uncertain_index(self):
+        """Positions of the uncertain parameters inside the full parameter vector, with the reference's
+        substring matching (Model.run_model, :351-369): parameter names that occur inside the
+        blank-joined uncertain names are uncertain, and the n-th uncertain VALUE goes to the n-th such name."""
+        unpar = list(self.unpar_name)
+        n_model = len(self.param_nom)
+        if len(unpar) >= n_model:
+            return np.arange(n_model, dtype=np.int32)          # param = var_param (:368-369)
+        joined = " ".join(unpar)
+        idx = [i for i, name in enumerate(self.param_names) if joined.find(name) >= 0]
+        if len(idx) < len(unpar):
+            raise ValueError("uncertain parameters {} not found among the model parameters {}".format(unpar, list(self.param_names)))
+        return np.asarray(idx[: len(unpar)], dtype=np.int32)
+
+    def run_model(self, var_param):
+        """Kept for interface compatibility: evaluates the model through the user's numpy ``fun_x`` with the
+        reference's parameter mapping.  NOT used by the device samplers or by device propagation."""
+        if self.input_file_name:
+            self.model_eval = self.fun_x(self.input_file_name, self.unpar_name, var_param)
+            return
+        idx = self.uncertain_index()
+        if len(list(self.unpar_name)) < len(self.param_nom):
+            vec = self.param_nom
+            for n, i in enumerate(idx):
+                vec[i] = var_param[n]
+            self.param = vec
+        else:
+            self.param = var_param
+        self.model_eval = self.fun_x()
+
+    def get_gradient_model(self, var_param):
+        self.model_grad = self.d_fx_dparam()
+
+
+class Likelihood:
+    """Gaussian likelihood over {model_id: Data} and {model_id: Model} (bayesian_inference.py:399-542)."""
+
+    def __init__(self, exp_data, model_list, gamma=1.0):
+        self.data = exp_data
+        self.models = model_list
+        self.SS_X = 0
+        self.arg_LL = 0
+        self.gamma = gamma
+        self.model_eval = {}
+
+    def lower(self, lb, ub):
+        """ProblemSpec of the (single) model/data pair with the box prior [lb, ub]."""
+        ids = list(self.models.keys())
+        if len(ids) != 1:
+            raise capi.UnsupportedProblem(capi.PBU_ERR_UNSUPPORTED,
+                                          "the device path handles one model per posterior, got {}".format(ids))
+        mid = ids[0]
+        model, data = self.models[mid], self.data[mid]
+        if model.input_file_name:
+            raise capi.UnsupportedProblem(capi.PBU_ERR_UNSUPPORTED, "external-solver models (input_file) cannot run on the device")
+        if model.device_model not in capi.MODEL_IDS:
+            raise capi.UnsupportedProblem(
+                capi.PBU_ERR_UNSUPPORTED,
+                "model class {} does not declare a registered device model (device_model = one of {}); "
+                "there is no CPU fallback".format(type(model).__name__, sorted(capi.MODEL_IDS)))
+        y = np.stack([np.asarray(data.y[r], dtype=np.float64) for r in range(data.n_runs)])
+        return ProblemSpec(model=model.device_model, theta_nom=np.array(model.param_nom, dtype=np.float64),
+                           unc_idx=model.uncertain_index(), y=y, std_y=np.asarray(data.std_y, dtype=np.float64),
+                           lb=np.asarray(lb, dtype=np.float64), ub=np.asarray(ub, dtype=np.float64),
+                           gamma=float(self.gamma), design=model.device_design())
+
+
+class BayesianPosterior:
+    """prior x likelihood in the sampling space (bayesian_inference.py:15-139)."""
+
+    def __init__(self, prior, likelihood, class_model, param_init):
+        self.param_init = param_init
+        self.prior = prior
+        self.likelihood = likelihood
+        self.model = class_model
+        self.dim = len(param_init)
+        self.name_random_var = list(self.model.unpar_name)
+        self._engine = None
+
+    def get_dim(self):
+        return len(self.param_init)
+
+    def lower(self):
+        """Flat problem descriptor for the CUDA engine; refuses what it cannot represent."""
+        m = self.model
+        probe = np.asarray(self.param_init, dtype=np.float64)
+        if (np.any(np.asarray(m.parametrization_backward(probe)) != probe) or m.parametrization_det_jac(probe) != 1):
+            raise capi.UnsupportedProblem(capi.PBU_ERR_UNSUPPORTED, "re-parametrised models are not lowered to the device yet")
+        if not hasattr(self.prior, "box"):
+            raise capi.UnsupportedProblem(capi.PBU_ERR_UNSUPPORTED, "only a Mixture of Uniform priors can be lowered (SURVEY Q12)")
+        lb, ub = self.prior.box()
+        return self.likelihood.lower(lb, ub)
+
+    # single evaluations through the device (diagnostics; the samplers never call these per iteration)
+    def _eval_engine(self):
+        if self._engine is None:
+            from .engine import ChainEngine, SamplerConfig
+            self._engine = ChainEngine(self.lower(), SamplerConfig(algo="RWMH"), 1)
+        return self._engine
+
+    def compute_log_value(self, Y):
+        return float(self._eval_engine().log_posterior(np.asarray(Y, dtype=np.float64)[None, :])[0])
+
+    def compute_value(self, Y):
+        return float(np.exp(self.compute_log_value(Y)))
+
+    def save_sample(self, IO_fileID, value):
+        """Chain row in the sampling space and in the model space (bayesian_inference.py:131-138)."""
+        np.savetxt(IO_fileID['MChains_reparam'], np.array([value]), fmt="%f", delimiter=",")
+        X = self.model.parametrization_backward(value)
+        np.savetxt(IO_fileID['MChains'], np.array([X]), fmt="%f", delimiter=",")
+
+    def save_value(self, IO_util, current_it, model_eval):
+        """output/model_eval/<id>_fun_eval-<it>.npy (Likelihood.write_fun_eval, :448-454)."""
+        for model_id in self.likelihood.models.keys():
+            p = pathlib.Path(IO_util['path']['fun_eval_folder'], f"{model_id}_fun_eval-{current_it}.npy")
+            np.save(p, model_eval)

@@ -588,6 +588,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine 
         q.st = e->st;
         q.streams = e->streams;
         if (out) q.out = *out;
+        if (q.out.n_sample_chains <= 0 || q.out.n_sample_chains > e->C) q.out.n_sample_chains = e->C;
         q.Cmat = e->d_Cmat;
         q.it0 = e->iteration;
         q.n_steps = n_steps;
@@ -615,6 +616,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine 
     p.st = e->st;
     p.streams = e->streams;
     if (out) p.out = *out;
+    if (p.out.n_sample_chains <= 0 || p.out.n_sample_chains > e->C) p.out.n_sample_chains = e->C;
     p.it0 = e->iteration;
     p.n_steps = n_steps;
     p.thin = thin;

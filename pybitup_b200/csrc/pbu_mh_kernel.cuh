@@ -568,9 +568,9 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_c
                             }
                     }
                     const int64_t row = it / p.thin - p.it0 / p.thin - 1;
-                    if (p.out.samples) {
+                    if (p.out.samples && cq < p.out.n_sample_chains) {
 #pragma unroll
-                        for (int i = 0; i < D; ++i) p.out.samples[(row * D + i) * C + cq] = x[q][i];
+                        for (int i = 0; i < D; ++i) p.out.samples[(row * D + i) * p.out.n_sample_chains + cq] = x[q][i];
                     }
                     if (p.out.lp_kept) p.out.lp_kept[row * C + cq] = lp[q];
                 }

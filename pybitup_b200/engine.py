@@ -135,7 +135,8 @@ class RunResult:
     """Device-resident outputs of one ``ChainEngine.run`` (torch tensors, chain-minor layout)."""
     n_steps: int
     thin: int
-    samples: object = None      # [n_keep, d, C]
+    samples: object = None      # [n_keep, d, Cs]  (Cs = sample_chains leading chains)
+    aux: object = None          # [n_keep, d, Cs]  ISDE momentum
     lp_kept: object = None      # [n_keep, C]
     trace_lp1: object = None    # [n_steps, C]
     trace_lp2: object = None    # [n_steps, C]
@@ -232,7 +233,8 @@ class ChainEngine:
         return dict(lanes=a.value, chains_per_thread=q.value, block=b.value, grid=g.value, smem_bytes=m.value)
 
     # -- the hot loop -------------------------------------------------------------------------
-    def run(self, n_steps, thin=1, keep_samples=True, keep_lp=False, trace=False, out=None):
+    def run(self, n_steps, thin=1, keep_samples=True, keep_lp=False, trace=False, out=None, sample_chains=None,
+            keep_aux=False):
         """Advance all chains by n_steps iterations in one kernel launch (asynchronous)."""
         torch = self._torch
         n_steps, thin = int(n_steps), int(thin)
@@ -240,9 +242,12 @@ class ChainEngine:
         res = out if out is not None else RunResult(n_steps=n_steps, thin=thin)
         n_keep = int(capi.lib.pbu_engine_n_keep(self._h, n_steps, thin))
         Cn, d = self.n_chains, self.d
+        Cs = Cn if sample_chains is None else max(1, min(int(sample_chains), Cn))
         if out is None:
             if keep_samples:
-                res.samples = torch.empty((n_keep, d, Cn), dtype=torch.float64, device=dev)
+                res.samples = torch.empty((n_keep, d, Cs), dtype=torch.float64, device=dev)
+            if keep_aux:
+                res.aux = torch.empty((n_keep, d, Cs), dtype=torch.float64, device=dev)
             if keep_lp:
                 res.lp_kept = torch.empty((n_keep, Cn), dtype=torch.float64, device=dev)
             if trace:
@@ -250,7 +255,8 @@ class ChainEngine:
                 res.trace_lp2 = torch.empty((n_steps, Cn), dtype=torch.float64, device=dev)
                 res.trace_acc = torch.empty((n_steps, Cn), dtype=torch.uint8, device=dev)
         o = capi.pbu_run_outputs()
-        for name in ("samples", "lp_kept", "trace_lp1", "trace_lp2", "trace_acc"):
+        o.n_sample_chains = res.samples.shape[2] if res.samples is not None else (res.aux.shape[2] if res.aux is not None else Cn)
+        for name in ("samples", "lp_kept", "trace_lp1", "trace_lp2", "trace_acc", "aux"):
             t = getattr(res, name)
             setattr(o, name, C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else None)
         capi.check(capi.lib.pbu_engine_run(self._h, n_steps, thin, C.byref(o)))

@@ -1,0 +1,322 @@
+"""Sampler classes: host-side mirror of ``pybitup/metropolis_hastings_algorithms.py``.
+
+Same class names, constructor signatures and ``run_algorithm()`` entry point as the reference
+(``MetropolisHastings`` :26-368, ``AdaptiveMetropolisHastings`` :370-487, ``DelayedRejectionMetropolisHastings``
+:490-567, ``DelayedRejectionAdaptiveMetropolisHastings`` :570-595, ``ito_SDE`` :886-1040), but the per-iteration
+Python loop is one fused CUDA kernel over ``n_chains`` independent chains (``ChainEngine``).  Engine-only options
+ride in ``opt_arg`` (the ``Sampler`` copies them from the ``Algorithm`` JSON block): ``n_chains`` (default 1),
+``seed``, ``init_jitter``, ``device``, ``launch_iterations``, ``save_all_chains``.
+
+Side effects reproduced: ``output/mcmc_chain.csv`` and ``mcmc_chain_reparam.csv`` (T+1 rows of
+chain 0, ``%f``), the ``output.txt`` header parsed by ``post_process`` (lines 1 and 3) and footer,
+``output/model_eval/<id>_fun_eval-<it>.npy`` every ``save_eval_freq`` iterations, ``./cov.csv``, the in-place update
+of the caller's ``param_init`` to the final state.  Random numbers come from Philox on the device (the reference
+uses the unseeded stdlib generator), so chains agree with the reference statistically; arithmetic parity with
+injected streams is what ``tests/test_gpu_parity.py`` checks through the C ABI.
+"""
+import time
+
+import numpy as np
+
+from .engine import ChainEngine, SamplerConfig
+
+
+def time_it(f):
+    def wrapped(*args, **kw):
+        t0 = time.perf_counter()
+        result = f(*args, **kw)
+        print("{}: {:.3f} s".format(f.__name__, time.perf_counter() - t0))
+        return result
+    return wrapped
+
+
+def compute_hessian_fd(fun_batch, x, eps=0.01, compute_all_element=True, positive_diag=True):
+    """Finite-difference Hessian with the reference's stencil (computeHessianFD, mha.py:1115-1212), all stencil points
+    evaluated in ONE batched device call: fun_batch(X[S, d]) -> f[S].
+
+    Diagonal: central second difference with step x_i*eps, forced to -|.| when positive_diag (:1162-1164).
+    Off-diagonal (i < j): (f_ij+ - f_i+ - f_j+ + 2 f_0 - f_i- - f_j- + f_ij-) / (2 d_i d_j).  In the reference the
+    doubly perturbed points are built IN PLACE on the i-perturbed vectors (:1186-1189 alias them), so for a given i the
+    perturbations of successive j accumulate; that is reproduced here because it decides the preconditioner."""
+    x = np.asarray(x, dtype=np.float64)
+    n = x.size
+    delta = x * eps
+    pts = [x.copy()]
+    for i in range(n):
+        for sgn in (1.0, -1.0):
+            q = x.copy()
+            q[i] = x[i] + sgn * delta[i]
+            pts.append(q)
+    pair_slots = {}
+    if compute_all_element:
+        for i in range(n):
+            acc_p, acc_m = x.copy(), x.copy()
+            acc_p[i] = x[i] + delta[i]
+            acc_m[i] = x[i] - delta[i]
+            for j in range(i + 1, n):
+                acc_p[j] = acc_p[j] + delta[j]          # cumulative over j: the reference's aliasing
+                acc_m[j] = acc_m[j] - delta[j]
+                pair_slots[(i, j)] = len(pts)
+                pts.append(acc_p.copy())
+                pts.append(acc_m.copy())
+    f = np.asarray(fun_batch(np.array(pts)), dtype=np.float64)
+    f0 = f[0]
+    H = np.zeros((n, n))
+    for i in range(n):
+        num = f[1 + 2 * i] - 2 * f0 + f[2 + 2 * i]
+        H[i, i] = -np.abs(num / delta[i] ** 2) if positive_diag else num / delta[i] ** 2
+    for (i, j), k in pair_slots.items():
+        H[i, j] = (f[k] - f[1 + 2 * i] - f[1 + 2 * j] + 2 * f0 - f[2 + 2 * i] - f[2 + 2 * j] + f[k + 1]) / (2 * delta[j] * delta[i])
+        H[j, i] = H[i, j]
+    return H
+
+
+class _DeviceSampler:
+    """Common driver: build the engine, run the iterations in a few launches, write the reference's files."""
+
+    algo_name = "RWMH"
+
+    def _setup(self, IO_util, nIterations, param_init, V, prob_distr, opt_arg):
+        self.nIterations = int(nIterations)
+        self.opt_arg = dict(opt_arg or {})
+        self.save_eval_freq = int(self.opt_arg.get("save_eval_freq", 10))
+        self.estimate_max_distr = bool(self.opt_arg.get("estimate_max_distr", False))
+        self.bool_estimate_sigma = bool(self.opt_arg.get("estimate_sigma", False))
+        self.V = None if V is None else np.array(V, dtype=np.float64)
+        self.V_0 = self.V
+        self.prob_distr = prob_distr
+        self.param_init = param_init                      # aliased and updated in place, as the reference does (:95-99)
+        self.n_param = int(np.size(param_init))
+        self.current_val = self.param_init
+        self.IO_util = IO_util
+        self.IO_fileID = IO_util["fileID"]
+        self.n_chains = int(self.opt_arg.get("n_chains", 1))
+        self.n_rejected = 0
+        self.mean_r = 0.0
+        self.it = 0
+        self.problem = prob_distr.lower()                 # raises UnsupportedProblem: no CPU fallback
+        self.engine = None
+
+    # -- configuration of the engine (overridden per algorithm) -----------------------------------------
+    def _config(self):
+        return SamplerConfig(algo=self.algo_name)
+
+    def _proposal_matrix(self, eng):
+        return self.V
+
+    def _start_points(self):
+        x0 = np.tile(np.asarray(self.param_init, dtype=np.float64), (self.n_chains, 1))
+        jitter = float(self.opt_arg.get("init_jitter", 0.0))
+        if self.n_chains > 1 and jitter > 0.0:
+            rng = np.random.default_rng(int(self.opt_arg.get("seed", 0)) + 7919)
+            scale = np.where(x0[0] == 0.0, 1.0, np.abs(x0[0]))
+            x0[1:] += jitter * scale * rng.standard_normal((self.n_chains - 1, self.n_param))
+            lb, ub = self.problem.lb, self.problem.ub
+            x0 = np.minimum(np.maximum(x0, lb), ub)
+        return x0
+
+    def _write_header(self):
+        f = self.IO_fileID['out_data']                    # mha.py:131-135
+        f.write("$RandomVarName$\n")
+        for name in self.prob_distr.name_random_var:
+            f.write(name + ' ')
+        f.write("\n$IterationNumber$\n{}\n".format(self.nIterations))
+
+    def _write_rows(self, rows):
+        """rows [n, d] of chain 0 -> both chain files, %f, comma (bayesian_inference.py:131-138)."""
+        if len(rows) == 0:
+            return
+        np.savetxt(self.IO_fileID['MChains_reparam'], rows, fmt="%f", delimiter=",")
+        back = np.array([self.prob_distr.model.parametrization_backward(r) for r in rows])
+        np.savetxt(self.IO_fileID['MChains'], back, fmt="%f", delimiter=",")
+
+    def _launch_len(self):
+        n = int(self.opt_arg.get("launch_iterations", 0))
+        if n <= 0:
+            n = max(1, min(self.nIterations, 2000))
+        return n
+
+    @time_it
+    def run_algorithm(self):
+        cfg = self._config()
+        cfg.seed = int(self.opt_arg.get("seed", 0))
+        cfg.chain_offset = int(self.opt_arg.get("chain_offset", 0))
+        self.engine = eng = ChainEngine(self.problem, cfg, self.n_chains, device=int(self.opt_arg.get("device", 0)))
+        self.t1 = time.perf_counter()
+        x0 = self._start_points()
+        eng.init_chains(x0, self._proposal_matrix(eng))
+        for key in ('MChains', 'MChains_reparam'):
+            self.IO_fileID[key].seek(0)
+        self._write_header()
+        if self.algo_name == "DRAM":                      # double __init__ writes the header twice
+            self._write_header()
+        self._write_rows(x0[:1])
+        save_all = str(self.opt_arg.get("save_all_chains", "no")) == "yes"
+        kept0, kept_all, aux_rows = [x0[0].copy()], [], []
+        done = 0
+        isde = self.algo_name == "ISDE"
+        while done < self.nIterations:
+            n = min(self._launch_len(), self.nIterations - done)
+            res = eng.run(n, thin=1, keep_samples=True, sample_chains=None if save_all else 1, keep_aux=isde)
+            eng.synchronize()
+            s = res.samples.cpu().numpy()                 # [n, d, Cs]
+            rows = np.ascontiguousarray(s[:, :, 0])
+            self._write_rows(rows)
+            if isde:
+                aux_rows.append(np.ascontiguousarray(res.aux.cpu().numpy()[:, :, 0]))
+            kept0.append(rows)
+            if save_all:
+                kept_all.append(s)
+            # model evaluations of the current (last accepted) state every save_eval_freq iterations (:366-368)
+            its = np.arange(done + 1, done + n + 1)
+            sel = its[its % self.save_eval_freq == 0]
+            if sel.size and self.save_eval_freq <= self.nIterations:
+                ev = eng.model_eval(rows[sel - done - 1])
+                for k, it in enumerate(sel):
+                    self.prob_distr.save_value(self.IO_util, int(it), ev[k])
+            done += n
+            self.it = done
+        self.chain = np.vstack([kept0[0][None, :]] + kept0[1:]) if len(kept0) > 1 else kept0[0][None, :]
+        if save_all and kept_all:
+            self.chains_all = np.concatenate(kept_all, axis=0)
+            np.save(str(self.IO_util['path']['out_folder'] / "mcmc_chains_all.npy"), self.chains_all)
+        if isde:
+            self._write_aux(x0[0], aux_rows)
+        self._finish()
+
+    def _write_aux(self, x0, aux_rows):
+        """aux_variables.csv: per iteration the d rows [P_nm, xi_nm] BEFORE the update (mha.py:1032)."""
+        if 'aux_variables' not in self.IO_fileID or not aux_rows:
+            return
+        P = np.vstack([np.zeros((1, self.n_param))] + aux_rows)
+        for it in range(self.nIterations):
+            np.savetxt(self.IO_fileID['aux_variables'], np.transpose(np.array([P[it], self.chain[it]])), fmt="%f", delimiter=",")
+
+    def _finish(self):
+        eng = self.engine
+        x, lp = eng.state()
+        ctr = eng.counters()
+        self.param_init[...] = x[0]                       # in-place: the caller's array ends at the final state (:215)
+        self.current_val = self.param_init
+        self.distr_fun_current_val = float(lp[0])
+        self.n_rejected = int(ctr["n_rejected"][0])
+        self.mean_r = float(ctr["mean_r"][0])
+        self.status = ctr["status"]
+        if np.any(ctr["status"] & 1):
+            raise np.linalg.LinAlgError("adapted covariance not positive definite in {} chain(s) "
+                                        "(scipy.linalg.cholesky raises here in the reference, mha.py:487)".format(int(np.sum(ctr["status"] & 1 > 0))))
+        prop = eng.proposal()
+        self.R = prop["R"][0]
+        self.V_i = prop["V"][0]
+        self.X_av_i = prop["X_av"][0]
+        # compute_covariance (:295-307): mean / covariance of chain 0 (from the exact states, not the 6-decimal CSV)
+        self.mean_c = np.mean(self.chain, axis=0)
+        self.cov_c = np.atleast_2d(np.cov(self.chain, rowvar=False)) if self.chain.shape[0] > 1 else np.zeros((self.n_param, self.n_param))
+        np.savetxt("cov.csv", self.cov_c, delimiter=",")
+        # many-chain statistics (new): pooled mean / covariance, Gelman-Rubin R-hat
+        self.statistics = eng.statistics() if self.n_chains > 1 else None
+        rejection_rate = 0 if self.nIterations == 0 else self.n_rejected / self.nIterations * 100
+        print("\nRejection rate is {} %".format(rejection_rate))
+        f = self.IO_fileID['out_data']                    # terminate_loop (:322-357)
+        f.write("\nRejection rate is {} % \n".format(rejection_rate))
+        f.write("\nElapsed time: {} \n".format(time.strftime("%H:%M:%S", time.gmtime(time.perf_counter() - self.t1))))
+        f.write("\nMaximum Likelihood Estimator (MLE) \n")
+        f.write("Log-likelihood value \n")
+        f.write("\nCovariance Matrix is \n{}".format(self.cov_c))
+        if self.statistics is not None:
+            f.write("\nChains: {}\nPooled mean \n{}\nPooled covariance \n{}\nGelman-Rubin R-hat \n{}".format(
+                self.n_chains, self.statistics["mean"], self.statistics["cov"], self.statistics["rhat"]))
+        for key in ('MChains', 'MChains_reparam', 'out_data'):
+            self.IO_fileID[key].flush()
+        eng.close()
+
+
+class MetropolisHastings(_DeviceSampler):
+    """Random-walk Metropolis-Hastings (mha.py:26-368)."""
+    algo_name = "RWMH"
+
+    def __init__(self, IO_util, nIterations, param_init, V, prob_distr, opt_arg):
+        self._setup(IO_util, nIterations, param_init, V, prob_distr, opt_arg)
+
+
+class AdaptiveMetropolisHastings(_DeviceSampler):
+    """Adaptive Metropolis (mha.py:370-487); starting_it is parsed and unused, as in the reference."""
+    algo_name = "AMH"
+
+    def __init__(self, IO_util, nIterations, param_init, V, prob_distr, starting_it, updating_it, eps_v, opt_arg):
+        self._setup(IO_util, nIterations, param_init, V, prob_distr, opt_arg)
+        self.starting_it, self.updating_it, self.eps_v = int(starting_it), int(updating_it), float(eps_v)
+
+    def _config(self):
+        return SamplerConfig(algo=self.algo_name, updating_it=self.updating_it, eps_v=self.eps_v,
+                             am_welford=str(self.opt_arg.get("am_welford", "no")) == "yes")
+
+
+class DelayedRejectionMetropolisHastings(_DeviceSampler):
+    """Delayed rejection (mha.py:490-567)."""
+    algo_name = "DR"
+
+    def __init__(self, IO_util, nIterations, param_init, V, prob_distr, gamma, opt_arg):
+        self._setup(IO_util, nIterations, param_init, V, prob_distr, opt_arg)
+        self.gamma = float(gamma)
+
+    def _config(self):
+        return SamplerConfig(algo=self.algo_name, gamma_dr=self.gamma)
+
+
+class DelayedRejectionAdaptiveMetropolisHastings(_DeviceSampler):
+    """DRAM (mha.py:570-595)."""
+    algo_name = "DRAM"
+
+    def __init__(self, IO_util, nIterations, param_init, V, prob_distr, starting_it, updating_it, eps_v, gamma, opt_arg):
+        self._setup(IO_util, nIterations, param_init, V, prob_distr, opt_arg)
+        self.starting_it, self.updating_it, self.eps_v, self.gamma = int(starting_it), int(updating_it), float(eps_v), float(gamma)
+
+    def _config(self):
+        return SamplerConfig(algo=self.algo_name, updating_it=self.updating_it, eps_v=self.eps_v, gamma_dr=self.gamma,
+                             am_welford=str(self.opt_arg.get("am_welford", "no")) == "yes")
+
+
+class ito_SDE(_DeviceSampler):
+    """Ito-SDE sampler (mha.py:886-1040) with the GradientBasedMCMC preconditioner options the device supports:
+    covariance.value in {"Identity", "Matrix"} (:661-664, :689-693); Hessian-based values are not lowered."""
+    algo_name = "ISDE"
+
+    def __init__(self, IO_fileID, nIterations, param_init, prob_distr, C_matrix, gradient, h, f0, opt_arg):
+        self._setup(IO_fileID, nIterations, param_init, None, prob_distr, opt_arg)
+        self.C_matrix, self.gradient, self.h, self.f0 = dict(C_matrix), gradient, float(h), float(f0)
+        if gradient not in ("Numerical", "Analytical"):
+            raise ValueError('Unknown gradient type "{}" for estimating gradients.'.format(gradient))     # :730-731
+        value = self.C_matrix.get("value", "Identity")
+        if value == "Identity":                                              # :661-664
+            self.V = None
+        elif value == "Matrix":                                              # :689-693
+            self.V = np.array(self.C_matrix["matrix_value"], dtype=np.float64)
+        elif value not in ("Hessian", "Hessian_diag"):                       # :653-660, computed in _proposal_matrix
+            from ._capi import UnsupportedProblem, PBU_ERR_UNSUPPORTED
+            raise UnsupportedProblem(PBU_ERR_UNSUPPORTED, 'preconditioner "{}" is not available on the device path '
+                                     '(Identity, Matrix, Hessian, Hessian_diag are)'.format(value))
+        self.starting_it = int(self.C_matrix['starting_it'])
+        self.update_it = int(self.C_matrix['update_it'])
+        self.end_it = int(self.C_matrix['end_it']) if self.C_matrix.get("end_it") is not None else self.nIterations + 1
+
+    def _proposal_matrix(self, eng):
+        """C_approx: identity, a given matrix, or the inverse of minus the finite-difference Hessian of the
+        log-posterior at the initial point (mha.py:653-660), its stencil evaluated in one device batch."""
+        value = self.C_matrix.get("value", "Identity")
+        if value in ("Hessian", "Hessian_diag"):
+            self.hess_mat = -compute_hessian_fd(eng.log_posterior, np.array(self.param_init, dtype=np.float64), eps=0.001,
+                                                compute_all_element=(value == "Hessian"))
+            self.V = np.linalg.inv(self.hess_mat)
+        return self.V
+
+    def _config(self):
+        return SamplerConfig(algo="ISDE", isde_h=self.h, isde_f0=self.f0, isde_gradient=self.gradient,
+                             adapt_start=self.starting_it, adapt_update=self.update_it, adapt_end=self.end_it)
+
+    def _finish(self):
+        st = self.engine.isde_state()
+        self.P_nm, self.C_approx = st["P"][0], st["C"][0]
+        _DeviceSampler._finish(self)
+        self.xi_nm = self.current_val
+        self.inv_L_c = self.R

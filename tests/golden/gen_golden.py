@@ -293,3 +293,20 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def gen_hessian_fd():
+    """computeHessianFD (mha.py:1115-1212) of a fixed smooth function, all four flag combinations; pins
+    pybitup_b200.metropolis_hastings_algorithms.compute_hessian_fd including the in-place aliasing of :1186-1189."""
+    A = np.array([[4., 1., .5, .2], [1., 3., .3, .1], [.5, .3, 2., .4], [.2, .1, .4, 1.5]])
+    x = np.array([0.7, -1.3, 2.1, 0.4])
+    f = lambda z: float(-0.5 * z @ A @ z + 0.1 * np.sin(z).sum() + 0.05 * z[0] * z[1] * z[2])   # noqa: E731
+    out = {}
+    for full in (True, False):
+        for pos in (True, False):
+            out["H_%d_%d" % (full, pos)] = mha.computeHessianFD(f, x, eps=0.001, compute_all_element=full, positive_diag=pos)
+    np.savez(os.path.join(HERE, "hessian_fd.npz"), A=A, x=x, **out)
+
+
+if __name__ == "__main__" and "--hessian" in sys.argv:
+    gen_hessian_fd()

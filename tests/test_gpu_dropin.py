@@ -1,0 +1,153 @@
+"""End to end through the reference's Python surface: JSON input -> Sampling(...).sample(models) /
+Propagation(...).propagate(models) with a bi.Model subclass, on the CUDA engine.  Checks the reference's output files
+ and the statistical known answers of the reference's own heat-conduction case (§8c)."""
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import cpu_models
+
+pytestmark = pytest.mark.gpu
+
+# posterior moments of the heat-conduction case by grid quadrature (tests/golden/gen_heat_posterior.py)
+TRUE_MEAN = np.array([-18.418010706591474, 0.0019146479526173403])
+TRUE_COV = np.array([[0.023064064360743076, -2.2297224870054396e-06], [-2.2297224870054396e-06, 2.309329769136012e-10]])
+# moments of the reference's saved DRAM chain (pybitup/test/test_pce/mcmc_chain.csv): one chain of 1e4
+# iterations, effective sample size ~146 (batch means), Monte-Carlo standard error 0.0165 on phi and 1.7e-6 on h
+REF_MEAN = np.array([-18.365, 1.9091e-3])
+REF_SE = np.array([0.0165, 1.7e-6])
+
+HEAT_JSON = """
+/* heat conduction, after pybitup/test/test_pce/heat_conduction_1.json */
+{
+  "Sampling": {
+    "BayesianPosterior": {
+      "Data": [{"Type": "ReadFromFile", "FileName": "heat_conduction_data", "xField": ["x"], "yField": ["T"], "sigmaField": ["std_T"]}],
+      "Model": [{"param_names": ["a", "b", "k", "T_amb", "phi", "h"],
+                 "param_values": [0.95, 0.95, 2.37, 21.29, -18.41, 0.00191], "parametrization": "no"}],
+      "Prior": {"Distribution": "Mixture",
+                "Param": {"phi": {"initial_val": -18.41, "prior_name": "Uniform", "prior_param": [-100, 0.0]},
+                          "h": {"initial_val": 0.00191, "prior_name": "Uniform", "prior_param": [0.00001, 1.0]}}},
+      "Likelihood": {"function": "Gaussian", "distance": "L2"}
+    },
+    "Algorithm": {
+      "name": "DRAM", // the reference's own test uses DRAM
+      "DRAM": {"starting_it": 1e2, "updating_it": 1e1, "eps_v": 1e-12, "gamma": 0.2},
+      "n_iterations": 4e3,
+      "n_chains": 64, "seed": 11, "save_eval_freq": 1000,
+      "proposal": {"name": "Gaussian", "covariance": {"type": "full", "value": [[2.1034e-2, -2.0286e-6], [-2.0286e-6, 2.0972e-10]]}}
+    }
+  },
+  "Propagation": {
+    "Model": [{"model_id": "heat", "design_points": {"filename": "design_points.csv", "field": "x"},
+               "param_names": ["a", "b", "k", "T_amb", "phi", "h"],
+               "param_values": [0.95, 0.95, 2.37, 21.29, -18.41, 0.00191], "parametrization": "no", "emulator": "None"}],
+    "Uncertain_param": {"phi": {"filename": "output/mcmc_chain.csv", "field": 0}, "h": {"filename": "output/mcmc_chain.csv", "field": 1}},
+    "Model_evaluation": {}
+  }
+}
+"""
+
+
+def _heat_model():
+    from pybitup_b200 import bayesian_inference as bi
+
+    class HeatConduction(bi.Model):
+        device_model = "heat"
+
+        def fun_x(self):
+            return cpu_models.heat_conduction(self.param, np.asarray(self.x, dtype=np.float64))
+
+    return HeatConduction()
+
+
+def test_sampling_and_propagation_from_json(tmp_path, monkeypatch):
+    from pybitup_b200 import synthetic
+    from pybitup_b200.solve_problem import Sampling, Propagation
+    monkeypatch.chdir(tmp_path)
+    p = synthetic.heat_problem()
+    pd.DataFrame({"x": p["design"]["x"], "T": p["y"][0], "std_T": p["std_y"]}).to_csv("heat_conduction_data.csv", index=False)
+    pd.DataFrame({"x": np.linspace(10.0, 66.0, 29)}).to_csv("design_points.csv", index=False)
+    with open("heat.json", "w") as f:
+        f.write(HEAT_JSON)
+    model = _heat_model()
+    job = Sampling("heat.json")
+    run = job.sample({"heat": model})
+    job.close()
+    T = 4000
+    chain = pd.read_csv("output/mcmc_chain.csv", header=None).values
+    assert chain.shape == (T + 1, 2) and np.allclose(chain[0], [-18.41, 0.00191])
+    assert pd.read_csv("output/mcmc_chain_reparam.csv", header=None).values.shape == (T + 1, 2)
+    lines = open("output/output.txt").read().splitlines()
+    assert lines[0] == "$RandomVarName$" and lines[1].split() == ["phi", "h"] and int(lines[3]) == T     # post_process.py:41-50
+    assert "Rejection rate is" in "\n".join(lines) and "Covariance Matrix is" in "\n".join(lines)
+    assert np.loadtxt("cov.csv", delimiter=",").shape == (2, 2)
+    ev = np.load("output/model_eval/heat_fun_eval-1000.npy")
+    assert ev.shape == (15,) and np.allclose(ev, cpu_models.heat_conduction(
+        np.array([0.95, 0.95, 2.37, 21.29, run.chain[1000, 0], run.chain[1000, 1]]), p["design"]["x"]), rtol=1e-11)
+    assert os.path.exists("output/data.bin")
+    # the caller's initial vector was updated in place to the final state (mha.py:95-99, :215)
+    assert np.array_equal(run.param_init, run.chain[-1]) and not np.array_equal(run.chain[-1], [-18.41, 0.00191])
+    # statistical known answer: pooled posterior moments of 64 chains vs the reference's saved chain
+    st = run.statistics
+    assert st["n_chains"] == 64 and st["n"] == 64 * T
+    assert np.all(np.abs(st["mean"] - TRUE_MEAN) < 5 * np.sqrt(np.diag(TRUE_COV)) / np.sqrt(64 * T / 30.0))
+    assert np.all(np.abs(st["cov"] - TRUE_COV) < 0.1 * np.abs(TRUE_COV))
+    assert np.all(np.abs(st["mean"] - REF_MEAN) < 4 * REF_SE)          # within the reference chain's own Monte-Carlo error
+    assert np.all(st["rhat"] < 1.1)
+    assert 0.3 < 1.0 - run.n_rejected / T < 0.99
+
+    # ---- propagation of the chain through the model (solve_problem.py:467-647)
+    res = Propagation("heat.json").propagate({"heat": _heat_model()})["heat"]
+    xs = pd.read_csv("output/mcmc_chain.csv").values          # first row becomes the header, as in the reference (Q15)
+    x_design = np.linspace(10.0, 66.0, 29)
+    fe = np.array([cpu_models.heat_conduction(np.array([0.95, 0.95, 2.37, 21.29, s[0], s[1]]), x_design) for s in xs])
+    assert res["n_samples"] == T
+    assert np.allclose(res["mean"], fe.mean(axis=0), rtol=1e-11)
+    assert np.allclose(res["ci_lb"], np.percentile(fe, 2.5, axis=0), rtol=1e-10)
+    assert np.allclose(res["ci_ub"], np.percentile(fe, 97.5, axis=0), rtol=1e-10)
+    ci = pd.read_csv("output/heat_CI.csv")
+    iv = pd.read_csv("output/heat_interval.csv")
+    assert list(ci.columns) == ["x", "CI_lb", "CI_ub"] and list(iv.columns) == ["x", "mean", "lower_bound", "upper_bound"]
+    assert np.allclose(iv["upper_bound"], fe.max(axis=0), rtol=1e-11) and len(ci) == 29
+
+
+def test_isde_from_json_on_cubic(tmp_path, monkeypatch):
+    from pybitup_b200 import synthetic, bayesian_inference as bi
+    from pybitup_b200.solve_problem import Sampling
+    monkeypatch.chdir(tmp_path)
+    p = synthetic.cubic_problem(n_points=400)
+    pd.DataFrame({"x": p["design"]["x"], "y": p["y"][0], "s": p["std_y"]}).to_csv("cubic.csv", index=False)
+
+    class Cubic(bi.Model):
+        device_model = "poly"
+
+    T = 1500
+    cfg = {"Sampling": {"BayesianPosterior": {
+        "Data": [{"Type": "ReadFromFile", "FileName": "cubic", "xField": ["x"], "yField": ["y"], "sigmaField": ["s"]}],
+        "Model": [{"param_names": ["c0", "c1", "c2", "c3"], "param_values": [1.0, -2.0, 0.5, 3.0]}],
+        "Prior": {"Distribution": "Mixture", "Param": {n: {"initial_val": v, "prior_name": "Uniform", "prior_param": [-10, 10]}
+                                                      for n, v in zip(["c0", "c1", "c2", "c3"], [1.0, -2.0, 0.5, 3.0])}},
+        "Likelihood": {"function": "Gaussian"}},
+        "Algorithm": {"name": "ISDE", "n_iterations": T, "n_chains": 32, "seed": 5, "save_eval_freq": 1e9,
+                      "covariance": {"value": "Hessian_diag", "starting_it": 200, "update_it": 50, "end_it": 1000},
+                      "gradient": "Analytical", "ISDE": {"h": 0.3, "f0": 4.0}}}}
+    with open("cubic.json", "w") as f:
+        json.dump(cfg, f)
+    job = Sampling("cubic.json")
+    run = job.sample({"cubic": Cubic()})
+    job.close()
+    assert pd.read_csv("output/mcmc_chain.csv", header=None).values.shape == (T + 1, 4)
+    aux = pd.read_csv("output/aux_variables.csv", header=None).values
+    assert aux.shape == (T * 4, 2) and np.all(aux[:4, 0] == 0.0)          # first rows: P_0 = 0, xi_0
+    # posterior of a linear-Gaussian problem: mean = least squares solution, cov = (Phi^T Phi)^-1 sigma^2
+    x = p["design"]["x"]
+    Phi = np.stack([x ** j for j in range(4)], axis=1)
+    cov = np.linalg.inv(Phi.T @ Phi) * 0.1 ** 2
+    mean = cov @ Phi.T @ p["y"][0] / 0.1 ** 2
+    st = run.statistics
+    assert np.all(np.abs(st["mean"] - mean) < 4 * np.sqrt(np.diag(cov)) / np.sqrt(32 * 20))
+    assert np.all(np.abs(np.diag(st["cov"]) / np.diag(cov) - 1.0) < 0.35)
