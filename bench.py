@@ -41,7 +41,7 @@ if ROOT not in sys.path:
 METRIC = "chain-steps/sec"
 UNIT = "chain-steps/s"
 CHAINS_PER_GPU = 65536
-ITERS_PER_STEP = 100
+ITERS_PER_STEP = 1000
 N_POINTS = 1000
 D = 4
 WORKLOAD = "cubic polynomial (Horner), d=4, N=1000, adaptive Metropolis (updating_it=10, eps_v=1e-10), " \
@@ -71,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
@@ -197,7 +197,8 @@ def run_gpu_arm(args):
     cfg = SamplerConfig(algo="AMH", seed=2026, chain_offset=rank * C, **AM)
     x0 = synthetic.chain_starts(p["x0"], C, jitter=0.01, seed=1000 + rank)
 
-    fp64_peak, _ = _capi.measure_fp64_peak(local_rank, 4096, 5)
+    fp64_burst, _ = _capi.measure_fp64_peak(local_rank, 4096, 5)
+    fp64_peak, _ = _capi.measure_fp64_peak(local_rank, 4096, -150)        # ~0.7 s of back-to-back DFMA launches
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -294,8 +295,10 @@ def run_gpu_arm(args):
                          "frac": achieved / fp64_peak, "traffic": None,
                          "kernel": "mh_step_kernel<PolyModel<4>,4,G,adapt>",
                          "flops_per_chain_step": FLOPS_PER_CHAIN_STEP,
-                         "peak_source": "live DFMA micro-benchmark on this GPU (pbu_measure_fp64_peak); "
-                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "peak_source": "live DFMA micro-benchmark on this GPU, sustained over ~0.7 s of back-to-back launches "
+                                        "(pbu_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                         "peak_burst": fp64_burst, "ms_per_launch": {"min": float(min(ms)), "median": float(np.median(ms)),
+                                                                     "max": float(max(ms))},
                          "hbm": {"achieved": bytes_launch / (ms_launch * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": bytes_launch / (ms_launch * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src}},
             "cpu_baseline": cpu,

@@ -218,7 +218,8 @@ int pbu_propagation_select_result(pbu_propagation *p, double *values_host /*[N][
 int pbu_propagation_get_evals(pbu_propagation *p, int64_t s0, int64_t n, double *f_host);
 
 /* ---- measurement helper: achieved FP64 FMA throughput of the device (TFLOP/s, FMA = 2 flops) from a
- *      register-resident DFMA loop; the denominator of the FP64 roofline in bench.py ------------- */
+ *      register-resident DFMA loop; the denominator of the FP64 roofline in bench.py.  reps > 0: best of `reps`
+ *      launches (burst); reps < 0: mean of -reps launches back to back (sustained) ---------------- */
 int pbu_measure_fp64_peak(int device, int iters, int reps, double *tflops, double *ms);
 
 #ifdef __cplusplus

@@ -144,7 +144,8 @@ def list_kernels():
 
 
 def measure_fp64_peak(device=0, iters=4096, reps=5):
-    """Achieved FP64 TFLOP/s of a register-resident DFMA loop (FMA = 2 flops)."""
+    """Achieved FP64 TFLOP/s of a register-resident DFMA loop (FMA = 2 flops); reps < 0: sustained mean of -reps
+    back-to-back launches."""
     tf, ms = C.c_double(0.0), C.c_double(0.0)
     check(lib.pbu_measure_fp64_peak(device, iters, reps, C.byref(tf), C.byref(ms)))
     return tf.value, ms.value

@@ -75,8 +75,8 @@ extern "C" __attribute__((visibility("default"))) int pbu_list_kernels(char *buf
     int n = 0;
     for (const MhKernelEntry *t = pbu_mh_kernels(&n); t && s.size() < 1u << 20 && n > 0; --n, ++t) {
         char line[128];
-        snprintf(line, sizeof line, "mh model=%d P=%d d=%d lanes=%d chains_per_thread=%d algo=%d\n", t->model, t->n_param, t->n_unc,
-                 t->lanes, t->chains_per_thread, t->algo);
+        snprintf(line, sizeof line, "mh model=%d P=%d d=%d lanes=%d chains_per_thread=%d algo=%d streamed=%d\n", t->model, t->n_param, t->n_unc,
+                 t->lanes, t->chains_per_thread, t->algo, t->streamed);
         s += line;
     }
     int total = 0;
@@ -88,20 +88,22 @@ extern "C" __attribute__((visibility("default"))) int pbu_list_kernels(char *buf
     return total;
 }
 
-static const MhKernelEntry *find_mh(int model, int P, int d, int lanes, int q, int algo) {
+static const MhKernelEntry *find_mh(int model, int P, int d, int lanes, int q, int algo, int streamed) {
     int n = 0;
     const MhKernelEntry *t = pbu_mh_kernels(&n);
     for (int i = 0; i < n; ++i)
         if (t[i].model == model && t[i].n_param == P && t[i].n_unc == d && t[i].lanes == lanes && t[i].chains_per_thread == q &&
-            t[i].algo == algo)
+            t[i].algo == algo && t[i].streamed == streamed)
             return &t[i];
     return nullptr;
 }
-static const IsdeKernelEntry *find_isde(int model, int P, int d, int lanes, int q) {
+static const IsdeKernelEntry *find_isde(int model, int P, int d, int lanes, int q, int streamed) {
     int n = 0;
     const IsdeKernelEntry *t = pbu_isde_kernels(&n);
     for (int i = 0; i < n; ++i)
-        if (t[i].model == model && t[i].n_param == P && t[i].n_unc == d && t[i].lanes == lanes && t[i].chains_per_thread == q) return &t[i];
+        if (t[i].model == model && t[i].n_param == P && t[i].n_unc == d && t[i].lanes == lanes && t[i].chains_per_thread == q &&
+            t[i].streamed == streamed)
+            return &t[i];
     return nullptr;
 }
 static const EvalKernelEntry *find_eval(int model, int P, int d) {
@@ -188,6 +190,7 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
     const double S0 = 60.0 + 15.0 * e->d;           // per-iteration scalar part (RNG, proposal, accept, adaptation), in DFMA-equivalents
     const int cand[5][2] = {{1, 1}, {1, 2}, {2, 2}, {4, 2}, {8, 1}};     // (lanes per chain, chains per thread)
     const bool isde = algo == PBU_ALGO_ISDE;
+    const int streamed = e->tile_points < e->prob.n_points ? 1 : 0;
     const double ops = isde ? 2.0 * e->ev->ops : (double)e->ev->ops;     // value + gradient
     double best = 1e300;
     bool found = false;
@@ -205,10 +208,10 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
         const MhKernelEntry *km = nullptr;
         const IsdeKernelEntry *ki = nullptr;
         if (isde) {
-            ki = find_isde(model, e->P, e->d, g, q);
+            ki = find_isde(model, e->P, e->d, g, q, streamed);
             if (ki) fn = ki->fn;
         } else {
-            km = find_mh(model, e->P, e->d, g, q, algo);
+            km = find_mh(model, e->P, e->d, g, q, algo, streamed);
             if (km) fn = km->fn;
         }
         if (!fn) continue;
@@ -296,7 +299,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
             return fail(PBU_ERR_INVALID, "ISDE needs h > 0 and f0 >= 0");
         }
         if (cfg->isde_gradient == 0) {
-            const IsdeKernelEntry *k = find_isde(pr->model, pr->n_param, pr->n_unc, 1, 1);
+            const IsdeKernelEntry *k = find_isde(pr->model, pr->n_param, pr->n_unc, 1, 1, 0);
             if (!k || !k->has_grad) {
                 delete e;
                 return fail(PBU_ERR_UNSUPPORTED, "model %d has no analytical gradient on the device; use gradient \"Numerical\"", pr->model);
@@ -347,7 +350,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
             smem = 128 + all;
             return;
         }
-        const size_t slot = std::min<size_t>(65536, ((size_t)max_smem - 128) / TileStream::S);
+        const size_t slot = std::min<size_t>(65536, ((size_t)max_smem - 128) / TileStream<2>::S);
         tile_points = (int)(slot / rec_bytes);
         if (want_tile > 0) tile_points = std::min(tile_points, want_tile);
         tile_points = std::max(1, std::min(tile_points, pr->n_points));
@@ -355,7 +358,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
             tile_points = pr->n_points;
             smem = 128 + all;
         } else {
-            smem = 128 + (size_t)TileStream::S * tile_points * rec_bytes;
+            smem = 128 + (size_t)TileStream<2>::S * tile_points * rec_bytes;
         }
     };
     plan_tiles((size_t)ev->nc * 8, cfg->tile_points, e->tile_points, e->smem_bytes);

@@ -3,20 +3,25 @@
 #include "pbu_isde_kernel.cuh"
 #include "pbu_registry.h"
 
-#define PBU_MH(MODEL, P, D, G, Q, A) \
-    { MODEL::ID, P, D, G, Q, A, (const void *)&pbu::mh_step_kernel<MODEL, D, G, A, Q> }
-#define PBU_MH_ALGOS(MODEL, P, D, G, Q) \
-    PBU_MH(MODEL, P, D, G, Q, 0), PBU_MH(MODEL, P, D, G, Q, 1), PBU_MH(MODEL, P, D, G, Q, 2), PBU_MH(MODEL, P, D, G, Q, 3)
-// data-parallel models, (lanes per chain, chains per thread): (1,1) (1,2) (2,2) (4,2) and (8,1) for very few chains
-#define PBU_MH_ALL(MODEL, P, D)                                                                                  \
-    PBU_MH_ALGOS(MODEL, P, D, 1, 1), PBU_MH_ALGOS(MODEL, P, D, 1, 2), PBU_MH_ALGOS(MODEL, P, D, 2, 2),           \
-        PBU_MH_ALGOS(MODEL, P, D, 4, 2), PBU_MH_ALGOS(MODEL, P, D, 8, 1)
-#define PBU_MH_SEQ(MODEL, P, D) PBU_MH_ALGOS(MODEL, P, D, 1, 1)
-// Ito-SDE step kernel variants (lanes per chain, chains per thread)
-#define PBU_ISDE(MODEL, P, D, G, Q) \
-    { MODEL::ID, P, D, G, Q, MODEL::HAS_GRAD ? 1 : 0, (const void *)&pbu::isde_step_kernel<MODEL, D, G, Q> }
-#define PBU_ISDE_ALL(MODEL, P, D) PBU_ISDE(MODEL, P, D, 1, 1), PBU_ISDE(MODEL, P, D, 1, 2), PBU_ISDE(MODEL, P, D, 2, 2), PBU_ISDE(MODEL, P, D, 8, 1)
-#define PBU_ISDE_SEQ(MODEL, P, D) PBU_ISDE(MODEL, P, D, 1, 1)
+// S = 0: records resident in shared memory; S = 1: streamed in tiles (data sets larger than shared memory)
+#define PBU_MH(MODEL, P, D, G, Q, A, S) \
+    { MODEL::ID, P, D, G, Q, A, S, (const void *)&pbu::mh_step_kernel<MODEL, D, G, A, Q, (S != 0)> }
+#define PBU_MH_ALGOS(MODEL, P, D, G, Q, S) \
+    PBU_MH(MODEL, P, D, G, Q, 0, S), PBU_MH(MODEL, P, D, G, Q, 1, S), PBU_MH(MODEL, P, D, G, Q, 2, S), PBU_MH(MODEL, P, D, G, Q, 3, S)
+// data-parallel models, (lanes per chain, chains per thread): (1,1) (1,2) (2,2) (4,2), (8,1) for very few chains;
+// streamed: (1,1) (1,2) (8,1)
+#define PBU_MH_ALL(MODEL, P, D)                                                                                        \
+    PBU_MH_ALGOS(MODEL, P, D, 1, 1, 0), PBU_MH_ALGOS(MODEL, P, D, 1, 2, 0), PBU_MH_ALGOS(MODEL, P, D, 2, 2, 0),        \
+        PBU_MH_ALGOS(MODEL, P, D, 4, 2, 0), PBU_MH_ALGOS(MODEL, P, D, 8, 1, 0), PBU_MH_ALGOS(MODEL, P, D, 1, 1, 1),    \
+        PBU_MH_ALGOS(MODEL, P, D, 1, 2, 1), PBU_MH_ALGOS(MODEL, P, D, 8, 1, 1)
+#define PBU_MH_SEQ(MODEL, P, D) PBU_MH_ALGOS(MODEL, P, D, 1, 1, 0), PBU_MH_ALGOS(MODEL, P, D, 1, 1, 1)
+// Ito-SDE step kernel variants (lanes per chain, chains per thread, streamed)
+#define PBU_ISDE(MODEL, P, D, G, Q, S) \
+    { MODEL::ID, P, D, G, Q, MODEL::HAS_GRAD ? 1 : 0, S, (const void *)&pbu::isde_step_kernel<MODEL, D, G, Q, (S != 0)> }
+#define PBU_ISDE_ALL(MODEL, P, D)                                                                                   \
+    PBU_ISDE(MODEL, P, D, 1, 1, 0), PBU_ISDE(MODEL, P, D, 1, 2, 0), PBU_ISDE(MODEL, P, D, 2, 2, 0), PBU_ISDE(MODEL, P, D, 8, 1, 0), \
+        PBU_ISDE(MODEL, P, D, 1, 1, 1), PBU_ISDE(MODEL, P, D, 1, 2, 1), PBU_ISDE(MODEL, P, D, 8, 1, 1)
+#define PBU_ISDE_SEQ(MODEL, P, D) PBU_ISDE(MODEL, P, D, 1, 1, 0), PBU_ISDE(MODEL, P, D, 1, 1, 1)
 #define PBU_EVAL(MODEL, P, D)                                                                 \
     { MODEL::ID, P, D, MODEL::SEQUENTIAL ? 1 : 0, MODEL::NC, MODEL::NCR, MODEL::OPS, MODEL::WF, (const void *)&pbu::eval_logpost_kernel<MODEL, D>, \
       (const void *)&pbu::eval_model_kernel<MODEL, D> }

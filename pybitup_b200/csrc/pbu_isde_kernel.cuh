@@ -69,9 +69,9 @@ __device__ __forceinline__ void inv_upper_packed(const double (&R)[tri_size(D)],
 }
 
 // Gradient of the log-likelihood (and the log-posterior value) at x for the Q chains of a thread.
-template <class M, int D, int G, int Q>
-__device__ __forceinline__ void grad_log_like(const double (&x)[Q][D], const ProblemDev &prob, TileStream &ts, int sub, unsigned group_mask,
-                                              double (&grad)[Q][D], double (&lp)[Q]) {
+template <class M, int D, int G, int Q, bool STREAM>
+__device__ __forceinline__ void grad_log_like(const double (&x)[Q][D], const ProblemDev &prob, TileStream<M::NC> &ts, int tile_points, int sub,
+                                              unsigned group_mask, double (&grad)[Q][D], double (&lp)[Q]) {
     constexpr int U = (M::UNROLL > 2) ? 2 : M::UNROLL;
     constexpr int NP = M::NPARAM;
     typename M::Ctx ctx[Q];
@@ -85,12 +85,20 @@ __device__ __forceinline__ void grad_log_like(const double (&x)[Q][D], const Pro
 #pragma unroll
         for (int j = 0; j < (M::HAS_GRAD ? NP : 1); ++j) g[q][j] = 0.0;
     }
-    ts.begin_pass();
-    for (int t = 0; t < ts.n_tiles; ++t) {
-        int cnt;
-        const double *tile = ts.acquire(t, cnt);
-        tile_accumulate<M, G, Q, U, M::HAS_GRAD>(ctx, seq, tile, cnt, sub, J, g);
-        ts.release(t);
+    if constexpr (!STREAM) {
+        tile_accumulate<M, G, Q, U, M::HAS_GRAD>(ctx, seq, reinterpret_cast<const double *>(TileStream<M::NC>::smem() + 128), prob.n_points, sub,
+                                                 J, g);
+    } else {
+        const double *const records = prob.records;
+        const int n = prob.n_points;
+        ts.begin_pass(records, n, tile_points);
+        const int nt = TileStream<M::NC>::n_tiles(n, tile_points);
+        for (int t = 0; t < nt; ++t) {
+            int cnt;
+            const double *tile = ts.acquire(n, tile_points, t, cnt);
+            tile_accumulate<M, G, Q, U, M::HAS_GRAD>(ctx, seq, tile, cnt, sub, J, g);
+            ts.release(records, n, tile_points, t);
+        }
     }
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
@@ -112,12 +120,11 @@ __device__ __forceinline__ void grad_log_like(const double (&x)[Q][D], const Pro
     }
 }
 
-template <class M, int D, int G, int Q>
+template <class M, int D, int G, int Q, bool STREAM>
 __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) isde_step_kernel(const __grid_constant__ IsdeParams p) {
     constexpr int NT = tri_size(D);
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileStream ts;
-    ts.init(smem_raw, p.prob.records, p.prob.n_points, p.tile_points, M::NC);
+    TileStream<M::NC> ts;
+    ts.init(p.prob.records, p.prob.n_points, p.tile_points);
 
     const int64_t C = p.st.n_chains;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) isde_step_kernel(const __grid
         // ---- gradient at xi_n (:994)
         double grad[Q][D], lpn[Q];
         if (!p.fd_gradient) {
-            grad_log_like<M, D, G, Q>(xn, p.prob, ts, sub, group_mask, grad, lpn);
+            grad_log_like<M, D, G, Q, STREAM>(xn, p.prob, ts, p.tile_points, sub, group_mask, grad, lpn);
 #pragma unroll
             for (int q = 0; q < Q; ++q) n_eval[q] += 1;
         } else {
@@ -250,7 +257,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) isde_step_kernel(const __grid
             double f0v[Q], fp[Q], xp[Q][D];
 #pragma unroll
             for (int q = 0; q < Q; ++q) want[q] = true;
-            log_posterior<M, D, G, Q>(xn, want, p.prob, ts, sub, group_mask, f0v);
+            log_posterior<M, D, G, Q, STREAM>(xn, want, p.prob, ts, p.tile_points, sub, group_mask, f0v);
 #pragma unroll 1
             for (int i = 0; i < D; ++i) {
                 double delta[Q];
@@ -268,7 +275,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) isde_step_kernel(const __grid
                     for (int j = 0; j < D; ++j)
                         if (j == i) xp[q][j] = __dadd_rn(xv, delta[q]);
                 }
-                log_posterior<M, D, G, Q>(xp, want, p.prob, ts, sub, group_mask, fp);
+                log_posterior<M, D, G, Q, STREAM>(xp, want, p.prob, ts, p.tile_points, sub, group_mask, fp);
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
                     const double gi = (fp[q] - f0v[q]) / delta[q];

@@ -40,73 +40,72 @@ constexpr int MH_MAX_BLOCK = 512;
 //               one read of the records per block and pass, served by L2 (the record set is shared by
 //               every block of every launch).
 // ------------------------------------------------------------------------------------------------
+// The stream keeps ONE register of state (tiles consumed so far); everything else is re-derived from kernel
+// parameters (constant bank) and the compile-time record size, so the resident path costs the data loop nothing.
+template <int NCOL>
 struct TileStream {
-    static constexpr int S = 2;          // ring slots
-    const char *gsrc;                    // records in global memory
-    char *buf;                           // S slots of slot_bytes each
-    uint64_t *full;                      // S mbarriers
-    uint32_t rec_bytes;                  // bytes per record
-    uint32_t slot_bytes;
-    int n_points, tile_points, n_tiles;
-    uint32_t tseq;                       // tiles consumed so far by this block (selects slot and mbarrier phase)
-    bool resident;
+    static constexpr int S = 2;                      // ring slots
+    static constexpr uint32_t REC = NCOL * 8u;       // bytes per record
+    uint32_t tseq;                                   // tiles consumed so far by this block (selects slot and mbarrier phase)
 
-    __device__ __forceinline__ void issue(int tile, uint32_t slot) {
+    static __device__ __forceinline__ unsigned char *smem() {
+        extern __shared__ __align__(128) unsigned char pbu_smem[];
+        return pbu_smem;                             // [S mbarriers, padded to 128 B][slot 0][slot 1]
+    }
+    static __device__ __forceinline__ uint64_t *full() { return reinterpret_cast<uint64_t *>(smem()); }
+    static __device__ __forceinline__ char *slot_ptr(uint32_t slot, int tile_points) {
+        return reinterpret_cast<char *>(smem() + 128) + (size_t)slot * (uint32_t)tile_points * REC;
+    }
+    static __device__ __forceinline__ bool resident(int n, int tile_points) { return tile_points >= n; }
+    static __device__ __forceinline__ int n_tiles(int n, int tile_points) { return (n + tile_points - 1) / tile_points; }
+
+    static __device__ __forceinline__ void issue(const double *records, int n, int tile_points, int tile, uint32_t slot) {
         const int first = tile * tile_points;
-        const int cnt = (n_points - first < tile_points) ? (n_points - first) : tile_points;
-        const uint32_t bytes = (uint32_t)cnt * rec_bytes;
-        uint64_t *bar = full + slot;
+        const int cnt = (n - first < tile_points) ? (n - first) : tile_points;
+        const uint32_t bytes = (uint32_t)cnt * REC;
+        uint64_t *bar = full() + slot;
         mbar_expect_tx(bar, bytes);
         const uint32_t CH = 32768u;
         for (uint32_t off = 0; off < bytes; off += CH) {
-            const uint32_t n = (bytes - off < CH) ? (bytes - off) : CH;
-            tma_load_1d(buf + (size_t)slot * slot_bytes + off, gsrc + (size_t)first * rec_bytes + off, n, bar);
+            const uint32_t m = (bytes - off < CH) ? (bytes - off) : CH;
+            tma_load_1d(slot_ptr(slot, tile_points) + off, reinterpret_cast<const char *>(records) + (size_t)first * REC + off, m, bar);
         }
     }
-    // smem layout: [S mbarriers, padded to 128 B][slot 0][slot 1]...
-    __device__ __forceinline__ void init(unsigned char *smem, const double *records, int n, int tile_pts, int ncol) {
-        full = reinterpret_cast<uint64_t *>(smem);
-        buf = reinterpret_cast<char *>(smem + 128);
-        gsrc = reinterpret_cast<const char *>(records);
-        rec_bytes = (uint32_t)ncol * 8u;
-        n_points = n;
-        tile_points = tile_pts;
-        n_tiles = (n + tile_pts - 1) / tile_pts;
-        resident = (n_tiles == 1);
-        slot_bytes = (uint32_t)tile_pts * rec_bytes;
+    __device__ __forceinline__ void init(const double *records, int n, int tile_points) {
         tseq = 0;
         if (threadIdx.x == 0) {
-            for (int i = 0; i < S; ++i) mbar_init(full + i, 1);
+            for (int i = 0; i < S; ++i) mbar_init(full() + i, 1);
             mbar_fence_init();
         }
         __syncthreads();
-        if (resident) {
-            if (threadIdx.x == 0) issue(0, 0);
-            mbar_wait(full, 0);
+        if (resident(n, tile_points)) {
+            if (threadIdx.x == 0) issue(records, n, tile_points, 0, 0);
+            mbar_wait(full(), 0);
         }
     }
-    __device__ __forceinline__ void begin_pass() {
-        if (resident) return;
+    __device__ __forceinline__ void begin_pass(const double *records, int n, int tile_points) {
+        if (resident(n, tile_points)) return;
         if (threadIdx.x == 0) {
-            for (int i = 0; i < S && i < n_tiles; ++i) issue(i, (tseq + i) % S);
+            const int nt = n_tiles(n, tile_points);
+            for (int i = 0; i < S && i < nt; ++i) issue(records, n, tile_points, i, (tseq + i) % S);
         }
     }
     // points of tile t of the current pass; blocks until the tile has landed
-    __device__ __forceinline__ const double *acquire(int t, int &count) {
-        if (resident) {
-            count = n_points;
-            return reinterpret_cast<const double *>(buf);
+    __device__ __forceinline__ const double *acquire(int n, int tile_points, int t, int &count) {
+        if (resident(n, tile_points)) {
+            count = n;
+            return reinterpret_cast<const double *>(smem() + 128);
         }
         const uint32_t slot = tseq % S;
-        mbar_wait(full + slot, (tseq / S) & 1u);
+        mbar_wait(full() + slot, (tseq / S) & 1u);
         const int first = t * tile_points;
-        count = (n_points - first < tile_points) ? (n_points - first) : tile_points;
-        return reinterpret_cast<const double *>(buf + (size_t)slot * slot_bytes);
+        count = (n - first < tile_points) ? (n - first) : tile_points;
+        return reinterpret_cast<const double *>(slot_ptr(slot, tile_points));
     }
-    __device__ __forceinline__ void release(int t) {
-        if (resident) return;
+    __device__ __forceinline__ void release(const double *records, int n, int tile_points, int t) {
+        if (resident(n, tile_points)) return;
         __syncthreads();                                    // every thread is done with the slot
-        if (threadIdx.x == 0 && t + S < n_tiles) issue(t + S, tseq % S);
+        if (threadIdx.x == 0 && t + S < n_tiles(n, tile_points)) issue(records, n, tile_points, t + S, tseq % S);
         tseq += 1;
     }
 };
@@ -230,9 +229,9 @@ __device__ __forceinline__ void begin_chain(const double (&x)[D], const ProblemD
 // parametrisation, for the Q chains of a thread: -inf outside the prior box WITHOUT evaluating the
 // model (:53-55), otherwise log_prior - log(1) + (-(1/2) J).  In resident mode the data pass is skipped
 // when no chain of the thread needs it.
-template <class M, int D, int G, int Q>
-__device__ __forceinline__ void log_posterior(const double (&x)[Q][D], const bool (&want)[Q], const ProblemDev &prob, TileStream &ts, int sub,
-                                              unsigned group_mask, double (&lp)[Q]) {
+template <class M, int D, int G, int Q, bool STREAM>
+__device__ __forceinline__ void log_posterior(const double (&x)[Q][D], const bool (&want)[Q], const ProblemDev &prob, TileStream<M::NC> &ts,
+                                              int tile_points, int sub, unsigned group_mask, double (&lp)[Q]) {
     constexpr int U = M::UNROLL;   // tools/ubench: U = 4 points x Q = 2 chains in flight reaches 83% of the DFMA peak at 12 warps/SM
     bool inb[Q], any = false;
 #pragma unroll
@@ -241,7 +240,7 @@ __device__ __forceinline__ void log_posterior(const double (&x)[Q][D], const boo
         any = any || inb[q];
         lp[q] = -INFINITY;
     }
-    if (ts.resident && !any) return;      // streaming: the whole block walks the tiles together
+    if (!STREAM && !any) return;          // streaming: the whole block walks the tiles together
     typename M::Ctx ctx[Q];
     typename M::Seq seq[Q];
     double J[Q][U], gdummy[Q][1];
@@ -251,12 +250,20 @@ __device__ __forceinline__ void log_posterior(const double (&x)[Q][D], const boo
 #pragma unroll
         for (int u = 0; u < U; ++u) J[q][u] = 0.0;
     }
-    ts.begin_pass();
-    for (int t = 0; t < ts.n_tiles; ++t) {
-        int cnt;
-        const double *tile = ts.acquire(t, cnt);
-        if (any) tile_accumulate<M, G, Q, U, false>(ctx, seq, tile, cnt, sub, J, gdummy);
-        ts.release(t);
+    if constexpr (!STREAM) {
+        tile_accumulate<M, G, Q, U, false>(ctx, seq, reinterpret_cast<const double *>(TileStream<M::NC>::smem() + 128), prob.n_points, sub, J,
+                                           gdummy);
+    } else {
+        const double *const records = prob.records;
+        const int n = prob.n_points;
+        ts.begin_pass(records, n, tile_points);
+        const int nt = TileStream<M::NC>::n_tiles(n, tile_points);
+        for (int t = 0; t < nt; ++t) {
+            int cnt;
+            const double *tile = ts.acquire(n, tile_points, t, cnt);
+            if (any) tile_accumulate<M, G, Q, U, false>(ctx, seq, tile, cnt, sub, J, gdummy);
+            ts.release(records, n, tile_points, t);
+        }
     }
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
@@ -327,14 +334,13 @@ __device__ __forceinline__ bool draw_injected(const StreamsDev &s, int64_t c, bo
 // The kernel.  ALGO = pbu_algo_id of the MH family: bit 0 adaptive (AM, DRAM), bit 1 delayed
 // rejection (DR, DRAM).  Q = chains per thread; thread group g owns chains g, g + n_groups, ...
 // ------------------------------------------------------------------------------------------------
-template <class M, int D, int G, int ALGO, int Q>
+template <class M, int D, int G, int ALGO, int Q, bool STREAM>
 __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_constant__ MhParams p) {
     constexpr bool ADAPT = (ALGO & 1) != 0;
     constexpr bool DELAYED = (ALGO & 2) != 0;
     constexpr int NT = tri_size(D);
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileStream ts;
-    ts.init(smem_raw, p.prob.records, p.prob.n_points, p.tile_points, M::NC);
+    TileStream<M::NC> ts;
+    ts.init(p.prob.records, p.prob.n_points, p.tile_points);
 
     const int64_t C = p.st.n_chains;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -404,7 +410,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_c
                 }
                 n_eval[q] += 1;
             }
-            log_posterior<M, D, G, Q>(y, want, p.prob, ts, sub, group_mask, lpy);
+            log_posterior<M, D, G, Q, STREAM>(y, want, p.prob, ts, p.tile_points, sub, group_mask, lpy);
             bool again = false;
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
@@ -457,7 +463,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_c
                     want[q] = false;
                 }
             }
-            if (!ts.resident) again = __syncthreads_or(again) != 0;     // streaming: the block walks the tiles together
+            if (STREAM) again = __syncthreads_or(again) != 0;     // streaming: the block walks the tiles together
             if (!again) break;
         }
 
@@ -601,9 +607,8 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_c
 template <class M, int D>
 __global__ void __launch_bounds__(256) eval_logpost_kernel(const __grid_constant__ ProblemDev prob, const double *X /*[d][S]*/, int64_t S,
                                                            double *lp_out, int tile_points) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileStream ts;
-    ts.init(smem_raw, prob.records, prob.n_points, tile_points, M::NC);
+    TileStream<M::NC> ts;
+    ts.init(prob.records, prob.n_points, tile_points);
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool livet = t < S;
     if (!livet) t = S - 1;                  // all threads of the block walk the tiles together
@@ -611,7 +616,7 @@ __global__ void __launch_bounds__(256) eval_logpost_kernel(const __grid_constant
     const bool want[1] = {livet};
 #pragma unroll
     for (int i = 0; i < D; ++i) x[0][i] = X[i * S + t];
-    log_posterior<M, D, 1, 1>(x, want, prob, ts, 0, 1u << (threadIdx.x & 31), lp);
+    log_posterior<M, D, 1, 1, true>(x, want, prob, ts, tile_points, 0, 1u << (threadIdx.x & 31), lp);
     if (livet) lp_out[t] = lp[0];
 }
 
@@ -619,9 +624,9 @@ __global__ void __launch_bounds__(256) eval_logpost_kernel(const __grid_constant
 template <class M, int D>
 __global__ void __launch_bounds__(256) eval_model_kernel(const __grid_constant__ ProblemDev prob, const double *X /*[d][S]*/, int64_t S,
                                                          double *f_out, int tile_points) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileStream ts;
-    ts.init(smem_raw, prob.raw, prob.n_points, tile_points, M::NCR);
+    TileStream<M::NCR> ts;
+    ts.init(prob.raw, prob.n_points, tile_points);
+    const int n_tl = TileStream<M::NCR>::n_tiles(prob.n_points, tile_points);
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool livet = t < S;
     if (!livet) t = S - 1;
@@ -631,17 +636,17 @@ __global__ void __launch_bounds__(256) eval_model_kernel(const __grid_constant__
     typename M::Ctx ctx;
     typename M::Seq seq;
     begin_chain<M, D>(x, prob, ctx, seq);
-    ts.begin_pass();
-    for (int tl = 0; tl < ts.n_tiles; ++tl) {
+    ts.begin_pass(prob.raw, prob.n_points, tile_points);
+    for (int tl = 0; tl < n_tl; ++tl) {
         int cnt;
-        const double *tile = ts.acquire(tl, cnt);
+        const double *tile = ts.acquire(prob.n_points, tile_points, tl, cnt);
         for (int k = 0; k < cnt; ++k) {
             double raw[M::NCR];
             load_record<M::NCR>(tile, k, raw);
             const double f = M::value(ctx, seq, raw);
-            if (livet) f_out[(int64_t)(tl * ts.tile_points + k) * S + t] = f;
+            if (livet) f_out[(int64_t)(tl * tile_points + k) * S + t] = f;
         }
-        ts.release(tl);
+        ts.release(prob.raw, prob.n_points, tile_points, tl);
     }
 }
 

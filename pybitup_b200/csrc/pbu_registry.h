@@ -6,10 +6,11 @@ namespace pbu {
 
 struct MhKernelEntry {
     int model, n_param, n_unc, lanes, chains_per_thread, algo;   // algo = pbu_algo_id (RWMH, AM, DR, DRAM)
+    int streamed;             // 0: records resident in shared memory, 1: streamed in tiles
     const void *fn;   // __global__ void (*)(const MhParams)
 };
 struct IsdeKernelEntry {
-    int model, n_param, n_unc, lanes, chains_per_thread, has_grad;
+    int model, n_param, n_unc, lanes, chains_per_thread, has_grad, streamed;
     const void *fn;   // __global__ void (*)(const IsdeParams)
 };
 struct EvalKernelEntry {

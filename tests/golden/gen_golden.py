@@ -305,7 +305,7 @@ def gen_hessian_fd():
     for full in (True, False):
         for pos in (True, False):
             out["H_%d_%d" % (full, pos)] = mha.computeHessianFD(f, x, eps=0.001, compute_all_element=full, positive_diag=pos)
-    np.savez(os.path.join(HERE, "hessian_fd.npz"), A=A, x=x, **out)
+    np.savez(os.path.join(HERE, "_hessian_fd.npz"), A=A, x=x, **out)
 
 
 if __name__ == "__main__" and "--hessian" in sys.argv:

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("algo", ["RWMH", "DRAM"])
-@pytest.mark.parametrize("builder,kwargs,lanes", [("cubic_problem", {"n_points": 301}, 1), ("cubic_problem", {"n_points": 301}, 2),
+@pytest.mark.parametrize("builder,kwargs,lanes", [("cubic_problem", {"n_points": 301}, 1), ("cubic_problem", {"n_points": 301}, 8),
                                                   ("regression_problem", {"n_points": 500, "d": 10}, 1),
                                                   ("arrhenius_problem", {"n_steps": 60, "dT": 10.0}, 1)])
 def test_mh_streamed_equals_resident(builder, kwargs, lanes, algo):

@@ -136,7 +136,7 @@ def test_percentile_lerp_matches_numpy():
 def test_hessian_fd_matches_reference_golden():
     """compute_hessian_fd vs the reference's computeHessianFD (recorded by tests/golden/gen_golden.py --hessian)."""
     from pybitup_b200.metropolis_hastings_algorithms import compute_hessian_fd
-    g = np.load(os.path.join(ROOT, "tests", "golden", "hessian_fd.npz"))
+    g = np.load(os.path.join(ROOT, "tests", "golden", "_hessian_fd.npz"))
     A, x = g["A"], g["x"]
     f = lambda X: np.array([float(-0.5 * z @ A @ z + 0.1 * np.sin(z).sum() + 0.05 * z[0] * z[1] * z[2]) for z in X])   # noqa: E731
     for full in (True, False):
