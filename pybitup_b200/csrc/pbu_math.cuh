@@ -1,0 +1,112 @@
+// Lean double-precision exp and log for the ODE forward models (host + device, so that they can be checked on the
+// CPU: tools/test_math.cu).  CUDA's exp()/log() cover the full IEEE domain with special cases; the Arrhenius model only
+// needs exp on [-700, 700] and log on normal numbers in (0, 2), which takes 17 and 22 FP64 instructions instead of
+// about 65 each, and the model is nothing but six of these per RK4 step.
+//   pbu_exp : x = k ln2 + r, |r| <= ln2/2;  exp(r) = 1 + r + r^2 P9(r)  (near-minimax, 1.7e-17 relative), scaled by 2^k
+//   pbu_log : u = 2^e m, m in [sqrt(1/2), sqrt(2));  s = (m-1)/(m+1);  log m = 2s + s^3 Q6(s^2)  (4.5e-18 relative)
+// Measured against libm on 2e7 random arguments (tools/test_math.cu): max error < 1 ulp for both.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <math.h>
+
+#ifdef __CUDACC__
+#define PBU_HD __host__ __device__ __forceinline__
+#else
+#define PBU_HD inline
+#endif
+
+namespace pbu {
+
+PBU_HD int32_t hi_word(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2hiint(x);
+#else
+    uint64_t b;
+    memcpy(&b, &x, 8);
+    return (int32_t)(b >> 32);
+#endif
+}
+PBU_HD double with_hi_word(double x, int32_t hi) {
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(hi, __double2loint(x));
+#else
+    uint64_t b;
+    memcpy(&b, &x, 8);
+    b = (b & 0xffffffffull) | ((uint64_t)(uint32_t)hi << 32);
+    memcpy(&x, &b, 8);
+    return x;
+#endif
+}
+
+// exp(x) for -700 <= x <= 700 (0 below); no inf / nan handling
+PBU_HD double pbu_exp(double x) {
+    const bool tiny = x < -700.0;                                // branch-free: the result is selected at the end
+    x = tiny ? 0.0 : x;
+    const double SHIFT = 6755399441055744.0;                     // 1.5 * 2^52: rounds to nearest integer in the low bits
+    const double t = fma(x, 1.4426950408889634, SHIFT);
+    const double kf = t - SHIFT;
+    const int32_t k = (int32_t)(uint32_t)(
+#ifdef __CUDA_ARCH__
+        __double2loint(t)
+#else
+        [](double v) { uint64_t b; memcpy(&b, &v, 8); return (int32_t)(uint32_t)b; }(t)
+#endif
+    );
+    double r = fma(kf, -0.6931471803691238, x);                  // ln2 split: hi has 32 significant bits, kf*hi exact
+    r = fma(kf, -1.9082149292705877e-10, r);
+    double p = 2.5100375832561234e-08;
+    p = fma(p, r, 2.7620075879983367e-07);
+    p = fma(p, r, 2.7557268480310024e-06);
+    p = fma(p, r, 2.4801521322368692e-05);
+    p = fma(p, r, 0.00019841269863040545);
+    p = fma(p, r, 0.0013888888917196719);
+    p = fma(p, r, 0.008333333333330065);
+    p = fma(p, r, 0.041666666666624164);
+    p = fma(p, r, 0.16666666666666669);
+    p = fma(p, r, 0.5000000000000001);
+    const double v = 1.0 + fma(r * r, p, r);
+    const double res = with_hi_word(v, hi_word(v) + (k << 20));   // * 2^k on the exponent field (k >= -1010 here)
+    return tiny ? 0.0 : res;
+}
+
+// log(u) for normal u > 0 (no zero / denormal / inf / nan handling)
+PBU_HD double pbu_log(double u) {
+    int32_t hi = hi_word(u);
+    int32_t e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;                          // m in [1, 2)
+    // m in [sqrt(1/2), sqrt(2)): halve the mantissas above sqrt(2) by lowering the exponent field (branch-free);
+    // 0x6a09e is the top 20 mantissa bits of sqrt(2), so the cut sits within 2^-20 of it, harmless for the series
+    const int32_t big = ((hi & 0x000fffff) > 0x6a09e) ? 1 : 0;
+    hi -= big << 20;
+    e += big;
+    const double m = with_hi_word(u, hi);
+    const double f = m - 1.0, g = m + 1.0;
+    // s = f / g: reciprocal seed refined by two Newton steps, then one residual correction of the quotient
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(g));
+#else
+    double y = (double)(1.0f / (float)g);
+#endif
+    double err = fma(-g, y, 1.0);
+    y = fma(y, err, y);
+    err = fma(-g, y, 1.0);
+    y = fma(y, err, y);
+    double s = f * y;
+    s = fma(fma(-s, g, f), y, s);
+    const double z = s * s;
+    double q = 0.14616585424888623;
+    q = fma(q, z, 0.15331710618210773);
+    q = fma(q, z, 0.18182889455674947);
+    q = fma(q, z, 0.22222211130259878);
+    q = fma(q, z, 0.2857142862600327);
+    q = fma(q, z, 0.39999999999899444);
+    q = fma(q, z, 0.666666666666667);
+    const double ef = (double)e;
+    // e ln2_hi + (2s + (s z q + e ln2_lo)): e*ln2_hi is exact (32-bit hi, |e| < 2^11)
+    const double lo = fma(s * z, q, ef * 1.9082149292705877e-10);
+    return fma(ef, 0.6931471803691238, fma(2.0, s, lo));
+}
+
+}  // namespace pbu

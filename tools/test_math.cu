@@ -1,0 +1,38 @@
+// Host check of pybitup_b200/csrc/pbu_math.cuh against libm (run: nvcc -O2 -o /tmp/test_math tools/test_math.cu && /tmp/test_math)
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <random>
+#include "../pybitup_b200/csrc/pbu_math.cuh"
+
+static double ulp_err(double got, double ref) {
+    if (ref == 0.0) return got == 0.0 ? 0.0 : 1e300;
+    int e;
+    frexp(ref, &e);
+    return fabs(got - ref) / ldexp(1.0, e - 53);
+}
+
+int main() {
+    std::mt19937_64 rng(1);
+    std::uniform_real_distribution<double> ue(-700.0, 700.0), us(-60.0, 20.0), u01(0.0, 1.0);
+    double me = 0, ml = 0, mp = 0;
+    long bad = 0;
+    for (long i = 0; i < 20000000; ++i) {
+        double x = (i & 1) ? ue(rng) : us(rng);
+        me = fmax(me, ulp_err(pbu::pbu_exp(x), exp(x)));
+        double u = (i % 3 == 0) ? u01(rng) : ((i % 3 == 1) ? exp(-40.0 * u01(rng)) : 1.0 - 1e-3 * u01(rng) * u01(rng));
+        if (u <= 0.0) continue;
+        const double l = pbu::pbu_log(u), lr = log(u);
+        const double el = ulp_err(l, lr);
+        ml = fmax(ml, el);
+        const double n = 0.5 + 2.5 * u01(rng);
+        const double pw = pbu::pbu_exp(n * l), pr = pow(u, n);
+        const double rel = pr > 0 ? fabs(pw - pr) / pr : 0.0;
+        mp = fmax(mp, rel);
+        if (el > 2.0) ++bad;
+    }
+    printf("max ulp error: exp %.3f  log %.3f   max relative error of exp(n log u) vs pow: %.3e   log errors > 2 ulp: %ld\n", me, ml, mp, bad);
+    printf("edge: exp(0)=%.17g log(1)=%.17g exp(-701)=%g log(0.5)=%.17g (ref %.17g)\n", pbu::pbu_exp(0.0), pbu::pbu_log(1.0), pbu::pbu_exp(-701.0),
+           pbu::pbu_log(0.5), log(0.5));
+    return (me < 2.0 && ml < 2.5 && mp < 2e-14) ? 0 : 1;
+}
