@@ -109,15 +109,16 @@ struct Philox {
     }
 };
 
-// two standard normals from two 32-bit words: Box-Muller in fp32 (as curand_normal does), widened.
+// two standard normals from two 32-bit words: Box-Muller in fp32 (as curand_normal does), widened.  The special
+// function unit does the transcendental work (lg2.approx, sin/cos.approx on an argument reduced to [-pi, pi), sqrt
+// .approx): absolute error ~2^-21 on the uniform scale, i.e. the proposal draws are float-accurate normals, at a
+// quarter of the instructions of logf / sincospif.  (Parity runs inject their draws and never come here.)
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, double &z0, double &z1) {
-    float u = (float)a * 2.3283064365386963e-10f + 1.1641532182693481e-10f;   // (0,1]
-    float v = (float)b * 2.3283064365386963e-10f + 1.1641532182693481e-10f;
-    float s = sqrtf(-2.0f * logf(u));
-    float sn, cs;
-    sincospif(2.0f * v, &sn, &cs);
-    z0 = (double)(s * cs);
-    z1 = (double)(s * sn);
+    const float u = (float)a * 2.3283064365386963e-10f + 1.1641532182693481e-10f;   // (0,1]
+    const float ang = (float)(int32_t)b * 1.4629180792671596e-09f;                   // 2 pi * b / 2^32 in [-pi, pi)
+    const float s = __fsqrt_rn(-1.3862943611198906f * __log2f(u));                   // sqrt(-2 ln u)
+    z0 = (double)(s * __cosf(ang));
+    z1 = (double)(s * __sinf(ang));
 }
 
 // uniform in (0,1) with 53 random bits

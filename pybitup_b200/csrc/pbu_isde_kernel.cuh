@@ -154,8 +154,15 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) isde_step_kernel(const __grid
     const double hfm = 1.0 - p.h * p.f0 / 4.0, hfp = 1.0 + p.h * p.f0 / 4.0;      // :928-929
     const double sqrt_h = sqrt(p.h), sqrt_f0 = sqrt(p.f0);
 
+    int32_t to_update = (int32_t)(p.update_it - p.it0 % p.update_it);     // countdowns instead of a 64-bit modulo per iteration
+    int32_t to_keep = (int32_t)(p.thin - p.it0 % p.thin);
+    int64_t row = 0;
     for (int64_t s = 0; s < p.n_steps; ++s) {
         const int64_t it = p.it0 + s + 1;
+        const bool upd = (--to_update == 0);                            // it % update_it == 0
+        if (upd) to_update = (int32_t)p.update_it;
+        const bool keep = (--to_keep == 0);                             // it % thin == 0
+        if (keep) to_keep = (int32_t)p.thin;
         double xn[Q][D], WP[Q][D];
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
@@ -211,7 +218,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) isde_step_kernel(const __grid
                     for (int i = 0; i < D; ++i) gxav[(int64_t)i * C] = xb[i];
                 }
             }
-            if (it >= p.starting_it && it <= p.end_it + 1 && (it % p.update_it == 0)) {                         // :767-777
+            if (it >= p.starting_it && it <= p.end_it + 1 && upd) {                         // :767-777
                 double Vc[NT], Lc[NT], IL[NT];
 #pragma unroll
                 for (int i = 0; i < NT; ++i) Vc[i] = gV[(int64_t)i * C];
@@ -319,7 +326,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) isde_step_kernel(const __grid
 
             if (live[q] && sub == 0) {
                 if (p.out.trace_lp1) p.out.trace_lp1[s * C + cq] = lpn[q];
-                if (it % p.thin == 0) {
+                if (keep) {
                     {
                         const int64_t wc = p.st.wcount[cq] + 1;
                         p.st.wcount[cq] = wc;
@@ -340,7 +347,6 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) isde_step_kernel(const __grid
                                 *w2 = fma(dl[i], xi[q][j] - mu[j], *w2);
                             }
                     }
-                    const int64_t row = it / p.thin - p.it0 / p.thin - 1;
                     if (p.out.samples && cq < p.out.n_sample_chains) {
 #pragma unroll
                         for (int i = 0; i < D; ++i) p.out.samples[(row * D + i) * p.out.n_sample_chains + cq] = xi[q][i];
@@ -353,6 +359,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) isde_step_kernel(const __grid
                 }
             }
         }
+        if (keep) row += 1;
     }
 
 #pragma unroll

@@ -370,6 +370,10 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_c
     // The per-chain adaptive state (X_av, V_i, R) lives in global memory, chain-minor: every lane of a group
     // reads and, if live, writes the same values, so each thread only ever reads back its own stores.
 
+    // iteration counters kept as small countdowns: a 64-bit modulo per iteration costs ~100 instructions
+    int32_t to_refresh = ADAPT ? (int32_t)(p.updating_it - p.it0 % p.updating_it) : 0;   // iterations until it % updating_it == 0
+    int32_t to_keep = (int32_t)(p.thin - p.it0 % p.thin);                                 // iterations until it % thin == 0
+    int64_t row = 0;                                                                      // kept rows written by this launch
     for (int64_t s = 0; s < p.n_steps; ++s) {
         const int64_t it = p.it0 + s + 1;
         // Up to two proposal stages share ONE inlined copy of the posterior evaluation (code size):
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_c
                 bool accept;
                 if (stage == 0) {
                     lp1[q] = lpy[q];
-                    r[q] = (lp1[q] == -INFINITY) ? 0.0 : exp(lp1[q] - lp[q]);         // :200-205
+                    r[q] = (lp1[q] == -INFINITY) ? 0.0 : exp(lp1[q] - lp[q]);         // :200-205 (full-domain exp: the difference may be anything)
                     if (r[q] != r[q]) {
                         status[q] |= ST_NAN_RATIO;
                         if (p.nan_rejects) r[q] = 0.0;
@@ -467,6 +471,10 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_c
             if (!again) break;
         }
 
+        const bool refresh = ADAPT && (--to_refresh == 0);          // it % updating_it == 0  (:470)
+        if (refresh) to_refresh = p.updating_it;
+        const bool keep = (--to_keep == 0);                          // it % thin == 0
+        if (keep) to_keep = (int32_t)p.thin;
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
             const int64_t cq = c[q];
@@ -476,7 +484,6 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_c
                 double *const gV = p.st.V + cq;
                 double *const gxav = p.st.xav + cq;
                 const double fi = (double)it;
-                const bool refresh = (it % p.updating_it == 0);                 // :470
                 double Vc[NT];
                 if (!p.am_welford) {
                     // literal Haario/Smith recursion, evaluated in the reference's operation order
@@ -550,7 +557,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_c
                 if (p.out.trace_lp1) p.out.trace_lp1[s * C + cq] = lp1[q];
                 if (p.out.trace_lp2) p.out.trace_lp2[s * C + cq] = lp2[q];
                 if (p.out.trace_acc) p.out.trace_acc[s * C + cq] = (uint8_t)acc[q];
-                if (it % p.thin == 0) {
+                if (keep) {
                     // running (Welford) moments of the KEPT states, held in global memory so that they cost
                     // no registers in the data loop; input of the moment reduction (K4: pooled covariance, R-hat)
                     {
@@ -573,7 +580,6 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_c
                                 *w2 = fma(dl[i], x[q][j] - mu[j], *w2);
                             }
                     }
-                    const int64_t row = it / p.thin - p.it0 / p.thin - 1;
                     if (p.out.samples && cq < p.out.n_sample_chains) {
 #pragma unroll
                         for (int i = 0; i < D; ++i) p.out.samples[(row * D + i) * p.out.n_sample_chains + cq] = x[q][i];
@@ -582,6 +588,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_c
                 }
             }
         }
+        if (keep) row += 1;
     }
 
     // ---- store state
