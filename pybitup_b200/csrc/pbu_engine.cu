@@ -88,12 +88,12 @@ extern "C" __attribute__((visibility("default"))) int pbu_list_kernels(char *buf
     return total;
 }
 
-static const MhKernelEntry *find_mh(int model, int P, int d, int lanes, int q, int algo, int streamed) {
+static const MhKernelEntry *find_mh(int model, int P, int d, int lanes, int q, int algo, int streamed, int mixed = 0) {
     int n = 0;
     const MhKernelEntry *t = pbu_mh_kernels(&n);
     for (int i = 0; i < n; ++i)
         if (t[i].model == model && t[i].n_param == P && t[i].n_unc == d && t[i].lanes == lanes && t[i].chains_per_thread == q &&
-            t[i].algo == algo && t[i].streamed == streamed)
+            t[i].algo == algo && t[i].streamed == streamed && t[i].mixed == mixed)
             return &t[i];
     return nullptr;
 }
@@ -188,17 +188,19 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, e->device);
     const double N = (double)e->prob.n_points;
     const double S0 = 60.0 + 15.0 * e->d;           // per-iteration scalar part (RNG, proposal, accept, adaptation), in DFMA-equivalents
-    const int cand[5][2] = {{1, 1}, {1, 2}, {2, 2}, {4, 2}, {8, 1}};     // (lanes per chain, chains per thread)
+    // (lanes per chain, chains per thread, mixed): mixed = the last warps of a block use twice the lanes
+    const int cand[6][3] = {{1, 1, 0}, {1, 2, 0}, {2, 2, 0}, {2, 2, 1}, {4, 2, 0}, {8, 1, 0}};
     const bool isde = algo == PBU_ALGO_ISDE;
     const int streamed = e->tile_points < e->prob.n_points ? 1 : 0;
     const double ops = isde ? 2.0 * e->ev->ops : (double)e->ev->ops;     // value + gradient
     double best = 1e300;
     bool found = false;
     for (const auto &gq : cand) {
-        const int g = gq[0], q = gq[1];
+        const int g = gq[0], q = gq[1], mixed = gq[2];
         if (want_lanes > 0 && g != want_lanes) continue;
         if (want_q > 0 && q != want_q) continue;
         if (sequential && g != 1) continue;
+        if (mixed && (isde || streamed || want_block > 0 || want_lanes > 0)) continue;
         // delayed rejection: the second stage runs for a thread when ANY of its chains was rejected, so pairing
         // chains wastes evaluations; one chain per thread unless asked otherwise
         if ((algo == PBU_ALGO_DR || algo == PBU_ALGO_DRAM) && q != 1 && want_q <= 0 && want_lanes <= 0) continue;
@@ -211,12 +213,13 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
             ki = find_isde(model, e->P, e->d, g, q, streamed);
             if (ki) fn = ki->fn;
         } else {
-            km = find_mh(model, e->P, e->d, g, q, algo, streamed);
+            km = find_mh(model, e->P, e->d, g, q, algo, streamed, mixed);
             if (km) fn = km->fn;
         }
         if (!fn) continue;
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
         const int64_t groups_needed = (e->C + q - 1) / q;
+        const double work = q * ((sequential ? N : std::ceil(N / g)) * ops + S0);      // per thread of a G-lane warp
         for (int B = MH_MAX_BLOCK; B >= 32; B -= 32) {
             if (want_block > 0 && B != want_block) continue;
             int occ = 0;
@@ -224,21 +227,32 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
                 cudaGetLastError();
                 continue;
             }
-            const double blocks = std::ceil((double)groups_needed * g / B);
-            const double per_sm = std::ceil(blocks / nsm);          // blocks the busiest SM runs, `occ` at a time
-            const double warps = std::min(per_sm, (double)occ) * B / 32.0;
-            const double work = q * ((sequential ? N : std::ceil(N / g)) * ops + S0);
-            const double t = per_sm * B * work / loop_efficiency(q, warps);
-            if (t < best * (1.0 - 1e-3)) {
-                best = t;
-                e->mh = km;
-                e->isde = ki;
-                e->step_fn = fn;
-                e->lanes = g;
-                e->q = q;
-                e->block = B;
-                e->grid = (int)blocks;
-                found = true;
+            const int W = B / 32;
+            for (int nwide = (mixed ? 4 : 0); nwide <= (mixed ? std::min(W - 4, 8) : 0); nwide += 4) {
+                if (mixed && W % 4 != 0) break;
+                const int nfull = W - nwide;
+                const int gpb = nfull * (32 / g) + nwide * (16 / g);                  // chain groups per block
+                const double blocks = std::ceil((double)groups_needed / gpb);
+                const double per_sm = std::ceil(blocks / nsm);          // blocks the busiest SM runs, `occ` at a time
+                const double conc = std::min(per_sm, (double)occ);
+                const double warps = conc * W;
+                // warps go round-robin to the 4 schedulers of an SM: the busiest one sets the pace.  A wide warp carries
+                // half the points per lane, i.e. half a unit of work.
+                const double sched_units = mixed ? (nfull / 4.0 + nwide / 8.0) : std::ceil(conc * W / 4.0) / conc;
+                const double t = per_sm * sched_units * 4.0 * 32.0 * work / loop_efficiency(q, warps);
+                if (t < best * (1.0 - 1e-3)) {
+                    best = t;
+                    e->mh = km;
+                    e->isde = ki;
+                    e->step_fn = fn;
+                    e->lanes = g;
+                    e->q = q;
+                    e->block = B;
+                    e->grid = (int)blocks;
+                    e->n_full_warps = mixed ? nfull : 0;
+                    e->groups_per_block = gpb;
+                    found = true;
+                }
             }
         }
     }
@@ -596,7 +610,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine 
         q.it0 = e->iteration;
         q.n_steps = n_steps;
         q.thin = thin;
-        q.n_groups = (int64_t)e->grid * e->block / e->lanes;
+        q.n_groups = (int64_t)e->grid * e->groups_per_block;
         q.seed = e->cfg.seed;
         q.chain_offset = e->cfg.chain_offset;
         q.h = e->cfg.isde_h;
@@ -634,7 +648,9 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine 
     p.nan_rejects = e->cfg.nan_rejects;
     p.resident = e->tile_points >= e->prob.n_points;
     p.tile_points = e->tile_points;
-    p.n_groups = (int64_t)e->grid * e->block / e->lanes;
+    p.n_groups = (int64_t)e->grid * e->groups_per_block;
+    p.n_full_warps = e->n_full_warps;
+    p.groups_per_block = e->groups_per_block;
     for (size_t i = 0; i < e->R0.size(); ++i) p.R0[i] = e->R0[i];
     void *args[] = {(void *)&p};
     CUDA_TRY(cudaLaunchKernel(e->step_fn, dim3((unsigned)e->grid), dim3(e->block), args, e->smem_bytes, e->stream));

@@ -37,6 +37,8 @@ struct pbu_engine {
     const pbu::EvalKernelEntry *ev = nullptr;
     int lanes = 1;
     int q = 1;                    // chains per thread
+    int n_full_warps = 0;         // mixed kernels: warps per block with `lanes` lanes per chain, the rest use 2 * lanes
+    int groups_per_block = 0;     // chain groups (G-lane teams) per block
     int block = 128;
     int grid = 1;
     size_t smem_bytes = 0;        // step / log-posterior kernels: barrier + likelihood records

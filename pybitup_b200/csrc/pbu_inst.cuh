@@ -5,7 +5,10 @@
 
 // S = 0: records resident in shared memory; S = 1: streamed in tiles (data sets larger than shared memory)
 #define PBU_MH(MODEL, P, D, G, Q, A, S) \
-    { MODEL::ID, P, D, G, Q, A, S, (const void *)&pbu::mh_step_kernel<MODEL, D, G, A, Q, (S != 0)> }
+    { MODEL::ID, P, D, G, Q, A, S, 0, (const void *)&pbu::mh_step_kernel<MODEL, D, G, A, Q, (S != 0), false> }
+// mixed: the last warps of each block use 2G lanes per chain (scheduler-level load balance)
+#define PBU_MH_MIXED(MODEL, P, D, G, Q, A) \
+    { MODEL::ID, P, D, G, Q, A, 0, 1, (const void *)&pbu::mh_step_kernel<MODEL, D, G, A, Q, false, true> }
 #define PBU_MH_ALGOS(MODEL, P, D, G, Q, S) \
     PBU_MH(MODEL, P, D, G, Q, 0, S), PBU_MH(MODEL, P, D, G, Q, 1, S), PBU_MH(MODEL, P, D, G, Q, 2, S), PBU_MH(MODEL, P, D, G, Q, 3, S)
 // data-parallel models, (lanes per chain, chains per thread): (1,1) (1,2) (2,2) (4,2), (8,1) for very few chains;
@@ -13,7 +16,8 @@
 #define PBU_MH_ALL(MODEL, P, D)                                                                                        \
     PBU_MH_ALGOS(MODEL, P, D, 1, 1, 0), PBU_MH_ALGOS(MODEL, P, D, 1, 2, 0), PBU_MH_ALGOS(MODEL, P, D, 2, 2, 0),        \
         PBU_MH_ALGOS(MODEL, P, D, 4, 2, 0), PBU_MH_ALGOS(MODEL, P, D, 8, 1, 0), PBU_MH_ALGOS(MODEL, P, D, 1, 1, 1),    \
-        PBU_MH_ALGOS(MODEL, P, D, 1, 2, 1), PBU_MH_ALGOS(MODEL, P, D, 8, 1, 1)
+        PBU_MH_ALGOS(MODEL, P, D, 1, 2, 1), PBU_MH_ALGOS(MODEL, P, D, 8, 1, 1), PBU_MH_MIXED(MODEL, P, D, 2, 2, 0),     \
+        PBU_MH_MIXED(MODEL, P, D, 2, 2, 1)
 #define PBU_MH_SEQ(MODEL, P, D) PBU_MH_ALGOS(MODEL, P, D, 1, 1, 0), PBU_MH_ALGOS(MODEL, P, D, 1, 1, 1)
 // Ito-SDE step kernel variants (lanes per chain, chains per thread, streamed)
 #define PBU_ISDE(MODEL, P, D, G, Q, S) \

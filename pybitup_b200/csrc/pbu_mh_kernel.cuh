@@ -335,16 +335,11 @@ __device__ __forceinline__ bool draw_injected(const StreamsDev &s, int64_t c, bo
 // rejection (DR, DRAM).  Q = chains per thread; thread group g owns chains g, g + n_groups, ...
 // ------------------------------------------------------------------------------------------------
 template <class M, int D, int G, int ALGO, int Q, bool STREAM>
-__global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_constant__ MhParams p) {
+__device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::NC> &ts, const int64_t group, const int sub) {
     constexpr bool ADAPT = (ALGO & 1) != 0;
     constexpr bool DELAYED = (ALGO & 2) != 0;
     constexpr int NT = tri_size(D);
-    TileStream<M::NC> ts;
-    ts.init(p.prob.records, p.prob.n_points, p.tile_points);
-
     const int64_t C = p.st.n_chains;
-    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int sub = (int)(gtid % G);
     const int lane = threadIdx.x & 31;
     const unsigned group_mask = (G == 1) ? (1u << lane) : (((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(G - 1)));
     const bool injected = p.streams.normals != nullptr;
@@ -356,7 +351,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_c
     int32_t n_rej[Q], n_eval[Q], status[Q];     // n_rej / n_eval: per-launch increments of the int64 counters
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-        c[q] = gtid / G + (int64_t)q * p.n_groups;
+        c[q] = group + (int64_t)q * p.n_groups;
         live[q] = c[q] < C;
         if (!live[q]) c[q] = C - 1;             // padding slots shadow the last chain, never write
 #pragma unroll
@@ -603,6 +598,30 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_c
             p.st.n_rej[cq] += n_rej[q];
             p.st.n_eval[cq] += n_eval[q];
             p.st.status[cq] = status[q];
+        }
+    }
+}
+
+// The kernel proper.  MIXED: the last warps of every block (from warp index p.n_full_warps on) give each chain 2G lanes
+// instead of G, i.e. carry half as many chains.  With equal warps the 2048 warps of 65,536 chains (G = 2, Q = 2) cannot
+// be spread evenly over the 592 warp schedulers of a B200 (3.46 each: the schedulers holding four set the pace);
+// three full warps and one half warp per scheduler can (3.5 units each).
+template <class M, int D, int G, int ALGO, int Q, bool STREAM, bool MIXED>
+__global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_constant__ MhParams p) {
+    TileStream<M::NC> ts;
+    ts.init(p.prob.records, p.prob.n_points, p.tile_points);
+    const int lane = threadIdx.x & 31;
+    if constexpr (!MIXED) {
+        const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        mh_chain_loop<M, D, G, ALGO, Q, STREAM>(p, ts, gtid / G, (int)(gtid % G));
+    } else {
+        const int warp = threadIdx.x >> 5;
+        const int64_t base = (int64_t)blockIdx.x * p.groups_per_block;
+        if (warp < p.n_full_warps) {
+            mh_chain_loop<M, D, G, ALGO, Q, STREAM>(p, ts, base + warp * (32 / G) + lane / G, lane % G);
+        } else {
+            mh_chain_loop<M, D, 2 * G, ALGO, Q, STREAM>(p, ts, base + p.n_full_warps * (32 / G) + (warp - p.n_full_warps) * (16 / G) + lane / (2 * G),
+                                                       lane % (2 * G));
         }
     }
 }
