@@ -239,7 +239,9 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
                 // warps go round-robin to the 4 schedulers of an SM: the busiest one sets the pace.  A wide warp carries
                 // half the points per lane, i.e. half a unit of work.
                 const double sched_units = mixed ? (nfull / 4.0 + nwide / 8.0) : std::ceil(conc * W / 4.0) / conc;
-                const double t = per_sm * sched_units * 4.0 * 32.0 * work / loop_efficiency(q, warps);
+                // a handful of warps on the whole GPU is latency-bound: only the serial work of a thread counts
+                const bool tiny = blocks * W < nsm;
+                const double t = tiny ? work : per_sm * sched_units * 4.0 * 32.0 * work / loop_efficiency(q, warps);
                 if (t < best * (1.0 - 1e-3)) {
                     best = t;
                     e->mh = km;
