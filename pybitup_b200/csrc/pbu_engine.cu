@@ -189,7 +189,7 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
     const double N = (double)e->prob.n_points;
     const double S0 = 60.0 + 15.0 * e->d;           // per-iteration scalar part (RNG, proposal, accept, adaptation), in DFMA-equivalents
     // (lanes per chain, chains per thread, mixed): mixed = the last warps of a block use twice the lanes
-    const int cand[6][3] = {{1, 1, 0}, {1, 2, 0}, {2, 2, 0}, {2, 2, 1}, {4, 2, 0}, {8, 1, 0}};
+    const int cand[8][3] = {{1, 1, 0}, {1, 2, 0}, {2, 2, 0}, {2, 2, 1}, {4, 2, 0}, {2, 1, 0}, {4, 1, 0}, {8, 1, 0}};
     const bool isde = algo == PBU_ALGO_ISDE;
     const int streamed = e->tile_points < e->prob.n_points ? 1 : 0;
     const double ops = isde ? 2.0 * e->ev->ops : (double)e->ev->ops;     // value + gradient
@@ -219,7 +219,10 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
         if (!fn) continue;
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
         const int64_t groups_needed = (e->C + q - 1) / q;
-        const double work = q * ((sequential ? N : std::ceil(N / g)) * ops + S0);      // per thread of a G-lane warp
+        // 8 lanes reading 8 consecutive records collide in the shared-memory banks when the record stride is an even
+        // number of 16-byte units (two wavefronts per load)
+        const double conflict = (g >= 8 && (e->ev->nc / 2) % 2 == 0) ? 1.1 : 1.0;
+        const double work = q * ((sequential ? N : std::ceil(N / g)) * ops * conflict + S0);      // per thread of a G-lane warp
         for (int B = MH_MAX_BLOCK; B >= 32; B -= 32) {
             if (want_block > 0 && B != want_block) continue;
             int occ = 0;

@@ -24,7 +24,8 @@
     { MODEL::ID, P, D, G, Q, MODEL::HAS_GRAD ? 1 : 0, S, (const void *)&pbu::isde_step_kernel<MODEL, D, G, Q, (S != 0)> }
 #define PBU_ISDE_ALL(MODEL, P, D)                                                                                   \
     PBU_ISDE(MODEL, P, D, 1, 1, 0), PBU_ISDE(MODEL, P, D, 1, 2, 0), PBU_ISDE(MODEL, P, D, 2, 2, 0), PBU_ISDE(MODEL, P, D, 8, 1, 0), \
-        PBU_ISDE(MODEL, P, D, 1, 1, 1), PBU_ISDE(MODEL, P, D, 1, 2, 1), PBU_ISDE(MODEL, P, D, 8, 1, 1)
+        PBU_ISDE(MODEL, P, D, 1, 1, 1), PBU_ISDE(MODEL, P, D, 1, 2, 1), PBU_ISDE(MODEL, P, D, 8, 1, 1),               \
+        PBU_ISDE(MODEL, P, D, 4, 1, 0), PBU_ISDE(MODEL, P, D, 4, 1, 1), PBU_ISDE(MODEL, P, D, 2, 1, 1)
 #define PBU_ISDE_SEQ(MODEL, P, D) PBU_ISDE(MODEL, P, D, 1, 1, 0), PBU_ISDE(MODEL, P, D, 1, 1, 1)
 #define PBU_EVAL(MODEL, P, D)                                                                 \
     { MODEL::ID, P, D, MODEL::SEQUENTIAL ? 1 : 0, MODEL::NC, MODEL::NCR, MODEL::OPS, MODEL::WF, (const void *)&pbu::eval_logpost_kernel<MODEL, D>, \

@@ -127,10 +127,10 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) isde_step_kernel(const __grid
     ts.init(p.prob.records, p.prob.n_points, p.tile_points);
 
     const int64_t C = p.st.n_chains;
-    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int sub = (int)(gtid % G);
     const int lane = threadIdx.x & 31;
-    const unsigned group_mask = (G == 1) ? (1u << lane) : (((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(G - 1)));
+    const int sub = lane_sub<G>(lane);
+    const int64_t group = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 / G) + lane_chain<G>(lane);
+    const unsigned group_mask = lane_group_mask<G>(lane);
     const bool injected = p.streams.normals != nullptr;
 
     int64_t c[Q];
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) isde_step_kernel(const __grid
     int32_t status[Q], n_eval[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-        c[q] = gtid / G + (int64_t)q * p.n_groups;
+        c[q] = group + (int64_t)q * p.n_groups;
         live[q] = c[q] < C;
         if (!live[q]) c[q] = C - 1;
 #pragma unroll

@@ -183,10 +183,25 @@ __device__ __forceinline__ void tile_accumulate(const typename M::Ctx (&ctx)[Q],
     }
 }
 
+// Lane layout of a warp when G lanes share a chain: the warp carries 32/G chains; lane l works for chain l % (32/G) and
+// takes the points with index = (l / (32/G)) mod G.  Lanes that read the same record are then CONTIGUOUS (whole
+// quarter-warps for G <= 4), which is what the shared-memory pipe wants: a 16-byte load is served one quarter-warp
+// at a time, and a quarter whose lanes all read one address is a single broadcast wavefront.
+template <int G>
+__device__ __forceinline__ int lane_sub(int lane) { return lane / (32 / G); }
+template <int G>
+__device__ __forceinline__ int lane_chain(int lane) { return lane % (32 / G); }
+template <int G>
+__device__ __forceinline__ unsigned lane_group_mask(int lane) {
+    unsigned m = 0u;
+#pragma unroll
+    for (int j = 0; j < G; ++j) m |= 1u << (lane_chain<G>(lane) + j * (32 / G));
+    return m;
+}
 template <int G>
 __device__ __forceinline__ double group_sum(double v, unsigned group_mask) {
 #pragma unroll
-    for (int s = 1; s < G; s <<= 1) v += __shfl_xor_sync(group_mask, v, s);
+    for (int s = 1; s < G; s <<= 1) v += __shfl_xor_sync(group_mask, v, s * (32 / G));
     return v;
 }
 
@@ -341,7 +356,7 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
     constexpr int NT = tri_size(D);
     const int64_t C = p.st.n_chains;
     const int lane = threadIdx.x & 31;
-    const unsigned group_mask = (G == 1) ? (1u << lane) : (((G == 32) ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(G - 1)));
+    const unsigned group_mask = lane_group_mask<G>(lane);
     const bool injected = p.streams.normals != nullptr;
 
     // ---- chain state kept in registers across the launch
@@ -612,16 +627,16 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_c
     ts.init(p.prob.records, p.prob.n_points, p.tile_points);
     const int lane = threadIdx.x & 31;
     if constexpr (!MIXED) {
-        const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        mh_chain_loop<M, D, G, ALGO, Q, STREAM>(p, ts, gtid / G, (int)(gtid % G));
+        const int64_t warp_g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        mh_chain_loop<M, D, G, ALGO, Q, STREAM>(p, ts, warp_g * (32 / G) + lane_chain<G>(lane), lane_sub<G>(lane));
     } else {
         const int warp = threadIdx.x >> 5;
         const int64_t base = (int64_t)blockIdx.x * p.groups_per_block;
         if (warp < p.n_full_warps) {
-            mh_chain_loop<M, D, G, ALGO, Q, STREAM>(p, ts, base + warp * (32 / G) + lane / G, lane % G);
+            mh_chain_loop<M, D, G, ALGO, Q, STREAM>(p, ts, base + warp * (32 / G) + lane_chain<G>(lane), lane_sub<G>(lane));
         } else {
-            mh_chain_loop<M, D, 2 * G, ALGO, Q, STREAM>(p, ts, base + p.n_full_warps * (32 / G) + (warp - p.n_full_warps) * (16 / G) + lane / (2 * G),
-                                                       lane % (2 * G));
+            mh_chain_loop<M, D, 2 * G, ALGO, Q, STREAM>(p, ts, base + p.n_full_warps * (32 / G) + (warp - p.n_full_warps) * (16 / G) + lane_chain<2 * G>(lane),
+                                                       lane_sub<2 * G>(lane));
         }
     }
 }
