@@ -106,7 +106,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
-def _cpu_chain_worker(args):
+def _cpu_chain_worker(args, return_chain=False):
     """One chain of the workload through the oracle port; returns (iterations, seconds)."""
     seed, n_it = args
     from oracle import mcmc_oracle as orc
@@ -118,15 +118,17 @@ def _cpu_chain_worker(args):
     st = orc.Streams(rng.standard_normal(n_it * D), rng.random(n_it))
     x0 = synthetic.chain_starts(p["x0"], 1, jitter=0.01, seed=seed)[0]
     t0 = time.perf_counter()
-    orc.run_mh(prob, x0, p["prop_cov"], n_it, st, adaptive=True, delayed=False, **AM)
+    out = orc.run_mh(prob, x0, p["prop_cov"], n_it, st, adaptive=True, delayed=False, **AM)
+    if return_chain:
+        return n_it, time.perf_counter() - t0, out["chain"]
     return n_it, time.perf_counter() - t0
 
 
-def cpu_port_rate(n_procs, n_it, pool=None):
+def cpu_port_rate(n_procs, n_it, pool=None, return_chain=False):
     """chain-steps/s of the oracle port with n_procs independent single-chain processes."""
     if n_procs == 1 or pool is None:
-        it, dt = _cpu_chain_worker((0, n_it))
-        return it / dt, dt
+        r = _cpu_chain_worker((0, n_it), return_chain)
+        return (r[0] / r[1], r[1], r[2]) if return_chain else (r[0] / r[1], r[1])
     t0 = time.perf_counter()
     res = pool.map(_cpu_chain_worker, [(s, n_it) for s in range(n_procs)], chunksize=1)
     wall = time.perf_counter() - t0
@@ -243,7 +245,7 @@ def run_gpu_arm(args):
     x0_pin = torch.from_numpy(x0).pin_memory()
     x0_host = x0_pin.numpy()
     eng = ChainEngine(spec, cfg, C, device=local_rank)
-    h2d = C * 8 * (2 * D + 2 * 10 + 1)            # x0, xav, packed R and V, evaluation counters
+    h2d = C * 8 * D                               # the chains' starting points (everything else is built on the device)
     d2h = C * 8 * (D + 1) + C * (8 + 8 + 8 + 4)
     for _ in range(min(W, 3)):
         eng.init_chains(x0_host, p["prop_cov"])
@@ -268,13 +270,33 @@ def run_gpu_arm(args):
     e2e_value = world * C * T * K / (float(t_e2e.item()) * 1e-3)
     eng.close()
 
+    # ---- effective sample size per chain-step (same batch-means estimator on both sides) ----------
+    ess = None
+    if rank == 0 and not args.no_cpu:
+        from pybitup_b200.diagnostics import ess_batch_means
+        n_probe, T_ess = 16, 24000           # the CPU chain below is cut into segments of the same length
+        with ChainEngine(spec, cfg, 4096, device=local_rank) as eng2:
+            eng2.init_chains(synthetic.chain_starts(p["x0"], 4096, jitter=0.01, seed=5), p["prop_cov"])
+            eng2.run(2000, thin=2000, keep_samples=False)                 # burn-in / adaptation
+            res = eng2.run(T_ess, thin=1, sample_chains=n_probe)
+            eng2.synchronize()
+            smp = res.samples.cpu().numpy()                               # [T, d, n_probe]
+        ess_step = float(np.nanmean([ess_batch_means(smp[:, :, c]) for c in range(n_probe)])) / T_ess
+        ess = {"estimator": "batch means, min over parameters", "gpu_ess_per_chain_step": ess_step,
+               "gpu_ess_per_s": ess_step * value}
+
     # ---- CPU baseline (rank 0, single GPU runs only) ----------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         n_it = 100000
-        rate, dt = cpu_port_rate(1, n_it)
+        rate, dt, chain = cpu_port_rate(1, n_it, return_chain=True)
         cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": "1 chain x %d AM iterations of the same cubic problem through oracle/mcmc_oracle.py (%.1f s)" % (n_it, dt)}
+        if ess is not None:
+            from pybitup_b200.diagnostics import ess_batch_means
+            segs = [chain[2000 + i * 24000: 2000 + (i + 1) * 24000] for i in range((len(chain) - 2000) // 24000)]
+            e_cpu = float(np.mean([ess_batch_means(sg) for sg in segs])) / 24000
+            ess.update({"cpu_ess_per_chain_step": e_cpu, "cpu_ess_per_s": e_cpu * rate})
 
     if rank == 0:
         ms_launch = total_ms / K
@@ -302,6 +324,7 @@ def run_gpu_arm(args):
                          "hbm": {"achieved": bytes_launch / (ms_launch * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": bytes_launch / (ms_launch * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src}},
             "cpu_baseline": cpu,
+            "ess": ess,
         }
         prof = os.path.join(ROOT, "profiles", "traffic_r1.json")
         if os.path.exists(prof):

@@ -453,13 +453,25 @@ static void inv_upper_host(const std::vector<double> &R, int d, std::vector<doub
     }
 }
 
-// fill rows of a chain-minor [n_rows][C] device array with one value per row
+// fill rows of a chain-minor [n_rows][C] device array with one value per row (values travel as kernel arguments)
+__global__ void fill_i64_kernel(int64_t *dst, int64_t n, int64_t v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = v;
+}
+struct RowValues {
+    double v[tri_size(PBU_MAX_DIM)];
+};
+__global__ void broadcast_rows_kernel(double *dst, int64_t C, int n_rows, RowValues vals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C) return;
+    for (int r = 0; r < n_rows; ++r) dst[(int64_t)r * C + i] = vals.v[r];
+}
 static int broadcast_rows(pbu_engine *e, double *dev, const std::vector<double> &vals) {
-    const int64_t C = e->C;
-    std::vector<double> buf(vals.size() * (size_t)C);
-    for (size_t i = 0; i < vals.size(); ++i) std::fill(buf.begin() + i * C, buf.begin() + (i + 1) * C, vals[i]);
-    CUDA_TRY(cudaMemcpyAsync(dev, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    RowValues rv;
+    if (vals.size() > sizeof(rv.v) / sizeof(double)) return fail(PBU_ERR_INVALID, "too many rows");
+    for (size_t i = 0; i < vals.size(); ++i) rv.v[i] = vals[i];
+    broadcast_rows_kernel<<<(unsigned)((e->C + 255) / 256), 256, 0, e->stream>>>(dev, e->C, (int)vals.size(), rv);
+    CUDA_TRY(cudaGetLastError());
     return PBU_OK;
 }
 
@@ -506,7 +518,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_init_chains(pbu
             // V_i = V_0 (mha.py:404), X_av_i = param_init (:405); Welford mode starts from M2 = 0
             if (e->cfg.am_welford) std::fill(Vp.begin(), Vp.end(), 0.0);
             if ((rc = broadcast_rows(e, e->st.V, Vp))) return rc;
-            CUDA_TRY(cudaMemcpyAsync(e->st.xav, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+            CUDA_TRY(cudaMemcpyAsync(e->st.xav, e->st.x, soa.size() * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
         }
     }
     CUDA_TRY(cudaMemsetAsync(e->st.mean_r, 0, C * sizeof(double), e->stream));
@@ -519,8 +531,8 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_init_chains(pbu
     CUDA_TRY(cudaMemsetAsync(e->streams.cur_n, 0, C * sizeof(int64_t), e->stream));
     CUDA_TRY(cudaMemsetAsync(e->streams.cur_u, 0, C * sizeof(int64_t), e->stream));
     // initial posterior evaluation(s): once, twice for DRAM (double __init__, mha.py:588-589)
-    std::vector<int64_t> ne((size_t)C, e->cfg.algo == PBU_ALGO_DRAM ? 2 : 1);
-    CUDA_TRY(cudaMemcpyAsync(e->st.n_eval, ne.data(), C * sizeof(int64_t), cudaMemcpyHostToDevice, e->stream));
+    fill_i64_kernel<<<(unsigned)((C + 255) / 256), 256, 0, e->stream>>>(e->st.n_eval, C, e->cfg.algo == PBU_ALGO_DRAM ? 2 : 1);
+    CUDA_TRY(cudaGetLastError());
     rc = launch_eval_lp(e, e->st.x, C, e->st.lp);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(e->stream));
