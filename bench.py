@@ -272,7 +272,7 @@ def run_gpu_arm(args):
 
     # ---- effective sample size per chain-step (same batch-means estimator on both sides) ----------
     ess = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:
         from pybitup_b200.diagnostics import ess_batch_means
         n_probe, T_ess = 16, 24000           # the CPU chain below is cut into segments of the same length
         with ChainEngine(spec, cfg, 4096, device=local_rank) as eng2:
