@@ -401,6 +401,95 @@ def run_isde(prob, x0, n_it, streams, h, f0, gradient="Analytical", C0=None,
     return dict(chain=chain, P=Ps, C=C, X_av=X_av, V_i=V_i)
 
 
+# --------------------------------------------------------------------------- Hamiltonian Monte Carlo
+def run_hmc(prob, x0, n_it, streams, step_size, num_steps, gradient="Analytical", C0=None,
+            starting_it=None, update_it=1, end_it=None):
+    """HamiltonianMonteCarlo (:779-884) driven by MetropolisHastings.run_algorithm (:158-182) for ONE chain.
+
+    Per iteration: adapt_covariance (:736-777, as for ISDE); p = z @ inv_L_c^T (d normals, :829-830); half momentum
+    step with the gradient at the CURRENT state (:836); L position / momentum leapfrog steps with the preconditioner
+    C (:842-850); final half step and sign flip (:852-855); r = exp(U_cur - U_new + K_cur - K_new) with
+    K = sum((p @ C) * p)/2 (:862-879; the `is -np.inf` test never fires, exp(-inf) gives 0 anyway); one uniform (:213).
+    On acceptance the stored gradient becomes the one at the end of the trajectory (:221).
+    Returns chain[T+1,d], acc[T], lp[T+1], n_rejected, mean_r, final C.
+    """
+    d = prob.d
+    cur = np.array(x0, dtype=np.float64)
+    C = np.eye(d) if C0 is None else np.array(C0, dtype=np.float64)
+    L_c = chol_upper(C)
+    inv_L_c = inv_upper(L_c)
+    inv_L_c_T = inv_upper(np.transpose(L_c)) if C0 is None else np.transpose(inv_L_c)
+    if starting_it is None:
+        starting_it = n_it + 10
+    if end_it is None:
+        end_it = n_it + 1
+    S_d, eps_Id = 1.0, 1e-10 * np.eye(d)
+    X_av, V_i = np.array(x0, dtype=np.float64), None
+    if gradient == "Analytical":
+        def grad(X):
+            return grad_log_post(prob, X)
+    else:
+        def grad(X):
+            return grad_fd(lambda Z: log_post(prob, Z), X, eps=0.0000000001)
+    lp_cur = log_post(prob, cur)
+    g_cur = grad(cur)
+    chain = np.zeros((n_it + 1, d))
+    lps = np.zeros(n_it + 1)
+    acc = np.zeros(n_it, dtype=np.int32)
+    chain[0], lps[0] = cur, lp_cur
+    rows = [np.array(cur)]
+    n_rejected, mean_r = 0, 0.0
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        for it in range(1, n_it + 1):
+            if starting_it <= it <= end_it + 1:
+                if it == starting_it:
+                    vals = np.array(rows)
+                    X_av = np.mean(vals, axis=0)
+                    V_i = S_d * (np.atleast_2d(np.cov(vals, rowvar=False)) + eps_Id)
+                elif it <= end_it:
+                    X_i = cur
+                    X_av_ip = X_i + (it) / (it + 1) * (X_av - X_i)
+                    V_i = (it - 1) / it * V_i + S_d / it * (
+                        it * np.tensordot(X_av, X_av, axes=0) - (it + 1) * np.tensordot(X_av_ip, X_av_ip, axes=0)
+                        + np.tensordot(X_i, X_i, axes=0) + eps_Id)
+                    X_av = X_av_ip
+                if it % update_it == 0:
+                    C = V_i
+                    L_c = chol_upper(C)
+                    inv_L_c = inv_upper(L_c)
+                    inv_L_c_T = np.transpose(inv_L_c)
+            new = np.array(cur)
+            z = np.array([streams.gauss(0, 1) for _ in range(d)])
+            p = np.matmul(z, inv_L_c_T)
+            cur_p = p
+            p = p - step_size * (-g_cur) / 2
+            g_new = g_cur
+            for i in range(num_steps):
+                new = new + step_size * (np.matmul(p, C))
+                g_new = grad(new)
+                if i != (num_steps - 1):
+                    p = p - step_size * (-g_new)
+            p = p - step_size * (-g_new) / 2
+            p = -p
+            cur_K = np.sum(np.matmul(cur_p, C) * cur_p) / 2
+            lp_new = log_post(prob, new)
+            prop_K = np.sum(np.matmul(p, C) * p) / 2
+            r = np.exp((-lp_cur) - (-lp_new) + cur_K - prop_K)
+            alpha = py_min1(r)
+            u = streams.random()
+            if u < alpha:
+                cur = np.array(new)
+                lp_cur = lp_new
+                g_cur = g_new
+                acc[it - 1] = 1
+            else:
+                n_rejected += 1
+            mean_r += alpha
+            chain[it], lps[it] = cur, lp_cur
+            rows.append(np.array(cur))
+    return dict(chain=chain, lp=lps, acc=acc, n_rejected=n_rejected, mean_r=mean_r, C=C)
+
+
 # --------------------------------------------------------------------------- propagation
 def propagate(prob, samples):
     """Monte-Carlo propagation, emulator == 'None' (solve_problem.py:543-647).

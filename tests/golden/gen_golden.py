@@ -197,6 +197,14 @@ def isde_algo(n_it, h, f0, gradient, starting_it, update_it, end_it=None):
             "covariance": cov, "gradient": gradient, "ISDE": {"h": h, "f0": f0}}
 
 
+def hmc_algo(n_it, step_size, num_steps, gradient, starting_it, update_it, end_it=None):
+    cov = {"value": "Identity", "starting_it": starting_it, "update_it": update_it}
+    if end_it is not None:
+        cov["end_it"] = end_it
+    return {"name": "HMC", "n_iterations": n_it, "save_eval_freq": 10 ** 9, "covariance": cov, "gradient": gradient,
+            "HMC": {"step_size": step_size, "num_steps": num_steps}}
+
+
 def build_model(prob, names):
     if prob["model"] == "linear":
         m = LinearModel()
@@ -291,8 +299,11 @@ def main():
     run_case("linear_isde_fd", lin, lin_names, isde_algo(100, 0.002, 4.0, "Numerical", 10 ** 6, 10), 53, 100 * 3)
 
 
-if __name__ == "__main__":
-    main()
+def gen_hmc():
+    reg = synthetic.regression_problem(n_points=200, d=5)
+    reg_names = ["b%d" % i for i in range(5)]
+    run_case("regression_hmc", reg, reg_names, hmc_algo(150, 0.01, 5, "Analytical", 10 ** 6, 10), 61, 150 * 6)
+    run_case("regression_hmc_adapt", reg, reg_names, hmc_algo(400, 0.01, 4, "Analytical", 150, 25, 300), 62, 400 * 6)
 
 
 def gen_hessian_fd():
@@ -308,5 +319,12 @@ def gen_hessian_fd():
     np.savez(os.path.join(HERE, "_hessian_fd.npz"), A=A, x=x, **out)
 
 
-if __name__ == "__main__" and "--hessian" in sys.argv:
-    gen_hessian_fd()
+if __name__ == "__main__":
+    if "--hessian" in sys.argv:
+        gen_hessian_fd()
+    elif "--hmc" in sys.argv:
+        gen_hmc()
+    else:
+        main()
+        gen_hmc()
+        gen_hessian_fd()
