@@ -60,7 +60,8 @@ typedef enum {
     PBU_ALGO_AM = 1,   /* AdaptiveMetropolisHastings                 mha.py:370-487  */
     PBU_ALGO_DR = 2,   /* DelayedRejectionMetropolisHastings         mha.py:490-567  */
     PBU_ALGO_DRAM = 3, /* DelayedRejectionAdaptiveMetropolisHastings mha.py:570-595  */
-    PBU_ALGO_ISDE = 4  /* ito_SDE                                    mha.py:886-1040 */
+    PBU_ALGO_ISDE = 4, /* ito_SDE                                    mha.py:886-1040 */
+    PBU_ALGO_HMC = 5   /* HamiltonianMonteCarlo                      mha.py:779-884  */
 } pbu_algo_id;
 
 /* One Bayesian inverse problem: what Sampling.sample builds at solve_problem.py:184-337
@@ -106,6 +107,9 @@ typedef struct {
                                  tiles; > 0 forces tiles of at most that many points (testing)            */
     uint64_t seed;            /* Philox key                                                       */
     uint64_t chain_offset;    /* global index of this engine's first chain (multi-GPU sharding)   */
+    double hmc_step_size;     /* HMC.step_size (epsilon)       (mha.py:818)                       */
+    int32_t hmc_num_steps;    /* HMC.num_steps (L)             (mha.py:819)                       */
+    int32_t pad0;
 } pbu_sampler_cfg;
 
 /* Per-run outputs that live on the device; any pointer may be NULL (= not recorded).
@@ -141,8 +145,8 @@ int pbu_engine_set_stream(pbu_engine *e, void *cuda_stream);
 
 /* Initial state: x0 host [C][d] (MetropolisHastings.__init__: current_val = param_init, :95-99),
  * proposal covariance V0 host [d][d] shared by all chains (:80, :142-143; R = upper Cholesky).
- * Evaluates the initial log-posterior on the device (:102). For ISDE V0 is the preconditioner
- * C_approx (:653-711) and may be NULL for identity. */
+ * Evaluates the initial log-posterior on the device (:102). For ISDE / HMC V0 is the preconditioner
+ * C_approx (:653-711) and may be NULL for identity; HMC also evaluates the initial gradient (:815). */
 int pbu_engine_init_chains(pbu_engine *e, const double *x0_host, const double *V0_host);
 
 /* Parity mode: replace Philox by pre-generated streams (what `mha.random = obj` does to the

@@ -23,7 +23,7 @@ PBU_ERR_NOT_PD = -4
 PBU_ERR_STREAM_EXHAUSTED = -5
 
 MODEL_IDS = {"linear": 0, "poly": 1, "arrhenius": 2, "heat": 3}
-ALGO_IDS = {"RWMH": 0, "AMH": 1, "DR": 2, "DRAM": 3, "ISDE": 4}
+ALGO_IDS = {"RWMH": 0, "AMH": 1, "DR": 2, "DRAM": 3, "ISDE": 4, "HMC": 5}
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -43,7 +43,8 @@ class pbu_sampler_cfg(C.Structure):
                 ("adapt_start", C.c_int32), ("adapt_update", C.c_int32), ("adapt_end", C.c_int32),
                 ("am_welford", C.c_int32), ("nan_rejects", C.c_int32), ("lanes_per_chain", C.c_int32),
                 ("block_threads", C.c_int32), ("chains_per_thread", C.c_int32), ("tile_points", C.c_int32),
-                ("seed", C.c_uint64), ("chain_offset", C.c_uint64)]
+                ("seed", C.c_uint64), ("chain_offset", C.c_uint64), ("hmc_step_size", C.c_double),
+                ("hmc_num_steps", C.c_int32), ("pad0", C.c_int32)]
 
 
 class pbu_run_outputs(C.Structure):

@@ -106,6 +106,15 @@ static const IsdeKernelEntry *find_isde(int model, int P, int d, int lanes, int 
             return &t[i];
     return nullptr;
 }
+static const IsdeKernelEntry *find_hmc(int model, int P, int d, int lanes, int q, int streamed) {
+    int n = 0;
+    const IsdeKernelEntry *t = pbu_hmc_kernels(&n);
+    for (int i = 0; i < n; ++i)
+        if (t[i].model == model && t[i].n_param == P && t[i].n_unc == d && t[i].lanes == lanes && t[i].chains_per_thread == q &&
+            t[i].streamed == streamed)
+            return &t[i];
+    return nullptr;
+}
 static const EvalKernelEntry *find_eval(int model, int P, int d) {
     int n = 0;
     const EvalKernelEntry *t = pbu_eval_kernels(&n);
@@ -190,7 +199,8 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
     const double S0 = 60.0 + 15.0 * e->d;           // per-iteration scalar part (RNG, proposal, accept, adaptation), in DFMA-equivalents
     // (lanes per chain, chains per thread, mixed): mixed = the last warps of a block use twice the lanes
     const int cand[8][3] = {{1, 1, 0}, {1, 2, 0}, {2, 2, 0}, {2, 2, 1}, {4, 2, 0}, {2, 1, 0}, {4, 1, 0}, {8, 1, 0}};
-    const bool isde = algo == PBU_ALGO_ISDE;
+    const bool hmc = algo == PBU_ALGO_HMC;
+    const bool isde = algo == PBU_ALGO_ISDE || hmc;
     const int streamed = e->tile_points < e->prob.n_points ? 1 : 0;
     const double ops = isde ? 2.0 * e->ev->ops : (double)e->ev->ops;     // value + gradient
     double best = 1e300;
@@ -210,7 +220,7 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
         const MhKernelEntry *km = nullptr;
         const IsdeKernelEntry *ki = nullptr;
         if (isde) {
-            ki = find_isde(model, e->P, e->d, g, q, streamed);
+            ki = hmc ? find_hmc(model, e->P, e->d, g, q, streamed) : find_isde(model, e->P, e->d, g, q, streamed);
             if (ki) fn = ki->fn;
         } else {
             km = find_mh(model, e->P, e->d, g, q, algo, streamed, mixed);
@@ -312,8 +322,12 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
         delete e;
         return fail(PBU_ERR_INVALID, "block_threads must be a multiple of 32 in [32, %d]", MH_MAX_BLOCK);
     }
-    if (cfg->algo == PBU_ALGO_ISDE) {
-        if (!(cfg->isde_h > 0.0) || !(cfg->isde_f0 >= 0.0)) {
+    if (cfg->algo == PBU_ALGO_HMC && (!(cfg->hmc_step_size > 0.0) || cfg->hmc_num_steps < 1)) {
+        delete e;
+        return fail(PBU_ERR_INVALID, "HMC needs step_size > 0 and num_steps >= 1");
+    }
+    if (cfg->algo == PBU_ALGO_ISDE || cfg->algo == PBU_ALGO_HMC) {
+        if (cfg->algo == PBU_ALGO_ISDE && (!(cfg->isde_h > 0.0) || !(cfg->isde_f0 >= 0.0))) {
             delete e;
             return fail(PBU_ERR_INVALID, "ISDE needs h > 0 and f0 >= 0");
         }
@@ -405,7 +419,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
         (rc = dev_alloc(e, &st.n_rej, (size_t)C)) || (rc = dev_alloc(e, &st.n_eval, (size_t)C)) ||
         (rc = dev_alloc(e, &st.status, (size_t)C)) || (rc = dev_alloc(e, &st.wmean, (size_t)e->d * C)) ||
         (rc = dev_alloc(e, &st.wM2, (size_t)e->nt * C)) || (rc = dev_alloc(e, &st.wcount, (size_t)C)) ||
-        (rc = dev_alloc(e, &st.P, (size_t)e->d * C)) || (rc = dev_alloc(e, &e->d_Cmat, (size_t)(cfg->algo == PBU_ALGO_ISDE ? e->nt : 0) * C)) || (rc = dev_alloc(e, &e->streams.cur_n, (size_t)C)) ||
+        (rc = dev_alloc(e, &st.P, (size_t)e->d * C)) || (rc = dev_alloc(e, &e->d_Cmat, (size_t)((cfg->algo == PBU_ALGO_ISDE || cfg->algo == PBU_ALGO_HMC) ? e->nt : 0) * C)) || (rc = dev_alloc(e, &e->streams.cur_n, (size_t)C)) ||
         (rc = dev_alloc(e, &e->streams.cur_u, (size_t)C)))
         return rc;
     CUDA_TRY(cudaStreamSynchronize(e->stream));
@@ -485,7 +499,8 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_init_chains(pbu
     transpose_to_soa(x0_host, C, d, soa);
     CUDA_TRY(cudaMemcpyAsync(e->st.x, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     const bool adapt = e->cfg.algo == PBU_ALGO_AM || e->cfg.algo == PBU_ALGO_DRAM;
-    const bool isde = e->cfg.algo == PBU_ALGO_ISDE;
+    const bool hmc = e->cfg.algo == PBU_ALGO_HMC;
+    const bool isde = e->cfg.algo == PBU_ALGO_ISDE || hmc;
     std::vector<double> Vid;
     if (!V0_host) {
         Vid.assign((size_t)d * d, 0.0);
@@ -531,10 +546,20 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_init_chains(pbu
     CUDA_TRY(cudaMemsetAsync(e->streams.cur_n, 0, C * sizeof(int64_t), e->stream));
     CUDA_TRY(cudaMemsetAsync(e->streams.cur_u, 0, C * sizeof(int64_t), e->stream));
     // initial posterior evaluation(s): once, twice for DRAM (double __init__, mha.py:588-589)
-    fill_i64_kernel<<<(unsigned)((C + 255) / 256), 256, 0, e->stream>>>(e->st.n_eval, C, e->cfg.algo == PBU_ALGO_DRAM ? 2 : 1);
+    // ... and twice for HMC (MetropolisHastings.__init__ :102 and HamiltonianMonteCarlo.__init__ :814)
+    fill_i64_kernel<<<(unsigned)((C + 255) / 256), 256, 0, e->stream>>>(e->st.n_eval, C, (e->cfg.algo == PBU_ALGO_DRAM || hmc) ? 2 : 1);
     CUDA_TRY(cudaGetLastError());
     rc = launch_eval_lp(e, e->st.x, C, e->st.lp);
     if (rc) return rc;
+    if (hmc) {      // distr_grad_log_like_current_val = computeGrad(current_val)  (:815), kept in st.P
+        CUDA_TRY(cudaFuncSetAttribute(e->ev->eval_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+        const int block = 128;
+        const unsigned grid = (unsigned)((C + block - 1) / block);
+        int64_t S = C;
+        int fd = e->cfg.isde_gradient != 0;
+        void *gargs[] = {(void *)&e->prob, (void *)&e->st.x, (void *)&S, (void *)&e->st.P, (void *)&e->tile_points, (void *)&fd};
+        CUDA_TRY(cudaLaunchKernel(e->ev->eval_grad, dim3(grid), dim3(block), gargs, e->smem_bytes, e->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     e->iteration = 0;
     e->initialised = true;
@@ -552,7 +577,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_set_proposal(pb
         for (int j = i; j < d; ++j) Vp[tri_idx(d, i, j)] = V_host[i * d + j];
     int rc;
     CUDA_TRY(cudaStreamSynchronize(e->stream));
-    if (e->cfg.algo == PBU_ALGO_ISDE) {
+    if (e->cfg.algo == PBU_ALGO_ISDE || e->cfg.algo == PBU_ALGO_HMC) {
         std::vector<double> IL;
         inv_upper_host(Rp, d, IL);
         if ((rc = broadcast_rows(e, e->d_Cmat, Vp)) || (rc = broadcast_rows(e, e->st.R, IL))) return rc;
@@ -615,7 +640,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine 
     if (n_steps < 0 || thin < 1) return fail(PBU_ERR_INVALID, "need n_steps >= 0 and thin >= 1");
     if (n_steps == 0) return PBU_OK;
     CUDA_TRY(cudaSetDevice(e->device));
-    if (e->cfg.algo == PBU_ALGO_ISDE) {
+    if (e->cfg.algo == PBU_ALGO_ISDE || e->cfg.algo == PBU_ALGO_HMC) {
         IsdeParams q;
         memset(&q, 0, sizeof q);
         q.prob = e->prob;
@@ -630,7 +655,8 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine 
         q.n_groups = (int64_t)e->grid * e->groups_per_block;
         q.seed = e->cfg.seed;
         q.chain_offset = e->cfg.chain_offset;
-        q.h = e->cfg.isde_h;
+        q.h = e->cfg.algo == PBU_ALGO_HMC ? e->cfg.hmc_step_size : e->cfg.isde_h;
+        q.hmc_steps = e->cfg.hmc_num_steps;
         q.f0 = e->cfg.isde_f0;
         q.S_d = 1.0;                 // mha.py:630
         q.eps_id = 1e-10;            // mha.py:631
@@ -759,7 +785,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_get_proposal(pb
 
 extern "C" __attribute__((visibility("default"))) int pbu_engine_get_isde_state(pbu_engine *e, double *P_host, double *C_host) {
     if (!e) return fail(PBU_ERR_INVALID, "null engine");
-    if (e->cfg.algo != PBU_ALGO_ISDE) return fail(PBU_ERR_INVALID, "not an ISDE engine");
+    if (e->cfg.algo != PBU_ALGO_ISDE && e->cfg.algo != PBU_ALGO_HMC) return fail(PBU_ERR_INVALID, "not an ISDE / HMC engine");
     CUDA_TRY(cudaSetDevice(e->device));
     const int d = e->d;
     const int64_t C = e->C;

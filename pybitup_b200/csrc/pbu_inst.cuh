@@ -27,11 +27,21 @@
         PBU_ISDE(MODEL, P, D, 1, 1, 1), PBU_ISDE(MODEL, P, D, 1, 2, 1), PBU_ISDE(MODEL, P, D, 8, 1, 1),               \
         PBU_ISDE(MODEL, P, D, 4, 1, 0), PBU_ISDE(MODEL, P, D, 4, 1, 1), PBU_ISDE(MODEL, P, D, 2, 1, 1)
 #define PBU_ISDE_SEQ(MODEL, P, D) PBU_ISDE(MODEL, P, D, 1, 1, 0), PBU_ISDE(MODEL, P, D, 1, 1, 1)
+// Hamiltonian Monte Carlo step kernel variants (same table type as ISDE; `kind` 1)
+#define PBU_HMC(MODEL, P, D, G, Q, S) \
+    { MODEL::ID, P, D, G, Q, MODEL::HAS_GRAD ? 1 : 0, S, (const void *)&pbu::hmc_step_kernel<MODEL, D, G, Q, (S != 0)> }
+#define PBU_HMC_ALL(MODEL, P, D) PBU_HMC(MODEL, P, D, 1, 1, 0), PBU_HMC(MODEL, P, D, 4, 1, 0), PBU_HMC(MODEL, P, D, 8, 1, 0), PBU_HMC(MODEL, P, D, 1, 1, 1)
+#define PBU_HMC_SEQ(MODEL, P, D) PBU_HMC(MODEL, P, D, 1, 1, 0), PBU_HMC(MODEL, P, D, 1, 1, 1)
 #define PBU_EVAL(MODEL, P, D)                                                                 \
     { MODEL::ID, P, D, MODEL::SEQUENTIAL ? 1 : 0, MODEL::NC, MODEL::NCR, MODEL::OPS, MODEL::WF, (const void *)&pbu::eval_logpost_kernel<MODEL, D>, \
-      (const void *)&pbu::eval_model_kernel<MODEL, D> }
+      (const void *)&pbu::eval_model_kernel<MODEL, D>, (const void *)&pbu::eval_grad_kernel<MODEL, D> }
 
-#define PBU_DEFINE_SLICE(name, MH_LIST, EVAL_LIST, ISDE_LIST)                        \
+#define PBU_DEFINE_SLICE(name, MH_LIST, EVAL_LIST, ISDE_LIST, HMC_LIST)              \
+    static const pbu::IsdeKernelEntry hmc_tab_##name[] = {HMC_LIST};                 \
+    const pbu::IsdeKernelEntry *pbu_hmc_slice_##name(int *n) {                       \
+        *n = (int)(sizeof(hmc_tab_##name) / sizeof(hmc_tab_##name[0]));              \
+        return hmc_tab_##name;                                                       \
+    }                                                                                \
     static const pbu::MhKernelEntry mh_tab_##name[] = {MH_LIST};                     \
     static const pbu::EvalKernelEntry ev_tab_##name[] = {EVAL_LIST};                 \
     static const pbu::IsdeKernelEntry isde_tab_##name[] = {ISDE_LIST};               \

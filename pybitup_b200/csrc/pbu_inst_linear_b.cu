@@ -4,4 +4,5 @@ using namespace pbu;
 #define MH_LIST PBU_MH_ALL(LinearModel<4>, 4, 4), PBU_MH_ALL(LinearModel<5>, 5, 5), PBU_MH_ALL(LinearModel<6>, 6, 6)
 #define EV_LIST PBU_EVAL(LinearModel<4>, 4, 4), PBU_EVAL(LinearModel<5>, 5, 5), PBU_EVAL(LinearModel<6>, 6, 6)
 #define ISDE_LIST PBU_ISDE_ALL(LinearModel<4>, 4, 4), PBU_ISDE_ALL(LinearModel<5>, 5, 5), PBU_ISDE_ALL(LinearModel<6>, 6, 6)
-PBU_DEFINE_SLICE(linear_b, MH_LIST, EV_LIST, ISDE_LIST)
+#define HMC_LIST PBU_HMC_ALL(LinearModel<4>, 4, 4), PBU_HMC_ALL(LinearModel<5>, 5, 5), PBU_HMC_ALL(LinearModel<6>, 6, 6)
+PBU_DEFINE_SLICE(linear_b, MH_LIST, EV_LIST, ISDE_LIST, HMC_LIST)

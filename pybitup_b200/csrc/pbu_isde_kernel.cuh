@@ -35,6 +35,8 @@ struct IsdeParams {
     int64_t starting_it, update_it, end_it;
     int32_t tile_points;
     int32_t fd_gradient;      // 1: forward differences with relative step 1e-10 (mha.py:726, :1069-1088)
+    int32_t hmc_steps;        // HMC: leapfrog steps L (mha.py:819); the step size epsilon travels in h
+    int32_t pad0;
 };
 
 // symmetric packed matrix (upper triangle stored) times vector, reading the matrix from global memory
@@ -66,6 +68,80 @@ __device__ __forceinline__ void inv_upper_packed(const double (&R)[tri_size(D)],
             X[tri_idx(D, i, j)] = -s / R[tri_idx(D, i, i)];
         }
     }
+}
+
+// GradientBasedMCMC.adapt_covariance (mha.py:736-777) for one chain: before the window a Welford accumulation of the
+// states (rows 0..it-1 of the chain, which the reference re-reads from its CSV at :744); at starting_it the window
+// opens with X_av = mean, V_i = S_d (cov + eps I); inside it the Haario recursion; every update_it iterations the
+// preconditioner C, its upper Cholesky factor and the inverse of that are refreshed.  x = current_val.
+template <int D>
+__device__ __forceinline__ void adapt_preconditioner(const IsdeParams &p, int64_t it, bool upd, const double (&x)[D], bool live, double *gC,
+                                                     double *gIL, double *gV, double *gxav, int64_t C, int32_t &status) {
+    constexpr int NT = tri_size(D);
+    if (it <= p.starting_it) {
+        // Welford over rows 0..it-1 of the chain (the rows the reference re-reads from its CSV at :744)
+        const double inv_n = 1.0 / (double)it;
+        double dl[D], mu[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const double m = (it == 1) ? 0.0 : gxav[(int64_t)i * C];
+            dl[i] = x[i] - m;
+            mu[i] = fma(dl[i], inv_n, m);
+            if (live) gxav[(int64_t)i * C] = mu[i];
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = i; j < D; ++j) {
+                const int64_t o = (int64_t)tri_idx(D, i, j) * C;
+                double v = fma(dl[i], x[j] - mu[j], (it == 1) ? 0.0 : gV[o]);
+                if (it == p.starting_it)        // V_i = S_d (cov + eps I), np.cov with ddof = 1   (:745-746)
+                    v = p.S_d * (v / (double)(it - 1) + ((i == j) ? p.eps_id : 0.0));
+                if (live) gV[o] = v;
+            }
+    } else if (it <= p.end_it) {
+        const double fi = (double)it;
+        double xa[D], xb[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            xa[i] = gxav[(int64_t)i * C];
+            xb[i] = __dadd_rn(x[i], __dmul_rn(fi / (fi + 1.0), __dadd_rn(xa[i], -x[i])));      // :752
+        }
+        const double c1 = (fi - 1.0) / fi, c2 = p.S_d / fi;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = i; j < D; ++j) {
+                double t = __dadd_rn(__dmul_rn(fi, __dmul_rn(xa[i], xa[j])), -__dmul_rn(fi + 1.0, __dmul_rn(xb[i], xb[j])));
+                t = __dadd_rn(t, __dmul_rn(x[i], x[j]));
+                t = __dadd_rn(t, (i == j) ? p.eps_id : 0.0);
+                const int64_t o = (int64_t)tri_idx(D, i, j) * C;
+                const double v = __dadd_rn(__dmul_rn(c1, gV[o]), __dmul_rn(c2, t));                       // :753
+                if (live) gV[o] = v;
+            }
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) gxav[(int64_t)i * C] = xb[i];
+        }
+    }
+    if (it >= p.starting_it && it <= p.end_it + 1 && upd) {                         // :767-777
+        double Vc[NT], Lc[NT], IL[NT];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) Vc[i] = gV[(int64_t)i * C];
+        if (chol_upper_packed<D>(Vc, Lc)) {
+            inv_upper_packed<D>(Lc, IL);
+            if (live) {
+#pragma unroll
+                for (int i = 0; i < NT; ++i) {
+                    gC[(int64_t)i * C] = Vc[i];
+                    gIL[(int64_t)i * C] = IL[i];
+                }
+            }
+        } else {
+            status |= ST_NOT_PD;
+        }
+    }
+
 }
 
 // Gradient of the log-likelihood (and the log-posterior value) at x for the Q chains of a thread.
@@ -172,69 +248,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) isde_step_kernel(const __grid
             double *const gV = p.st.V + cq;
             double *const gxav = p.st.xav + cq;
             // ---- adaptation of the preconditioner (:736-777); current_val = xi_nm (:958)
-            if (it <= p.starting_it) {
-                // Welford over rows 0..it-1 of the chain (the rows the reference re-reads from its CSV at :744)
-                const double inv_n = 1.0 / (double)it;
-                double dl[D], mu[D];
-#pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    const double m = (it == 1) ? 0.0 : gxav[(int64_t)i * C];
-                    dl[i] = xi[q][i] - m;
-                    mu[i] = fma(dl[i], inv_n, m);
-                    if (live[q]) gxav[(int64_t)i * C] = mu[i];
-                }
-#pragma unroll
-                for (int i = 0; i < D; ++i)
-#pragma unroll
-                    for (int j = i; j < D; ++j) {
-                        const int64_t o = (int64_t)tri_idx(D, i, j) * C;
-                        double v = fma(dl[i], xi[q][j] - mu[j], (it == 1) ? 0.0 : gV[o]);
-                        if (it == p.starting_it)        // V_i = S_d (cov + eps I), np.cov with ddof = 1   (:745-746)
-                            v = p.S_d * (v / (double)(it - 1) + ((i == j) ? p.eps_id : 0.0));
-                        if (live[q]) gV[o] = v;
-                    }
-            } else if (it <= p.end_it) {
-                const double fi = (double)it;
-                double xa[D], xb[D];
-#pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    xa[i] = gxav[(int64_t)i * C];
-                    xb[i] = __dadd_rn(xi[q][i], __dmul_rn(fi / (fi + 1.0), __dadd_rn(xa[i], -xi[q][i])));      // :752
-                }
-                const double c1 = (fi - 1.0) / fi, c2 = p.S_d / fi;
-#pragma unroll
-                for (int i = 0; i < D; ++i)
-#pragma unroll
-                    for (int j = i; j < D; ++j) {
-                        double t = __dadd_rn(__dmul_rn(fi, __dmul_rn(xa[i], xa[j])), -__dmul_rn(fi + 1.0, __dmul_rn(xb[i], xb[j])));
-                        t = __dadd_rn(t, __dmul_rn(xi[q][i], xi[q][j]));
-                        t = __dadd_rn(t, (i == j) ? p.eps_id : 0.0);
-                        const int64_t o = (int64_t)tri_idx(D, i, j) * C;
-                        const double v = __dadd_rn(__dmul_rn(c1, gV[o]), __dmul_rn(c2, t));                       // :753
-                        if (live[q]) gV[o] = v;
-                    }
-                if (live[q]) {
-#pragma unroll
-                    for (int i = 0; i < D; ++i) gxav[(int64_t)i * C] = xb[i];
-                }
-            }
-            if (it >= p.starting_it && it <= p.end_it + 1 && upd) {                         // :767-777
-                double Vc[NT], Lc[NT], IL[NT];
-#pragma unroll
-                for (int i = 0; i < NT; ++i) Vc[i] = gV[(int64_t)i * C];
-                if (chol_upper_packed<D>(Vc, Lc)) {
-                    inv_upper_packed<D>(Lc, IL);
-                    if (live[q]) {
-#pragma unroll
-                        for (int i = 0; i < NT; ++i) {
-                            gC[(int64_t)i * C] = Vc[i];
-                            gIL[(int64_t)i * C] = IL[i];
-                        }
-                    }
-                } else {
-                    status[q] |= ST_NOT_PD;
-                }
-            }
+            adapt_preconditioner<D>(p, it, upd, xi[q], live[q], gC, gIL, gV, gxav, C, status[q]);
 
             // ---- first half step (:990-991)
             double z[D], udummy;
@@ -375,6 +389,283 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) isde_step_kernel(const __grid
             p.st.n_eval[cq] += n_eval[q];
             p.st.status[cq] = status[q];
         }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// K2b: fused Hamiltonian Monte Carlo step kernel (HamiltonianMonteCarlo, mha.py:779-884, driven by
+// MetropolisHastings.run_algorithm :158-182).  Per chain and iteration:
+//   adaptation of the preconditioner as for ISDE                              :826, :736-777
+//   p = z @ inv_L_c^T = inv_L_c z (d normals);  K_cur = sum((p C) p)/2        :829-831, :862-866
+//   p += eps g_cur / 2                                                        :836
+//   L times:  x += eps (p C);  g = grad(x);  p += eps g  (not after the last) :842-850
+//   p += eps g / 2;  p = -p;  K_new = sum((p C) p)/2                          :852-855, :871-874
+//   r = exp(U_cur - U_new + K_cur - K_new), U = -log posterior;  u < min(1, r) accepts          :876-881, :210-224
+// The stored gradient of the current state (p.st.P) follows the state on acceptance (:221).  The log-posterior at the
+// end of the trajectory comes from the same data pass as the last gradient.
+// ------------------------------------------------------------------------------------------------
+template <class M, int D, int G, int Q, bool STREAM>
+__global__ void __launch_bounds__(MH_MAX_BLOCK, 1) hmc_step_kernel(const __grid_constant__ IsdeParams p) {
+    TileStream<M::NC> ts;
+    ts.init(p.prob.records, p.prob.n_points, p.tile_points);
+
+    const int64_t C = p.st.n_chains;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane_sub<G>(lane);
+    const int64_t group = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 / G) + lane_chain<G>(lane);
+    const unsigned group_mask = lane_group_mask<G>(lane);
+    const bool injected = p.streams.normals != nullptr;
+
+    int64_t c[Q];
+    bool live[Q];
+    double x[Q][D], gcur[Q][D], lp[Q], mean_r[Q];
+    int32_t status[Q], n_eval[Q], n_rej[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        c[q] = group + (int64_t)q * p.n_groups;
+        live[q] = c[q] < C;
+        if (!live[q]) c[q] = C - 1;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            x[q][i] = p.st.x[i * C + c[q]];
+            gcur[q][i] = p.st.P[i * C + c[q]];
+        }
+        lp[q] = p.st.lp[c[q]];
+        mean_r[q] = p.st.mean_r[c[q]];
+        status[q] = p.st.status[c[q]];
+        n_eval[q] = 0;
+        n_rej[q] = 0;
+    }
+    const double eps = p.h;
+
+    // gradient (and log-posterior) at xn for all chains of the thread
+    auto gradient = [&](const double (&xn)[Q][D], double (&g)[Q][D], double (&lpn)[Q]) {
+        if (!p.fd_gradient) {
+            grad_log_like<M, D, G, Q, STREAM>(xn, p.prob, ts, p.tile_points, sub, group_mask, g, lpn);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) n_eval[q] += 0;       // compute_grad_log_value does not call compute_log_value
+        } else {
+            bool want[Q];
+            double fp[Q], xp[Q][D];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) want[q] = true;
+            log_posterior<M, D, G, Q, STREAM>(xn, want, p.prob, ts, p.tile_points, sub, group_mask, lpn);
+#pragma unroll 1
+            for (int i = 0; i < D; ++i) {
+                double delta[Q];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    double xv = 0.0;
+#pragma unroll
+                    for (int j = 0; j < D; ++j) {
+                        xp[q][j] = xn[q][j];
+                        if (j == i) xv = xn[q][j];
+                    }
+                    delta[q] = __dmul_rn(xv, 1e-10);
+                    if (delta[q] == 0.0) delta[q] = 1e-10;
+#pragma unroll
+                    for (int j = 0; j < D; ++j)
+                        if (j == i) xp[q][j] = __dadd_rn(xv, delta[q]);
+                }
+                log_posterior<M, D, G, Q, STREAM>(xp, want, p.prob, ts, p.tile_points, sub, group_mask, fp);
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const double gi = (fp[q] - lpn[q]) / delta[q];
+#pragma unroll
+                    for (int j = 0; j < D; ++j)
+                        if (j == i) g[q][j] = gi;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) n_eval[q] += D + 1;
+        }
+    };
+
+    int32_t to_update = (int32_t)(p.update_it - p.it0 % p.update_it);
+    int32_t to_keep = (int32_t)(p.thin - p.it0 % p.thin);
+    int64_t row = 0;
+    for (int64_t s = 0; s < p.n_steps; ++s) {
+        const int64_t it = p.it0 + s + 1;
+        const bool upd = (--to_update == 0);
+        if (upd) to_update = (int32_t)p.update_it;
+        const bool keep = (--to_keep == 0);
+        if (keep) to_keep = (int32_t)p.thin;
+        double xn[Q][D], mom[Q][D], Kcur[Q], u[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int64_t cq = c[q];
+            double *const gC = p.Cmat + cq;
+            double *const gIL = p.st.R + cq;
+            adapt_preconditioner<D>(p, it, upd, x[q], live[q], gC, gIL, p.st.V + cq, p.st.xav + cq, C, status[q]);
+            double z[D];
+            if (injected) {
+                if (!draw_injected<D, true>(p.streams, cq, live[q] && sub == 0, group_mask, z, u[q])) status[q] |= ST_STREAM_EXHAUSTED;
+            } else {
+                draw_philox<D>(p.seed, p.chain_offset + (uint64_t)cq, (uint64_t)it, 0u, z, u[q]);
+            }
+            double pc[D], CP[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {                  // p = z @ inv_L_c^T, inv_L_c upper triangular (:830)
+                double acc = 0.0;
+#pragma unroll
+                for (int j = i; j < D; ++j) acc = __dadd_rn(acc, __dmul_rn(z[j], gIL[(int64_t)tri_idx(D, i, j) * C]));
+                pc[i] = acc;
+            }
+            symv_global<D>(gC, C, pc, CP);
+            double k = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) k = __dadd_rn(k, __dmul_rn(CP[i], pc[i]));
+            Kcur[q] = k / 2.0;                             // :862-866
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                mom[q][i] = __dadd_rn(pc[i], -(__dmul_rn(eps, -gcur[q][i]) / 2.0));      // :836
+                xn[q][i] = x[q][i];
+            }
+        }
+        double gnew[Q][D], lpn[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            lpn[q] = lp[q];
+#pragma unroll
+            for (int i = 0; i < D; ++i) gnew[q][i] = gcur[q][i];
+        }
+#pragma unroll 1
+        for (int l = 0; l < p.hmc_steps; ++l) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                double CP[D];
+                symv_global<D>(p.Cmat + c[q], C, mom[q], CP);
+#pragma unroll
+                for (int i = 0; i < D; ++i) xn[q][i] = __dadd_rn(xn[q][i], __dmul_rn(eps, CP[i]));            // :843
+            }
+            gradient(xn, gnew, lpn);
+            if (l != p.hmc_steps - 1) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q)
+#pragma unroll
+                    for (int i = 0; i < D; ++i) mom[q][i] = __dadd_rn(mom[q][i], -__dmul_rn(eps, -gnew[q][i]));  // :848
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int64_t cq = c[q];
+            double pf[D], CP[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) pf[i] = -__dadd_rn(mom[q][i], -(__dmul_rn(eps, -gnew[q][i]) / 2.0));     // :852, :855
+            symv_global<D>(p.Cmat + cq, C, pf, CP);
+            double k = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) k = __dadd_rn(k, __dmul_rn(CP[i], pf[i]));
+            const double Knew = k / 2.0;
+            n_eval[q] += 1;                                // distr_fun(new_val) (:868)
+            double r = exp(__dadd_rn(__dadd_rn(__dadd_rn(-lp[q], lpn[q]), Kcur[q]), -Knew));                    // :879
+            if (r != r) {
+                status[q] |= ST_NAN_RATIO;
+                r = 0.0;
+            }
+            const double alpha = py_min1(r);
+            if (u[q] < alpha) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    x[q][i] = xn[q][i];
+                    gcur[q][i] = gnew[q][i];
+                }
+                lp[q] = lpn[q];
+            } else {
+                n_rej[q] += 1;
+            }
+            mean_r[q] += alpha;                            // :170
+            if (live[q] && sub == 0) {
+                if (p.out.trace_lp1) p.out.trace_lp1[s * C + cq] = lpn[q];
+                if (keep) {
+                    const int64_t wc = p.st.wcount[cq] + 1;
+                    p.st.wcount[cq] = wc;
+                    const double inv_n = 1.0 / (double)wc;
+                    double dl[D], mu[D];
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+                        const double m = p.st.wmean[i * C + cq];
+                        dl[i] = x[q][i] - m;
+                        mu[i] = fma(dl[i], inv_n, m);
+                        p.st.wmean[i * C + cq] = mu[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < D; ++i)
+#pragma unroll
+                        for (int j = i; j < D; ++j) {
+                            double *w2 = &p.st.wM2[tri_idx(D, i, j) * C + cq];
+                            *w2 = fma(dl[i], x[q][j] - mu[j], *w2);
+                        }
+                    if (p.out.samples && cq < p.out.n_sample_chains) {
+#pragma unroll
+                        for (int i = 0; i < D; ++i) p.out.samples[(row * D + i) * p.out.n_sample_chains + cq] = x[q][i];
+                    }
+                    if (p.out.lp_kept) p.out.lp_kept[row * C + cq] = lp[q];
+                }
+            }
+        }
+        if (keep) row += 1;
+    }
+
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        if (live[q] && sub == 0) {
+            const int64_t cq = c[q];
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                p.st.x[i * C + cq] = x[q][i];
+                p.st.P[i * C + cq] = gcur[q][i];
+            }
+            p.st.lp[cq] = lp[q];
+            p.st.mean_r[cq] = mean_r[q];
+            p.st.n_rej[cq] += n_rej[q];
+            p.st.n_eval[cq] += n_eval[q];
+            p.st.status[cq] = status[q];
+        }
+    }
+}
+
+// gradient of the log-posterior at S points (initial stored gradient of HMC, mha.py:815): G[i][s]
+template <class M, int D>
+__global__ void __launch_bounds__(256) eval_grad_kernel(const __grid_constant__ ProblemDev prob, const double *X /*[d][S]*/, int64_t S,
+                                                        double *G_out /*[d][S]*/, int tile_points, int fd_gradient) {
+    TileStream<M::NC> ts;
+    ts.init(prob.records, prob.n_points, tile_points);
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool livet = t < S;
+    if (!livet) t = S - 1;
+    double x[1][D], g[1][D], lp[1];
+#pragma unroll
+    for (int i = 0; i < D; ++i) x[0][i] = X[i * S + t];
+    const unsigned mask = 1u << (threadIdx.x & 31);
+    if (!fd_gradient) {
+        grad_log_like<M, D, 1, 1, true>(x, prob, ts, tile_points, 0, mask, g, lp);
+    } else {
+        const bool want[1] = {true};
+        double fp[1], xp[1][D];
+        log_posterior<M, D, 1, 1, true>(x, want, prob, ts, tile_points, 0, mask, lp);
+        for (int i = 0; i < D; ++i) {
+            double xv = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                xp[0][j] = x[0][j];
+                if (j == i) xv = x[0][j];
+            }
+            double delta = __dmul_rn(xv, 1e-10);
+            if (delta == 0.0) delta = 1e-10;
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                if (j == i) xp[0][j] = __dadd_rn(xv, delta);
+            log_posterior<M, D, 1, 1, true>(xp, want, prob, ts, tile_points, 0, mask, fp);
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                if (j == i) g[0][j] = (fp[0] - lp[0]) / delta;
+        }
+    }
+    if (livet) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) G_out[i * S + t] = g[0][i];
     }
 }
 

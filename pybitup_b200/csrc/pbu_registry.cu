@@ -59,3 +59,20 @@ const pbu::IsdeKernelEntry *pbu_isde_kernels(int *n) {
     *n = (int)all.size();
     return all.data();
 }
+
+const pbu::IsdeKernelEntry *pbu_hmc_kernels(int *n) {
+    static const std::vector<pbu::IsdeKernelEntry> all = [] {
+        std::vector<pbu::IsdeKernelEntry> v;
+        append(v, pbu_hmc_slice_linear_a);
+        append(v, pbu_hmc_slice_linear_b);
+        append(v, pbu_hmc_slice_linear_c);
+        append(v, pbu_hmc_slice_linear_d);
+        append(v, pbu_hmc_slice_poly_a);
+        append(v, pbu_hmc_slice_poly_b);
+        append(v, pbu_hmc_slice_arrhenius);
+        append(v, pbu_hmc_slice_heat);
+        return v;
+    }();
+    *n = (int)all.size();
+    return all.data();
+}

@@ -20,6 +20,7 @@ struct EvalKernelEntry {
     int ops, wf;              // FP64 instructions / shared-memory wavefronts per point (launch planning)
     const void *eval_lp;      // __global__ void (*)(const ProblemDev, const double*, int64_t, double*)
     const void *eval_model;   // same signature
+    const void *eval_grad;    // __global__ void (*)(const ProblemDev, const double*, int64_t, double*, int, int)
 };
 
 }  // namespace pbu
@@ -27,12 +28,14 @@ struct EvalKernelEntry {
 const pbu::MhKernelEntry *pbu_mh_kernels(int *n);
 const pbu::EvalKernelEntry *pbu_eval_kernels(int *n);
 const pbu::IsdeKernelEntry *pbu_isde_kernels(int *n);
+const pbu::IsdeKernelEntry *pbu_hmc_kernels(int *n);
 
 // slices
 #define PBU_DECLARE_SLICE(name)                                     \
     const pbu::MhKernelEntry *pbu_mh_slice_##name(int *n);          \
     const pbu::EvalKernelEntry *pbu_eval_slice_##name(int *n);      \
-    const pbu::IsdeKernelEntry *pbu_isde_slice_##name(int *n);
+    const pbu::IsdeKernelEntry *pbu_isde_slice_##name(int *n);      \
+    const pbu::IsdeKernelEntry *pbu_hmc_slice_##name(int *n);
 PBU_DECLARE_SLICE(linear_a)
 PBU_DECLARE_SLICE(linear_b)
 PBU_DECLARE_SLICE(linear_c)

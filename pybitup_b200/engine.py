@@ -112,6 +112,8 @@ class SamplerConfig:
     tile_points: int = 0
     seed: int = 0
     chain_offset: int = 0
+    hmc_step_size: float = 0.0
+    hmc_num_steps: int = 0
 
     def _c_struct(self):
         s = capi.pbu_sampler_cfg()
@@ -127,6 +129,7 @@ class SamplerConfig:
         s.chains_per_thread = int(self.chains_per_thread)
         s.tile_points = int(self.tile_points)
         s.seed, s.chain_offset = int(self.seed) & (2 ** 64 - 1), int(self.chain_offset)
+        s.hmc_step_size, s.hmc_num_steps = float(self.hmc_step_size), int(self.hmc_num_steps)
         return s
 
 

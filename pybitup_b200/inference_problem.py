@@ -23,10 +23,8 @@ class Sampler:
         self.opt_arg = {}
         av_algo = {'RWMH': "random-walk Metropolis-Hastings", 'AMH': "adaptive Metropolis-Hastings",
                    'DR': "delayed-rejection Metropolis-Hastings", 'DRAM': "delayed-rejection adative Metropolis-Hastings",
-                   'ISDE': "Ito-SDE"}
+                   'HMC': "Hamiltonian Monte Carlo", 'ISDE': "Ito-SDE"}
         self.algo_name = self.algo['name']
-        if self.algo_name == "HMC":
-            raise ValueError('Algorithm "HMC" is not available on the device path yet.')
         if self.algo_name not in av_algo:
             raise ValueError('Algorithm "{}" unknown.'.format(self.algo_name))
         print("Running {} algorithm on the CUDA engine.".format(av_algo[self.algo_name]))
@@ -64,6 +62,9 @@ class Sampler:
             run = mha.DelayedRejectionAdaptiveMetropolisHastings(self.IO_fileID, self.n_iterations, sample_init, self.proposal_cov,
                                                                  self.prob_dist, int(a['DRAM']['starting_it']), int(a['DRAM']['updating_it']),
                                                                  a['DRAM']['eps_v'], a['DRAM']['gamma'], self.opt_arg)
+        elif n == "HMC":
+            run = mha.HamiltonianMonteCarlo(self.IO_fileID, self.n_iterations, sample_init, self.prob_dist, a['covariance'], a['gradient'],
+                                            a['HMC']['step_size'], a['HMC']['num_steps'], self.opt_arg)
         else:
             run = mha.ito_SDE(self.IO_fileID, self.n_iterations, sample_init, self.prob_dist, a['covariance'], a['gradient'],
                               a['ISDE']['h'], a['ISDE']['f0'], self.opt_arg)

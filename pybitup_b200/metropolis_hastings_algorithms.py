@@ -154,7 +154,7 @@ class _DeviceSampler:
         save_all = str(self.opt_arg.get("save_all_chains", "no")) == "yes"
         kept0, kept_all, aux_rows = [x0[0].copy()], [], []
         done = 0
-        isde = self.algo_name == "ISDE"
+        isde = self.algo_name == "ISDE"                 # aux_variables.csv rows (the HMC file is opened but left empty)
         while done < self.nIterations:
             n = min(self._launch_len(), self.nIterations - done)
             res = eng.run(n, thin=1, keep_samples=True, sample_chains=None if save_all else 1, keep_aux=isde)
@@ -277,14 +277,11 @@ class DelayedRejectionAdaptiveMetropolisHastings(_DeviceSampler):
                              am_welford=str(self.opt_arg.get("am_welford", "no")) == "yes")
 
 
-class ito_SDE(_DeviceSampler):
-    """Ito-SDE sampler (mha.py:886-1040) with the GradientBasedMCMC preconditioner options the device supports:
-    covariance.value in {"Identity", "Matrix"} (:661-664, :689-693); Hessian-based values are not lowered."""
-    algo_name = "ISDE"
+class _GradientSampler(_DeviceSampler):
+    """Shared by ito_SDE and HamiltonianMonteCarlo: the GradientBasedMCMC preconditioner options (mha.py:621-731)."""
 
-    def __init__(self, IO_fileID, nIterations, param_init, prob_distr, C_matrix, gradient, h, f0, opt_arg):
-        self._setup(IO_fileID, nIterations, param_init, None, prob_distr, opt_arg)
-        self.C_matrix, self.gradient, self.h, self.f0 = dict(C_matrix), gradient, float(h), float(f0)
+    def _setup_gradient(self, C_matrix, gradient):
+        self.C_matrix, self.gradient = dict(C_matrix), gradient
         if gradient not in ("Numerical", "Analytical"):
             raise ValueError('Unknown gradient type "{}" for estimating gradients.'.format(gradient))     # :730-731
         value = self.C_matrix.get("value", "Identity")
@@ -309,6 +306,37 @@ class ito_SDE(_DeviceSampler):
                                                 compute_all_element=(value == "Hessian"))
             self.V = np.linalg.inv(self.hess_mat)
         return self.V
+
+
+class HamiltonianMonteCarlo(_GradientSampler):
+    """Hamiltonian Monte Carlo (mha.py:779-884): leapfrog trajectories of num_steps steps of size step_size."""
+    algo_name = "HMC"
+
+    def __init__(self, IO_fileID, nIterations, param_init, prob_distr, C_matrix, gradient, step_size, num_steps, opt_arg):
+        self._setup(IO_fileID, nIterations, param_init, None, prob_distr, opt_arg)
+        self._setup_gradient(C_matrix, gradient)
+        self.epsilon, self.L = float(step_size), int(num_steps)
+
+    def _config(self):
+        return SamplerConfig(algo="HMC", hmc_step_size=self.epsilon, hmc_num_steps=self.L, isde_gradient=self.gradient,
+                             adapt_start=self.starting_it, adapt_update=self.update_it, adapt_end=self.end_it)
+
+    def _finish(self):
+        st = self.engine.isde_state()
+        self.distr_grad_log_like_current_val, self.C_approx = st["P"][0], st["C"][0]
+        _DeviceSampler._finish(self)
+        self.inv_L_c = self.R
+
+
+class ito_SDE(_GradientSampler):
+    """Ito-SDE sampler (mha.py:886-1040) with the GradientBasedMCMC preconditioner options the device supports:
+    covariance.value in {"Identity", "Matrix", "Hessian", "Hessian_diag"}."""
+    algo_name = "ISDE"
+
+    def __init__(self, IO_fileID, nIterations, param_init, prob_distr, C_matrix, gradient, h, f0, opt_arg):
+        self._setup(IO_fileID, nIterations, param_init, None, prob_distr, opt_arg)
+        self._setup_gradient(C_matrix, gradient)
+        self.h, self.f0 = float(h), float(f0)
 
     def _config(self):
         return SamplerConfig(algo="ISDE", isde_h=self.h, isde_f0=self.f0, isde_gradient=self.gradient,

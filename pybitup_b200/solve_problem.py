@@ -85,7 +85,7 @@ class Sampling(SolveProblem):
             self.algo_inputs = self.user_inputs["Sampling"].get('Algorithm')
             if self.algo_inputs.get("estimate_sigma") == "yes":
                 new_file_list['estimated_sigma'] = "estimated_sigma.csv"
-            if self.algo_inputs.get("ISDE") is not None:
+            if self.algo_inputs.get("ISDE") is not None or self.algo_inputs.get("HMC") is not None:
                 new_file_list['aux_variables'] = "aux_variables.csv"
             if self.algo_inputs.get("estimate_max_distr") == "yes":
                 new_file_list['estimate_arg_max_val_distr'] = "arg_MAP_estimation.csv"

@@ -112,3 +112,57 @@ def test_isde_many_chains_vs_oracle(builder, kwargs):
     finally:
         orc.chol_upper, orc.inv_upper = orc_chol, orc_inv
     eng.close()
+
+
+@pytest.mark.parametrize("lanes", [1, 4])
+def test_hmc_golden(lanes):
+    """Hamiltonian Monte Carlo (mha.py:779-884) against the recorded reference run with the same draws."""
+    from pybitup_b200.engine import ChainEngine, ProblemSpec, SamplerConfig
+    g = H.load_golden("regression_hmc")
+    a = g["algo"]
+    T, C = int(a["n_iterations"]), 3
+    cfg = SamplerConfig(algo="HMC", hmc_step_size=float(a["HMC"]["step_size"]), hmc_num_steps=int(a["HMC"]["num_steps"]),
+                        isde_gradient=a["gradient"], adapt_start=int(a["covariance"]["starting_it"]),
+                        adapt_update=int(a["covariance"]["update_it"]), lanes_per_chain=lanes)
+    with ChainEngine(ProblemSpec.from_dict(H.problem_dict(g)), cfg, C) as eng:
+        eng.init_chains(np.tile(g["x0"], (C, 1)), None)
+        eng.set_streams(np.tile(g["normals"], (C, 1)), np.tile(g["uniforms"], (C, 1)))
+        res = eng.run(T, thin=1)
+        eng.synchronize()
+        xs = res.samples.cpu().numpy()
+        ctr = eng.counters()
+    for c in range(C):
+        chain = np.concatenate([g["x0"][None, :], xs[:, :, c]], axis=0)
+        assert np.array_equal(np.any(chain[1:] != chain[:-1], axis=1), np.any(g["chain"][1:] != g["chain"][:-1], axis=1))
+        assert H.rel_err(chain, g["chain"]) < 1e-9
+        assert ctr["n_rejected"][c] == int(g["n_rejected"]) and ctr["n_eval"][c] == len(g["eval_lp"])
+        assert H.rel_err(ctr["mean_r"][c], float(g["mean_r"])) < 1e-9
+
+
+def test_hmc_many_chains_vs_oracle_with_adaptation_and_fd():
+    from pybitup_b200 import synthetic
+    from pybitup_b200.engine import ChainEngine, ProblemSpec, SamplerConfig
+    p = synthetic.cubic_problem(n_points=150)
+    prob = H.oracle_problem(p)
+    C, T, d = 24, 80, 4
+    rng = np.random.default_rng(21)
+    x0 = synthetic.chain_starts(p["x0"], C, jitter=1e-3, seed=4)
+    nz, un = rng.standard_normal((C, T * d)), rng.random((C, T))
+    C0 = np.diag([1e-5, 5e-5, 1e-4, 1e-4])
+    cfg = SamplerConfig(algo="HMC", hmc_step_size=0.3, hmc_num_steps=3, isde_gradient="Analytical", adapt_start=30, adapt_update=10,
+                        adapt_end=60)
+    with ChainEngine(ProblemSpec.from_dict(p), cfg, C) as eng:
+        eng.init_chains(x0, C0)
+        eng.set_streams(nz, un)
+        res = eng.run(T, thin=1)
+        eng.synchronize()
+        xs = res.samples.cpu().numpy()
+    orc_chol, orc_inv = orc.chol_upper, orc.inv_upper
+    orc.chol_upper, orc.inv_upper = orc.chol_upper_plain, orc.inv_upper_plain
+    try:
+        for c in range(0, C, 5):
+            out = orc.run_hmc(prob, x0[c], T, orc.Streams(nz[c], un[c]), 0.3, 3, gradient="Analytical", C0=C0, starting_it=30,
+                              update_it=10, end_it=60)
+            assert H.rel_err(xs[:, :, c], out["chain"][1:]) < 1e-6, c
+    finally:
+        orc.chol_upper, orc.inv_upper = orc_chol, orc_inv
