@@ -50,8 +50,10 @@ typedef enum {
     PBU_MODEL_POLY = 1,      /* Horner polynomial in x, theta = coefficients; design = x (N x 1) */
     PBU_MODEL_ARRHENIUS = 2, /* one-reaction pyrolysis ODE, RK4 over a temperature ramp;
                                 theta = (log10 A, E, n, F); consts = {T0, dT, beta}; no design    */
-    PBU_MODEL_HEAT = 3       /* the reference's test model (test/test_pce/heat_conduction.py:27-41);
+    PBU_MODEL_HEAT = 3,      /* the reference's test model (test/test_pce/heat_conduction.py:27-41);
                                 theta = (a,b,k,T_amb,phi,h); design = x; consts = {L}             */
+    PBU_MODEL_SOIZE = 4      /* not a forward model: the 2-D test density SoizePDF (distributions.py:483-506)
+                                written as two pseudo-residuals; design = selector column (N = 2)  */
 } pbu_model_id;
 
 /* Samplers (inference_problem.py:23-33, :79-107). */
@@ -82,6 +84,10 @@ typedef struct {
     const double *ub;         /* host [d] Uniform.ub (distributions.py:277)                       */
     double gamma;             /* Likelihood.gamma (bayesian_inference.py:407)                     */
     double consts[8];         /* model constants, see pbu_model_id                                */
+    double log_const;         /* used when has_log_const != 0: constant added to -J/2 INSTEAD of the log-prior
+                                 constant (sampling an analytic density, solve_problem.py:134-164)  */
+    int32_t has_log_const;
+    int32_t pad0;
 } pbu_problem;
 
 /* Algorithm block: inference_problem.py:37-107 (JSON keys in SURVEY.md 9.2). */

@@ -22,7 +22,7 @@ PBU_ERR_CUDA = -3
 PBU_ERR_NOT_PD = -4
 PBU_ERR_STREAM_EXHAUSTED = -5
 
-MODEL_IDS = {"linear": 0, "poly": 1, "arrhenius": 2, "heat": 3}
+MODEL_IDS = {"linear": 0, "poly": 1, "arrhenius": 2, "heat": 3, "soize": 4}
 ALGO_IDS = {"RWMH": 0, "AMH": 1, "DR": 2, "DRAM": 3, "ISDE": 4, "HMC": 5}
 
 _dp = C.POINTER(C.c_double)
@@ -34,7 +34,8 @@ class pbu_problem(C.Structure):
     _fields_ = [("model", C.c_int32), ("n_param", C.c_int32), ("n_unc", C.c_int32), ("n_points", C.c_int32),
                 ("n_runs", C.c_int32), ("n_design_cols", C.c_int32),
                 ("theta_nom", _dp), ("unc_idx", _ip), ("design", _dp), ("y", _dp), ("std_y", _dp),
-                ("lb", _dp), ("ub", _dp), ("gamma", C.c_double), ("consts", C.c_double * 8)]
+                ("lb", _dp), ("ub", _dp), ("gamma", C.c_double), ("consts", C.c_double * 8),
+                ("log_const", C.c_double), ("has_log_const", C.c_int32), ("pad0", C.c_int32)]
 
 
 class pbu_sampler_cfg(C.Structure):

@@ -290,6 +290,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
         case PBU_MODEL_POLY: nd = 1; break;
         case PBU_MODEL_ARRHENIUS: nd = 2; break;
         case PBU_MODEL_HEAT: nd = 1; break;
+        case PBU_MODEL_SOIZE: nd = 1; break;
         default: return fail(PBU_ERR_INVALID, "unknown model id %d", pr->model);
     }
     if (pr->model != PBU_MODEL_ARRHENIUS && (pr->n_design_cols != nd || !pr->design))
@@ -369,7 +370,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
         pd.ub[i] = pr->ub[i];
         lpc += std::log(1.0 / std::fabs(pr->ub[i] - pr->lb[i]));      // distributions.py:278, :475
     }
-    pd.log_prior_const = lpc;
+    pd.log_prior_const = pr->has_log_const ? pr->log_const : lpc;
     for (int i = 0; i < pr->n_param; ++i) pd.theta_nom[i] = pr->theta_nom[i];
     for (int i = 0; i < 8; ++i) pd.consts[i] = pr->consts[i];
 

@@ -226,4 +226,38 @@ struct HeatModel {
     __device__ __forceinline__ static void grad_acc(const Ctx &, const double (&)[NC], double, double (&)[6]) {}
 };
 
+// ------------------------------------------------------------------------------------------------
+// SOIZE: the reference's 2-D sampler test density (SoizePDF, distributions.py:483-506),
+//   log p(X) = -15 (X0^3 - X1)^2 - (X1 - 0.3)^4,
+// as -J/2 with two pseudo-residuals t_0 = sqrt(30) (X0^3 - X1), t_1 = sqrt(2) (X1 - 0.3)^2.
+//   likelihood record [selector | 1 | 0 | pad];  raw record [selector | pad];  value() returns the residual itself
+struct SoizeModel {
+    static constexpr int NPARAM = 2;
+    static constexpr int NC = 4;
+    static constexpr int NCR = 2;
+    static constexpr bool SEQUENTIAL = false;
+    static constexpr bool HAS_GRAD = false;
+    static constexpr int ID = PBU_MODEL_SOIZE;
+    static constexpr int UNROLL = 1;
+    static constexpr int OPS = 8;
+    static constexpr int WF = 3;
+    struct Ctx {
+        double t0, t1;
+    };
+    struct Seq {};
+    __device__ __forceinline__ static void begin(Ctx &c, const double (&th)[2], const ProblemDev &) {
+        const double a = th[0] * th[0] * th[0] - th[1], b = th[1] - 0.3;
+        c.t0 = 5.477225575051661 * a;          // sqrt(30)
+        c.t1 = 1.4142135623730951 * (b * b);   // sqrt(2)
+    }
+    __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const ProblemDev &) {}
+    __device__ __forceinline__ static double value(const Ctx &c, Seq &, const double *raw) { return (raw[0] == 0.0) ? c.t0 : c.t1; }
+    template <int U>
+    __device__ __forceinline__ static void resid_batch(const Ctx &c, Seq &s, const double (&rec)[U][NC], double (&t)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) t[u] = value(c, s, rec[u]);
+    }
+    __device__ __forceinline__ static void grad_acc(const Ctx &, const double (&)[NC], double, double (&)[2]) {}
+};
+
 }  // namespace pbu

@@ -20,6 +20,7 @@ const pbu::MhKernelEntry *pbu_mh_kernels(int *n) {
         append(v, pbu_mh_slice_poly_b);
         append(v, pbu_mh_slice_arrhenius);
         append(v, pbu_mh_slice_heat);
+        append(v, pbu_mh_slice_soize);
         return v;
     }();
     *n = (int)all.size();
@@ -37,6 +38,7 @@ const pbu::EvalKernelEntry *pbu_eval_kernels(int *n) {
         append(v, pbu_eval_slice_poly_b);
         append(v, pbu_eval_slice_arrhenius);
         append(v, pbu_eval_slice_heat);
+        append(v, pbu_eval_slice_soize);
         return v;
     }();
     *n = (int)all.size();
@@ -54,6 +56,7 @@ const pbu::IsdeKernelEntry *pbu_isde_kernels(int *n) {
         append(v, pbu_isde_slice_poly_b);
         append(v, pbu_isde_slice_arrhenius);
         append(v, pbu_isde_slice_heat);
+        append(v, pbu_isde_slice_soize);
         return v;
     }();
     *n = (int)all.size();
@@ -71,6 +74,7 @@ const pbu::IsdeKernelEntry *pbu_hmc_kernels(int *n) {
         append(v, pbu_hmc_slice_poly_b);
         append(v, pbu_hmc_slice_arrhenius);
         append(v, pbu_hmc_slice_heat);
+        append(v, pbu_hmc_slice_soize);
         return v;
     }();
     *n = (int)all.size();

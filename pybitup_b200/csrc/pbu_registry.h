@@ -44,3 +44,4 @@ PBU_DECLARE_SLICE(poly_a)
 PBU_DECLARE_SLICE(poly_b)
 PBU_DECLARE_SLICE(arrhenius)
 PBU_DECLARE_SLICE(heat)
+PBU_DECLARE_SLICE(soize)

@@ -28,13 +28,14 @@ class ProblemSpec:
     ub: np.ndarray                   # f64[d]
     gamma: float = 1.0
     design: dict = field(default_factory=dict)
+    log_const: float = None          # analytic densities: constant that replaces the log-prior constant
 
     @classmethod
     def from_dict(cls, p):
         return cls(model=str(p["model"]), theta_nom=_f64(p["theta_nom"]),
                    unc_idx=np.ascontiguousarray(np.asarray(p["unc_idx"], dtype=np.int32)),
                    y=_f64(np.atleast_2d(p["y"])), std_y=_f64(p["std_y"]), lb=_f64(p["lb"]), ub=_f64(p["ub"]),
-                   gamma=float(p.get("gamma", 1.0)), design=dict(p.get("design", {})))
+                   gamma=float(p.get("gamma", 1.0)), design=dict(p.get("design", {})), log_const=p.get("log_const"))
 
     @property
     def d(self):
@@ -65,6 +66,9 @@ class ProblemSpec:
             if design.shape != (N, len(theta)):
                 raise ValueError("linear model: Phi must be [N, P] = [%d, %d], got %s" % (N, len(theta), design.shape))
             ncols = design.shape[1]
+        elif self.model == "soize":
+            design = np.array([[0.0], [1.0]])
+            ncols = 1
         elif self.model in ("poly", "heat"):
             design = _f64(self.design["x"]).reshape(N, 1)
             ncols = 1
@@ -88,6 +92,8 @@ class ProblemSpec:
         s.y, s.std_y, s.lb, s.ub = capi.dptr(y), capi.dptr(std), capi.dptr(lb), capi.dptr(ub)
         s.gamma = float(self.gamma)
         s.consts = (C.c_double * 8)(*consts)
+        s.has_log_const = 0 if self.log_const is None else 1
+        s.log_const = 0.0 if self.log_const is None else float(self.log_const)
         return s, keep
 
 

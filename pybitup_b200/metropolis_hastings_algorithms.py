@@ -127,7 +127,8 @@ class _DeviceSampler:
         if len(rows) == 0:
             return
         np.savetxt(self.IO_fileID['MChains_reparam'], rows, fmt="%f", delimiter=",")
-        back = np.array([self.prob_distr.model.parametrization_backward(r) for r in rows])
+        model = getattr(self.prob_distr, "model", None)       # analytic densities have no model / parametrisation
+        back = rows if model is None else np.array([model.parametrization_backward(r) for r in rows])
         np.savetxt(self.IO_fileID['MChains'], back, fmt="%f", delimiter=",")
 
     def _launch_len(self):
@@ -170,7 +171,7 @@ class _DeviceSampler:
             # model evaluations of the current (last accepted) state every save_eval_freq iterations (:366-368)
             its = np.arange(done + 1, done + n + 1)
             sel = its[its % self.save_eval_freq == 0]
-            if sel.size and self.save_eval_freq <= self.nIterations:
+            if sel.size and self.save_eval_freq <= self.nIterations and hasattr(self.prob_distr, "likelihood"):
                 ev = eng.model_eval(rows[sel - done - 1])
                 for k, it in enumerate(sel):
                     self.prob_distr.save_value(self.IO_util, int(it), ev[k])

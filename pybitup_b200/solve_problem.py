@@ -125,7 +125,7 @@ class Sampling(SolveProblem):
             raise ValueError('Ask for sampling distribution but no Sampling inputs were provided')
         S = self.user_inputs["Sampling"]
         if S.get("Distribution") is not None:
-            raise NotImplementedError("Sampling.Distribution (analytic densities) is outside the device hot path")
+            return self._sample_distribution(S)
         if S.get("BayesianPosterior") is None:
             raise ValueError('No samling distribution provided or invalid name.')
         self.IO_util['path']['fun_eval_folder'].mkdir(exist_ok=True)
@@ -162,6 +162,25 @@ class Sampling(SolveProblem):
             self.sampler = sampler.sample(unpar_init_val)
         if S.get('ComputeAnalyticalDistribution') is not None:
             raise NotImplementedError("ComputeAnalyticalDistribution (grid evaluation for plots) is outside the device hot path")
+        return getattr(self, "sampler", None)
+
+
+    def _sample_distribution(self, S):
+        """Sampling.Distribution: sample a known density (solve_problem.py:134-164).  Unlike the reference, which
+        crashes at the end of such a run (its covariance step reads a chain file that this branch never writes,
+        SURVEY.md 8f-2), both chain files are written."""
+        D = S['Distribution']
+        distr_param = []
+        for h in D['hyperparameters']:
+            distr_param.append(pd.read_csv(h, header=None).values if isinstance(h, str) else h)
+        if isinstance(D["init_val"], str):
+            unpar_init_val = np.transpose(pd.read_csv(D["init_val"], header=None).values)[0].astype(np.float64)
+        else:
+            unpar_init_val = np.array(D["init_val"], dtype=np.float64)
+        self.sample_dist = distributions.set_probability_dist([D['name']], distr_param, D['n_rand_var'])
+        if S.get('Algorithm') is not None:
+            sampler = inference_problem.Sampler(self.IO_util, self.sample_dist, S["Algorithm"])
+            self.sampler = sampler.sample(unpar_init_val)
         return getattr(self, "sampler", None)
 
 

@@ -151,3 +151,91 @@ def test_isde_from_json_on_cubic(tmp_path, monkeypatch):
     st = run.statistics
     assert np.all(np.abs(st["mean"] - mean) < 4 * np.sqrt(np.diag(cov)) / np.sqrt(32 * 20))
     assert np.all(np.abs(np.diag(st["cov"]) / np.diag(cov) - 1.0) < 0.35)
+
+
+@pytest.mark.parametrize("name", ["Gaussian", "SoizePDF"])
+def test_sampling_a_known_distribution(tmp_path, monkeypatch, name):
+    """Sampling.Distribution (solve_problem.py:134-164): the reference's sampler test bed, on the device."""
+    from pybitup_b200.solve_problem import Sampling
+    from pybitup_b200 import distributions
+    monkeypatch.chdir(tmp_path)
+    mean, cov = [1.0, -2.0, 0.5], [[2.0, 0.3, 0.1], [0.3, 1.0, 0.2], [0.1, 0.2, 0.5]]
+    if name == "Gaussian":
+        dist = {"name": "Gaussian", "hyperparameters": [[mean], cov], "n_rand_var": 3, "init_val": mean}
+        prop = (np.array(cov) * 0.8).tolist()
+    else:
+        dist = {"name": "SoizePDF", "hyperparameters": [], "n_rand_var": 2, "init_val": [0.0, 0.3]}
+        prop = [[0.2, 0.0], [0.0, 0.2]]
+    T = 3000
+    cfg = {"Sampling": {"Distribution": dist,
+                        "Algorithm": {"name": "AMH", "AMH": {"starting_it": 100, "updating_it": 50, "eps_v": 1e-8}, "n_iterations": T,
+                                      "n_chains": 256, "seed": 3, "proposal": {"covariance": {"type": "full", "value": prop}}}}}
+    with open("dist.json", "w") as f:
+        json.dump(cfg, f)
+    job = Sampling("dist.json")
+    run = job.sample()
+    job.close()
+    d = len(dist["init_val"])
+    assert pd.read_csv("output/mcmc_chain.csv", header=None).values.shape == (T + 1, d)
+    st = run.statistics
+    if name == "Gaussian":
+        se = np.sqrt(np.diag(cov) / (256 * T / 40.0))
+        assert np.all(np.abs(st["mean"] - mean) < 5 * se)
+        assert np.all(np.abs(st["cov"] - np.array(cov)) < 0.1 * np.sqrt(np.outer(np.diag(cov), np.diag(cov))))
+        # log-density on the device vs scipy (what the reference's Gaussian.compute_log_value returns, :234-236)
+        import scipy.stats
+        from pybitup_b200.engine import ChainEngine, SamplerConfig
+        g = distributions.set_probability_dist(["Gaussian"], [[mean], cov], 3)
+        X = np.random.default_rng(0).standard_normal((20, 3))
+        with ChainEngine(g.lower(), SamplerConfig(), 1) as eng:
+            assert np.allclose(eng.log_posterior(X), scipy.stats.multivariate_normal(mean, cov).logpdf(X), rtol=1e-12)
+    else:
+        # moments of the Soize density by quadrature on a fine grid
+        s = distributions.SoizePDF([], 2)
+        g0, g1 = np.meshgrid(np.linspace(-2.5, 2.5, 1201), np.linspace(-2.5, 3.0, 1201), indexing="ij")
+        w = np.exp(-15 * (g0 ** 3 - g1) ** 2 - (g1 - 0.3) ** 4)
+        w /= w.sum()
+        m = np.array([(w * g0).sum(), (w * g1).sum()])
+        v = np.array([(w * (g0 - m[0]) ** 2).sum(), (w * (g1 - m[1]) ** 2).sum()])
+        assert np.all(np.abs(st["mean"] - m) < 0.05) and np.all(np.abs(np.diag(st["cov"]) / v - 1) < 0.15)
+        from pybitup_b200.engine import ChainEngine, SamplerConfig
+        X = np.random.default_rng(1).uniform(-1.5, 1.5, (30, 2))
+        with ChainEngine(s.lower(), SamplerConfig(), 1) as eng:
+            assert np.allclose(eng.log_posterior(X), [s.compute_log_value(x) for x in X], rtol=1e-13, atol=1e-13)
+
+
+def test_hmc_from_json(tmp_path, monkeypatch):
+    from pybitup_b200 import synthetic, bayesian_inference as bi
+    from pybitup_b200.solve_problem import Sampling
+    monkeypatch.chdir(tmp_path)
+    p = synthetic.cubic_problem(n_points=300)
+    pd.DataFrame({"x": p["design"]["x"], "y": p["y"][0], "s": p["std_y"]}).to_csv("cubic.csv", index=False)
+
+    class Cubic(bi.Model):
+        device_model = "poly"
+
+    T = 800
+    names = ["c0", "c1", "c2", "c3"]
+    cfg = {"Sampling": {"BayesianPosterior": {
+        "Data": [{"Type": "ReadFromFile", "FileName": "cubic", "xField": ["x"], "yField": ["y"], "sigmaField": ["s"]}],
+        "Model": [{"param_names": names, "param_values": [1.0, -2.0, 0.5, 3.0]}],
+        "Prior": {"Distribution": "Mixture", "Param": {n: {"initial_val": v, "prior_name": "Uniform", "prior_param": [-10, 10]}
+                                                      for n, v in zip(names, [1.0, -2.0, 0.5, 3.0])}},
+        "Likelihood": {"function": "Gaussian"}},
+        "Algorithm": {"name": "HMC", "n_iterations": T, "n_chains": 64, "seed": 8, "save_eval_freq": 1e9,
+                      "covariance": {"value": "Hessian_diag", "starting_it": 100, "update_it": 50, "end_it": 500},
+                      "gradient": "Analytical", "HMC": {"step_size": 0.4, "num_steps": 4}}}}
+    with open("hmc.json", "w") as f:
+        json.dump(cfg, f)
+    job = Sampling("hmc.json")
+    run = job.sample({"cubic": Cubic()})
+    job.close()
+    assert pd.read_csv("output/mcmc_chain.csv", header=None).values.shape == (T + 1, 4)
+    x = p["design"]["x"]
+    Phi = np.stack([x ** j for j in range(4)], axis=1)
+    cov = np.linalg.inv(Phi.T @ Phi) * 0.1 ** 2
+    mean = cov @ Phi.T @ p["y"][0] / 0.1 ** 2
+    st = run.statistics
+    assert np.all(np.abs(st["mean"] - mean) < 5 * np.sqrt(np.diag(cov)) / np.sqrt(64 * 20))
+    assert np.all(np.abs(np.diag(st["cov"]) / np.diag(cov) - 1.0) < 0.3)
+    assert 0.3 < 1.0 - run.n_rejected / T <= 1.0

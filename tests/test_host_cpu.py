@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_structs_match_header_layout():
     from pybitup_b200 import _capi
     # sizes the C compiler gives the structs (LP64): checked against a tiny C program's view via field offsets
-    assert ctypes.sizeof(_capi.pbu_problem) == 6 * 4 + 7 * 8 + 8 + 8 * 8
+    assert ctypes.sizeof(_capi.pbu_problem) == 6 * 4 + 7 * 8 + 8 + 8 * 8 + 8 + 2 * 4
     assert ctypes.sizeof(_capi.pbu_sampler_cfg) == 2 * 4 + 4 * 8 + 10 * 4 + 2 * 8 + 8 + 2 * 4
     assert ctypes.sizeof(_capi.pbu_run_outputs) == 7 * 8
 
