@@ -115,7 +115,8 @@ typedef struct {
     uint64_t chain_offset;    /* global index of this engine's first chain (multi-GPU sharding)   */
     double hmc_step_size;     /* HMC.step_size (epsilon)       (mha.py:818)                       */
     int32_t hmc_num_steps;    /* HMC.num_steps (L)             (mha.py:819)                       */
-    int32_t pad0;
+    int32_t cooperative;      /* 0 auto; 1: cooperative teams (lanes_per_chain lanes own as many chains, each
+                                 lane does the scalar part of one); -1: replicated layout only          */
 } pbu_sampler_cfg;
 
 /* Per-run outputs that live on the device; any pointer may be NULL (= not recorded).

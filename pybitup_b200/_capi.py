@@ -45,7 +45,7 @@ class pbu_sampler_cfg(C.Structure):
                 ("am_welford", C.c_int32), ("nan_rejects", C.c_int32), ("lanes_per_chain", C.c_int32),
                 ("block_threads", C.c_int32), ("chains_per_thread", C.c_int32), ("tile_points", C.c_int32),
                 ("seed", C.c_uint64), ("chain_offset", C.c_uint64), ("hmc_step_size", C.c_double),
-                ("hmc_num_steps", C.c_int32), ("pad0", C.c_int32)]
+                ("hmc_num_steps", C.c_int32), ("cooperative", C.c_int32)]
 
 
 class pbu_run_outputs(C.Structure):

@@ -81,6 +81,8 @@ struct MhParams {
     int32_t resident;         // 1: all records fit in shared memory
     int32_t tile_points;      // streaming mode: points per shared-memory tile
     int32_t n_full_warps;     // mixed kernels: warps of a block with G lanes per chain (the rest use 2G)
+    int32_t state_smem_off;   // cooperative adaptive kernels: byte offset of the per-thread (V_i, X_av, R) block in shared
+                              // memory, 0 = the adaptive state stays in global memory
     int32_t groups_per_block; // mixed kernels: chain groups per block
     double R0[PBU_MAX_DIM * (PBU_MAX_DIM + 1) / 2];   // packed upper Cholesky factor shared by all chains (non-adaptive samplers)
 };

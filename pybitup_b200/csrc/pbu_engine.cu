@@ -75,8 +75,8 @@ extern "C" __attribute__((visibility("default"))) int pbu_list_kernels(char *buf
     int n = 0;
     for (const MhKernelEntry *t = pbu_mh_kernels(&n); t && s.size() < 1u << 20 && n > 0; --n, ++t) {
         char line[128];
-        snprintf(line, sizeof line, "mh model=%d P=%d d=%d lanes=%d chains_per_thread=%d algo=%d streamed=%d\n", t->model, t->n_param, t->n_unc,
-                 t->lanes, t->chains_per_thread, t->algo, t->streamed);
+        snprintf(line, sizeof line, "mh model=%d P=%d d=%d lanes=%d chains_per_thread=%d algo=%d streamed=%d mixed=%d coop=%d\n", t->model, t->n_param,
+                 t->n_unc, t->lanes, t->chains_per_thread, t->algo, t->streamed, t->mixed, t->coop);
         s += line;
     }
     int total = 0;
@@ -88,12 +88,12 @@ extern "C" __attribute__((visibility("default"))) int pbu_list_kernels(char *buf
     return total;
 }
 
-static const MhKernelEntry *find_mh(int model, int P, int d, int lanes, int q, int algo, int streamed, int mixed = 0) {
+static const MhKernelEntry *find_mh(int model, int P, int d, int lanes, int q, int algo, int streamed, int mixed = 0, int coop = 0) {
     int n = 0;
     const MhKernelEntry *t = pbu_mh_kernels(&n);
     for (int i = 0; i < n; ++i)
         if (t[i].model == model && t[i].n_param == P && t[i].n_unc == d && t[i].lanes == lanes && t[i].chains_per_thread == q &&
-            t[i].algo == algo && t[i].streamed == streamed && t[i].mixed == mixed)
+            t[i].algo == algo && t[i].streamed == streamed && t[i].mixed == mixed && t[i].coop == coop)
             return &t[i];
     return nullptr;
 }
@@ -192,13 +192,16 @@ static double loop_efficiency(int q, double warps) {
     return e[6];
 }
 
-static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int want_lanes, int want_q, int want_block) {
+static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int want_lanes, int want_q, int want_block, int want_coop) {
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, e->device);
     const double N = (double)e->prob.n_points;
     const double S0 = 60.0 + 15.0 * e->d;           // per-iteration scalar part (RNG, proposal, accept, adaptation), in DFMA-equivalents
-    // (lanes per chain, chains per thread, mixed): mixed = the last warps of a block use twice the lanes
-    const int cand[8][3] = {{1, 1, 0}, {1, 2, 0}, {2, 2, 0}, {2, 2, 1}, {4, 2, 0}, {2, 1, 0}, {4, 1, 0}, {8, 1, 0}};
+    // (lanes, chains per thread or per team, mixed, coop): mixed = the last warps of a block use twice the lanes;
+    // coop = teams of `lanes` lanes own `lanes` chains (pbu_mh_coop.cuh)
+    const int cand[10][4] = {{1, 1, 0, 0}, {1, 2, 0, 0}, {2, 2, 0, 0}, {2, 2, 1, 0}, {4, 2, 0, 0}, {2, 1, 0, 0}, {4, 1, 0, 0}, {8, 1, 0, 0},
+                             {4, 4, 0, 1}, {4, 4, 1, 1}};
+    const char *force = getenv("PBU_FORCE_VARIANT");      // "lanes,q,mixed,coop": diagnostics
     const bool hmc = algo == PBU_ALGO_HMC;
     const bool isde = algo == PBU_ALGO_ISDE || hmc;
     const int streamed = e->tile_points < e->prob.n_points ? 1 : 0;
@@ -206,16 +209,27 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
     double best = 1e300;
     bool found = false;
     for (const auto &gq : cand) {
-        const int g = gq[0], q = gq[1], mixed = gq[2];
+        const int g = gq[0], q = gq[1], mixed = gq[2], coop = gq[3];
+        if (force) {
+            int f[4] = {0, 0, 0, 0};
+            sscanf(force, "%d,%d,%d,%d", &f[0], &f[1], &f[2], &f[3]);
+            if (f[0] != g || f[1] != q || f[2] != mixed || f[3] != coop) continue;
+        } else {
+            if (want_coop > 0 && !coop) continue;
+            if (want_coop < 0 && coop) continue;
+            if (want_coop == 0 && coop && (want_lanes > 0 || want_q > 0 || want_block > 0)) continue;
+            if (coop && mixed && want_block > 0) continue;
+        }
+        if (coop && (isde || streamed)) continue;
         if (want_lanes > 0 && g != want_lanes) continue;
         if (want_q > 0 && q != want_q) continue;
         if (sequential && g != 1) continue;
-        if (mixed && (isde || streamed || want_block > 0 || want_lanes > 0)) continue;
+        if (mixed && (isde || streamed || (!force && (want_block > 0 || want_lanes > 0)))) continue;
         // delayed rejection: the second stage runs for a thread when ANY of its chains was rejected, so pairing
         // chains wastes evaluations; one chain per thread unless asked otherwise
-        if ((algo == PBU_ALGO_DR || algo == PBU_ALGO_DRAM) && q != 1 && want_q <= 0 && want_lanes <= 0) continue;
+        if ((algo == PBU_ALGO_DR || algo == PBU_ALGO_DRAM) && q != 1 && !coop && want_q <= 0 && want_lanes <= 0) continue;
         // wide states spill heavily with two chains per thread
-        if (e->d > 6 && q != 1 && want_q <= 0 && want_lanes <= 0) continue;
+        if (e->d > 6 && q != 1 && ((coop && want_coop <= 0) || (!coop && want_q <= 0 && want_lanes <= 0))) continue;
         const void *fn = nullptr;
         const MhKernelEntry *km = nullptr;
         const IsdeKernelEntry *ki = nullptr;
@@ -223,20 +237,37 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
             ki = hmc ? find_hmc(model, e->P, e->d, g, q, streamed) : find_isde(model, e->P, e->d, g, q, streamed);
             if (ki) fn = ki->fn;
         } else {
-            km = find_mh(model, e->P, e->d, g, q, algo, streamed, mixed);
+            km = find_mh(model, e->P, e->d, g, q, algo, streamed, mixed, coop);
             if (km) fn = km->fn;
         }
         if (!fn) continue;
-        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+        int max_smem = 0;
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device);
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        const bool adaptive = algo == PBU_ALGO_AM || algo == PBU_ALGO_DRAM;
+        const size_t rec_aligned = (e->smem_bytes + 127) & ~(size_t)127;
+        // replicated layout: a group of g lanes carries q chains per lane-set; cooperative: a team of g lanes owns q = g chains
         const int64_t groups_needed = (e->C + q - 1) / q;
         // 8 lanes reading 8 consecutive records collide in the shared-memory banks when the record stride is an even
         // number of 16-byte units (two wavefronts per load)
         const double conflict = (g >= 8 && (e->ev->nc / 2) % 2 == 0) ? 1.1 : 1.0;
-        const double work = q * ((sequential ? N : std::ceil(N / g)) * ops * conflict + S0);      // per thread of a G-lane warp
+        // per thread of a warp: every lane evaluates q chains on its share of the points; the scalar part is done for q chains
+        // per lane in the replicated layout and for one chain per lane in the cooperative one
+        const double work = q * (sequential ? N : std::ceil(N / g)) * ops * conflict + (coop ? 1.0 : (double)q) * S0;
         for (int B = MH_MAX_BLOCK; B >= 32; B -= 32) {
             if (want_block > 0 && B != want_block) continue;
+            // cooperative adaptive kernels stage (V_i, X_av, R) of every thread's chain in shared memory when there is room
+            size_t smem_launch = e->smem_bytes;
+            int state_off = 0;
+            if (coop && adaptive && getenv("PBU_STATE_SMEM")) {      // experiment: measured slower than global (L1/L2) state
+                const size_t state = (size_t)(2 * e->nt + e->d) * sizeof(double) * B;
+                if (rec_aligned + state <= (size_t)max_smem) {
+                    state_off = (int)rec_aligned;
+                    smem_launch = rec_aligned + state;
+                }
+            }
             int occ = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, B, e->smem_bytes) != cudaSuccess || occ < 1) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, B, smem_launch) != cudaSuccess || occ < 1) {
                 cudaGetLastError();
                 continue;
             }
@@ -254,7 +285,10 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
                 const double sched_units = mixed ? (nfull / 4.0 + nwide / 8.0) : std::ceil(conc * W / 4.0) / conc;
                 // a handful of warps on the whole GPU is latency-bound: only the serial work of a thread counts
                 const bool tiny = blocks * W < nsm;
-                const double t = tiny ? work : per_sm * sched_units * 4.0 * 32.0 * work / loop_efficiency(q, warps);
+                // measured at cfg 2 (tools/bench_configs.py): cooperative teams win for RWMH / DR / DRAM (0.76 / 0.59 / 0.56 of the
+                // DFMA peak against 0.71 / 0.47 / 0.50), the replicated mixed layout for plain AM (0.655 against 0.61)
+                const double eff = loop_efficiency(q, warps) * ((coop && algo == PBU_ALGO_AM) ? 0.9 : 1.0);
+                const double t = tiny ? work : per_sm * sched_units * 4.0 * 32.0 * work / eff;
                 if (t < best * (1.0 - 1e-3)) {
                     best = t;
                     e->mh = km;
@@ -266,6 +300,8 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
                     e->grid = (int)blocks;
                     e->n_full_warps = mixed ? nfull : 0;
                     e->groups_per_block = gpb;
+                    e->state_smem_off = state_off;
+                    e->launch_smem = smem_launch;
                     found = true;
                 }
             }
@@ -405,7 +441,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
     pd.raw = e->d_raw;
 
     // ---- launch geometry
-    if ((rc = plan_launch(e, pr->model, ev->sequential != 0, cfg->algo, cfg->lanes_per_chain, cfg->chains_per_thread, cfg->block_threads)) != PBU_OK) {
+    if ((rc = plan_launch(e, pr->model, ev->sequential != 0, cfg->algo, cfg->lanes_per_chain, cfg->chains_per_thread, cfg->block_threads, cfg->cooperative)) != PBU_OK) {
         pbu_engine_destroy(e);
         return rc;
     }
@@ -631,7 +667,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_get_launch(cons
     if (chains_per_thread) *chains_per_thread = e->q;
     if (block) *block = e->block;
     if (grid) *grid = e->grid;
-    if (smem_bytes) *smem_bytes = (int64_t)e->smem_bytes;
+    if (smem_bytes) *smem_bytes = (int64_t)e->launch_smem;
     return PBU_OK;
 }
 
@@ -667,7 +703,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine 
         q.tile_points = e->tile_points;
         q.fd_gradient = e->cfg.isde_gradient != 0;
         void *iargs[] = {(void *)&q};
-        CUDA_TRY(cudaLaunchKernel(e->step_fn, dim3((unsigned)e->grid), dim3(e->block), iargs, e->smem_bytes, e->stream));
+        CUDA_TRY(cudaLaunchKernel(e->step_fn, dim3((unsigned)e->grid), dim3(e->block), iargs, e->launch_smem, e->stream));
         e->iteration += n_steps;
         return PBU_OK;
     }
@@ -695,9 +731,10 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine 
     p.n_groups = (int64_t)e->grid * e->groups_per_block;
     p.n_full_warps = e->n_full_warps;
     p.groups_per_block = e->groups_per_block;
+    p.state_smem_off = e->state_smem_off;
     for (size_t i = 0; i < e->R0.size(); ++i) p.R0[i] = e->R0[i];
     void *args[] = {(void *)&p};
-    CUDA_TRY(cudaLaunchKernel(e->step_fn, dim3((unsigned)e->grid), dim3(e->block), args, e->smem_bytes, e->stream));
+    CUDA_TRY(cudaLaunchKernel(e->step_fn, dim3((unsigned)e->grid), dim3(e->block), args, e->launch_smem, e->stream));
     e->iteration += n_steps;
     return PBU_OK;
 }

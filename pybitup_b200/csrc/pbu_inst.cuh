@@ -1,31 +1,36 @@
 // Helper macros to instantiate kernel variants and describe them in a table slice.
 #pragma once
 #include "pbu_isde_kernel.cuh"
+#include "pbu_mh_coop.cuh"
 #include "pbu_registry.h"
 
 // S = 0: records resident in shared memory; S = 1: streamed in tiles (data sets larger than shared memory)
 #define PBU_MH(MODEL, P, D, G, Q, A, S) \
-    { MODEL::ID, P, D, G, Q, A, S, 0, (const void *)&pbu::mh_step_kernel<MODEL, D, G, A, Q, (S != 0), false> }
+    { MODEL::ID, P, D, G, Q, A, S, 0, 0, (const void *)&pbu::mh_step_kernel<MODEL, D, G, A, Q, (S != 0), false> }
 // mixed: the last warps of each block use 2G lanes per chain (scheduler-level load balance)
 #define PBU_MH_MIXED(MODEL, P, D, G, Q, A) \
-    { MODEL::ID, P, D, G, Q, A, 0, 1, (const void *)&pbu::mh_step_kernel<MODEL, D, G, A, Q, false, true> }
+    { MODEL::ID, P, D, G, Q, A, 0, 1, 0, (const void *)&pbu::mh_step_kernel<MODEL, D, G, A, Q, false, true> }
+// cooperative: teams of G lanes own G chains (pbu_mh_coop.cuh); MX = 1: the last warps of a block use 2G lanes
+#define PBU_MH_COOP(MODEL, P, D, G, A, MX) \
+    { MODEL::ID, P, D, G, G, A, 0, MX, 1, (const void *)&pbu::mh_coop_kernel<MODEL, D, G, A, false, (MX != 0)> }
+#define PBU_MH_COOP_ALGOS(MODEL, P, D, G, MX) \
+    PBU_MH_COOP(MODEL, P, D, G, 0, MX), PBU_MH_COOP(MODEL, P, D, G, 1, MX), PBU_MH_COOP(MODEL, P, D, G, 2, MX), PBU_MH_COOP(MODEL, P, D, G, 3, MX)
 #define PBU_MH_ALGOS(MODEL, P, D, G, Q, S) \
     PBU_MH(MODEL, P, D, G, Q, 0, S), PBU_MH(MODEL, P, D, G, Q, 1, S), PBU_MH(MODEL, P, D, G, Q, 2, S), PBU_MH(MODEL, P, D, G, Q, 3, S)
-// data-parallel models, (lanes per chain, chains per thread): (1,1) (1,2) (2,2) (4,2), (8,1) for very few chains;
-// streamed: (1,1) (1,2) (8,1)
+// data-parallel models.  Replicated layout (lanes per chain, chains per thread): (1,1) (1,2) (2,2), (2,2) mixed, (8,1) for
+// very few chains; cooperative teams of 4 lanes x 4 chains, plain and mixed; streamed records: (1,1) (1,2) (8,1)
 #define PBU_MH_ALL(MODEL, P, D)                                                                                        \
     PBU_MH_ALGOS(MODEL, P, D, 1, 1, 0), PBU_MH_ALGOS(MODEL, P, D, 1, 2, 0), PBU_MH_ALGOS(MODEL, P, D, 2, 2, 0),        \
-        PBU_MH_ALGOS(MODEL, P, D, 4, 2, 0), PBU_MH_ALGOS(MODEL, P, D, 8, 1, 0), PBU_MH_ALGOS(MODEL, P, D, 1, 1, 1),    \
-        PBU_MH_ALGOS(MODEL, P, D, 1, 2, 1), PBU_MH_ALGOS(MODEL, P, D, 8, 1, 1), PBU_MH_MIXED(MODEL, P, D, 2, 2, 0),     \
-        PBU_MH_MIXED(MODEL, P, D, 2, 2, 1)
+        PBU_MH_ALGOS(MODEL, P, D, 8, 1, 0), PBU_MH_ALGOS(MODEL, P, D, 1, 1, 1), PBU_MH_ALGOS(MODEL, P, D, 1, 2, 1),    \
+        PBU_MH_ALGOS(MODEL, P, D, 8, 1, 1), PBU_MH_MIXED(MODEL, P, D, 2, 2, 0), PBU_MH_MIXED(MODEL, P, D, 2, 2, 1),     \
+        PBU_MH_COOP_ALGOS(MODEL, P, D, 4, 0), PBU_MH_COOP_ALGOS(MODEL, P, D, 4, 1)
 #define PBU_MH_SEQ(MODEL, P, D) PBU_MH_ALGOS(MODEL, P, D, 1, 1, 0), PBU_MH_ALGOS(MODEL, P, D, 1, 1, 1)
 // Ito-SDE step kernel variants (lanes per chain, chains per thread, streamed)
 #define PBU_ISDE(MODEL, P, D, G, Q, S) \
     { MODEL::ID, P, D, G, Q, MODEL::HAS_GRAD ? 1 : 0, S, (const void *)&pbu::isde_step_kernel<MODEL, D, G, Q, (S != 0)> }
 #define PBU_ISDE_ALL(MODEL, P, D)                                                                                   \
-    PBU_ISDE(MODEL, P, D, 1, 1, 0), PBU_ISDE(MODEL, P, D, 1, 2, 0), PBU_ISDE(MODEL, P, D, 2, 2, 0), PBU_ISDE(MODEL, P, D, 8, 1, 0), \
-        PBU_ISDE(MODEL, P, D, 1, 1, 1), PBU_ISDE(MODEL, P, D, 1, 2, 1), PBU_ISDE(MODEL, P, D, 8, 1, 1),               \
-        PBU_ISDE(MODEL, P, D, 4, 1, 0), PBU_ISDE(MODEL, P, D, 4, 1, 1), PBU_ISDE(MODEL, P, D, 2, 1, 1)
+    PBU_ISDE(MODEL, P, D, 1, 1, 0), PBU_ISDE(MODEL, P, D, 1, 2, 0), PBU_ISDE(MODEL, P, D, 2, 2, 0), PBU_ISDE(MODEL, P, D, 4, 1, 0), \
+        PBU_ISDE(MODEL, P, D, 8, 1, 0), PBU_ISDE(MODEL, P, D, 1, 1, 1), PBU_ISDE(MODEL, P, D, 4, 1, 1), PBU_ISDE(MODEL, P, D, 8, 1, 1)
 #define PBU_ISDE_SEQ(MODEL, P, D) PBU_ISDE(MODEL, P, D, 1, 1, 0), PBU_ISDE(MODEL, P, D, 1, 1, 1)
 // Hamiltonian Monte Carlo step kernel variants (same table type as ISDE; `kind` 1)
 #define PBU_HMC(MODEL, P, D, G, Q, S) \

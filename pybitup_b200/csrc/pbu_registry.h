@@ -8,6 +8,7 @@ struct MhKernelEntry {
     int model, n_param, n_unc, lanes, chains_per_thread, algo;   // algo = pbu_algo_id (RWMH, AM, DR, DRAM)
     int streamed;             // 0: records resident in shared memory, 1: streamed in tiles
     int mixed;                // 1: the last warps of a block use 2 * lanes per chain
+    int coop;                 // 1: cooperative teams (pbu_mh_coop.cuh): `lanes` lanes own `chains_per_thread` (= lanes) chains
     const void *fn;   // __global__ void (*)(const MhParams)
 };
 struct IsdeKernelEntry {

@@ -120,6 +120,7 @@ class SamplerConfig:
     chain_offset: int = 0
     hmc_step_size: float = 0.0
     hmc_num_steps: int = 0
+    cooperative: int = 0             # 0 auto, 1 cooperative teams, -1 replicated layout only
 
     def _c_struct(self):
         s = capi.pbu_sampler_cfg()
@@ -136,6 +137,7 @@ class SamplerConfig:
         s.tile_points = int(self.tile_points)
         s.seed, s.chain_offset = int(self.seed) & (2 ** 64 - 1), int(self.chain_offset)
         s.hmc_step_size, s.hmc_num_steps = float(self.hmc_step_size), int(self.hmc_num_steps)
+        s.cooperative = int(self.cooperative)
         return s
 
 

@@ -18,7 +18,7 @@ def _isde_engine(p, a, n_chains, **kw):
     return ChainEngine(ProblemSpec.from_dict(H.problem_dict(p)), cfg, n_chains)
 
 
-@pytest.mark.parametrize("lanes,q", [(1, 1), (1, 2), (2, 2), (8, 1)])
+@pytest.mark.parametrize("lanes,q", [(1, 1), (1, 2), (2, 2), (4, 1), (8, 1)])
 def test_isde_analytical_golden(lanes, q):
     g = H.load_golden("regression_isde")
     a = g["algo"]

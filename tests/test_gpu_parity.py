@@ -46,18 +46,18 @@ def _eval_sequence(res, lp0, n_init, delayed, chain=0):
     return np.array(seq), acc
 
 
-@pytest.mark.parametrize("lanes", [1, 2, 8])
+@pytest.mark.parametrize("lanes", [1, 2, 8, -4])
 @pytest.mark.parametrize("case", MH_CASES)
 def test_mh_golden_parity(case, lanes):
-    """CUDA engine vs the recorded reference run, fed the same streams."""
+    """CUDA engine vs the recorded reference run, fed the same streams.  lanes < 0: cooperative teams of -lanes lanes."""
     g = H.load_golden(case)
     algo = g["algo"]
     if g["model"] == "arrhenius" and lanes != 1:
         pytest.skip("sequential ODE model: one lane per chain")
     T = int(algo["n_iterations"])
     tol = CASE_TOL.get(case, TOL)
-    n_chains = 3            # the same chain three times: every chain must reproduce the reference
-    eng = _engine(g, algo, n_chains, lanes_per_chain=lanes)
+    n_chains = 3 if lanes > 0 else 11       # the same chain several times: every chain must reproduce the reference
+    eng = _engine(g, algo, n_chains, lanes_per_chain=abs(lanes), cooperative=(1 if lanes < 0 else -1))
     eng.init_chains(np.tile(g["x0"], (n_chains, 1)), g["prop_cov"])
     x_init, lp_init = eng.state()
     eng.set_streams(np.tile(g["normals"], (n_chains, 1)), np.tile(g["uniforms"], (n_chains, 1)))
@@ -93,7 +93,8 @@ def test_mh_golden_parity(case, lanes):
 
 @pytest.mark.parametrize("algo_name", ["RWMH", "AMH", "DR", "DRAM"])
 @pytest.mark.parametrize("builder,lanes", [("linear_problem", 1), ("linear_problem", 8), ("cubic_problem", 2),
-                                           ("heat_problem", 1), ("arrhenius_problem", 1)])
+                                           ("heat_problem", 1), ("arrhenius_problem", 1), ("cubic_problem", -4),
+                                           ("linear_problem", -4), ("heat_problem", -4)])
 def test_many_chains_vs_oracle(builder, lanes, algo_name):
     """64 different chains (own start, own streams) against the CPU oracle, chain by chain."""
     from pybitup_b200 import synthetic
@@ -110,7 +111,7 @@ def test_many_chains_vs_oracle(builder, lanes, algo_name):
     uniforms = rng.random((n_chains, 2 * T))
     algo = {"name": algo_name, "AMH": {"updating_it": 7, "eps_v": 1e-10}, "DR": {"gamma": 0.3},
             "DRAM": {"updating_it": 7, "eps_v": 1e-10, "gamma": 0.3}}
-    eng = _engine(p, algo, n_chains, lanes_per_chain=lanes)
+    eng = _engine(p, algo, n_chains, lanes_per_chain=abs(lanes), cooperative=(1 if lanes < 0 else -1))
     eng.init_chains(x0, p["prop_cov"])
     _, lp_init = eng.state()
     eng.set_streams(normals, uniforms)

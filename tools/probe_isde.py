@@ -5,7 +5,7 @@ from pybitup_b200 import synthetic
 from pybitup_b200.engine import ChainEngine, ProblemSpec, SamplerConfig
 p = synthetic.regression_problem()
 C = 131072
-for lanes, q, block in ((0, 0, 0), (1, 1, 512), (2, 1, 512), (4, 1, 512), (8, 1, 512), (4, 1, 256), (1, 1, 448), (4, 1, 384)):
+for lanes, q, block in ((0, 0, 0), (1, 1, 512), (4, 1, 512), (8, 1, 512)):
     try:
         cfg = SamplerConfig(algo="ISDE", seed=1, isde_h=0.05, isde_f0=4.0, isde_gradient="Analytical", lanes_per_chain=lanes, chains_per_thread=q, block_threads=block)
         eng = ChainEngine(ProblemSpec.from_dict(p), cfg, C)

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(1024) dfma3_kernel(double *out, int iters, dou
 
 // cubic Horner + weighted residual + square, records [x, w, wy, pad] broadcast from shared memory
 template <int U, int Q, int G = 1>
-__global__ void __launch_bounds__(1024) horner_kernel(double *out, const double *rec_g, int n, int reps) {
+__global__ void __launch_bounds__(512) horner_kernel(double *out, const double *rec_g, int n, int reps) {
     extern __shared__ double rec[];
     for (int i = threadIdx.x; i < n * 4; i += blockDim.x) rec[i] = rec_g[i];
     __syncthreads();
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(1024) horner_kernel(double *out, const double 
     }
     for (int r = 0; r < reps; ++r) {
 #pragma unroll 1
-        for (int k = (G == 1) ? 0 : (int)(threadIdx.x % G); k + (U - 1) * G < n; k += U * G) {
+        for (int k = (G == 1) ? 0 : (int)((threadIdx.x & 31) / (32 / G)); k + (U - 1) * G < n; k += U * G) {
             double x[U], w[U], wy[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -99,8 +99,8 @@ template <int U, int Q, int G = 1>
 static void run_horner(double *out, const double *rec, int nsm) {
     const int n = 1000, reps = 200;
     CK(cudaFuncSetAttribute(horner_kernel<U, Q, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, n * 32));
-    for (int warps : {4, 7, 8, 12, 14, 16, 24, 32}) {
-        if (warps * 32 > 1024) continue;
+    for (int warps : {4, 8, 12, 14, 16}) {
+        if (warps * 32 > 512) continue;
         float ms = time_ms([&] { horner_kernel<U, Q, G><<<nsm, warps * 32, n * 32>>>(out, rec, n, reps); });
         double instr = 5.0 * Q * (double)(n / (U * G) * U) * reps * nsm * warps * 32;   // DFMA thread-instructions
         printf("horner U=%d Q=%d G=%d warps/SM=%2d  %.2f TFLOP/s (2 flops per DFMA)  %.3f ms\n", U, Q, G, warps, 2 * instr / (ms * 1e-3) / 1e12, ms);
@@ -117,8 +117,8 @@ int main() {
     for (int i = 0; i < 1000; ++i) { h[4 * i] = -1.0 + 0.002 * i; h[4 * i + 1] = 10.0; h[4 * i + 2] = 3.0; h[4 * i + 3] = 0; }
     CK(cudaMemcpy(rec, h, sizeof h, cudaMemcpyHostToDevice));
     if (getenv("UBENCH_DFMA")) { run_dfma<1>(out, nsm); run_dfma<2>(out, nsm); run_dfma<4>(out, nsm); run_dfma<8>(out, nsm); }
-    run_horner<4, 1>(out, rec, nsm); run_horner<4, 2>(out, rec, nsm); run_horner<4, 2, 2>(out, rec, nsm); run_horner<4, 2, 4>(out, rec, nsm);
-    run_horner<3, 2>(out, rec, nsm); run_horner<6, 2>(out, rec, nsm); run_horner<4, 3>(out, rec, nsm); run_horner<4, 4>(out, rec, nsm);
-    run_horner<2, 3>(out, rec, nsm); run_horner<3, 3>(out, rec, nsm);
+    run_horner<4, 2>(out, rec, nsm); run_horner<4, 2, 2>(out, rec, nsm); run_horner<2, 4>(out, rec, nsm); run_horner<2, 4, 4>(out, rec, nsm);
+    run_horner<3, 4, 4>(out, rec, nsm); run_horner<4, 4, 4>(out, rec, nsm); run_horner<2, 3>(out, rec, nsm); run_horner<3, 3>(out, rec, nsm);
+    run_horner<2, 4, 8>(out, rec, nsm); run_horner<1, 4, 4>(out, rec, nsm); run_horner<2, 8, 8>(out, rec, nsm);
     return 0;
 }
