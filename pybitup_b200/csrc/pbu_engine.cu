@@ -259,7 +259,7 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
             // cooperative adaptive kernels stage (V_i, X_av, R) of every thread's chain in shared memory when there is room
             size_t smem_launch = e->smem_bytes;
             int state_off = 0;
-            if (coop && adaptive && getenv("PBU_STATE_SMEM")) {      // experiment: measured slower than global (L1/L2) state
+            if (false && coop && adaptive) {      // staging the adaptive state in shared memory was measured slower: disabled
                 const size_t state = (size_t)(2 * e->nt + e->d) * sizeof(double) * B;
                 if (rec_aligned + state <= (size_t)max_smem) {
                     state_off = (int)rec_aligned;
@@ -285,9 +285,7 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
                 const double sched_units = mixed ? (nfull / 4.0 + nwide / 8.0) : std::ceil(conc * W / 4.0) / conc;
                 // a handful of warps on the whole GPU is latency-bound: only the serial work of a thread counts
                 const bool tiny = blocks * W < nsm;
-                // measured at cfg 2 (tools/bench_configs.py): cooperative teams win for RWMH / DR / DRAM (0.76 / 0.59 / 0.56 of the
-                // DFMA peak against 0.71 / 0.47 / 0.50), the replicated mixed layout for plain AM (0.655 against 0.61)
-                const double eff = loop_efficiency(q, warps) * ((coop && algo == PBU_ALGO_AM) ? 0.9 : 1.0);
+                const double eff = loop_efficiency(q, warps);
                 const double t = tiny ? work : per_sm * sched_units * 4.0 * 32.0 * work / eff;
                 if (t < best * (1.0 - 1e-3)) {
                     best = t;
@@ -674,7 +672,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_get_launch(cons
 extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine *e, int64_t n_steps, int64_t thin, const pbu_run_outputs *out) {
     if (!e) return fail(PBU_ERR_INVALID, "null engine");
     if (!e->initialised) return fail(PBU_ERR_INVALID, "pbu_engine_init_chains has not been called");
-    if (n_steps < 0 || thin < 1) return fail(PBU_ERR_INVALID, "need n_steps >= 0 and thin >= 1");
+    if (n_steps < 0 || thin < 1 || n_steps > 2000000000LL) return fail(PBU_ERR_INVALID, "need 0 <= n_steps <= 2e9 per launch and thin >= 1");
     if (n_steps == 0) return PBU_OK;
     CUDA_TRY(cudaSetDevice(e->device));
     if (e->cfg.algo == PBU_ALGO_ISDE || e->cfg.algo == PBU_ALGO_HMC) {

@@ -43,33 +43,18 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
     lp = p.st.lp[c];
     mean_r = p.st.mean_r[c];
     int32_t n_rej = 0, n_eval = 0, status = p.st.status[c];
-    // Adaptive state (V_i, X_av, R) of the own chain: in global memory (stride C), or -- when the host found room --
-    // staged for the whole launch in shared memory, one column per thread (stride blockDim.x): the per-iteration
-    // read-modify-write then never leaves the SM (measured at cfg 2: 0.35 ms of 2.95 per 100 iterations).
-    double *gR = p.st.R + c, *gV = p.st.V + c, *gxav = p.st.xav + c;
-    int64_t sS = C;
-    const bool state_smem = ADAPT && p.state_smem_off > 0;
-    if (state_smem) {
-        double *base = reinterpret_cast<double *>(TileStream<M::NC>::smem() + p.state_smem_off) + threadIdx.x;
-        const int64_t B = blockDim.x;
-#pragma unroll
-        for (int i = 0; i < NT; ++i) base[i * B] = gV[(int64_t)i * C];
-#pragma unroll
-        for (int i = 0; i < D; ++i) base[(NT + i) * B] = gxav[(int64_t)i * C];
-#pragma unroll
-        for (int i = 0; i < NT; ++i) base[(NT + D + i) * B] = gR[(int64_t)i * C];
-        gV = base;
-        gxav = base + NT * B;
-        gR = base + (NT + D) * B;
-        sS = B;
-    }
-
+    // The adaptive state (V_i, X_av, R) of the own chain lives in global memory (chain-minor, stride C): its addresses are
+    // rebuilt from the kernel parameters where they are used, so that no pointer stays live across the data loop (at the
+    // 128-register cap every register the loop loses costs operand-reuse slots, i.e. DFMA issue rate).  Staging this
+    // state in shared memory for the launch was tried and measured slower (3.18 against 2.96 ms per 100 iterations).
+    const int64_t sS = C;
     int32_t to_refresh = ADAPT ? (int32_t)(p.updating_it - p.it0 % p.updating_it) : 0;
     int32_t to_keep = (int32_t)(p.thin - p.it0 % p.thin);
-    int64_t row = 0;
-    for (int64_t s = 0; s < p.n_steps; ++s) {
+    int32_t row = 0;
+    const int32_t n_steps = (int32_t)p.n_steps;      // a launch is at most 2^31 iterations (checked on the host)
+    for (int32_t s = 0; s < n_steps; ++s) {
         const int64_t it = p.it0 + s + 1;
-        double y[D] = {}, y1[DELAYED ? D : 1], u = 1.0, lp1 = 0.0, lp2 = nan(""), r = 0.0, alpha = 0.0;
+        double y[D] = {}, u = 1.0, lp1 = 0.0, lp2 = nan(""), r = 0.0, alpha = 0.0;
         int acc = 0;
         bool want = owner;                   // lanes beyond the team's chains only lend their arithmetic to the data loop
 #pragma unroll 1
@@ -88,7 +73,7 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
                     double sj = 0.0;
 #pragma unroll
                     for (int j = i; j < D; ++j) {
-                        const double rij = ADAPT ? gR[(int64_t)tri_idx(D, i, j) * sS] : p.R0[tri_idx(D, i, j)];
+                        const double rij = ADAPT ? p.st.R[(int64_t)tri_idx(D, i, j) * sS + c] : p.R0[tri_idx(D, i, j)];
                         sj = fma(rij, z[j], sj);
                     }
                     y[i] = x[i] + scale * sj;
@@ -156,11 +141,12 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
                     double M2 = 0.0, M4 = 0.0;                                          // inv_V = diag(1/R_ii^2)
 #pragma unroll
                     for (int i = 0; i < D; ++i) {
-                        const double rii = ADAPT ? gR[(int64_t)tri_idx(D, i, i) * sS] : p.R0[tri_idx(D, i, i)];
+                        const double rii = ADAPT ? p.st.R[(int64_t)tri_idx(D, i, i) * sS + c] : p.R0[tri_idx(D, i, i)];
                         const double ir = 1.0 / rii;
                         const double iv = ir * ir;
-                        const double d1 = y1[DELAYED ? i : 0] - y[i];
-                        const double d2 = y1[DELAYED ? i : 0] - x[i];
+                        const double y1i = p.st.P[(int64_t)i * C + c];     // first-stage proposal, parked in global memory
+                        const double d1 = y1i - y[i];
+                        const double d2 = y1i - x[i];
                         M2 += (d1 * iv) * d1;
                         M4 += (d2 * iv) * d2;
                     }
@@ -178,8 +164,12 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
                     acc = stage + 1;
                     want = false;
                 } else if (DELAYED && stage == 0) {
+                    // keep the rejected first proposal for the second-stage ratio (:549-556) out of the registers: the
+                    // (otherwise unused) momentum array is this chain's scratch
+                    if (live) {
 #pragma unroll
-                    for (int i = 0; i < D; ++i) y1[DELAYED ? i : 0] = y[i];
+                        for (int i = 0; i < D; ++i) p.st.P[(int64_t)i * C + c] = y[i];
+                    }
                     again_own = true;                                                   // :535
                 } else {
                     n_rej += 1;                                                         // :224, :567
@@ -204,7 +194,7 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
                 double xa[D], xb[D];
 #pragma unroll
                 for (int i = 0; i < D; ++i) {
-                    xa[i] = (it == 1) ? x[i] : gxav[(int64_t)i * sS];                      // X_av aliases the state at it == 1 (Q3)
+                    xa[i] = (it == 1) ? x[i] : p.st.xav[(int64_t)i * sS + c];                      // X_av aliases the state at it == 1 (Q3)
                     xb[i] = __dadd_rn(x[i], __dmul_rn(fi / (fi + 1.0), __dadd_rn(xa[i], -x[i])));       // :455
                 }
                 const double c1 = (fi - 1.0) / fi, c2 = p.S_d / fi;
@@ -216,13 +206,13 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
                         t = __dadd_rn(t, __dmul_rn(x[i], x[j]));
                         t = __dadd_rn(t, (i == j) ? p.eps_v : 0.0);
                         const int64_t o = (int64_t)tri_idx(D, i, j) * sS;
-                        const double v = __dadd_rn(__dmul_rn(c1, gV[o]), __dmul_rn(c2, t));             // :463
+                        const double v = __dadd_rn(__dmul_rn(c1, p.st.V[o + c]), __dmul_rn(c2, t));             // :463
                         Vc[tri_idx(D, i, j)] = v;
-                        if (live) gV[o] = v;
+                        if (live) p.st.V[o + c] = v;
                     }
                 if (live) {
 #pragma unroll
-                    for (int i = 0; i < D; ++i) gxav[(int64_t)i * sS] = xb[i];
+                    for (int i = 0; i < D; ++i) p.st.xav[(int64_t)i * sS + c] = xb[i];
                 }
             } else {
                 const double inv_n = 1.0 / (fi + 1.0);
@@ -230,7 +220,7 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
                 double dl[D], mu[D];
 #pragma unroll
                 for (int i = 0; i < D; ++i) {
-                    const double m = gxav[(int64_t)i * sS];
+                    const double m = p.st.xav[(int64_t)i * sS + c];
                     dl[i] = x[i] - m;
                     mu[i] = fma(dl[i], inv_n, m);
                 }
@@ -239,13 +229,13 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
 #pragma unroll
                     for (int j = i; j < D; ++j) {
                         const int64_t o = (int64_t)tri_idx(D, i, j) * sS;
-                        const double v = fma(dl[i], x[j] - mu[j], gV[o]);
+                        const double v = fma(dl[i], x[j] - mu[j], p.st.V[o + c]);
                         Vc[tri_idx(D, i, j)] = sc * v + ((i == j) ? p.S_d * p.eps_v : 0.0);
-                        if (live) gV[o] = v;
+                        if (live) p.st.V[o + c] = v;
                     }
                 if (live) {
 #pragma unroll
-                    for (int i = 0; i < D; ++i) gxav[(int64_t)i * sS] = mu[i];
+                    for (int i = 0; i < D; ++i) p.st.xav[(int64_t)i * sS + c] = mu[i];
                 }
             }
             if (refresh) {                                  // :486-487, :591-595
@@ -253,7 +243,7 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
                 if (chol_upper_packed<D>(Vc, Rn)) {
                     if (live) {
 #pragma unroll
-                        for (int i = 0; i < NT; ++i) gR[(int64_t)i * sS] = Rn[i];
+                        for (int i = 0; i < NT; ++i) p.st.R[(int64_t)i * sS + c] = Rn[i];
                     }
                 } else {
                     status |= ST_NOT_PD;
@@ -266,9 +256,9 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
 
         // ---- outputs of the own chain
         if (live) {
-            if (p.out.trace_lp1) p.out.trace_lp1[s * C + c] = lp1;
-            if (p.out.trace_lp2) p.out.trace_lp2[s * C + c] = lp2;
-            if (p.out.trace_acc) p.out.trace_acc[s * C + c] = (uint8_t)acc;
+            if (p.out.trace_lp1) p.out.trace_lp1[(int64_t)s * C + c] = lp1;
+            if (p.out.trace_lp2) p.out.trace_lp2[(int64_t)s * C + c] = lp2;
+            if (p.out.trace_acc) p.out.trace_acc[(int64_t)s * C + c] = (uint8_t)acc;
             if (keep) {
                 const int64_t wc = p.st.wcount[c] + 1;
                 p.st.wcount[c] = wc;
@@ -290,22 +280,14 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
                     }
                 if (p.out.samples && c < p.out.n_sample_chains) {
 #pragma unroll
-                    for (int i = 0; i < D; ++i) p.out.samples[(row * D + i) * p.out.n_sample_chains + c] = x[i];
+                    for (int i = 0; i < D; ++i) p.out.samples[((int64_t)row * D + i) * p.out.n_sample_chains + c] = x[i];
                 }
-                if (p.out.lp_kept) p.out.lp_kept[row * C + c] = lp;
+                if (p.out.lp_kept) p.out.lp_kept[(int64_t)row * C + c] = lp;
             }
         }
         if (keep) row += 1;
     }
 
-    if (live && state_smem) {
-#pragma unroll
-        for (int i = 0; i < NT; ++i) p.st.V[(int64_t)i * C + c] = gV[i * sS];
-#pragma unroll
-        for (int i = 0; i < D; ++i) p.st.xav[(int64_t)i * C + c] = gxav[i * sS];
-#pragma unroll
-        for (int i = 0; i < NT; ++i) p.st.R[(int64_t)i * C + c] = gR[i * sS];
-    }
     if (live) {
 #pragma unroll
         for (int i = 0; i < D; ++i) p.st.x[i * C + c] = x[i];

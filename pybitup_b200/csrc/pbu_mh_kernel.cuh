@@ -27,7 +27,10 @@
 
 namespace pbu {
 
-constexpr int MH_MAX_BLOCK = 512;
+#ifndef PBU_MAX_BLOCK
+#define PBU_MAX_BLOCK 512
+#endif
+constexpr int MH_MAX_BLOCK = PBU_MAX_BLOCK;
 
 // ------------------------------------------------------------------------------------------------
 // Shared-memory staging of the point records with bulk TMA copies (cp.async.bulk + mbarrier).
