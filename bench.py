@@ -215,6 +215,9 @@ def run_gpu_arm(args):
     # ---- device-resident timing -----------------------------------------------------------------
     eng = ChainEngine(spec, cfg, C, device=local_rank)
     eng.init_chains(x0, p["prop_cov"])
+    geom = eng.launch_geometry()
+    coop = geom["chains_per_thread"] == geom["lanes"] and geom["lanes"] > 1      # teams of G lanes own G chains
+    kernel_name = "%s<PolyModel<4>,D=4,G=%d,ALGO=AM>" % ("mh_coop_kernel" if coop else "mh_step_kernel", geom["lanes"])
     out = None
     for _ in range(W):
         out = eng.run(T, thin=T, keep_samples=True, out=None)
@@ -315,7 +318,7 @@ def run_gpu_arm(args):
             "gpu_launches": K,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak, "traffic": None,
-                         "kernel": "mh_step_kernel<PolyModel<4>,4,G,adapt>",
+                         "kernel": kernel_name, "launch": geom,
                          "flops_per_chain_step": FLOPS_PER_CHAIN_STEP,
                          "peak_source": "live DFMA micro-benchmark on this GPU, sustained over ~0.7 s of back-to-back launches "
                                         "(pbu_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",

@@ -243,6 +243,11 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
         if (!fn) continue;
         int max_smem = 0;
         cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device);
+        cudaFuncAttributes fattr;
+        CUDA_TRY(cudaFuncGetAttributes(&fattr, fn));
+        if ((int)fattr.sharedSizeBytes > PBU_STATIC_SMEM_RESERVE)
+            return fail(PBU_ERR_UNSUPPORTED, "a step kernel uses %zu B of static shared memory, more than the %d B reserved", fattr.sharedSizeBytes, PBU_STATIC_SMEM_RESERVE);
+        max_smem -= PBU_STATIC_SMEM_RESERVE;
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         const bool adaptive = algo == PBU_ALGO_AM || algo == PBU_ALGO_DRAM;
         const size_t rec_aligned = (e->smem_bytes + 127) & ~(size_t)127;
@@ -317,6 +322,8 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
     if (pr->n_unc < 1 || pr->n_unc > PBU_MAX_DIM || pr->n_param < pr->n_unc || pr->n_param > PBU_MAX_PARAM)
         return fail(PBU_ERR_INVALID, "bad parameter counts P=%d d=%d", pr->n_param, pr->n_unc);
     if (pr->n_points < 1 || pr->n_runs < 1) return fail(PBU_ERR_INVALID, "need n_points >= 1 and n_runs >= 1");
+    if (pr->model == PBU_MODEL_ARRHENIUS && !(pr->consts[0] > 0.0 && pr->consts[1] > 0.0 && pr->consts[2] > 0.0))
+        return fail(PBU_ERR_INVALID, "the Arrhenius model needs T0 > 0, dT > 0 (a heating ramp) and beta > 0");
     if (!pr->theta_nom || !pr->unc_idx || !pr->y || !pr->std_y || !pr->lb || !pr->ub) return fail(PBU_ERR_INVALID, "null problem array");
     int nd;
     switch (pr->model) {
@@ -411,6 +418,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
     // resident when every record fits in shared memory, otherwise streamed in tiles through a 2-slot ring
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    max_smem -= PBU_STATIC_SMEM_RESERVE;          // a model's lookup tables live in static shared memory
     auto plan_tiles = [&](size_t rec_bytes, int want_tile, int &tile_points, size_t &smem) {
         const size_t all = (size_t)pr->n_points * rec_bytes;
         if (want_tile <= 0 && 128 + all <= (size_t)max_smem) {

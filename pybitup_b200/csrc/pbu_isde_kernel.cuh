@@ -200,6 +200,7 @@ template <class M, int D, int G, int Q, bool STREAM>
 __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) isde_step_kernel(const __grid_constant__ IsdeParams p) {
     constexpr int NT = tri_size(D);
     TileStream<M::NC> ts;
+    M::block_init();
     ts.init(p.prob.records, p.prob.n_points, p.tile_points);
 
     const int64_t C = p.st.n_chains;
@@ -408,6 +409,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) isde_step_kernel(const __grid
 template <class M, int D, int G, int Q, bool STREAM>
 __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) hmc_step_kernel(const __grid_constant__ IsdeParams p) {
     TileStream<M::NC> ts;
+    M::block_init();
     ts.init(p.prob.records, p.prob.n_points, p.tile_points);
 
     const int64_t C = p.st.n_chains;
@@ -631,6 +633,7 @@ template <class M, int D>
 __global__ void __launch_bounds__(256) eval_grad_kernel(const __grid_constant__ ProblemDev prob, const double *X /*[d][S]*/, int64_t S,
                                                         double *G_out /*[d][S]*/, int tile_points, int fd_gradient) {
     TileStream<M::NC> ts;
+    M::block_init();
     ts.init(prob.records, prob.n_points, tile_points);
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool livet = t < S;

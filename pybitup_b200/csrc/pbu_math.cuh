@@ -9,6 +9,7 @@
 #include <stdint.h>
 #include <string.h>
 #include <math.h>
+#include "pbu_math_tables.h"
 
 #ifdef __CUDACC__
 #define PBU_HD __host__ __device__ __forceinline__
@@ -107,6 +108,73 @@ PBU_HD double pbu_log(double u) {
     // e ln2_hi + (2s + (s z q + e ln2_lo)): e*ln2_hi is exact (32-bit hi, |e| < 2^11)
     const double lo = fma(s * z, q, ef * 1.9082149292705877e-10);
     return fma(ef, 0.6931471803691238, fma(2.0, s, lo));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Table-driven variants: the same functions at 10 FP64 instructions each (against 17 and 22), paid for with one
+// shared-memory load.  The FP64 pipe is what bounds the ODE models, the load/store pipe is idle there.
+//   pbu_exp_tab : x = (64 k + j) ln2/64 + r, |r| <= ln2/128;  exp(x) = 2^k T[j] (1 + r + r^2 P3(r)),  T[j] = 2^(j/64)
+//   pbu_log_tab : u = 2^e m, m in [1, 2), i = top 7 mantissa bits;  r = m c_i - 1, |r| <= 2^-8 (one FMA, exact to
+//                 rounding);  log u = e ln2 - ln c_i + (r - r^2/2 + ... - r^6/6)
+// Tables: pbu_math_tables.h (generated by tools/gen_math_tables.py), 64 + 2*128 doubles.  On the device the kernels
+// stage them in shared memory once per block (Model::block_init) and pass the pointer; on the host the static copy.
+// Checked against libm in tools/test_math.cu: exp <= 1 ulp; log <= 1 ulp of max(|log u|, 1) -- the error that
+// matters for exp(n log u) is the absolute one (c_127 = 1/2 keeps it below 6e-17 for u just below 1).
+#define PBU_MATH_TABLE_DOUBLES (64 + 256)
+static const double pbu_math_tables_host[PBU_MATH_TABLE_DOUBLES] = {PBU_EXP2_TABLE, PBU_LOG_TABLE};
+#ifdef __CUDACC__
+static __device__ const double pbu_math_tables_dev[PBU_MATH_TABLE_DOUBLES] = {PBU_EXP2_TABLE, PBU_LOG_TABLE};
+#endif
+
+// tab: the PBU_MATH_TABLE_DOUBLES doubles above (exp2 table first).  Domain x < 709; x <= -708 (and -inf) returns a
+// denormal (< 5e-309) instead of the exact tail: the range test and the result selection are integer instructions, the
+// FP64 pipe sees the ten arithmetic ones only.  NaN propagates.
+PBU_HD double pbu_exp_tab(double x, const double *tab) {
+    const bool tiny = (uint32_t)(hi_word(x) - (int32_t)0xC0862000) <= 0x3F69E000u;      // -inf <= x <= -708
+    const double SHIFT = 6755399441055744.0;
+    const double t = fma(x, 92.33248261689366, SHIFT);           // 64 / ln2
+    const double kf = t - SHIFT;                                 // 64 k + j as a double
+    const int32_t m = (int32_t)(uint32_t)(
+#ifdef __CUDA_ARCH__
+        __double2loint(t)
+#else
+        [](double v) { uint64_t b; memcpy(&b, &v, 8); return (int32_t)(uint32_t)b; }(t)
+#endif
+    );
+    double r = fma(kf, -0.6931471803691238 / 64.0, x);           // (ln2/64)_hi keeps 32 significant bits: kf * hi exact
+    r = fma(kf, -1.9082149292705877e-10 / 64.0, r);
+    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    const double v = fma(r * r, p, r);                           // exp(r) - 1, remainder r^6/720 < 4e-17
+    const double T = tab[m & 63];
+    const double e = fma(T, v, T);
+    const int32_t rh = hi_word(e) + ((m >> 6) << 20);            // * 2^k on the exponent field (k >= -1022 here)
+    return with_hi_word(e, tiny ? 0 : rh);
+}
+
+// true for positive, normal, finite u: the arguments pbu_log_tab accepts (an integer test)
+PBU_HD bool pbu_log_arg_ok(double u) { return (uint32_t)(hi_word(u) - 0x00100000) < 0x7FE00000u; }
+
+PBU_HD double pbu_log_tab(double u, const double *tab) {
+    const int32_t hi = hi_word(u);
+    const int32_t e = (hi >> 20) - 1023;
+    const int32_t i = (hi >> 13) & 127;
+    const double m = with_hi_word(u, (hi & 0x000fffff) | 0x3ff00000);
+#ifdef __CUDA_ARCH__
+    const double2 cl = reinterpret_cast<const double2 *>(tab + 64)[i];
+    const double c = cl.x, nlc = cl.y;
+#else
+    const double c = tab[64 + 2 * i], nlc = tab[64 + 2 * i + 1];
+#endif
+    const double r = fma(m, c, -1.0);
+    double q = fma(r, -1.0 / 6.0, 0.2);
+    q = fma(q, r, -0.25);
+    q = fma(q, r, 1.0 / 3.0);
+    q = fma(q, r, -0.5);
+    const double ef = (double)e;
+    const double lo = fma(r * r, q, fma(ef, 1.9082149292705877e-10, r));
+    return fma(ef, 0.6931471803691238, nlc + lo);                // e*ln2_hi exact inside the FMA: one rounding at full size
 }
 
 }  // namespace pbu

@@ -304,6 +304,7 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
 template <class M, int D, int G, int ALGO, bool STREAM, bool MIXED>
 __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_coop_kernel(const __grid_constant__ MhParams p) {
     TileStream<M::NC> ts;
+    M::block_init();
     ts.init(p.prob.records, p.prob.n_points, p.tile_points);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;

@@ -627,6 +627,7 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
 template <class M, int D, int G, int ALGO, int Q, bool STREAM, bool MIXED>
 __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_constant__ MhParams p) {
     TileStream<M::NC> ts;
+    M::block_init();
     ts.init(p.prob.records, p.prob.n_points, p.tile_points);
     const int lane = threadIdx.x & 31;
     if constexpr (!MIXED) {
@@ -652,6 +653,7 @@ template <class M, int D>
 __global__ void __launch_bounds__(256) eval_logpost_kernel(const __grid_constant__ ProblemDev prob, const double *X /*[d][S]*/, int64_t S,
                                                            double *lp_out, int tile_points) {
     TileStream<M::NC> ts;
+    M::block_init();
     ts.init(prob.records, prob.n_points, tile_points);
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool livet = t < S;
@@ -669,6 +671,7 @@ template <class M, int D>
 __global__ void __launch_bounds__(256) eval_model_kernel(const __grid_constant__ ProblemDev prob, const double *X /*[d][S]*/, int64_t S,
                                                          double *f_out, int tile_points) {
     TileStream<M::NCR> ts;
+    M::block_init();
     ts.init(prob.raw, prob.n_points, tile_points);
     const int n_tl = TileStream<M::NCR>::n_tiles(prob.n_points, tile_points);
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -47,6 +47,7 @@ struct LinearModel {
 #pragma unroll
         for (int j = 0; j < P; ++j) c.th[j] = theta[j];
     }
+    __device__ __forceinline__ static void block_init() {}
     __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const ProblemDev &) {}
     // written stage-by-stage across the U points so that the U dependency chains interleave in program order
     template <int U>
@@ -92,6 +93,7 @@ struct PolyModel {
 #pragma unroll
         for (int j = 0; j < P; ++j) c.th[j] = theta[j];
     }
+    __device__ __forceinline__ static void block_init() {}
     __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const ProblemDev &) {}
     template <int U>
     __device__ __forceinline__ static void resid_batch(const Ctx &c, Seq &, const double (&rec)[U][NC], double (&t)[U]) {
@@ -146,7 +148,7 @@ struct ArrheniusModel {
         double alpha, g0;
     };
     __device__ __forceinline__ static void begin(Ctx &c, const double (&theta)[4], const ProblemDev &p) {
-        c.c0 = 2.302585092994046 * theta[0] - log(p.consts[2]);   // ln(10)*log10A - ln(beta)
+        c.c0 = 2.302585092994046 * theta[0] - log(p.consts[2]) + log(p.consts[1]);   // ln(10)*log10A - ln(beta) + ln(h)
         c.ER = theta[1] / R_GAS;
         c.n = theta[2];
         c.F = theta[3];
@@ -157,24 +159,39 @@ struct ArrheniusModel {
         s.alpha = 0.0;
         s.g0 = c.g_start;
     }
-    // u^n for u in (0, 1] as exp(n log u) with the lean pbu_exp / pbu_log (pbu_math.cuh): relative error below 1e-14
-    // against pow() (tools/test_math.cu), far inside the 1e-10 parity bar, at a quarter of pow()'s instructions
-    __device__ __forceinline__ static double pw(double u, double n) {
-        const bool pos = u > 2.3e-308;                           // branch-free: evaluate on a safe argument, select at the end
-        const double v = pbu_exp(n * pbu_log(pos ? u : 1.0));
-        return pos ? v : 0.0;
+    // exp / log lookup tables of pbu_math.cuh, staged once per block (every kernel calls block_init before its first
+    // __syncthreads): 2.5 KB of static shared memory
+    __device__ __forceinline__ static double *tables() {
+        __shared__ __align__(16) double tab[PBU_MATH_TABLE_DOUBLES];
+        return tab;
     }
+    __device__ __forceinline__ static void block_init() {
+        double *t = tables();
+        for (int i = threadIdx.x; i < PBU_MATH_TABLE_DOUBLES; i += blockDim.x) t[i] = pbu_math_tables_dev[i];
+    }
+    // u^n for u in (0, 1] as exp(n log u) with the table-driven pbu_exp_tab / pbu_log_tab (pbu_math.cuh): relative
+    // error below 1e-14 against pow() (tools/test_math.cu), far inside the 1e-10 parity bar, at 22 FP64 instructions
+    // u <= 0 (conversion complete, or overshot by a stage), denormal or NaN u: 0.  The log of such an argument is finite
+    // garbage, discarded by the selection; no FP64 instruction is spent on the test.
+    __device__ __forceinline__ static double pw(double u, double n) {
+        const double v = pbu_exp_tab(n * pbu_log_tab(u, tables()), tables());
+        return pbu_log_arg_ok(u) ? v : 0.0;
+    }
+    // One RK4 step of d(alpha)/dT = g(T) (1 - alpha)^n.  c.c0 carries ln(h) (see begin): the exponentials return the
+    // stage rates already multiplied by the step.  Written on u = 1 - alpha for the stage arguments; this differs from
+    // the oracle's 1 - (alpha + k/2) by rounding only (<= 2 ulp of u), far inside the 1e-10 parity bar.
     __device__ __forceinline__ static double step(const Ctx &c, Seq &s, double inv_mid, double inv_end) {
-        const double gm = pbu_exp(c.c0 - c.ER * inv_mid);
-        const double g1 = pbu_exp(c.c0 - c.ER * inv_end);
+        const double gm = pbu_exp_tab(fma(-c.ER, inv_mid, c.c0), tables());
+        const double g1 = pbu_exp_tab(fma(-c.ER, inv_end, c.c0), tables());
         const double a = s.alpha;
-        const double k1 = c.h * s.g0 * pw(1.0 - a, c.n);
-        const double k2 = c.h * gm * pw(1.0 - (a + 0.5 * k1), c.n);
-        const double k3 = c.h * gm * pw(1.0 - (a + 0.5 * k2), c.n);
-        const double k4 = c.h * g1 * pw(1.0 - (a + k3), c.n);
-        s.alpha = fma(k1 + 2.0 * k2 + 2.0 * k3 + k4, 1.0 / 6.0, a);     // (.)/6 as a multiplication: <= 1 ulp from the oracle's division
+        const double u0 = 1.0 - a;
+        const double k1 = s.g0 * pw(u0, c.n);
+        const double k2 = gm * pw(fma(-0.5, k1, u0), c.n);
+        const double k3 = gm * pw(fma(-0.5, k2, u0), c.n);
+        const double k4 = g1 * pw(u0 - k3, c.n);
+        s.alpha = fma((k1 + k4) + 2.0 * (k2 + k3), 1.0 / 6.0, a);
         s.g0 = g1;
-        return 1.0 - c.F * s.alpha;
+        return fma(-c.F, s.alpha, 1.0);
     }
     template <int U>
     __device__ __forceinline__ static void resid_batch(const Ctx &c, Seq &s, const double (&rec)[U][NC], double (&t)[U]) {
@@ -213,6 +230,7 @@ struct HeatModel {
         c.c2 = phi / (k * gamma) + c1;
         c.T_amb = th[3];
     }
+    __device__ __forceinline__ static void block_init() {}
     __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const ProblemDev &) {}
     __device__ __forceinline__ static double value(const Ctx &c, Seq &, const double *raw) {
         const double x = raw[0];
@@ -250,6 +268,7 @@ struct SoizeModel {
         c.t0 = 5.477225575051661 * a;          // sqrt(30)
         c.t1 = 1.4142135623730951 * (b * b);   // sqrt(2)
     }
+    __device__ __forceinline__ static void block_init() {}
     __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const ProblemDev &) {}
     __device__ __forceinline__ static double value(const Ctx &c, Seq &, const double *raw) { return (raw[0] == 0.0) ? c.t0 : c.t1; }
     template <int U>

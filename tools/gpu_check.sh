@@ -10,8 +10,8 @@ python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2>&1; echo "ref rc=$?"; cat $OUT/bench_ref_$TAG.json
 timeout 600 python tools/bench_configs.py > $OUT/configs_$TAG.log 2>&1; echo "configs rc=$?"; cut -c1-400 $OUT/configs_$TAG.log
 python bench.py --steps 3 --warmup 3 --no-cpu --iters 100 > $OUT/plain_$TAG.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'mh_step|eval_|broadcast|fill|elementwise|Fill' -c 60 --csv --log-file $OUT/launches_$TAG.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'mh_step|mh_coop|eval_|broadcast|fill|elementwise|Fill' -c 60 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu --iters 100 > $OUT/ncu_launches_$TAG.log 2>&1; echo "ncu launches rc=$?"
 python tools/profile_one.py cubic 100 3 > $OUT/plain2_$TAG.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:mh_step -s 1 -c 1 -f -o $OUT/prof_cubic_$TAG \
+ncu --set full --clock-control none --import-source on -k regex:'mh_step|mh_coop' -s 1 -c 1 -f -o $OUT/prof_cubic_$TAG \
     python tools/profile_one.py cubic 100 3 > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
