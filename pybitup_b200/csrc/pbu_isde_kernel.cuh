@@ -197,7 +197,7 @@ __device__ __forceinline__ void grad_log_like(const double (&x)[Q][D], const Pro
 }
 
 template <class M, int D, int G, int Q, bool STREAM>
-__global__ void __launch_bounds__(MH_MAX_BLOCK, 1) isde_step_kernel(const __grid_constant__ IsdeParams p) {
+__global__ void __launch_bounds__(MH_MAX_BLOCK, M::MIN_BLOCKS) isde_step_kernel(const __grid_constant__ IsdeParams p) {
     constexpr int NT = tri_size(D);
     TileStream<M::NC> ts;
     M::block_init();
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, 1) isde_step_kernel(const __grid
 // end of the trajectory comes from the same data pass as the last gradient.
 // ------------------------------------------------------------------------------------------------
 template <class M, int D, int G, int Q, bool STREAM>
-__global__ void __launch_bounds__(MH_MAX_BLOCK, 1) hmc_step_kernel(const __grid_constant__ IsdeParams p) {
+__global__ void __launch_bounds__(MH_MAX_BLOCK, M::MIN_BLOCKS) hmc_step_kernel(const __grid_constant__ IsdeParams p) {
     TileStream<M::NC> ts;
     M::block_init();
     ts.init(p.prob.records, p.prob.n_points, p.tile_points);

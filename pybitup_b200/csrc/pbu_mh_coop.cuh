@@ -302,7 +302,7 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
 // Cooperative kernel: teams of G lanes own G chains.  MIXED: from warp p.n_full_warps on, teams are 2G lanes wide (and
 // still own G chains): half a unit of work per warp, for scheduler-level balance (see mh_step_kernel).
 template <class M, int D, int G, int ALGO, bool STREAM, bool MIXED>
-__global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_coop_kernel(const __grid_constant__ MhParams p) {
+__global__ void __launch_bounds__(MH_MAX_BLOCK, M::MIN_BLOCKS) mh_coop_kernel(const __grid_constant__ MhParams p) {
     TileStream<M::NC> ts;
     M::block_init();
     ts.init(p.prob.records, p.prob.n_points, p.tile_points);

@@ -625,7 +625,7 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
 // be spread evenly over the 592 warp schedulers of a B200 (3.46 each: the schedulers holding four set the pace);
 // three full warps and one half warp per scheduler can (3.5 units each).
 template <class M, int D, int G, int ALGO, int Q, bool STREAM, bool MIXED>
-__global__ void __launch_bounds__(MH_MAX_BLOCK, 1) mh_step_kernel(const __grid_constant__ MhParams p) {
+__global__ void __launch_bounds__(MH_MAX_BLOCK, M::MIN_BLOCKS) mh_step_kernel(const __grid_constant__ MhParams p) {
     TileStream<M::NC> ts;
     M::block_init();
     ts.init(p.prob.records, p.prob.n_points, p.tile_points);

@@ -39,6 +39,7 @@ struct LinearModel {
     static constexpr int UNROLL = (P <= 4) ? 4 : ((P <= 6) ? 3 : 2);
     static constexpr int OPS = P + 1;   // FP64 instructions per point and chain
     static constexpr int WF = P + 1;    // shared-memory wavefronts (8 B per lane) per point
+    static constexpr int MIN_BLOCKS = 1;   // resident blocks per SM the step kernels are compiled for (register cap)
     struct Ctx {
         double th[P];
     };
@@ -85,6 +86,7 @@ struct PolyModel {
     static constexpr int UNROLL = 4;
     static constexpr int OPS = P + 1;
     static constexpr int WF = 3;
+    static constexpr int MIN_BLOCKS = 1;   // resident blocks per SM the step kernels are compiled for (register cap)
     struct Ctx {
         double th[P];
     };
@@ -140,6 +142,7 @@ struct ArrheniusModel {
     static constexpr int UNROLL = 1;
     static constexpr int OPS = 400;     // two exp and four pow per RK4 step dominate
     static constexpr int WF = 4;
+    static constexpr int MIN_BLOCKS = 2;   // resident blocks per SM the step kernels are compiled for (register cap)
     static constexpr double R_GAS = 8.314462618;
     struct Ctx {
         double c0, ER, n, F, h, g_start;
@@ -216,6 +219,7 @@ struct HeatModel {
     static constexpr int UNROLL = 2;
     static constexpr int OPS = 60;      // two exp per point
     static constexpr int WF = 3;
+    static constexpr int MIN_BLOCKS = 1;   // resident blocks per SM the step kernels are compiled for (register cap)
     struct Ctx {
         double gamma, c1, c2, T_amb;
     };
@@ -259,6 +263,7 @@ struct SoizeModel {
     static constexpr int UNROLL = 1;
     static constexpr int OPS = 8;
     static constexpr int WF = 3;
+    static constexpr int MIN_BLOCKS = 1;   // resident blocks per SM the step kernels are compiled for (register cap)
     struct Ctx {
         double t0, t1;
     };

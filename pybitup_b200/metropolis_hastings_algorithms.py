@@ -14,6 +14,7 @@ of the caller's ``param_init`` to the final state.  Random numbers come from Phi
 uses the unseeded stdlib generator), so chains agree with the reference statistically; arithmetic parity with
 injected streams is what ``tests/test_gpu_parity.py`` checks through the C ABI.
 """
+import os
 import time
 
 import numpy as np
@@ -69,6 +70,29 @@ def compute_hessian_fd(fun_batch, x, eps=0.01, compute_all_element=True, positiv
         H[i, j] = (f[k] - f[1 + 2 * i] - f[1 + 2 * j] + 2 * f0 - f[2 + 2 * i] - f[2 + 2 * j] + f[k + 1]) / (2 * delta[j] * delta[i])
         H[j, i] = H[i, j]
     return H
+
+
+def nearPD(A, nit=10):
+    """The reference's nearPD (mha.py:1253-1284, helpers :1214-1250), restated with plain arrays.
+
+    As written upstream it is Higham's alternating projections run on A ITSELF (the correlation matrix computed at
+    :1266 is overwritten by ``corr = A`` at :1267) with the identity weight: project on the positive semi-definite
+    cone by clipping eigenvalues (_getAplus; eigenvectors from the general ``eig``), then put ones on the diagonal
+    (_getPu with W = I), ``nit`` times; the result is finally scaled by sigma_i sigma_j, sigma = sqrt|diag A|."""
+    A = np.asarray(A, dtype=np.float64)
+    n = A.shape[0]
+    sigma = np.sqrt(np.abs(np.diag(A)))
+    W = np.identity(n)
+    delta_s = 0
+    Yk = A.copy()
+    for _ in range(nit):
+        Rk = Yk - delta_s
+        eigval, Q = np.linalg.eig(Rk)                          # _getPs with W = I is _getAplus
+        Xk = (Q @ np.diag(np.maximum(eigval, 0)) @ Q.T)
+        delta_s = Xk - Rk
+        Yk = np.array(Xk, copy=True)
+        Yk[W > 0] = W[W > 0]                                   # _getPu
+    return Yk * np.outer(sigma, sigma)                         # computeCovMat
 
 
 class _DeviceSampler:
@@ -290,10 +314,15 @@ class _GradientSampler(_DeviceSampler):
             self.V = None
         elif value == "Matrix":                                              # :689-693
             self.V = np.array(self.C_matrix["matrix_value"], dtype=np.float64)
-        elif value not in ("Hessian", "Hessian_diag"):                       # :653-660, computed in _proposal_matrix
-            from ._capi import UnsupportedProblem, PBU_ERR_UNSUPPORTED
-            raise UnsupportedProblem(PBU_ERR_UNSUPPORTED, 'preconditioner "{}" is not available on the device path '
-                                     '(Identity, Matrix, Hessian, Hessian_diag are)'.format(value))
+        elif value == "from_file":                                           # :694-697 (the generalised eigenproblem it
+            path = os.path.join(str(self.IO_util['path']['cwd']), "cov.csv")      # then prints, :699-706, is diagnostics only)
+            self.V = np.atleast_2d(np.loadtxt(path, delimiter=",", dtype=np.float64))
+        elif value == "PSD":                                                 # :674-678: estimate_hessian_model hard-codes
+            from ._capi import UnsupportedProblem, PBU_ERR_UNSUPPORTED        # a 14-species chemistry model
+            raise UnsupportedProblem(PBU_ERR_UNSUPPORTED, 'preconditioner "PSD" is not available on the device path '
+                                     '(Identity, Matrix, from_file, Hessian, Hessian_diag, nearPD are)')
+        elif value not in ("Hessian", "Hessian_diag", "nearPD"):             # :653-660, :679-684, computed in _proposal_matrix
+            raise ValueError('Unknown matrix type "{}" for estimating the conditioning matrix G .'.format(value))     # :708
         self.starting_it = int(self.C_matrix['starting_it'])
         self.update_it = int(self.C_matrix['update_it'])
         self.end_it = int(self.C_matrix['end_it']) if self.C_matrix.get("end_it") is not None else self.nIterations + 1
@@ -302,10 +331,12 @@ class _GradientSampler(_DeviceSampler):
         """C_approx: identity, a given matrix, or the inverse of minus the finite-difference Hessian of the
         log-posterior at the initial point (mha.py:653-660), its stencil evaluated in one device batch."""
         value = self.C_matrix.get("value", "Identity")
-        if value in ("Hessian", "Hessian_diag"):
+        if value in ("Hessian", "Hessian_diag", "nearPD"):
             self.hess_mat = -compute_hessian_fd(eng.log_posterior, np.array(self.param_init, dtype=np.float64), eps=0.001,
-                                                compute_all_element=(value == "Hessian"))
+                                                compute_all_element=(value != "Hessian_diag"))
             self.V = np.linalg.inv(self.hess_mat)
+            if value == "nearPD":                                            # :679-684
+                self.V = nearPD(self.V)
         return self.V
 
 
@@ -331,7 +362,7 @@ class HamiltonianMonteCarlo(_GradientSampler):
 
 class ito_SDE(_GradientSampler):
     """Ito-SDE sampler (mha.py:886-1040) with the GradientBasedMCMC preconditioner options the device supports:
-    covariance.value in {"Identity", "Matrix", "Hessian", "Hessian_diag"}."""
+    covariance.value in {"Identity", "Matrix", "from_file", "Hessian", "Hessian_diag", "nearPD"}."""
     algo_name = "ISDE"
 
     def __init__(self, IO_fileID, nIterations, param_init, prob_distr, C_matrix, gradient, h, f0, opt_arg):

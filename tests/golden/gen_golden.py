@@ -319,8 +319,31 @@ def gen_hessian_fd():
     np.savez(os.path.join(HERE, "_hessian_fd.npz"), A=A, x=x, **out)
 
 
+def gen_near_pd():
+    """nearPD (mha.py:1253-1284) on an indefinite symmetric matrix, a positive definite one and a badly scaled
+    inverse-Hessian-like one; pins pybitup_b200.metropolis_hastings_algorithms.nearPD."""
+    import warnings
+    rng = np.random.default_rng(5)
+    mats = {}
+    B = rng.standard_normal((4, 4))
+    mats["indefinite"] = (B + B.T) / 2.0
+    mats["pd"] = B @ B.T + 0.5 * np.eye(4)
+    S = np.diag([1e-3, 2.0, 40.0])
+    C = np.array([[1.0, 0.95, -0.9], [0.95, 1.0, 0.2], [-0.9, 0.2, 1.0]])          # not a valid correlation matrix
+    mats["scaled"] = S @ C @ S
+    out = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                     # np.matrix PendingDeprecationWarning
+        for k, A in mats.items():
+            out["A_" + k] = A
+            out["Y_" + k] = np.asarray(mha.nearPD(A.copy()))
+    np.savez(os.path.join(HERE, "_near_pd.npz"), **out)
+
+
 if __name__ == "__main__":
-    if "--hessian" in sys.argv:
+    if "--nearpd" in sys.argv:
+        gen_near_pd()
+    elif "--hessian" in sys.argv:
         gen_hessian_fd()
     elif "--hmc" in sys.argv:
         gen_hmc()
@@ -328,3 +351,4 @@ if __name__ == "__main__":
         main()
         gen_hmc()
         gen_hessian_fd()
+        gen_near_pd()

@@ -115,7 +115,8 @@ def test_sampling_and_propagation_from_json(tmp_path, monkeypatch):
     assert np.allclose(iv["upper_bound"], fe.max(axis=0), rtol=1e-11) and len(ci) == 29
 
 
-def test_isde_from_json_on_cubic(tmp_path, monkeypatch):
+@pytest.mark.parametrize("precond", ["Hessian_diag", "Hessian", "nearPD", "from_file"])
+def test_isde_from_json_on_cubic(tmp_path, monkeypatch, precond):
     from pybitup_b200 import synthetic, bayesian_inference as bi
     from pybitup_b200.solve_problem import Sampling
     monkeypatch.chdir(tmp_path)
@@ -133,10 +134,14 @@ def test_isde_from_json_on_cubic(tmp_path, monkeypatch):
                                                       for n, v in zip(["c0", "c1", "c2", "c3"], [1.0, -2.0, 0.5, 3.0])}},
         "Likelihood": {"function": "Gaussian"}},
         "Algorithm": {"name": "ISDE", "n_iterations": T, "n_chains": 32, "seed": 5, "save_eval_freq": 1e9,
-                      "covariance": {"value": "Hessian_diag", "starting_it": 200, "update_it": 50, "end_it": 1000},
+                      "covariance": {"value": precond, "starting_it": 200, "update_it": 50, "end_it": 1000},
                       "gradient": "Analytical", "ISDE": {"h": 0.3, "f0": 4.0}}}}
     with open("cubic.json", "w") as f:
         json.dump(cfg, f)
+    x = p["design"]["x"]
+    if precond == "from_file":          # ./cov.csv of an earlier run (mha.py:694-697): here the exact posterior covariance
+        Phi0 = np.stack([x ** j for j in range(4)], axis=1)
+        np.savetxt("cov.csv", np.linalg.inv(Phi0.T @ Phi0) * 0.1 ** 2, delimiter=",")
     job = Sampling("cubic.json")
     run = job.sample({"cubic": Cubic()})
     job.close()
@@ -144,7 +149,6 @@ def test_isde_from_json_on_cubic(tmp_path, monkeypatch):
     aux = pd.read_csv("output/aux_variables.csv", header=None).values
     assert aux.shape == (T * 4, 2) and np.all(aux[:4, 0] == 0.0)          # first rows: P_0 = 0, xi_0
     # posterior of a linear-Gaussian problem: mean = least squares solution, cov = (Phi^T Phi)^-1 sigma^2
-    x = p["design"]["x"]
     Phi = np.stack([x ** j for j in range(4)], axis=1)
     cov = np.linalg.inv(Phi.T @ Phi) * 0.1 ** 2
     mean = cov @ Phi.T @ p["y"][0] / 0.1 ** 2

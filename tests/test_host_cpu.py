@@ -143,3 +143,37 @@ def test_hessian_fd_matches_reference_golden():
         for pos in (True, False):
             H = compute_hessian_fd(f, x, eps=0.001, compute_all_element=full, positive_diag=pos)
             assert np.array_equal(H, g["H_%d_%d" % (full, pos)])
+
+
+def test_near_pd_matches_reference_golden():
+    """nearPD vs the reference's (recorded by tests/golden/gen_golden.py --nearpd), bit for bit."""
+    from pybitup_b200.metropolis_hastings_algorithms import nearPD
+    g = np.load(os.path.join(ROOT, "tests", "golden", "_near_pd.npz"))
+    for k in ("indefinite", "pd", "scaled"):
+        Y = nearPD(g["A_" + k])
+        assert np.array_equal(Y, g["Y_" + k]), k
+        assert np.allclose(np.diag(Y), np.abs(np.diag(g["A_" + k])))          # unit diagonal scaled back by sigma^2
+
+
+def test_gradient_sampler_preconditioner_options(tmp_path):
+    """covariance.value: Matrix / from_file are read on the host, PSD is refused loudly, anything else is the
+    reference's ValueError (mha.py:708)."""
+    from pybitup_b200 import _capi
+    from pybitup_b200.metropolis_hastings_algorithms import ito_SDE
+    C = np.array([[2.0, 0.3], [0.3, 1.0]])
+    np.savetxt(tmp_path / "cov.csv", C, delimiter=",")
+    io = {"fileID": {}, "path": {"cwd": tmp_path, "out_folder": tmp_path}}
+    base = {"starting_it": 10, "update_it": 5}
+
+    def mk(value, **extra):
+        s = ito_SDE.__new__(ito_SDE)
+        s.IO_util, s.nIterations = io, 100
+        s._setup_gradient(dict(base, value=value, **extra), "Analytical")
+        return s
+    assert np.array_equal(mk("from_file").V, C)
+    assert np.array_equal(mk("Matrix", matrix_value=C.tolist()).V, C)
+    assert mk("nearPD").end_it == 101
+    with pytest.raises(_capi.UnsupportedProblem):
+        mk("PSD")
+    with pytest.raises(ValueError, match="Unknown matrix type"):
+        mk("Cholesky")

@@ -14,6 +14,10 @@ from pybitup_b200.engine import ChainEngine, ProblemSpec, SamplerConfig      # n
 from pybitup_b200.propagation import DevicePropagation                      # noqa: E402
 
 
+FP64_INST_RK4 = 119          # DFMA + DMUL + DADD in the RK4 loop of mh_step_kernel<ArrheniusModel,...> (cuobjdump -sass)
+FP64_INST_RK4_EVAL = 117     # same loop in eval_model_kernel<ArrheniusModel, 4> (no residual / sum of squares)
+
+
 def timed_runs(eng, steps, reps):
     eng.run(steps, thin=steps, keep_samples=False)
     eng.synchronize()
@@ -68,7 +72,10 @@ def main():
             r = C * 20 / (ms * 1e-3)
             print(json.dumps({"cfg": 3, "what": "Arrhenius RK4x500 DRAM, 262,144 chains x 20 iterations", "geom": eng.launch_geometry(), "ms": ms,
                               "chain_steps_per_s": r, "evals_per_step": ev, "tflops_alg": r * ev * 2.17e4 / 1e12,
-                              "frac_fp64_alg": r * ev * 2.17e4 / 1e12 / peak}))
+                              "frac_fp64_alg": r * ev * 2.17e4 / 1e12 / peak,
+                              # the kernel's RK4 step is 119 FP64 instructions (cuobjdump -sass; 2 exp + 4 pow by table-driven
+                              # exp / log): issue slots of the FP64 pipe in use, each counted as one DFMA (2 flops)
+                              "fp64_inst_per_rk4_step": FP64_INST_RK4, "frac_fp64_issue": r * ev * 500 * FP64_INST_RK4 * 2 / 1e12 / peak}))
     if "4" in which:
         p = synthetic.regression_problem()
         C = 131072           # 1,048,576 chains over 8 GPUs
@@ -97,6 +104,7 @@ def main():
                 print(json.dumps({"cfg": 5, "what": "Arrhenius propagation, 1.25e7 samples x 500 points, evaluations in HBM (50 GB)",
                                   "eval_s": t1 - t0, "statistics_s": t2 - t1, "samples_per_s_eval": S / (t1 - t0),
                                   "samples_per_s_total": S / (t2 - t0), "tflops_alg_eval": S * 2.15e4 / (t1 - t0) / 1e12,
+                                  "frac_fp64_issue_eval": S * 500 * FP64_INST_RK4_EVAL * 2 / (t1 - t0) / 1e12 / peak,
                                   "hbm_write_GBs": S * 4000 / (t1 - t0) / 1e9, "mean_first_last": [float(st["mean"][0]), float(st["mean"][-1])],
                                   "ci_last": [float(st["ci_lb"][-1]), float(st["ci_ub"][-1])]}))
 
