@@ -32,6 +32,7 @@ extern "C" {
 #define PBU_ABI_VERSION 1
 #define PBU_MAX_PARAM 16 /* max length of the full model parameter vector (P)   */
 #define PBU_MAX_DIM 16   /* max number of uncertain parameters (d)              */
+#define PBU_MAX_MODELS 4 /* max models (Likelihood.models) of one posterior     */
 
 typedef enum {
     PBU_OK = 0,
@@ -87,7 +88,18 @@ typedef struct {
     double log_const;         /* used when has_log_const != 0: constant added to -J/2 INSTEAD of the log-prior
                                  constant (sampling an analytic density, solve_problem.py:134-164)  */
     int32_t has_log_const;
-    int32_t pad0;
+    /* Several models in one likelihood (Likelihood.models / .data are dicts keyed by model id, summed at
+     * bayesian_inference.py:500-524).  n_models <= 1: one model, the fields above are all there is.  n_models > 1:
+     * the points of the models are CONCATENATED in design / y / std_y (model m owns points model_first[m] ..
+     * model_first[m] + model_count[m] - 1), all models are the same registered device model with the same P, and
+     * each has its own nominal parameters, name map and constants; theta_nom / unc_idx / consts above are ignored. */
+    int32_t n_models;
+    const int32_t *model_first;     /* host [n_models]                                                          */
+    const int32_t *model_count;     /* host [n_models]                                                          */
+    const double *model_theta_nom;  /* host [n_models][P]                                                       */
+    const int32_t *model_unc_idx;   /* host [n_models][d]: position inside that model's theta, -1 = not a
+                                       parameter of that model (Model.run_model's name search finds nothing)    */
+    const double *model_consts;     /* host [n_models][8]                                                       */
 } pbu_problem;
 
 /* Algorithm block: inference_problem.py:37-107 (JSON keys in SURVEY.md 9.2). */

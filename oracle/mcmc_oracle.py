@@ -45,6 +45,13 @@ class Problem:
     ub: np.ndarray                   # f64[d]
     gamma: float = 1.0
     design: dict = field(default_factory=dict)   # model specific (Phi | x | T0,dT,n_steps,beta)
+    # further models of the same likelihood (Likelihood.models is a dict, summed over at bayesian_inference.py:500-524):
+    # Problems that share lb / ub / gamma with this one; each has its own data, nominal parameters and name map
+    extra: list = field(default_factory=list)
+
+    @property
+    def members(self):
+        return [self] + list(self.extra)
 
     @property
     def d(self):
@@ -52,7 +59,7 @@ class Problem:
 
     @property
     def n_points(self):
-        return self.y.shape[1]
+        return sum(m.y.shape[1] for m in self.members)
 
     def full_theta(self, X):
         # Model.run_model: uncertain values written into the nominal vector (:361-369)
@@ -62,6 +69,12 @@ class Problem:
         return th
 
     def model_eval(self, X):
+        """Model outputs of every model of the likelihood, concatenated in order."""
+        if not self.extra:
+            return self.model_eval_one(X)
+        return np.concatenate([m.model_eval_one(X) for m in self.members])
+
+    def model_eval_one(self, X):
         th = self.full_theta(X)
         if self.model == "linear":
             return cpu_models.linear_design(th, self.design["Phi"])
@@ -100,12 +113,13 @@ def log_prior(prob, X):
 
 
 def arg_gauss_likelihood(prob, X):
-    """J = sum_runs sum_k ((y - f)/(std_y*gamma))^2   (bayesian_inference.py:495-542)."""
-    f = prob.model_eval(X)
+    """J = sum_models sum_runs sum_k ((y - f)/(std_y*gamma))^2   (bayesian_inference.py:495-542)."""
     J = 0
-    for c_run in range(prob.y.shape[0]):
-        arg_exp = (prob.y[c_run] - f) / (prob.std_y * prob.gamma)
-        J = J + np.sum(arg_exp ** 2, axis=0)
+    for m in prob.members:
+        f = m.model_eval_one(X)
+        for c_run in range(m.y.shape[0]):
+            arg_exp = (m.y[c_run] - f) / (m.std_y * prob.gamma)
+            J = J + np.sum(arg_exp ** 2, axis=0)
     return J
 
 
@@ -121,14 +135,15 @@ def log_post(prob, X):
 def grad_log_post(prob, X):
     """Analytical gradient: compute_grad_log_value (:573-623) with inv_jac = I, det_jac = 1.
 
-    Only run 0 enters (:606-608) and the prior does not (:80-82).
+    Only run 0 enters (:606-608) and the prior does not (:80-82); the models of the likelihood add up (:596).
     """
-    f = prob.model_eval(X)
-    mg = prob.model_grad(X)
-    ss_x = (prob.y[0] - f) / (prob.std_y ** 2 * prob.gamma ** 2)
     grad = np.zeros(prob.d)
-    for i in range(prob.d):
-        grad[i] = grad[i] + np.matmul(ss_x, mg[i])
+    for m in prob.members:
+        f = m.model_eval_one(X)
+        mg = m.model_grad(X)
+        ss_x = (m.y[0] - f) / (m.std_y ** 2 * prob.gamma ** 2)
+        for i in range(prob.d):
+            grad[i] = grad[i] + np.matmul(ss_x, mg[i])
     return grad
 
 

@@ -35,7 +35,9 @@ class pbu_problem(C.Structure):
                 ("n_runs", C.c_int32), ("n_design_cols", C.c_int32),
                 ("theta_nom", _dp), ("unc_idx", _ip), ("design", _dp), ("y", _dp), ("std_y", _dp),
                 ("lb", _dp), ("ub", _dp), ("gamma", C.c_double), ("consts", C.c_double * 8),
-                ("log_const", C.c_double), ("has_log_const", C.c_int32), ("pad0", C.c_int32)]
+                ("log_const", C.c_double), ("has_log_const", C.c_int32), ("n_models", C.c_int32),
+                ("model_first", _ip), ("model_count", _ip), ("model_theta_nom", _dp), ("model_unc_idx", _ip),
+                ("model_consts", _dp)]
 
 
 class pbu_sampler_cfg(C.Structure):

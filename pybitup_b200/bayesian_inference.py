@@ -135,25 +135,55 @@ class Likelihood:
         self.model_eval = {}
 
     def lower(self, lb, ub):
-        """ProblemSpec of the (single) model/data pair with the box prior [lb, ub]."""
+        """ProblemSpec of the model/data pairs with the box prior [lb, ub].
+
+        Several models (the dicts are walked in key order, as arg_gauss_likelihood does at :500) become model blocks of
+        one device problem: same registered device model, same number of parameters and of runs; each keeps its own
+        nominal parameters, name map and design."""
         ids = list(self.models.keys())
-        if len(ids) != 1:
-            raise capi.UnsupportedProblem(capi.PBU_ERR_UNSUPPORTED,
-                                          "the device path handles one model per posterior, got {}".format(ids))
-        mid = ids[0]
-        model, data = self.models[mid], self.data[mid]
-        if model.input_file_name:
-            raise capi.UnsupportedProblem(capi.PBU_ERR_UNSUPPORTED, "external-solver models (input_file) cannot run on the device")
-        if model.device_model not in capi.MODEL_IDS:
-            raise capi.UnsupportedProblem(
-                capi.PBU_ERR_UNSUPPORTED,
-                "model class {} does not declare a registered device model (device_model = one of {}); "
-                "there is no CPU fallback".format(type(model).__name__, sorted(capi.MODEL_IDS)))
-        y = np.stack([np.asarray(data.y[r], dtype=np.float64) for r in range(data.n_runs)])
-        return ProblemSpec(model=model.device_model, theta_nom=np.array(model.param_nom, dtype=np.float64),
-                           unc_idx=model.uncertain_index(), y=y, std_y=np.asarray(data.std_y, dtype=np.float64),
+        if not ids:
+            raise capi.UnsupportedProblem(capi.PBU_ERR_UNSUPPORTED, "the likelihood has no model")
+        specs = []
+        for mid in ids:
+            model, data = self.models[mid], self.data[mid]
+            if model.input_file_name:
+                raise capi.UnsupportedProblem(capi.PBU_ERR_UNSUPPORTED, "external-solver models (input_file) cannot run on the device")
+            if model.device_model not in capi.MODEL_IDS:
+                raise capi.UnsupportedProblem(
+                    capi.PBU_ERR_UNSUPPORTED,
+                    "model class {} does not declare a registered device model (device_model = one of {}); "
+                    "there is no CPU fallback".format(type(model).__name__, sorted(capi.MODEL_IDS)))
+            y = np.stack([np.asarray(data.y[r], dtype=np.float64) for r in range(data.n_runs)])
+            specs.append(dict(model=model.device_model, theta_nom=np.array(model.param_nom, dtype=np.float64),
+                              unc_idx=model.uncertain_index(), y=y, std_y=np.asarray(data.std_y, dtype=np.float64),
+                              design=model.device_design()))
+        first = specs[0]
+        blocks = None
+        y, std_y = first["y"], first["std_y"]
+        if len(specs) > 1:
+            for sp in specs[1:]:
+                if (sp["model"] != first["model"] or sp["theta_nom"].shape != first["theta_nom"].shape
+                        or sp["y"].shape[0] != first["y"].shape[0]):
+                    raise capi.UnsupportedProblem(
+                        capi.PBU_ERR_UNSUPPORTED,
+                        "the models {} of one posterior must be the same registered device model with the same number of "
+                        "parameters and of data runs to be lowered together".format(ids))
+            blocks = [dict(theta_nom=sp["theta_nom"], unc_idx=sp["unc_idx"], design=sp["design"], n_points=sp["y"].shape[1])
+                      for sp in specs]
+            y = np.concatenate([sp["y"] for sp in specs], axis=1)
+            std_y = np.concatenate([sp["std_y"] for sp in specs])
+        return ProblemSpec(model=first["model"], theta_nom=first["theta_nom"], unc_idx=first["unc_idx"], y=y, std_y=std_y,
                            lb=np.asarray(lb, dtype=np.float64), ub=np.asarray(ub, dtype=np.float64),
-                           gamma=float(self.gamma), design=model.device_design())
+                           gamma=float(self.gamma), design=first["design"], blocks=blocks)
+
+    def model_slices(self):
+        """{model id: slice of the concatenated points} in the order lower() lays the models out."""
+        out, at = {}, 0
+        for mid in self.models.keys():
+            n = len(np.asarray(self.data[mid].std_y))
+            out[mid] = slice(at, at + n)
+            at += n
+        return out
 
 
 class BayesianPosterior:
@@ -203,6 +233,7 @@ class BayesianPosterior:
 
     def save_value(self, IO_util, current_it, model_eval):
         """output/model_eval/<id>_fun_eval-<it>.npy (Likelihood.write_fun_eval, :448-454)."""
+        slices = self.likelihood.model_slices()
         for model_id in self.likelihood.models.keys():
             p = pathlib.Path(IO_util['path']['fun_eval_folder'], f"{model_id}_fun_eval-{current_it}.npy")
-            np.save(p, model_eval)
+            np.save(p, np.asarray(model_eval)[slices[model_id]])

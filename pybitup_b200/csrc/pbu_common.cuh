@@ -13,6 +13,14 @@ namespace pbu {
 // small per-problem vectors live in the constant bank and indexing them with unrolled loop
 // counters costs nothing.
 // ------------------------------------------------------------------------------------------------
+// One model of the likelihood: its points are records first .. first + count - 1
+struct ModelBlockDev {
+    int32_t first, count;
+    int32_t unc_idx[PBU_MAX_DIM];     // -1: uncertain parameter i is not a parameter of this model
+    double theta_nom[PBU_MAX_PARAM];
+    double consts[8];
+};
+
 struct ProblemDev {
     const double *records;   // dev [N][NC]  likelihood records, pre-scaled by w = sqrt(n_runs)/(std_y*gamma) (pbu_models.cuh)
     const double *raw;       // dev [N][NCR] raw design records (Model.run_model / propagation)
@@ -29,6 +37,11 @@ struct ProblemDev {
     double ub[PBU_MAX_DIM];
     double log_prior_const;  // sum_i log(1/|ub_i-lb_i|)  (Mixture.compute_log_value, distributions.py:456-479)
     double consts[8];
+    // Likelihood.models (bayesian_inference.py:500-524): blk[0] repeats the fields above for a single model.  The
+    // replicated-layout kernels and the evaluation kernels walk the blocks; the cooperative kernel is single-model.
+    int32_t n_blocks;
+    int32_t pad_blocks;
+    ModelBlockDev blk[PBU_MAX_MODELS];
 };
 
 // Chain state, structure-of-arrays with stride = n_chains (coalesced for one thread per chain).

@@ -125,8 +125,19 @@ static const EvalKernelEntry *find_eval(int model, int P, int d) {
 
 // Lower the problem to the two record streams of pbu_models.cuh.  Several runs are folded exactly:
 // sum_r (y_r - f)^2 = n_r (ybar - f)^2 + sum_r (y_r - ybar)^2  (second term -> J_const).
-static void build_records(const pbu_problem *pr, int nc, int ncr, std::vector<double> &rec, std::vector<double> &raw, double &J_const) {
+struct HostBlock {          // one model of the likelihood (pbu_problem.n_models), or the whole problem
+    int first, count;
+    const double *theta_nom;
+    const int32_t *unc_idx;
+    const double *consts;
+};
+
+static void build_records(const pbu_problem *pr, const std::vector<HostBlock> &blocks, int nc, int ncr, std::vector<double> &rec,
+                          std::vector<double> &raw, double &J_const) {
     const int N = pr->n_points, nr = pr->n_runs, P = pr->n_param;
+    std::vector<int> block_of(N, 0);
+    for (size_t b = 0; b < blocks.size(); ++b)
+        for (int k = blocks[b].first; k < blocks[b].first + blocks[b].count; ++k) block_of[k] = (int)b;
     rec.assign((size_t)N * nc, 0.0);
     raw.assign((size_t)N * ncr, 0.0);
     J_const = 0.0;
@@ -154,10 +165,12 @@ static void build_records(const pbu_problem *pr, int nc, int ncr, std::vector<do
                 }
                 r[P] = wy;
                 break;
-            case PBU_MODEL_ARRHENIUS: {
-                const double T0 = pr->consts[0], dT = pr->consts[1];
-                q[0] = r[0] = 1.0 / (T0 + ((double)k + 0.5) * dT);
-                q[1] = r[1] = 1.0 / (T0 + ((double)k + 1.0) * dT);
+            case PBU_MODEL_ARRHENIUS: {          // every model has its own ramp; k counts from the start of the model's points
+                const HostBlock &hb = blocks[block_of[k]];
+                const double T0 = hb.consts[0], dT = hb.consts[1];
+                const double kr = (double)(k - hb.first);
+                q[0] = r[0] = 1.0 / (T0 + (kr + 0.5) * dT);
+                q[1] = r[1] = 1.0 / (T0 + (kr + 1.0) * dT);
                 r[2] = w;
                 r[3] = wy;
                 break;
@@ -221,6 +234,7 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
             if (coop && mixed && want_block > 0) continue;
         }
         if (coop && (isde || streamed)) continue;
+        if (coop && e->prob.n_blocks > 1) continue;          // the cooperative kernel evaluates one model
         if (want_lanes > 0 && g != want_lanes) continue;
         if (want_q > 0 && q != want_q) continue;
         if (sequential && g != 1) continue;
@@ -322,9 +336,25 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
     if (pr->n_unc < 1 || pr->n_unc > PBU_MAX_DIM || pr->n_param < pr->n_unc || pr->n_param > PBU_MAX_PARAM)
         return fail(PBU_ERR_INVALID, "bad parameter counts P=%d d=%d", pr->n_param, pr->n_unc);
     if (pr->n_points < 1 || pr->n_runs < 1) return fail(PBU_ERR_INVALID, "need n_points >= 1 and n_runs >= 1");
-    if (pr->model == PBU_MODEL_ARRHENIUS && !(pr->consts[0] > 0.0 && pr->consts[1] > 0.0 && pr->consts[2] > 0.0))
-        return fail(PBU_ERR_INVALID, "the Arrhenius model needs T0 > 0, dT > 0 (a heating ramp) and beta > 0");
-    if (!pr->theta_nom || !pr->unc_idx || !pr->y || !pr->std_y || !pr->lb || !pr->ub) return fail(PBU_ERR_INVALID, "null problem array");
+    if (!pr->y || !pr->std_y || !pr->lb || !pr->ub) return fail(PBU_ERR_INVALID, "null problem array");
+    std::vector<HostBlock> blocks;
+    if (pr->n_models <= 1) {
+        if (!pr->theta_nom || !pr->unc_idx) return fail(PBU_ERR_INVALID, "null problem array");
+        blocks.push_back({0, pr->n_points, pr->theta_nom, pr->unc_idx, pr->consts});
+    } else {
+        if (pr->n_models > PBU_MAX_MODELS) return fail(PBU_ERR_UNSUPPORTED, "at most %d models per posterior, got %d", PBU_MAX_MODELS, pr->n_models);
+        if (!pr->model_first || !pr->model_count || !pr->model_theta_nom || !pr->model_unc_idx || !pr->model_consts)
+            return fail(PBU_ERR_INVALID, "null model-block array");
+        int at = 0;
+        for (int m = 0; m < pr->n_models; ++m) {
+            if (pr->model_first[m] != at || pr->model_count[m] < 1)
+                return fail(PBU_ERR_INVALID, "model %d: the models' points must be contiguous, in order and non-empty", m);
+            blocks.push_back({at, pr->model_count[m], pr->model_theta_nom + (size_t)m * pr->n_param, pr->model_unc_idx + (size_t)m * pr->n_unc,
+                              pr->model_consts + (size_t)m * 8});
+            at += pr->model_count[m];
+        }
+        if (at != pr->n_points) return fail(PBU_ERR_INVALID, "the models' points add up to %d, n_points is %d", at, pr->n_points);
+    }
     int nd;
     switch (pr->model) {
         case PBU_MODEL_LINEAR: nd = pr->n_param; break;
@@ -336,12 +366,20 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
     }
     if (pr->model != PBU_MODEL_ARRHENIUS && (pr->n_design_cols != nd || !pr->design))
         return fail(PBU_ERR_INVALID, "model %d needs %d design column(s), got %d", pr->model, nd, pr->n_design_cols);
-    for (int i = 0; i < pr->n_unc; ++i)
-        if (pr->unc_idx[i] < 0 || pr->unc_idx[i] >= pr->n_param) return fail(PBU_ERR_INVALID, "unc_idx[%d] out of range", i);
-    if (pr->n_unc == pr->n_param)
-        // all parameters uncertain: the reference aliases param = var_param (bayesian_inference.py:368-369), i.e. identity order
-        for (int i = 0; i < pr->n_unc; ++i)
-            if (pr->unc_idx[i] != i) return fail(PBU_ERR_INVALID, "with every parameter uncertain unc_idx must be 0..d-1 (Model.run_model aliases param = var_param)");
+    for (size_t b = 0; b < blocks.size(); ++b) {
+        const HostBlock &hb = blocks[b];
+        if (pr->model == PBU_MODEL_ARRHENIUS && !(hb.consts[0] > 0.0 && hb.consts[1] > 0.0 && hb.consts[2] > 0.0))
+            return fail(PBU_ERR_INVALID, "the Arrhenius model needs T0 > 0, dT > 0 (a heating ramp) and beta > 0");
+        for (int i = 0; i < pr->n_unc; ++i) {
+            // a posterior with several models may have uncertain parameters that a given model does not use (-1)
+            const bool absent = blocks.size() > 1 && hb.unc_idx[i] == -1;
+            if (!absent && (hb.unc_idx[i] < 0 || hb.unc_idx[i] >= pr->n_param)) return fail(PBU_ERR_INVALID, "unc_idx[%d] out of range", i);
+        }
+        if (pr->n_unc == pr->n_param)
+            // all parameters uncertain: the reference aliases param = var_param (bayesian_inference.py:368-369), i.e. identity order
+            for (int i = 0; i < pr->n_unc; ++i)
+                if (hb.unc_idx[i] != i) return fail(PBU_ERR_INVALID, "with every parameter uncertain unc_idx must be 0..d-1 (Model.run_model aliases param = var_param)");
+    }
     const bool adapt = cfg->algo == PBU_ALGO_AM || cfg->algo == PBU_ALGO_DRAM;
     if (adapt && cfg->updating_it < 1) return fail(PBU_ERR_INVALID, "updating_it must be >= 1");
 
@@ -393,7 +431,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
     // ---- problem records
     std::vector<double> rec, raw;
     double J_const;
-    build_records(pr, ev->nc, ev->ncr, rec, raw, J_const);
+    build_records(pr, blocks, ev->nc, ev->ncr, rec, raw, J_const);
     ProblemDev &pd = e->prob;
     memset(&pd, 0, sizeof pd);
     pd.n_points = pr->n_points;
@@ -406,14 +444,23 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
     for (int i = 0; i < PBU_MAX_DIM; ++i) pd.unc_idx[i] = -1;
     double lpc = 0.0;
     for (int i = 0; i < pr->n_unc; ++i) {
-        pd.unc_idx[i] = pr->unc_idx[i];
+        pd.unc_idx[i] = blocks[0].unc_idx[i];
         pd.lb[i] = pr->lb[i];
         pd.ub[i] = pr->ub[i];
         lpc += std::log(1.0 / std::fabs(pr->ub[i] - pr->lb[i]));      // distributions.py:278, :475
     }
     pd.log_prior_const = pr->has_log_const ? pr->log_const : lpc;
-    for (int i = 0; i < pr->n_param; ++i) pd.theta_nom[i] = pr->theta_nom[i];
-    for (int i = 0; i < 8; ++i) pd.consts[i] = pr->consts[i];
+    for (int i = 0; i < pr->n_param; ++i) pd.theta_nom[i] = blocks[0].theta_nom[i];
+    for (int i = 0; i < 8; ++i) pd.consts[i] = blocks[0].consts[i];
+    pd.n_blocks = (int)blocks.size();
+    for (size_t b = 0; b < blocks.size(); ++b) {
+        ModelBlockDev &mb = pd.blk[b];
+        mb.first = blocks[b].first;
+        mb.count = blocks[b].count;
+        for (int i = 0; i < PBU_MAX_DIM; ++i) mb.unc_idx[i] = (i < pr->n_unc) ? blocks[b].unc_idx[i] : -1;
+        for (int i = 0; i < pr->n_param; ++i) mb.theta_nom[i] = blocks[b].theta_nom[i];
+        for (int i = 0; i < 8; ++i) mb.consts[i] = blocks[b].consts[i];
+    }
 
     // resident when every record fits in shared memory, otherwise streamed in tiles through a 2-slot ring
     int max_smem = 0;
@@ -439,6 +486,11 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
     };
     plan_tiles((size_t)ev->nc * 8, cfg->tile_points, e->tile_points, e->smem_bytes);
     plan_tiles((size_t)ev->ncr * 8, cfg->tile_points, e->tile_points_raw, e->smem_raw_bytes);
+    if (blocks.size() > 1 && e->tile_points < pr->n_points) {
+        pbu_engine_destroy(e);
+        return fail(PBU_ERR_UNSUPPORTED, "several models per posterior need all %d likelihood records resident in shared memory (%zu B); "
+                    "streamed records are single-model", pr->n_points, (size_t)pr->n_points * ev->nc * 8);
+    }
     int rc;
     if ((rc = dev_alloc(e, &e->d_records, rec.size())) != PBU_OK || (rc = dev_alloc(e, &e->d_raw, raw.size())) != PBU_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(e->d_records, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));

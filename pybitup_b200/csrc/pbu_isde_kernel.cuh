@@ -152,19 +152,42 @@ __device__ __forceinline__ void grad_log_like(const double (&x)[Q][D], const Pro
     constexpr int NP = M::NPARAM;
     typename M::Ctx ctx[Q];
     typename M::Seq seq[Q];
-    double J[Q][U], g[Q][M::HAS_GRAD ? NP : 1];
+    double J[Q][U], g[Q][M::HAS_GRAD ? NP : 1], gd[Q][D];
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-        begin_chain<M, D>(x[q], prob, ctx[q], seq[q]);
 #pragma unroll
         for (int u = 0; u < U; ++u) J[q][u] = 0.0;
 #pragma unroll
         for (int j = 0; j < (M::HAS_GRAD ? NP : 1); ++j) g[q][j] = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) gd[q][i] = 0.0;
     }
     if constexpr (!STREAM) {
-        tile_accumulate<M, G, Q, U, M::HAS_GRAD>(ctx, seq, reinterpret_cast<const double *>(TileStream<M::NC>::smem() + 128), prob.n_points, sub,
-                                                 J, g);
+        // one pass per model of the likelihood (value :500-524, gradient :596-612); a single model is one block
+        const double *const base = reinterpret_cast<const double *>(TileStream<M::NC>::smem() + 128);
+        const int nb = prob.n_blocks;
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) begin_chain_block<M, D>(x[q], prob, b, ctx[q], seq[q]);
+            tile_accumulate<M, G, Q, U, M::HAS_GRAD>(ctx, seq, base + (size_t)prob.blk[b].first * M::NC, prob.blk[b].count, sub, J, g);
+            if constexpr (M::HAS_GRAD) {          // model-parameter gradient -> uncertain parameters, by this block's name map
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+#pragma unroll
+                        for (int j = 0; j < NP; ++j)
+                            if (D == NP ? (j == i) : (prob.blk[b].unc_idx[i] == j)) gd[q][i] += g[q][j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) g[q][j] = 0.0;
+                }
+            }
+        }
     } else {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) begin_chain<M, D>(x[q], prob, ctx[q], seq[q]);        // streamed records: one model (host-checked)
         const double *const records = prob.records;
         const int n = prob.n_points;
         ts.begin_pass(records, n, tile_points);
@@ -175,6 +198,15 @@ __device__ __forceinline__ void grad_log_like(const double (&x)[Q][D], const Pro
             tile_accumulate<M, G, Q, U, M::HAS_GRAD>(ctx, seq, tile, cnt, sub, J, g);
             ts.release(records, n, tile_points, t);
         }
+        if constexpr (M::HAS_GRAD) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = 0; j < NP; ++j)
+                        if (D == NP ? (j == i) : (prob.unc_idx[i] == j)) gd[q][i] = g[q][j];
+        }
     }
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
@@ -184,15 +216,7 @@ __device__ __forceinline__ void grad_log_like(const double (&x)[Q][D], const Pro
         Jq = group_sum<G>(Jq, group_mask) + prob.J_const;
         lp[q] = inside_box<D>(x[q], prob) ? (prob.log_prior_const - 0.0) + (-0.5 * Jq) : -INFINITY;
 #pragma unroll
-        for (int i = 0; i < D; ++i) {
-            double gi = 0.0;
-            if constexpr (M::HAS_GRAD) {
-#pragma unroll
-                for (int j = 0; j < NP; ++j)
-                    if (D == NP ? (j == i) : (prob.unc_idx[i] == j)) gi = g[q][j];
-            }
-            grad[q][i] = group_sum<G>(gi, group_mask);
-        }
+        for (int i = 0; i < D; ++i) grad[q][i] = group_sum<G>(gd[q][i], group_mask);
     }
 }
 
@@ -629,6 +653,36 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, M::MIN_BLOCKS) hmc_step_kernel(c
 }
 
 // gradient of the log-posterior at S points (initial stored gradient of HMC, mha.py:815): G[i][s]
+// gradient of the log-likelihood at one point per thread, analytical or by forward differences (:1069-1088)
+template <class M, int D, bool ST>
+__device__ __forceinline__ void eval_grad_point(const double (&x)[1][D], const ProblemDev &prob, TileStream<M::NC> &ts, int tile_points, unsigned mask,
+                                                int fd_gradient, double (&g)[1][D], double (&lp)[1]) {
+    if (!fd_gradient) {
+        grad_log_like<M, D, 1, 1, ST>(x, prob, ts, tile_points, 0, mask, g, lp);
+    } else {
+        const bool want[1] = {true};
+        double fp[1], xp[1][D];
+        log_posterior<M, D, 1, 1, ST>(x, want, prob, ts, tile_points, 0, mask, lp);
+        for (int i = 0; i < D; ++i) {
+            double xv = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                xp[0][j] = x[0][j];
+                if (j == i) xv = x[0][j];
+            }
+            double delta = __dmul_rn(xv, 1e-10);
+            if (delta == 0.0) delta = 1e-10;
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                if (j == i) xp[0][j] = __dadd_rn(xv, delta);
+            log_posterior<M, D, 1, 1, ST>(xp, want, prob, ts, tile_points, 0, mask, fp);
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                if (j == i) g[0][j] = (fp[0] - lp[0]) / delta;
+        }
+    }
+}
+
 template <class M, int D>
 __global__ void __launch_bounds__(256) eval_grad_kernel(const __grid_constant__ ProblemDev prob, const double *X /*[d][S]*/, int64_t S,
                                                         double *G_out /*[d][S]*/, int tile_points, int fd_gradient) {
@@ -642,30 +696,10 @@ __global__ void __launch_bounds__(256) eval_grad_kernel(const __grid_constant__ 
 #pragma unroll
     for (int i = 0; i < D; ++i) x[0][i] = X[i * S + t];
     const unsigned mask = 1u << (threadIdx.x & 31);
-    if (!fd_gradient) {
-        grad_log_like<M, D, 1, 1, true>(x, prob, ts, tile_points, 0, mask, g, lp);
-    } else {
-        const bool want[1] = {true};
-        double fp[1], xp[1][D];
-        log_posterior<M, D, 1, 1, true>(x, want, prob, ts, tile_points, 0, mask, lp);
-        for (int i = 0; i < D; ++i) {
-            double xv = 0.0;
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-                xp[0][j] = x[0][j];
-                if (j == i) xv = x[0][j];
-            }
-            double delta = __dmul_rn(xv, 1e-10);
-            if (delta == 0.0) delta = 1e-10;
-#pragma unroll
-            for (int j = 0; j < D; ++j)
-                if (j == i) xp[0][j] = __dadd_rn(xv, delta);
-            log_posterior<M, D, 1, 1, true>(xp, want, prob, ts, tile_points, 0, mask, fp);
-#pragma unroll
-            for (int j = 0; j < D; ++j)
-                if (j == i) g[0][j] = (fp[0] - lp[0]) / delta;
-        }
-    }
+    if (TileStream<M::NC>::resident(prob.n_points, tile_points))        // (uniform branch) the resident path walks the model blocks
+        eval_grad_point<M, D, false>(x, prob, ts, tile_points, mask, fd_gradient, g, lp);
+    else
+        eval_grad_point<M, D, true>(x, prob, ts, tile_points, mask, fd_gradient, g, lp);
     if (livet) {
 #pragma unroll
         for (int i = 0; i < D; ++i) G_out[i * S + t] = g[0][i];

@@ -210,13 +210,13 @@ __device__ __forceinline__ double group_sum(double v, unsigned group_mask) {
 
 // Full parameter vector from the uncertain ones (Model.run_model, bayesian_inference.py:361-369).
 template <class M, int D>
-__device__ __forceinline__ void full_theta(const double (&x)[D], const ProblemDev &prob, double (&theta)[M::NPARAM]) {
+__device__ __forceinline__ void full_theta(const double (&x)[D], const double *theta_nom, const int32_t *unc_idx, double (&theta)[M::NPARAM]) {
 #pragma unroll
     for (int q = 0; q < M::NPARAM; ++q) {
-        double v = prob.theta_nom[q];
+        double v = theta_nom[q];
 #pragma unroll
         for (int i = 0; i < D; ++i)
-            if (prob.unc_idx[i] == q) v = x[i];
+            if (unc_idx[i] == q) v = x[i];
         theta[q] = v;
     }
 }
@@ -234,13 +234,28 @@ __device__ __forceinline__ bool inside_box(const double (&x)[D], const ProblemDe
 template <class M, int D>
 __device__ __forceinline__ void begin_chain(const double (&x)[D], const ProblemDev &prob, typename M::Ctx &ctx, typename M::Seq &seq) {
     if constexpr (D == M::NPARAM) {
-        M::begin(ctx, x, prob);
+        M::begin(ctx, x, prob.consts);
     } else {
         double theta[M::NPARAM];
-        full_theta<M, D>(x, prob, theta);
-        M::begin(ctx, theta, prob);
+        full_theta<M, D>(x, prob.theta_nom, prob.unc_idx, theta);
+        M::begin(ctx, theta, prob.consts);
     }
-    M::seq_init(ctx, seq, prob);
+    M::seq_init(ctx, seq, prob.consts);
+}
+// ... of model block b of the likelihood (Likelihood.models, bayesian_inference.py:500-507): own nominal parameters,
+// own name map, own constants.  The block index is a run-time value: the small vectors are read from the constant
+// bank with an indexed load, once per evaluation.
+template <class M, int D>
+__device__ __forceinline__ void begin_chain_block(const double (&x)[D], const ProblemDev &prob, int b, typename M::Ctx &ctx, typename M::Seq &seq) {
+    const ModelBlockDev &blk = prob.blk[b];
+    if constexpr (D == M::NPARAM) {
+        M::begin(ctx, x, blk.consts);
+    } else {
+        double theta[M::NPARAM];
+        full_theta<M, D>(x, blk.theta_nom, blk.unc_idx, theta);
+        M::begin(ctx, theta, blk.consts);
+    }
+    M::seq_init(ctx, seq, blk.consts);
 }
 
 // BayesianPosterior.compute_log_value (bayesian_inference.py:44-64) with the identity
@@ -264,14 +279,33 @@ __device__ __forceinline__ void log_posterior(const double (&x)[Q][D], const boo
     double J[Q][U], gdummy[Q][1];
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-        begin_chain<M, D>(x[q], prob, ctx[q], seq[q]);
 #pragma unroll
         for (int u = 0; u < U; ++u) J[q][u] = 0.0;
     }
     if constexpr (!STREAM) {
-        tile_accumulate<M, G, Q, U, false>(ctx, seq, reinterpret_cast<const double *>(TileStream<M::NC>::smem() + 128), prob.n_points, sub, J,
-                                           gdummy);
+        // one pass per model of the likelihood (bayesian_inference.py:500-524); a single model is one block
+        const double *const base = reinterpret_cast<const double *>(TileStream<M::NC>::smem() + 128);
+        const int nb = prob.n_blocks;
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+            // block 0 is read from the top-level fields (compile-time constant-bank addresses): a single model pays nothing
+            const double *recs = base;
+            int cnt = prob.n_points;
+            if (b == 0) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q) begin_chain<M, D>(x[q], prob, ctx[q], seq[q]);
+                if (nb > 1) cnt = prob.blk[0].count;
+            } else {
+#pragma unroll
+                for (int q = 0; q < Q; ++q) begin_chain_block<M, D>(x[q], prob, b, ctx[q], seq[q]);
+                recs = base + (size_t)prob.blk[b].first * M::NC;
+                cnt = prob.blk[b].count;
+            }
+            tile_accumulate<M, G, Q, U, false>(ctx, seq, recs, cnt, sub, J, gdummy);
+        }
     } else {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) begin_chain<M, D>(x[q], prob, ctx[q], seq[q]);        // streamed records: one model (host-checked)
         const double *const records = prob.records;
         const int n = prob.n_points;
         ts.begin_pass(records, n, tile_points);
@@ -662,7 +696,10 @@ __global__ void __launch_bounds__(256) eval_logpost_kernel(const __grid_constant
     const bool want[1] = {livet};
 #pragma unroll
     for (int i = 0; i < D; ++i) x[0][i] = X[i * S + t];
-    log_posterior<M, D, 1, 1, true>(x, want, prob, ts, tile_points, 0, 1u << (threadIdx.x & 31), lp);
+    if (TileStream<M::NC>::resident(prob.n_points, tile_points))        // (uniform branch) the resident path walks the model blocks
+        log_posterior<M, D, 1, 1, false>(x, want, prob, ts, tile_points, 0, 1u << (threadIdx.x & 31), lp);
+    else
+        log_posterior<M, D, 1, 1, true>(x, want, prob, ts, tile_points, 0, 1u << (threadIdx.x & 31), lp);
     if (livet) lp_out[t] = lp[0];
 }
 
@@ -682,12 +719,18 @@ __global__ void __launch_bounds__(256) eval_model_kernel(const __grid_constant__
     for (int i = 0; i < D; ++i) x[i] = X[i * S + t];
     typename M::Ctx ctx;
     typename M::Seq seq;
-    begin_chain<M, D>(x, prob, ctx, seq);
+    int b = 0, next = prob.blk[0].count;          // model blocks are contiguous point ranges: restart at each boundary
+    begin_chain_block<M, D>(x, prob, 0, ctx, seq);
     ts.begin_pass(prob.raw, prob.n_points, tile_points);
     for (int tl = 0; tl < n_tl; ++tl) {
         int cnt;
         const double *tile = ts.acquire(prob.n_points, tile_points, tl, cnt);
         for (int k = 0; k < cnt; ++k) {
+            if (tl * tile_points + k == next) {
+                b += 1;
+                next += prob.blk[b].count;
+                begin_chain_block<M, D>(x, prob, b, ctx, seq);
+            }
             double raw[M::NCR];
             load_record<M::NCR>(tile, k, raw);
             const double f = M::value(ctx, seq, raw);

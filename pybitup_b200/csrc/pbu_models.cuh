@@ -44,12 +44,12 @@ struct LinearModel {
         double th[P];
     };
     struct Seq {};
-    __device__ __forceinline__ static void begin(Ctx &c, const double (&theta)[P], const ProblemDev &) {
+    __device__ __forceinline__ static void begin(Ctx &c, const double (&theta)[P], const double *) {
 #pragma unroll
         for (int j = 0; j < P; ++j) c.th[j] = theta[j];
     }
     __device__ __forceinline__ static void block_init() {}
-    __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const ProblemDev &) {}
+    __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const double *) {}
     // written stage-by-stage across the U points so that the U dependency chains interleave in program order
     template <int U>
     __device__ __forceinline__ static void resid_batch(const Ctx &c, Seq &, const double (&rec)[U][NC], double (&t)[U]) {
@@ -91,12 +91,12 @@ struct PolyModel {
         double th[P];
     };
     struct Seq {};
-    __device__ __forceinline__ static void begin(Ctx &c, const double (&theta)[P], const ProblemDev &) {
+    __device__ __forceinline__ static void begin(Ctx &c, const double (&theta)[P], const double *) {
 #pragma unroll
         for (int j = 0; j < P; ++j) c.th[j] = theta[j];
     }
     __device__ __forceinline__ static void block_init() {}
-    __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const ProblemDev &) {}
+    __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const double *) {}
     template <int U>
     __device__ __forceinline__ static void resid_batch(const Ctx &c, Seq &, const double (&rec)[U][NC], double (&t)[U]) {
         double f[U];
@@ -150,15 +150,15 @@ struct ArrheniusModel {
     struct Seq {
         double alpha, g0;
     };
-    __device__ __forceinline__ static void begin(Ctx &c, const double (&theta)[4], const ProblemDev &p) {
-        c.c0 = 2.302585092994046 * theta[0] - log(p.consts[2]) + log(p.consts[1]);   // ln(10)*log10A - ln(beta) + ln(h)
+    __device__ __forceinline__ static void begin(Ctx &c, const double (&theta)[4], const double *consts) {
+        c.c0 = 2.302585092994046 * theta[0] - log(consts[2]) + log(consts[1]);   // ln(10)*log10A - ln(beta) + ln(h)
         c.ER = theta[1] / R_GAS;
         c.n = theta[2];
         c.F = theta[3];
-        c.h = p.consts[1];
-        c.g_start = exp(c.c0 - c.ER * (1.0 / p.consts[0]));
+        c.h = consts[1];
+        c.g_start = exp(c.c0 - c.ER * (1.0 / consts[0]));
     }
-    __device__ __forceinline__ static void seq_init(const Ctx &c, Seq &s, const ProblemDev &) {
+    __device__ __forceinline__ static void seq_init(const Ctx &c, Seq &s, const double *) {
         s.alpha = 0.0;
         s.g0 = c.g_start;
     }
@@ -224,8 +224,8 @@ struct HeatModel {
         double gamma, c1, c2, T_amb;
     };
     struct Seq {};
-    __device__ __forceinline__ static void begin(Ctx &c, const double (&th)[6], const ProblemDev &p) {
-        const double a = th[0], b = th[1], k = th[2], phi = th[4], h = th[5], L = p.consts[0];
+    __device__ __forceinline__ static void begin(Ctx &c, const double (&th)[6], const double *consts) {
+        const double a = th[0], b = th[1], k = th[2], phi = th[4], h = th[5], L = consts[0];
         const double gamma = sqrt(2.0 * (a + b) * h / (a * b * k));
         const double ep = exp(gamma * L), em = exp(-gamma * L);
         const double c1 = -phi / (k * gamma) * (ep * (h + k * gamma) / (em * (h - k * gamma) + ep * (h + k * gamma)));
@@ -235,7 +235,7 @@ struct HeatModel {
         c.T_amb = th[3];
     }
     __device__ __forceinline__ static void block_init() {}
-    __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const ProblemDev &) {}
+    __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const double *) {}
     __device__ __forceinline__ static double value(const Ctx &c, Seq &, const double *raw) {
         const double x = raw[0];
         return c.c1 * exp(-c.gamma * x) + c.c2 * exp(c.gamma * x) + c.T_amb;
@@ -268,13 +268,13 @@ struct SoizeModel {
         double t0, t1;
     };
     struct Seq {};
-    __device__ __forceinline__ static void begin(Ctx &c, const double (&th)[2], const ProblemDev &) {
+    __device__ __forceinline__ static void begin(Ctx &c, const double (&th)[2], const double *) {
         const double a = th[0] * th[0] * th[0] - th[1], b = th[1] - 0.3;
         c.t0 = 5.477225575051661 * a;          // sqrt(30)
         c.t1 = 1.4142135623730951 * (b * b);   // sqrt(2)
     }
     __device__ __forceinline__ static void block_init() {}
-    __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const ProblemDev &) {}
+    __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const double *) {}
     __device__ __forceinline__ static double value(const Ctx &c, Seq &, const double *raw) { return (raw[0] == 0.0) ? c.t0 : c.t1; }
     template <int U>
     __device__ __forceinline__ static void resid_batch(const Ctx &c, Seq &s, const double (&rec)[U][NC], double (&t)[U]) {

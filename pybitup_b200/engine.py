@@ -29,13 +29,18 @@ class ProblemSpec:
     gamma: float = 1.0
     design: dict = field(default_factory=dict)
     log_const: float = None          # analytic densities: constant that replaces the log-prior constant
+    # several models in one likelihood (Likelihood.models, bayesian_inference.py:500-524): one dict per model with
+    # theta_nom [P], unc_idx [d] (-1 = not a parameter of that model), design {...}, n_points; y / std_y hold the
+    # models' points concatenated in this order, and theta_nom / unc_idx / design above are those of the first model
+    blocks: list = None
 
     @classmethod
     def from_dict(cls, p):
         return cls(model=str(p["model"]), theta_nom=_f64(p["theta_nom"]),
                    unc_idx=np.ascontiguousarray(np.asarray(p["unc_idx"], dtype=np.int32)),
                    y=_f64(np.atleast_2d(p["y"])), std_y=_f64(p["std_y"]), lb=_f64(p["lb"]), ub=_f64(p["ub"]),
-                   gamma=float(p.get("gamma", 1.0)), design=dict(p.get("design", {})), log_const=p.get("log_const"))
+                   gamma=float(p.get("gamma", 1.0)), design=dict(p.get("design", {})), log_const=p.get("log_const"),
+                   blocks=p.get("blocks"))
 
     @property
     def d(self):
@@ -44,6 +49,32 @@ class ProblemSpec:
     @property
     def n_points(self):
         return int(self.y.shape[1])
+
+    @staticmethod
+    def _design_and_consts(model, design_dict, N, P):
+        """(design [N, ncols] or None, ncols, consts[8]) of one model's N points."""
+        consts = [0.0] * 8
+        design, ncols = None, 0
+        if model == "linear":
+            design = _f64(design_dict["Phi"])
+            if design.shape != (N, P):
+                raise ValueError("linear model: Phi must be [N, P] = [%d, %d], got %s" % (N, P, design.shape))
+            ncols = design.shape[1]
+        elif model == "soize":
+            design = np.array([[0.0], [1.0]])
+            ncols = 1
+        elif model in ("poly", "heat"):
+            design = _f64(design_dict["x"]).reshape(N, 1)
+            ncols = 1
+            if model == "heat":
+                consts[0] = float(design_dict.get("L", 70.0))
+        elif model == "arrhenius":
+            dg = design_dict
+            if int(dg["n_steps"]) != N:
+                raise ValueError("arrhenius model: n_steps (%d) must equal the number of data points (%d)"
+                                 % (int(dg["n_steps"]), N))
+            consts[0], consts[1], consts[2] = float(dg["T0"]), float(dg["dT"]), float(dg["beta"])
+        return design, ncols, consts
 
     def _c_struct(self):
         """Build the pbu_problem struct; returns (struct, keepalive list)."""
@@ -58,32 +89,49 @@ class ProblemSpec:
         std = _f64(self.std_y)
         lb, ub = _f64(self.lb), _f64(self.ub)
         N = y.shape[1]
-        consts = [0.0] * 8
-        design = None
-        ncols = 0
-        if self.model == "linear":
-            design = _f64(self.design["Phi"])
-            if design.shape != (N, len(theta)):
-                raise ValueError("linear model: Phi must be [N, P] = [%d, %d], got %s" % (N, len(theta), design.shape))
-            ncols = design.shape[1]
-        elif self.model == "soize":
-            design = np.array([[0.0], [1.0]])
-            ncols = 1
-        elif self.model in ("poly", "heat"):
-            design = _f64(self.design["x"]).reshape(N, 1)
-            ncols = 1
-            if self.model == "heat":
-                consts[0] = float(self.design.get("L", 70.0))
-        elif self.model == "arrhenius":
-            dg = self.design
-            if int(dg["n_steps"]) != N:
-                raise ValueError("arrhenius model: n_steps (%d) must equal the number of data points (%d)"
-                                 % (int(dg["n_steps"]), N))
-            consts[0], consts[1], consts[2] = float(dg["T0"]), float(dg["dT"]), float(dg["beta"])
+        s = capi.pbu_problem()
+        if not self.blocks:
+            design, ncols, consts = self._design_and_consts(self.model, self.design, N, len(theta))
+            s.n_models = 0
+        else:
+            # several models in one likelihood: points concatenated, per-model parameters / name map / constants
+            P, d = len(theta), len(unc)
+            first, count, th, ui, cs, designs = [], [], [], [], [], []
+            at = 0
+            for blk in self.blocks:
+                n = int(blk["n_points"])
+                dsg, ncols, c = self._design_and_consts(self.model, blk["design"], n, P)
+                bt = _f64(blk["theta_nom"])
+                bu = np.asarray(blk["unc_idx"], dtype=np.int32)
+                if bt.shape != (P,) or bu.shape != (d,):
+                    raise capi.UnsupportedProblem(capi.PBU_ERR_UNSUPPORTED,
+                                                  "the models of one posterior must have the same number of parameters")
+                first.append(at)
+                count.append(n)
+                th.append(bt)
+                ui.append(bu)
+                cs.append(c)
+                designs.append(dsg)
+                at += n
+            if at != N:
+                raise ValueError("the models' points add up to %d, the data has %d" % (at, N))
+            design = None if designs[0] is None else np.ascontiguousarray(np.concatenate(designs, axis=0))
+            consts = cs[0]
+            mf = np.ascontiguousarray(np.array(first, dtype=np.int32))
+            mc = np.ascontiguousarray(np.array(count, dtype=np.int32))
+            mt = np.ascontiguousarray(np.stack(th))
+            mu = np.ascontiguousarray(np.stack(ui).astype(np.int32))
+            mk = np.ascontiguousarray(np.array(cs, dtype=np.float64))
+            keep += [mf, mc, mt, mu, mk]
+            s.n_models = len(self.blocks)
+            s.model_first = mf.ctypes.data_as(C.POINTER(C.c_int32))
+            s.model_count = mc.ctypes.data_as(C.POINTER(C.c_int32))
+            s.model_theta_nom = capi.dptr(mt)
+            s.model_unc_idx = mu.ctypes.data_as(C.POINTER(C.c_int32))
+            s.model_consts = capi.dptr(mk)
         if std.shape != (N,) or lb.shape != unc.shape or ub.shape != unc.shape:
             raise ValueError("inconsistent problem array shapes")
         keep += [theta, unc, y, std, lb, ub, design]
-        s = capi.pbu_problem()
         s.model = capi.MODEL_IDS[self.model]
         s.n_param, s.n_unc, s.n_points, s.n_runs, s.n_design_cols = len(theta), len(unc), N, y.shape[0], ncols
         s.theta_nom = capi.dptr(theta)

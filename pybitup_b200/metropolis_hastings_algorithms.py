@@ -337,6 +337,16 @@ class _GradientSampler(_DeviceSampler):
             self.V = np.linalg.inv(self.hess_mat)
             if value == "nearPD":                                            # :679-684
                 self.V = nearPD(self.V)
+        if self.V is not None:
+            # :713-722: a preconditioner scipy cannot factorise is replaced by the identity (the FD Hessian of
+            # computeHessianFD is easily indefinite: its aliased stencil)
+            import scipy.linalg
+            try:
+                self.L_c = scipy.linalg.cholesky(np.asarray(self.V, dtype=np.float64))
+            except (scipy.linalg.LinAlgError, ValueError):
+                print('Non positive defintie Hessian matrix. Set to identity matrix.')
+                self.V = None
+        self.C_approx = np.identity(self.n_param) if self.V is None else np.asarray(self.V, dtype=np.float64)
         return self.V
 
 

@@ -306,6 +306,84 @@ def gen_hmc():
     run_case("regression_hmc_adapt", reg, reg_names, hmc_algo(400, 0.01, 4, "Analytical", 150, 25, 300), 62, 400 * 6)
 
 
+def write_multi_case(workdir, probs, names, algo_block):
+    """Two (or more) Data / Model entries in one posterior: solve_problem.py:186-271 pairs them by position with the
+    keys of the `models` dict; the likelihood sums over them (bayesian_inference.py:500-524)."""
+    p0 = probs[0]
+    data, model = [], []
+    for m, prob in enumerate(probs):
+        x_col = prob["design"].get("x", np.arange(prob["y"].shape[1], dtype=float))
+        pd.DataFrame({"x": x_col, "y": prob["y"][0], "std_y": prob["std_y"]}).to_csv(os.path.join(workdir, "data%d.csv" % m))
+        data.append({"Type": "ReadFromFile", "FileName": "data%d" % m, "xField": ["x"], "yField": ["y"], "sigmaField": ["std_y"]})
+        model.append({"param_names": names, "param_values": [float(v) for v in prob["theta_nom"]], "parametrization": "no"})
+    prior = {}
+    for k, idx in enumerate(int(i) for i in p0["unc_idx"]):
+        prior[names[idx]] = {"initial_val": float(p0["x0"][k]), "prior_name": "Uniform",
+                             "prior_param": [float(p0["lb"][k]), float(p0["ub"][k])]}
+    js = {"Sampling": {"BayesianPosterior": {"Data": data, "Model": model, "Prior": {"Distribution": "Mixture", "Param": prior},
+                                             "Likelihood": {"function": "Gaussian", "distance": "L2"}},
+                       "Algorithm": algo_block}}
+    with open(os.path.join(workdir, "case.json"), "w") as f:
+        json.dump(js, f, indent=1)
+
+
+def run_multi_case(case, probs, names, algo, seed, stream_len):
+    rng = np.random.default_rng(seed)
+    normals = rng.standard_normal(stream_len)
+    uniforms = rng.random(stream_len)
+    with tempfile.TemporaryDirectory() as wd:
+        write_multi_case(wd, probs, names, algo)
+        models = {"m%d" % m: build_model(prob, names) for m, prob in enumerate(probs)}
+        rec = run_reference(wd, "case.json", models, normals, uniforms)
+    s = rec.sampler
+    out = pack_problem(probs[0])
+    out["n_models"] = len(probs)
+    for m, prob in enumerate(probs[1:], start=1):
+        for k, v in pack_problem(prob).items():
+            if k in ("theta_nom", "unc_idx", "y", "std_y") or k.startswith("design_"):
+                out["m%d_%s" % (m, k)] = v
+    out.update(algo_json=json.dumps(algo), normals=normals[:rec.n_normals_used], uniforms=uniforms[:rec.n_uniforms_used],
+               eval_x=np.array(rec.eval_x), eval_lp=np.array(rec.eval_lp), chain=np.array(rec.saved),
+               n_rejected=s.n_rejected, mean_r=float(s.mean_r))
+    for attr in ("R", "V_i", "X_av_i", "inv_V", "C_approx", "P_nm", "xi_nm", "L_c", "inv_L_c"):
+        if hasattr(s, attr):
+            out["final_" + attr] = np.array(getattr(s, attr), dtype=np.float64)
+    path = os.path.join(HERE, case + ".npz")
+    np.savez_compressed(path, **out)
+    print("%-22s evals=%d chain=%s n_rej=%d -> %s (%d B)" % (case, len(rec.eval_lp), np.array(rec.saved).shape, s.n_rejected,
+                                                             os.path.basename(path), os.path.getsize(path)))
+
+
+def gen_multi():
+    """Several models in one likelihood: (1) one pyrolysis reaction observed at two heating rates (two Arrhenius models
+    with their own ramp, beta and fixed F), log10A and E uncertain, DRAM; (2) two cubic data sets on different grids,
+    all four coefficients uncertain, Ito-SDE with the analytical gradient summed over both models."""
+    a0 = synthetic.arrhenius_problem(n_steps=40, dT=15.0)
+    names = ["log10A", "E", "n", "F"]
+    theta_b = np.array([6.0, 1.0e5, 1.5, 0.35])
+    dg_b = dict(T0=350.0, dT=10.0, n_steps=50, beta=30.0 / 60.0)
+    rng = np.random.default_rng(77)
+    f_b = synthetic.arrhenius_reference(theta_b, dg_b["T0"], dg_b["dT"], dg_b["n_steps"], dg_b["beta"])
+    y_b = f_b + 5e-3 * rng.standard_normal(50)
+    unc = np.array([0, 1])
+    common = dict(unc_idx=unc, lb=a0["lb"][:2], ub=a0["ub"][:2], x0=a0["x0"][:2], prop_cov=a0["prop_cov"][:2, :2] * 4.0)
+    pa = dict(a0, **common)
+    pb = dict(a0, theta_nom=theta_b, y=y_b[None, :], std_y=np.full(50, 5e-3),
+              design=dict(dg_b, x=dg_b["T0"] + dg_b["dT"] * np.arange(1, 51)), **common)
+    run_multi_case("multi_arrhenius_dram", [pa, pb], names,
+                   mh_algo("DRAM", 200, common["prop_cov"], updating_it=10, eps_v=1e-10, gamma=0.2), 71, 10 * 200 * 2)
+
+    c0 = synthetic.cubic_problem(n_points=60)
+    c0 = dict(c0, prop_cov=c0["prop_cov"] * 10)
+    xb = np.linspace(0.0, 2.0, 45)
+    th = c0["theta_nom"]
+    yb = ((th[3] * xb + th[2]) * xb + th[1]) * xb + th[0] + 0.1 * rng.standard_normal(45)
+    c1 = dict(c0, y=yb[None, :], std_y=np.full(45, 0.1), design=dict(x=xb))
+    cn = ["c0", "c1", "c2", "c3"]
+    run_multi_case("multi_cubic_am", [c0, c1], cn, mh_algo("AMH", 200, c0["prop_cov"], updating_it=10, eps_v=1e-10), 72, 5 * 200 * 4)
+    run_multi_case("multi_cubic_isde", [c0, c1], cn, isde_algo(150, 0.02, 4.0, "Analytical", 10 ** 6, 10), 73, 150 * 4)
+
+
 def gen_hessian_fd():
     """computeHessianFD (mha.py:1115-1212) of a fixed smooth function, all four flag combinations; pins
     pybitup_b200.metropolis_hastings_algorithms.compute_hessian_fd including the in-place aliasing of :1186-1189."""
@@ -343,6 +421,8 @@ def gen_near_pd():
 if __name__ == "__main__":
     if "--nearpd" in sys.argv:
         gen_near_pd()
+    elif "--multi" in sys.argv:
+        gen_multi()
     elif "--hessian" in sys.argv:
         gen_hessian_fd()
     elif "--hmc" in sys.argv:
@@ -352,3 +432,4 @@ if __name__ == "__main__":
         gen_hmc()
         gen_hessian_fd()
         gen_near_pd()
+        gen_multi()

@@ -22,26 +22,61 @@ def load_golden(case):
     return g
 
 
+def _design_of(g, prefix):
+    return {k[len(prefix):]: (v.item() if getattr(v, "ndim", 1) == 0 else v) for k, v in g.items() if k.startswith(prefix)}
+
+
+def model_members(g):
+    """The models of a golden fixture's likelihood, one dict each (a single-model fixture has one)."""
+    members = [dict(theta_nom=g["theta_nom"], unc_idx=g["unc_idx"], y=g["y"], std_y=g["std_y"], design=_design_of(g, "design_"))]
+    for m in range(1, int(g["n_models"]) if "n_models" in g else 1):
+        pre = "m%d_" % m
+        members.append(dict(theta_nom=g[pre + "theta_nom"], unc_idx=g[pre + "unc_idx"], y=g[pre + "y"], std_y=g[pre + "std_y"],
+                            design=_design_of(g, pre + "design_")))
+    return members
+
+
 def problem_dict(g):
     """The dict layout of pybitup_b200.synthetic builders, from a golden fixture or a builder dict."""
     if "design" in g:
         return g
-    design = {k[len("design_"):]: (v.item() if getattr(v, "ndim", 1) == 0 else v)
-              for k, v in g.items() if k.startswith("design_")}
-    return dict(model=str(g["model"]), theta_nom=g["theta_nom"], unc_idx=g["unc_idx"], y=g["y"],
-                std_y=g["std_y"], lb=g["lb"], ub=g["ub"], gamma=float(g["gamma"]), design=design,
-                x0=g["x0"], prop_cov=g["prop_cov"])
+    mem = model_members(g)
+    out = dict(model=str(g["model"]), theta_nom=g["theta_nom"], unc_idx=g["unc_idx"], y=g["y"],
+               std_y=g["std_y"], lb=g["lb"], ub=g["ub"], gamma=float(g["gamma"]), design=mem[0]["design"],
+               x0=g["x0"], prop_cov=g["prop_cov"])
+    if len(mem) > 1:          # several models: points concatenated, one block per model
+        out["y"] = np.concatenate([np.atleast_2d(m["y"]) for m in mem], axis=1)
+        out["std_y"] = np.concatenate([m["std_y"] for m in mem])
+        out["blocks"] = [dict(theta_nom=m["theta_nom"], unc_idx=m["unc_idx"], design=m["design"],
+                              n_points=np.atleast_2d(m["y"]).shape[1]) for m in mem]
+    return out
+
+
+def _oracle_member(model, m, lb, ub, gamma):
+    design = dict(m["design"])
+    if "n_steps" in design:
+        design["n_steps"] = int(design["n_steps"])
+    return orc.Problem(model=model, theta_nom=np.array(m["theta_nom"], dtype=np.float64),
+                       unc_idx=np.array(m["unc_idx"], dtype=np.int64), y=np.array(np.atleast_2d(m["y"]), dtype=np.float64),
+                       std_y=np.array(m["std_y"], dtype=np.float64), lb=np.array(lb, dtype=np.float64),
+                       ub=np.array(ub, dtype=np.float64), gamma=float(gamma), design=design)
 
 
 def oracle_problem(g):
-    p = problem_dict(g)
-    design = dict(p["design"])
-    if "n_steps" in design:
-        design["n_steps"] = int(design["n_steps"])
-    return orc.Problem(model=p["model"], theta_nom=np.array(p["theta_nom"], dtype=np.float64),
-                       unc_idx=np.array(p["unc_idx"], dtype=np.int64), y=np.array(p["y"], dtype=np.float64),
-                       std_y=np.array(p["std_y"], dtype=np.float64), lb=np.array(p["lb"], dtype=np.float64),
-                       ub=np.array(p["ub"], dtype=np.float64), gamma=float(p["gamma"]), design=design)
+    if "design" in g and "blocks" not in g:
+        mem = [dict(theta_nom=g["theta_nom"], unc_idx=g["unc_idx"], y=g["y"], std_y=g["std_y"], design=g["design"])]
+    elif "blocks" in g:
+        mem, at = [], 0
+        for b in g["blocks"]:
+            n = int(b["n_points"])
+            mem.append(dict(theta_nom=b["theta_nom"], unc_idx=b["unc_idx"], y=np.atleast_2d(g["y"])[:, at:at + n],
+                            std_y=g["std_y"][at:at + n], design=b["design"]))
+            at += n
+    else:
+        mem = model_members(g)
+    probs = [_oracle_member(str(g["model"]), m, g["lb"], g["ub"], g["gamma"]) for m in mem]
+    probs[0].extra = probs[1:]
+    return probs[0]
 
 
 def mh_kwargs(algo):

@@ -18,9 +18,11 @@ def _isde_engine(p, a, n_chains, **kw):
     return ChainEngine(ProblemSpec.from_dict(H.problem_dict(p)), cfg, n_chains)
 
 
+@pytest.mark.parametrize("case", ["regression_isde", "multi_cubic_isde"])
 @pytest.mark.parametrize("lanes,q", [(1, 1), (1, 2), (2, 2), (4, 1), (8, 1)])
-def test_isde_analytical_golden(lanes, q):
-    g = H.load_golden("regression_isde")
+def test_isde_analytical_golden(lanes, q, case):
+    """multi_cubic_isde: two models in one likelihood (value and gradient summed over the model blocks)."""
+    g = H.load_golden(case)
     a = g["algo"]
     T, C = int(a["n_iterations"]), 3
     eng = _isde_engine(g, a, C, lanes_per_chain=lanes, chains_per_thread=q)

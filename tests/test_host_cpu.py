@@ -31,12 +31,26 @@ def test_library_exports_every_declared_symbol():
     assert n > 100 and "model=1 P=4 d=4" in listing
 
 
-def test_ctypes_structs_match_header_layout():
+def test_ctypes_structs_match_header_layout(tmp_path):
+    """The ctypes mirrors against the C compiler's view of include/pybitup_b200.h: sizes and every field offset."""
+    import subprocess
     from pybitup_b200 import _capi
-    # sizes the C compiler gives the structs (LP64): checked against a tiny C program's view via field offsets
-    assert ctypes.sizeof(_capi.pbu_problem) == 6 * 4 + 7 * 8 + 8 + 8 * 8 + 8 + 2 * 4
-    assert ctypes.sizeof(_capi.pbu_sampler_cfg) == 2 * 4 + 4 * 8 + 10 * 4 + 2 * 8 + 8 + 2 * 4
-    assert ctypes.sizeof(_capi.pbu_run_outputs) == 7 * 8
+    structs = {"pbu_problem": _capi.pbu_problem, "pbu_sampler_cfg": _capi.pbu_sampler_cfg, "pbu_run_outputs": _capi.pbu_run_outputs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "pybitup_b200.h"', 'int main(void) {']
+    for name, st in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for fname, _ in st._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, fname, name, fname))
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    seen = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for name, st in structs.items():
+        assert int(seen[name]) == ctypes.sizeof(st), name
+        for fname, _ in st._fields_:
+            assert int(seen["%s.%s" % (name, fname)]) == getattr(st, fname).offset, (name, fname)
 
 
 def test_strip_json_comments():
