@@ -232,8 +232,14 @@ int pbu_propagation_buffers(pbu_propagation *p, double **X_dev, double **f_dev);
 /* per design point sum, min, max over this engine's samples, host [N] each (:607-627) */
 int pbu_propagation_moments(pbu_propagation *p, double *sum_host, double *min_host, double *max_host);
 /* exact order statistics by radix select.  ranks host [n_ranks] (<= 4): 0-based ranks in the sorted GLOBAL sample.
- * For pass = 0..7: select_pass -> hist_host [N][n_ranks][256] (this engine's counts); sum over GPUs; select_update. */
-int pbu_propagation_select_begin(pbu_propagation *p, const int64_t *ranks, int n_ranks);
+ * row_min / row_max host [N] (both or neither, may be NULL): the GLOBAL minimum / maximum of every design point (the
+ * moments above, reduced over GPUs); the leading key bytes that all values share are then not scanned, and *first_pass
+ * (may be NULL) receives the first pass to run (0 without bounds, 8 when every design point is constant).
+ * For pass = first_pass..7: select_pass -> hist_host [N][n_ranks][256] (this engine's counts); sum over GPUs;
+ * select_update.  On a single GPU both histogram pointers may be NULL: the counts then never leave the device and the
+ * passes are queued back to back.  (np.percentile of fun_eval, solve_problem.py:639-647) */
+int pbu_propagation_select_begin(pbu_propagation *p, const int64_t *ranks, int n_ranks, const double *row_min, const double *row_max,
+                                 int *first_pass);
 int pbu_propagation_select_pass(pbu_propagation *p, int pass, uint64_t *hist_host);
 int pbu_propagation_select_update(pbu_propagation *p, int pass, const uint64_t *hist_total_host);
 int pbu_propagation_select_result(pbu_propagation *p, double *values_host /*[N][n_ranks]*/);

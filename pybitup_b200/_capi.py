@@ -106,7 +106,7 @@ def _load():
         "pbu_propagation_eval_gaussian": (C.c_int, [E, _dp, _dp, C.c_uint64, C.c_uint64]),
         "pbu_propagation_buffers": (C.c_int, [E, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
         "pbu_propagation_moments": (C.c_int, [E, _dp, _dp, _dp]),
-        "pbu_propagation_select_begin": (C.c_int, [E, _lp, C.c_int]),
+        "pbu_propagation_select_begin": (C.c_int, [E, _lp, C.c_int, _dp, _dp, C.POINTER(C.c_int)]),
         "pbu_propagation_select_pass": (C.c_int, [E, C.c_int, C.POINTER(C.c_uint64)]),
         "pbu_propagation_select_update": (C.c_int, [E, C.c_int, C.POINTER(C.c_uint64)]),
         "pbu_propagation_select_result": (C.c_int, [E, _dp]),

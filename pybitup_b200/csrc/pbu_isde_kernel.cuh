@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, M::MIN_BLOCKS) isde_step_kernel(
             // ---- first half step (:990-991)
             double z[D], udummy;
             if (injected) {
-                if (!draw_injected<D, false>(p.streams, cq, live[q] && sub == 0, group_mask, z, udummy)) status[q] |= ST_STREAM_EXHAUSTED;
+                if (!draw_injected<D, false>(p.streams, cq, live[q], live[q] && sub == 0, group_mask, z, udummy)) status[q] |= ST_STREAM_EXHAUSTED;
             } else {
                 draw_philox<D>(p.seed, p.chain_offset + (uint64_t)cq, (uint64_t)it, 0u, z, udummy);
             }
@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, M::MIN_BLOCKS) hmc_step_kernel(c
             adapt_preconditioner<D>(p, it, upd, x[q], live[q], gC, gIL, p.st.V + cq, p.st.xav + cq, C, status[q]);
             double z[D];
             if (injected) {
-                if (!draw_injected<D, true>(p.streams, cq, live[q] && sub == 0, group_mask, z, u[q])) status[q] |= ST_STREAM_EXHAUSTED;
+                if (!draw_injected<D, true>(p.streams, cq, live[q], live[q] && sub == 0, group_mask, z, u[q])) status[q] |= ST_STREAM_EXHAUSTED;
             } else {
                 draw_philox<D>(p.seed, p.chain_offset + (uint64_t)cq, (uint64_t)it, 0u, z, u[q]);
             }

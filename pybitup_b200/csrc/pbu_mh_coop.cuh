@@ -56,14 +56,14 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
         const int64_t it = p.it0 + s + 1;
         double y[D] = {}, u = 1.0, lp1 = 0.0, lp2 = nan(""), r = 0.0, alpha = 0.0;
         int acc = 0;
-        bool want = owner;                   // lanes beyond the team's chains only lend their arithmetic to the data loop
+        bool want = live;                    // lanes beyond the team's chains (and padding owners) only lend their arithmetic to the data loop
 #pragma unroll 1
         for (int stage = 0; stage < (DELAYED ? 2 : 1); ++stage) {
             bool inb = false;
             if (want) {
                 double z[D];
                 if (injected) {
-                    if (!draw_injected<D>(p.streams, c, live, 1u << lane, z, u)) status |= ST_STREAM_EXHAUSTED;
+                    if (!draw_injected<D>(p.streams, c, live, live, 1u << lane, z, u)) status |= ST_STREAM_EXHAUSTED;
                 } else {
                     draw_philox<D>(p.seed, p.chain_offset + (uint64_t)c, (uint64_t)it, (uint32_t)stage, z, u);
                 }

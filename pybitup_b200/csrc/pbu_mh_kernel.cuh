@@ -359,8 +359,17 @@ __device__ __forceinline__ void draw_philox(uint64_t seed, uint64_t chain, uint6
 
 // Parity mode: the chain's next D normals and one uniform from the injected streams; the cursors live
 // in global memory (every lane of a group reads them, the writer lane advances them after the draw).
+// A padding group (live == false: its chain index is clamped onto the last real chain) must NOT read that chain's
+// cursors: the real owner advances them concurrently, so two lanes of the padding group could see different values,
+// disagree on the proposal and on whether it is inside the prior box, and part ways before the group's shuffles.
 template <int D, bool UNIFORM = true>
-__device__ __forceinline__ bool draw_injected(const StreamsDev &s, int64_t c, bool advance, unsigned group_mask, double (&z)[D], double &u) {
+__device__ __forceinline__ bool draw_injected(const StreamsDev &s, int64_t c, bool live, bool advance, unsigned group_mask, double (&z)[D], double &u) {
+    if (!live) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) z[i] = 0.0;
+        u = 1.0;
+        return true;
+    }
     const int64_t cn = s.cur_n[c], cu = s.cur_u[c];
     __syncwarp(group_mask);
     const bool ok = !(cn + D > s.n_normals || (UNIFORM && cu + 1 > s.n_uniforms));
@@ -432,9 +441,16 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
         bool want[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-            want[q] = true;
+            // padding slots (chain index clamped onto the last real chain) sit the iteration out: they would read that
+            // chain's adaptive state and stream cursors while its owner updates them, and the lanes of one padding group
+            // could then disagree on a proposal and leave the group's shuffles at different points
+            want[q] = live[q];
             acc[q] = 0;
+            lp1[q] = 0.0;
             lp2[q] = nan("");
+            r[q] = 0.0;
+            alpha[q] = 0.0;
+            u[q] = 1.0;
         }
 #pragma unroll 1
         for (int stage = 0; stage < (DELAYED ? 2 : 1); ++stage) {
@@ -444,7 +460,7 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
                 if (!want[q]) continue;
                 double z[D];
                 if (injected) {
-                    if (!draw_injected<D>(p.streams, c[q], live[q] && sub == 0, group_mask, z, u[q])) status[q] |= ST_STREAM_EXHAUSTED;
+                    if (!draw_injected<D>(p.streams, c[q], live[q], live[q] && sub == 0, group_mask, z, u[q])) status[q] |= ST_STREAM_EXHAUSTED;
                 } else {
                     draw_philox<D>(p.seed, p.chain_offset + (uint64_t)c[q], (uint64_t)it, (uint32_t)stage, z, u[q]);
                 }

@@ -95,6 +95,11 @@ __device__ __forceinline__ unsigned long long order_key(double v) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(v);
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
+static inline unsigned long long order_key_host(double v) {
+    unsigned long long b;
+    memcpy(&b, &v, sizeof b);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
 __host__ __device__ inline double key_to_double(unsigned long long k) {
     const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
     double v;
@@ -106,30 +111,81 @@ __host__ __device__ inline double key_to_double(unsigned long long k) {
     return v;
 }
 
-// one pass of the MSD radix select: byte `pass` (0 = most significant) of the keys that match prefix[row][t]
+// one pass of the MSD radix select: byte `pass` (0 = most significant) of the keys that match prefix[row][t].
+//   * eight loads in flight per thread (the pass is a pure HBM stream of the evaluations);
+//   * ranks whose prefixes coincide (the two order statistics around one percentile nearly always do) are counted once;
+//   * each thread run-length encodes its matches: the samples of a design point cluster, so in the early passes nearly
+//     every key falls in the same bin -- one shared-memory atomic per run instead of a 32-way conflict per key.
+// run-length counting of one rank's matches (all state in scalars: arrays indexed by the rank end up in local memory)
+__device__ __forceinline__ void select_feed(bool on, unsigned long long km, unsigned long long pf, int digit, int &cur, unsigned int &cnt,
+                                            unsigned int *bins) {
+    if (on && km == pf) {
+        if (digit == cur) {
+            cnt += 1u;
+        } else {
+            if (cnt) atomicAdd(&bins[cur], cnt);
+            cur = digit;
+            cnt = 1u;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) select_hist_kernel(const double *f, int64_t S, int T, int pass, const unsigned long long *prefix,
                                                           unsigned long long *hist) {
+    static_assert(MAX_T == 4, "the kernel is written out for four ranks");
     __shared__ unsigned int sh[MAX_T][256];
     const int row = blockIdx.x, split = blockIdx.y;
     for (int i = threadIdx.x; i < MAX_T * 256; i += blockDim.x) (&sh[0][0])[i] = 0u;
     __syncthreads();
     const int shift = 56 - 8 * pass;
     const unsigned long long mask = (pass == 0) ? 0ull : (~0ull << (shift + 8));
-    unsigned long long pf[MAX_T];
-    for (int t = 0; t < MAX_T; ++t) pf[t] = (t < T) ? prefix[(int64_t)row * T + t] : 0ull;
+    const unsigned long long *pr = prefix + (int64_t)row * T;
+    const unsigned long long pf0 = pr[0] & mask, pf1 = (T > 1) ? (pr[1] & mask) : 0ull, pf2 = (T > 2) ? (pr[2] & mask) : 0ull,
+                             pf3 = (T > 3) ? (pr[3] & mask) : 0ull;
+    // rep_t: first rank with the same (masked) prefix -- the one that is counted
+    const int rep1 = (pf1 == pf0) ? 0 : 1;
+    const int rep2 = (pf2 == pf0) ? 0 : ((pf2 == pf1) ? 1 : 2);
+    const int rep3 = (pf3 == pf0) ? 0 : ((pf3 == pf1) ? 1 : ((pf3 == pf2) ? 2 : 3));
+    const bool on1 = T > 1 && rep1 == 1, on2 = T > 2 && rep2 == 2, on3 = T > 3 && rep3 == 3;
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    unsigned int n0 = 0u, n1 = 0u, n2 = 0u, n3 = 0u;
     const int64_t per = (S + gridDim.y - 1) / gridDim.y;
     const int64_t lo = split * per, hi = (lo + per < S) ? lo + per : S;
     const double *r = f + (int64_t)row * S;
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        const unsigned long long k = order_key(r[i]);
-        const unsigned int digit = (unsigned int)(k >> shift) & 255u;
-        for (int t = 0; t < MAX_T; ++t)
-            if (t < T && ((k ^ pf[t]) & mask) == 0ull) atomicAdd(&sh[t][digit], 1u);
+    int64_t i = lo + threadIdx.x;
+    const int64_t st = blockDim.x;
+#define PBU_SELECT_FEED(v)                                    \
+    do {                                                      \
+        const unsigned long long k_ = order_key(v);           \
+        const int dg_ = (int)((k_ >> shift) & 255ull);        \
+        const unsigned long long km_ = k_ & mask;             \
+        select_feed(true, km_, pf0, dg_, c0, n0, sh[0]);      \
+        select_feed(on1, km_, pf1, dg_, c1, n1, sh[1]);       \
+        select_feed(on2, km_, pf2, dg_, c2, n2, sh[2]);       \
+        select_feed(on3, km_, pf3, dg_, c3, n3, sh[3]);       \
+    } while (0)
+    for (; i + 7 * st < hi; i += 8 * st) {          // eight loads in flight per thread: ~64 KB per SM, what 6 TB/s needs
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcs(r + i + u * st);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) PBU_SELECT_FEED(v[u]);
     }
+    for (; i < hi; i += st) {
+        const double v = r[i];
+        PBU_SELECT_FEED(v);
+    }
+#undef PBU_SELECT_FEED
+    if (n0) atomicAdd(&sh[0][c0], n0);
+    if (n1) atomicAdd(&sh[1][c1], n1);
+    if (n2) atomicAdd(&sh[2][c2], n2);
+    if (n3) atomicAdd(&sh[3][c3], n3);
     __syncthreads();
-    for (int i = threadIdx.x; i < T * 256; i += blockDim.x) {
-        const unsigned int v = (&sh[0][0])[i];
-        if (v) atomicAdd(&hist[(int64_t)row * T * 256 + i], (unsigned long long)v);
+    for (int j = threadIdx.x; j < T * 256; j += blockDim.x) {
+        const int t = j >> 8;
+        const int src = (t == 0) ? 0 : ((t == 1) ? rep1 : ((t == 2) ? rep2 : rep3));
+        const unsigned int v = sh[src][j & 255];
+        if (v) atomicAdd(&hist[(int64_t)row * T * 256 + j], (unsigned long long)v);
     }
 }
 
@@ -267,46 +323,76 @@ PBU_API int pbu_propagation_moments(pbu_propagation *p, double *sum_host, double
 }
 
 // radix select of `n_ranks` order statistics per design point.  ranks host [n_ranks]: 0-based ranks in the sorted
-// GLOBAL sample (all GPUs).  Protocol per pass 0..7: select_pass fills hist_host [N][n_ranks][256] with this engine's
-// counts; the caller sums them over GPUs and hands the total to select_update.
-PBU_API int pbu_propagation_select_begin(pbu_propagation *p, const int64_t *ranks, int n_ranks) {
+// GLOBAL sample (all GPUs).  Protocol per pass first_pass..7: select_pass fills hist_host [N][n_ranks][256] with this
+// engine's counts; the caller sums them over GPUs and hands the total to select_update.
+PBU_API int pbu_propagation_select_begin(pbu_propagation *p, const int64_t *ranks, int n_ranks, const double *row_min, const double *row_max,
+                                         int *first_pass) {
     if (!p || !ranks || n_ranks < 1 || n_ranks > MAX_T) return fail(PBU_ERR_INVALID, "need 1..%d ranks", MAX_T);
     if (!p->evaluated) return fail(PBU_ERR_INVALID, "propagation has not been evaluated");
+    if ((row_min == nullptr) != (row_max == nullptr)) return fail(PBU_ERR_INVALID, "row_min and row_max go together");
     pbu_engine *e = p->e;
     CUDA_TRY(cudaSetDevice(e->device));
     p->T = n_ranks;
     std::vector<long long> r((size_t)p->N * n_ranks);
+    std::vector<unsigned long long> pre((size_t)p->N * n_ranks, 0ull);
     for (int k = 0; k < p->N; ++k)
         for (int t = 0; t < n_ranks; ++t) r[(size_t)k * n_ranks + t] = ranks[t];
+    // With the GLOBAL minimum and maximum of every design point (the moments, reduced over all GPUs) the leading bytes
+    // that all its keys share are known: those passes are skipped, for every point alike (the smallest shared length).
+    int skip = 0;
+    if (row_min) {
+        skip = 8;
+        for (int k = 0; k < p->N; ++k) {
+            if (!(row_min[k] <= row_max[k])) {          // NaN bounds: no information
+                skip = 0;
+                break;
+            }
+            const unsigned long long x = order_key_host(row_min[k]) ^ order_key_host(row_max[k]);
+            int same = 8;
+            for (int b = 0; b < 8; ++b)
+                if ((x >> (56 - 8 * b)) & 255ull) {
+                    same = b;
+                    break;
+                }
+            skip = std::min(skip, same);
+        }
+        const unsigned long long keep = (skip == 0) ? 0ull : ((skip >= 8) ? ~0ull : (~0ull << (64 - 8 * skip)));
+        for (int k = 0; k < p->N; ++k)
+            for (int t = 0; t < n_ranks; ++t) pre[(size_t)k * n_ranks + t] = order_key_host(row_min[k]) & keep;
+    }
+    if (first_pass) *first_pass = skip;
     CUDA_TRY(cudaMemcpyAsync(p->d_rank, r.data(), r.size() * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(cudaMemsetAsync(p->d_prefix, 0, (size_t)p->N * n_ranks * sizeof(unsigned long long), e->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->d_prefix, pre.data(), pre.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     return PBU_OK;
 }
 
 PBU_API int pbu_propagation_select_pass(pbu_propagation *p, int pass, uint64_t *hist_host) {
-    if (!p || p->T < 1 || pass < 0 || pass > 7 || !hist_host) return fail(PBU_ERR_INVALID, "bad argument");
+    if (!p || p->T < 1 || pass < 0 || pass > 7) return fail(PBU_ERR_INVALID, "bad argument");
     pbu_engine *e = p->e;
     CUDA_TRY(cudaSetDevice(e->device));
     const size_t n = (size_t)p->N * p->T * 256;
     CUDA_TRY(cudaMemsetAsync(p->d_hist, 0, n * sizeof(unsigned long long), e->stream));
     select_hist_kernel<<<dim3(p->N, NSPLIT), 256, 0, e->stream>>>(p->d_f, p->S, p->T, pass, p->d_prefix, p->d_hist);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(hist_host, p->d_hist, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
-    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (hist_host) {          // NULL: single GPU, the counts stay on the device for select_update(..., NULL)
+        CUDA_TRY(cudaMemcpyAsync(hist_host, p->d_hist, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    }
     return PBU_OK;
 }
 
 PBU_API int pbu_propagation_select_update(pbu_propagation *p, int pass, const uint64_t *hist_total_host) {
-    if (!p || p->T < 1 || pass < 0 || pass > 7 || !hist_total_host) return fail(PBU_ERR_INVALID, "bad argument");
+    if (!p || p->T < 1 || pass < 0 || pass > 7) return fail(PBU_ERR_INVALID, "bad argument");
     pbu_engine *e = p->e;
     CUDA_TRY(cudaSetDevice(e->device));
     const size_t n = (size_t)p->N * p->T * 256;
-    CUDA_TRY(cudaMemcpyAsync(p->d_hist, hist_total_host, n * sizeof(unsigned long long), cudaMemcpyHostToDevice, e->stream));
+    if (hist_total_host)      // NULL: use the counts select_pass left on the device (single GPU, nothing to sum)
+        CUDA_TRY(cudaMemcpyAsync(p->d_hist, hist_total_host, n * sizeof(unsigned long long), cudaMemcpyHostToDevice, e->stream));
     const int items = p->N * p->T;
     select_update_kernel<<<(items + 127) / 128, 128, 0, e->stream>>>(p->N, p->T, pass, p->d_prefix, p->d_rank, p->d_hist);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (hist_total_host) CUDA_TRY(cudaStreamSynchronize(e->stream));
     return PBU_OK;
 }
 

@@ -92,10 +92,18 @@ class DevicePropagation:
             ranks.extend(percentile_ranks(n_total, q))
         r = np.ascontiguousarray(np.asarray(ranks, dtype=np.int64))
         T = len(ranks)
-        capi.check(capi.lib.pbu_propagation_select_begin(self._h, r.ctypes.data_as(C.POINTER(C.c_int64)), T))
+        # the reduced min / max bound every key: the passes over the bytes they share are skipped
+        first = C.c_int(0)
+        gmn, gmx = np.ascontiguousarray(mn, dtype=np.float64), np.ascontiguousarray(mx, dtype=np.float64)
+        capi.check(capi.lib.pbu_propagation_select_begin(self._h, r.ctypes.data_as(C.POINTER(C.c_int64)), T, capi.dptr(gmn), capi.dptr(gmx),
+                                                         C.byref(first)))
         hist = np.empty((N, T, 256), dtype=np.uint64)
         hp = hist.ctypes.data_as(C.POINTER(C.c_uint64))
-        for p in range(8):
+        for p in range(first.value, 8):
+            if reduce is None:          # one GPU: the histograms stay on the device, the passes are queued back to back
+                capi.check(capi.lib.pbu_propagation_select_pass(self._h, p, None))
+                capi.check(capi.lib.pbu_propagation_select_update(self._h, p, None))
+                continue
             capi.check(capi.lib.pbu_propagation_select_pass(self._h, p, hp))
             tot = np.ascontiguousarray(ident(hist.view(np.int64), "sum")).view(np.uint64)
             capi.check(capi.lib.pbu_propagation_select_update(self._h, p, tot.ctypes.data_as(C.POINTER(C.c_uint64))))

@@ -65,7 +65,7 @@ def test_propagation_gaussian_samples_and_sharding():
         assert np.array_equal(np.minimum(*mns), whole["min"]) and np.array_equal(np.maximum(*mxs), whole["max"])
         ranks = np.array(list(percentile_ranks(S, 2.5)) + list(percentile_ranks(S, 97.5)), dtype=np.int64)
         for h in halves:
-            capi.check(capi.lib.pbu_propagation_select_begin(h._h, ranks.ctypes.data_as(C.POINTER(C.c_int64)), 4))
+            capi.check(capi.lib.pbu_propagation_select_begin(h._h, ranks.ctypes.data_as(C.POINTER(C.c_int64)), 4, None, None, None))
         for ps in range(8):
             hs = []
             for h in halves:
