@@ -111,28 +111,30 @@ PBU_HD double pbu_log(double u) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Table-driven variants: the same functions at 10 FP64 instructions each (against 17 and 22), paid for with one
-// shared-memory load.  The FP64 pipe is what bounds the ODE models, the load/store pipe is idle there.
-//   pbu_exp_tab : x = (64 k + j) ln2/64 + r, |r| <= ln2/128;  exp(x) = 2^k T[j] (1 + r + r^2 P3(r)),  T[j] = 2^(j/64)
-//   pbu_log_tab : u = 2^e m, m in [1, 2), i = top 7 mantissa bits;  r = m c_i - 1, |r| <= 2^-8 (one FMA, exact to
-//                 rounding);  log u = e ln2 - ln c_i + (r - r^2/2 + ... - r^6/6)
+// Table-driven base-2 variants: 2^y in 9 and log2(u) in 8 FP64 instructions (against 17 and 22 above), paid for with
+// one shared-memory load each.  The FP64 pipe is what bounds the ODE models, the load/store pipe is idle there.  Base 2
+// makes both argument reductions exact and removes the ln2 hi/lo bookkeeping; u^n = 2^(n log2 u) needs nothing else.
+//   pbu_exp2_tab : y = k + j/64 + r, |r| <= 2^-7 (r = y - (64k+j)/64 EXACTLY, one FMA);
+//                  2^y = 2^k T[j] (1 + r (b1 + b2 r + .. + b5 r^4)),  T[j] = 2^(j/64),  b_i = ln2^i / i!
+//   pbu_log2_tab : u = 2^e m, m in [1, 2), i = top 7 mantissa bits;  r = m c_i - 1, |r| <= 2^-8 (one FMA);
+//                  log2 u = e + (-log2 c_i + r (a1 + a2 r + .. + a6 r^5)),  a_i = (-1)^(i+1) / (i ln2)
 // Tables: pbu_math_tables.h (generated by tools/gen_math_tables.py), 64 + 2*128 doubles.  On the device the kernels
 // stage them in shared memory once per block (Model::block_init) and pass the pointer; on the host the static copy.
-// Checked against libm in tools/test_math.cu: exp <= 1 ulp; log <= 1 ulp of max(|log u|, 1) -- the error that
-// matters for exp(n log u) is the absolute one (c_127 = 1/2 keeps it below 6e-17 for u just below 1).
+// Checked against libm in tools/test_math.cu: exp2 <= 1 ulp; log2 <= 1 ulp of max(|log2 u|, 1) -- the error that
+// matters for 2^(n log2 u) is the absolute one.
 #define PBU_MATH_TABLE_DOUBLES (64 + 256)
-static const double pbu_math_tables_host[PBU_MATH_TABLE_DOUBLES] = {PBU_EXP2_TABLE, PBU_LOG_TABLE};
+static const double pbu_math_tables_host[PBU_MATH_TABLE_DOUBLES] = {PBU_EXP2_TABLE, PBU_LOG2_TABLE};
 #ifdef __CUDACC__
-static __device__ const double pbu_math_tables_dev[PBU_MATH_TABLE_DOUBLES] = {PBU_EXP2_TABLE, PBU_LOG_TABLE};
+static __device__ const double pbu_math_tables_dev[PBU_MATH_TABLE_DOUBLES] = {PBU_EXP2_TABLE, PBU_LOG2_TABLE};
 #endif
 
-// tab: the PBU_MATH_TABLE_DOUBLES doubles above (exp2 table first).  Domain x < 709; x <= -708 (and -inf) returns a
-// denormal (< 5e-309) instead of the exact tail: the range test and the result selection are integer instructions, the
-// FP64 pipe sees the ten arithmetic ones only.  NaN propagates.
-PBU_HD double pbu_exp_tab(double x, const double *tab) {
-    const bool tiny = (uint32_t)(hi_word(x) - (int32_t)0xC0862000) <= 0x3F69E000u;      // -inf <= x <= -708
-    const double SHIFT = 6755399441055744.0;
-    const double t = fma(x, 92.33248261689366, SHIFT);           // 64 / ln2
+// 2^y.  tab: the PBU_MATH_TABLE_DOUBLES doubles above (exp2 table first).  Domain y < 1024; y <= -1022 (and -inf)
+// returns a denormal (< 5e-309) instead of the exact tail: the range test and the result selection are integer
+// instructions, the FP64 pipe sees the nine arithmetic ones only.  NaN propagates.
+PBU_HD double pbu_exp2_tab(double y, const double *tab) {
+    const bool tiny = (uint32_t)(hi_word(y) - (int32_t)0xC08FF000) <= 0x3F601000u;      // -inf <= y <= -1022
+    const double SHIFT = 6755399441055744.0;                     // 1.5 * 2^52
+    const double t = fma(y, 64.0, SHIFT);
     const double kf = t - SHIFT;                                 // 64 k + j as a double
     const int32_t m = (int32_t)(uint32_t)(
 #ifdef __CUDA_ARCH__
@@ -141,22 +143,22 @@ PBU_HD double pbu_exp_tab(double x, const double *tab) {
         [](double v) { uint64_t b; memcpy(&b, &v, 8); return (int32_t)(uint32_t)b; }(t)
 #endif
     );
-    double r = fma(kf, -0.6931471803691238 / 64.0, x);           // (ln2/64)_hi keeps 32 significant bits: kf * hi exact
-    r = fma(kf, -1.9082149292705877e-10 / 64.0, r);
-    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
-    const double v = fma(r * r, p, r);                           // exp(r) - 1, remainder r^6/720 < 4e-17
+    const double r = fma(kf, -0.015625, y);                      // exact
+    double p = fma(r, 1.3333558146428443e-03, 9.6181291076284772e-03);      // ln2^5/120, ln2^4/24
+    p = fma(p, r, 5.5504108664821580e-02);                       // ln2^3/6
+    p = fma(p, r, 2.4022650695910072e-01);                       // ln2^2/2
+    p = fma(p, r, 6.9314718055994531e-01);                       // ln2
+    const double v = p * r;                                      // 2^r - 1, remainder (r ln2)^6/720 < 4e-17
     const double T = tab[m & 63];
     const double e = fma(T, v, T);
     const int32_t rh = hi_word(e) + ((m >> 6) << 20);            // * 2^k on the exponent field (k >= -1022 here)
     return with_hi_word(e, tiny ? 0 : rh);
 }
 
-// true for positive, normal, finite u: the arguments pbu_log_tab accepts (an integer test)
+// true for positive, normal, finite u: the arguments pbu_log2_tab accepts (an integer test)
 PBU_HD bool pbu_log_arg_ok(double u) { return (uint32_t)(hi_word(u) - 0x00100000) < 0x7FE00000u; }
 
-PBU_HD double pbu_log_tab(double u, const double *tab) {
+PBU_HD double pbu_log2_tab(double u, const double *tab) {
     const int32_t hi = hi_word(u);
     const int32_t e = (hi >> 20) - 1023;
     const int32_t i = (hi >> 13) & 127;
@@ -168,13 +170,12 @@ PBU_HD double pbu_log_tab(double u, const double *tab) {
     const double c = tab[64 + 2 * i], nlc = tab[64 + 2 * i + 1];
 #endif
     const double r = fma(m, c, -1.0);
-    double q = fma(r, -1.0 / 6.0, 0.2);
-    q = fma(q, r, -0.25);
-    q = fma(q, r, 1.0 / 3.0);
-    q = fma(q, r, -0.5);
-    const double ef = (double)e;
-    const double lo = fma(r * r, q, fma(ef, 1.9082149292705877e-10, r));
-    return fma(ef, 0.6931471803691238, nlc + lo);                // e*ln2_hi exact inside the FMA: one rounding at full size
+    double q = fma(r, -2.4044917348149392e-01, 2.8853900817779266e-01);     // -1/(6 ln2), 1/(5 ln2)
+    q = fma(q, r, -3.6067376022224085e-01);                      // -1/(4 ln2)
+    q = fma(q, r, 4.8089834696298783e-01);                       // 1/(3 ln2)
+    q = fma(q, r, -7.2134752044448170e-01);                      // -1/(2 ln2)
+    q = fma(q, r, 1.4426950408889634e+00);                       // 1/ln2
+    return fma(r, q, nlc) + (double)e;                           // small part first: one rounding at full size
 }
 
 }  // namespace pbu

@@ -150,13 +150,17 @@ struct ArrheniusModel {
     struct Seq {
         double alpha, g0;
     };
+    // c0 and ER are kept in base 2 (divided by ln 2): the stage rates are 2^(c0 - ER/T) (pbu_exp2_tab); c0 also carries
+    // log2(h), so that the exponentials return the rates already multiplied by the step
     __device__ __forceinline__ static void begin(Ctx &c, const double (&theta)[4], const double *consts) {
-        c.c0 = 2.302585092994046 * theta[0] - log(consts[2]) + log(consts[1]);   // ln(10)*log10A - ln(beta) + ln(h)
-        c.ER = theta[1] / R_GAS;
+        const double c0 = 2.302585092994046 * theta[0] - log(consts[2]) + log(consts[1]);   // ln(10)*log10A - ln(beta) + ln(h)
+        const double ER = theta[1] / R_GAS;
+        c.c0 = c0 * 1.4426950408889634;
+        c.ER = ER * 1.4426950408889634;
         c.n = theta[2];
         c.F = theta[3];
         c.h = consts[1];
-        c.g_start = exp(c.c0 - c.ER * (1.0 / consts[0]));
+        c.g_start = exp(c0 - ER * (1.0 / consts[0]));
     }
     __device__ __forceinline__ static void seq_init(const Ctx &c, Seq &s, const double *) {
         s.alpha = 0.0;
@@ -172,20 +176,20 @@ struct ArrheniusModel {
         double *t = tables();
         for (int i = threadIdx.x; i < PBU_MATH_TABLE_DOUBLES; i += blockDim.x) t[i] = pbu_math_tables_dev[i];
     }
-    // u^n for u in (0, 1] as exp(n log u) with the table-driven pbu_exp_tab / pbu_log_tab (pbu_math.cuh): relative
-    // error below 1e-14 against pow() (tools/test_math.cu), far inside the 1e-10 parity bar, at 22 FP64 instructions
+    // u^n for u in (0, 1] as 2^(n log2 u) with the table-driven pbu_exp2_tab / pbu_log2_tab (pbu_math.cuh): relative
+    // error below 2e-14 against pow() (tools/test_math.cu), far inside the 1e-10 parity bar, at 18 FP64 instructions
     // u <= 0 (conversion complete, or overshot by a stage), denormal or NaN u: 0.  The log of such an argument is finite
     // garbage, discarded by the selection; no FP64 instruction is spent on the test.
     __device__ __forceinline__ static double pw(double u, double n) {
-        const double v = pbu_exp_tab(n * pbu_log_tab(u, tables()), tables());
+        const double v = pbu_exp2_tab(n * pbu_log2_tab(u, tables()), tables());
         return pbu_log_arg_ok(u) ? v : 0.0;
     }
     // One RK4 step of d(alpha)/dT = g(T) (1 - alpha)^n.  c.c0 carries ln(h) (see begin): the exponentials return the
     // stage rates already multiplied by the step.  Written on u = 1 - alpha for the stage arguments; this differs from
     // the oracle's 1 - (alpha + k/2) by rounding only (<= 2 ulp of u), far inside the 1e-10 parity bar.
     __device__ __forceinline__ static double step(const Ctx &c, Seq &s, double inv_mid, double inv_end) {
-        const double gm = pbu_exp_tab(fma(-c.ER, inv_mid, c.c0), tables());
-        const double g1 = pbu_exp_tab(fma(-c.ER, inv_end, c.c0), tables());
+        const double gm = pbu_exp2_tab(fma(-c.ER, inv_mid, c.c0), tables());
+        const double g1 = pbu_exp2_tab(fma(-c.ER, inv_end, c.c0), tables());
         const double a = s.alpha;
         const double u0 = 1.0 - a;
         const double k1 = s.g0 * pw(u0, c.n);

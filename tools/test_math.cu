@@ -32,17 +32,18 @@ int main() {
         mp = fmax(mp, rel);
         if (el > 2.0) ++bad;
         // table-driven variants: exp in ulp; log in ulp of max(|log u|, 1) (absolute accuracy is what exp(n log u) needs)
-        met = fmax(met, ulp_err(pbu::pbu_exp_tab(x, tab), exp(x)));
-        const double lt = pbu::pbu_log_tab(u, tab);
-        mlt = fmax(mlt, fabs(lt - lr) / ldexp(1.0, ilogb(fmax(fabs(lr), 1.0)) - 52));
-        const double pwt = pbu::pbu_exp_tab(n * lt, tab);
+        met = fmax(met, ulp_err(pbu::pbu_exp2_tab(x, tab), exp2(x)));
+        const double lt = pbu::pbu_log2_tab(u, tab), lr2 = log2(u);
+        mlt = fmax(mlt, fabs(lt - lr2) / ldexp(1.0, ilogb(fmax(fabs(lr2), 1.0)) - 52));
+        const double pwt = pbu::pbu_exp2_tab(n * lt, tab);
         mpt = fmax(mpt, pr > 0 ? fabs(pwt - pr) / pr : 0.0);
     }
     printf("max ulp error: exp %.3f  log %.3f   max relative error of exp(n log u) vs pow: %.3e   log errors > 2 ulp: %ld\n", me, ml, mp, bad);
     printf("edge: exp(0)=%.17g log(1)=%.17g exp(-701)=%g log(0.5)=%.17g (ref %.17g)\n", pbu::pbu_exp(0.0), pbu::pbu_log(1.0), pbu::pbu_exp(-701.0),
            pbu::pbu_log(0.5), log(0.5));
-    printf("table-driven: max ulp error exp %.3f  log (ulp of max(|log|, 1)) %.3f   exp(n log u) vs pow: %.3e\n", met, mlt, mpt);
-    printf("edge: exp_tab(0)=%.17g log_tab(1)=%.17g log_tab(1-2^-53)=%.17g (ref %.17g) log_tab(0.5)=%.17g\n", pbu::pbu_exp_tab(0.0, tab),
-           pbu::pbu_log_tab(1.0, tab), pbu::pbu_log_tab(1.0 - ldexp(1.0, -53), tab), log(1.0 - ldexp(1.0, -53)), pbu::pbu_log_tab(0.5, tab));
+    printf("table-driven, base 2: max ulp error exp2 %.3f  log2 (ulp of max(|log2|, 1)) %.3f   2^(n log2 u) vs pow: %.3e\n", met, mlt, mpt);
+    printf("edge: exp2_tab(0)=%.17g log2_tab(1)=%.17g log2_tab(1-2^-53)=%.17g (ref %.17g) log2_tab(0.5)=%.17g exp2_tab(-1022.5)=%g\n",
+           pbu::pbu_exp2_tab(0.0, tab), pbu::pbu_log2_tab(1.0, tab), pbu::pbu_log2_tab(1.0 - ldexp(1.0, -53), tab),
+           log2(1.0 - ldexp(1.0, -53)), pbu::pbu_log2_tab(0.5, tab), pbu::pbu_exp2_tab(-1022.5, tab));
     return (me < 2.0 && ml < 2.5 && mp < 2e-14 && met < 2.0 && mlt < 2.5 && mpt < 2e-14) ? 0 : 1;
 }
