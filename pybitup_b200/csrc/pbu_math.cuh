@@ -128,11 +128,40 @@ static const double pbu_math_tables_host[PBU_MATH_TABLE_DOUBLES] = {PBU_EXP2_TAB
 static __device__ const double pbu_math_tables_dev[PBU_MATH_TABLE_DOUBLES] = {PBU_EXP2_TABLE, PBU_LOG2_TABLE};
 #endif
 
-// 2^y.  tab: the PBU_MATH_TABLE_DOUBLES doubles above (exp2 table first).  Domain y < 1024; y <= -1022 (and -inf)
-// returns a denormal (< 5e-309) instead of the exact tail: the range test and the result selection are integer
-// instructions, the FP64 pipe sees the nine arithmetic ones only.  NaN propagates.
-PBU_HD double pbu_exp2_tab(double y, const double *tab) {
-    const bool tiny = (uint32_t)(hi_word(y) - (int32_t)0xC08FF000) <= 0x3F601000u;      // -inf <= y <= -1022
+// Polynomial coefficients.  On the device they are read as constant-bank operands of the DFMAs (a __constant__ array
+// the compiler cannot fold): written as literals ptxas rebuilds every 64-bit constant with two UMOVs inside the loop,
+// about 30 instruction-issue slots per RK4 step, and on this kernel every issued instruction is a cycle the FP64 pipe
+// idles (an FP64 instruction holds the issue port for 2 cycles, everything else for 1; ncu: issue slots add up to the
+// elapsed cycles).
+#define PBU_K_B5 1.3333558146428443e-03                          // ln2^5/120
+#define PBU_K_B4 9.6181291076284772e-03                          // ln2^4/24
+#define PBU_K_B3 5.5504108664821580e-02                          // ln2^3/6
+#define PBU_K_B2 2.4022650695910072e-01                          // ln2^2/2
+#define PBU_K_B1 6.9314718055994531e-01                          // ln2
+#define PBU_K_A6 -2.4044917348149392e-01                         // -1/(6 ln2)
+#define PBU_K_A5 2.8853900817779266e-01                          // 1/(5 ln2)
+#define PBU_K_A4 -3.6067376022224085e-01                         // -1/(4 ln2)
+#define PBU_K_A3 4.8089834696298783e-01                          // 1/(3 ln2)
+#define PBU_K_A2 -7.2134752044448170e-01                         // -1/(2 ln2)
+#define PBU_K_A1 1.4426950408889634e+00                          // 1/ln2
+#ifdef __CUDACC__
+static __constant__ double pbu_kc[11] = {PBU_K_B5, PBU_K_B4, PBU_K_B3, PBU_K_B2, PBU_K_B1, PBU_K_A6,
+                                         PBU_K_A5, PBU_K_A4, PBU_K_A3, PBU_K_A2, PBU_K_A1};
+#endif
+#ifdef __CUDA_ARCH__
+#define PBU_KC(i, lit) pbu_kc[i]
+#else
+#define PBU_KC(i, lit) (lit)
+#endif
+
+// 2^y, hi word of the result forced to 0 where !keep (the caller's own range test rides on the selection that is
+// already there).  tab: the PBU_MATH_TABLE_DOUBLES doubles above (exp2 table first).  Domain y < 1024; y <= -1022 (and
+// -inf) returns a denormal (< 2.3e-308) instead of the exact tail: the hi word of y is clamped as an unsigned integer
+// (one instruction; negative doubles order by magnitude), which lands in k = -1022 or -1023 and leaves at most the
+// mantissa bits.  The FP64 pipe sees the nine arithmetic instructions only.  NaN with the sign bit clear propagates.
+PBU_HD double pbu_exp2_tab_sel(double y, const double *tab, bool keep) {
+    const uint32_t yh = (uint32_t)hi_word(y);
+    y = with_hi_word(y, (int32_t)(yh < 0xC08FF000u ? yh : 0xC08FF000u));        // y >= -1022.001
     const double SHIFT = 6755399441055744.0;                     // 1.5 * 2^52
     const double t = fma(y, 64.0, SHIFT);
     const double kf = t - SHIFT;                                 // 64 k + j as a double
@@ -144,16 +173,22 @@ PBU_HD double pbu_exp2_tab(double y, const double *tab) {
 #endif
     );
     const double r = fma(kf, -0.015625, y);                      // exact
-    double p = fma(r, 1.3333558146428443e-03, 9.6181291076284772e-03);      // ln2^5/120, ln2^4/24
-    p = fma(p, r, 5.5504108664821580e-02);                       // ln2^3/6
-    p = fma(p, r, 2.4022650695910072e-01);                       // ln2^2/2
-    p = fma(p, r, 6.9314718055994531e-01);                       // ln2
+    double p = fma(r, PBU_KC(0, PBU_K_B5), PBU_KC(1, PBU_K_B4));
+    p = fma(p, r, PBU_KC(2, PBU_K_B3));
+    p = fma(p, r, PBU_KC(3, PBU_K_B2));
+    p = fma(p, r, PBU_KC(4, PBU_K_B1));
     const double v = p * r;                                      // 2^r - 1, remainder (r ln2)^6/720 < 4e-17
     const double T = tab[m & 63];
     const double e = fma(T, v, T);
-    const int32_t rh = hi_word(e) + ((m >> 6) << 20);            // * 2^k on the exponent field (k >= -1022 here)
-    return with_hi_word(e, tiny ? 0 : rh);
+    int32_t rh;                                                  // * 2^k on the exponent field (k >= -1023 here)
+#ifdef __CUDA_ARCH__
+    asm("{\n\t.reg .s32 k;\n\tshr.s32 k, %1, 6;\n\tmad.lo.s32 %0, k, 1048576, %2;\n\t}" : "=r"(rh) : "r"(m), "r"(hi_word(e)));
+#else
+    rh = hi_word(e) + (m >> 6) * 1048576;
+#endif
+    return with_hi_word(e, keep ? rh : 0);
 }
+PBU_HD double pbu_exp2_tab(double y, const double *tab) { return pbu_exp2_tab_sel(y, tab, true); }
 
 // true for positive, normal, finite u: the arguments pbu_log2_tab accepts (an integer test)
 PBU_HD bool pbu_log_arg_ok(double u) { return (uint32_t)(hi_word(u) - 0x00100000) < 0x7FE00000u; }
@@ -162,19 +197,19 @@ PBU_HD double pbu_log2_tab(double u, const double *tab) {
     const int32_t hi = hi_word(u);
     const int32_t e = (hi >> 20) - 1023;
     const int32_t i = (hi >> 13) & 127;
-    const double m = with_hi_word(u, (hi & 0x000fffff) | 0x3ff00000);
+    const double m = with_hi_word(u, (hi & 0x000FFFFF) | 0x3FF00000);
 #ifdef __CUDA_ARCH__
-    const double2 cl = reinterpret_cast<const double2 *>(tab + 64)[i];
+    const double2 cl = *reinterpret_cast<const double2 *>(tab + 64 + 2 * i);    // one 16-byte shared-memory load
     const double c = cl.x, nlc = cl.y;
 #else
     const double c = tab[64 + 2 * i], nlc = tab[64 + 2 * i + 1];
 #endif
     const double r = fma(m, c, -1.0);
-    double q = fma(r, -2.4044917348149392e-01, 2.8853900817779266e-01);     // -1/(6 ln2), 1/(5 ln2)
-    q = fma(q, r, -3.6067376022224085e-01);                      // -1/(4 ln2)
-    q = fma(q, r, 4.8089834696298783e-01);                       // 1/(3 ln2)
-    q = fma(q, r, -7.2134752044448170e-01);                      // -1/(2 ln2)
-    q = fma(q, r, 1.4426950408889634e+00);                       // 1/ln2
+    double q = fma(r, PBU_KC(5, PBU_K_A6), PBU_KC(6, PBU_K_A5));
+    q = fma(q, r, PBU_KC(7, PBU_K_A4));
+    q = fma(q, r, PBU_KC(8, PBU_K_A3));
+    q = fma(q, r, PBU_KC(9, PBU_K_A2));
+    q = fma(q, r, PBU_KC(10, PBU_K_A1));
     return fma(r, q, nlc) + (double)e;                           // small part first: one rounding at full size
 }
 

@@ -178,11 +178,10 @@ struct ArrheniusModel {
     }
     // u^n for u in (0, 1] as 2^(n log2 u) with the table-driven pbu_exp2_tab / pbu_log2_tab (pbu_math.cuh): relative
     // error below 2e-14 against pow() (tools/test_math.cu), far inside the 1e-10 parity bar, at 18 FP64 instructions
-    // u <= 0 (conversion complete, or overshot by a stage), denormal or NaN u: 0.  The log of such an argument is finite
-    // garbage, discarded by the selection; no FP64 instruction is spent on the test.
+    // u <= 0 (conversion complete, or overshot by a stage), denormal or NaN u: 0 up to a denormal (hi word cleared).  The
+    // log of such an argument is finite garbage, discarded by the selection; no FP64 instruction is spent on the test.
     __device__ __forceinline__ static double pw(double u, double n) {
-        const double v = pbu_exp2_tab(n * pbu_log2_tab(u, tables()), tables());
-        return pbu_log_arg_ok(u) ? v : 0.0;
+        return pbu_exp2_tab_sel(n * pbu_log2_tab(u, tables()), tables(), pbu_log_arg_ok(u));
     }
     // One RK4 step of d(alpha)/dT = g(T) (1 - alpha)^n.  c.c0 carries ln(h) (see begin): the exponentials return the
     // stage rates already multiplied by the step.  Written on u = 1 - alpha for the stage arguments; this differs from
