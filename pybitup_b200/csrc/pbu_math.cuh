@@ -111,18 +111,19 @@ PBU_HD double pbu_log(double u) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Table-driven base-2 variants: 2^y in 9 and log2(u) in 8 FP64 instructions (against 17 and 22 above), paid for with
+// Table-driven base-2 variants: 2^y in 8 and log2(u) in 7 FP64 instructions (against 17 and 22 above), paid for with
 // one shared-memory load each.  The FP64 pipe is what bounds the ODE models, the load/store pipe is idle there.  Base 2
 // makes both argument reductions exact and removes the ln2 hi/lo bookkeeping; u^n = 2^(n log2 u) needs nothing else.
-//   pbu_exp2_tab : y = k + j/64 + r, |r| <= 2^-7 (r = y - (64k+j)/64 EXACTLY, one FMA);
-//                  2^y = 2^k T[j] (1 + r (b1 + b2 r + .. + b5 r^4)),  T[j] = 2^(j/64),  b_i = ln2^i / i!
-//   pbu_log2_tab : u = 2^e m, m in [1, 2), i = top 7 mantissa bits;  r = m c_i - 1, |r| <= 2^-8 (one FMA);
-//                  log2 u = e + (-log2 c_i + r (a1 + a2 r + .. + a6 r^5)),  a_i = (-1)^(i+1) / (i ln2)
-// Tables: pbu_math_tables.h (generated by tools/gen_math_tables.py), 64 + 2*128 doubles.  On the device the kernels
+//   pbu_exp2_tab : y = k + j/512 + r, |r| <= 2^-10 (r = y - (512k+j)/512 EXACTLY, one FMA);
+//                  2^y = 2^k T[j] (1 + r (b1 + b2 r + b3 r^2 + b4 r^3)),  T[j] = 2^(j/512),  b_i = ln2^i / i!
+//   pbu_log2_tab : u = 2^e m, m in [1, 2), i = top 8 mantissa bits;  r = m c_i - 1, |r| <= 2^-9 (one FMA);
+//                  log2 u = e + (-log2 c_i + r (a1 + a2 r + .. + a5 r^4)),  a_i = (-1)^(i+1) / (i ln2)
+// Tables: pbu_math_tables.h (generated by tools/gen_math_tables.py), 512 + 2*256 doubles (8 KB).  On the device the kernels
 // stage them in shared memory once per block (Model::block_init) and pass the pointer; on the host the static copy.
 // Checked against libm in tools/test_math.cu: exp2 <= 1 ulp; log2 <= 1 ulp of max(|log2 u|, 1) -- the error that
 // matters for 2^(n log2 u) is the absolute one.
-#define PBU_MATH_TABLE_DOUBLES (64 + 256)
+#define PBU_MATH_TABLE_DOUBLES (512 + 512)
+#define PBU_LOG2_TABLE_OFFSET 512
 static const double pbu_math_tables_host[PBU_MATH_TABLE_DOUBLES] = {PBU_EXP2_TABLE, PBU_LOG2_TABLE};
 #ifdef __CUDACC__
 static __device__ const double pbu_math_tables_dev[PBU_MATH_TABLE_DOUBLES] = {PBU_EXP2_TABLE, PBU_LOG2_TABLE};
@@ -133,20 +134,17 @@ static __device__ const double pbu_math_tables_dev[PBU_MATH_TABLE_DOUBLES] = {PB
 // about 30 instruction-issue slots per RK4 step, and on this kernel every issued instruction is a cycle the FP64 pipe
 // idles (an FP64 instruction holds the issue port for 2 cycles, everything else for 1; ncu: issue slots add up to the
 // elapsed cycles).
-#define PBU_K_B5 1.3333558146428443e-03                          // ln2^5/120
 #define PBU_K_B4 9.6181291076284772e-03                          // ln2^4/24
 #define PBU_K_B3 5.5504108664821580e-02                          // ln2^3/6
 #define PBU_K_B2 2.4022650695910072e-01                          // ln2^2/2
 #define PBU_K_B1 6.9314718055994531e-01                          // ln2
-#define PBU_K_A6 -2.4044917348149392e-01                         // -1/(6 ln2)
 #define PBU_K_A5 2.8853900817779266e-01                          // 1/(5 ln2)
 #define PBU_K_A4 -3.6067376022224085e-01                         // -1/(4 ln2)
 #define PBU_K_A3 4.8089834696298783e-01                          // 1/(3 ln2)
 #define PBU_K_A2 -7.2134752044448170e-01                         // -1/(2 ln2)
 #define PBU_K_A1 1.4426950408889634e+00                          // 1/ln2
 #ifdef __CUDACC__
-static __constant__ double pbu_kc[11] = {PBU_K_B5, PBU_K_B4, PBU_K_B3, PBU_K_B2, PBU_K_B1, PBU_K_A6,
-                                         PBU_K_A5, PBU_K_A4, PBU_K_A3, PBU_K_A2, PBU_K_A1};
+static __constant__ double pbu_kc[9] = {PBU_K_B4, PBU_K_B3, PBU_K_B2, PBU_K_B1, PBU_K_A5, PBU_K_A4, PBU_K_A3, PBU_K_A2, PBU_K_A1};
 #endif
 #ifdef __CUDA_ARCH__
 #define PBU_KC(i, lit) pbu_kc[i]
@@ -158,13 +156,13 @@ static __constant__ double pbu_kc[11] = {PBU_K_B5, PBU_K_B4, PBU_K_B3, PBU_K_B2,
 // already there).  tab: the PBU_MATH_TABLE_DOUBLES doubles above (exp2 table first).  Domain y < 1024; y <= -1022 (and
 // -inf) returns a denormal (< 2.3e-308) instead of the exact tail: the hi word of y is clamped as an unsigned integer
 // (one instruction; negative doubles order by magnitude), which lands in k = -1022 or -1023 and leaves at most the
-// mantissa bits.  The FP64 pipe sees the nine arithmetic instructions only.  NaN with the sign bit clear propagates.
+// mantissa bits.  The FP64 pipe sees the eight arithmetic instructions only.  NaN with the sign bit clear propagates.
 PBU_HD double pbu_exp2_tab_sel(double y, const double *tab, bool keep) {
     const uint32_t yh = (uint32_t)hi_word(y);
     y = with_hi_word(y, (int32_t)(yh < 0xC08FF000u ? yh : 0xC08FF000u));        // y >= -1022.001
     const double SHIFT = 6755399441055744.0;                     // 1.5 * 2^52
-    const double t = fma(y, 64.0, SHIFT);
-    const double kf = t - SHIFT;                                 // 64 k + j as a double
+    const double t = fma(y, 512.0, SHIFT);
+    const double kf = t - SHIFT;                                 // 512 k + j as a double
     const int32_t m = (int32_t)(uint32_t)(
 #ifdef __CUDA_ARCH__
         __double2loint(t)
@@ -172,19 +170,24 @@ PBU_HD double pbu_exp2_tab_sel(double y, const double *tab, bool keep) {
         [](double v) { uint64_t b; memcpy(&b, &v, 8); return (int32_t)(uint32_t)b; }(t)
 #endif
     );
-    const double r = fma(kf, -0.015625, y);                      // exact
-    double p = fma(r, PBU_KC(0, PBU_K_B5), PBU_KC(1, PBU_K_B4));
-    p = fma(p, r, PBU_KC(2, PBU_K_B3));
-    p = fma(p, r, PBU_KC(3, PBU_K_B2));
-    p = fma(p, r, PBU_KC(4, PBU_K_B1));
-    const double v = p * r;                                      // 2^r - 1, remainder (r ln2)^6/720 < 4e-17
-    const double T = tab[m & 63];
+    const double r = fma(kf, -0.001953125, y);                   // exact
+    double p = fma(r, PBU_KC(0, PBU_K_B4), PBU_KC(1, PBU_K_B3));
+    p = fma(p, r, PBU_KC(2, PBU_K_B2));
+    p = fma(p, r, PBU_KC(3, PBU_K_B1));
+    const double v = p * r;                                      // 2^r - 1, remainder (r ln2)^5/120 < 1.3e-18
+#ifdef __CUDA_ARCH__
+    double T;                                                    // explicit shared-space load with the address built as
+    asm("{\n\t.reg .u32 j;\n\tand.b32 j, %1, 511;\n\tmad.lo.u32 j, j, 8, %2;\n\tld.shared.f64 %0, [j];\n\t}"       // mask, multiply-add
+        : "=d"(T) : "r"(m), "r"((uint32_t)__cvta_generic_to_shared(tab)));   // (two instructions; shift, mask, add otherwise)
+#else
+    const double T = tab[m & 511];
+#endif
     const double e = fma(T, v, T);
     int32_t rh;                                                  // * 2^k on the exponent field (k >= -1023 here)
 #ifdef __CUDA_ARCH__
-    asm("{\n\t.reg .s32 k;\n\tshr.s32 k, %1, 6;\n\tmad.lo.s32 %0, k, 1048576, %2;\n\t}" : "=r"(rh) : "r"(m), "r"(hi_word(e)));
+    asm("{\n\t.reg .s32 k;\n\tshr.s32 k, %1, 9;\n\tmad.lo.s32 %0, k, 1048576, %2;\n\t}" : "=r"(rh) : "r"(m), "r"(hi_word(e)));
 #else
-    rh = hi_word(e) + (m >> 6) * 1048576;
+    rh = hi_word(e) + (m >> 9) * 1048576;
 #endif
     return with_hi_word(e, keep ? rh : 0);
 }
@@ -196,20 +199,20 @@ PBU_HD bool pbu_log_arg_ok(double u) { return (uint32_t)(hi_word(u) - 0x00100000
 PBU_HD double pbu_log2_tab(double u, const double *tab) {
     const int32_t hi = hi_word(u);
     const int32_t e = (hi >> 20) - 1023;
-    const int32_t i = (hi >> 13) & 127;
     const double m = with_hi_word(u, (hi & 0x000FFFFF) | 0x3FF00000);
 #ifdef __CUDA_ARCH__
-    const double2 cl = *reinterpret_cast<const double2 *>(tab + 64 + 2 * i);    // one 16-byte shared-memory load
+    const int32_t i = (hi >> 12) & 255;
+    const double2 cl = *reinterpret_cast<const double2 *>(tab + PBU_LOG2_TABLE_OFFSET + 2 * i);    // one 16-byte shared-memory load
     const double c = cl.x, nlc = cl.y;
 #else
-    const double c = tab[64 + 2 * i], nlc = tab[64 + 2 * i + 1];
+    const int32_t i = (hi >> 12) & 255;
+    const double c = tab[PBU_LOG2_TABLE_OFFSET + 2 * i], nlc = tab[PBU_LOG2_TABLE_OFFSET + 2 * i + 1];
 #endif
     const double r = fma(m, c, -1.0);
-    double q = fma(r, PBU_KC(5, PBU_K_A6), PBU_KC(6, PBU_K_A5));
-    q = fma(q, r, PBU_KC(7, PBU_K_A4));
-    q = fma(q, r, PBU_KC(8, PBU_K_A3));
-    q = fma(q, r, PBU_KC(9, PBU_K_A2));
-    q = fma(q, r, PBU_KC(10, PBU_K_A1));
+    double q = fma(r, PBU_KC(4, PBU_K_A5), PBU_KC(5, PBU_K_A4));     // remainder r^6 / (6 ln2) < 1.4e-17
+    q = fma(q, r, PBU_KC(6, PBU_K_A3));
+    q = fma(q, r, PBU_KC(7, PBU_K_A2));
+    q = fma(q, r, PBU_KC(8, PBU_K_A1));
     return fma(r, q, nlc) + (double)e;                           // small part first: one rounding at full size
 }
 

@@ -167,7 +167,7 @@ struct ArrheniusModel {
         s.g0 = c.g_start;
     }
     // exp / log lookup tables of pbu_math.cuh, staged once per block (every kernel calls block_init before its first
-    // __syncthreads): 2.5 KB of static shared memory
+    // __syncthreads): 8 KB of static shared memory
     __device__ __forceinline__ static double *tables() {
         __shared__ __align__(16) double tab[PBU_MATH_TABLE_DOUBLES];
         return tab;
@@ -177,7 +177,7 @@ struct ArrheniusModel {
         for (int i = threadIdx.x; i < PBU_MATH_TABLE_DOUBLES; i += blockDim.x) t[i] = pbu_math_tables_dev[i];
     }
     // u^n for u in (0, 1] as 2^(n log2 u) with the table-driven pbu_exp2_tab / pbu_log2_tab (pbu_math.cuh): relative
-    // error below 2e-14 against pow() (tools/test_math.cu), far inside the 1e-10 parity bar, at 18 FP64 instructions
+    // error below 2e-14 against pow() (tools/test_math.cu), far inside the 1e-10 parity bar, at 16 FP64 instructions
     // u <= 0 (conversion complete, or overshot by a stage), denormal or NaN u: 0 up to a denormal (hi word cleared).  The
     // log of such an argument is finite garbage, discarded by the selection; no FP64 instruction is spent on the test.
     __device__ __forceinline__ static double pw(double u, double n) {
