@@ -142,6 +142,7 @@ __device__ __forceinline__ void tile_accumulate(const typename M::Ctx (&ctx)[Q],
                                                 int sub, double (&J)[Q][U], double (&g)[Q][GRAD ? M::NPARAM : 1]) {
     constexpr int NC = M::NC;
     if (M::SEQUENTIAL) {
+#pragma unroll 2
         for (int k = 0; k < n; ++k) {
             double rec[1][NC];
             load_record<NC>(tile, k, rec[0]);
