@@ -243,6 +243,22 @@ int pbu_propagation_select_begin(pbu_propagation *p, const int64_t *ranks, int n
 int pbu_propagation_select_pass(pbu_propagation *p, int pass, uint64_t *hist_host);
 int pbu_propagation_select_update(pbu_propagation *p, int pass, const uint64_t *hist_total_host);
 int pbu_propagation_select_result(pbu_propagation *p, double *values_host /*[N][n_ranks]*/);
+/* Bracketed select, the fast path for large S (same np.percentile, solve_problem.py:639-647, ONE pass over the evaluations
+ * instead of up to eight).  n_q = 1 or 2 percentiles.
+ *   1. bracket_sample: radix-selects a subsample (every stride-th chunk of 256 values of each design point) at ranks six
+ *      binomial standard deviations either side of fractions[q] (in [0, 1]) -> brackets_host [N][n_q][2] = (a, b), -inf / +inf
+ *      where the margin reaches the ends.  Over GPUs: min-reduce a, max-reduce b.
+ *   2. bracket_pass: one pass with the global brackets: sum / min / max as pbu_propagation_moments (this replaces that
+ *      call), below / inside host [N][n_q] = this engine's counts of values < a and in [a, b]; the values inside go to a
+ *      candidate buffer of 4 cap_hint + 4096 slots per (point, percentile), *overflow != 0 if that was too small.  Over
+ *      GPUs: sum the counts, max-reduce the flag.  The wanted global ranks r must satisfy below <= r < below + inside for
+ *      every point, else (or on overflow) fall back to pbu_propagation_select_begin.
+ *   3. bracket_select_begin with ranks_in_bracket host [N][2 n_q] (= r - below) and the global brackets, then select_pass /
+ *      select_update / select_result exactly as above, over the candidates only. */
+int pbu_propagation_bracket_sample(pbu_propagation *p, const double *fractions, int n_q, int stride, double *brackets_host);
+int pbu_propagation_bracket_pass(pbu_propagation *p, const double *brackets_host, int n_q, int64_t cap_hint, double *sum_host, double *min_host,
+                                 double *max_host, int64_t *below_host, int64_t *inside_host, int *overflow);
+int pbu_propagation_bracket_select_begin(pbu_propagation *p, const int64_t *ranks_in_bracket, const double *brackets_host, int *first_pass);
 /* evaluations of samples [s0, s0+n) on the host, sample-major [n][N] (fun_eval, :571) */
 int pbu_propagation_get_evals(pbu_propagation *p, int64_t s0, int64_t n, double *f_host);
 

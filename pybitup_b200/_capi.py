@@ -110,6 +110,9 @@ def _load():
         "pbu_propagation_select_pass": (C.c_int, [E, C.c_int, C.POINTER(C.c_uint64)]),
         "pbu_propagation_select_update": (C.c_int, [E, C.c_int, C.POINTER(C.c_uint64)]),
         "pbu_propagation_select_result": (C.c_int, [E, _dp]),
+        "pbu_propagation_bracket_sample": (C.c_int, [E, _dp, C.c_int, C.c_int, _dp]),
+        "pbu_propagation_bracket_pass": (C.c_int, [E, _dp, C.c_int, C.c_int64, _dp, _dp, _dp, _lp, _lp, C.POINTER(C.c_int)]),
+        "pbu_propagation_bracket_select_begin": (C.c_int, [E, _lp, _dp, C.POINTER(C.c_int)]),
         "pbu_propagation_get_evals": (C.c_int, [E, C.c_int64, C.c_int64, _dp]),
         "pbu_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp]),
     }

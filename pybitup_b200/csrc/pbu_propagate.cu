@@ -30,6 +30,15 @@ struct pbu_propagation {
     long long *d_rank = nullptr;              // [N][T] remaining rank inside the prefix class
     unsigned long long *d_hist = nullptr;     // [N][T][256]
     bool evaluated = false;
+    // bracketed select (large S): subsample, bracket values, candidates between the brackets
+    double *d_sub = nullptr;                  // [N][sub_m] every stride-th 256-chunk of each row
+    int64_t sub_m = 0;
+    double *d_brk = nullptr;                  // [N][nq][2] bracket (a, b) per design point and percentile
+    unsigned long long *d_cnt = nullptr;      // [2][N][nq]: values below a | values inside [a, b]
+    double *d_cand = nullptr;                 // [N][nq][cap] the values inside [a, b], unordered
+    int64_t cap = 0;
+    int nq = 0;
+    bool cand_mode = false;                   // select_pass reads the candidates instead of the evaluations
 };
 
 static constexpr int NSPLIT = 16;
@@ -208,6 +217,157 @@ __global__ void select_update_kernel(int n_rows, int T, int pass, unsigned long 
     prefix[i] |= (unsigned long long)digit << (56 - 8 * pass);
 }
 
+
+// ------------------------------------------------------------------------------------------------ bracketed select
+// For large S the eight full passes of the radix select are replaced by ONE pass over the evaluations:
+//   1. a subsample (every stride-th chunk of 256 values of each row) is radix-selected at ranks a safe distance either
+//      side of each percentile: a bracket [a, b] that holds the wanted order statistics unless the subsample is freakishly
+//      unrepresentative (the counts of step 2 tell; the caller then falls back to the full radix select);
+//   2. one pass over the evaluations accumulates sum / min / max, counts the values below a and copies the values
+//      inside [a, b] (a fraction of a percent) to a candidate buffer;
+//   3. the radix select runs on the candidates alone.
+// Sharded over GPUs the brackets are min / max-reduced, the counts summed, and step 3 sums histograms as before.
+__global__ void subsample_gather_kernel(const double *f, int64_t S, int stride, int64_t m, double *sub) {
+    const int row = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int64_t src = (i >> 8) * 256 * stride + (i & 255);
+    sub[(int64_t)row * m + i] = f[(int64_t)row * S + src];
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(256) bracket_pass_kernel(const double *f, int64_t S, const double *brk, double *part, unsigned long long *below,
+                                                           unsigned long long *inside, double *cand, int64_t cap) {
+    __shared__ double wbuf[8][NQ][64];        // per warp and percentile: values waiting to be flushed (at most 63)
+    __shared__ double sh[3][8];
+    const int row = blockIdx.x, split = blockIdx.y, w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const unsigned lt = (1u << l) - 1u;
+    double a[NQ], b[NQ];
+    unsigned int nb[NQ];
+    int wc[NQ];                               // warp-uniform fill of wbuf[w][q]
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        a[q] = brk[((int64_t)row * NQ + q) * 2];
+        b[q] = brk[((int64_t)row * NQ + q) * 2 + 1];
+        nb[q] = 0u;
+        wc[q] = 0;
+    }
+    const int64_t per = (S + gridDim.y - 1) / gridDim.y;
+    const int64_t lo = split * per, hi = (lo + per < S) ? lo + per : S;
+    const double *r = f + (int64_t)row * S;
+    double sum = 0.0, mn = INFINITY, mx = -INFINITY;
+    // one warp-wide flush of wbuf[w][q]: a single global atomic reserves the slots
+    auto flush = [&](int q) {
+        __syncwarp();
+        const int n = wc[q];
+        unsigned long long off = 0ull;
+        if (l == 0) off = atomicAdd(&inside[(int64_t)row * NQ + q], (unsigned long long)n);
+        off = __shfl_sync(0xffffffffu, off, 0);
+        double *dst = cand + ((int64_t)row * NQ + q) * cap;
+        for (int j = l; j < n; j += 32)
+            if ((int64_t)(off + j) < cap) dst[off + j] = wbuf[w][q][j];
+        __syncwarp();
+        wc[q] = 0;
+    };
+    auto feed = [&](bool valid, double v) {
+        bool in[NQ], any = false;
+        if (valid) {
+            sum += v;
+            mn = fmin(mn, v);
+            mx = fmax(mx, v);
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            nb[q] += (valid && v < a[q]) ? 1u : 0u;
+            in[q] = valid && v >= a[q] && v <= b[q];
+            any = any || in[q];
+        }
+        if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const unsigned msk = __ballot_sync(0xffffffffu, in[q]);
+                if (msk) {
+                    if (in[q]) wbuf[w][q][wc[q] + __popc(msk & lt)] = v;
+                    wc[q] += __popc(msk);
+                    if (wc[q] >= 32) flush(q);
+                }
+            }
+        }
+    };
+    const int64_t st = blockDim.x;
+    int64_t base = lo;
+    for (; base + 8 * st <= hi; base += 8 * st) {          // block-uniform trip count: the warp votes need every lane
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcs(r + base + threadIdx.x + u * st);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) feed(true, v[u]);
+    }
+    for (; base < hi; base += st) {
+        const int64_t i = base + threadIdx.x;
+        const bool valid = i < hi;
+        feed(valid, valid ? r[i] : 0.0);
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        if (wc[q] > 0) flush(q);
+        unsigned int c = nb[q];
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (l == 0 && c) atomicAdd(&below[(int64_t)row * NQ + q], (unsigned long long)c);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (l == 0) {
+        sh[0][w] = sum;
+        sh[1][w] = mn;
+        sh[2][w] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) {
+            sum += sh[0][i];
+            mn = fmin(mn, sh[1][i]);
+            mx = fmax(mx, sh[2][i]);
+        }
+        double *o = part + ((int64_t)row * gridDim.y + split) * 3;
+        o[0] = sum;
+        o[1] = mn;
+        o[2] = mx;
+    }
+}
+
+// one radix pass over the candidates of (row, percentile): the two ranks 2q, 2q+1 of that percentile; one block each,
+// so the histogram rows are written, not accumulated
+__global__ void __launch_bounds__(256) cand_hist_kernel(const double *cand, const unsigned long long *inside, int64_t cap, int nq, int pass,
+                                                        const unsigned long long *prefix, unsigned long long *hist) {
+    __shared__ unsigned int sh[2][256];
+    const int rq = blockIdx.x, row = rq / nq, q = rq - row * nq, T = 2 * nq;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) (&sh[0][0])[i] = 0u;
+    __syncthreads();
+    const int shift = 56 - 8 * pass;
+    const unsigned long long mask = (pass == 0) ? 0ull : (~0ull << (shift + 8));
+    const unsigned long long pf0 = prefix[(int64_t)row * T + 2 * q] & mask, pf1 = prefix[(int64_t)row * T + 2 * q + 1] & mask;
+    const bool two = pf1 != pf0;
+    unsigned long long n = inside[rq];
+    if (n > (unsigned long long)cap) n = (unsigned long long)cap;
+    const double *c = cand + (int64_t)rq * cap;
+    for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long k = order_key(c[i]);
+        const unsigned long long km = k & mask;
+        const int dg = (int)((k >> shift) & 255ull);
+        if (km == pf0) atomicAdd(&sh[0][dg], 1u);
+        if (two && km == pf1) atomicAdd(&sh[1][dg], 1u);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 512; j += blockDim.x) {
+        const int t = j >> 8;
+        hist[((int64_t)row * T + 2 * q + t) * 256 + (j & 255)] = sh[(t == 1 && !two) ? 0 : t][j & 255];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ C ABI
 PBU_API int pbu_propagation_create(pbu_engine *e, int64_t n_samples, pbu_propagation **out) {
     if (!e || !out || n_samples < 1) return fail(PBU_ERR_INVALID, "bad argument");
@@ -244,6 +404,7 @@ PBU_API int pbu_propagation_destroy(pbu_propagation *p) {
     cudaSetDevice(p->e->device);
     cudaStreamSynchronize(p->e->stream);
     cudaFree(p->d_X), cudaFree(p->d_f), cudaFree(p->d_part), cudaFree(p->d_prefix), cudaFree(p->d_rank), cudaFree(p->d_hist);
+    cudaFree(p->d_sub), cudaFree(p->d_brk), cudaFree(p->d_cnt), cudaFree(p->d_cand);
     delete p;
     return PBU_OK;
 }
@@ -333,6 +494,7 @@ PBU_API int pbu_propagation_select_begin(pbu_propagation *p, const int64_t *rank
     pbu_engine *e = p->e;
     CUDA_TRY(cudaSetDevice(e->device));
     p->T = n_ranks;
+    p->cand_mode = false;
     std::vector<long long> r((size_t)p->N * n_ranks);
     std::vector<unsigned long long> pre((size_t)p->N * n_ranks, 0ull);
     for (int k = 0; k < p->N; ++k)
@@ -373,7 +535,10 @@ PBU_API int pbu_propagation_select_pass(pbu_propagation *p, int pass, uint64_t *
     CUDA_TRY(cudaSetDevice(e->device));
     const size_t n = (size_t)p->N * p->T * 256;
     CUDA_TRY(cudaMemsetAsync(p->d_hist, 0, n * sizeof(unsigned long long), e->stream));
-    select_hist_kernel<<<dim3(p->N, NSPLIT), 256, 0, e->stream>>>(p->d_f, p->S, p->T, pass, p->d_prefix, p->d_hist);
+    if (p->cand_mode)
+        cand_hist_kernel<<<p->N * p->nq, 256, 0, e->stream>>>(p->d_cand, p->d_cnt + (size_t)p->N * p->nq, p->cap, p->nq, pass, p->d_prefix, p->d_hist);
+    else
+        select_hist_kernel<<<dim3(p->N, NSPLIT), 256, 0, e->stream>>>(p->d_f, p->S, p->T, pass, p->d_prefix, p->d_hist);
     CUDA_TRY(cudaGetLastError());
     if (hist_host) {          // NULL: single GPU, the counts stay on the device for select_update(..., NULL)
         CUDA_TRY(cudaMemcpyAsync(hist_host, p->d_hist, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
@@ -405,6 +570,164 @@ PBU_API int pbu_propagation_select_result(pbu_propagation *p, double *values_hos
     CUDA_TRY(cudaMemcpyAsync(k.data(), p->d_prefix, k.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     for (size_t i = 0; i < k.size(); ++i) values_host[i] = key_to_double(k[i]);
+    return PBU_OK;
+}
+
+// ---- bracketed select (see the kernels above).  n_q = 1 or 2 percentiles, fractions[q] in [0, 1].
+// Step 1: brackets from this engine's subsample.  brackets_host [N][n_q][2] = (a, b); -inf / +inf where the safety margin
+// reaches the ends of the subsample.  The caller min-reduces a and max-reduces b over GPUs.
+static int shared_key_bytes(double lo, double hi) {
+    const unsigned long long x = order_key_host(lo) ^ order_key_host(hi);
+    for (int b = 0; b < 8; ++b)
+        if ((x >> (56 - 8 * b)) & 255ull) return b;
+    return 8;
+}
+
+PBU_API int pbu_propagation_bracket_sample(pbu_propagation *p, const double *fractions, int n_q, int stride, double *brackets_host) {
+    if (!p || !fractions || n_q < 1 || 2 * n_q > MAX_T || stride < 1 || !brackets_host) return fail(PBU_ERR_INVALID, "bad argument");
+    if (!p->evaluated) return fail(PBU_ERR_INVALID, "propagation has not been evaluated");
+    pbu_engine *e = p->e;
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int64_t group = (int64_t)256 * stride, full = p->S / group, rem = p->S - full * group;
+    const int64_t m = full * 256 + std::min<int64_t>(rem, 256);
+    if (m < 1024) return fail(PBU_ERR_INVALID, "subsample of %lld values is too small for a bracket: use the full radix select", (long long)m);
+    if (p->sub_m != m) {
+        cudaFree(p->d_sub);
+        p->d_sub = nullptr;
+        p->sub_m = 0;
+        CUDA_TRY(cudaMalloc(&p->d_sub, (size_t)p->N * m * sizeof(double)));
+        p->sub_m = m;
+    }
+    subsample_gather_kernel<<<dim3((unsigned)((m + 255) / 256), p->N), 256, 0, e->stream>>>(p->d_f, p->S, stride, m, p->d_sub);
+    CUDA_TRY(cudaGetLastError());
+    // ranks in the subsample: the percentile's position -/+ 6 standard deviations of a binomial count (+ slack)
+    const int T = 2 * n_q;
+    std::vector<long long> rk((size_t)p->N * T);
+    std::vector<int> open_lo(n_q), open_hi(n_q);
+    for (int q = 0; q < n_q; ++q) {
+        const double f = std::min(1.0, std::max(0.0, fractions[q]));
+        const double k = f * (double)(m - 1), dl = 6.0 * std::sqrt((double)m * f * (1.0 - f)) + 8.0;
+        long long lo = (long long)std::floor(k - dl), hi = (long long)std::ceil(k + dl) + 1;
+        open_lo[q] = lo < 0;
+        open_hi[q] = hi > m - 1;
+        lo = std::max<long long>(lo, 0);
+        hi = std::min<long long>(hi, m - 1);
+        for (int r = 0; r < p->N; ++r) {
+            rk[(size_t)r * T + 2 * q] = lo;
+            rk[(size_t)r * T + 2 * q + 1] = hi;
+        }
+    }
+    p->T = T;
+    p->cand_mode = false;
+    CUDA_TRY(cudaMemcpyAsync(p->d_rank, rk.data(), rk.size() * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemsetAsync(p->d_prefix, 0, (size_t)p->N * T * sizeof(unsigned long long), e->stream));
+    for (int pass = 0; pass < 8; ++pass) {
+        CUDA_TRY(cudaMemsetAsync(p->d_hist, 0, (size_t)p->N * T * 256 * sizeof(unsigned long long), e->stream));
+        select_hist_kernel<<<dim3(p->N, NSPLIT), 256, 0, e->stream>>>(p->d_sub, m, T, pass, p->d_prefix, p->d_hist);
+        select_update_kernel<<<(p->N * T + 127) / 128, 128, 0, e->stream>>>(p->N, T, pass, p->d_prefix, p->d_rank, p->d_hist);
+    }
+    CUDA_TRY(cudaGetLastError());
+    std::vector<unsigned long long> k((size_t)p->N * T);
+    CUDA_TRY(cudaMemcpyAsync(k.data(), p->d_prefix, k.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    for (int r = 0; r < p->N; ++r)
+        for (int q = 0; q < n_q; ++q) {
+            brackets_host[((size_t)r * n_q + q) * 2] = open_lo[q] ? -INFINITY : key_to_double(k[(size_t)r * T + 2 * q]);
+            brackets_host[((size_t)r * n_q + q) * 2 + 1] = open_hi[q] ? INFINITY : key_to_double(k[(size_t)r * T + 2 * q + 1]);
+        }
+    p->T = 0;
+    return PBU_OK;
+}
+
+// Step 2: the one pass over the evaluations with the (global) brackets.  Per design point: sum, min, max as
+// pbu_propagation_moments; below / inside host [N][n_q]: this engine's counts of values < a and in [a, b].  *overflow != 0:
+// more candidates than `cap_hint` (the expected number, the buffer holds four times as many + 4096) -- the caller falls
+// back to the full radix select.
+PBU_API int pbu_propagation_bracket_pass(pbu_propagation *p, const double *brackets_host, int n_q, int64_t cap_hint, double *sum_host, double *min_host,
+                                         double *max_host, int64_t *below_host, int64_t *inside_host, int *overflow) {
+    if (!p || !brackets_host || n_q < 1 || 2 * n_q > MAX_T || cap_hint < 0 || !below_host || !inside_host || !overflow)
+        return fail(PBU_ERR_INVALID, "bad argument");
+    if (!p->evaluated) return fail(PBU_ERR_INVALID, "propagation has not been evaluated");
+    pbu_engine *e = p->e;
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int64_t cap = ((4 * cap_hint + 4096 + 255) / 256) * 256;
+    const size_t nrq = (size_t)p->N * n_q;
+    if (p->cap != cap || p->nq != n_q) {
+        cudaFree(p->d_cand), cudaFree(p->d_brk), cudaFree(p->d_cnt);
+        p->d_cand = p->d_brk = nullptr;
+        p->d_cnt = nullptr;
+        p->cap = 0, p->nq = 0;
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (nrq * (size_t)cap * 8 + (64u << 20) > free_b) return fail(PBU_ERR_INVALID, "no room for %.2f GB of bracket candidates", nrq * (double)cap * 8 / 1e9);
+        CUDA_TRY(cudaMalloc(&p->d_cand, nrq * (size_t)cap * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&p->d_brk, nrq * 2 * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&p->d_cnt, 2 * nrq * sizeof(unsigned long long)));
+        p->cap = cap, p->nq = n_q;
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->d_brk, brackets_host, nrq * 2 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemsetAsync(p->d_cnt, 0, 2 * nrq * sizeof(unsigned long long), e->stream));
+    if (n_q == 1)
+        bracket_pass_kernel<1><<<dim3(p->N, NSPLIT), 256, 0, e->stream>>>(p->d_f, p->S, p->d_brk, p->d_part, p->d_cnt, p->d_cnt + nrq, p->d_cand, cap);
+    else
+        bracket_pass_kernel<2><<<dim3(p->N, NSPLIT), 256, 0, e->stream>>>(p->d_f, p->S, p->d_brk, p->d_part, p->d_cnt, p->d_cnt + nrq, p->d_cand, cap);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<double> part((size_t)p->N * NSPLIT * 3);
+    std::vector<unsigned long long> cnt(2 * nrq);
+    CUDA_TRY(cudaMemcpyAsync(part.data(), p->d_part, part.size() * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(cnt.data(), p->d_cnt, cnt.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    for (int k = 0; k < p->N; ++k) {
+        double s = 0.0, mn = INFINITY, mx = -INFINITY;
+        for (int j = 0; j < NSPLIT; ++j) {
+            const double *o = &part[((size_t)k * NSPLIT + j) * 3];
+            s += o[0];
+            mn = std::min(mn, o[1]);
+            mx = std::max(mx, o[2]);
+        }
+        if (sum_host) sum_host[k] = s;
+        if (min_host) min_host[k] = mn;
+        if (max_host) max_host[k] = mx;
+    }
+    *overflow = 0;
+    for (size_t i = 0; i < nrq; ++i) {
+        below_host[i] = (int64_t)cnt[i];
+        inside_host[i] = (int64_t)cnt[nrq + i];
+        if (cnt[nrq + i] > (unsigned long long)cap) *overflow = 1;
+    }
+    return PBU_OK;
+}
+
+// Step 3: radix select among the candidates.  ranks_in_bracket host [N][2 n_q]: 0-based ranks among ALL GPUs'
+// candidates of that design point and percentile (global rank - global count below a).  brackets_host: the global
+// brackets of step 2 (their shared leading key bytes are skipped).  Then pbu_propagation_select_pass / _update /
+// _result as for the full select, passes *first_pass .. 7, histograms [N][2 n_q][256].
+PBU_API int pbu_propagation_bracket_select_begin(pbu_propagation *p, const int64_t *ranks_in_bracket, const double *brackets_host, int *first_pass) {
+    if (!p || !ranks_in_bracket || !brackets_host || p->nq < 1 || !p->d_cand) return fail(PBU_ERR_INVALID, "no bracket pass has been run");
+    pbu_engine *e = p->e;
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int T = 2 * p->nq;
+    int skip = 8;
+    for (size_t i = 0; i < (size_t)p->N * p->nq; ++i) {
+        const double a = brackets_host[2 * i], b = brackets_host[2 * i + 1];
+        // a zero bound: -0.0 and +0.0 compare equal but their keys differ in the first byte
+        skip = std::min(skip, (!(a <= b) || a == 0.0 || b == 0.0) ? 0 : shared_key_bytes(a, b));
+    }
+    if (skip > 7) skip = 7;
+    const unsigned long long keep = (skip == 0) ? 0ull : (~0ull << (64 - 8 * skip));
+    std::vector<unsigned long long> pre((size_t)p->N * T);
+    std::vector<long long> r((size_t)p->N * T);
+    for (int k = 0; k < p->N; ++k)
+        for (int t = 0; t < T; ++t) {
+            pre[(size_t)k * T + t] = order_key_host(brackets_host[((size_t)k * p->nq + t / 2) * 2]) & keep;
+            r[(size_t)k * T + t] = ranks_in_bracket[(size_t)k * T + t];
+        }
+    p->T = T;
+    p->cand_mode = true;
+    if (first_pass) *first_pass = skip;
+    CUDA_TRY(cudaMemcpyAsync(p->d_rank, r.data(), r.size() * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->d_prefix, pre.data(), pre.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
     return PBU_OK;
 }
 

@@ -76,31 +76,59 @@ class DevicePropagation:
         capi.check(capi.lib.pbu_propagation_get_evals(self._h, int(first), int(count), capi.dptr(out)))
         return out
 
-    def statistics(self, percentiles=(2.5, 97.5), reduce=None, n_total=None):
+    # below this many samples per GPU the full radix select is cheap and the bracket of a subsample is loose
+    BRACKET_MIN_SAMPLES = 1 << 18
+    BRACKET_STRIDE = 64
+
+    def statistics(self, percentiles=(2.5, 97.5), reduce=None, n_total=None, bracket=None):
         """mean, min, max and the percentiles per design point.
 
         reduce(array, op) sums ('sum') or takes the min/max ('min'/'max') of a numpy array over all ranks and returns
-        it; None = single GPU.  n_total = number of samples over all ranks."""
+        it; None = single GPU.  n_total = number of samples over all ranks.  bracket: True / False forces / forbids the
+        one-pass bracketed select (default: used from BRACKET_MIN_SAMPLES samples per GPU and for one or two
+        percentiles); both paths return the same exact order statistics."""
         N = self.n_points
         n_total = self.n_samples if n_total is None else int(n_total)
         ident = (lambda a, op: a) if reduce is None else reduce
-        s, mn, mx = np.empty(N), np.empty(N), np.empty(N)
-        capi.check(capi.lib.pbu_propagation_moments(self._h, capi.dptr(s), capi.dptr(mn), capi.dptr(mx)))
-        s, mn, mx = ident(s, "sum"), ident(mn, "min"), ident(mx, "max")
         ranks = []
         for q in percentiles:
             ranks.extend(percentile_ranks(n_total, q))
         r = np.ascontiguousarray(np.asarray(ranks, dtype=np.int64))
         T = len(ranks)
-        # the reduced min / max bound every key: the passes over the bytes they share are skipped
-        first = C.c_int(0)
-        gmn, gmx = np.ascontiguousarray(mn, dtype=np.float64), np.ascontiguousarray(mx, dtype=np.float64)
-        capi.check(capi.lib.pbu_propagation_select_begin(self._h, r.ctypes.data_as(C.POINTER(C.c_int64)), T, capi.dptr(gmn), capi.dptr(gmx),
-                                                         C.byref(first)))
+        nq = len(percentiles)
+        if bracket is None:          # every rank must take the same branch
+            bracket = bool(ident(np.array([float(self.n_samples >= self.BRACKET_MIN_SAMPLES)]), "min")[0] > 0.0)
+        bracket = bracket and nq in (1, 2)
+        s = mn = mx = None
+        vals = None
+        self.last_select = "radix"
+        if bracket:
+            s, mn, mx, vals = self._bracketed(percentiles, r, n_total, ident, reduce is None)
+        if s is None:
+            s, mn, mx = np.empty(N), np.empty(N), np.empty(N)
+            capi.check(capi.lib.pbu_propagation_moments(self._h, capi.dptr(s), capi.dptr(mn), capi.dptr(mx)))
+            s, mn, mx = ident(s, "sum"), ident(mn, "min"), ident(mx, "max")
+        if vals is None:
+            # the reduced min / max bound every key: the passes over the bytes they share are skipped
+            first = C.c_int(0)
+            gmn, gmx = np.ascontiguousarray(mn, dtype=np.float64), np.ascontiguousarray(mx, dtype=np.float64)
+            capi.check(capi.lib.pbu_propagation_select_begin(self._h, r.ctypes.data_as(C.POINTER(C.c_int64)), T, capi.dptr(gmn), capi.dptr(gmx),
+                                                             C.byref(first)))
+            vals = self._select_passes(first.value, T, ident, reduce is None)
+        out = dict(mean=s / n_total, min=mn, max=mx, n_samples=n_total)
+        for i, q in enumerate(percentiles):
+            out["p%g" % q] = np.array([lerp_percentile(n_total, q, vals[k, 2 * i], vals[k, 2 * i + 1]) for k in range(N)])
+        if tuple(percentiles) == (2.5, 97.5):
+            out["ci_lb"], out["ci_ub"] = out["p2.5"], out["p97.5"]
+        return out
+
+    def _select_passes(self, first, T, ident, single):
+        """radix passes first..7 over whatever select_begin / bracket_select_begin armed; returns the values [N][T]"""
+        N = self.n_points
         hist = np.empty((N, T, 256), dtype=np.uint64)
         hp = hist.ctypes.data_as(C.POINTER(C.c_uint64))
-        for p in range(first.value, 8):
-            if reduce is None:          # one GPU: the histograms stay on the device, the passes are queued back to back
+        for p in range(first, 8):
+            if single:          # one GPU: the histograms stay on the device, the passes are queued back to back
                 capi.check(capi.lib.pbu_propagation_select_pass(self._h, p, None))
                 capi.check(capi.lib.pbu_propagation_select_update(self._h, p, None))
                 continue
@@ -109,12 +137,38 @@ class DevicePropagation:
             capi.check(capi.lib.pbu_propagation_select_update(self._h, p, tot.ctypes.data_as(C.POINTER(C.c_uint64))))
         vals = np.empty((N, T))
         capi.check(capi.lib.pbu_propagation_select_result(self._h, capi.dptr(vals)))
-        out = dict(mean=s / n_total, min=mn, max=mx, n_samples=n_total)
-        for i, q in enumerate(percentiles):
-            out["p%g" % q] = np.array([lerp_percentile(n_total, q, vals[k, 2 * i], vals[k, 2 * i + 1]) for k in range(N)])
-        if tuple(percentiles) == (2.5, 97.5):
-            out["ci_lb"], out["ci_ub"] = out["p2.5"], out["p97.5"]
-        return out
+        return vals
+
+    def _bracketed(self, percentiles, ranks, n_total, ident, single):
+        """One-pass path (include/pybitup_b200.h, 'Bracketed select').  Returns (sum, min, max, values); values is None
+        when the brackets missed a wanted rank or the candidate buffer overflowed (the moments are still good)."""
+        N, nq, S = self.n_points, len(percentiles), self.n_samples
+        stride = self.BRACKET_STRIDE
+        fr = np.ascontiguousarray([q / 100.0 for q in percentiles], dtype=np.float64)
+        brk = np.empty((N, nq, 2))
+        capi.check(capi.lib.pbu_propagation_bracket_sample(self._h, capi.dptr(fr), nq, stride, capi.dptr(brk)))
+        brk = np.ascontiguousarray(np.stack([ident(np.ascontiguousarray(brk[..., 0]), "min"), ident(np.ascontiguousarray(brk[..., 1]), "max")], axis=-1))
+        m = max(S // stride, 1)
+        hint = int(max(S * (2.0 * (6.0 * np.sqrt(m * f * (1.0 - f)) + 8.0) + 3.0) / m for f in fr))
+        s, mn, mx = np.empty(N), np.empty(N), np.empty(N)
+        below, inside = np.empty((N, nq), dtype=np.int64), np.empty((N, nq), dtype=np.int64)
+        ovf = C.c_int(0)
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+        capi.check(capi.lib.pbu_propagation_bracket_pass(self._h, capi.dptr(brk), nq, hint, capi.dptr(s), capi.dptr(mn), capi.dptr(mx), ip(below), ip(inside),
+                                                         C.byref(ovf)))
+        s, mn, mx = ident(s, "sum"), ident(mn, "min"), ident(mx, "max")
+        below, inside = ident(below, "sum"), ident(inside, "sum")
+        overflow = ident(np.array([float(ovf.value)]), "max")[0] > 0.0
+        rk = np.asarray(ranks, dtype=np.int64).reshape(nq, 2)
+        inb = np.ascontiguousarray((rk[None, :, :] - below[:, :, None]).reshape(N, 2 * nq))
+        ok = (not overflow) and bool(np.all(inb >= 0)) and bool(np.all(inb < np.repeat(inside, 2, axis=1)))
+        if not ok:
+            self.last_select = "radix (bracket missed)"
+            return s, mn, mx, None
+        first = C.c_int(0)
+        capi.check(capi.lib.pbu_propagation_bracket_select_begin(self._h, ip(inb), capi.dptr(brk), C.byref(first)))
+        self.last_select = "bracket"
+        return s, mn, mx, self._select_passes(first.value, 2 * nq, ident, single)
 
 
 def propagate(engine, X, percentiles=(2.5, 97.5), return_evals=False):

@@ -83,3 +83,109 @@ def test_propagation_gaussian_samples_and_sharding():
         assert np.array_equal(whole["ci_lb"], np.percentile(fe, 2.5, axis=0))
         for h in halves:
             h.close()
+
+
+def _bracket_problem():
+    from pybitup_b200 import synthetic
+    return synthetic.arrhenius_problem(n_steps=24, dT=25.0)
+
+
+@pytest.mark.parametrize("percentiles", [(2.5, 97.5), (50.0,), (0.001, 99.999)])
+def test_bracketed_select_is_exact(percentiles):
+    """The one-pass bracketed select (subsample brackets -> one pass -> select among the candidates) returns the same
+    exact order statistics as np.percentile / the full radix select, ties and open brackets included."""
+    from pybitup_b200.engine import ChainEngine, ProblemSpec, SamplerConfig
+    from pybitup_b200.propagation import DevicePropagation
+    p = _bracket_problem()
+    S = 200_000 + 37
+    with ChainEngine(ProblemSpec.from_dict(p), SamplerConfig(algo="RWMH"), 1) as eng:
+        with DevicePropagation(eng, S) as dp:
+            dp.evaluate_gaussian(p["x0"], 0.01 * np.abs(p["x0"]), seed=3)
+            fast = dp.statistics(percentiles, bracket=True)
+            assert dp.last_select == "bracket"
+            slow = dp.statistics(percentiles, bracket=False)
+            assert dp.last_select == "radix"
+            fe = dp.evals()
+    for q in percentiles:
+        assert np.array_equal(fast["p%g" % q], np.percentile(fe, q, axis=0))
+        assert np.array_equal(fast["p%g" % q], slow["p%g" % q])
+    assert np.array_equal(fast["min"], fe.min(axis=0)) and np.array_equal(fast["max"], fe.max(axis=0))
+    assert H.rel_err(fast["mean"], fe.mean(axis=0)) < 1e-12
+    assert np.array_equal(fast["mean"], slow["mean"])
+
+
+def test_bracketed_select_falls_back_when_the_subsample_misleads():
+    """Samples laid out so that exactly the chunks the subsample reads come from another distribution: the brackets miss
+    the wanted ranks, the counts of the pass show it, and the full radix select gives the exact answer."""
+    from pybitup_b200 import synthetic
+    from pybitup_b200.engine import ChainEngine, ProblemSpec, SamplerConfig
+    from pybitup_b200.propagation import DevicePropagation
+    p = synthetic.cubic_problem(n_points=9)
+    S = 64 * 256 * 12
+    rng = np.random.default_rng(5)
+    X = p["x0"][None, :] * (1.0 + 0.01 * rng.standard_normal((S, len(p["x0"]))))
+    chunk = (np.arange(S) // 256) % DevicePropagation.BRACKET_STRIDE == 0
+    X[chunk, 0] += 5.0
+    with ChainEngine(ProblemSpec.from_dict(p), SamplerConfig(algo="RWMH"), 1) as eng:
+        with DevicePropagation(eng, S) as dp:
+            dp.evaluate(X)
+            st = dp.statistics(bracket=True)
+            assert dp.last_select == "radix (bracket missed)"
+            fe = dp.evals()
+    assert np.array_equal(st["ci_lb"], np.percentile(fe, 2.5, axis=0))
+    assert np.array_equal(st["ci_ub"], np.percentile(fe, 97.5, axis=0))
+    assert np.array_equal(st["min"], fe.min(axis=0)) and np.array_equal(st["max"], fe.max(axis=0))
+
+
+def test_bracketed_select_sharded_equals_unsharded():
+    """Two shards run the bracket protocol in lock step through a reducer that combines them as an all-reduce would:
+    bit-identical order statistics to the single-engine run."""
+    from pybitup_b200.engine import ChainEngine, ProblemSpec, SamplerConfig
+    from pybitup_b200.propagation import DevicePropagation
+    import threading
+    p = _bracket_problem()
+    S = 300_000
+    mean, std = p["x0"], 0.01 * np.abs(p["x0"])
+    with ChainEngine(ProblemSpec.from_dict(p), SamplerConfig(algo="RWMH"), 1) as eng:
+        with DevicePropagation(eng, S) as dp:
+            dp.evaluate_gaussian(mean, std, seed=11)
+            whole = dp.statistics(bracket=True)
+        halves = [DevicePropagation(eng, S // 2), DevicePropagation(eng, S // 2)]
+        for i, h in enumerate(halves):
+            h.evaluate_gaussian(mean, std, seed=11, sample_offset=i * (S // 2))
+        # a two-party all-reduce between two threads (each drives one shard; the C ABI serialises on the engine's stream)
+        barrier = threading.Barrier(2)
+        slots = [None, None]
+        lock = threading.Lock()
+
+        def make_reduce(me):
+            def red(a, op):
+                a = np.ascontiguousarray(a)
+                slots[me] = a
+                barrier.wait()
+                other = slots[1 - me]
+                res = {"sum": a + other, "min": np.minimum(a, other), "max": np.maximum(a, other)}[op]
+                barrier.wait()
+                return res
+            return red
+
+        outs, errs = [None, None], []
+
+        def run(me):
+            try:
+                outs[me] = halves[me].statistics(reduce=make_reduce(me), n_total=S, bracket=True)
+                assert halves[me].last_select == "bracket"
+            except Exception as ex:          # pragma: no cover
+                errs.append(ex)
+                barrier.abort()
+
+        th = [threading.Thread(target=run, args=(i,)) for i in range(2)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        for h in halves:
+            h.close()
+    assert not errs, errs
+    for o in outs:
+        assert np.array_equal(o["ci_lb"], whole["ci_lb"]) and np.array_equal(o["ci_ub"], whole["ci_ub"])
+        assert np.array_equal(o["min"], whole["min"]) and np.array_equal(o["max"], whole["max"])
+        assert H.rel_err(o["mean"], whole["mean"]) < 1e-13
