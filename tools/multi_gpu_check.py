@@ -58,6 +58,23 @@ def main():
             assert np.array_equal(st["min"], ref["min"]) and np.array_equal(st["max"], ref["max"])
             assert np.allclose(st["mean"], ref["mean"], rtol=1e-13)
             out["propagation"] = "sharded == unsharded"
+    # the one-pass bracketed select over NCCL (brackets min / max-reduced, counts and candidate histograms summed)
+    S = 1 << 21
+    s_first, s_count = shard_range(S, world, rank)
+    with ChainEngine(ProblemSpec.from_dict(pa), SamplerConfig(algo="RWMH"), 1, device=local) as eng:
+        with DevicePropagation(eng, s_count) as dp:
+            dp.evaluate_gaussian(pa["x0"], 0.01 * np.abs(pa["x0"]), seed=6, sample_offset=s_first)
+            st = dp.statistics(reduce=red, n_total=S, bracket=True)
+            how = dp.last_select
+        if rank == 0:
+            with DevicePropagation(eng, S) as dp:
+                dp.evaluate_gaussian(pa["x0"], 0.01 * np.abs(pa["x0"]), seed=6, sample_offset=0)
+                ref = dp.statistics(bracket=False)
+            assert how == "bracket", how
+            assert np.array_equal(st["ci_lb"], ref["ci_lb"]) and np.array_equal(st["ci_ub"], ref["ci_ub"])
+            assert np.array_equal(st["min"], ref["min"]) and np.array_equal(st["max"], ref["max"])
+            assert np.allclose(st["mean"], ref["mean"], rtol=1e-13)
+            out["propagation_bracketed"] = "sharded == unsharded (2^21 samples)"
     dist.barrier()
     if rank == 0:
         print("MULTI_GPU_OK " + json.dumps(out))
