@@ -369,6 +369,16 @@ __global__ void __launch_bounds__(256) cand_hist_kernel(const double *cand, cons
 }
 
 // ------------------------------------------------------------------------------------------------ C ABI
+// bracketed select: subsample length for a stride, and the candidate slots that hold four times the expected number of
+// values in a bracket six binomial standard deviations either side of fraction f of an m-value subsample
+static int64_t bracket_sub_len(int64_t S, int stride) {
+    const int64_t group = (int64_t)256 * stride, full = S / group, rem = S - full * group;
+    return full * 256 + std::min<int64_t>(rem, 256);
+}
+static int64_t bracket_cap(int64_t cap_hint) { return ((4 * cap_hint + 4096 + 255) / 256) * 256; }
+static constexpr int BRACKET_STRIDE_DEFAULT = 64;
+static constexpr int64_t BRACKET_MIN_SAMPLES = 1 << 18;
+
 PBU_API int pbu_propagation_create(pbu_engine *e, int64_t n_samples, pbu_propagation **out) {
     if (!e || !out || n_samples < 1) return fail(PBU_ERR_INVALID, "bad argument");
     CUDA_TRY(cudaSetDevice(e->device));
@@ -379,7 +389,16 @@ PBU_API int pbu_propagation_create(pbu_engine *e, int64_t n_samples, pbu_propaga
     const size_t fbytes = (size_t)p->N * (size_t)n_samples * sizeof(double);
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    if (fbytes + (size_t)e->d * n_samples * 8 + (64u << 20) > free_b) {
+    // large S: the buffers of the bracketed select are taken now (any one or two percentiles fit: sized for the median),
+    // so that statistics never allocates -- 1.6 % + ~10 % of the evaluations
+    int64_t sub_m = 0, cap = 0;
+    if (n_samples >= BRACKET_MIN_SAMPLES) {
+        sub_m = bracket_sub_len(n_samples, BRACKET_STRIDE_DEFAULT);
+        const double dl = 6.0 * std::sqrt(0.25 * (double)sub_m) + 8.0;
+        cap = bracket_cap((int64_t)((double)n_samples * (2.0 * dl + 3.0) / (double)sub_m));
+    }
+    const size_t bbytes = ((size_t)sub_m + 2 * (size_t)cap) * p->N * sizeof(double);
+    if (fbytes + bbytes + (size_t)e->d * n_samples * 8 + (64u << 20) > free_b) {
         delete p;
         return fail(PBU_ERR_INVALID, "propagation of %lld samples x %d points needs %.1f GB of device memory, %.1f GB free: shard the samples",
                     (long long)n_samples, e->prob.n_points, fbytes / 1e9, free_b / 1e9);
@@ -390,7 +409,15 @@ PBU_API int pbu_propagation_create(pbu_engine *e, int64_t n_samples, pbu_propaga
     if (ce == cudaSuccess) ce = cudaMalloc(&p->d_prefix, (size_t)p->N * MAX_T * sizeof(unsigned long long));
     if (ce == cudaSuccess) ce = cudaMalloc(&p->d_rank, (size_t)p->N * MAX_T * sizeof(long long));
     if (ce == cudaSuccess) ce = cudaMalloc(&p->d_hist, (size_t)p->N * MAX_T * 256 * sizeof(unsigned long long));
+    if (ce == cudaSuccess) ce = cudaMalloc(&p->d_brk, (size_t)p->N * 2 * 2 * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMalloc(&p->d_cnt, (size_t)2 * p->N * 2 * sizeof(unsigned long long));
+    if (ce == cudaSuccess && sub_m > 0) {
+        ce = cudaMalloc(&p->d_sub, (size_t)p->N * sub_m * sizeof(double));
+        if (ce == cudaSuccess) ce = cudaMalloc(&p->d_cand, (size_t)p->N * 2 * cap * sizeof(double));
+        if (ce == cudaSuccess) p->sub_m = sub_m, p->cap = cap;
+    }
     if (ce != cudaSuccess) {
+        cudaFree(p->d_sub), cudaFree(p->d_cand), cudaFree(p->d_brk), cudaFree(p->d_cnt);
         cudaFree(p->d_X), cudaFree(p->d_f), cudaFree(p->d_part), cudaFree(p->d_prefix), cudaFree(p->d_rank), cudaFree(p->d_hist);
         delete p;
         return fail(PBU_ERR_CUDA, "propagation buffers: %s", cudaGetErrorString(ce));
@@ -588,8 +615,7 @@ PBU_API int pbu_propagation_bracket_sample(pbu_propagation *p, const double *fra
     if (!p->evaluated) return fail(PBU_ERR_INVALID, "propagation has not been evaluated");
     pbu_engine *e = p->e;
     CUDA_TRY(cudaSetDevice(e->device));
-    const int64_t group = (int64_t)256 * stride, full = p->S / group, rem = p->S - full * group;
-    const int64_t m = full * 256 + std::min<int64_t>(rem, 256);
+    const int64_t m = bracket_sub_len(p->S, stride);
     if (m < 1024) return fail(PBU_ERR_INVALID, "subsample of %lld values is too small for a bracket: use the full radix select", (long long)m);
     if (p->sub_m != m) {
         cudaFree(p->d_sub);
@@ -641,8 +667,8 @@ PBU_API int pbu_propagation_bracket_sample(pbu_propagation *p, const double *fra
 
 // Step 2: the one pass over the evaluations with the (global) brackets.  Per design point: sum, min, max as
 // pbu_propagation_moments; below / inside host [N][n_q]: this engine's counts of values < a and in [a, b].  *overflow != 0:
-// more candidates than `cap_hint` (the expected number, the buffer holds four times as many + 4096) -- the caller falls
-// back to the full radix select.
+// more candidates than the buffer holds (at least 4 cap_hint + 4096 per point and percentile; cap_hint = the expected
+// number) -- the caller falls back to the full radix select.
 PBU_API int pbu_propagation_bracket_pass(pbu_propagation *p, const double *brackets_host, int n_q, int64_t cap_hint, double *sum_host, double *min_host,
                                          double *max_host, int64_t *below_host, int64_t *inside_host, int *overflow) {
     if (!p || !brackets_host || n_q < 1 || 2 * n_q > MAX_T || cap_hint < 0 || !below_host || !inside_host || !overflow)
@@ -650,21 +676,22 @@ PBU_API int pbu_propagation_bracket_pass(pbu_propagation *p, const double *brack
     if (!p->evaluated) return fail(PBU_ERR_INVALID, "propagation has not been evaluated");
     pbu_engine *e = p->e;
     CUDA_TRY(cudaSetDevice(e->device));
-    const int64_t cap = ((4 * cap_hint + 4096 + 255) / 256) * 256;
     const size_t nrq = (size_t)p->N * n_q;
-    if (p->cap != cap || p->nq != n_q) {
-        cudaFree(p->d_cand), cudaFree(p->d_brk), cudaFree(p->d_cnt);
-        p->d_cand = p->d_brk = nullptr;
-        p->d_cnt = nullptr;
-        p->cap = 0, p->nq = 0;
+    if (bracket_cap(cap_hint) > p->cap) {          // buffers are for two percentiles whatever n_q (pbu_propagation_create took them for large S)
+        const int64_t want = bracket_cap(cap_hint);
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        cudaFree(p->d_cand);
+        p->d_cand = nullptr;
+        p->cap = 0;
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        if (nrq * (size_t)cap * 8 + (64u << 20) > free_b) return fail(PBU_ERR_INVALID, "no room for %.2f GB of bracket candidates", nrq * (double)cap * 8 / 1e9);
-        CUDA_TRY(cudaMalloc(&p->d_cand, nrq * (size_t)cap * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&p->d_brk, nrq * 2 * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&p->d_cnt, 2 * nrq * sizeof(unsigned long long)));
-        p->cap = cap, p->nq = n_q;
+        if ((size_t)p->N * 2 * (size_t)want * 8 + (64u << 20) > free_b)
+            return fail(PBU_ERR_INVALID, "no room for %.2f GB of bracket candidates", (double)p->N * 2 * (double)want * 8 / 1e9);
+        CUDA_TRY(cudaMalloc(&p->d_cand, (size_t)p->N * 2 * (size_t)want * sizeof(double)));
+        p->cap = want;
     }
+    const int64_t cap = p->cap;
+    p->nq = n_q;
     CUDA_TRY(cudaMemcpyAsync(p->d_brk, brackets_host, nrq * 2 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(cudaMemsetAsync(p->d_cnt, 0, 2 * nrq * sizeof(unsigned long long), e->stream));
     if (n_q == 1)

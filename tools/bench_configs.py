@@ -101,8 +101,15 @@ def main():
                 t1 = time.perf_counter()
                 st = dp.statistics()
                 t2 = time.perf_counter()
+                how = dp.last_select
+                st = dp.statistics()          # again with the subsample / candidate buffers already allocated
+                t3 = time.perf_counter()
+                stf = dp.statistics(bracket=False)
+                t4 = time.perf_counter()
+                assert np.array_equal(st["ci_lb"], stf["ci_lb"]) and np.array_equal(st["ci_ub"], stf["ci_ub"])
                 print(json.dumps({"cfg": 5, "what": "Arrhenius propagation, 1.25e7 samples x 500 points, evaluations in HBM (50 GB)",
-                                  "eval_s": t1 - t0, "statistics_s": t2 - t1, "samples_per_s_eval": S / (t1 - t0),
+                                  "eval_s": t1 - t0, "statistics_s": t2 - t1, "statistics_select": how, "statistics_s_second_call": t3 - t2,
+                                  "statistics_s_full_radix_select": t4 - t3, "samples_per_s_eval": S / (t1 - t0),
                                   "samples_per_s_total": S / (t2 - t0), "tflops_alg_eval": S * 2.15e4 / (t1 - t0) / 1e12,
                                   "frac_fp64_issue_eval": S * 500 * FP64_INST_RK4_EVAL * 2 / (t1 - t0) / 1e12 / peak,
                                   "hbm_write_GBs": S * 4000 / (t1 - t0) / 1e9, "mean_first_last": [float(st["mean"][0]), float(st["mean"][-1])],
