@@ -198,25 +198,42 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const double *f, int64
     }
 }
 
-// after the (all-reduced) histogram of a pass: pick the digit that holds the wanted rank
+// after the (all-reduced) histogram of a pass: pick the digit that holds the wanted rank.  One warp per (point, rank):
+// each lane owns eight consecutive bins, a shuffle scan finds the lane, the lane finds the bin.
 __global__ void select_update_kernel(int n_rows, int T, int pass, unsigned long long *prefix, long long *rank, const unsigned long long *hist) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, l = threadIdx.x & 31;
     if (i >= n_rows * T) return;
-    const unsigned long long *h = hist + (int64_t)i * 256;
-    long long k = rank[i];
-    int digit = 255;
-    for (int b = 0; b < 256; ++b) {
-        const long long c = (long long)h[b];
-        if (k < c) {
-            digit = b;
-            break;
-        }
-        k -= c;
+    const unsigned long long *h = hist + (int64_t)i * 256 + 8 * l;
+    long long c[8], tot = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        c[b] = (long long)h[b];
+        tot += c[b];
     }
-    rank[i] = k;
-    prefix[i] |= (unsigned long long)digit << (56 - 8 * pass);
+    long long incl = tot;
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (l >= o) incl += up;
+    }
+    const long long k = rank[i];
+    // first lane whose inclusive count exceeds k holds the bin (none: the last bin, as a guard against a bad rank)
+    const unsigned hit = __ballot_sync(0xffffffffu, k < incl);
+    const int owner = hit ? (__ffs(hit) - 1) : 31;
+    if (l == owner) {
+        long long r = k - (incl - tot);
+        int digit = 8 * l + 7;
+        for (int b = 0; b < 8; ++b) {
+            if (r < c[b]) {
+                digit = 8 * l + b;
+                break;
+            }
+            r -= c[b];
+        }
+        if (!hit) digit = 255;
+        rank[i] = r;
+        prefix[i] |= (unsigned long long)digit << (56 - 8 * pass);
+    }
 }
-
 
 // ------------------------------------------------------------------------------------------------ bracketed select
 // For large S the eight full passes of the radix select are replaced by ONE pass over the evaluations:
@@ -241,7 +258,7 @@ __global__ void __launch_bounds__(256) bracket_pass_kernel(const double *f, int6
     __shared__ double wbuf[8][NQ][64];        // per warp and percentile: values waiting to be flushed (at most 63)
     __shared__ double sh[3][8];
     const int row = blockIdx.x, split = blockIdx.y, w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    const unsigned lt = (1u << l) - 1u;
+    const unsigned lanes_below = (1u << l) - 1u;
     double a[NQ], b[NQ];
     unsigned int nb[NQ];
     int wc[NQ];                               // warp-uniform fill of wbuf[w][q]
@@ -269,17 +286,21 @@ __global__ void __launch_bounds__(256) bracket_pass_kernel(const double *f, int6
         __syncwarp();
         wc[q] = 0;
     };
+    // per value: four compares, one add, two compare-and-keep (fmin / fmax cost seven instructions each for their NaN
+    // rules; NaN is ignored here as there) -- the pass is bound by instruction issue, not by HBM, beyond ~44 issue
+    // cycles per warp and value
     auto feed = [&](bool valid, double v) {
         bool in[NQ], any = false;
         if (valid) {
             sum += v;
-            mn = fmin(mn, v);
-            mx = fmax(mx, v);
+            if (v < mn) mn = v;
+            if (v > mx) mx = v;
         }
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-            nb[q] += (valid && v < a[q]) ? 1u : 0u;
-            in[q] = valid && v >= a[q] && v <= b[q];
+            const bool ge = v >= a[q];          // one compare serves the count and the range test (a NaN counts as below)
+            nb[q] += (valid && !ge) ? 1u : 0u;
+            in[q] = valid && ge && v <= b[q];
             any = any || in[q];
         }
         if (__any_sync(0xffffffffu, any)) {
@@ -287,7 +308,7 @@ __global__ void __launch_bounds__(256) bracket_pass_kernel(const double *f, int6
             for (int q = 0; q < NQ; ++q) {
                 const unsigned msk = __ballot_sync(0xffffffffu, in[q]);
                 if (msk) {
-                    if (in[q]) wbuf[w][q][wc[q] + __popc(msk & lt)] = v;
+                    if (in[q]) wbuf[w][q][wc[q] + __popc(msk & lanes_below)] = v;
                     wc[q] += __popc(msk);
                     if (wc[q] >= 32) flush(q);
                 }
@@ -582,7 +603,7 @@ PBU_API int pbu_propagation_select_update(pbu_propagation *p, int pass, const ui
     if (hist_total_host)      // NULL: use the counts select_pass left on the device (single GPU, nothing to sum)
         CUDA_TRY(cudaMemcpyAsync(p->d_hist, hist_total_host, n * sizeof(unsigned long long), cudaMemcpyHostToDevice, e->stream));
     const int items = p->N * p->T;
-    select_update_kernel<<<(items + 127) / 128, 128, 0, e->stream>>>(p->N, p->T, pass, p->d_prefix, p->d_rank, p->d_hist);
+    select_update_kernel<<<(items * 32 + 127) / 128, 128, 0, e->stream>>>(p->N, p->T, pass, p->d_prefix, p->d_rank, p->d_hist);
     CUDA_TRY(cudaGetLastError());
     if (hist_total_host) CUDA_TRY(cudaStreamSynchronize(e->stream));
     return PBU_OK;
@@ -647,10 +668,12 @@ PBU_API int pbu_propagation_bracket_sample(pbu_propagation *p, const double *fra
     p->cand_mode = false;
     CUDA_TRY(cudaMemcpyAsync(p->d_rank, rk.data(), rk.size() * sizeof(long long), cudaMemcpyHostToDevice, e->stream));
     CUDA_TRY(cudaMemsetAsync(p->d_prefix, 0, (size_t)p->N * T * sizeof(unsigned long long), e->stream));
+    // all eight key bytes: design points whose values agree to many digits (an ODE output before the reaction starts:
+    // 1 - 1e-11) need the low bits, a bracket from the leading bytes alone would hold every value
     for (int pass = 0; pass < 8; ++pass) {
         CUDA_TRY(cudaMemsetAsync(p->d_hist, 0, (size_t)p->N * T * 256 * sizeof(unsigned long long), e->stream));
         select_hist_kernel<<<dim3(p->N, NSPLIT), 256, 0, e->stream>>>(p->d_sub, m, T, pass, p->d_prefix, p->d_hist);
-        select_update_kernel<<<(p->N * T + 127) / 128, 128, 0, e->stream>>>(p->N, T, pass, p->d_prefix, p->d_rank, p->d_hist);
+        select_update_kernel<<<(p->N * T * 32 + 127) / 128, 128, 0, e->stream>>>(p->N, T, pass, p->d_prefix, p->d_rank, p->d_hist);
     }
     CUDA_TRY(cudaGetLastError());
     std::vector<unsigned long long> k((size_t)p->N * T);
