@@ -242,6 +242,10 @@ int pbu_propagation_select_begin(pbu_propagation *p, const int64_t *ranks, int n
                                  int *first_pass);
 int pbu_propagation_select_pass(pbu_propagation *p, int pass, uint64_t *hist_host);
 int pbu_propagation_select_update(pbu_propagation *p, int pass, const uint64_t *hist_total_host);
+/* the same two steps with the histogram in a caller-owned DEVICE buffer [N][n_ranks][256] (one process per GPU: the
+ * caller all-reduces it in place with NCCL on the engine's stream between the two calls; no host copy, no sync) */
+int pbu_propagation_select_pass_dev(pbu_propagation *p, int pass, uint64_t *hist_dev);
+int pbu_propagation_select_update_dev(pbu_propagation *p, int pass, const uint64_t *hist_total_dev);
 int pbu_propagation_select_result(pbu_propagation *p, double *values_host /*[N][n_ranks]*/);
 /* Bracketed select, the fast path for large S (same np.percentile, solve_problem.py:639-647, ONE pass over the evaluations
  * instead of up to eight).  n_q = 1 or 2 percentiles.

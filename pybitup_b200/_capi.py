@@ -109,6 +109,8 @@ def _load():
         "pbu_propagation_select_begin": (C.c_int, [E, _lp, C.c_int, _dp, _dp, C.POINTER(C.c_int)]),
         "pbu_propagation_select_pass": (C.c_int, [E, C.c_int, C.POINTER(C.c_uint64)]),
         "pbu_propagation_select_update": (C.c_int, [E, C.c_int, C.POINTER(C.c_uint64)]),
+        "pbu_propagation_select_pass_dev": (C.c_int, [E, C.c_int, C.c_void_p]),
+        "pbu_propagation_select_update_dev": (C.c_int, [E, C.c_int, C.c_void_p]),
         "pbu_propagation_select_result": (C.c_int, [E, _dp]),
         "pbu_propagation_bracket_sample": (C.c_int, [E, _dp, C.c_int, C.c_int, _dp]),
         "pbu_propagation_bracket_pass": (C.c_int, [E, _dp, C.c_int, C.c_int64, _dp, _dp, _dp, _lp, _lp, C.POINTER(C.c_int)]),

@@ -577,17 +577,25 @@ PBU_API int pbu_propagation_select_begin(pbu_propagation *p, const int64_t *rank
     return PBU_OK;
 }
 
+// one pass into `hist` (device, [N][T][256]): the evaluations, or the candidates of the bracketed select
+static int select_pass_into(pbu_propagation *p, int pass, unsigned long long *hist) {
+    pbu_engine *e = p->e;
+    const size_t n = (size_t)p->N * p->T * 256;
+    CUDA_TRY(cudaMemsetAsync(hist, 0, n * sizeof(unsigned long long), e->stream));
+    if (p->cand_mode)
+        cand_hist_kernel<<<p->N * p->nq, 256, 0, e->stream>>>(p->d_cand, p->d_cnt + (size_t)p->N * p->nq, p->cap, p->nq, pass, p->d_prefix, hist);
+    else
+        select_hist_kernel<<<dim3(p->N, NSPLIT), 256, 0, e->stream>>>(p->d_f, p->S, p->T, pass, p->d_prefix, hist);
+    CUDA_TRY(cudaGetLastError());
+    return PBU_OK;
+}
+
 PBU_API int pbu_propagation_select_pass(pbu_propagation *p, int pass, uint64_t *hist_host) {
     if (!p || p->T < 1 || pass < 0 || pass > 7) return fail(PBU_ERR_INVALID, "bad argument");
     pbu_engine *e = p->e;
     CUDA_TRY(cudaSetDevice(e->device));
     const size_t n = (size_t)p->N * p->T * 256;
-    CUDA_TRY(cudaMemsetAsync(p->d_hist, 0, n * sizeof(unsigned long long), e->stream));
-    if (p->cand_mode)
-        cand_hist_kernel<<<p->N * p->nq, 256, 0, e->stream>>>(p->d_cand, p->d_cnt + (size_t)p->N * p->nq, p->cap, p->nq, pass, p->d_prefix, p->d_hist);
-    else
-        select_hist_kernel<<<dim3(p->N, NSPLIT), 256, 0, e->stream>>>(p->d_f, p->S, p->T, pass, p->d_prefix, p->d_hist);
-    CUDA_TRY(cudaGetLastError());
+    if (int rc = select_pass_into(p, pass, p->d_hist)) return rc;
     if (hist_host) {          // NULL: single GPU, the counts stay on the device for select_update(..., NULL)
         CUDA_TRY(cudaMemcpyAsync(hist_host, p->d_hist, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
         CUDA_TRY(cudaStreamSynchronize(e->stream));
@@ -606,6 +614,26 @@ PBU_API int pbu_propagation_select_update(pbu_propagation *p, int pass, const ui
     select_update_kernel<<<(items * 32 + 127) / 128, 128, 0, e->stream>>>(p->N, p->T, pass, p->d_prefix, p->d_rank, p->d_hist);
     CUDA_TRY(cudaGetLastError());
     if (hist_total_host) CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PBU_OK;
+}
+
+// The same two steps with the histogram in a caller-owned DEVICE buffer ([N][n_ranks][256] uint64, e.g. a torch tensor):
+// select_pass_dev fills it on the engine's stream, the caller all-reduces it in place on that stream (NCCL), and
+// select_update_dev consumes it -- no host copy and no synchronisation per pass.
+PBU_API int pbu_propagation_select_pass_dev(pbu_propagation *p, int pass, uint64_t *hist_dev) {
+    if (!p || p->T < 1 || pass < 0 || pass > 7 || !hist_dev) return fail(PBU_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(p->e->device));
+    return select_pass_into(p, pass, (unsigned long long *)hist_dev);
+}
+
+PBU_API int pbu_propagation_select_update_dev(pbu_propagation *p, int pass, const uint64_t *hist_total_dev) {
+    if (!p || p->T < 1 || pass < 0 || pass > 7 || !hist_total_dev) return fail(PBU_ERR_INVALID, "bad argument");
+    pbu_engine *e = p->e;
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int items = p->N * p->T;
+    select_update_kernel<<<(items * 32 + 127) / 128, 128, 0, e->stream>>>(p->N, p->T, pass, p->d_prefix, p->d_rank,
+                                                                          (const unsigned long long *)hist_total_dev);
+    CUDA_TRY(cudaGetLastError());
     return PBU_OK;
 }
 

@@ -44,6 +44,18 @@ class Reducer:
                         group=self.group)
         return t.cpu().numpy().astype(a.dtype, copy=False).reshape(a.shape)
 
+    @property
+    def device_sum(self):
+        """In-place sum of a CUDA tensor over the ranks on the current stream (NCCL), or None when the group cannot do
+        that (gloo, a single rank): callers then go through __call__ with host arrays."""
+        if not self.active or self.world_size == 1 or self._dist.get_backend(self.group) != "nccl":
+            return None
+
+        def f(t):
+            self._dist.all_reduce(t, op=self._dist.ReduceOp.SUM, group=self.group)
+            return t
+        return f
+
 
 def global_chain_statistics(local_sums_fn, d, reducer=None, mu0=None):
     """Pooled mean / covariance / R-hat over the chains of all ranks.

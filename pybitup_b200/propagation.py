@@ -103,7 +103,7 @@ class DevicePropagation:
         vals = None
         self.last_select = "radix"
         if bracket:
-            s, mn, mx, vals = self._bracketed(percentiles, r, n_total, ident, reduce is None)
+            s, mn, mx, vals = self._bracketed(percentiles, r, n_total, ident, reduce)
         if s is None:
             s, mn, mx = np.empty(N), np.empty(N), np.empty(N)
             capi.check(capi.lib.pbu_propagation_moments(self._h, capi.dptr(s), capi.dptr(mn), capi.dptr(mx)))
@@ -114,7 +114,7 @@ class DevicePropagation:
             gmn, gmx = np.ascontiguousarray(mn, dtype=np.float64), np.ascontiguousarray(mx, dtype=np.float64)
             capi.check(capi.lib.pbu_propagation_select_begin(self._h, r.ctypes.data_as(C.POINTER(C.c_int64)), T, capi.dptr(gmn), capi.dptr(gmx),
                                                              C.byref(first)))
-            vals = self._select_passes(first.value, T, ident, reduce is None)
+            vals = self._select_passes(first.value, T, ident, reduce)
         out = dict(mean=s / n_total, min=mn, max=mx, n_samples=n_total)
         for i, q in enumerate(percentiles):
             out["p%g" % q] = np.array([lerp_percentile(n_total, q, vals[k, 2 * i], vals[k, 2 * i + 1]) for k in range(N)])
@@ -122,32 +122,45 @@ class DevicePropagation:
             out["ci_lb"], out["ci_ub"] = out["p2.5"], out["p97.5"]
         return out
 
-    def _select_passes(self, first, T, ident, single):
+    def _select_passes(self, first, T, ident, reduce):
         """radix passes first..7 over whatever select_begin / bracket_select_begin armed; returns the values [N][T]"""
         N = self.n_points
-        hist = np.empty((N, T, 256), dtype=np.uint64)
-        hp = hist.ctypes.data_as(C.POINTER(C.c_uint64))
-        for p in range(first, 8):
-            if single:          # one GPU: the histograms stay on the device, the passes are queued back to back
+        dev_sum = getattr(reduce, "device_sum", None)
+        if reduce is None:          # one GPU: the histograms stay on the device, the passes are queued back to back
+            for p in range(first, 8):
                 capi.check(capi.lib.pbu_propagation_select_pass(self._h, p, None))
                 capi.check(capi.lib.pbu_propagation_select_update(self._h, p, None))
-                continue
-            capi.check(capi.lib.pbu_propagation_select_pass(self._h, p, hp))
-            tot = np.ascontiguousarray(ident(hist.view(np.int64), "sum")).view(np.uint64)
-            capi.check(capi.lib.pbu_propagation_select_update(self._h, p, tot.ctypes.data_as(C.POINTER(C.c_uint64))))
+        elif dev_sum is not None:   # NCCL: the histogram is all-reduced where it lies, on the engine's stream
+            import torch
+            hist = torch.empty((N, T, 256), dtype=torch.int64, device=torch.device("cuda", self.engine.device))
+            hp = C.c_void_p(hist.data_ptr())
+            for p in range(first, 8):
+                capi.check(capi.lib.pbu_propagation_select_pass_dev(self._h, p, hp))
+                dev_sum(hist)
+                capi.check(capi.lib.pbu_propagation_select_update_dev(self._h, p, hp))
+        else:                       # any other reducer: through host arrays
+            hist = np.empty((N, T, 256), dtype=np.uint64)
+            hp = hist.ctypes.data_as(C.POINTER(C.c_uint64))
+            for p in range(first, 8):
+                capi.check(capi.lib.pbu_propagation_select_pass(self._h, p, hp))
+                tot = np.ascontiguousarray(ident(hist.view(np.int64), "sum")).view(np.uint64)
+                capi.check(capi.lib.pbu_propagation_select_update(self._h, p, tot.ctypes.data_as(C.POINTER(C.c_uint64))))
         vals = np.empty((N, T))
         capi.check(capi.lib.pbu_propagation_select_result(self._h, capi.dptr(vals)))
         return vals
 
-    def _bracketed(self, percentiles, ranks, n_total, ident, single):
+    def _bracketed(self, percentiles, ranks, n_total, ident, reduce):
         """One-pass path (include/pybitup_b200.h, 'Bracketed select').  Returns (sum, min, max, values); values is None
-        when the brackets missed a wanted rank or the candidate buffer overflowed (the moments are still good)."""
+        when the brackets missed a wanted rank or the candidate buffer overflowed (the moments are still good).
+        Three small reductions over the ranks: brackets (a, -b) by min; (sum, below, inside, overflow) by sum -- the
+        counts are exact in float64 -- and (min, -max) by min."""
         N, nq, S = self.n_points, len(percentiles), self.n_samples
         stride = self.BRACKET_STRIDE
         fr = np.ascontiguousarray([q / 100.0 for q in percentiles], dtype=np.float64)
         brk = np.empty((N, nq, 2))
         capi.check(capi.lib.pbu_propagation_bracket_sample(self._h, capi.dptr(fr), nq, stride, capi.dptr(brk)))
-        brk = np.ascontiguousarray(np.stack([ident(np.ascontiguousarray(brk[..., 0]), "min"), ident(np.ascontiguousarray(brk[..., 1]), "max")], axis=-1))
+        ab = ident(np.ascontiguousarray(np.stack([brk[..., 0], -brk[..., 1]])), "min")
+        brk = np.ascontiguousarray(np.stack([ab[0], -ab[1]], axis=-1))
         m = max(S // stride, 1)
         hint = int(max(S * (2.0 * (6.0 * np.sqrt(m * f * (1.0 - f)) + 8.0) + 3.0) / m for f in fr))
         s, mn, mx = np.empty(N), np.empty(N), np.empty(N)
@@ -156,9 +169,13 @@ class DevicePropagation:
         ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
         capi.check(capi.lib.pbu_propagation_bracket_pass(self._h, capi.dptr(brk), nq, hint, capi.dptr(s), capi.dptr(mn), capi.dptr(mx), ip(below), ip(inside),
                                                          C.byref(ovf)))
-        s, mn, mx = ident(s, "sum"), ident(mn, "min"), ident(mx, "max")
-        below, inside = ident(below, "sum"), ident(inside, "sum")
-        overflow = ident(np.array([float(ovf.value)]), "max")[0] > 0.0
+        tot = ident(np.concatenate([s, below.ravel().astype(np.float64), inside.ravel().astype(np.float64), [float(ovf.value)]]), "sum")
+        s = np.ascontiguousarray(tot[:N])
+        below = np.rint(tot[N:N + N * nq]).astype(np.int64).reshape(N, nq)
+        inside = np.rint(tot[N + N * nq:N + 2 * N * nq]).astype(np.int64).reshape(N, nq)
+        overflow = tot[-1] > 0.0
+        ext = ident(np.concatenate([mn, -mx]), "min")
+        mn, mx = np.ascontiguousarray(ext[:N]), np.ascontiguousarray(-ext[N:])
         rk = np.asarray(ranks, dtype=np.int64).reshape(nq, 2)
         inb = np.ascontiguousarray((rk[None, :, :] - below[:, :, None]).reshape(N, 2 * nq))
         ok = (not overflow) and bool(np.all(inb >= 0)) and bool(np.all(inb < np.repeat(inside, 2, axis=1)))
@@ -168,7 +185,7 @@ class DevicePropagation:
         first = C.c_int(0)
         capi.check(capi.lib.pbu_propagation_bracket_select_begin(self._h, ip(inb), capi.dptr(brk), C.byref(first)))
         self.last_select = "bracket"
-        return s, mn, mx, self._select_passes(first.value, 2 * nq, ident, single)
+        return s, mn, mx, self._select_passes(first.value, 2 * nq, ident, reduce)
 
 
 def propagate(engine, X, percentiles=(2.5, 97.5), return_evals=False):
