@@ -255,7 +255,9 @@ int pbu_propagation_select_result(pbu_propagation *p, double *values_host /*[N][
  *   2. bracket_pass: one pass with the global brackets: sum / min / max as pbu_propagation_moments (this replaces that
  *      call), below / inside host [N][n_q] = this engine's counts of values < a and in [a, b]; the values inside go to a
  *      candidate buffer of at least 4 cap_hint + 4096 slots per (point, percentile) (pbu_propagation_create takes it,
- *      sized for any percentile, from 2^18 samples on), *overflow != 0 if that was too small.  Over
+ *      sized for any percentile, from 2^18 samples on), *overflow != 0 if that was too small.  Where a == b (the
+ *      subsample has a tie across the bracket, e.g. a constant design point) nothing is copied and nothing can overflow:
+ *      if the rank test below holds the order statistic IS a, whatever select_result reports for that entry.  Over
  *      GPUs: sum the counts, max-reduce the flag.  The wanted global ranks r must satisfy below <= r < below + inside for
  *      every point, else (or on overflow) fall back to pbu_propagation_select_begin.
  *   3. bracket_select_begin with ranks_in_bracket host [N][2 n_q] (= r - below) and the global brackets, then select_pass /

@@ -281,8 +281,9 @@ __global__ void __launch_bounds__(256) bracket_pass_kernel(const double *f, int6
         if (l == 0) off = atomicAdd(&inside[(int64_t)row * NQ + q], (unsigned long long)n);
         off = __shfl_sync(0xffffffffu, off, 0);
         double *dst = cand + ((int64_t)row * NQ + q) * cap;
-        for (int j = l; j < n; j += 32)
-            if ((int64_t)(off + j) < cap) dst[off + j] = wbuf[w][q][j];
+        if (a[q] < b[q])          // a == b (a tie across the bracket: a constant design point): the count alone decides
+            for (int j = l; j < n; j += 32)
+                if ((int64_t)(off + j) < cap) dst[off + j] = wbuf[w][q][j];
         __syncwarp();
         wc[q] = 0;
     };
@@ -771,7 +772,7 @@ PBU_API int pbu_propagation_bracket_pass(pbu_propagation *p, const double *brack
     for (size_t i = 0; i < nrq; ++i) {
         below_host[i] = (int64_t)cnt[i];
         inside_host[i] = (int64_t)cnt[nrq + i];
-        if (cnt[nrq + i] > (unsigned long long)cap) *overflow = 1;
+        if (cnt[nrq + i] > (unsigned long long)cap && brackets_host[2 * i] < brackets_host[2 * i + 1]) *overflow = 1;
     }
     return PBU_OK;
 }

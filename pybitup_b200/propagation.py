@@ -185,7 +185,11 @@ class DevicePropagation:
         first = C.c_int(0)
         capi.check(capi.lib.pbu_propagation_bracket_select_begin(self._h, ip(inb), capi.dptr(brk), C.byref(first)))
         self.last_select = "bracket"
-        return s, mn, mx, self._select_passes(first.value, 2 * nq, ident, reduce)
+        vals = self._select_passes(first.value, 2 * nq, ident, reduce)
+        # a == b: the values between the brackets are all equal (they were counted, not collected)
+        tie = np.repeat(brk[..., 0] == brk[..., 1], 2, axis=1)
+        vals[tie] = np.repeat(brk[..., 0], 2, axis=1)[tie]
+        return s, mn, mx, vals
 
 
 def propagate(engine, X, percentiles=(2.5, 97.5), return_evals=False):

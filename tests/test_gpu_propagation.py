@@ -189,3 +189,27 @@ def test_bracketed_select_sharded_equals_unsharded():
         assert np.array_equal(o["ci_lb"], whole["ci_lb"]) and np.array_equal(o["ci_ub"], whole["ci_ub"])
         assert np.array_equal(o["min"], whole["min"]) and np.array_equal(o["max"], whole["max"])
         assert H.rel_err(o["mean"], whole["mean"]) < 1e-13
+
+
+def test_bracketed_select_with_constant_and_heavily_tied_design_points():
+    """A design point where every sample gives the same value (and one where half of them do): the bracket collapses to
+    a == b, the values are counted instead of collected, and the answer is still the exact order statistic."""
+    from pybitup_b200 import synthetic
+    from pybitup_b200.engine import ChainEngine, ProblemSpec, SamplerConfig
+    from pybitup_b200.propagation import DevicePropagation
+    p = synthetic.cubic_problem(n_points=7)
+    S = 300_000
+    rng = np.random.default_rng(2)
+    d = len(p["x0"])
+    Xc = np.repeat(p["x0"][None, :], S, axis=0)                      # every sample identical: all points constant
+    Xh = Xc * (1.0 + 0.01 * rng.standard_normal((S, d)) * (rng.random((S, 1)) < 0.5))      # half of the samples identical
+    with ChainEngine(ProblemSpec.from_dict(p), SamplerConfig(algo="RWMH"), 1) as eng:
+        for X, pcts in ((Xc, (2.5, 97.5)), (Xh, (40.0, 60.0)), (Xh, (2.5, 97.5))):
+            with DevicePropagation(eng, S) as dp:
+                dp.evaluate(X)
+                st = dp.statistics(pcts, bracket=True)
+                assert dp.last_select == "bracket"
+                fe = dp.evals()
+            for q in pcts:
+                assert np.array_equal(st["p%g" % q], np.percentile(fe, q, axis=0))
+            assert np.array_equal(st["min"], fe.min(axis=0)) and np.array_equal(st["max"], fe.max(axis=0))
