@@ -60,11 +60,26 @@ __global__ void gaussian_samples_kernel(double *X, int64_t S, int d, const doubl
     }
 }
 
+// Slice `split` of `n_split` of row `row` of f[N][S]: [lo, hi).  Interior boundaries fall on 256-byte lines of the
+// ARRAY (not of the row), so that a warp's 256-byte loads never straddle lines: with streaming (evict-first) loads a
+// straddled line is fetched from DRAM twice (ncu: 60 GB read for a 50 GB pass before this).
+__device__ __forceinline__ void row_slice(int row, int split, int n_split, int64_t S, int64_t &lo, int64_t &hi) {
+    const int64_t per = (S + n_split - 1) / n_split, off = (int64_t)row * S;
+    auto cut = [&](int64_t k) -> int64_t {          // boundary k of the row, moved up to the next line of the array
+        if (k <= 0) return 0;
+        if (k >= S) return S;
+        const int64_t a = ((off + k + 31) & ~(int64_t)31) - off;
+        return a < S ? a : S;
+    };
+    lo = cut((int64_t)split * per);
+    hi = cut((int64_t)(split + 1) * per);
+}
+
 // per design point (row of f) and slice: sum, min, max
 __global__ void __launch_bounds__(256) row_moments_kernel(const double *f, int64_t S, double *part) {
     const int row = blockIdx.x, split = blockIdx.y;
-    const int64_t per = (S + gridDim.y - 1) / gridDim.y;
-    const int64_t lo = split * per, hi = (lo + per < S) ? lo + per : S;
+    int64_t lo, hi;
+    row_slice(row, split, gridDim.y, S, lo, hi);
     const double *r = f + (int64_t)row * S;
     double sum = 0.0, mn = INFINITY, mx = -INFINITY;
     for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
@@ -158,8 +173,8 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const double *f, int64
     const bool on1 = T > 1 && rep1 == 1, on2 = T > 2 && rep2 == 2, on3 = T > 3 && rep3 == 3;
     int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
     unsigned int n0 = 0u, n1 = 0u, n2 = 0u, n3 = 0u;
-    const int64_t per = (S + gridDim.y - 1) / gridDim.y;
-    const int64_t lo = split * per, hi = (lo + per < S) ? lo + per : S;
+    int64_t lo, hi;
+    row_slice(row, split, gridDim.y, S, lo, hi);
     const double *r = f + (int64_t)row * S;
     int64_t i = lo + threadIdx.x;
     const int64_t st = blockDim.x;
@@ -252,6 +267,19 @@ __global__ void subsample_gather_kernel(const double *f, int64_t S, int stride, 
     sub[(int64_t)row * m + i] = f[(int64_t)row * S + src];
 }
 
+// the warp hands its n parked values over: one global atomic reserves the slots; `store` false (a == b, a tie across the
+// bracket: a constant design point) counts without copying
+__device__ __noinline__ void bracket_flush(const double *buf, int n, unsigned long long *counter, double *dst, int64_t cap, int lane, bool store) {
+    __syncwarp();
+    unsigned long long off = 0ull;
+    if (lane == 0) off = atomicAdd(counter, (unsigned long long)n);
+    off = __shfl_sync(0xffffffffu, off, 0);
+    if (store)
+        for (int j = lane; j < n; j += 32)
+            if ((int64_t)(off + j) < cap) dst[off + j] = buf[j];
+    __syncwarp();
+}
+
 template <int NQ>
 __global__ void __launch_bounds__(256) bracket_pass_kernel(const double *f, int64_t S, const double *brk, double *part, unsigned long long *below,
                                                            unsigned long long *inside, double *cand, int64_t cap) {
@@ -269,22 +297,14 @@ __global__ void __launch_bounds__(256) bracket_pass_kernel(const double *f, int6
         nb[q] = 0u;
         wc[q] = 0;
     }
-    const int64_t per = (S + gridDim.y - 1) / gridDim.y;
-    const int64_t lo = split * per, hi = (lo + per < S) ? lo + per : S;
+    int64_t lo, hi;
+    row_slice(row, split, gridDim.y, S, lo, hi);
     const double *r = f + (int64_t)row * S;
     double sum = 0.0, mn = INFINITY, mx = -INFINITY;
-    // one warp-wide flush of wbuf[w][q]: a single global atomic reserves the slots
+    // one warp-wide flush of wbuf[w][q] (bracket_flush: out of line, the pass is sixteen copies of feed() and the
+    // instruction cache was missing as often as the loads were stalling)
     auto flush = [&](int q) {
-        __syncwarp();
-        const int n = wc[q];
-        unsigned long long off = 0ull;
-        if (l == 0) off = atomicAdd(&inside[(int64_t)row * NQ + q], (unsigned long long)n);
-        off = __shfl_sync(0xffffffffu, off, 0);
-        double *dst = cand + ((int64_t)row * NQ + q) * cap;
-        if (a[q] < b[q])          // a == b (a tie across the bracket: a constant design point): the count alone decides
-            for (int j = l; j < n; j += 32)
-                if ((int64_t)(off + j) < cap) dst[off + j] = wbuf[w][q][j];
-        __syncwarp();
+        bracket_flush(&wbuf[w][q][0], wc[q], &inside[(int64_t)row * NQ + q], cand + ((int64_t)row * NQ + q) * cap, cap, l, a[q] < b[q]);
         wc[q] = 0;
     };
     // per value: four compares, one add, two compare-and-keep (fmin / fmax cost seven instructions each for their NaN
