@@ -15,3 +15,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'mh_step|mh_c
 python tools/profile_one.py cubic 100 3 > $OUT/plain2_$TAG.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:'mh_step|mh_coop' -s 1 -c 1 -f -o $OUT/prof_cubic_$TAG \
     python tools/profile_one.py cubic 100 3 > $OUT/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
+python tools/profile_propagation.py > $OUT/prop_plain_$TAG.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum --clock-control none --csv --log-file $OUT/launches_prop_$TAG.csv \
+    python tools/profile_propagation.py > $OUT/prop_ncu_$TAG.log 2>&1; echo "ncu propagation launches rc=$?"
