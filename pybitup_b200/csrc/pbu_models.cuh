@@ -145,13 +145,15 @@ struct ArrheniusModel {
     static constexpr int MIN_BLOCKS = 2;   // resident blocks per SM the step kernels are compiled for (register cap)
     static constexpr double R_GAS = 8.314462618;
     struct Ctx {
-        double c0, ER, n, F, h, g_start;
+        double c0, ER, n, F, h, y_start;
     };
     struct Seq {
-        double alpha, g0;
+        double alpha, y0;
     };
-    // c0 and ER are kept in base 2 (divided by ln 2): the stage rates are 2^(c0 - ER/T) (pbu_exp2_tab); c0 also carries
-    // log2(h), so that the exponentials return the rates already multiplied by the step
+    // Everything is kept in base 2: c0 and ER are divided by ln 2 and c0 also carries log2(h), so y(T) = c0 - ER/T is
+    // the log2 of the stage rate times the step.  A stage is k = h g(T) u^n = 2^(y + n log2 u): ONE exp2 per stage on the
+    // sum of the two exponents, no exp2 for the rate alone and no product g * u^n (76 FP64 instructions per RK4 step
+    // where exp2(rate) x exp2(n log2 u) took 96).
     __device__ __forceinline__ static void begin(Ctx &c, const double (&theta)[4], const double *consts) {
         const double c0 = 2.302585092994046 * theta[0] - log(consts[2]) + log(consts[1]);   // ln(10)*log10A - ln(beta) + ln(h)
         const double ER = theta[1] / R_GAS;
@@ -160,11 +162,11 @@ struct ArrheniusModel {
         c.n = theta[2];
         c.F = theta[3];
         c.h = consts[1];
-        c.g_start = exp(c0 - ER * (1.0 / consts[0]));
+        c.y_start = fma(-c.ER, 1.0 / consts[0], c.c0);
     }
     __device__ __forceinline__ static void seq_init(const Ctx &c, Seq &s, const double *) {
         s.alpha = 0.0;
-        s.g0 = c.g_start;
+        s.y0 = c.y_start;
     }
     // exp / log lookup tables of pbu_math.cuh, staged once per block (every kernel calls block_init before its first
     // __syncthreads): 8 KB of static shared memory
@@ -176,27 +178,27 @@ struct ArrheniusModel {
         double *t = tables();
         for (int i = threadIdx.x; i < PBU_MATH_TABLE_DOUBLES; i += blockDim.x) t[i] = pbu_math_tables_dev[i];
     }
-    // u^n for u in (0, 1] as 2^(n log2 u) with the table-driven pbu_exp2_tab / pbu_log2_tab (pbu_math.cuh): relative
-    // error below 2e-14 against pow() (tools/test_math.cu), far inside the 1e-10 parity bar, at 16 FP64 instructions
-    // u <= 0 (conversion complete, or overshot by a stage), denormal or NaN u: 0 up to a denormal (hi word cleared).  The
-    // log of such an argument is finite garbage, discarded by the selection; no FP64 instruction is spent on the test.
-    __device__ __forceinline__ static double pw(double u, double n) {
-        return pbu_exp2_tab_sel(n * pbu_log2_tab(u, tables()), tables(), pbu_log_arg_ok(u));
+    // One stage increment h g(T) u^n = 2^(y + n log2 u) with the table-driven pbu_exp2_tab / pbu_log2_tab (pbu_math.cuh):
+    // relative error below 2e-14 against exp() * pow() (tools/test_math.cu), far inside the 1e-10 parity bar, at 16 FP64
+    // instructions.  u <= 0 (conversion complete, or overshot by a stage), denormal or NaN u: 0 up to a denormal (hi word
+    // cleared).  The log of such an argument is finite garbage, discarded by the selection; no FP64 instruction is spent
+    // on the test.  A sum of exponents below -1022 (u -> 0) gives a denormal as well.
+    __device__ __forceinline__ static double stage(double y, double u, double n) {
+        return pbu_exp2_tab_sel(fma(n, pbu_log2_tab(u, tables()), y), tables(), pbu_log_arg_ok(u));
     }
-    // One RK4 step of d(alpha)/dT = g(T) (1 - alpha)^n.  c.c0 carries ln(h) (see begin): the exponentials return the
-    // stage rates already multiplied by the step.  Written on u = 1 - alpha for the stage arguments; this differs from
-    // the oracle's 1 - (alpha + k/2) by rounding only (<= 2 ulp of u), far inside the 1e-10 parity bar.
+    // One RK4 step of d(alpha)/dT = g(T) (1 - alpha)^n.  Written on u = 1 - alpha for the stage arguments; this differs
+    // from the oracle's 1 - (alpha + k/2) by rounding only (<= 2 ulp of u), far inside the 1e-10 parity bar.
     __device__ __forceinline__ static double step(const Ctx &c, Seq &s, double inv_mid, double inv_end) {
-        const double gm = pbu_exp2_tab(fma(-c.ER, inv_mid, c.c0), tables());
-        const double g1 = pbu_exp2_tab(fma(-c.ER, inv_end, c.c0), tables());
+        const double ym = fma(-c.ER, inv_mid, c.c0);
+        const double y1 = fma(-c.ER, inv_end, c.c0);
         const double a = s.alpha;
         const double u0 = 1.0 - a;
-        const double k1 = s.g0 * pw(u0, c.n);
-        const double k2 = gm * pw(fma(-0.5, k1, u0), c.n);
-        const double k3 = gm * pw(fma(-0.5, k2, u0), c.n);
-        const double k4 = g1 * pw(u0 - k3, c.n);
+        const double k1 = stage(s.y0, u0, c.n);
+        const double k2 = stage(ym, fma(-0.5, k1, u0), c.n);
+        const double k3 = stage(ym, fma(-0.5, k2, u0), c.n);
+        const double k4 = stage(y1, u0 - k3, c.n);
         s.alpha = fma((k1 + k4) + 2.0 * (k2 + k3), 1.0 / 6.0, a);
-        s.g0 = g1;
+        s.y0 = y1;
         return fma(-c.F, s.alpha, 1.0);
     }
     template <int U>

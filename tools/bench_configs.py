@@ -14,8 +14,8 @@ from pybitup_b200.engine import ChainEngine, ProblemSpec, SamplerConfig      # n
 from pybitup_b200.propagation import DevicePropagation                      # noqa: E402
 
 
-FP64_INST_RK4 = 96           # DFMA + DMUL + DADD in the RK4 loop of mh_step_kernel<ArrheniusModel,...> (cuobjdump -sass)
-FP64_INST_RK4_EVAL = 96      # same loop in eval_model_kernel<ArrheniusModel, 4> (no residual / sum of squares)
+FP64_INST_RK4 = 77           # DFMA + DMUL + DADD in the RK4 loop of mh_step_kernel<ArrheniusModel,...> (cuobjdump -sass)
+FP64_INST_RK4_EVAL = 77      # same loop in eval_model_kernel<ArrheniusModel, 4> (no residual / sum of squares)
 
 
 def timed_runs(eng, steps, reps):
@@ -73,7 +73,7 @@ def main():
             print(json.dumps({"cfg": 3, "what": "Arrhenius RK4x500 DRAM, 262,144 chains x 20 iterations", "geom": eng.launch_geometry(), "ms": ms,
                               "chain_steps_per_s": r, "evals_per_step": ev, "tflops_alg": r * ev * 2.17e4 / 1e12,
                               "frac_fp64_alg": r * ev * 2.17e4 / 1e12 / peak,
-                              # the kernel's RK4 step is 96 FP64 instructions (cuobjdump -sass; 2 exp + 4 pow by table-driven base-2
+                              # the kernel's RK4 step is 77 FP64 instructions (cuobjdump -sass; four stages 2^(y + n log2 u) by table-driven base-2
                               # exp / log): issue slots of the FP64 pipe in use, each counted as one DFMA (2 flops)
                               "fp64_inst_per_rk4_step": FP64_INST_RK4, "frac_fp64_issue": r * ev * 500 * FP64_INST_RK4 * 2 / 1e12 / peak}))
     if "4" in which:
