@@ -20,8 +20,8 @@ int pbu_fail(int code, const char *fmt, ...);
 #define PBU_API extern "C" __attribute__((visibility("default")))
 
 // static shared memory a kernel may use besides the dynamic record tiles (the Arrhenius model's exp / log lookup
-// tables, pbu_math.cuh: 8,192 B); taken off the opt-in maximum when the tiles are planned
-#define PBU_STATIC_SMEM_RESERVE 8704
+// tables, pbu_math.cuh: 12,288 B with their alignment slack); taken off the opt-in maximum when the tiles are planned
+#define PBU_STATIC_SMEM_RESERVE 12800
 
 struct pbu_engine {
     int device = 0;

@@ -119,7 +119,8 @@ PBU_HD double pbu_log(double u) {
 //   pbu_log2_tab : u = 2^e m, m in [1, 2), i = top 8 mantissa bits;  r = m c_i - 1, |r| <= 2^-9 (one FMA);
 //                  log2 u = e + (-log2 c_i + r (a1 + a2 r + .. + a5 r^4)),  a_i = (-1)^(i+1) / (i ln2)
 // Tables: pbu_math_tables.h (generated by tools/gen_math_tables.py), 512 + 2*256 doubles (8 KB).  On the device the kernels
-// stage them in shared memory once per block (Model::block_init) and pass the pointer; on the host the static copy.
+// stage them in shared memory once per block (Model::block_init), on a 4 KB boundary of the shared window, and pass the
+// pointer; on the host the static copy.
 // Checked against libm in tools/test_math.cu: exp2 <= 1 ulp; log2 <= 1 ulp of max(|log2 u|, 1) -- the error that
 // matters for 2^(n log2 u) is the absolute one.
 #define PBU_MATH_TABLE_DOUBLES (512 + 512)
@@ -152,6 +153,17 @@ static __constant__ double pbu_kc[9] = {PBU_K_B4, PBU_K_B3, PBU_K_B2, PBU_K_B1, 
 #define PBU_KC(i, lit) (lit)
 #endif
 
+#ifdef __CUDA_ARCH__
+// 32-bit shared-window address of the tables, which the caller has placed on a 4 KB boundary of that window
+// (ArrheniusModel::tables).  The mov hides the known-zero low bits from the front end, which would otherwise turn
+// base | offset back into an add; ptxas folds the mov and merges mask and OR into one LOP3.
+__device__ __forceinline__ uint32_t pbu_tab_base(const double *tab) {
+    uint32_t b;
+    asm("mov.u32 %0, %1;" : "=r"(b) : "r"((uint32_t)__cvta_generic_to_shared(tab)));
+    return b;
+}
+#endif
+
 // 2^y, hi word of the result forced to 0 where !keep (the caller's own range test rides on the selection that is
 // already there).  tab: the PBU_MATH_TABLE_DOUBLES doubles above (exp2 table first).  Domain y < 1024; y <= -1022 (and
 // -inf) returns a denormal (< 2.3e-308) instead of the exact tail: the hi word of y is clamped as an unsigned integer
@@ -176,9 +188,8 @@ PBU_HD double pbu_exp2_tab_sel(double y, const double *tab, bool keep) {
     p = fma(p, r, PBU_KC(3, PBU_K_B1));
     const double v = p * r;                                      // 2^r - 1, remainder (r ln2)^5/120 < 1.3e-18
 #ifdef __CUDA_ARCH__
-    double T;                                                    // explicit shared-space load with the address built as
-    asm("{\n\t.reg .u32 j;\n\tand.b32 j, %1, 511;\n\tmad.lo.u32 j, j, 8, %2;\n\tld.shared.f64 %0, [j];\n\t}"       // mask, multiply-add
-        : "=d"(T) : "r"(m), "r"((uint32_t)__cvta_generic_to_shared(tab)));   // (two instructions; shift, mask, add otherwise)
+    double T;                                                    // tab is 4 KB aligned in the shared window: base | offset
+    asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(pbu_tab_base(tab) | (((uint32_t)m << 3) & 0xFF8u)));      // is one LOP3
 #else
     const double T = tab[m & 511];
 #endif
@@ -201,9 +212,9 @@ PBU_HD double pbu_log2_tab(double u, const double *tab) {
     const int32_t e = (hi >> 20) - 1023;
     const double m = with_hi_word(u, (hi & 0x000FFFFF) | 0x3FF00000);
 #ifdef __CUDA_ARCH__
-    const int32_t i = (hi >> 12) & 255;
-    const double2 cl = *reinterpret_cast<const double2 *>(tab + PBU_LOG2_TABLE_OFFSET + 2 * i);    // one 16-byte shared-memory load
-    const double c = cl.x, nlc = cl.y;
+    double c, nlc;                                               // one 16-byte shared-memory load, address as in exp2
+    asm("ld.shared.v2.f64 {%0, %1}, [%2+4096];" : "=d"(c), "=d"(nlc)                 // 4096 = 8 * PBU_LOG2_TABLE_OFFSET
+        : "r"(pbu_tab_base(tab) | (((uint32_t)hi >> 8) & 0xFF0u)));
 #else
     const int32_t i = (hi >> 12) & 255;
     const double c = tab[PBU_LOG2_TABLE_OFFSET + 2 * i], nlc = tab[PBU_LOG2_TABLE_OFFSET + 2 * i + 1];

@@ -169,10 +169,14 @@ struct ArrheniusModel {
         s.y0 = c.y_start;
     }
     // exp / log lookup tables of pbu_math.cuh, staged once per block (every kernel calls block_init before its first
-    // __syncthreads): 8 KB of static shared memory
+    // __syncthreads): 12 KB of static shared memory
+    // The two 4 KB tables start on a 4 KB boundary of the SHARED WINDOW (the 32-bit shared address, whatever offset the
+    // block's static segment has in it), found at run time inside a 12 KB array: a table address is then base | offset,
+    // which folds into the one LOP3 that masks the index (pbu_math.cuh), instead of mask + add.
     __device__ __forceinline__ static double *tables() {
-        __shared__ __align__(16) double tab[PBU_MATH_TABLE_DOUBLES];
-        return tab;
+        __shared__ __align__(16) double raw[PBU_MATH_TABLE_DOUBLES + 512];
+        const uint32_t a = (uint32_t)__cvta_generic_to_shared(raw);
+        return raw + (((0u - a) & 4095u) >> 3);
     }
     __device__ __forceinline__ static void block_init() {
         double *t = tables();
