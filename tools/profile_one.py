@@ -11,6 +11,7 @@ CFG = {
     "linear": (lambda: synthetic.linear_problem(), "RWMH", 1 << 20, {}),
     "arrhenius": (lambda: synthetic.arrhenius_problem(), "DRAM", 262144, dict(updating_it=10, eps_v=1e-10, gamma_dr=0.2)),
     "heat": (lambda: synthetic.heat_problem(), "DRAM", 65536, dict(updating_it=10, eps_v=1e-10, gamma_dr=0.2)),
+    "isde": (lambda: synthetic.regression_problem(), "ISDE", 131072, dict(isde_h=0.05, isde_f0=4.0, isde_gradient="Analytical")),
 }
 
 
@@ -22,7 +23,8 @@ def main():
     build, algo, C, kw = CFG[name]
     p = build()
     eng = ChainEngine(ProblemSpec.from_dict(p), SamplerConfig(algo=algo, seed=1, lanes_per_chain=lanes, **kw), C)
-    eng.init_chains(synthetic.chain_starts(p["x0"], C, jitter=1e-3), p["prop_cov"])
+    import numpy as np
+    eng.init_chains(synthetic.chain_starts(p["x0"], C, jitter=1e-3), np.eye(len(p["x0"])) * 2.5e-5 if algo == "ISDE" else p["prop_cov"])
     for _ in range(launches):
         eng.run(steps, thin=steps, keep_samples=False)
     eng.synchronize()
