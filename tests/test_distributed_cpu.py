@@ -67,7 +67,11 @@ def _worker(rank, world, port, q):
     mn = red(np.array([float(rank)]), "min")
     mx = red(np.array([float(rank)]), "max")
     hist = red(np.arange(6, dtype=np.int64).reshape(2, 3) * (rank + 1), "sum")
-    q.put((rank, st["mean"], st["cov"], st["rhat"], st["n_chains"], mn[0], mx[0], hist))
+    # the packed reductions of the bracketed select (propagation.py): brackets as (a, -b) under min with open ends, counts
+    # as float64 under sum (exact below 2^53); gloo has no in-place device reduction, so the host path is taken
+    ab = red(np.array([[-np.inf, 0.25 + rank], [-(1.0 + rank), -np.inf]]), "min")
+    big = red(np.array([float(2 ** 51 + rank), 12500000.0 * (rank + 1)]), "sum")
+    q.put((rank, st["mean"], st["cov"], st["rhat"], st["n_chains"], mn[0], mx[0], hist, ab, big, red.device_sum is None))
     dist.destroy_process_group()
 
 
@@ -86,7 +90,9 @@ def test_two_rank_gloo_allreduce_matches_numpy():
         p.join(timeout=60)
         assert p.exitcode == 0
     m, cov, rhat = _reference(_chains())
-    for rank, mean_r, cov_r, rhat_r, nch, mn, mx, hist in res:
+    for rank, mean_r, cov_r, rhat_r, nch, mn, mx, hist, ab, big, host_path in res:
+        assert np.array_equal(ab, np.array([[-np.inf, 0.25], [-2.0, -np.inf]])) and host_path
+        assert big[0] == float(2 ** 52 + 1) and big[1] == 37500000.0
         assert np.allclose(mean_r, m, rtol=1e-13) and np.allclose(cov_r, cov, rtol=1e-11) and np.allclose(rhat_r, rhat, rtol=1e-11)
         assert nch == 12 and mn == 0.0 and mx == 1.0
         assert np.array_equal(hist, np.arange(6).reshape(2, 3) * 3)
