@@ -106,70 +106,92 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
-def _cpu_chain_worker(args, return_chain=False):
-    """One chain of the workload through the oracle port; returns (iterations, seconds)."""
-    seed, n_it = args
-    from oracle import mcmc_oracle as orc
-    from pybitup_b200 import synthetic
-    p = synthetic.cubic_problem(n_points=N_POINTS)
-    prob = orc.Problem(model=p["model"], theta_nom=p["theta_nom"], unc_idx=p["unc_idx"], y=p["y"], std_y=p["std_y"],
-                       lb=p["lb"], ub=p["ub"], gamma=p["gamma"], design=p["design"])
-    rng = np.random.default_rng(seed)
-    st = orc.Streams(rng.standard_normal(n_it * D), rng.random(n_it))
-    x0 = synthetic.chain_starts(p["x0"], 1, jitter=0.01, seed=seed)[0]
-    t0 = time.perf_counter()
-    out = orc.run_mh(prob, x0, p["prop_cov"], n_it, st, adaptive=True, delayed=False, **AM)
-    if return_chain:
-        return n_it, time.perf_counter() - t0, out["chain"]
-    return n_it, time.perf_counter() - t0
+# The CPU legs time the UNMODIFIED reference (oracle/_ref, a byte-for-byte copy of the package made by oracle/make_ref.py)
+# through its own entry point, Sampling(json).sample(models): one chain per process, one process per host core.  They never
+# import the pybitup_b200 package (oracle/ref_bench.py loads the numpy problem builders by file path), so the CUDA
+# library is not mapped into these processes.
+BENCH_PROBLEM = ("cubic_problem", {"n_points": N_POINTS}, "AMH")
 
 
-def cpu_port_rate(n_procs, n_it, pool=None, return_chain=False):
-    """chain-steps/s of the oracle port with n_procs independent single-chain processes."""
-    if n_procs == 1 or pool is None:
-        r = _cpu_chain_worker((0, n_it), return_chain)
-        return (r[0] / r[1], r[1], r[2]) if return_chain else (r[0] / r[1], r[1])
-    t0 = time.perf_counter()
-    res = pool.map(_cpu_chain_worker, [(s, n_it) for s in range(n_procs)], chunksize=1)
-    wall = time.perf_counter() - t0
-    # the processes run their chains concurrently: rate = all iterations / wall time of the slowest
-    return sum(it for it, _ in res) / max(dt for _, dt in res), wall
+def bench_config(chains_per_gpu=CHAINS_PER_GPU, iters=ITERS_PER_STEP):
+    """The `config` object of the JSON line: identical in both arms."""
+    return {"workload": WORKLOAD, "chains_per_gpu": int(chains_per_gpu), "iterations_per_step": int(iters)}
+
+
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
 def run_reference_arm(args):
     rank, _, world = dist_env()
     if rank != 0:
         return 0
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    n_it = 20000
+    from oracle import make_ref, ref_bench
+    make_ref.make()                          # no-op on the GPU box (prebuilt copy), refresh in the build container
+    cores = host_cores()
+    n_it = args.ref_iters
     import multiprocessing as mp
+    os.environ.setdefault("PYTHONWARNINGS", "ignore")     # the reference's own SyntaxWarnings (post_process.py) in the workers
     pool = mp.get_context("spawn").Pool(cores) if cores > 1 else None
+    builder, bkw, algo = BENCH_PROBLEM
     try:
         for _ in range(min(args.warmup, 1)):
-            cpu_port_rate(cores, 500, pool)
+            ref_bench.rate(pool, cores, builder, bkw, algo, 500, "as_shipped")
         rates, t_all = [], 0.0
         for _ in range(args.steps):
-            r, wall = cpu_port_rate(cores, n_it, pool)
+            r, wall = ref_bench.rate(pool, cores, builder, bkw, algo, n_it, "as_shipped")
             rates.append(r)
             t_all += wall
+        stub, _ = ref_bench.rate(pool, cores, builder, bkw, algo, n_it, "save_sample_stubbed")
+        port, _ = ref_bench.rate(pool, cores, builder, bkw, algo, n_it, "port")
     finally:
         if pool is not None:
             pool.close()
             pool.join()
     value = float(np.mean(rates))
-    sample = "%d independent chains (one process per core) x %d AM iterations per bench step" % (cores, n_it)
+    sample = "%d independent chains (one process per core) x %d AM iterations of the same cubic problem per bench step, each " \
+             "through the unmodified reference's Sampling(json).sample(models)" % (cores, n_it)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU port of the reference loop (oracle/mcmc_oracle.py); the reference is "
-                   "pure Python and is not present on the GPU box"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": bench_config(args.chains, args.iters),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample,
+                         "variants": {"as_shipped": value, "save_sample_stubbed": float(stub), "port": float(port)},
+                         "variants_note": "as_shipped = the unmodified reference (oracle/_ref), chain rows written with np.savetxt "
+                                          "every iteration; save_sample_stubbed = the same with BayesianPosterior.save_sample a "
+                                          "no-op after three rows; port = the numpy restatement oracle/mcmc_oracle.py"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def cpu_baseline_leg():
+    """cpu_baseline of the GPU arm (rank 0, one GPU): a bounded sample in a child process, so that this process keeps the
+    reference package and its import stubs out of its module table."""
+    code = ("import json,sys; sys.path.insert(0, %r); from oracle import make_ref, ref_bench as rb; make_ref.make(); "
+            "b=%r; n=30000; "
+            "a=rb.worker((b[0], b[1], b[2], n, 'as_shipped', 0)); s=rb.worker((b[0], b[1], b[2], n, 'save_sample_stubbed', 0)); "
+            "from oracle import ref_bench; syn=rb.load_synthetic(); p=getattr(syn,b[0])(**b[1]); "
+            "p=dict(p, x0=syn.chain_starts(p['x0'],1,jitter=0.01,seed=0)[0]); "
+            "m=rb.run_port_chain(p, rb.algo_block(b[2], 100000, p), 0); "
+            "import numpy as np; np.save(sys.argv[1], m[2]); "
+            "print(json.dumps({'as_shipped': a[0]/a[1], 'stubbed': s[0]/s[1], 'port': m[0]/m[1], 'n': n, 't': a[1]+s[1]+m[1]}))"
+            % (ROOT, BENCH_PROBLEM))
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "chain.npy")
+        out = subprocess.run([sys.executable, "-W", "ignore", "-c", code, path], capture_output=True, text=True, timeout=600)
+        if out.returncode != 0:
+            raise RuntimeError("cpu_baseline leg failed: " + out.stderr[-2000:])
+        r = json.loads(out.stdout.strip().splitlines()[-1])
+        chain = np.load(path)
+    cpu = {"value": r["as_shipped"], "unit": UNIT, "cores": 1, "kind": "reference",
+           "sample": "1 chain x %d AM iterations of the same cubic problem through the unmodified reference's "
+                     "Sampling(json).sample(models) (oracle/_ref), %.1f s for the three variants" % (r["n"], r["t"]),
+           "variants": {"as_shipped": r["as_shipped"], "save_sample_stubbed": r["stubbed"], "port": r["port"]}}
+    return cpu, chain
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -288,18 +310,16 @@ def run_gpu_arm(args):
         ess = {"estimator": "batch means, min over parameters", "gpu_ess_per_chain_step": ess_step,
                "gpu_ess_per_s": ess_step * value}
 
-    # ---- CPU baseline (rank 0, single GPU runs only) ----------------------------------------------
+    # ---- CPU baseline (rank 0, single GPU runs only): the unmodified reference, in a child process -----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        n_it = 100000
-        rate, dt, chain = cpu_port_rate(1, n_it, return_chain=True)
-        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "1 chain x %d AM iterations of the same cubic problem through oracle/mcmc_oracle.py (%.1f s)" % (n_it, dt)}
+        cpu, chain = cpu_baseline_leg()
         if ess is not None:
             from pybitup_b200.diagnostics import ess_batch_means
             segs = [chain[2000 + i * 24000: 2000 + (i + 1) * 24000] for i in range((len(chain) - 2000) // 24000)]
             e_cpu = float(np.mean([ess_batch_means(sg) for sg in segs])) / 24000
-            ess.update({"cpu_ess_per_chain_step": e_cpu, "cpu_ess_per_s": e_cpu * rate})
+            ess.update({"cpu_ess_per_chain_step": e_cpu, "cpu_ess_per_s": e_cpu * cpu["variants"]["port"],
+                        "cpu_ess_note": "chain of the numpy port (same sampler, injected draws); rate of the port"})
 
     if rank == 0:
         ms_launch = total_ms / K
@@ -351,6 +371,7 @@ def main():
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
     ap.add_argument("--iters", type=int, default=ITERS_PER_STEP, help="sampler iterations per bench step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ref-iters", type=int, default=20000, help="reference arm: sampler iterations per chain and bench step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -25,6 +25,7 @@ The reference's own unit tests assert nothing about chains, so
 those recorded runs are the pin.
 """
 from dataclasses import dataclass, field
+from fractions import Fraction
 
 import numpy as np
 import scipy.linalg
@@ -199,27 +200,92 @@ def inv_upper(R):
     return scipy.linalg.inv(np.asarray(R, dtype=np.float64))
 
 
+def fma(a, b, c):
+    """Correctly rounded a*b + c (one rounding), by exact rational arithmetic: what an FMA instruction returns."""
+    a, b, c = float(a), float(b), float(c)
+    if not (np.isfinite(a) and np.isfinite(b) and np.isfinite(c)):
+        return a * b + c
+    return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+
 def chol_upper_plain(V):
-    """Row-by-row upper Cholesky (the order the CUDA device function uses).  Same mathematics as
-    LAPACK's potrf but a different rounding order: on the nearly singular V_i that adaptive
-    Metropolis produces in its first iterations the two differ by cond(V)*eps, which feeds back
-    into the chain (tests/test_oracle_golden.py::test_cholesky_order_sensitivity)."""
+    """Upper Cholesky in the operation order of LAPACK's unblocked dpotf2('U') -- the routine behind
+    scipy.linalg.cholesky at these sizes (mha.py:143, :487, :592) -- written out so that the CUDA device function
+    (pbu_common.cuh::chol_upper_packed) can be held to it operation by operation:
+
+        dot = sum_k R_kj^2          accumulated from zero with fused multiply-adds (ddot)
+        ajj = sqrt(V_jj - dot)      one subtraction
+        t_i = sum_k R_kj R_ki       from zero with fused multiply-adds (dgemv), i > j
+        R_ji = (V_ji - t_i) * (1/ajj)   scaled by the RECIPROCAL (dscal)
+
+    Up to d = 4 this is bit-identical to scipy with OpenBLAS (test_cholesky_potf2_order_is_scipys); from d = 5 on
+    OpenBLAS's vectorised dot / gemv kernels sum in lane order (e.g. ((p0+p2)+(p1+p3)) for a length-4 dot on this
+    image's SkylakeX build), which depends on the BLAS build; the two then agree to rounding."""
     V = np.asarray(V, dtype=np.float64)
     n = V.shape[0]
     R = np.zeros((n, n))
-    for i in range(n):
-        s = V[i, i]
-        for k in range(i):
-            s -= R[k, i] * R[k, i]
+    for j in range(n):
+        dot = 0.0
+        for k in range(j):
+            dot = fma(R[k, j], R[k, j], dot)
+        s = V[j, j] - dot
         if not s > 0.0:
             raise np.linalg.LinAlgError("matrix not positive definite")
-        R[i, i] = np.sqrt(s)
-        for j in range(i + 1, n):
-            t = V[i, j]
-            for k in range(i):
-                t -= R[k, i] * R[k, j]
-            R[i, j] = t / R[i, i]
+        ajj = float(np.sqrt(s))
+        R[j, j] = ajj
+        rinv = 1.0 / ajj
+        for i in range(j + 1, n):
+            t = 0.0
+            for k in range(j):
+                t = fma(R[k, j], R[k, i], t)
+            R[j, i] = (V[j, i] - t) * rinv
     return R
+
+
+def proposal_matvec(R, z):
+    """R @ z of the proposal, the reference's literal call (np.matmul, mha.py:193, :543)."""
+    return np.matmul(R, z)
+
+
+def proposal_matvec_plain(R, z):
+    """R @ z (R upper triangular) in the summation order the CUDA kernels use (pbu_common.cuh::upper_matvec), which up
+    to d = 4 is the order numpy/OpenBLAS produces on the image the golden vectors were recorded on
+    (test_proposal_matvec_order_is_numpys); from d = 5 on a fused multiply-add chain over j >= i."""
+    R = np.asarray(R, dtype=np.float64)
+    d = R.shape[0]
+    p = [[float(R[i, j]) * float(z[j]) for j in range(d)] for i in range(d)]
+    if d == 1:
+        return np.array([p[0][0]])
+    if d == 2:
+        return np.array([fma(R[0, 0], z[0], p[0][1]), p[1][1]])
+    if d == 3:
+        return np.array([fma(R[0, 2], z[2], fma(R[0, 0], z[0], p[0][1])), fma(R[1, 2], z[2], p[1][1]), p[2][2]])
+    if d == 4:
+        return np.array([(p[0][0] + p[0][2]) + (p[0][1] + p[0][3]), p[1][2] + (p[1][1] + p[1][3]), p[2][2] + p[2][3], p[3][3]])
+    out = np.zeros(d)
+    for i in range(d):
+        s = 0.0
+        for j in range(i, d):
+            s = fma(R[i, j], z[j], s)
+        out[i] = s
+    return out
+
+
+class kernel_order:
+    """Context manager: run the restatement with the WRITTEN-OUT operation orders the CUDA kernels implement (dpotf2
+    Cholesky, back-substitution inverse, proposal mat-vec) instead of the scipy / numpy calls the reference makes.  Up to
+    d = 4 the two are bit-identical on the image the golden vectors come from; the written-out forms make a device-vs-
+    oracle comparison independent of the BLAS build of the machine the test runs on."""
+
+    def __enter__(self):
+        g = globals()
+        self.saved = (g["chol_upper"], g["inv_upper"], g["proposal_matvec"])
+        g["chol_upper"], g["inv_upper"], g["proposal_matvec"] = chol_upper_plain, inv_upper_plain, proposal_matvec_plain
+        return self
+
+    def __exit__(self, *a):
+        g = globals()
+        g["chol_upper"], g["inv_upper"], g["proposal_matvec"] = self.saved
 
 
 def inv_upper_plain(R):
@@ -278,7 +344,7 @@ def run_mh(prob, x0, V, n_it, streams, adaptive=False, delayed=False,
     with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
         for it in range(1, n_it + 1):
             z = np.array([streams.gauss(0, 1) for _ in range(d)])
-            new = cur + np.matmul(R, z)                      # :193
+            new = cur + proposal_matvec(R, z)                # :193
             lp_new = post(new)
             if lp_new == -np.inf:
                 r = 0
@@ -292,7 +358,7 @@ def run_mh(prob, x0, V, n_it, streams, adaptive=False, delayed=False,
                 acc[it - 1] = 1
             elif delayed:
                 z2 = np.array([streams.gauss(0, 1) for _ in range(d)])
-                new2 = cur + gamma_dr * np.matmul(R, z2)     # :543
+                new2 = cur + gamma_dr * proposal_matvec(R, z2)   # :543
                 lp2 = post(new2)
                 r_12 = np.exp(lp_new - lp2)
                 alpha_12 = py_min1(r_12)

@@ -17,7 +17,12 @@ import re
 import sys
 import types
 
+import os
+
 REFERENCE_ROOT = "/root/reference"
+# byte-for-byte copy of the package made by oracle/make_ref.py (git-ignored; travels to the GPU box, where
+# /root/reference does not exist)
+REFERENCE_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
 class _Anything(types.ModuleType):
@@ -71,8 +76,9 @@ class _Comm:
         raise RuntimeError("single-process shim")
 
 
-def install():
-    """Make ``import pybitup`` resolve to the unmodified reference."""
+def install(prefer_copy=False):
+    """Make ``import pybitup`` resolve to the unmodified reference: ``/root/reference`` (the build container; what the
+    golden-vector generator uses), or the copy under ``oracle/_ref`` when that is asked for or is all there is."""
     for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors", "matplotlib.cm",
                  "matplotlib.patches", "matplotlib.ticker", "matplotlib.lines",
                  "seaborn", "tikzplotlib", "sobol_seq"):
@@ -92,7 +98,13 @@ def install():
     import scipy.integrate
     if not hasattr(scipy.integrate, "simps"):
         scipy.integrate.simps = scipy.integrate.simpson
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    root = REFERENCE_ROOT
+    if prefer_copy or not os.path.isdir(os.path.join(REFERENCE_ROOT, "pybitup")):
+        root = REFERENCE_COPY
+        if not os.path.isdir(os.path.join(root, "pybitup")):
+            raise ImportError("the reference is not available: neither %s nor %s (python oracle/make_ref.py builds the copy)"
+                              % (REFERENCE_ROOT, REFERENCE_COPY))
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import pybitup  # noqa: F401  (the reference)
     return pybitup

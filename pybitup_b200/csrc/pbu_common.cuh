@@ -187,28 +187,72 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src
 // ------------------------------------------------------------------------------------------------
 // Small dense helpers on packed upper triangles, fully unrolled (D compile time).
 // ------------------------------------------------------------------------------------------------
-// Upper Cholesky V = R^T R, row by row (the order scipy's potrf result is compared against in
-// tests/test_oracle_golden.py::test_cholesky_order_sensitivity). Returns false if not PD.
+// Upper Cholesky V = R^T R in the operation order of LAPACK's unblocked dpotf2 ('U'), which is what
+// scipy.linalg.cholesky runs at these sizes (mha.py:143, :487, :592): for row j, dot = sum_k R_kj^2 accumulated
+// FROM ZERO with fused multiply-adds, ajj = sqrt(V_jj - dot) (one subtraction); then for every i > j the gemv term
+// t = sum_k R_kj R_ki from zero with FMAs, and R_ji = (V_ji - t) * (1/ajj): subtract once, scale by the RECIPROCAL
+// (dscal).  The intrinsics keep nvcc from re-contracting.  Up to d = 4 this is bit-identical to scipy/OpenBLAS
+// (tests/test_oracle_golden.py::test_cholesky_potf2_order_is_scipys); from d = 5 on OpenBLAS's vectorised dot / gemv
+// kernels sum in a lane order that depends on its build, so agreement is to rounding.  Returns false if not PD.
 template <int D>
 __device__ __forceinline__ bool chol_upper_packed(const double (&V)[tri_size(D)], double (&R)[tri_size(D)]) {
     bool ok = true;
 #pragma unroll
-    for (int i = 0; i < D; ++i) {
-        double s = V[tri_idx(D, i, i)];
+    for (int j = 0; j < D; ++j) {
+        double dot = 0.0;
 #pragma unroll
-        for (int k = 0; k < i; ++k) s -= R[tri_idx(D, k, i)] * R[tri_idx(D, k, i)];
+        for (int k = 0; k < j; ++k) dot = __fma_rn(R[tri_idx(D, k, j)], R[tri_idx(D, k, j)], dot);
+        const double s = __dsub_rn(V[tri_idx(D, j, j)], dot);
         if (!(s > 0.0)) ok = false;
-        double rii = sqrt(s);
-        R[tri_idx(D, i, i)] = rii;
+        const double ajj = __dsqrt_rn(s);
+        R[tri_idx(D, j, j)] = ajj;
+        const double rinv = __drcp_rn(ajj);
 #pragma unroll
-        for (int j = i + 1; j < D; ++j) {
-            double t = V[tri_idx(D, i, j)];
+        for (int i = j + 1; i < D; ++i) {
+            double t = 0.0;
 #pragma unroll
-            for (int k = 0; k < i; ++k) t -= R[tri_idx(D, k, i)] * R[tri_idx(D, k, j)];
-            R[tri_idx(D, i, j)] = t / rii;
+            for (int k = 0; k < j; ++k) t = __fma_rn(R[tri_idx(D, k, j)], R[tri_idx(D, k, i)], t);
+            R[tri_idx(D, j, i)] = __dmul_rn(__dsub_rn(V[tri_idx(D, j, i)], t), rinv);
         }
     }
     return ok;
+}
+
+// R @ z for the proposal new = cur + R @ z (mha.py:193, :543), R upper triangular: s_i = sum_{j >= i} R_ij z_j.
+// np.matmul hands this to BLAS, whose small-size kernels do not sum left to right, and in adaptive Metropolis with a tiny
+// eps_v an ulp in a proposal is amplified by cond(V_i) through the next Cholesky factor, so the ORDER decides whether a
+// chain stays within 1e-10 of the reference.  Up to d = 4 (every fixture recorded from the reference) the order is the
+// one numpy/OpenBLAS uses (tests/test_oracle_golden.py::test_proposal_matvec_order_is_numpys):
+//   d = 2:  fma(a0, z0, a1 z1)            d = 3:  fma(a2, z2, fma(a0, z0, a1 z1))
+//   d = 4:  (a0 z0 + a2 z2) + (a1 z1 + a3 z3), plain products (a 4-lane vector dot)
+// where the zeros below the diagonal drop out exactly.  From d = 5 on the order depends on the BLAS build: an FMA chain.
+// rget(i, j) returns R_ij for j >= i.
+template <int D, class RGet>
+__device__ __forceinline__ void upper_matvec(RGet rget, const double (&z)[D], double (&s)[D]) {
+    if constexpr (D == 1) {
+        s[0] = __dmul_rn(rget(0, 0), z[0]);
+    } else if constexpr (D == 2) {
+        s[0] = __fma_rn(rget(0, 0), z[0], __dmul_rn(rget(0, 1), z[1]));
+        s[1] = __dmul_rn(rget(1, 1), z[1]);
+    } else if constexpr (D == 3) {
+        s[0] = __fma_rn(rget(0, 2), z[2], __fma_rn(rget(0, 0), z[0], __dmul_rn(rget(0, 1), z[1])));
+        s[1] = __fma_rn(rget(1, 2), z[2], __dmul_rn(rget(1, 1), z[1]));
+        s[2] = __dmul_rn(rget(2, 2), z[2]);
+    } else if constexpr (D == 4) {
+        s[0] = __dadd_rn(__dadd_rn(__dmul_rn(rget(0, 0), z[0]), __dmul_rn(rget(0, 2), z[2])),
+                         __dadd_rn(__dmul_rn(rget(0, 1), z[1]), __dmul_rn(rget(0, 3), z[3])));
+        s[1] = __dadd_rn(__dmul_rn(rget(1, 2), z[2]), __dadd_rn(__dmul_rn(rget(1, 1), z[1]), __dmul_rn(rget(1, 3), z[3])));
+        s[2] = __dadd_rn(__dmul_rn(rget(2, 2), z[2]), __dmul_rn(rget(2, 3), z[3]));
+        s[3] = __dmul_rn(rget(3, 3), z[3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            double sj = 0.0;
+#pragma unroll
+            for (int j = i; j < D; ++j) sj = fma(rget(i, j), z[j], sj);
+            s[i] = sj;
+        }
+    }
 }
 
 // Python's min(1, r): r only when r < 1, so NaN -> 1

@@ -49,18 +49,22 @@ static void transpose_from_soa(const std::vector<double> &src, int64_t C, int d,
 }
 
 static bool chol_upper_host(const double *V, int d, std::vector<double> &Rp) {
-    // same row-by-row order as pbu::chol_upper_packed
+    // LAPACK dpotf2 order, as pbu::chol_upper_packed: dot and gemv sums from zero with FMAs, one subtraction, scaled by
+    // the reciprocal of the pivot (volatile keeps the host compiler from contracting or reassociating)
     Rp.assign(tri_size(d), 0.0);
-    for (int i = 0; i < d; ++i) {
-        double s = V[i * d + i];
-        for (int k = 0; k < i; ++k) s -= Rp[tri_idx(d, k, i)] * Rp[tri_idx(d, k, i)];
+    for (int j = 0; j < d; ++j) {
+        double dot = 0.0;
+        for (int k = 0; k < j; ++k) dot = std::fma(Rp[tri_idx(d, k, j)], Rp[tri_idx(d, k, j)], dot);
+        volatile double s = V[j * d + j] - dot;
         if (!(s > 0.0)) return false;
-        double rii = std::sqrt(s);
-        Rp[tri_idx(d, i, i)] = rii;
-        for (int j = i + 1; j < d; ++j) {
-            double t = V[i * d + j];
-            for (int k = 0; k < i; ++k) t -= Rp[tri_idx(d, k, i)] * Rp[tri_idx(d, k, j)];
-            Rp[tri_idx(d, i, j)] = t / rii;
+        const double ajj = std::sqrt(s);
+        Rp[tri_idx(d, j, j)] = ajj;
+        volatile double rinv = 1.0 / ajj;
+        for (int i = j + 1; i < d; ++i) {
+            double t = 0.0;
+            for (int k = 0; k < j; ++k) t = std::fma(Rp[tri_idx(d, k, j)], Rp[tri_idx(d, k, i)], t);
+            volatile double diff = V[j * d + i] - t;
+            Rp[tri_idx(d, j, i)] = diff * rinv;
         }
     }
     return true;

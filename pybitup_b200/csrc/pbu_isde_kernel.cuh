@@ -273,7 +273,10 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, M::MIN_BLOCKS) isde_step_kernel(
             double *const gV = p.st.V + cq;
             double *const gxav = p.st.xav + cq;
             // ---- adaptation of the preconditioner (:736-777); current_val = xi_nm (:958)
-            adapt_preconditioner<D>(p, it, upd, xi[q], live[q], gC, gIL, gV, gxav, C, status[q]);
+            // one lane of the chain's group runs the recursion on the global-memory state, then the group synchronises (all
+            // lanes doing it would race on V_i / X_av: a late lane would apply the update to already updated values)
+            if (G == 1 || sub == 0) adapt_preconditioner<D>(p, it, upd, xi[q], live[q], gC, gIL, gV, gxav, C, status[q]);
+            if constexpr (G > 1) __syncwarp(group_mask);
 
             // ---- first half step (:990-991)
             double z[D], udummy;
@@ -523,7 +526,8 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, M::MIN_BLOCKS) hmc_step_kernel(c
             const int64_t cq = c[q];
             double *const gC = p.Cmat + cq;
             double *const gIL = p.st.R + cq;
-            adapt_preconditioner<D>(p, it, upd, x[q], live[q], gC, gIL, p.st.V + cq, p.st.xav + cq, C, status[q]);
+            if (G == 1 || sub == 0) adapt_preconditioner<D>(p, it, upd, x[q], live[q], gC, gIL, p.st.V + cq, p.st.xav + cq, C, status[q]);
+            if constexpr (G > 1) __syncwarp(group_mask);
             double z[D];
             if (injected) {
                 if (!draw_injected<D, true>(p.streams, cq, live[q], live[q] && sub == 0, group_mask, z, u[q])) status[q] |= ST_STREAM_EXHAUSTED;

@@ -68,16 +68,10 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
                     draw_philox<D>(p.seed, p.chain_offset + (uint64_t)c, (uint64_t)it, (uint32_t)stage, z, u);
                 }
                 const double scale = (stage == 0) ? 1.0 : p.gamma_dr;
+                double sj[D];                                                   // new = cur + scale * R @ z, R upper (:193, :543)
+                upper_matvec<D>([&](int i, int j) { return ADAPT ? p.st.R[(int64_t)tri_idx(D, i, j) * sS + c] : p.R0[tri_idx(D, i, j)]; }, z, sj);
 #pragma unroll
-                for (int i = 0; i < D; ++i) {                                   // new = cur + scale * R @ z, R upper (:193, :543)
-                    double sj = 0.0;
-#pragma unroll
-                    for (int j = i; j < D; ++j) {
-                        const double rij = ADAPT ? p.st.R[(int64_t)tri_idx(D, i, j) * sS + c] : p.R0[tri_idx(D, i, j)];
-                        sj = fma(rij, z[j], sj);
-                    }
-                    y[i] = x[i] + scale * sj;
-                }
+                for (int i = 0; i < D; ++i) y[i] = __dadd_rn(x[i], __dmul_rn(scale, sj[i]));
                 n_eval += 1;
                 inb = inside_box<D>(y, p.prob);
             }

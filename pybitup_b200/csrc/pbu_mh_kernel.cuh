@@ -466,16 +466,10 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
                     draw_philox<D>(p.seed, p.chain_offset + (uint64_t)c[q], (uint64_t)it, (uint32_t)stage, z, u[q]);
                 }
                 // new = cur + scale * R @ z with R UPPER triangular (mha.py:193, :543)
+                double sj[D];
+                upper_matvec<D>([&](int i, int j) { return ADAPT ? p.st.R[(int64_t)tri_idx(D, i, j) * C + c[q]] : p.R0[tri_idx(D, i, j)]; }, z, sj);
 #pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    double sj = 0.0;
-#pragma unroll
-                    for (int j = i; j < D; ++j) {
-                        const double rij = ADAPT ? p.st.R[(int64_t)tri_idx(D, i, j) * C + c[q]] : p.R0[tri_idx(D, i, j)];
-                        sj = fma(rij, z[j], sj);
-                    }
-                    y[q][i] = x[q][i] + scale * sj;
-                }
+                for (int i = 0; i < D; ++i) y[q][i] = __dadd_rn(x[q][i], __dmul_rn(scale, sj[i]));
                 n_eval[q] += 1;
             }
             log_posterior<M, D, G, Q, STREAM>(y, want, p.prob, ts, p.tile_points, sub, group_mask, lpy);
@@ -542,8 +536,11 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
             const int64_t cq = c[q];
-            // ---- covariance adaptation (mha.py:432-487)
-            if (ADAPT) {
+            // ---- covariance adaptation (mha.py:432-487).  With G > 1 lanes per chain the group's lanes carry the chain
+            // redundantly, but the adaptive state (V_i, X_av, R) lives in global memory and is read back only from there: ONE
+            // lane (sub == 0) runs the recursion and stores it, then the group synchronises.  (All lanes doing it would
+            // race: a lane that ran late would read values its neighbour has already updated and apply the update twice.)
+            if (ADAPT && (G == 1 || sub == 0)) {
                 double *const gR = p.st.R + cq;
                 double *const gV = p.st.V + cq;
                 double *const gxav = p.st.xav + cq;
@@ -611,10 +608,9 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
                         status[q] |= ST_NOT_PD;                 // scipy raises LinAlgError here (:487)
                     }
                 }
-                mean_r[q] += r[q];                              // :419 (unclipped)
-            } else {
-                mean_r[q] += alpha[q];                          // :170
             }
+            if constexpr (ADAPT && G > 1) __syncwarp(group_mask);
+            mean_r[q] += ADAPT ? r[q] : alpha[q];               // :419 (unclipped) / :170
 
             // ---- outputs
             if (live[q] && sub == 0) {

@@ -30,15 +30,7 @@ def _gaussian_posterior(Phi, y, sigma):
     return mean, cov
 
 
-class _plain_cholesky:
-    """The kernel's row-by-row Cholesky order in the oracle, so that rounding-level agreement is meaningful."""
-
-    def __enter__(self):
-        self.saved = (orc.chol_upper, orc.inv_upper)
-        orc.chol_upper, orc.inv_upper = orc.chol_upper_plain, orc.inv_upper_plain
-
-    def __exit__(self, *a):
-        orc.chol_upper, orc.inv_upper = self.saved
+_plain_cholesky = orc.kernel_order      # the kernels' written-out operation orders in the oracle
 
 
 # ------------------------------------------------------------------------------------------------ cfg 1
@@ -172,7 +164,7 @@ def test_cfg3_full_size_arrhenius_dram():
             out = orc.run_mh(prob, x0[c], p["prop_cov"], T, orc.Streams(normals[c], uniforms[c]), adaptive=True,
                              delayed=True, **kw)
             assert np.array_equal(acc[:, c], out["acc"]), c
-            assert H.rel_err(xs[:, :, c], out["chain"][1:]) < 1e-6, c
+            assert H.rel_err(xs[:, :, c], out["chain"][1:]) < 1e-9, c
     del normals, uniforms, xs, acc, lp1
     with _mk(p, "DRAM", C, seed=5, **kw) as eng:
         eng.init_chains(x0, p["prop_cov"])

@@ -104,15 +104,11 @@ def test_isde_many_chains_vs_oracle(builder, kwargs):
     res = eng.run(T, thin=1)
     eng.synchronize()
     xs = res.samples.cpu().numpy()
-    orc_chol, orc_inv = orc.chol_upper, orc.inv_upper
-    orc.chol_upper, orc.inv_upper = orc.chol_upper_plain, orc.inv_upper_plain
-    try:
+    with orc.kernel_order():
         for c in range(0, C, 4):
             out = orc.run_isde(prob, x0[c], T, orc.Streams(normals[c], np.zeros(1)), 0.01, 4.0, gradient="Analytical",
                                C0=C0, starting_it=20, update_it=5, end_it=45)
             assert H.rel_err(xs[:, :, c], out["chain"][1:]) < 1e-6, c
-    finally:
-        orc.chol_upper, orc.inv_upper = orc_chol, orc_inv
     eng.close()
 
 
@@ -159,12 +155,8 @@ def test_hmc_many_chains_vs_oracle_with_adaptation_and_fd():
         res = eng.run(T, thin=1)
         eng.synchronize()
         xs = res.samples.cpu().numpy()
-    orc_chol, orc_inv = orc.chol_upper, orc.inv_upper
-    orc.chol_upper, orc.inv_upper = orc.chol_upper_plain, orc.inv_upper_plain
-    try:
+    with orc.kernel_order():
         for c in range(0, C, 5):
             out = orc.run_hmc(prob, x0[c], T, orc.Streams(nz[c], un[c]), 0.3, 3, gradient="Analytical", C0=C0, starting_it=30,
                               update_it=10, end_it=60)
             assert H.rel_err(xs[:, :, c], out["chain"][1:]) < 1e-6, c
-    finally:
-        orc.chol_upper, orc.inv_upper = orc_chol, orc_inv

@@ -14,10 +14,6 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 
 MH_CASES = [c for c in H.golden_cases() if "isde" not in c and "hmc" not in c]
-# Adaptive runs on the badly scaled Arrhenius problem amplify the rounding-order difference between
-# LAPACK's Cholesky and the kernel's row-by-row Cholesky (see
-# tests/test_oracle_golden.py::test_cholesky_order_sensitivity); decisions must still be identical.
-CASE_TOL = {"arrhenius_dram": 1e-6, "multi_arrhenius_dram": 1e-6, "multi_cubic_am": 1e-6}
 TOL = 1e-10
 
 
@@ -57,7 +53,7 @@ def test_mh_golden_parity(case, lanes):
     if "n_models" in g and lanes < 0:
         pytest.skip("several models per likelihood run in the replicated layout (the cooperative kernel is single-model)")
     T = int(algo["n_iterations"])
-    tol = CASE_TOL.get(case, TOL)
+    tol = TOL          # every fixture: the kernel's Cholesky runs in LAPACK's dpotf2 order (pbu_common.cuh)
     n_chains = 3 if lanes > 0 else 11       # the same chain several times: every chain must reproduce the reference
     eng = _engine(g, algo, n_chains, lanes_per_chain=abs(lanes), cooperative=(1 if lanes < 0 else -1))
     eng.init_chains(np.tile(g["x0"], (n_chains, 1)), g["prop_cov"])
@@ -122,19 +118,12 @@ def test_many_chains_vs_oracle(builder, lanes, algo_name):
     x_fin, lp_fin = eng.state()
     samples = res.samples.cpu().numpy()
     acc_dev = res.trace_acc.cpu().numpy()
-    tol = 1e-6 if (builder == "arrhenius_problem" and algo_name in ("AMH", "DRAM")) else 1e-9
+    tol = 1e-9
     import tests.helpers as helpers
     for c in range(0, n_chains, 3):
         st = orc.Streams(normals[c], uniforms[c])
-        if algo_name in ("AMH", "DRAM"):
-            # the kernel's Cholesky order, so that rounding-level agreement is meaningful
-            orc_chol, orc_inv = orc.chol_upper, orc.inv_upper
-            orc.chol_upper, orc.inv_upper = orc.chol_upper_plain, orc.inv_upper_plain
-        try:
+        with orc.kernel_order():      # the written-out operation orders of the kernels (bit-identical to scipy / numpy up to d = 4)
             out = orc.run_mh(prob, x0[c], p["prop_cov"], T, st, **helpers.mh_kwargs(algo))
-        finally:
-            if algo_name in ("AMH", "DRAM"):
-                orc.chol_upper, orc.inv_upper = orc_chol, orc_inv
         assert np.array_equal(acc_dev[:, c], out["acc"]), "chain %d: accept codes differ" % c
         assert H.rel_err(samples[:, :, c], out["chain"][1:]) < tol
         assert H.rel_err(lp_fin[c], out["lp"][-1]) < tol

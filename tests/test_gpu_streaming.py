@@ -33,7 +33,7 @@ def test_mh_streamed_equals_resident(builder, kwargs, lanes, algo):
         outs.append((res.samples.cpu().numpy(), res.trace_acc.cpu().numpy(), res.trace_lp1.cpu().numpy()))
         eng.close()
     assert np.array_equal(outs[0][1], outs[1][1])
-    tol = 1e-6 if builder == "arrhenius_problem" and algo == "DRAM" else 1e-10
+    tol = 1e-10
     assert H.rel_err(outs[1][0], outs[0][0]) < tol
     assert H.rel_err(outs[1][2], outs[0][2]) < tol
 
