@@ -12,17 +12,24 @@ What is timed
   value    chain states resident in HBM, CUDA events around each kernel launch on the launching stream,
            L2 flushed between timed launches, max over ranks (barrier + synchronize on both sides).
   e2e      the same through the public host API with HOST buffers: every step uploads the chains' starting
-           points from pinned host memory, initialises the chains, runs ITERS_PER_STEP iterations and reads
-           the final states, log-posteriors and counters back to the host.
+           points from pinned host memory, initialises the chains, runs ITERS_PER_STEP iterations, reduces the
+           pooled moments of ALL chains (pooled mean / covariance, Gelman-Rubin R-hat; at N > 1 this is the NCCL
+           all-reduce of the chain sums, the only collective of the path) and reads the final states,
+           log-posteriors, counters and statistics back into pinned host buffers.  At N > 1 rank 0 then re-runs
+           every rank's chains on its own GPU and checks the pooled moments (shard == whole).
   roofline the step kernel is FP64-pipe bound (the data shared by all chains stays in shared
            memory, so HBM does not bind); achieved = algorithmic flops per launch / mean launch duration,
            peak = a DFMA micro-benchmark run live on the same GPU (MEASURED_PEAKS.json has no FP64 entry).
            The HBM view (algorithmic bytes / duration vs MEASURED_PEAKS.json hbm_gbs) is reported beside it.
-  cpu_baseline  the CPU oracle port of the reference's loop (oracle/mcmc_oracle.py), one chain on one core,
-           on a bounded sample of the same workload (rank 0, N = 1 only).
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref, a byte-for-byte copy of the package made by
+           oracle/make_ref.py) through Sampling(json).sample(models), one chain on one core, on a bounded sample
+           of the same workload (rank 0, N = 1 only); three labelled figures: as shipped, with the per-iteration
+           chain-file writes stubbed, and the numpy port.
+  configs  the other BASELINE.json configurations (1, 1b, 3 weak + strong, 4 with its moment all-reduce, 5) at their
+           per-GPU sizes, each a short device-timed measurement with its own roofline, in the same run.
 
---impl reference times the reference's CPU implementation of the path (the oracle port: the reference is
-pure Python and /root/reference does not exist on the GPU box) on all host cores, one chain per process.
+--impl reference times the unmodified reference's CPU implementation of the path on all host cores, one chain
+per process through Sampling(json).sample(models); the processes never import the pybitup_b200 package.
 """
 import argparse
 import json
@@ -195,10 +202,154 @@ def cpu_baseline_leg():
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+FP64_INST_RK4 = 77           # FP64 instructions of one RK4 step of the Arrhenius kernels (cuobjdump -sass)
+
+
+def _finite(o):
+    """JSON has no inf / nan: replace them by null."""
+    if isinstance(o, dict):
+        return {k: _finite(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_finite(v) for v in o]
+    if isinstance(o, float) and not np.isfinite(o):
+        return None
+    return o
+
+
+def _timed(fn, reps, barrier, max_over_ranks, flush=None):
+    """median over reps of the device time of fn() in ms (CUDA events on the current stream, max over ranks)"""
+    import torch
+    ms = []
+    for _ in range(reps):
+        if flush is not None:
+            flush()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ms.append(max_over_ranks(e0.elapsed_time(e1)))
+    return float(np.median(ms))
+
+
+def measure_configs(rank, local_rank, world, red, fp64_peak, hbm_peak, barrier, max_over_ranks, flush, which):
+    """The other BASELINE.json configurations at their per-GPU sizes, each a short measurement in the same run (device
+    timed, L2 flushed before every timed launch, max over ranks).  Flop / byte counts per unit: SURVEY.md 8(d)."""
+    import torch
+    from pybitup_b200 import synthetic
+    from pybitup_b200.engine import ChainEngine, ProblemSpec, SamplerConfig
+    from pybitup_b200.propagation import DevicePropagation
+    out = {}
+
+    def frac(tflops):
+        return tflops / fp64_peak
+
+    if "1" in which and rank == 0:
+        # cfg 1: ONE chain x 1e5 iterations (the reference's own CPU-runnable case): latency of a serial chain, no roofline
+        p = synthetic.linear_problem()
+        with ChainEngine(ProblemSpec.from_dict(p), SamplerConfig(algo="RWMH", seed=1), 1, device=local_rank) as eng:
+            eng.init_chains(p["x0"][None, :], p["prop_cov"])
+            eng.run(1000, thin=1000, keep_samples=False)
+            ms = _timed(lambda: eng.run(100000, thin=100000, keep_samples=False), 3, lambda: torch.cuda.synchronize(), lambda v: v)
+            out["cfg1"] = {"workload": "linear model d=3 N=50, RWMH, 1 chain x 1e5 iterations (one GPU thread group; rank 0 only)",
+                           "ms": ms, "ns_per_chain_step": ms * 1e6 / 1e5, "chain_steps_per_s": 1e5 / (ms * 1e-3),
+                           "roofline": None, "note": "a single serial chain is bound by dependent-instruction latency: no throughput roofline applies"}
+    if "1b" in which:
+        p = synthetic.linear_problem()
+        C, T = 1 << 20, 200
+        with ChainEngine(ProblemSpec.from_dict(p), SamplerConfig(algo="RWMH", seed=1, chain_offset=rank * C), C, device=local_rank) as eng:
+            eng.init_chains(synthetic.chain_starts(p["x0"], C, jitter=1e-3, seed=rank), p["prop_cov"])
+            eng.run(T, thin=T, keep_samples=False)
+            ms = _timed(lambda: eng.run(T, thin=T, keep_samples=False), 3, barrier, max_over_ranks, flush)
+            r = world * C * T / (ms * 1e-3)
+            tf = r / world * 512 / 1e12
+            out["cfg1b"] = {"workload": "linear model d=3 N=50, RWMH, 1,048,576 chains per GPU x %d iterations" % T, "scaling": "weak",
+                            "ms": ms, "chain_steps_per_s": r, "launch": eng.launch_geometry(),
+                            "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": frac(tf),
+                                         "flops_per_chain_step": 512}}
+    if "3" in which:
+        p = synthetic.arrhenius_problem()
+        T = 20
+        for mode, C in (("weak", 262144), ("strong", 262144 // world)):
+            if mode == "strong" and world == 1:
+                continue
+            first = rank * C
+            cfg = SamplerConfig(algo="DRAM", seed=1, updating_it=10, eps_v=1e-10, gamma_dr=0.2, chain_offset=first)
+            with ChainEngine(ProblemSpec.from_dict(p), cfg, C, device=local_rank) as eng:
+                eng.init_chains(synthetic.chain_starts(p["x0"], C, jitter=1e-3, seed=rank), p["prop_cov"])
+                eng.run(T, thin=T, keep_samples=False)
+                ms = _timed(lambda: eng.run(T, thin=T, keep_samples=False), 3, barrier, max_over_ranks, flush)
+                ev = float(eng.read_state()["n_eval"].mean()) / eng.iteration
+                r = world * C * T / (ms * 1e-3)
+                tf_alg = r / world * ev * 2.17e4 / 1e12
+                tf_issue = r / world * ev * 500 * FP64_INST_RK4 * 2 / 1e12
+                out["cfg3" if mode == "weak" else "cfg3_strong"] = {
+                    "workload": "Arrhenius pyrolysis ODE (RK4 x 500), d=4, DRAM, %d chains per GPU (%d in all) x %d iterations" % (C, world * C, T),
+                    "scaling": mode, "ms": ms, "chain_steps_per_s": r, "evals_per_chain_step": ev, "launch": eng.launch_geometry(),
+                    "roofline": {"bound": "fp64", "achieved": tf_alg, "peak": fp64_peak, "unit": "TFLOP/s", "frac": frac(tf_alg),
+                                 "flops_per_evaluation": 2.17e4,
+                                 "fp64_issue": {"achieved": tf_issue, "frac": frac(tf_issue), "fp64_inst_per_rk4_step": FP64_INST_RK4,
+                                                "note": "FP64 instructions the kernel issues, each counted as an FMA (2 flops): what the pipe "
+                                                        "is busy with; the algorithmic count takes exp / pow as 1 flop each"}}}
+    if "4" in which:
+        p = synthetic.regression_problem()
+        C, T = 131072, 4
+        cfg = SamplerConfig(algo="ISDE", seed=1, isde_h=0.05, isde_f0=4.0, isde_gradient="Analytical", chain_offset=rank * C)
+        with ChainEngine(ProblemSpec.from_dict(p), cfg, C, device=local_rank) as eng:
+            eng.init_chains(synthetic.chain_starts(p["x0"], C, jitter=1e-2, seed=rank), np.eye(10) * 2.5e-5)
+            eng.run(T, thin=1, keep_samples=False)
+            eng.pooled_statistics(red, apply=True)
+            ms = _timed(lambda: eng.run(T, thin=1, keep_samples=False), 3, barrier, max_over_ranks, flush)
+            ms_stat = _timed(lambda: eng.pooled_statistics(red, apply=True), 5, barrier, max_over_ranks)
+            st = eng.statistics_dict(eng.pooled_statistics(red))
+            r = world * C * T / (ms * 1e-3)
+            tf = r / world * 4.4e5 / 1e12
+            out["cfg4"] = {"workload": "correlated Gaussian regression d=10 N=1e4 (records streamed), Ito-SDE, 131,072 chains per GPU "
+                                       "(%d in all) x %d iterations, pooled preconditioner" % (world * C, T), "scaling": "weak", "ms": ms,
+                           "chain_steps_per_s": r, "launch": eng.launch_geometry(),
+                           "pooled_moment_allreduce_ms": ms_stat,
+                           "pooled_moment_allreduce_what": "two passes over the per-chain moments, %s, finalisation (pooled covariance, R-hat, "
+                                                           "Cholesky) and the refresh of every chain's preconditioner, all on the device"
+                                                           % ("two NCCL all-reduces (12 + 97 doubles)" if world > 1 else "no collective on one GPU"),
+                           "chains_total": st["n_chains"], "rhat_max_after_%d_iterations_from_dispersed_starts" % (5 * T): float(np.nanmax(st["rhat"])),
+                           "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": frac(tf),
+                                        "flops_per_chain_step": 4.4e5}}
+    if "5" in which:
+        p = synthetic.arrhenius_problem()
+        S = 12500000
+        with ChainEngine(ProblemSpec.from_dict(p), SamplerConfig(algo="RWMH"), 1, device=local_rank) as eng:
+            with DevicePropagation(eng, S) as dp:
+                mean, std = p["x0"], 0.01 * np.abs(p["x0"])
+                dp.evaluate_gaussian(mean, std, seed=0, sample_offset=rank * S)
+                ms_eval = _timed(lambda: dp.evaluate_gaussian(mean, std, seed=0, sample_offset=rank * S), 2, barrier, max_over_ranks)
+                rd = red if (red is not None and red.active and world > 1) else None
+                dp.statistics(reduce=rd, n_total=world * S)
+                barrier()
+                t0 = time.perf_counter()
+                st = dp.statistics(reduce=rd, n_total=world * S)
+                torch.cuda.synchronize()
+                ms_stat = max_over_ranks((time.perf_counter() - t0) * 1e3)
+                tf_issue = S * 500 * FP64_INST_RK4 * 2 / (ms_eval * 1e-3) / 1e12
+                out["cfg5"] = {"workload": "Monte-Carlo propagation through the pyrolysis ODE, 1.25e7 samples per GPU (%.3g in all) x 500 "
+                                           "points, evaluations materialised in HBM (50 GB per GPU)" % (world * S), "scaling": "weak",
+                               "eval_ms": ms_eval, "statistics_ms": ms_stat, "statistics_select": dp.last_select,
+                               "samples_per_s_eval": world * S / (ms_eval * 1e-3),
+                               "samples_per_s_total": world * S / ((ms_eval + ms_stat) * 1e-3),
+                               "ci_last_point": [float(st["ci_lb"][-1]), float(st["ci_ub"][-1])],
+                               "roofline": {"bound": "fp64", "achieved": S * 2.15e4 / (ms_eval * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                                            "frac": frac(S * 2.15e4 / (ms_eval * 1e-3) / 1e12), "flops_per_sample": 2.15e4,
+                                            "fp64_issue": {"achieved": tf_issue, "frac": frac(tf_issue), "fp64_inst_per_rk4_step": FP64_INST_RK4},
+                                            "hbm_write": {"achieved": S * 4000 / (ms_eval * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                                          "frac": S * 4000 / (ms_eval * 1e-3) / 1e9 / hbm_peak}}}
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
     from pybitup_b200 import _capi, synthetic
+    from pybitup_b200.distributed import Reducer
     from pybitup_b200.engine import ChainEngine, ProblemSpec, SamplerConfig
 
     rank, local_rank, world = dist_env()
@@ -208,11 +359,19 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    red = Reducer()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return float(v)
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     C, T = args.chains, args.iters
     K, W = args.steps, args.warmup
@@ -234,15 +393,17 @@ def run_gpu_arm(args):
 
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
+    def flush():
+        flush_buf.fill_(1)
+
     # ---- device-resident timing -----------------------------------------------------------------
     eng = ChainEngine(spec, cfg, C, device=local_rank)
     eng.init_chains(x0, p["prop_cov"])
     geom = eng.launch_geometry()
     coop = geom["chains_per_thread"] == geom["lanes"] and geom["lanes"] > 1      # teams of G lanes own G chains
     kernel_name = "%s<PolyModel<4>,D=4,G=%d,ALGO=AM>" % ("mh_coop_kernel" if coop else "mh_step_kernel", geom["lanes"])
-    out = None
     for _ in range(W):
-        out = eng.run(T, thin=T, keep_samples=True, out=None)
+        eng.run(T, thin=T, keep_samples=True)
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -251,49 +412,68 @@ def run_gpu_arm(args):
     for k in range(K):
         flush_buf.fill_(k & 0xff)                                          # L2 flush between timed launches
         ev[k][0].record()
-        out = eng.run(T, thin=T, keep_samples=True)
+        eng.run(T, thin=T, keep_samples=True)
         ev[k][1].record()
     barrier()
     clk = clocks.stop()
     ms = [a.elapsed_time(b) for a, b in ev]
-    t_dev = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    total_ms = float(t_dev.item())
-    ctr = eng.counters()
+    total_ms = max_over_ranks(sum(ms))
+    ctr = eng.read_state()
     acc_rate = 1.0 - float(ctr["n_rejected"].mean()) / max(eng.iteration, 1)
     bad = int(np.count_nonzero(ctr["status"]))
     eng.close()
     value = world * C * T * K / (total_ms * 1e-3)
 
     # ---- end to end through the host API --------------------------------------------------------
+    # every step: starting points from pinned host memory -> device, chain initialisation, T iterations, the pooled
+    # moments of ALL chains (at N > 1: the NCCL all-reduce of the chain sums, pooled covariance and R-hat), and the final
+    # states, log-posteriors, counters and statistics back into pinned host buffers
     x0_pin = torch.from_numpy(x0).pin_memory()
     x0_host = x0_pin.numpy()
     eng = ChainEngine(spec, cfg, C, device=local_rank)
+    n_stats = int(_capi.lib.pbu_engine_pooled_stats_len(eng._h))
+    stats_pin = torch.empty(n_stats, dtype=torch.float64).pin_memory()
     h2d = C * 8 * D                               # the chains' starting points (everything else is built on the device)
-    d2h = C * 8 * (D + 1) + C * (8 + 8 + 8 + 4)
-    for _ in range(min(W, 3)):
+    d2h = C * 8 * (D + 1) + C * (8 + 8 + 8 + 4) + 8 * n_stats
+
+    def e2e_step():
         eng.init_chains(x0_host, p["prop_cov"])
-        eng.run(T, thin=T, keep_samples=False)
-        eng.state()
-        eng.counters()
+        eng.run(T, thin=max(T // 10, 1), keep_samples=False)     # ten kept states per chain feed the moments (R-hat needs > 1)
+        stats = eng.pooled_statistics(red)
+        stats_pin.copy_(stats, non_blocking=True)
+        return eng.read_state()                    # one synchronisation: everything above has landed
+
+    for _ in range(min(W, 3)):
+        e2e_step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     e0.record()
     for k in range(K):
-        eng.init_chains(x0_host, p["prop_cov"])
-        eng.run(T, thin=T, keep_samples=False)
-        xs, lps = eng.state()
-        eng.counters()
+        st_host = e2e_step()
     e1.record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    t_e2e = torch.tensor([max(e0.elapsed_time(e1), 1e3 * t_wall)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = world * C * T * K / (float(t_e2e.item()) * 1e-3)
+    t_e2e = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * t_wall))
+    e2e_value = world * C * T * K / (t_e2e * 1e-3)
+    pooled = eng.statistics_dict(stats_pin)
+    ms_stat = _timed(lambda: eng.pooled_statistics(red), 5, barrier, max_over_ranks)
     eng.close()
+
+    # ---- shard == whole (N > 1): rank 0 runs every rank's chains on its own GPU and must find the same pooled moments ----
+    shard_check = None
+    if world > 1:
+        if rank == 0:
+            x_all = np.concatenate([synthetic.chain_starts(p["x0"], C, jitter=0.01, seed=1000 + r) for r in range(world)], axis=0)
+            with ChainEngine(spec, SamplerConfig(algo="AMH", seed=2026, chain_offset=0, **AM), world * C, device=local_rank) as whole:
+                whole.init_chains(x_all, p["prop_cov"])
+                whole.run(T, thin=max(T // 10, 1), keep_samples=False)
+                ref = whole.statistics()
+            err = max(float(np.max(np.abs(pooled["mean"] - ref["mean"]) / np.abs(ref["mean"]))),
+                      float(np.max(np.abs(pooled["cov"] - ref["cov"]) / np.abs(ref["cov"]))))
+            shard_check = {"chains": int(pooled["n_chains"]), "max_rel_err_pooled_mean_cov_vs_one_gpu": err, "ok": bool(err < 1e-9)}
+            assert pooled["n_chains"] == world * C and err < 1e-9, shard_check
+        barrier()
 
     # ---- effective sample size per chain-step (same batch-means estimator on both sides) ----------
     ess = None
@@ -321,6 +501,12 @@ def run_gpu_arm(args):
             ess.update({"cpu_ess_per_chain_step": e_cpu, "cpu_ess_per_s": e_cpu * cpu["variants"]["port"],
                         "cpu_ess_note": "chain of the numpy port (same sampler, injected draws); rate of the port"})
 
+    # ---- the other configurations, in the same run --------------------------------------------------
+    configs = None
+    if not args.no_configs:
+        configs = measure_configs(rank, local_rank, world, red, fp64_peak, hbm_peak, barrier, max_over_ranks, flush,
+                                  [c.strip() for c in args.configs.split(",")])
+
     if rank == 0:
         ms_launch = total_ms / K
         flops_launch = float(FLOPS_PER_CHAIN_STEP) * C * T
@@ -330,11 +516,16 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "chains_per_gpu": C, "iterations_per_step": T, "rng": "Philox4x32-10",
-                       "l2": "flushed between timed launches (256 MiB fill)", "acceptance_rate": acc_rate,
-                       "chains_with_status_flags": bad},
+            "config": bench_config(C, T),
+            "run": {"rng": "Philox4x32-10", "l2": "flushed between timed launches (256 MiB fill)", "acceptance_rate": acc_rate,
+                    "chains_with_status_flags": bad},
             "clocks": clk,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "includes": "upload of the starting points from pinned memory, chain initialisation, %d iterations, pooled "
+                                "moments of all chains (%s), final states / counters / statistics into pinned host buffers"
+                                % (T, "NCCL all-reduce of the chain sums over %d ranks" % world if world > 1 else "one GPU: no collective"),
+                    "pooled_statistics_ms": ms_stat, "pooled_rhat_max": float(np.nanmax(pooled["rhat"])),
+                    "pooled_chains": int(pooled["n_chains"]), "shard_equals_whole": shard_check},
             "gpu_launches": K,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak, "traffic": None,
@@ -348,6 +539,7 @@ def run_gpu_arm(args):
                                  "frac": bytes_launch / (ms_launch * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src}},
             "cpu_baseline": cpu,
             "ess": ess,
+            "configs": configs,
         }
         prof = os.path.join(ROOT, "profiles", "traffic_r1.json")
         if os.path.exists(prof):
@@ -356,7 +548,7 @@ def run_gpu_arm(args):
                     line["roofline"]["traffic"] = json.load(f).get("dram_bytes_per_launch")
             except (OSError, ValueError):
                 pass
-        print(json.dumps(line), flush=True)
+        print(json.dumps(_finite(line)), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -371,6 +563,8 @@ def main():
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
     ap.add_argument("--iters", type=int, default=ITERS_PER_STEP, help="sampler iterations per bench step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (the other BASELINE.json configurations)")
+    ap.add_argument("--configs", default="1,1b,3,4,5", help="which of the other configurations to measure")
     ap.add_argument("--ref-iters", type=int, default=20000, help="reference arm: sampler iterations per chain and bench step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -186,6 +186,11 @@ int pbu_engine_synchronize(pbu_engine *e);
 int pbu_engine_get_state(pbu_engine *e, double *x_host /*[C][d]*/, double *lp_host /*[C]*/);
 int pbu_engine_get_counters(pbu_engine *e, int64_t *n_rejected /*[C]*/, double *mean_r /*[C]*/,
                             int64_t *n_eval /*[C]*/, int32_t *status /*[C]*/);
+/* the same in one pass, for callers with pinned staging buffers: every array is copied straight into the caller's buffer
+ * and the stream is synchronised once; x comes back chain-minor [d][C] (its device layout).  Any pointer may be NULL.
+ * (current_val, distr_fun_current_val, n_rejected, mean_r: mha.py:99, :102, :146, :154) */
+int pbu_engine_read_state(pbu_engine *e, double *x_soa_host /*[d][C]*/, double *lp_host /*[C]*/, int64_t *n_rejected /*[C]*/,
+                          double *mean_r /*[C]*/, int64_t *n_eval /*[C]*/, int32_t *status /*[C]*/);
 /* per-chain proposal factor R (upper, V = R^T R; mha.py:143,:487), adaptive covariance V_i
  * (:463-466) and running mean X_av_i (:455,:467); any pointer may be NULL. Row-major [C][d][d]. */
 int pbu_engine_get_proposal(pbu_engine *e, double *R_host, double *V_host, double *xav_host);
@@ -210,6 +215,25 @@ int pbu_eval_model(pbu_engine *e, const double *X_host /*[S][d]*/, int64_t S, do
 int pbu_engine_chain_sums_len(const pbu_engine *e);
 int pbu_engine_chain_sums(pbu_engine *e, const double *mu_host, double *out_host);
 int pbu_engine_reset_moments(pbu_engine *e);
+/* Device-resident form (what the samplers use; one process per GPU).  Everything is queued on the engine's stream, nothing is
+ * allocated and nothing touches the host, so the caller can all-reduce the small vectors in place with NCCL between the
+ * calls: chain_sums_dev(mu = NULL) -> all-reduce -> pooled_mean_dev -> chain_sums_dev(mu) -> all-reduce -> pooled_finalize_dev.
+ *   chain_sums_dev     out_dev [pbu_engine_chain_sums_len] = this engine's sums about mu_dev [d] (NULL = 0); n_components > 0
+ *                      computes the leading n_components entries only (2 + d locate the mean: all the first pass needs).
+ *   pooled_mean_dev    mu_out_dev [d] = mu_in_dev (NULL = 0) + sum_c n_c delta_c / sum_c n_c from the all-reduced sums.
+ *   pooled_finalize_dev  stats_dev [pbu_engine_pooled_stats_len] from the all-reduced sums about mu_dev:
+ *        [0] chains [1] kept states [2] ok (proposal matrix positive definite) [3] reserved, then mean d | covariance d*d
+ *        (np.cov of all kept states, mha.py:303-304) | W d | B/n d | Gelman-Rubin R-hat d | V packed | R packed | inv(R)
+ *        packed, with V = scale (cov + eps I): the covariance refresh of mha.py:463 / :745-746 fed by ALL chains instead of
+ *        one chain's recursion (scale = 2.38^2/d, eps = eps_v for the MH family; 1 and 1e-10 for the Ito-SDE
+ *        preconditioner, :630-631).  apply != 0 writes the result into every chain: R = upper Cholesky of V for the MH
+ *        family (:486-487), C_approx / inv_L_c for ISDE and HMC (:773-777) -- unless V is not positive definite, in which
+ *        case the proposal stays as it was and ok = 0. */
+int pbu_engine_pooled_stats_len(const pbu_engine *e);
+int pbu_engine_chain_sums_dev(pbu_engine *e, const double *mu_dev, double *out_dev, int n_components);
+int pbu_engine_pooled_mean_dev(pbu_engine *e, const double *sums_dev, const double *mu_in_dev, double *mu_out_dev);
+int pbu_engine_pooled_finalize_dev(pbu_engine *e, const double *sums_dev, const double *mu_dev, double scale, double eps, int apply,
+                                   double *stats_dev);
 /* Replace the proposal covariance of EVERY chain (pooled-covariance mode): R = upper Cholesky of V host [d][d]
  * for the MH family (mha.py:486-487), C_approx / L_c / inv_L_c for ISDE (:773-777). */
 int pbu_engine_set_proposal(pbu_engine *e, const double *V_host);

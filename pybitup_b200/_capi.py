@@ -90,6 +90,7 @@ def _load():
         "pbu_engine_synchronize": (C.c_int, [E]),
         "pbu_engine_get_state": (C.c_int, [E, _dp, _dp]),
         "pbu_engine_get_counters": (C.c_int, [E, _lp, _dp, _lp, _ip]),
+        "pbu_engine_read_state": (C.c_int, [E, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
         "pbu_engine_get_proposal": (C.c_int, [E, _dp, _dp, _dp]),
         "pbu_engine_iteration": (C.c_int64, [E]),
         "pbu_engine_get_isde_state": (C.c_int, [E, _dp, _dp]),
@@ -99,6 +100,10 @@ def _load():
         "pbu_engine_chain_sums_len": (C.c_int, [E]),
         "pbu_engine_chain_sums": (C.c_int, [E, _dp, _dp]),
         "pbu_engine_reset_moments": (C.c_int, [E]),
+        "pbu_engine_pooled_stats_len": (C.c_int, [E]),
+        "pbu_engine_chain_sums_dev": (C.c_int, [E, C.c_void_p, C.c_void_p, C.c_int]),
+        "pbu_engine_pooled_mean_dev": (C.c_int, [E, C.c_void_p, C.c_void_p, C.c_void_p]),
+        "pbu_engine_pooled_finalize_dev": (C.c_int, [E, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p]),
         "pbu_engine_set_proposal": (C.c_int, [E, _dp]),
         "pbu_propagation_create": (C.c_int, [E, C.c_int64, C.POINTER(E)]),
         "pbu_propagation_destroy": (C.c_int, [E]),

@@ -519,8 +519,12 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
         (rc = dev_alloc(e, &st.status, (size_t)C)) || (rc = dev_alloc(e, &st.wmean, (size_t)e->d * C)) ||
         (rc = dev_alloc(e, &st.wM2, (size_t)e->nt * C)) || (rc = dev_alloc(e, &st.wcount, (size_t)C)) ||
         (rc = dev_alloc(e, &st.P, (size_t)e->d * C)) || (rc = dev_alloc(e, &e->d_Cmat, (size_t)((cfg->algo == PBU_ALGO_ISDE || cfg->algo == PBU_ALGO_HMC) ? e->nt : 0) * C)) || (rc = dev_alloc(e, &e->streams.cur_n, (size_t)C)) ||
-        (rc = dev_alloc(e, &e->streams.cur_u, (size_t)C)))
+        (rc = dev_alloc(e, &e->streams.cur_u, (size_t)C)) ||
+        (rc = dev_alloc(e, &e->d_mom_partial, (size_t)(2 + 4 * e->d + e->nt) * PBU_MOMENT_SLICES)) ||
+        (rc = dev_alloc(e, &e->d_mom_scratch, (size_t)(2 + 4 * e->d + e->nt) + e->d)))
         return rc;
+    CUDA_TRY(cudaMallocHost((void **)&e->h_R0_pinned, (size_t)(e->nt + 1) * sizeof(double)));
+    CUDA_TRY(cudaEventCreateWithFlags(&e->r0_event, cudaEventDisableTiming));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     *out = e;
     return PBU_OK;
@@ -533,6 +537,8 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_destroy(pbu_eng
     for (void *p : e->allocs) cudaFree(p);
     if (e->d_normals) cudaFree(e->d_normals);
     if (e->d_uniforms) cudaFree(e->d_uniforms);
+    if (e->h_R0_pinned) cudaFreeHost(e->h_R0_pinned);
+    if (e->r0_event) cudaEventDestroy(e->r0_event);
     delete e;
     return PBU_OK;
 }
@@ -571,6 +577,12 @@ __global__ void fill_i64_kernel(int64_t *dst, int64_t n, int64_t v) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = v;
 }
+// rows [C][d] -> chain-minor [d][C]
+__global__ void aos_to_soa_kernel(const double *src, int64_t C, int d, double *dst) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    for (int i = 0; i < d; ++i) dst[(int64_t)i * C + c] = src[c * d + i];
+}
 struct RowValues {
     double v[tri_size(PBU_MAX_DIM)];
 };
@@ -594,9 +606,12 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_init_chains(pbu
     const int d = e->d, nt = e->nt;
     const int64_t C = e->C;
     int rc;
-    std::vector<double> soa;
-    transpose_to_soa(x0_host, C, d, soa);
-    CUDA_TRY(cudaMemcpyAsync(e->st.x, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    // the caller's rows [C][d] go to the device as they are (asynchronous when they sit in pinned memory) and are turned
+    // chain-minor there; the momentum array, cleared below, is the staging area
+    const size_t n_state = (size_t)d * C;
+    CUDA_TRY(cudaMemcpyAsync(e->st.P, x0_host, n_state * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+    aos_to_soa_kernel<<<(unsigned)((C + 255) / 256), 256, 0, e->stream>>>(e->st.P, C, d, e->st.x);
+    CUDA_TRY(cudaGetLastError());
     const bool adapt = e->cfg.algo == PBU_ALGO_AM || e->cfg.algo == PBU_ALGO_DRAM;
     const bool hmc = e->cfg.algo == PBU_ALGO_HMC;
     const bool isde = e->cfg.algo == PBU_ALGO_ISDE || hmc;
@@ -632,7 +647,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_init_chains(pbu
             // V_i = V_0 (mha.py:404), X_av_i = param_init (:405); Welford mode starts from M2 = 0
             if (e->cfg.am_welford) std::fill(Vp.begin(), Vp.end(), 0.0);
             if ((rc = broadcast_rows(e, e->st.V, Vp))) return rc;
-            CUDA_TRY(cudaMemcpyAsync(e->st.xav, e->st.x, soa.size() * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+            CUDA_TRY(cudaMemcpyAsync(e->st.xav, e->st.x, n_state * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
         }
     }
     CUDA_TRY(cudaMemsetAsync(e->st.mean_r, 0, C * sizeof(double), e->stream));
@@ -676,6 +691,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_set_proposal(pb
         for (int j = i; j < d; ++j) Vp[tri_idx(d, i, j)] = V_host[i * d + j];
     int rc;
     CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->r0_pending = false;
     if (e->cfg.algo == PBU_ALGO_ISDE || e->cfg.algo == PBU_ALGO_HMC) {
         std::vector<double> IL;
         inv_upper_host(Rp, d, IL);
@@ -769,6 +785,11 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine 
         e->iteration += n_steps;
         return PBU_OK;
     }
+    if (e->r0_pending) {                 // pooled-covariance mode: the factor computed by pbu_engine_pooled_finalize_dev
+        CUDA_TRY(cudaEventSynchronize(e->r0_event));
+        e->r0_pending = false;
+        if (e->h_R0_pinned[e->nt] != 0.0) e->R0.assign(e->h_R0_pinned, e->h_R0_pinned + e->nt);
+    }
     MhParams p;
     memset(&p, 0, sizeof p);
     p.prob = e->prob;
@@ -839,6 +860,23 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_get_counters(pb
     if (mean_r) CUDA_TRY(cudaMemcpyAsync(mean_r, e->st.mean_r, e->C * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     if (n_eval) CUDA_TRY(cudaMemcpyAsync(n_eval, e->st.n_eval, e->C * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
     if (status) CUDA_TRY(cudaMemcpyAsync(status, e->st.status, e->C * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PBU_OK;
+}
+
+// State and counters in ONE pass: every array is copied straight into the caller's buffer (asynchronous when that is
+// pinned memory), the stream is synchronised once.  x comes back chain-minor [d][C], the layout it has on the device.
+extern "C" __attribute__((visibility("default"))) int pbu_engine_read_state(pbu_engine *e, double *x_soa_host, double *lp_host, int64_t *n_rejected,
+                                                                                  double *mean_r, int64_t *n_eval, int32_t *status) {
+    if (!e) return fail(PBU_ERR_INVALID, "null engine");
+    CUDA_TRY(cudaSetDevice(e->device));
+    const size_t C = (size_t)e->C;
+    if (x_soa_host) CUDA_TRY(cudaMemcpyAsync(x_soa_host, e->st.x, (size_t)e->d * C * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (lp_host) CUDA_TRY(cudaMemcpyAsync(lp_host, e->st.lp, C * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (n_rejected) CUDA_TRY(cudaMemcpyAsync(n_rejected, e->st.n_rej, C * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
+    if (mean_r) CUDA_TRY(cudaMemcpyAsync(mean_r, e->st.mean_r, C * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (n_eval) CUDA_TRY(cudaMemcpyAsync(n_eval, e->st.n_eval, C * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
+    if (status) CUDA_TRY(cudaMemcpyAsync(status, e->st.status, C * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     return PBU_OK;
 }

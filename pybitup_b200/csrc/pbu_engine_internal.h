@@ -23,6 +23,9 @@ int pbu_fail(int code, const char *fmt, ...);
 // tables, pbu_math.cuh: 12,288 B with their alignment slack); taken off the opt-in maximum when the tiles are planned
 #define PBU_STATIC_SMEM_RESERVE 12800
 
+// chain slices of the moment reduction (pbu_moments.cu): partial sums [L][slices], added in slice order
+#define PBU_MOMENT_SLICES 64
+
 struct pbu_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -50,6 +53,14 @@ struct pbu_engine {
     size_t smem_bytes = 0;        // step / log-posterior kernels: barrier + likelihood records
     size_t smem_raw_bytes = 0;    // model-evaluation kernel: barrier + raw records
     std::vector<double> R0;       // packed upper Cholesky factor of the shared proposal covariance
+    // K4 (pbu_moments.cu): persistent scratch, taken once when the engine is created
+    double *d_mom_partial = nullptr;   // [L][PBU_MOMENT_SLICES] slice partials
+    double *d_mom_scratch = nullptr;   // [L + d] sums and reference point of the host-buffer entry point
+    // pooled-covariance mode of the non-adaptive MH kernels: the shared factor R0 is a kernel parameter, so the factor the
+    // device computed comes back through pinned memory; pbu_engine_run waits for the event before its next launch
+    double *h_R0_pinned = nullptr;     // [nt + 1]: R packed, ok flag
+    cudaEvent_t r0_event = nullptr;
+    bool r0_pending = false;
     // device allocations
     double *d_records = nullptr;
     double *d_raw = nullptr;

@@ -11,6 +11,31 @@ import numpy as np
 from . import diagnostics
 
 
+def local_device():
+    """The CUDA device of this process: LOCAL_RANK under torchrun (one process per GPU), else torch's current device."""
+    import os
+    import torch
+    if "LOCAL_RANK" in os.environ and torch.cuda.is_available():
+        return int(os.environ["LOCAL_RANK"]) % max(torch.cuda.device_count(), 1)
+    return torch.cuda.current_device() if torch.cuda.is_available() else 0
+
+
+def ensure_process_group():
+    """Under torchrun (WORLD_SIZE > 1 in the environment) with no process group yet: bind this process to its LOCAL_RANK
+    GPU and initialise NCCL (gloo without CUDA: the CPU tests).  A no-op for a plain single-process run."""
+    import os
+    import torch
+    import torch.distributed as dist
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1 or not dist.is_available() or dist.is_initialized():
+        return
+    if torch.cuda.is_available():
+        dev = local_device()
+        torch.cuda.set_device(dev)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    else:
+        dist.init_process_group("gloo")
+
+
 def shard_range(n_total, world_size, rank):
     """Contiguous [first, first + count) of n_total units for `rank`; the remainder goes to the low ranks."""
     base, rem = divmod(int(n_total), int(world_size))
@@ -32,6 +57,8 @@ class Reducer:
         self.rank = dist.get_rank(group) if self.active else 0
         if device is None and self.active and dist.get_backend(group) == "nccl":
             device = torch.device("cuda", torch.cuda.current_device())
+        elif isinstance(device, int):
+            device = torch.device("cuda", device)
         self.device = device if device is not None else torch.device("cpu")
 
     def __call__(self, a, op="sum"):
@@ -42,6 +69,15 @@ class Reducer:
         t = self._torch.from_numpy(a.copy()).to(self.device)
         dist.all_reduce(t, op={"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX}[op],
                         group=self.group)
+        return t.cpu().numpy().astype(a.dtype, copy=False).reshape(a.shape)
+
+    def broadcast0(self, a):
+        """The array of rank 0 on every rank (small host arrays: the final state of global chain 0, file decisions)."""
+        a = np.ascontiguousarray(a)
+        if not self.active or self.world_size == 1:
+            return a
+        t = self._torch.from_numpy(a.copy()).to(self.device)
+        self._dist.broadcast(t, src=self._dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
         return t.cpu().numpy().astype(a.dtype, copy=False).reshape(a.shape)
 
     @property

@@ -341,6 +341,23 @@ class ChainEngine:
             n_eval.ctypes.data_as(C.POINTER(C.c_int64)), status.ctypes.data_as(C.POINTER(C.c_int32))))
         return dict(n_rejected=n_rej, mean_r=mean_r, n_eval=n_eval, status=status)
 
+    def read_state(self):
+        """State and counters of every chain through PINNED staging buffers (allocated once): one asynchronous copy per
+        array, one synchronisation.  Returns numpy views of the staging buffers (valid until the next call): x [C, d] (a
+        transposed view of the device layout [d, C]), lp, n_rejected, mean_r, n_eval, status."""
+        torch = self._torch
+        if not hasattr(self, "_stage"):
+            Cn, d = self.n_chains, self.d
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()      # noqa: E731
+            self._stage = dict(x=mk((d, Cn), torch.float64), lp=mk((Cn,), torch.float64), n_rejected=mk((Cn,), torch.int64),
+                               mean_r=mk((Cn,), torch.float64), n_eval=mk((Cn,), torch.int64), status=mk((Cn,), torch.int32))
+        st = self._stage
+        capi.check(capi.lib.pbu_engine_read_state(self._h, *[C.c_void_p(st[k].data_ptr()) for k in
+                                                             ("x", "lp", "n_rejected", "mean_r", "n_eval", "status")]))
+        out = {k: v.numpy() for k, v in st.items()}
+        out["x"] = out["x"].T
+        return out
+
     def proposal(self):
         R = np.empty((self.n_chains, self.d, self.d))
         V = np.empty((self.n_chains, self.d, self.d))
@@ -366,11 +383,68 @@ class ChainEngine:
             raise ValueError("V must be [d, d]")
         capi.check(capi.lib.pbu_engine_set_proposal(self._h, capi.dptr(V)))
 
+    def pooled_statistics(self, reducer=None, apply=False, scale=None, eps=None):
+        """Pooled mean / covariance / Gelman-Rubin R-hat of the kept states of ALL chains (of all ranks when `reducer` is
+        an active NCCL ``distributed.Reducer``), computed on the device: two passes over the per-chain running moments,
+        each followed by one in-place all-reduce (``2 + d``, then ``2 + 4d + d(d+1)/2`` doubles), and a finalisation kernel.  Nothing is
+        allocated per call after the first, nothing is copied to the host and the stream is not synchronised.
+
+        apply=True also turns the pooled covariance into every chain's proposal (MH family: ``R = chol(scale (cov + eps
+        I))``, mha.py:463, :486-487) or preconditioner (ISDE / HMC: ``C_approx``, ``inv_L_c``, mha.py:745-746, :773-777)
+        -- the pooled-covariance mode that replaces one chain's recursion by the covariance of all chains.
+        Returns the device statistics vector (torch tensor, layout in include/pybitup_b200.h); ``statistics_dict`` turns
+        it into the host dictionary."""
+        torch = self._torch
+        if not hasattr(self, "_mom"):
+            dev = torch.device("cuda", self.device)
+            L = int(capi.lib.pbu_engine_chain_sums_len(self._h))
+            n = int(capi.lib.pbu_engine_pooled_stats_len(self._h))
+            self._mom = dict(s1=torch.zeros(2 + self.d, dtype=torch.float64, device=dev), s2=torch.zeros(L, dtype=torch.float64, device=dev),
+                             mu=torch.zeros(self.d, dtype=torch.float64, device=dev),
+                             stats=torch.zeros(n, dtype=torch.float64, device=dev))
+        m = self._mom
+        dsum = reducer.device_sum if reducer is not None else None
+        if reducer is not None and reducer.active and reducer.world_size > 1 and dsum is None:
+            raise RuntimeError("pooled_statistics needs an NCCL process group (the all-reduce runs on the device)")
+        if dsum is not None and reducer.device.index != self.device:
+            raise RuntimeError("the reducer is bound to cuda:%s, the engine to cuda:%d" % (reducer.device.index, self.device))
+        vp = lambda t: C.c_void_p(t.data_ptr())          # noqa: E731
+        capi.check(capi.lib.pbu_engine_chain_sums_dev(self._h, None, vp(m["s1"]), 2 + self.d))     # pass 1: count and first moments
+        if dsum is not None:
+            dsum(m["s1"])
+        capi.check(capi.lib.pbu_engine_pooled_mean_dev(self._h, vp(m["s1"]), None, vp(m["mu"])))
+        capi.check(capi.lib.pbu_engine_chain_sums_dev(self._h, vp(m["mu"]), vp(m["s2"]), 0))
+        if dsum is not None:
+            dsum(m["s2"])
+        isde = self.config.algo in ("ISDE", "HMC")
+        if scale is None:
+            scale = 1.0 if isde else 2.38 ** 2 / self.d              # mha.py:630, :402
+        if eps is None:
+            eps = 1e-10 if isde else float(self.config.eps_v)        # mha.py:631, :403
+        capi.check(capi.lib.pbu_engine_pooled_finalize_dev(self._h, vp(m["s2"]), vp(m["mu"]), float(scale), float(eps),
+                                                           1 if apply else 0, vp(m["stats"])))
+        return m["stats"]
+
+    def statistics_dict(self, stats):
+        """Host dictionary of a statistics vector returned by ``pooled_statistics`` (one small device -> host copy)."""
+        v = stats.cpu().numpy()
+        d, nt = self.d, self.d * (self.d + 1) // 2
+        o = 4
+        out = dict(n_chains=int(round(v[0])), n=int(round(v[1])), proposal_ok=bool(v[2] != 0.0))
+        for name, n, shape in (("mean", d, (d,)), ("cov", d * d, (d, d)), ("W", d, (d,)), ("B_over_n", d, (d,)), ("rhat", d, (d,))):
+            out[name] = v[o:o + n].reshape(shape).copy()
+            o += n
+        iu = np.triu_indices(d)
+        for name in ("V", "R", "inv_R"):
+            M = np.zeros((d, d))
+            M[iu] = v[o:o + nt]
+            out[name] = M + np.triu(M, 1).T if name == "V" else M
+            o += nt
+        return out
+
     def statistics(self, reducer=None):
-        """Pooled mean / covariance and R-hat of the kept states of all chains (of all ranks with a reducer)."""
-        from .distributed import global_chain_statistics
-        x, _ = self.state()
-        return global_chain_statistics(self.chain_sums, self.d, reducer, mu0=None if reducer is not None else x[0])
+        """Pooled mean / covariance and R-hat of the kept states of all chains (of all ranks with an NCCL reducer)."""
+        return self.statistics_dict(self.pooled_statistics(reducer))
 
     def isde_state(self):
         P = np.empty((self.n_chains, self.d))
@@ -379,14 +453,20 @@ class ChainEngine:
         return dict(P=P, C=Cm)
 
     # -- evaluation only ----------------------------------------------------------------------
-    def log_posterior(self, X):
+    def _check_X(self, X):
         X = _f64(np.atleast_2d(X))
+        if X.ndim != 2 or X.shape[1] != self.d:
+            raise ValueError("X must be [S, d] = [S, %d], got %s" % (self.d, X.shape))
+        return X
+
+    def log_posterior(self, X):
+        X = self._check_X(X)
         out = np.empty(X.shape[0])
         capi.check(capi.lib.pbu_eval_logpost(self._h, capi.dptr(X), X.shape[0], capi.dptr(out)))
         return out
 
     def model_eval(self, X):
-        X = _f64(np.atleast_2d(X))
+        X = self._check_X(X)
         out = np.empty((X.shape[0], self.problem.n_points))
         capi.check(capi.lib.pbu_eval_model(self._h, capi.dptr(X), X.shape[0], capi.dptr(out)))
         return out

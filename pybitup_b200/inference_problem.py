@@ -4,7 +4,7 @@
 does (proposal covariance :37-49, n_iterations :53, save_eval_freq :57-60, estimate_* :64-73, per-algorithm keys
 :79-107) and instantiates the sampler classes of ``metropolis_hastings_algorithms`` -- which here drive the CUDA
 engine.  Engine-only keys of the block (n_chains, seed, init_jitter, device, launch_iterations, save_all_chains,
-am_welford) are forwarded through ``opt_arg``.
+am_welford, chain_offset, pooled_covariance, pooled_update_it) are forwarded through ``opt_arg``.
 """
 import numpy as np
 import pandas as pd
@@ -12,7 +12,7 @@ import pandas as pd
 from . import metropolis_hastings_algorithms as mha
 
 ENGINE_KEYS = ("n_chains", "seed", "init_jitter", "device", "launch_iterations", "save_all_chains", "am_welford",
-               "chain_offset")
+               "chain_offset", "pooled_covariance", "pooled_update_it")
 
 
 class Sampler:

@@ -5,7 +5,18 @@ Same class names, constructor signatures and ``run_algorithm()`` entry point as 
 :490-567, ``DelayedRejectionAdaptiveMetropolisHastings`` :570-595, ``ito_SDE`` :886-1040), but the per-iteration
 Python loop is one fused CUDA kernel over ``n_chains`` independent chains (``ChainEngine``).  Engine-only options
 ride in ``opt_arg`` (the ``Sampler`` copies them from the ``Algorithm`` JSON block): ``n_chains`` (default 1),
-``seed``, ``init_jitter``, ``device``, ``launch_iterations``, ``save_all_chains``.
+``seed``, ``init_jitter``, ``device``, ``launch_iterations``, ``save_all_chains``, ``am_welford``,
+``pooled_covariance`` / ``pooled_update_it``.
+
+One process per GPU: when ``torch.distributed`` is initialised (``torchrun``), ``n_chains`` is the GLOBAL number of chains;
+every rank owns a contiguous range of the global chain index space (``distributed.shard_range``; the reference splits
+its propagation samples over MPI ranks the same way, ``solve_problem.py:497-529``), runs on its ``LOCAL_RANK`` GPU with
+``chain_offset`` = the first global index (which keys the Philox streams, so a chain does not depend on how the chains
+are sharded), and rank 0 -- the owner of global chain 0 -- writes the reference's files.  The data path has no
+collective; the only exchange is the small moment all-reduce of ``ChainEngine.pooled_statistics``: once at the end
+(pooled mean / covariance, Gelman-Rubin R-hat) and, with ``"pooled_covariance": "yes"``, every ``updating_it`` /
+``update_it`` iterations, when the covariance of ALL chains replaces each chain's own recursion in the proposal
+(``adapt_covariance``, mha.py:432-487, :736-777).
 
 Side effects reproduced: ``output/mcmc_chain.csv`` and ``mcmc_chain_reparam.csv`` (T+1 rows of
 chain 0, ``%f``), the ``output.txt`` header parsed by ``post_process`` (lines 1 and 3) and footer,
@@ -114,7 +125,15 @@ class _DeviceSampler:
         self.current_val = self.param_init
         self.IO_util = IO_util
         self.IO_fileID = IO_util["fileID"]
-        self.n_chains = int(self.opt_arg.get("n_chains", 1))
+        from .distributed import Reducer, shard_range
+        self.reducer = Reducer()                          # active under torchrun: one process per GPU
+        self.rank, self.world = self.reducer.rank, self.reducer.world_size
+        self.n_chains_total = int(self.opt_arg.get("n_chains", 1))
+        if self.n_chains_total < self.world:
+            raise ValueError("n_chains ({}) must be at least the number of ranks ({})".format(self.n_chains_total, self.world))
+        self.chain_first, self.n_chains = shard_range(self.n_chains_total, self.world, self.rank)
+        self.writer = self.rank == 0                      # owner of global chain 0: writes the reference's files
+        self.pooled = str(self.opt_arg.get("pooled_covariance", "no")) == "yes"
         self.n_rejected = 0
         self.mean_r = 0.0
         self.it = 0
@@ -128,16 +147,27 @@ class _DeviceSampler:
     def _proposal_matrix(self, eng):
         return self.V
 
+    def _pooled_interval(self):
+        """Iterations between two pooled-covariance refreshes (pooled mode)."""
+        return int(self.opt_arg.get("pooled_update_it", 0))
+
+    def _pooled_due(self, it):
+        k = self._pooled_interval()
+        return self.pooled and k > 0 and it % k == 0
+
     def _start_points(self):
-        x0 = np.tile(np.asarray(self.param_init, dtype=np.float64), (self.n_chains, 1))
+        """Starting points of THIS rank's chains.  They are drawn for the global chain index space and sliced, so that a
+        chain starts at the same point however the chains are sharded."""
+        C = self.n_chains_total
+        x0 = np.tile(np.asarray(self.param_init, dtype=np.float64), (C, 1))
         jitter = float(self.opt_arg.get("init_jitter", 0.0))
-        if self.n_chains > 1 and jitter > 0.0:
+        if C > 1 and jitter > 0.0:
             rng = np.random.default_rng(int(self.opt_arg.get("seed", 0)) + 7919)
             scale = np.where(x0[0] == 0.0, 1.0, np.abs(x0[0]))
-            x0[1:] += jitter * scale * rng.standard_normal((self.n_chains - 1, self.n_param))
+            x0[1:] += jitter * scale * rng.standard_normal((C - 1, self.n_param))
             lb, ub = self.problem.lb, self.problem.ub
             x0 = np.minimum(np.maximum(x0, lb), ub)
-        return x0
+        return np.ascontiguousarray(x0[self.chain_first:self.chain_first + self.n_chains])
 
     def _write_header(self):
         f = self.IO_fileID['out_data']                    # mha.py:131-135
@@ -155,81 +185,103 @@ class _DeviceSampler:
         back = rows if model is None else np.array([model.parametrization_backward(r) for r in rows])
         np.savetxt(self.IO_fileID['MChains'], back, fmt="%f", delimiter=",")
 
-    def _launch_len(self):
+    def _launch_len(self, done=0):
         n = int(self.opt_arg.get("launch_iterations", 0))
         if n <= 0:
             n = max(1, min(self.nIterations, 2000))
+        k = self._pooled_interval() if self.pooled else 0
+        if k > 0:                                         # a launch ends where the pooled covariance is refreshed
+            n = min(n, k - done % k)
         return n
 
     @time_it
     def run_algorithm(self):
+        from .distributed import local_device
         cfg = self._config()
         cfg.seed = int(self.opt_arg.get("seed", 0))
-        cfg.chain_offset = int(self.opt_arg.get("chain_offset", 0))
-        self.engine = eng = ChainEngine(self.problem, cfg, self.n_chains, device=int(self.opt_arg.get("device", 0)))
+        cfg.chain_offset = int(self.opt_arg.get("chain_offset", 0)) + self.chain_first
+        device = int(self.opt_arg["device"]) if self.opt_arg.get("device") is not None else local_device()
+        if self.reducer.device_sum is not None and self.reducer.device.index != device:
+            raise RuntimeError("rank {} runs its chains on cuda:{} but its process group is bound to cuda:{}".format(
+                self.rank, device, self.reducer.device.index))
+        self.engine = eng = ChainEngine(self.problem, cfg, self.n_chains, device=device)
         self.t1 = time.perf_counter()
         x0 = self._start_points()
         eng.init_chains(x0, self._proposal_matrix(eng))
-        for key in ('MChains', 'MChains_reparam'):
-            self.IO_fileID[key].seek(0)
-        self._write_header()
-        if self.algo_name == "DRAM":                      # double __init__ writes the header twice
-            self._write_header()
-        self._write_rows(x0[:1])
         save_all = str(self.opt_arg.get("save_all_chains", "no")) == "yes"
+        isde = self.algo_name == "ISDE"                 # aux_variables.csv rows (the HMC file is opened but left empty)
+        if self.writer:
+            for key in ('MChains', 'MChains_reparam'):
+                self.IO_fileID[key].seek(0)
+            self._write_header()
+            if self.algo_name == "DRAM":                  # double __init__ writes the header twice
+                self._write_header()
+            self._write_rows(x0[:1])
         kept0, kept_all, aux_rows = [x0[0].copy()], [], []
         done = 0
-        isde = self.algo_name == "ISDE"                 # aux_variables.csv rows (the HMC file is opened but left empty)
         while done < self.nIterations:
-            n = min(self._launch_len(), self.nIterations - done)
-            res = eng.run(n, thin=1, keep_samples=True, sample_chains=None if save_all else 1, keep_aux=isde)
-            eng.synchronize()
-            s = res.samples.cpu().numpy()                 # [n, d, Cs]
-            rows = np.ascontiguousarray(s[:, :, 0])
-            self._write_rows(rows)
-            if isde:
-                aux_rows.append(np.ascontiguousarray(res.aux.cpu().numpy()[:, :, 0]))
-            kept0.append(rows)
-            if save_all:
-                kept_all.append(s)
-            # model evaluations of the current (last accepted) state every save_eval_freq iterations (:366-368)
-            its = np.arange(done + 1, done + n + 1)
-            sel = its[its % self.save_eval_freq == 0]
-            if sel.size and self.save_eval_freq <= self.nIterations and hasattr(self.prob_distr, "likelihood"):
-                ev = eng.model_eval(rows[sel - done - 1])
-                for k, it in enumerate(sel):
-                    self.prob_distr.save_value(self.IO_util, int(it), ev[k])
+            n = min(self._launch_len(done), self.nIterations - done)
+            # rank 0 records global chain 0 (the reference's chain files); the other ranks record nothing unless asked
+            keep = self.writer or save_all
+            res = eng.run(n, thin=1, keep_samples=keep, sample_chains=None if save_all else 1, keep_aux=isde and self.writer)
+            if self._pooled_due(done + n):                # covariance of ALL chains -> every chain's proposal (device only)
+                eng.pooled_statistics(self.reducer, apply=True)
+            if keep:
+                eng.synchronize()
+                s = res.samples.cpu().numpy()             # [n, d, Cs]
+                if save_all:
+                    kept_all.append(s)
+            if self.writer:
+                rows = np.ascontiguousarray(s[:, :, 0])
+                self._write_rows(rows)
+                if isde:
+                    aux_rows.append(np.ascontiguousarray(res.aux.cpu().numpy()[:, :, 0]))
+                kept0.append(rows)
+                # model evaluations of the current (last accepted) state every save_eval_freq iterations (:366-368)
+                its = np.arange(done + 1, done + n + 1)
+                sel = its[its % self.save_eval_freq == 0]
+                if sel.size and self.save_eval_freq <= self.nIterations and hasattr(self.prob_distr, "likelihood"):
+                    ev = eng.model_eval(rows[sel - done - 1])
+                    for k, it in enumerate(sel):
+                        self.prob_distr.save_value(self.IO_util, int(it), ev[k])
             done += n
             self.it = done
         self.chain = np.vstack([kept0[0][None, :]] + kept0[1:]) if len(kept0) > 1 else kept0[0][None, :]
         if save_all and kept_all:
             self.chains_all = np.concatenate(kept_all, axis=0)
-            np.save(str(self.IO_util['path']['out_folder'] / "mcmc_chains_all.npy"), self.chains_all)
-        if isde:
+            name = "mcmc_chains_all.npy" if self.world == 1 else "mcmc_chains_all_rank{}.npy".format(self.rank)
+            np.save(str(self.IO_util['path']['out_folder'] / name), self.chains_all)
+        if isde and self.writer:
             self._write_aux(x0[0], aux_rows)
         self._finish()
 
     def _write_aux(self, x0, aux_rows):
-        """aux_variables.csv: per iteration the d rows [P_nm, xi_nm] BEFORE the update (mha.py:1032)."""
+        """aux_variables.csv: T + 1 blocks of d rows [P, xi] -- the initial (0, xi_0) written by ito_SDE.__init__ and then
+        (P_n, xi_n) AFTER the update of every iteration (mha.py:1032 runs after the assignment at :1003-1004)."""
         if 'aux_variables' not in self.IO_fileID or not aux_rows:
             return
         P = np.vstack([np.zeros((1, self.n_param))] + aux_rows)
-        for it in range(self.nIterations):
+        for it in range(self.nIterations + 1):
             np.savetxt(self.IO_fileID['aux_variables'], np.transpose(np.array([P[it], self.chain[it]])), fmt="%f", delimiter=",")
 
     def _finish(self):
         eng = self.engine
+        # many-chain statistics (new): pooled mean / covariance, Gelman-Rubin R-hat over the chains of ALL ranks -- one
+        # small all-reduce on the device; every rank takes part
+        self.statistics = eng.statistics(self.reducer) if self.n_chains_total > 1 else None
         x, lp = eng.state()
         ctr = eng.counters()
-        self.param_init[...] = x[0]                       # in-place: the caller's array ends at the final state (:215)
+        # in-place: the caller's array ends at the final state of global chain 0 (:215), on every rank
+        self.param_init[...] = self.reducer.broadcast0(x[0])
         self.current_val = self.param_init
         self.distr_fun_current_val = float(lp[0])
         self.n_rejected = int(ctr["n_rejected"][0])
         self.mean_r = float(ctr["mean_r"][0])
         self.status = ctr["status"]
-        if np.any(ctr["status"] & 1):
+        n_bad = int(self.reducer(np.array([np.sum((ctr["status"] & 1) > 0)], dtype=np.float64), "sum")[0])
+        if n_bad:
             raise np.linalg.LinAlgError("adapted covariance not positive definite in {} chain(s) "
-                                        "(scipy.linalg.cholesky raises here in the reference, mha.py:487)".format(int(np.sum(ctr["status"] & 1 > 0))))
+                                        "(scipy.linalg.cholesky raises here in the reference, mha.py:487)".format(n_bad))
         prop = eng.proposal()
         self.R = prop["R"][0]
         self.V_i = prop["V"][0]
@@ -237,22 +289,21 @@ class _DeviceSampler:
         # compute_covariance (:295-307): mean / covariance of chain 0 (from the exact states, not the 6-decimal CSV)
         self.mean_c = np.mean(self.chain, axis=0)
         self.cov_c = np.atleast_2d(np.cov(self.chain, rowvar=False)) if self.chain.shape[0] > 1 else np.zeros((self.n_param, self.n_param))
-        np.savetxt("cov.csv", self.cov_c, delimiter=",")
-        # many-chain statistics (new): pooled mean / covariance, Gelman-Rubin R-hat
-        self.statistics = eng.statistics() if self.n_chains > 1 else None
         rejection_rate = 0 if self.nIterations == 0 else self.n_rejected / self.nIterations * 100
-        print("\nRejection rate is {} %".format(rejection_rate))
-        f = self.IO_fileID['out_data']                    # terminate_loop (:322-357)
-        f.write("\nRejection rate is {} % \n".format(rejection_rate))
-        f.write("\nElapsed time: {} \n".format(time.strftime("%H:%M:%S", time.gmtime(time.perf_counter() - self.t1))))
-        f.write("\nMaximum Likelihood Estimator (MLE) \n")
-        f.write("Log-likelihood value \n")
-        f.write("\nCovariance Matrix is \n{}".format(self.cov_c))
-        if self.statistics is not None:
-            f.write("\nChains: {}\nPooled mean \n{}\nPooled covariance \n{}\nGelman-Rubin R-hat \n{}".format(
-                self.n_chains, self.statistics["mean"], self.statistics["cov"], self.statistics["rhat"]))
-        for key in ('MChains', 'MChains_reparam', 'out_data'):
-            self.IO_fileID[key].flush()
+        if self.writer:
+            np.savetxt("cov.csv", self.cov_c, delimiter=",")
+            print("\nRejection rate is {} %".format(rejection_rate))
+            f = self.IO_fileID['out_data']                    # terminate_loop (:322-357)
+            f.write("\nRejection rate is {} % \n".format(rejection_rate))
+            f.write("\nElapsed time: {} \n".format(time.strftime("%H:%M:%S", time.gmtime(time.perf_counter() - self.t1))))
+            f.write("\nMaximum Likelihood Estimator (MLE) \n")
+            f.write("Log-likelihood value \n")
+            f.write("\nCovariance Matrix is \n{}".format(self.cov_c))
+            if self.statistics is not None:
+                f.write("\nChains: {}\nPooled mean \n{}\nPooled covariance \n{}\nGelman-Rubin R-hat \n{}".format(
+                    self.n_chains_total, self.statistics["mean"], self.statistics["cov"], self.statistics["rhat"]))
+            for key in ('MChains', 'MChains_reparam', 'out_data'):
+                self.IO_fileID[key].flush()
         eng.close()
 
 
@@ -273,8 +324,13 @@ class AdaptiveMetropolisHastings(_DeviceSampler):
         self.starting_it, self.updating_it, self.eps_v = int(starting_it), int(updating_it), float(eps_v)
 
     def _config(self):
+        if self.pooled:       # the covariance of all chains replaces the per-chain recursion: the RWMH kernel, refreshed factor
+            return SamplerConfig(algo="RWMH", eps_v=self.eps_v)
         return SamplerConfig(algo=self.algo_name, updating_it=self.updating_it, eps_v=self.eps_v,
                              am_welford=str(self.opt_arg.get("am_welford", "no")) == "yes")
+
+    def _pooled_interval(self):
+        return int(self.opt_arg.get("pooled_update_it", self.updating_it))
 
 
 class DelayedRejectionMetropolisHastings(_DeviceSampler):
@@ -298,8 +354,13 @@ class DelayedRejectionAdaptiveMetropolisHastings(_DeviceSampler):
         self.starting_it, self.updating_it, self.eps_v, self.gamma = int(starting_it), int(updating_it), float(eps_v), float(gamma)
 
     def _config(self):
+        if self.pooled:
+            return SamplerConfig(algo="DR", eps_v=self.eps_v, gamma_dr=self.gamma)
         return SamplerConfig(algo=self.algo_name, updating_it=self.updating_it, eps_v=self.eps_v, gamma_dr=self.gamma,
                              am_welford=str(self.opt_arg.get("am_welford", "no")) == "yes")
+
+    def _pooled_interval(self):
+        return int(self.opt_arg.get("pooled_update_it", self.updating_it))
 
 
 class _GradientSampler(_DeviceSampler):
@@ -326,6 +387,18 @@ class _GradientSampler(_DeviceSampler):
         self.starting_it = int(self.C_matrix['starting_it'])
         self.update_it = int(self.C_matrix['update_it'])
         self.end_it = int(self.C_matrix['end_it']) if self.C_matrix.get("end_it") is not None else self.nIterations + 1
+
+    def _pooled_interval(self):
+        return int(self.opt_arg.get("pooled_update_it", self.update_it))
+
+    def _pooled_due(self, it):
+        # the adaptation window of GradientBasedMCMC.adapt_covariance (:740, :767): refreshes at multiples of update_it
+        # inside [starting_it, end_it + 1]
+        return _DeviceSampler._pooled_due(self, it) and self.starting_it <= it <= self.end_it + 1
+
+    def _adapt_window(self):
+        """(adapt_start, adapt_update, adapt_end) of the engine: the per-chain window, switched off in pooled mode."""
+        return (0, self.update_it, 0) if self.pooled else (self.starting_it, self.update_it, self.end_it)
 
     def _proposal_matrix(self, eng):
         """C_approx: identity, a given matrix, or the inverse of minus the finite-difference Hessian of the
@@ -360,8 +433,9 @@ class HamiltonianMonteCarlo(_GradientSampler):
         self.epsilon, self.L = float(step_size), int(num_steps)
 
     def _config(self):
+        a0, au, a1 = self._adapt_window()
         return SamplerConfig(algo="HMC", hmc_step_size=self.epsilon, hmc_num_steps=self.L, isde_gradient=self.gradient,
-                             adapt_start=self.starting_it, adapt_update=self.update_it, adapt_end=self.end_it)
+                             adapt_start=a0, adapt_update=au, adapt_end=a1)
 
     def _finish(self):
         st = self.engine.isde_state()
@@ -381,8 +455,9 @@ class ito_SDE(_GradientSampler):
         self.h, self.f0 = float(h), float(f0)
 
     def _config(self):
+        a0, au, a1 = self._adapt_window()
         return SamplerConfig(algo="ISDE", isde_h=self.h, isde_f0=self.f0, isde_gradient=self.gradient,
-                             adapt_start=self.starting_it, adapt_update=self.update_it, adapt_end=self.end_it)
+                             adapt_start=a0, adapt_update=au, adapt_end=a1)
 
     def _finish(self):
         st = self.engine.isde_state()

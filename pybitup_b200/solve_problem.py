@@ -3,10 +3,15 @@ propagation paths.
 
 ``Sampling(json).sample({id: model})`` (reference :84-358) and ``Propagation(json).propagate({id: model})``
 (:361-647, ``emulator == "None"``) keep the reference's input schema, data loading and output files; the sampler loop
-and the per-sample model loop run on the CUDA engine.  Branches of the reference outside the hot path
-(``Sampling.Distribution``, ``ComputeAnalyticalDistribution``, the PCE emulator) raise ``NotImplementedError``.
+and the per-sample model loop run on the CUDA engine.  ``Sampling.Distribution`` (sampling an analytic density, :134-164)
+is lowered to a device pseudo-model; branches of the reference outside the hot path (``ComputeAnalyticalDistribution``,
+the PCE emulator) raise ``NotImplementedError``.
+
+One process per GPU (``torchrun``): every rank parses the input and builds the problem, rank 0 alone owns the output
+files (the other ranks' handles point at ``os.devnull``), chains / samples are sharded by global index.
 """
 import json
+import os
 import pathlib
 import pickle
 import shutil
@@ -59,11 +64,19 @@ class SolveProblem:
         self.IO_util['path']['out_folder'].mkdir(exist_ok=True)
         self.IO_util['path']['fun_eval_folder'] = pathlib.Path(self.IO_util['path']['out_folder'], "model_eval")
         self.IO_util['path']['out_data'] = pathlib.Path(self.IO_util['path']['out_folder'], "output.txt")
-        self.IO_util['fileID']['out_data'] = open(self.IO_util['path']['out_data'], 'a+')
-        try:
-            shutil.copy(input_file_name, self.IO_util['path']['out_folder'])
-        except shutil.SameFileError:
-            pass
+        from .distributed import ensure_process_group
+        ensure_process_group()                              # torchrun: one process per GPU, NCCL
+        self.rank = Reducer().rank
+        self.IO_util['fileID']['out_data'] = self._open(self.IO_util['path']['out_data'], 'a+')
+        if self.rank == 0:
+            try:
+                shutil.copy(input_file_name, self.IO_util['path']['out_folder'])
+            except shutil.SameFileError:
+                pass
+
+    def _open(self, path, mode):
+        """Output files belong to rank 0; the other ranks of a torchrun job get a sink (they would truncate its files)."""
+        return open(path, mode) if self.rank == 0 else open(os.devnull, "w+")
 
     def close(self):
         for f in self.IO_util['fileID'].values():
@@ -92,7 +105,7 @@ class Sampling(SolveProblem):
                 new_file_list['estimate_max_val_distr'] = "MAP_estimation.csv"
         for key, name in new_file_list.items():
             self.IO_util['path'][str(key)] = pathlib.Path(self.IO_util['path']['out_folder'], name)
-            self.IO_util['fileID'][str(key)] = open(self.IO_util['path'][str(key)], "w+")
+            self.IO_util['fileID'][str(key)] = self._open(self.IO_util['path'][str(key)], "w+")
 
     @staticmethod
     def _read_data(c_data, model):
@@ -139,8 +152,9 @@ class Sampling(SolveProblem):
             models[model_id].param_nom = np.array(c_model['param_values'])
             models[model_id].param_names = c_model['param_names']
             data[model_id] = self._read_data(BP['Data'][data_set], models[model_id])
-        with open(pathlib.Path(self.IO_util['path']['out_folder'], "data.bin"), 'wb') as f:
-            pickle.dump(data, f)
+        if self.rank == 0:
+            with open(pathlib.Path(self.IO_util['path']['out_folder'], "data.bin"), 'wb') as f:
+                pickle.dump(data, f)
         unpar_name = list(BP['Prior']['Param'].keys())
         for mid in models.keys():
             models[mid].unpar_name = unpar_name
@@ -192,7 +206,8 @@ class Propagation(SolveProblem):
         self.IO_util['path']['out_folder_prop'] = pathlib.Path(self.IO_util['path']['out_folder'], "propagation")
         self.IO_util['path']['out_folder_prop'].mkdir(exist_ok=True)
 
-    def propagate(self, models=[], device=0):
+    def propagate(self, models=[], device=None):
+        """device: CUDA device of this process; default LOCAL_RANK under torchrun, else torch's current device."""
         if self.user_inputs.get("Propagation") is None:
             raise ValueError('Ask for uncertainty propagation but no Propagation inputs were provided')
         from .engine import ChainEngine, ProblemSpec, SamplerConfig
@@ -211,7 +226,14 @@ class Propagation(SolveProblem):
         n_sample = P["Model_evaluation"].get("Sample_number") if P.get("Model_evaluation") else None
         n_sample = len(unpar[names[-1]]) if n_sample is None else int(n_sample)
         X_all = np.stack([unpar[name][:n_sample] for name in names], axis=1)
+        from .distributed import local_device
+        device = local_device() if device is None else int(device)
         red = Reducer()                                   # one process per GPU: samples sharded, statistics all-reduced
+        if red.device_sum is not None and red.device.index != device:
+            raise RuntimeError("rank {} propagates on cuda:{} but its process group is bound to cuda:{}".format(
+                red.rank, device, red.device.index))
+        if n_sample < red.world_size:
+            raise ValueError("Sample_number ({}) must be at least the number of ranks ({})".format(n_sample, red.world_size))
         first, count = shard_range(n_sample, red.world_size, red.rank)
         self.IO_util['path']['fun_eval_folder'].mkdir(exist_ok=True)
         results = {}
@@ -231,9 +253,8 @@ class Propagation(SolveProblem):
                                unc_idx=m.uncertain_index(), y=np.zeros((1, N)), std_y=np.ones(N),
                                lb=np.full(len(names), -np.inf), ub=np.full(len(names), np.inf), gamma=1.0, design=design)
             with ChainEngine(spec, SamplerConfig(algo="RWMH"), 1, device=device) as eng:
-                with DevicePropagation(eng, max(count, 1)) as dp:
-                    Xl = X_all[first:first + count] if count > 0 else X_all[:1]
-                    dp.evaluate(Xl)
+                with DevicePropagation(eng, count) as dp:
+                    dp.evaluate(X_all[first:first + count])
                     st = dp.statistics((2.5, 97.5), reduce=red if red.active else None, n_total=n_sample)
                     if red.rank == 0:
                         fe = dp.evals(0, min(count, int(P.get("Model_evaluation", {}).get("save_evaluations", 1000))))

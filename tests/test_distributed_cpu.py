@@ -108,3 +108,64 @@ def test_ess_batch_means_iid_and_correlated():
     for t in range(1, len(x)):
         y[t] = 0.9 * y[t - 1] + x[t]
     assert diagnostics.ess_batch_means(y) < 0.15 * 20000
+
+
+# ---- the rank-aware sampling driver (host logic only: no engine is created before run_algorithm) -------------------------
+def _sampler_worker(rank, world, port, workdir, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    os.chdir(workdir)
+    from pybitup_b200 import bayesian_inference as bi, distributions, inference_problem, solve_problem, synthetic
+    from pybitup_b200 import metropolis_hastings_algorithms as mha
+    job = solve_problem.SolveProblem("case.json")          # initialises the process group (gloo here), rank-aware handles
+    assert dist.is_initialized() and dist.get_world_size() == world
+    job.IO_util['fileID']['MChains'] = job._open(os.path.join(workdir, "output", "mcmc_chain.csv"), "w+")
+    p = synthetic.cubic_problem(n_points=20)
+
+    class Poly(bi.Model):
+        device_model = "poly"
+
+    m = Poly()
+    m.x, m.param, m.param_nom, m.param_names, m.unpar_name = p["design"]["x"], p["theta_nom"].copy(), p["theta_nom"].copy(), list("abcd"), list("abcd")
+    data = {"m": bi.Data("y", m.x, {0: p["y"][0]}, p["std_y"])}
+    prior = distributions.set_probability_dist(["Mixture"], [["Uniform"] * 4, [[-10.0, 10.0]] * 4], 4)
+    post = bi.BayesianPosterior(prior, bi.Likelihood(data, {"m": m}, 1.0), m, p["x0"].copy())
+    opt = {"n_chains": 11, "init_jitter": 0.05, "seed": 3, "pooled_covariance": "yes"}
+    s = mha.AdaptiveMetropolisHastings(job.IO_util, 100, p["x0"].copy(), p["prop_cov"], post, 100, 10, 1e-10, opt)
+    cfg = s._config()
+    q.put((rank, s.chain_first, s.n_chains, s._start_points(), s.writer, job.IO_util['fileID']['MChains'].name, cfg.algo,
+           [s._launch_len(done) for done in (0, 3, 10, 95)], s._pooled_due(20), s._pooled_due(25)))
+    job.close()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sampler_sharding(tmp_path):
+    """Under torchrun-style ranks the sampler shards the GLOBAL chain index space, draws shard-invariant starting points,
+    gives rank 0 alone the output files, and in pooled mode cuts its launches at the refresh interval."""
+    with open(tmp_path / "case.json", "w") as f:
+        f.write("{}")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sampler_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, f0, c0, x0, w0, name0, algo0, lens0, due20, due25), (r1, f1, c1, x1, w1, name1, algo1, _, _, _) = res
+    assert (f0, c0, f1, c1) == (0, 6, 6, 5) and w0 and not w1
+    assert name0.endswith("mcmc_chain.csv") and name1 == os.devnull
+    assert algo0 == algo1 == "RWMH"                       # pooled mode: the non-adaptive kernel with a refreshed factor
+    assert lens0 == [10, 7, 10, 5] and due20 and not due25
+    # shard-invariant starting points: the two shards stacked are what a single process draws
+    from pybitup_b200 import synthetic
+    p = synthetic.cubic_problem(n_points=20)
+    x_all = np.tile(p["x0"], (11, 1))
+    rng = np.random.default_rng(3 + 7919)
+    x_all[1:] += 0.05 * np.abs(p["x0"]) * rng.standard_normal((10, 4))
+    assert np.array_equal(np.vstack([x0, x1]), x_all)

@@ -151,7 +151,9 @@ def test_isde_from_json_on_cubic(tmp_path, monkeypatch, precond):
     job.close()
     assert pd.read_csv("output/mcmc_chain.csv", header=None).values.shape == (T + 1, 4)
     aux = pd.read_csv("output/aux_variables.csv", header=None).values
-    assert aux.shape == (T * 4, 2) and np.all(aux[:4, 0] == 0.0)          # first rows: P_0 = 0, xi_0
+    # T + 1 blocks of d rows: (0, xi_0) from ito_SDE.__init__ (mha.py:921), then (P_n, xi_n) after every update (:1032)
+    assert aux.shape == ((T + 1) * 4, 2) and np.all(aux[:4, 0] == 0.0)
+    assert np.allclose(aux[-4:, 1], run.chain[-1], atol=1e-6)
     if not exact:
         assert np.all(np.isfinite(run.chain)) and run.C_approx.shape == (4, 4)
         assert np.all(np.linalg.eigvalsh((run.C_approx + run.C_approx.T) / 2) > 0)      # a factorisable matrix, or the identity

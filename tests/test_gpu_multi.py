@@ -20,3 +20,6 @@ def test_sharded_equals_single_gpu():
            "--master-port", "29617", os.path.join(ROOT, "tools", "multi_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "multi_gpu_check_%dgpu.log" % n), "w") as f:
+        f.write(r.stdout[-20000:])

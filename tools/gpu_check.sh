@@ -8,7 +8,6 @@ python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "pytes
 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?"
 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"; cat $OUT/bench_$TAG.json
 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2>&1; echo "ref rc=$?"; cat $OUT/bench_ref_$TAG.json
-timeout 600 python tools/bench_configs.py > $OUT/configs_$TAG.log 2>&1; echo "configs rc=$?"; cut -c1-400 $OUT/configs_$TAG.log
 python bench.py --steps 3 --warmup 3 --no-cpu --iters 100 > $OUT/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'mh_step|mh_coop|eval_|broadcast|fill|elementwise|Fill' -c 60 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu --iters 100 > $OUT/ncu_launches_$TAG.log 2>&1; echo "ncu launches rc=$?"
