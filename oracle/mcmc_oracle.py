@@ -304,8 +304,17 @@ def inv_upper_plain(R):
 
 # --------------------------------------------------------------------------- MH family
 def run_mh(prob, x0, V, n_it, streams, adaptive=False, delayed=False,
-           updating_it=10, eps_v=0.0, gamma_dr=0.2):
+           updating_it=10, eps_v=0.0, gamma_dr=0.2, am_welford=False):
     """RWMH / AM / DR / DRAM for ONE chain, literal reference semantics.
+
+    ``am_welford=True`` replaces the literal Haario recursion (:455, :463) by the engine's production update
+    (north_star: "the adaptive-covariance update is a Welford accumulation"; pbu_mh_kernel.cuh / pbu_mh_coop.cuh):
+    running mean and sum of outer products of deviations over x_0 .. x_i,
+        delta = x_i - mean;  mean += delta / (i + 1);  M2 += delta (x_i - mean)^T;
+        V_i = S_d (M2 / i + eps_v I)
+    i.e. the same estimator S_d (cov(x_0..x_i) + eps I) without the recursion's cancellation (and without its i = 1
+    quirks Q3 / Q4).  Written with the kernel's fused multiply-adds.  This is NOT reference arithmetic: it pins the
+    engine's own opt-in mode.
 
     Returns a dict with chain[T+1,d], lp[T+1] (log-posterior of the current state after
     each iteration), acc[T] (0 rejected, 1 accepted at stage 1, 2 at stage 2),
@@ -379,7 +388,28 @@ def run_mh(prob, x0, V, n_it, streams, adaptive=False, delayed=False,
             else:
                 n_rejected += 1
 
-            if adaptive:
+            if adaptive and am_welford:
+                i = it
+                if X_av is None:
+                    X_av = np.array(x0, dtype=np.float64)      # mean of {x_0}
+                    V_i = np.zeros((d, d))                      # M2
+                inv_n = 1.0 / (i + 1.0)
+                sc = S_d / i
+                dl = cur - X_av
+                mu = np.array([fma(dl[a], inv_n, X_av[a]) for a in range(d)])
+                M2 = np.array(V_i)
+                for a in range(d):
+                    for b in range(a, d):
+                        M2[a, b] = M2[b, a] = fma(dl[a], cur[b] - mu[b], V_i[a, b])
+                V_i, X_av = M2, mu
+                if i % updating_it == 0:
+                    Vc = np.array([[fma(sc, M2[a, b], (S_d * eps_v) if a == b else 0.0) for b in range(d)] for a in range(d)])
+                    R = chol_upper(Vc)
+                    if delayed:
+                        inv_R = inv_upper(R)
+                        inv_V = np.transpose(inv_R) * inv_R
+                mean_r += r
+            elif adaptive:
                 i = it
                 X_i = cur
                 X_av_prev = cur if X_av is None else X_av    # aliasing at i == 1 (Q3)
@@ -400,6 +430,8 @@ def run_mh(prob, x0, V, n_it, streams, adaptive=False, delayed=False,
                 mean_r += alpha                              # :170
             chain[it] = cur
             lps[it] = lp_cur
+    if adaptive and am_welford and n_it > 0:
+        V_i = S_d / n_it * V_i + S_d * eps_v * np.eye(d)       # what pbu_engine_get_proposal reports for this mode
     return dict(chain=chain, lp=lps, acc=acc, eval_x=np.array(evals_x), eval_lp=np.array(evals_lp),
                 R=R, V_i=V_i, X_av=(cur if X_av is None else X_av), n_rejected=n_rejected,
                 mean_r=mean_r, n_eval=len(evals_lp))

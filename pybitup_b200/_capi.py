@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libpybitup_b200.so")
+# PBU_LIB: an experimental build of the same library (tools/build_variant.sh), for A/B measurements
+LIB_PATH = os.environ.get("PBU_LIB") or os.path.join(_HERE, "_lib", "libpybitup_b200.so")
 
 PBU_MAX_PARAM = 16
 PBU_MAX_DIM = 16

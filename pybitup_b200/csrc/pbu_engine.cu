@@ -267,7 +267,6 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
             return fail(PBU_ERR_UNSUPPORTED, "a step kernel uses %zu B of static shared memory, more than the %d B reserved", fattr.sharedSizeBytes, PBU_STATIC_SMEM_RESERVE);
         max_smem -= PBU_STATIC_SMEM_RESERVE;
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        const bool adaptive = algo == PBU_ALGO_AM || algo == PBU_ALGO_DRAM;
         const size_t rec_aligned = (e->smem_bytes + 127) & ~(size_t)127;
         // replicated layout: a group of g lanes carries q chains per lane-set; cooperative: a team of g lanes owns q = g chains
         const int64_t groups_needed = (e->C + q - 1) / q;
@@ -279,15 +278,15 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
         const double work = q * (sequential ? N : std::ceil(N / g)) * ops * conflict + (coop ? 1.0 : (double)q) * S0;
         for (int B = MH_MAX_BLOCK; B >= 32; B -= 32) {
             if (want_block > 0 && B != want_block) continue;
-            // cooperative adaptive kernels stage (V_i, X_av, R) of every thread's chain in shared memory when there is room
+            // cooperative kernels park the own chain's state (x, y, lp, mean_r, u: 2d + 3 doubles per thread, component stride
+            // MH_MAX_BLOCK) behind the records for the duration of the data loop (pbu_mh_coop.cuh)
             size_t smem_launch = e->smem_bytes;
             int state_off = 0;
-            if (false && coop && adaptive) {      // staging the adaptive state in shared memory was measured slower: disabled
-                const size_t state = (size_t)(2 * e->nt + e->d) * sizeof(double) * B;
-                if (rec_aligned + state <= (size_t)max_smem) {
-                    state_off = (int)rec_aligned;
-                    smem_launch = rec_aligned + state;
-                }
+            if (coop) {
+                const size_t state = (size_t)(2 * e->d + 3) * sizeof(double) * MH_MAX_BLOCK;
+                if (rec_aligned + state > (size_t)max_smem) continue;
+                state_off = (int)rec_aligned;
+                smem_launch = rec_aligned + state;
             }
             int occ = 0;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, B, smem_launch) != cudaSuccess || occ < 1) {

@@ -27,6 +27,7 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
     constexpr bool DELAYED = (ALGO & 2) != 0;
     constexpr int NT = tri_size(D);
     constexpr int U = (Q >= 4) ? ((M::UNROLL > 2) ? 2 : M::UNROLL) : M::UNROLL;
+    constexpr bool PARK = !STREAM;               // the host reserves the slots behind the resident records (plan_launch)
     const int64_t C = p.st.n_chains;
     const int lane = threadIdx.x & 31;
     const unsigned team_mask = lane_group_mask<G>(lane);
@@ -75,6 +76,20 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
                 n_eval += 1;
                 inb = inside_box<D>(y, p.prob);
             }
+            // ---- the own chain's state sits the data loop out in shared memory (one slot per thread, component stride
+            // MH_MAX_BLOCK doubles): x, y, lp, mean_r, u are 2D + 3 register pairs the loop can spend on keeping all Q x U
+            // dependency chains in flight instead (at the 128-register cap ptxas otherwise interleaves only two of them)
+            volatile double *const park = PARK ? reinterpret_cast<volatile double *>(TileStream<M::NC>::smem() + p.state_smem_off) + threadIdx.x : nullptr;
+            if constexpr (PARK) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    park[i * MH_MAX_BLOCK] = x[i];
+                    park[(D + i) * MH_MAX_BLOCK] = y[i];
+                }
+                park[(2 * D) * MH_MAX_BLOCK] = lp;
+                park[(2 * D + 1) * MH_MAX_BLOCK] = mean_r;
+                park[(2 * D + 2) * MH_MAX_BLOCK] = u;
+            }
             // ---- the team evaluates the proposals of its Q chains together
             typename M::Ctx ctx[Q];
             typename M::Seq seq[Q];
@@ -106,6 +121,16 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
                         ts.release(records, n, p.tile_points, t);
                     }
                 }
+            }
+            if constexpr (PARK) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    x[i] = park[i * MH_MAX_BLOCK];
+                    y[i] = park[(D + i) * MH_MAX_BLOCK];
+                }
+                lp = park[(2 * D) * MH_MAX_BLOCK];
+                mean_r = park[(2 * D + 1) * MH_MAX_BLOCK];
+                u = park[(2 * D + 2) * MH_MAX_BLOCK];
             }
             double Jown = 0.0;
 #pragma unroll

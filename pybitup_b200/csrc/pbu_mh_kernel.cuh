@@ -155,20 +155,50 @@ __device__ __forceinline__ void tile_accumulate(const typename M::Ctx (&ctx)[Q],
         }
     } else {
         int k = sub;
+        if constexpr (M::HAS_MULTI && !GRAD && (Q > 1)) {
+            // two batches of U points per trip: half the loop bookkeeping per point, the second batch's records in flight
+            // while the first is evaluated
+#pragma unroll 1
+            for (; k + (2 * U - 1) * G < n; k += 2 * U * G) {
+                double rec[2][U][NC];
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int u = 0; u < U; ++u) load_record<NC>(tile, k + (h * U + u) * G, rec[h][u]);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    double t[Q][U];
+                    M::template resid_multi<Q, U>(ctx, rec[h], t);
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int q = 0; q < Q; ++q) J[q][u] = fma(t[q][u], t[q][u], J[q][u]);
+                }
+            }
+        }
 #pragma unroll 1
         for (; k + (U - 1) * G < n; k += U * G) {
             double rec[U][NC];
 #pragma unroll
             for (int u = 0; u < U; ++u) load_record<NC>(tile, k + u * G, rec[u]);
+            if constexpr (M::HAS_MULTI && !GRAD && (Q > 1)) {
+                double t[Q][U];
+                M::template resid_multi<Q, U>(ctx, rec, t);
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                double t[U];
-                M::template resid_batch<U>(ctx[q], seq[q], rec, t);
+                for (int u = 0; u < U; ++u)
 #pragma unroll
-                for (int u = 0; u < U; ++u) J[q][u] = fma(t[u], t[u], J[q][u]);
-                if constexpr (GRAD) {
+                    for (int q = 0; q < Q; ++q) J[q][u] = fma(t[q][u], t[q][u], J[q][u]);
+            } else {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) M::grad_acc(ctx[q], rec[u], t[u], g[q]);
+                for (int q = 0; q < Q; ++q) {
+                    double t[U];
+                    M::template resid_batch<U>(ctx[q], seq[q], rec, t);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) J[q][u] = fma(t[u], t[u], J[q][u]);
+                    if constexpr (GRAD) {
+#pragma unroll
+                        for (int u = 0; u < U; ++u) M::grad_acc(ctx[q], rec[u], t[u], g[q]);
+                    }
                 }
             }
         }

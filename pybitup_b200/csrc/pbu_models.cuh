@@ -60,6 +60,22 @@ struct LinearModel {
 #pragma unroll
             for (int u = 0; u < U; ++u) t[u] = fma(-rec[u][j], c.th[j], t[u]);
     }
+    // The same for the Q chains a thread evaluates together, stage-major over ALL Q x U dependency chains: consecutive
+    // DFMAs share the record operand (register reuse slot) and each depends on the one Q*U back, not on its neighbour.
+    static constexpr bool HAS_MULTI = true;
+    template <int Q, int U>
+    __device__ __forceinline__ static void resid_multi(const Ctx (&c)[Q], const double (&rec)[U][NC], double (&t)[Q][U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < Q; ++q) t[q][u] = rec[u][P];
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int q = 0; q < Q; ++q) t[q][u] = fma(-rec[u][j], c[q].th[j], t[q][u]);
+    }
     __device__ __forceinline__ static double value(const Ctx &c, Seq &, const double *raw) {
         double f = raw[0] * c.th[0];
 #pragma unroll
@@ -109,6 +125,27 @@ struct PolyModel {
 #pragma unroll
         for (int u = 0; u < U; ++u) t[u] = fma(-f[u], rec[u][1], rec[u][2]);
     }
+    // The same for the Q chains a thread evaluates together, stage-major over ALL Q x U Horner chains: consecutive DFMAs
+    // share the operand x (register reuse slot) and each depends on the one Q*U back, not on its neighbour.
+    static constexpr bool HAS_MULTI = true;
+    template <int Q, int U>
+    __device__ __forceinline__ static void resid_multi(const Ctx (&c)[Q], const double (&rec)[U][NC], double (&t)[Q][U]) {
+        double f[Q][U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < Q; ++q) f[q][u] = c[q].th[P - 1];
+#pragma unroll
+        for (int j = P - 2; j >= 0; --j)
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int q = 0; q < Q; ++q) f[q][u] = fma(f[q][u], rec[u][0], c[q].th[j]);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < Q; ++q) t[q][u] = fma(-f[q][u], rec[u][1], rec[u][2]);
+    }
     __device__ __forceinline__ static double value(const Ctx &c, Seq &, const double *raw) {
         const double x = raw[0];
         double f = c.th[P - 1];
@@ -133,6 +170,7 @@ struct PolyModel {
 // The rate at the start of a step is the rate at the end of the previous one, so each step costs two
 // exp and four pow.
 struct ArrheniusModel {
+    static constexpr bool HAS_MULTI = false;
     static constexpr int NPARAM = 4;
     static constexpr int NC = 4;
     static constexpr int NCR = 2;
@@ -219,6 +257,7 @@ struct ArrheniusModel {
 // (pybitup/test/test_pce/heat_conduction.py:27-41); theta = (a,b,k,T_amb,phi,h), consts = {L}.
 //   likelihood record [x | w | w*y | pad];  raw record [x | pad]
 struct HeatModel {
+    static constexpr bool HAS_MULTI = false;
     static constexpr int NPARAM = 6;
     static constexpr int NC = 4;
     static constexpr int NCR = 2;
@@ -263,6 +302,7 @@ struct HeatModel {
 // as -J/2 with two pseudo-residuals t_0 = sqrt(30) (X0^3 - X1), t_1 = sqrt(2) (X1 - 0.3)^2.
 //   likelihood record [selector | 1 | 0 | pad];  raw record [selector | pad];  value() returns the residual itself
 struct SoizeModel {
+    static constexpr bool HAS_MULTI = false;
     static constexpr int NPARAM = 2;
     static constexpr int NC = 4;
     static constexpr int NCR = 2;

@@ -131,6 +131,45 @@ def test_many_chains_vs_oracle(builder, lanes, algo_name):
     eng.close()
 
 
+@pytest.mark.parametrize("algo_name", ["AMH", "DRAM"])
+@pytest.mark.parametrize("builder,lanes", [("linear_problem", 1), ("cubic_problem", 2), ("cubic_problem", -4), ("heat_problem", 8),
+                                           ("arrhenius_problem", 1)])
+def test_welford_adaptation_vs_oracle(builder, lanes, algo_name):
+    """am_welford=1 (the production update north_star names): 48 chains with injected streams against the oracle's
+    Welford restatement -- identical accept codes, states and final (V_i, X_av, R) -- in every kernel layout."""
+    from pybitup_b200 import synthetic
+    kwargs = {"linear_problem": {}, "cubic_problem": {"n_points": 257}, "heat_problem": {},
+              "arrhenius_problem": {"n_steps": 40, "dT": 15.0}}[builder]
+    p = getattr(synthetic, builder)(**kwargs)
+    prob = H.oracle_problem(p)
+    n_chains, T, d = 48, 60, prob.d
+    rng = np.random.default_rng(77)
+    x0 = np.minimum(np.maximum(synthetic.chain_starts(p["x0"], n_chains, jitter=1e-3, seed=9), p["lb"]), p["ub"])
+    normals = rng.standard_normal((n_chains, 2 * T * d))
+    uniforms = rng.random((n_chains, 2 * T))
+    algo = {"name": algo_name, "AMH": {"updating_it": 7, "eps_v": 1e-10}, "DRAM": {"updating_it": 7, "eps_v": 1e-10, "gamma": 0.3}}
+    eng = _engine(p, algo, n_chains, lanes_per_chain=abs(lanes), cooperative=(1 if lanes < 0 else -1), am_welford=True)
+    eng.init_chains(x0, p["prop_cov"])
+    eng.set_streams(normals, uniforms)
+    res = eng.run(T, thin=1, trace=True)
+    eng.synchronize()
+    samples = res.samples.cpu().numpy()
+    acc_dev = res.trace_acc.cpu().numpy()
+    prop = eng.proposal()
+    import tests.helpers as helpers
+    for c in range(0, n_chains, 5):
+        with orc.kernel_order():
+            out = orc.run_mh(prob, x0[c], p["prop_cov"], T, orc.Streams(normals[c], uniforms[c]), am_welford=True,
+                             **helpers.mh_kwargs(algo))
+        assert np.array_equal(acc_dev[:, c], out["acc"]), "chain %d: accept codes differ" % c
+        assert H.rel_err(samples[:, :, c], out["chain"][1:]) < 1e-9
+        assert H.rel_err(prop["X_av"][c], out["X_av"]) < 1e-10
+        assert H.rel_err(prop["V"][c], out["V_i"]) < 1e-8
+        assert H.rel_err(prop["R"][c], out["R"]) < 1e-7
+    assert not np.any(eng.counters()["status"] & 3)          # bit 2 (a NaN delayed-rejection ratio, Q6) is the reference's behaviour
+    eng.close()
+
+
 @pytest.mark.parametrize("builder", ["linear_problem", "cubic_problem", "heat_problem", "arrhenius_problem",
                                      "regression_problem"])
 def test_logposterior_and_model_eval(builder):

@@ -184,3 +184,25 @@ def test_hmc_matches_reference(case, quantised):
         s0 = int(c["starting_it"])
         assert H.rel_err(out["chain"][:s0], g["chain"][:s0]) < 1e-9
         assert np.max(np.abs(out["chain"] - g["chain"])) < 5e-2
+
+
+def test_welford_restatement_is_the_sample_covariance():
+    """The Welford mode of the oracle (the engine's opt-in production update, north_star) against an independent numpy
+    formula: after T iterations V_i = S_d (cov(x_0 .. x_T) + eps_v I) and X_av = mean(x_0 .. x_T)."""
+    from pybitup_b200 import synthetic
+    p = synthetic.cubic_problem(n_points=64)
+    prob = H.oracle_problem(p)
+    T, d = 120, prob.d
+    rng = np.random.default_rng(11)
+    st = orc.Streams(rng.standard_normal(2 * T * d), rng.random(2 * T))
+    out = orc.run_mh(prob, p["x0"], p["prop_cov"], T, st, adaptive=True, updating_it=10, eps_v=1e-10, am_welford=True)
+    assert 0 < out["n_rejected"] < T
+    S_d = 2.38 ** 2 / d
+    want = S_d * (np.cov(out["chain"], rowvar=False) + 1e-10 * np.eye(d))
+    assert H.rel_err(out["V_i"], want) < 1e-9
+    assert H.rel_err(out["X_av"], out["chain"].mean(axis=0)) < 1e-13
+    # and it is the estimator the literal recursion targets: same chain law, the two factors agree once the first-step
+    # quirks (Q3 / Q4) have been averaged out
+    st = orc.Streams(st.normals, st.uniforms)
+    lit = orc.run_mh(prob, p["x0"], p["prop_cov"], T, st, adaptive=True, updating_it=10, eps_v=1e-10)
+    assert np.array_equal(lit["acc"][:9], out["acc"][:9])          # identical until the first refresh
