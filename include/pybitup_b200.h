@@ -100,6 +100,17 @@ typedef struct {
     const int32_t *model_unc_idx;   /* host [n_models][d]: position inside that model's theta, -1 = not a
                                        parameter of that model (Model.run_model's name search finds nothing)    */
     const double *model_consts;     /* host [n_models][8]                                                       */
+    /* Element-wise change of variables between the sampling space Y and the model space X, i.e. the user's
+     * Model.parametrization_backward / _det_jac / _inv_jac hooks (bayesian_inference.py:314-336) lowered to the device:
+     * par_kind NULL = identity.  kind 0: X_i = a_i + b_i Y_i;  kind 1: X_i = a_i + b_i exp(c_i Y_i).  The posterior in Y is
+     * prior(X) - log(det_jac(X)) + loglike(X) (:44-64) with -log(det_jac(X)) = par_ldj_c0 + sum_i par_ldj_s[i] Y_i; its
+     * gradient is diag(dX/dY) grad_X loglike + par_ldj_s (:84-89, :604-636).  The prior box [lb, ub] lives in X. */
+    const int32_t *par_kind;        /* host [d] or NULL                                                         */
+    const double *par_a;            /* host [d]                                                                 */
+    const double *par_b;            /* host [d]                                                                 */
+    const double *par_c;            /* host [d]                                                                 */
+    const double *par_ldj_s;        /* host [d]                                                                 */
+    double par_ldj_c0;
 } pbu_problem;
 
 /* Algorithm block: inference_problem.py:37-107 (JSON keys in SURVEY.md 9.2). */
@@ -129,6 +140,9 @@ typedef struct {
     int32_t hmc_num_steps;    /* HMC.num_steps (L)             (mha.py:819)                       */
     int32_t cooperative;      /* 0 auto; 1: cooperative teams (lanes_per_chain lanes own as many chains, each
                                  lane does the scalar part of one); -1: replicated layout only          */
+    int32_t track_map;        /* 1: per-chain MAP estimate (opt_arg estimate_max_distr, mha.py:77, :138-139,
+                                 :226-237; Ito-SDE :1011-1019 with its extra evaluation per iteration)   */
+    int32_t reserved0;
 } pbu_sampler_cfg;
 
 /* Per-run outputs that live on the device; any pointer may be NULL (= not recorded).
@@ -186,6 +200,9 @@ int pbu_engine_synchronize(pbu_engine *e);
 int pbu_engine_get_state(pbu_engine *e, double *x_host /*[C][d]*/, double *lp_host /*[C]*/);
 int pbu_engine_get_counters(pbu_engine *e, int64_t *n_rejected /*[C]*/, double *mean_r /*[C]*/,
                             int64_t *n_eval /*[C]*/, int32_t *status /*[C]*/);
+/* MAP estimate of every chain (arg_MAP, MAP_val in log: mha.py:138-139, :232-234; written out at :352-355);
+ * needs cfg.track_map = 1 */
+int pbu_engine_get_map(pbu_engine *e, double *arg_map_host /*[C][d]*/, double *map_lp_host /*[C]*/);
 /* the same in one pass, for callers with pinned staging buffers: every array is copied straight into the caller's buffer
  * and the stream is synchronised once; x comes back chain-minor [d][C] (its device layout).  Any pointer may be NULL.
  * (current_val, distr_fun_current_val, n_rejected, mean_r: mha.py:99, :102, :146, :154) */

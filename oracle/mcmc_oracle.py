@@ -49,6 +49,28 @@ class Problem:
     # further models of the same likelihood (Likelihood.models is a dict, summed over at bayesian_inference.py:500-524):
     # Problems that share lb / ub / gamma with this one; each has its own data, nominal parameters and name map
     extra: list = field(default_factory=list)
+    # element-wise re-parametrisation of the uncertain parameters (the Model.parametrization_* hooks a user of the
+    # reference writes, bayesian_inference.py:314-336): {"kind": [...], "a", "b", "c", "det_jac": bool} with
+    # kind 0: X = a + b Y, kind 1: X = a + b exp(c Y); det_jac False = the hook left at the base class's constant 1
+    param: dict = None
+
+    def backward(self, Y):
+        """Model.parametrization_backward (:320-324)."""
+        Y = np.asarray(Y, dtype=np.float64)
+        if self.param is None:
+            return Y
+        k, a, b, c = (np.asarray(self.param[n], dtype=np.float64) for n in ("kind", "a", "b", "c"))
+        return np.where(k == 0, a + b * Y, a + b * np.exp(c * Y))
+
+    def dXdY(self, X):
+        k, a, b, c = (np.asarray(self.param[n], dtype=np.float64) for n in ("kind", "a", "b", "c"))
+        return np.where(k == 0, b, c * (np.asarray(X, dtype=np.float64) - a))
+
+    def det_jac(self, X):
+        """Model.parametrization_det_jac (:326-330)."""
+        if self.param is None or not self.param.get("det_jac", True):
+            return 1
+        return float(np.prod(1.0 / self.dXdY(X)))
 
     @property
     def members(self):
@@ -124,27 +146,44 @@ def arg_gauss_likelihood(prob, X):
     return J
 
 
-def log_post(prob, X):
-    """BayesianPosterior.compute_log_value with the identity parametrisation (:44-64)."""
+def log_post(prob, Y):
+    """BayesianPosterior.compute_log_value (:44-64): X = backward(Y); prior(X) - log(det_jac(X)) + loglike(X)."""
+    X = prob.backward(Y)
     lp = log_prior(prob, X)
     if lp == -np.inf:
         return -np.inf
     log_like = -(1 / 2) * arg_gauss_likelihood(prob, X)
-    return lp - np.log(1) + log_like
+    return lp - np.log(prob.det_jac(X)) + log_like
 
 
-def grad_log_post(prob, X):
-    """Analytical gradient: compute_grad_log_value (:573-623) with inv_jac = I, det_jac = 1.
+def grad_log_post(prob, Y):
+    """Analytical gradient, BayesianPosterior.compute_grad_log_like (:80-89): compute_grad_log_value (:573-623) with the
+    model's inv_jac = diag(dX/dY), minus compute_grad_log_det_jac (:626-636).
 
     Only run 0 enters (:606-608) and the prior does not (:80-82); the models of the likelihood add up (:596).
     """
+    X = prob.backward(Y)
     grad = np.zeros(prob.d)
+    inv_jac = np.eye(prob.d) if prob.param is None else np.diag(prob.dXdY(X))
     for m in prob.members:
         f = m.model_eval_one(X)
         mg = m.model_grad(X)
         ss_x = (m.y[0] - f) / (m.std_y ** 2 * prob.gamma ** 2)
         for i in range(prob.d):
-            grad[i] = grad[i] + np.matmul(ss_x, mg[i])
+            my_mat = np.matmul(ss_x, mg[i])
+            if prob.param is None:
+                grad[i] = grad[i] + my_mat
+            else:
+                for k in range(prob.d):
+                    grad[k] = grad[k] + my_mat * inv_jac[i, k]                     # :621
+    if prob.param is not None:
+        det = prob.det_jac(X)
+        if prob.param.get("det_jac", True):
+            k_, a = np.asarray(prob.param["kind"]), np.asarray(prob.param["a"], dtype=np.float64)
+            grad_det_jac = np.where(k_ == 0, 0.0, -det / (X - a))
+        else:
+            grad_det_jac = np.zeros(prob.d)
+        grad = grad - np.matmul(grad_det_jac, inv_jac) / det                        # :634, :89
     return grad
 
 
@@ -350,6 +389,7 @@ def run_mh(prob, x0, V, n_it, streams, adaptive=False, delayed=False,
     lps[0] = lp_cur
     n_rejected = 0
     mean_r = 0.0
+    arg_MAP, MAP_val = np.array(cur), lp_cur             # estimate_max state (:138-139)
     with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
         for it in range(1, n_it + 1):
             z = np.array([streams.gauss(0, 1) for _ in range(d)])
@@ -363,6 +403,8 @@ def run_mh(prob, x0, V, n_it, streams, adaptive=False, delayed=False,
             u = streams.random()
             if u < alpha:
                 cur = np.array(new)
+                if lp_new > MAP_val:                         # estimate_max (:226-237): first-stage acceptances only (Q10)
+                    arg_MAP, MAP_val = np.array(new), lp_new
                 lp_cur = lp_new
                 acc[it - 1] = 1
             elif delayed:
@@ -434,7 +476,7 @@ def run_mh(prob, x0, V, n_it, streams, adaptive=False, delayed=False,
         V_i = S_d / n_it * V_i + S_d * eps_v * np.eye(d)       # what pbu_engine_get_proposal reports for this mode
     return dict(chain=chain, lp=lps, acc=acc, eval_x=np.array(evals_x), eval_lp=np.array(evals_lp),
                 R=R, V_i=V_i, X_av=(cur if X_av is None else X_av), n_rejected=n_rejected,
-                mean_r=mean_r, n_eval=len(evals_lp))
+                mean_r=mean_r, n_eval=len(evals_lp), arg_MAP=arg_MAP, MAP_val=MAP_val)
 
 
 # --------------------------------------------------------------------------- Ito-SDE
@@ -444,8 +486,10 @@ def _csv_quantise(v):
 
 
 def run_isde(prob, x0, n_it, streams, h, f0, gradient="Analytical", C0=None,
-             starting_it=None, update_it=1, end_it=None, csv_quantise=False):
+             starting_it=None, update_it=1, end_it=None, csv_quantise=False, track_map=False):
     """ito_SDE.run_algorithm (:932-1040) for ONE chain.
+
+    track_map: estimate_max_distr -- one MORE posterior evaluation per iteration, at the new state (:1011-1019).
 
     C0: initial preconditioner (identity when None, the 'Identity' branch :661-664).
     Adaptation window as GradientBasedMCMC.adapt_covariance (:736-777).  The reference
@@ -479,6 +523,7 @@ def run_isde(prob, x0, n_it, streams, h, f0, gradient="Analytical", C0=None,
     chain = np.zeros((n_it + 1, d))
     Ps = np.zeros((n_it + 1, d))
     chain[0] = xi
+    arg_MAP, MAP_val = np.array(xi), (log_post(prob, xi) if track_map else None)     # :138-139 (MetropolisHastings.__init__)
     rows = [_csv_quantise(xi) if csv_quantise else np.array(xi)]
     with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
         for it in range(1, n_it + 1):
@@ -506,12 +551,16 @@ def run_isde(prob, x0, n_it, streams, h, f0, gradient="Analytical", C0=None,
             grad_phi = -grad(xi_n)                                                   # :994
             P_np = hfm / hfp * P + h / hfp * (-grad_phi) + np.sqrt(f0) / hfp * np.matmul(inv_L_c, WP)
             xi_np = xi_n + h / 2 * np.matmul(C, P_np)                                # :1001
+            if track_map:
+                lp_np = log_post(prob, xi_np)                                        # :1016
+                if lp_np > MAP_val:
+                    arg_MAP, MAP_val = np.array(xi_np), lp_np
             P = P_np
             xi = xi_np
             chain[it] = xi
             Ps[it] = P
             rows.append(_csv_quantise(xi) if csv_quantise else np.array(xi))
-    return dict(chain=chain, P=Ps, C=C, X_av=X_av, V_i=V_i)
+    return dict(chain=chain, P=Ps, C=C, X_av=X_av, V_i=V_i, arg_MAP=arg_MAP, MAP_val=MAP_val)
 
 
 # --------------------------------------------------------------------------- Hamiltonian Monte Carlo
@@ -552,6 +601,7 @@ def run_hmc(prob, x0, n_it, streams, step_size, num_steps, gradient="Analytical"
     chain[0], lps[0] = cur, lp_cur
     rows = [np.array(cur)]
     n_rejected, mean_r = 0, 0.0
+    arg_MAP, MAP_val = np.array(cur), lp_cur
     with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
         for it in range(1, n_it + 1):
             if starting_it <= it <= end_it + 1:
@@ -592,6 +642,8 @@ def run_hmc(prob, x0, n_it, streams, step_size, num_steps, gradient="Analytical"
             u = streams.random()
             if u < alpha:
                 cur = np.array(new)
+                if lp_new > MAP_val:                         # accept_reject -> estimate_max (:218)
+                    arg_MAP, MAP_val = np.array(new), lp_new
                 lp_cur = lp_new
                 g_cur = g_new
                 acc[it - 1] = 1
@@ -600,7 +652,7 @@ def run_hmc(prob, x0, n_it, streams, step_size, num_steps, gradient="Analytical"
             mean_r += alpha
             chain[it], lps[it] = cur, lp_cur
             rows.append(np.array(cur))
-    return dict(chain=chain, lp=lps, acc=acc, n_rejected=n_rejected, mean_r=mean_r, C=C)
+    return dict(chain=chain, lp=lps, acc=acc, n_rejected=n_rejected, mean_r=mean_r, C=C, arg_MAP=arg_MAP, MAP_val=MAP_val)
 
 
 # --------------------------------------------------------------------------- propagation

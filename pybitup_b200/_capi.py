@@ -38,7 +38,8 @@ class pbu_problem(C.Structure):
                 ("lb", _dp), ("ub", _dp), ("gamma", C.c_double), ("consts", C.c_double * 8),
                 ("log_const", C.c_double), ("has_log_const", C.c_int32), ("n_models", C.c_int32),
                 ("model_first", _ip), ("model_count", _ip), ("model_theta_nom", _dp), ("model_unc_idx", _ip),
-                ("model_consts", _dp)]
+                ("model_consts", _dp), ("par_kind", _ip), ("par_a", _dp), ("par_b", _dp), ("par_c", _dp), ("par_ldj_s", _dp),
+                ("par_ldj_c0", C.c_double)]
 
 
 class pbu_sampler_cfg(C.Structure):
@@ -48,7 +49,7 @@ class pbu_sampler_cfg(C.Structure):
                 ("am_welford", C.c_int32), ("nan_rejects", C.c_int32), ("lanes_per_chain", C.c_int32),
                 ("block_threads", C.c_int32), ("chains_per_thread", C.c_int32), ("tile_points", C.c_int32),
                 ("seed", C.c_uint64), ("chain_offset", C.c_uint64), ("hmc_step_size", C.c_double),
-                ("hmc_num_steps", C.c_int32), ("cooperative", C.c_int32)]
+                ("hmc_num_steps", C.c_int32), ("cooperative", C.c_int32), ("track_map", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class pbu_run_outputs(C.Structure):
@@ -106,6 +107,7 @@ def _load():
         "pbu_engine_pooled_mean_dev": (C.c_int, [E, C.c_void_p, C.c_void_p, C.c_void_p]),
         "pbu_engine_pooled_finalize_dev": (C.c_int, [E, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p]),
         "pbu_engine_set_proposal": (C.c_int, [E, _dp]),
+        "pbu_engine_get_map": (C.c_int, [E, _dp, _dp]),
         "pbu_propagation_create": (C.c_int, [E, C.c_int64, C.POINTER(E)]),
         "pbu_propagation_destroy": (C.c_int, [E]),
         "pbu_propagation_eval_host": (C.c_int, [E, _dp]),

@@ -186,6 +186,122 @@ class Likelihood:
         return out
 
 
+_NICE_RATES = (1.0, -1.0, float(np.log(10.0)), -float(np.log(10.0)), float(np.log(2.0)), -float(np.log(2.0)), 0.5, -0.5, 2.0, -2.0)
+
+
+def _snap(v, candidates, rtol=1e-9):
+    for c in candidates:
+        if abs(v - c) <= rtol * max(1.0, abs(c)):
+            return float(c)
+    return float(v)
+
+
+def lower_parametrization(model, Y0, need_gradient=False):
+    """The user's ``parametrization_*`` hooks (bayesian_inference.py:314-336) as a REGISTERED device change of variables,
+    or ``None`` for the identity.  The hooks are arbitrary Python; the device knows element-wise maps of two kinds,
+    X_i = a_i + b_i Y_i (scaling / shift) and X_i = a_i + b_i exp(c_i Y_i) (log, log10, shifted-log sampling), with
+    -log(det_jac(X)) affine in Y (true for these maps, and for a hook left at the base class's constant 1).  The hooks
+    are PROBED around the starting point: each component is identified from three equally spaced evaluations, then the
+    identified map -- and, for analytical-gradient samplers, ``parametrization_inv_jac`` / ``grad_det_jac`` -- must
+    reproduce the hooks at random points to 1e-11, else ``UnsupportedProblem`` (there is no CPU fallback)."""
+    Y0 = np.asarray(Y0, dtype=np.float64).copy()
+    d = Y0.size
+
+    def back(Y):
+        X = np.asarray(model.parametrization_backward(np.array(Y, dtype=np.float64)), dtype=np.float64)
+        if X.shape != (d,):
+            raise capi.UnsupportedProblem(capi.PBU_ERR_UNSUPPORTED, "parametrization_backward must map d values to d values")
+        return X
+
+    def neg_log_det(Y):
+        with np.errstate(all="ignore"):
+            return -float(np.log(model.parametrization_det_jac(back(Y))))
+
+    X0 = back(Y0)
+    rng = np.random.default_rng(12345)
+    h = 0.05 * np.maximum(np.abs(Y0), 1.0)
+    probes = [Y0 + h * rng.uniform(-2.0, 2.0, d) for _ in range(6)]
+    if (np.array_equal(X0, Y0) and all(np.array_equal(back(P), P) for P in probes)
+            and all(neg_log_det(P) == 0.0 for P in [Y0] + probes)):
+        return None
+    refuse = lambda why: capi.UnsupportedProblem(      # noqa: E731
+        capi.PBU_ERR_UNSUPPORTED, "the model's re-parametrisation cannot be lowered to the device: " + why)
+    kind, a, b, c = np.zeros(d, dtype=np.int32), np.zeros(d), np.ones(d), np.zeros(d)
+    for i in range(d):
+        e = np.zeros(d)
+        e[i] = h[i]
+        X1, X2 = back(Y0 + e), back(Y0 + 2 * e)
+        others = np.arange(d) != i
+        if not (np.array_equal(X1[others], X0[others]) and np.array_equal(X2[others], X0[others])):
+            raise refuse("it is not element-wise (component %d of Y moves other components of X)" % i)
+        d1, d2 = X1[i] - X0[i], X2[i] - X1[i]
+        if d1 == 0.0:
+            raise refuse("component %d of X does not depend on Y" % i)
+        if abs(d2 - d1) <= 1e-10 * abs(d1):
+            b[i] = _snap(0.5 * (d1 + d2) / h[i], (1.0, -1.0))
+            a[i] = X0[i] - b[i] * Y0[i]
+            if abs(a[i]) <= 1e-12 * max(1.0, abs(X0[i])):
+                a[i] = 0.0
+        else:
+            rho = d2 / d1
+            if not rho > 0.0:
+                raise refuse("component %d is neither affine nor exponential in Y" % i)
+            kind[i] = 1
+            c[i] = _snap(np.log(rho) / h[i], _NICE_RATES)
+            b[i] = d1 / (np.exp(c[i] * Y0[i]) * np.expm1(c[i] * h[i]))
+            b[i] = _snap(b[i], (1.0, -1.0))
+            a[i] = X0[i] - b[i] * np.exp(c[i] * Y0[i])
+            if abs(a[i]) <= 1e-11 * max(1.0, abs(X0[i])):
+                a[i] = 0.0
+            else:
+                a[i] = _snap(a[i], (round(a[i]),), rtol=1e-10)
+
+    def dev_back(Y):
+        return np.where(kind == 1, a + b * np.exp(c * Y), a + b * Y)
+
+    for P in [Y0] + probes:
+        Xu, Xd = back(P), dev_back(P)
+        if np.max(np.abs(Xu - Xd) / np.maximum(np.abs(Xu), 1e-300)) > 1e-11:
+            raise refuse("it is not of a registered kind (X = a + b Y or X = a + b exp(c Y) per component)")
+    # -log(det_jac) = c0 + s . Y
+    L0 = neg_log_det(Y0)
+    if not np.isfinite(L0):
+        raise refuse("parametrization_det_jac is not positive at the starting point")
+    s_ = np.zeros(d)
+    for i in range(d):
+        e = np.zeros(d)
+        e[i] = h[i]
+        s_[i] = _snap((neg_log_det(Y0 + e) - L0) / h[i], (0.0, c[i]), rtol=1e-8)
+    c0 = L0 - float(s_ @ Y0)
+    true_c0 = float(np.sum(np.log(np.abs(np.where(kind == 1, b * c, b)))))
+    for cand in (0.0, true_c0):
+        if abs(c0 - cand) <= 1e-9 * max(1.0, abs(cand)):
+            c0 = cand
+    for P in probes:
+        Lu, Ld = neg_log_det(P), c0 + float(s_ @ P)
+        if abs(Lu - Ld) > 1e-10 * max(1.0, abs(Lu)):
+            raise refuse("log(parametrization_det_jac) is not affine in the sampling variables")
+    # analytical gradient: inv_jac must be diag(dX/dY) and grad_det_jac consistent with det_jac (:604-636)
+    grad_ok, why = True, ""
+    try:
+        for P in probes[:3]:
+            X = back(P)
+            inv = np.asarray(model.parametrization_inv_jac(X), dtype=np.float64)
+            dxdy = np.where(kind == 1, c * (X - a), b)
+            if inv.shape != (d, d) or np.max(np.abs(inv - np.diag(dxdy))) > 1e-10 * np.max(np.abs(dxdy)):
+                grad_ok, why = False, "parametrization_inv_jac is not diag(dX/dY)"
+                break
+            gld = np.matmul(np.asarray(model.grad_det_jac(X), dtype=np.float64), inv) / model.parametrization_det_jac(X)
+            if np.max(np.abs(-gld - s_)) > 1e-9 * max(1.0, np.max(np.abs(s_))):
+                grad_ok, why = False, "grad_det_jac is not the gradient of parametrization_det_jac"
+                break
+    except Exception as exc:                       # the base class has no grad_det_jac and its inv_jac returns X (:332-336)
+        grad_ok, why = False, "parametrization_inv_jac / grad_det_jac: %s" % exc
+    if need_gradient and not grad_ok:
+        raise refuse(why)
+    return dict(kind=kind, a=a, b=b, c=c, ldj_c0=float(c0), ldj_s=s_, grad_ok=grad_ok, grad_why=why)
+
+
 class BayesianPosterior:
     """prior x likelihood in the sampling space (bayesian_inference.py:15-139)."""
 
@@ -203,14 +319,13 @@ class BayesianPosterior:
 
     def lower(self):
         """Flat problem descriptor for the CUDA engine; refuses what it cannot represent."""
-        m = self.model
-        probe = np.asarray(self.param_init, dtype=np.float64)
-        if (np.any(np.asarray(m.parametrization_backward(probe)) != probe) or m.parametrization_det_jac(probe) != 1):
-            raise capi.UnsupportedProblem(capi.PBU_ERR_UNSUPPORTED, "re-parametrised models are not lowered to the device yet")
         if not hasattr(self.prior, "box"):
             raise capi.UnsupportedProblem(capi.PBU_ERR_UNSUPPORTED, "only a Mixture of Uniform priors can be lowered (SURVEY Q12)")
         lb, ub = self.prior.box()
-        return self.likelihood.lower(lb, ub)
+        spec = self.likelihood.lower(lb, ub)
+        # the change of variables of the posterior is the one of `self.model` (:50, :61; solve_problem.py:336-339)
+        spec.param = lower_parametrization(self.model, self.param_init)
+        return spec
 
     # single evaluations through the device (diagnostics; the samplers never call these per iteration)
     def _eval_engine(self):

@@ -40,8 +40,14 @@ struct ProblemDev {
     // Likelihood.models (bayesian_inference.py:500-524): blk[0] repeats the fields above for a single model.  The
     // replicated-layout kernels and the evaluation kernels walk the blocks; the cooperative kernel is single-model.
     int32_t n_blocks;
-    int32_t pad_blocks;
+    int32_t par_any;         // 0: identity parametrisation (Model.parametrization_* of the base class, bayesian_inference.py:314-336)
     ModelBlockDev blk[PBU_MAX_MODELS];
+    // Element-wise change of variables between the sampling space Y and the model space X (parametrization_backward,
+    // :320-324; the posterior in Y, :44-64): kind 0  X_i = a_i + b_i Y_i;  kind 1  X_i = a_i + b_i exp(c_i Y_i).
+    // -log(det_jac(X)) is affine in Y for these (and for a user hook that returns the constant 1): ldj_c0 + sum_i ldj_s_i Y_i.
+    int32_t par_kind[PBU_MAX_DIM];
+    double par_a[PBU_MAX_DIM], par_b[PBU_MAX_DIM], par_c[PBU_MAX_DIM];
+    double par_ldj_c0, par_ldj_s[PBU_MAX_DIM];
 };
 
 // Chain state, structure-of-arrays with stride = n_chains (coalesced for one thread per chain).
@@ -62,7 +68,21 @@ struct ChainState {
     int64_t *wcount;  // [C]
     // ISDE
     double *P;        // [d][C]      momentum P_nm                    (mha.py:920)
+    // MAP tracking (estimate_max_distr, mha.py:138-139, :226-237, :1011-1019); nullptr = off
+    double *map_x;    // [d][C]      arg_MAP
+    double *map_lp;   // [C]         MAP_val (log)
 };
+
+// MetropolisHastings.estimate_max (mha.py:226-237): called on a FIRST-stage acceptance only (the delayed-rejection
+// acceptance at :562-565 does not call it); the state stays in global memory, touched on improvement.
+template <int D>
+__device__ __forceinline__ void track_map(const ChainState &st, int64_t c, const double (&x_new)[D], double lp_new) {
+    if (lp_new > st.map_lp[c]) {
+        st.map_lp[c] = lp_new;
+#pragma unroll
+        for (int i = 0; i < D; ++i) st.map_x[(int64_t)i * st.n_chains + c] = x_new[i];
+    }
+}
 
 struct StreamsDev {
     const double *normals;   // [C][n_normals]  (row per chain)
@@ -99,6 +119,36 @@ struct MhParams {
     int32_t groups_per_block; // mixed kernels: chain groups per block
     double R0[PBU_MAX_DIM * (PBU_MAX_DIM + 1) / 2];   // packed upper Cholesky factor shared by all chains (non-adaptive samplers)
 };
+
+// X = parametrization_backward(Y) and -log(det_jac(X)) (bayesian_inference.py:50, :61).  `a + b * v` keeps numpy's two
+// roundings.  Returns false when nothing is re-parametrised (X = Y, ldj = 0).
+template <int D>
+__device__ __forceinline__ void par_backward(const ProblemDev &prob, const double (&y)[D], double (&X)[D], double &ldj) {
+    ldj = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) X[i] = y[i];
+    if (prob.par_any) {
+        ldj = prob.par_ldj_c0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const double v = (prob.par_kind[i] == 1) ? exp(__dmul_rn(prob.par_c[i], y[i])) : y[i];
+            X[i] = __dadd_rn(prob.par_a[i], __dmul_rn(prob.par_b[i], v));
+            ldj = fma(prob.par_ldj_s[i], y[i], ldj);
+        }
+    }
+}
+// Gradient of the log-posterior with respect to Y from the gradient of the log-likelihood with respect to X
+// (Likelihood.compute_grad_log_value with inv_jac = diag(dX/dY), :604-621, minus compute_grad_log_det_jac, :626-636).
+template <int D>
+__device__ __forceinline__ void par_grad(const ProblemDev &prob, const double (&X)[D], double (&g)[D]) {
+    if (prob.par_any) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            const double dxdy = (prob.par_kind[i] == 1) ? __dmul_rn(prob.par_c[i], __dadd_rn(X[i], -prob.par_a[i])) : prob.par_b[i];
+            g[i] = __dadd_rn(__dmul_rn(g[i], dxdy), prob.par_ldj_s[i]);
+        }
+    }
+}
 
 // status bits
 enum { ST_NOT_PD = 1, ST_STREAM_EXHAUSTED = 2, ST_NAN_RATIO = 4 };

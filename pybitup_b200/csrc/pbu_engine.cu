@@ -455,6 +455,34 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
     pd.log_prior_const = pr->has_log_const ? pr->log_const : lpc;
     for (int i = 0; i < pr->n_param; ++i) pd.theta_nom[i] = blocks[0].theta_nom[i];
     for (int i = 0; i < 8; ++i) pd.consts[i] = blocks[0].consts[i];
+    pd.par_any = 0;
+    for (int i = 0; i < PBU_MAX_DIM; ++i) {
+        pd.par_kind[i] = 0;
+        pd.par_a[i] = 0.0;
+        pd.par_b[i] = 1.0;
+        pd.par_c[i] = 0.0;
+        pd.par_ldj_s[i] = 0.0;
+    }
+    pd.par_ldj_c0 = 0.0;
+    if (pr->par_kind) {
+        if (!pr->par_a || !pr->par_b || !pr->par_c || !pr->par_ldj_s) {
+            delete e;
+            return fail(PBU_ERR_INVALID, "par_kind without par_a / par_b / par_c / par_ldj_s");
+        }
+        pd.par_any = 1;
+        pd.par_ldj_c0 = pr->par_ldj_c0;
+        for (int i = 0; i < pr->n_unc; ++i) {
+            if (pr->par_kind[i] != 0 && pr->par_kind[i] != 1) {
+                delete e;
+                return fail(PBU_ERR_UNSUPPORTED, "parametrisation kind %d of parameter %d is not registered (0 affine, 1 exponential)", pr->par_kind[i], i);
+            }
+            pd.par_kind[i] = pr->par_kind[i];
+            pd.par_a[i] = pr->par_a[i];
+            pd.par_b[i] = pr->par_b[i];
+            pd.par_c[i] = pr->par_c[i];
+            pd.par_ldj_s[i] = pr->par_ldj_s[i];
+        }
+    }
     pd.n_blocks = (int)blocks.size();
     for (size_t b = 0; b < blocks.size(); ++b) {
         ModelBlockDev &mb = pd.blk[b];
@@ -517,7 +545,8 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
         (rc = dev_alloc(e, &st.n_rej, (size_t)C)) || (rc = dev_alloc(e, &st.n_eval, (size_t)C)) ||
         (rc = dev_alloc(e, &st.status, (size_t)C)) || (rc = dev_alloc(e, &st.wmean, (size_t)e->d * C)) ||
         (rc = dev_alloc(e, &st.wM2, (size_t)e->nt * C)) || (rc = dev_alloc(e, &st.wcount, (size_t)C)) ||
-        (rc = dev_alloc(e, &st.P, (size_t)e->d * C)) || (rc = dev_alloc(e, &e->d_Cmat, (size_t)((cfg->algo == PBU_ALGO_ISDE || cfg->algo == PBU_ALGO_HMC) ? e->nt : 0) * C)) || (rc = dev_alloc(e, &e->streams.cur_n, (size_t)C)) ||
+        (rc = dev_alloc(e, &st.P, (size_t)e->d * C)) ||
+        (cfg->track_map && ((rc = dev_alloc(e, &st.map_x, (size_t)e->d * C)) || (rc = dev_alloc(e, &st.map_lp, (size_t)C)))) || (rc = dev_alloc(e, &e->d_Cmat, (size_t)((cfg->algo == PBU_ALGO_ISDE || cfg->algo == PBU_ALGO_HMC) ? e->nt : 0) * C)) || (rc = dev_alloc(e, &e->streams.cur_n, (size_t)C)) ||
         (rc = dev_alloc(e, &e->streams.cur_u, (size_t)C)) ||
         (rc = dev_alloc(e, &e->d_mom_partial, (size_t)(2 + 4 * e->d + e->nt) * PBU_MOMENT_SLICES)) ||
         (rc = dev_alloc(e, &e->d_mom_scratch, (size_t)(2 + 4 * e->d + e->nt) + e->d)))
@@ -672,6 +701,10 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_init_chains(pbu
         int fd = e->cfg.isde_gradient != 0;
         void *gargs[] = {(void *)&e->prob, (void *)&e->st.x, (void *)&S, (void *)&e->st.P, (void *)&e->tile_points, (void *)&fd};
         CUDA_TRY(cudaLaunchKernel(e->ev->eval_grad, dim3(grid), dim3(block), gargs, e->smem_bytes, e->stream));
+    }
+    if (e->st.map_lp) {     // arg_MAP = current_val, MAP_val = distr_fun_current_val (mha.py:138-139)
+        CUDA_TRY(cudaMemcpyAsync(e->st.map_x, e->st.x, n_state * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+        CUDA_TRY(cudaMemcpyAsync(e->st.map_lp, e->st.lp, C * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     e->iteration = 0;
@@ -860,6 +893,23 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_get_counters(pb
     if (n_eval) CUDA_TRY(cudaMemcpyAsync(n_eval, e->st.n_eval, e->C * sizeof(int64_t), cudaMemcpyDeviceToHost, e->stream));
     if (status) CUDA_TRY(cudaMemcpyAsync(status, e->st.status, e->C * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PBU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int pbu_engine_get_map(pbu_engine *e, double *arg_map_host, double *map_lp_host) {
+    if (!e) return fail(PBU_ERR_INVALID, "null engine");
+    if (!e->st.map_lp) return fail(PBU_ERR_INVALID, "the engine was created without track_map");
+    CUDA_TRY(cudaSetDevice(e->device));
+    int rc;
+    if (arg_map_host) {
+        std::vector<double> soa;
+        if ((rc = d2h(e, e->st.map_x, (size_t)e->d * e->C, soa))) return rc;
+        transpose_from_soa(soa, e->C, e->d, arg_map_host);
+    }
+    if (map_lp_host) {
+        CUDA_TRY(cudaMemcpyAsync(map_lp_host, e->st.map_lp, e->C * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    }
     return PBU_OK;
 }
 

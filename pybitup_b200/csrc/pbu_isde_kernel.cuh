@@ -146,13 +146,16 @@ __device__ __forceinline__ void adapt_preconditioner(const IsdeParams &p, int64_
 
 // Gradient of the log-likelihood (and the log-posterior value) at x for the Q chains of a thread.
 template <class M, int D, int G, int Q, bool STREAM>
-__device__ __forceinline__ void grad_log_like(const double (&x)[Q][D], const ProblemDev &prob, TileStream<M::NC> &ts, int tile_points, int sub,
+__device__ __forceinline__ void grad_log_like(const double (&yv)[Q][D], const ProblemDev &prob, TileStream<M::NC> &ts, int tile_points, int sub,
                                               unsigned group_mask, double (&grad)[Q][D], double (&lp)[Q]) {
     constexpr int U = (M::UNROLL > 2) ? 2 : M::UNROLL;
     constexpr int NP = M::NPARAM;
     typename M::Ctx ctx[Q];
     typename M::Seq seq[Q];
     double J[Q][U], g[Q][M::HAS_GRAD ? NP : 1], gd[Q][D];
+    double x[Q][D], ldj[Q];        // X = parametrization_backward(Y) (bayesian_inference.py:84), -log(det_jac(X))
+#pragma unroll
+    for (int q = 0; q < Q; ++q) par_backward<D>(prob, yv[q], x[q], ldj[q]);
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
 #pragma unroll
@@ -214,9 +217,10 @@ __device__ __forceinline__ void grad_log_like(const double (&x)[Q][D], const Pro
 #pragma unroll
         for (int u = 0; u < U; ++u) Jq += J[q][u];
         Jq = group_sum<G>(Jq, group_mask) + prob.J_const;
-        lp[q] = inside_box<D>(x[q], prob) ? (prob.log_prior_const - 0.0) + (-0.5 * Jq) : -INFINITY;
+        lp[q] = inside_box<D>(x[q], prob) ? (prob.log_prior_const + ldj[q]) + (-0.5 * Jq) : -INFINITY;
 #pragma unroll
         for (int i = 0; i < D; ++i) grad[q][i] = group_sum<G>(gd[q][i], group_mask);
+        par_grad<D>(prob, x[q], grad[q]);          // d/dY = inv_jac^T d/dX - grad log det_jac  (:86-89, :604-636)
     }
 }
 
@@ -365,7 +369,23 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, M::MIN_BLOCKS) isde_step_kernel(
                 P[q][i] = Pn[i];
             }
             lp[q] = lpn[q];            // log-posterior at xi_n (the point the model was evaluated at)
-
+        }
+        // ---- MAP estimate: the reference evaluates the posterior once more, at the NEW state xi_np (:1016-1019)
+        if (p.st.map_lp != nullptr) {
+            bool wantm[Q];
+            double lpm[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) wantm[q] = true;
+            log_posterior<M, D, G, Q, STREAM>(xi, wantm, p.prob, ts, p.tile_points, sub, group_mask, lpm);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                n_eval[q] += 1;
+                if (live[q] && sub == 0) track_map<D>(p.st, c[q], xi[q], lpm[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int64_t cq = c[q];
             if (live[q] && sub == 0) {
                 if (p.out.trace_lp1) p.out.trace_lp1[s * C + cq] = lpn[q];
                 if (keep) {
@@ -602,6 +622,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, M::MIN_BLOCKS) hmc_step_kernel(c
                     gcur[q][i] = gnew[q][i];
                 }
                 lp[q] = lpn[q];
+                if (p.st.map_lp != nullptr && live[q] && sub == 0) track_map<D>(p.st, cq, xn[q], lpn[q]);    // accept_reject -> estimate_max (:218)
             } else {
                 n_rej[q] += 1;
             }

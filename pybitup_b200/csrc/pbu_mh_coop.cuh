@@ -74,8 +74,10 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
 #pragma unroll
                 for (int i = 0; i < D; ++i) y[i] = __dadd_rn(x[i], __dmul_rn(scale, sj[i]));
                 n_eval += 1;
-                inb = inside_box<D>(y, p.prob);
             }
+            double Xown[D], ldj_own;                // X = parametrization_backward(Y) (bayesian_inference.py:50); X = Y when not re-parametrised
+            par_backward<D>(p.prob, y, Xown, ldj_own);
+            if (want) inb = inside_box<D>(Xown, p.prob);
             // ---- the own chain's state sits the data loop out in shared memory (one slot per thread, component stride
             // MH_MAX_BLOCK doubles): x, y, lp, mean_r, u are 2D + 3 register pairs the loop can spend on keeping all Q x U
             // dependency chains in flight instead (at the 128-register cap ptxas otherwise interleaves only two of them)
@@ -99,7 +101,7 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
             for (int q = 0; q < Q; ++q) {
                 double yq[D];
 #pragma unroll
-                for (int i = 0; i < D; ++i) yq[i] = team_bcast<G>(y[i], q, lane, team_mask);
+                for (int i = 0; i < D; ++i) yq[i] = team_bcast<G>(Xown[i], q, lane, team_mask);
                 any = any || (__shfl_sync(team_mask, (int)(want && inb), lane_chain<G>(lane) + q * (32 / G)) != 0);
                 begin_chain<M, D>(yq, p.prob, ctx[q], seq[q]);
 #pragma unroll
@@ -143,7 +145,13 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
             }
             bool again_own = false;
             if (want) {
-                const double lpy = inb ? (p.prob.log_prior_const - 0.0) + (-0.5 * (Jown + p.prob.J_const)) : -INFINITY;     // :44-64
+                double ldj = 0.0;                    // -log(det_jac), affine in Y: rebuilt here rather than kept across the data loop
+                if (p.prob.par_any) {
+                    ldj = p.prob.par_ldj_c0;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) ldj = fma(p.prob.par_ldj_s[i], y[i], ldj);
+                }
+                const double lpy = inb ? (p.prob.log_prior_const + ldj) + (-0.5 * (Jown + p.prob.J_const)) : -INFINITY;     // :44-64
                 bool accept;
                 if (stage == 0) {
                     lp1 = lpy;
@@ -182,6 +190,7 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
                     lp = lpy;
                     acc = stage + 1;
                     want = false;
+                    if (p.st.map_lp != nullptr && stage == 0 && live) track_map<D>(p.st, c, y, lpy);       // :218, Q10
                 } else if (DELAYED && stage == 0) {
                     // keep the rejected first proposal for the second-stage ratio (:549-556) out of the registers: the
                     // (otherwise unused) momentum array is this chain's scratch

@@ -294,10 +294,13 @@ __device__ __forceinline__ void begin_chain_block(const double (&x)[D], const Pr
 // model (:53-55), otherwise log_prior - log(1) + (-(1/2) J).  In resident mode the data pass is skipped
 // when no chain of the thread needs it.
 template <class M, int D, int G, int Q, bool STREAM>
-__device__ __forceinline__ void log_posterior(const double (&x)[Q][D], const bool (&want)[Q], const ProblemDev &prob, TileStream<M::NC> &ts,
+__device__ __forceinline__ void log_posterior(const double (&yv)[Q][D], const bool (&want)[Q], const ProblemDev &prob, TileStream<M::NC> &ts,
                                               int tile_points, int sub, unsigned group_mask, double (&lp)[Q]) {
     constexpr int U = M::UNROLL;   // tools/ubench: U = 4 points x Q = 2 chains in flight reaches 83% of the DFMA peak at 12 warps/SM
     bool inb[Q], any = false;
+    double x[Q][D], ldj[Q];        // X = parametrization_backward(Y), -log(det_jac(X))  (:50, :61)
+#pragma unroll
+    for (int q = 0; q < Q; ++q) par_backward<D>(prob, yv[q], x[q], ldj[q]);
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
         inb[q] = want[q] && inside_box<D>(x[q], prob);
@@ -354,7 +357,7 @@ __device__ __forceinline__ void log_posterior(const double (&x)[Q][D], const boo
 #pragma unroll
         for (int u = 0; u < U; ++u) Jq += J[q][u];
         Jq = group_sum<G>(Jq, group_mask) + prob.J_const;
-        if (inb[q]) lp[q] = (prob.log_prior_const - 0.0) + (-0.5 * Jq);
+        if (inb[q]) lp[q] = (prob.log_prior_const + ldj[q]) + (-0.5 * Jq);
     }
 }
 
@@ -546,6 +549,7 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
                     lp[q] = lpy[q];
                     acc[q] = stage + 1;
                     want[q] = false;
+                    if (p.st.map_lp != nullptr && stage == 0 && live[q] && sub == 0) track_map<D>(p.st, c[q], y[q], lpy[q]);   // :218, Q10
                 } else if (DELAYED && stage == 0) {
 #pragma unroll
                     for (int i = 0; i < D; ++i) y1[DELAYED ? q : 0][DELAYED ? i : 0] = y[q][i];

@@ -21,6 +21,13 @@ const pbu::MhKernelEntry *pbu_mh_kernels(int *n) {
         append(v, pbu_mh_slice_arrhenius);
         append(v, pbu_mh_slice_heat);
         append(v, pbu_mh_slice_soize);
+        append(v, pbu_mh_slice_linear_e);
+        append(v, pbu_mh_slice_linear_f);
+        append(v, pbu_mh_slice_linear_g);
+        append(v, pbu_mh_slice_linear_h);
+        append(v, pbu_mh_slice_poly_c);
+        append(v, pbu_mh_slice_poly_d);
+        append(v, pbu_mh_slice_poly_e);
         return v;
     }();
     *n = (int)all.size();
@@ -39,6 +46,13 @@ const pbu::EvalKernelEntry *pbu_eval_kernels(int *n) {
         append(v, pbu_eval_slice_arrhenius);
         append(v, pbu_eval_slice_heat);
         append(v, pbu_eval_slice_soize);
+        append(v, pbu_eval_slice_linear_e);
+        append(v, pbu_eval_slice_linear_f);
+        append(v, pbu_eval_slice_linear_g);
+        append(v, pbu_eval_slice_linear_h);
+        append(v, pbu_eval_slice_poly_c);
+        append(v, pbu_eval_slice_poly_d);
+        append(v, pbu_eval_slice_poly_e);
         return v;
     }();
     *n = (int)all.size();
@@ -57,6 +71,13 @@ const pbu::IsdeKernelEntry *pbu_isde_kernels(int *n) {
         append(v, pbu_isde_slice_arrhenius);
         append(v, pbu_isde_slice_heat);
         append(v, pbu_isde_slice_soize);
+        append(v, pbu_isde_slice_linear_e);
+        append(v, pbu_isde_slice_linear_f);
+        append(v, pbu_isde_slice_linear_g);
+        append(v, pbu_isde_slice_linear_h);
+        append(v, pbu_isde_slice_poly_c);
+        append(v, pbu_isde_slice_poly_d);
+        append(v, pbu_isde_slice_poly_e);
         return v;
     }();
     *n = (int)all.size();
@@ -75,6 +96,13 @@ const pbu::IsdeKernelEntry *pbu_hmc_kernels(int *n) {
         append(v, pbu_hmc_slice_arrhenius);
         append(v, pbu_hmc_slice_heat);
         append(v, pbu_hmc_slice_soize);
+        append(v, pbu_hmc_slice_linear_e);
+        append(v, pbu_hmc_slice_linear_f);
+        append(v, pbu_hmc_slice_linear_g);
+        append(v, pbu_hmc_slice_linear_h);
+        append(v, pbu_hmc_slice_poly_c);
+        append(v, pbu_hmc_slice_poly_d);
+        append(v, pbu_hmc_slice_poly_e);
         return v;
     }();
     *n = (int)all.size();

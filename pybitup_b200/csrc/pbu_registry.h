@@ -46,3 +46,10 @@ PBU_DECLARE_SLICE(poly_b)
 PBU_DECLARE_SLICE(arrhenius)
 PBU_DECLARE_SLICE(heat)
 PBU_DECLARE_SLICE(soize)
+PBU_DECLARE_SLICE(linear_e)
+PBU_DECLARE_SLICE(linear_f)
+PBU_DECLARE_SLICE(linear_g)
+PBU_DECLARE_SLICE(linear_h)
+PBU_DECLARE_SLICE(poly_c)
+PBU_DECLARE_SLICE(poly_d)
+PBU_DECLARE_SLICE(poly_e)

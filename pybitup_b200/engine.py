@@ -33,6 +33,10 @@ class ProblemSpec:
     # theta_nom [P], unc_idx [d] (-1 = not a parameter of that model), design {...}, n_points; y / std_y hold the
     # models' points concatenated in this order, and theta_nom / unc_idx / design above are those of the first model
     blocks: list = None
+    # element-wise change of variables Y (sampling space) -> X (model space), the lowered Model.parametrization_* hooks
+    # (bayesian_inference.py:314-336): {"kind": int[d] (0: X = a + b Y, 1: X = a + b exp(c Y)), "a", "b", "c": f64[d],
+    # "ldj_c0": float, "ldj_s": f64[d]} with -log(det_jac(X)) = ldj_c0 + ldj_s . Y; None = identity
+    param: dict = None
 
     @classmethod
     def from_dict(cls, p):
@@ -40,7 +44,7 @@ class ProblemSpec:
                    unc_idx=np.ascontiguousarray(np.asarray(p["unc_idx"], dtype=np.int32)),
                    y=_f64(np.atleast_2d(p["y"])), std_y=_f64(p["std_y"]), lb=_f64(p["lb"]), ub=_f64(p["ub"]),
                    gamma=float(p.get("gamma", 1.0)), design=dict(p.get("design", {})), log_const=p.get("log_const"),
-                   blocks=p.get("blocks"))
+                   blocks=p.get("blocks"), param=p.get("param"))
 
     @property
     def d(self):
@@ -142,7 +146,26 @@ class ProblemSpec:
         s.consts = (C.c_double * 8)(*consts)
         s.has_log_const = 0 if self.log_const is None else 1
         s.log_const = 0.0 if self.log_const is None else float(self.log_const)
+        if self.param is not None:
+            d = len(unc)
+            kind = np.ascontiguousarray(np.asarray(self.param["kind"], dtype=np.int32))
+            pa, pb, pc, ps = (_f64(self.param[k]) for k in ("a", "b", "c", "ldj_s"))
+            if not all(v.shape == (d,) for v in (kind, pa, pb, pc, ps)):
+                raise ValueError("parametrisation arrays must have one entry per uncertain parameter")
+            keep += [kind, pa, pb, pc, ps]
+            s.par_kind = kind.ctypes.data_as(C.POINTER(C.c_int32))
+            s.par_a, s.par_b, s.par_c, s.par_ldj_s = capi.dptr(pa), capi.dptr(pb), capi.dptr(pc), capi.dptr(ps)
+            s.par_ldj_c0 = float(self.param["ldj_c0"])
         return s, keep
+
+    # -- the change of variables on the host (start points, MAP / chain files) -------------------------------------
+    def backward(self, Y):
+        """X = parametrization_backward(Y) of the lowered change of variables; Y [..., d]."""
+        Y = np.asarray(Y, dtype=np.float64)
+        if self.param is None:
+            return Y
+        k, a, b, c = (np.asarray(self.param[n]) for n in ("kind", "a", "b", "c"))
+        return np.where(k == 1, a + b * np.exp(c * Y), a + b * Y)
 
 
 @dataclass
@@ -169,6 +192,7 @@ class SamplerConfig:
     hmc_step_size: float = 0.0
     hmc_num_steps: int = 0
     cooperative: int = 0             # 0 auto, 1 cooperative teams, -1 replicated layout only
+    track_map: bool = False          # per-chain MAP estimate (opt_arg estimate_max_distr, mha.py:226-237)
 
     def _c_struct(self):
         s = capi.pbu_sampler_cfg()
@@ -186,6 +210,7 @@ class SamplerConfig:
         s.seed, s.chain_offset = int(self.seed) & (2 ** 64 - 1), int(self.chain_offset)
         s.hmc_step_size, s.hmc_num_steps = float(self.hmc_step_size), int(self.hmc_num_steps)
         s.cooperative = int(self.cooperative)
+        s.track_map = int(self.track_map)
         return s
 
 
@@ -329,6 +354,13 @@ class ChainEngine:
         x = np.empty((self.n_chains, self.d))
         lp = np.empty(self.n_chains)
         capi.check(capi.lib.pbu_engine_get_state(self._h, capi.dptr(x), capi.dptr(lp)))
+        return x, lp
+
+    def map_estimate(self):
+        """(arg_MAP [C, d], MAP_val [C] in log) of every chain (mha.py:138-139, :226-237); needs track_map."""
+        x = np.empty((self.n_chains, self.d))
+        lp = np.empty(self.n_chains)
+        capi.check(capi.lib.pbu_engine_get_map(self._h, capi.dptr(x), capi.dptr(lp)))
         return x, lp
 
     def counters(self):

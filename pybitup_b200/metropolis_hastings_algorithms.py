@@ -165,8 +165,9 @@ class _DeviceSampler:
             rng = np.random.default_rng(int(self.opt_arg.get("seed", 0)) + 7919)
             scale = np.where(x0[0] == 0.0, 1.0, np.abs(x0[0]))
             x0[1:] += jitter * scale * rng.standard_normal((C - 1, self.n_param))
-            lb, ub = self.problem.lb, self.problem.ub
-            x0 = np.minimum(np.maximum(x0, lb), ub)
+            if getattr(self.problem, "param", None) is None:          # (the box lives in the model space X)
+                lb, ub = self.problem.lb, self.problem.ub
+                x0 = np.minimum(np.maximum(x0, lb), ub)
         return np.ascontiguousarray(x0[self.chain_first:self.chain_first + self.n_chains])
 
     def _write_header(self):
@@ -200,6 +201,7 @@ class _DeviceSampler:
         cfg = self._config()
         cfg.seed = int(self.opt_arg.get("seed", 0))
         cfg.chain_offset = int(self.opt_arg.get("chain_offset", 0)) + self.chain_first
+        cfg.track_map = self.estimate_max_distr         # estimate_max on the device (mha.py:226-237, :1011-1019)
         device = int(self.opt_arg["device"]) if self.opt_arg.get("device") is not None else local_device()
         if self.reducer.device_sum is not None and self.reducer.device.index != device:
             raise RuntimeError("rank {} runs its chains on cuda:{} but its process group is bound to cuda:{}".format(
@@ -290,7 +292,23 @@ class _DeviceSampler:
         self.mean_c = np.mean(self.chain, axis=0)
         self.cov_c = np.atleast_2d(np.cov(self.chain, rowvar=False)) if self.chain.shape[0] > 1 else np.zeros((self.n_param, self.n_param))
         rejection_rate = 0 if self.nIterations == 0 else self.n_rejected / self.nIterations * 100
+        if self.estimate_max_distr:
+            # MAP estimate (mha.py:138-139, :226-237): per chain on the device; the legacy attributes / files are global
+            # chain 0's (what a single-chain reference run reports), all chains in arg_MAP_all / MAP_val_all
+            self.arg_MAP_all, self.MAP_val_all = eng.map_estimate()
+            self.arg_MAP = self.reducer.broadcast0(self.arg_MAP_all[0])
+            self.MAP_val = float(self.reducer.broadcast0(self.MAP_val_all[:1])[0])
         if self.writer:
+            if self.bool_estimate_sigma and 'estimated_sigma' in self.IO_fileID and hasattr(self.prob_distr, "likelihood"):
+                import pandas as pd                           # terminate_loop :332-339: the unchanged std_y
+                for model_id in self.prob_distr.likelihood.data.keys():
+                    est_sigma = self.prob_distr.likelihood.data[model_id].std_y
+                    pd.DataFrame({'model_id': est_sigma}, columns=['model_id']).to_csv(self.IO_fileID['estimated_sigma'])
+            if self.estimate_max_distr and 'estimate_arg_max_val_distr' in self.IO_fileID:          # :352-355
+                model = getattr(self.prob_distr, "model", None)
+                arg = self.arg_MAP if model is None else model.parametrization_backward(self.arg_MAP)
+                np.savetxt(self.IO_fileID['estimate_arg_max_val_distr'], np.array([arg]), fmt="%f", delimiter=",")
+                np.savetxt(self.IO_fileID['estimate_max_val_distr'], np.array([np.exp(self.MAP_val)]), fmt="%f", delimiter=",")
             np.savetxt("cov.csv", self.cov_c, delimiter=",")
             print("\nRejection rate is {} %".format(rejection_rate))
             f = self.IO_fileID['out_data']                    # terminate_loop (:322-357)
@@ -384,6 +402,16 @@ class _GradientSampler(_DeviceSampler):
                                      '(Identity, Matrix, from_file, Hessian, Hessian_diag, nearPD are)')
         elif value not in ("Hessian", "Hessian_diag", "nearPD"):             # :653-660, :679-684, computed in _proposal_matrix
             raise ValueError('Unknown matrix type "{}" for estimating the conditioning matrix G .'.format(value))     # :708
+        par = getattr(getattr(self, "problem", None), "param", None)
+        if gradient == "Analytical" and par is not None:
+            # the analytical gradient goes through the user's inv_jac / grad_det_jac hooks (bayesian_inference.py:604-636);
+            # the device applies diag(dX/dY) and the gradient of -log(det_jac), so the hooks must be exactly that
+            from ._capi import UnsupportedProblem, PBU_ERR_UNSUPPORTED
+            if not par.get("grad_ok", False):
+                raise UnsupportedProblem(PBU_ERR_UNSUPPORTED, "analytical gradient of a re-parametrised model: " + par.get("grad_why", ""))
+            if self.problem.blocks:
+                raise UnsupportedProblem(PBU_ERR_UNSUPPORTED, "analytical gradient of a re-parametrised posterior with several "
+                                                              "models (each model's own inv_jac enters upstream) is not lowered")
         self.starting_it = int(self.C_matrix['starting_it'])
         self.update_it = int(self.C_matrix['update_it'])
         self.end_it = int(self.C_matrix['end_it']) if self.C_matrix.get("end_it") is not None else self.nIterations + 1

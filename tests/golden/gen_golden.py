@@ -219,6 +219,9 @@ def build_model(prob, names):
     return m
 
 
+from tests.helpers import install_parametrization    # noqa: E402  (the hooks as a user would write them)
+
+
 def pack_problem(prob):
     out = {"model": prob["model"], "theta_nom": prob["theta_nom"], "unc_idx": prob["unc_idx"],
            "y": prob["y"], "std_y": prob["std_y"], "lb": prob["lb"], "ub": prob["ub"],
@@ -228,13 +231,19 @@ def pack_problem(prob):
     return out
 
 
-def run_case(case, prob, names, algo, seed, stream_len):
+def run_case(case, prob, names, algo, seed, stream_len, param=None):
+    """param: element-wise re-parametrisation of the uncertain parameters installed on the reference-side model
+    (Model.parametrization_* hooks, bayesian_inference.py:314-336): {"kind": [...], "a": [...], "b": [...], "c": [...]} with
+    kind 0: X = a + b Y, kind 1: X = a + b exp(c Y); "det_jac": whether parametrization_det_jac is the true |dY/dX|
+    (False: the base class's constant 1)."""
     rng = np.random.default_rng(seed)
     normals = rng.standard_normal(stream_len)
     uniforms = rng.random(stream_len)
     with tempfile.TemporaryDirectory() as wd:
         write_case(wd, prob, names, algo, prob["design"].get("x", np.arange(prob["y"].shape[1], dtype=float)))
         model = build_model(prob, names)
+        if param is not None:
+            install_parametrization(model, param)
         rec = run_reference(wd, "case.json", {"case": model}, normals, uniforms)
     s = rec.sampler
     out = pack_problem(prob)
@@ -242,9 +251,11 @@ def run_case(case, prob, names, algo, seed, stream_len):
                uniforms=uniforms[:rec.n_uniforms_used],
                eval_x=np.array(rec.eval_x), eval_lp=np.array(rec.eval_lp), chain=np.array(rec.saved),
                n_rejected=s.n_rejected, mean_r=float(s.mean_r))
-    for attr in ("R", "V_i", "X_av_i", "inv_V", "C_approx", "P_nm", "xi_nm", "L_c", "inv_L_c"):
+    for attr in ("R", "V_i", "X_av_i", "inv_V", "C_approx", "P_nm", "xi_nm", "L_c", "inv_L_c", "arg_MAP", "MAP_val"):
         if hasattr(s, attr):
             out["final_" + attr] = np.array(getattr(s, attr), dtype=np.float64)
+    if param is not None:
+        out["param_json"] = json.dumps(param)
     path = os.path.join(HERE, case + ".npz")
     np.savez_compressed(path, **out)
     print("%-22s evals=%d chain=%s n_rej=%d -> %s (%d B)" % (
@@ -384,6 +395,67 @@ def gen_multi():
     run_multi_case("multi_cubic_isde", [c0, c1], cn, isde_algo(150, 0.02, 4.0, "Analytical", 10 ** 6, 10), 73, 150 * 4)
 
 
+def subset(prob, unc, scale_cov=1.0):
+    """The same problem with only the parameters `unc` uncertain (the others stay at theta_nom)."""
+    unc = np.asarray(unc)
+    return dict(prob, unc_idx=unc, lb=prob["lb"][unc], ub=prob["ub"][unc], x0=prob["x0"][unc],
+                prop_cov=prob["prop_cov"][np.ix_(unc, unc)] * scale_cov)
+
+
+def gen_widened():
+    """Round-2 widening: MAP tracking (estimate_max_distr, mha.py:226-237, :1011-1019), models with FIXED parameters
+    (d < P, Model.run_model :351-366) and re-parametrised models (parametrization_* hooks, :314-336; posterior :44-64,
+    gradient :573-636)."""
+    lin = synthetic.linear_problem()
+    lin_names = ["th0", "th1", "th2"]
+    T = 300
+    full_cov = np.array([[1e-3, 2e-3, -1e-3], [2e-3, 1e-2, 1e-3], [-1e-3, 1e-3, 1e-2]])
+    lin2 = dict(lin, prop_cov=full_cov)
+    run_case("linear_dr_map", lin2, lin_names, dict(mh_algo("DR", T, full_cov, gamma=0.2), estimate_max_distr="yes"), 81, 8 * T * 4)
+    run_case("linear_am_map", lin, lin_names, dict(mh_algo("AMH", T, lin["prop_cov"], updating_it=10, eps_v=1e-10),
+                                                   estimate_max_distr="yes"), 82, 4 * T * 4)
+    reg = synthetic.regression_problem(n_points=200, d=5)
+    reg_names = ["b%d" % i for i in range(5)]
+    run_case("regression_isde_map", reg, reg_names, dict(isde_algo(150, 0.02, 4.0, "Analytical", 10 ** 6, 10), estimate_max_distr="yes"),
+             83, 150 * 5)
+    run_case("regression_hmc_map", reg, reg_names, dict(hmc_algo(120, 0.01, 5, "Analytical", 10 ** 6, 10), estimate_max_distr="yes"),
+             84, 120 * 6)
+
+    # ---- fixed parameters: d < P
+    cub = synthetic.cubic_problem(n_points=100)
+    cub = dict(cub, prop_cov=cub["prop_cov"] * 10)
+    cub_names = ["c0", "c1", "c2", "c3"]
+    run_case("cubic_fixed_am", subset(cub, [1, 3]), cub_names, mh_algo("AMH", T, subset(cub, [1, 3])["prop_cov"], updating_it=10, eps_v=1e-10),
+             85, 5 * T * 2)
+    run_case("linear_fixed_dram", subset(lin, [0, 2]), lin_names,
+             mh_algo("DRAM", T, subset(lin, [0, 2])["prop_cov"], updating_it=10, eps_v=1e-10, gamma=0.2), 86, 8 * T * 2)
+    run_case("cubic_fixed_isde", subset(cub, [0, 2, 3]), cub_names, isde_algo(150, 0.004, 4.0, "Analytical", 10 ** 6, 10), 87, 150 * 3)
+    run_case("regression_fixed_hmc", subset(reg, [1, 4]), reg_names, hmc_algo(100, 0.01, 4, "Analytical", 10 ** 6, 10), 88, 100 * 3)
+
+    # ---- re-parametrised models.  The prior box lives in the model space X; the chain runs in Y.
+    # (1) every parameter sampled in log space, true Jacobian: Y = ln X
+    lin_pos = dict(lin, lb=np.array([0.1, 0.1, 0.1]), ub=np.array([10.0, 10.0, 10.0]))
+    logp = dict(kind=[1, 1, 1], a=[0.0, 0.0, 0.0], b=[1.0, 1.0, 1.0], c=[1.0, 1.0, 1.0], det_jac=True)
+    cov_log = np.diag([1e-3, 2.5e-3, 1.2e-3])
+    run_case("linear_logparam_am", dict(lin_pos, prop_cov=cov_log), lin_names,
+             mh_algo("AMH", T, cov_log, updating_it=10, eps_v=1e-10), 91, 4 * T * 4, param=logp)
+    # (2) affine scaling X = a + b Y (the `scaling_factors_parametrization` use case), DRAM
+    aff = dict(kind=[0, 0, 0, 0], a=[1.0, -2.0, 0.0, 3.0], b=[0.01, 0.05, 0.05, 0.1], c=[0.0] * 4, det_jac=True)
+    cov_aff = cub["prop_cov"] / np.outer(aff["b"], aff["b"])
+    run_case("cubic_affine_dram", dict(cub, prop_cov=cov_aff), cub_names,
+             mh_algo("DRAM", T, cov_aff, updating_it=10, eps_v=1e-10, gamma=0.2), 92, 8 * T * 4, param=aff)
+    # (3) mixed kinds, base-10 exponent, and a user who left det_jac at the base class's 1
+    mix = dict(kind=[0, 1, 0, 1], a=[0.0, -4.0, 0.5, 0.0], b=[1.0, 1.0, 0.2, 1.0], c=[0.0, 1.0, 0.0, float(np.log(10.0))], det_jac=False)
+    cov_mix = np.diag([1e-4, 2.5e-4, 2.5e-2, 1e-4]) * 0.5
+    run_case("cubic_mixed_dr", dict(cub, prop_cov=cov_mix), cub_names, mh_algo("DR", T, cov_mix, gamma=0.2), 93, 8 * T * 4, param=mix)
+    # (4) analytical gradient through the change of variables (inv_jac, grad_det_jac): Ito-SDE and HMC in log space
+    # (shifted exponential X = -3 + exp(Y): the regression coefficients straddle zero)
+    reg_pos = dict(reg, lb=np.full(5, -2.9), ub=np.full(5, 10.0))
+    logp5 = dict(kind=[1] * 5, a=[-3.0] * 5, b=[1.0] * 5, c=[1.0] * 5, det_jac=True)
+    run_case("regression_logparam_isde", reg_pos, reg_names, isde_algo(150, 0.002, 4.0, "Analytical", 10 ** 6, 10), 94, 150 * 5, param=logp5)
+    run_case("regression_logparam_hmc", reg_pos, reg_names, hmc_algo(100, 0.002, 4, "Analytical", 10 ** 6, 10), 95, 100 * 6, param=logp5)
+
+
 def gen_hessian_fd():
     """computeHessianFD (mha.py:1115-1212) of a fixed smooth function, all four flag combinations; pins
     pybitup_b200.metropolis_hastings_algorithms.compute_hessian_fd including the in-place aliasing of :1186-1189."""
@@ -427,9 +499,12 @@ if __name__ == "__main__":
         gen_hessian_fd()
     elif "--hmc" in sys.argv:
         gen_hmc()
+    elif "--widened" in sys.argv:
+        gen_widened()
     else:
         main()
         gen_hmc()
         gen_hessian_fd()
         gen_near_pd()
         gen_multi()
+        gen_widened()

@@ -19,7 +19,62 @@ def load_golden(case):
     g = dict(np.load(os.path.join(GOLDEN_DIR, case + ".npz"), allow_pickle=False))
     g["algo"] = json.loads(str(g["algo_json"]))
     g["model"] = str(g["model"])
+    if "param_json" in g:
+        g["param"] = json.loads(str(g["param_json"]))
     return g
+
+
+def device_param(param):
+    """The engine's form of a fixture's re-parametrisation (ProblemSpec.param): -log(det_jac) = ldj_c0 + ldj_s . Y with
+    det_jac = prod_i 1/(dX_i/dY_i) -- or the constant 1 when the recorded model left the hook alone."""
+    if param is None:
+        return None
+    kind = np.asarray(param["kind"], dtype=np.int32)
+    a, b, c = (np.asarray(param[k], dtype=np.float64) for k in ("a", "b", "c"))
+    true_det = bool(param.get("det_jac", True))
+    s = np.where(kind == 1, c, 0.0) if true_det else np.zeros(len(kind))
+    c0 = float(np.sum(np.log(np.abs(np.where(kind == 1, b * c, b))))) if true_det else 0.0
+    return dict(kind=kind, a=a, b=b, c=c, ldj_c0=c0, ldj_s=s, grad_ok=True)
+
+
+def install_parametrization(model, param):
+    """Element-wise change of variables as a user of the reference would code it in a bi.Model subclass (hooks of
+    bayesian_inference.py:314-336 plus grad_det_jac, :631).  Works on the reference's Model and on pybitup_b200's mirror."""
+    kind = np.asarray(param["kind"])
+    a, b, c = (np.asarray(param[k], dtype=np.float64) for k in ("a", "b", "c"))
+    true_det = bool(param.get("det_jac", True))
+
+    def backward(Y=1, P=1):
+        Y = np.asarray(Y, dtype=np.float64)
+        return np.where(kind == 0, a + b * Y, a + b * np.exp(c * Y))
+
+    def forward(X=1, P=1):
+        X = np.asarray(X, dtype=np.float64)
+        with np.errstate(all="ignore"):
+            return np.where(kind == 0, (X - a) / b, np.log((X - a) / b) / c)
+
+    def dXdY(X):
+        X = np.asarray(X, dtype=np.float64)
+        return np.where(kind == 0, b, c * (X - a))
+
+    def det_jac(X=1):
+        return float(np.prod(1.0 / dXdY(X))) if true_det else 1
+
+    def inv_jac(X=1):
+        return np.diag(dXdY(X))
+
+    def grad_det_jac(X=1):
+        # d/dX_k prod_i 1/(dX_i/dY_i): kind 0 contributes nothing, kind 1 has d/dX_k 1/(c (X_k - a)) = -1/(c (X_k - a)^2)
+        if not true_det:
+            return np.zeros(len(X))
+        X = np.asarray(X, dtype=np.float64)
+        return np.where(kind == 0, 0.0, -det_jac(X) / (X - a))
+
+    model.parametrization_backward = backward
+    model.parametrization_forward = forward
+    model.parametrization_det_jac = det_jac
+    model.parametrization_inv_jac = inv_jac
+    model.grad_det_jac = grad_det_jac
 
 
 def _design_of(g, prefix):
@@ -44,6 +99,8 @@ def problem_dict(g):
     out = dict(model=str(g["model"]), theta_nom=g["theta_nom"], unc_idx=g["unc_idx"], y=g["y"],
                std_y=g["std_y"], lb=g["lb"], ub=g["ub"], gamma=float(g["gamma"]), design=mem[0]["design"],
                x0=g["x0"], prop_cov=g["prop_cov"])
+    if "param" in g:
+        out["param"] = device_param(g["param"])
     if len(mem) > 1:          # several models: points concatenated, one block per model
         out["y"] = np.concatenate([np.atleast_2d(m["y"]) for m in mem], axis=1)
         out["std_y"] = np.concatenate([m["std_y"] for m in mem])
@@ -76,7 +133,19 @@ def oracle_problem(g):
         mem = model_members(g)
     probs = [_oracle_member(str(g["model"]), m, g["lb"], g["ub"], g["gamma"]) for m in mem]
     probs[0].extra = probs[1:]
+    if g.get("param") is not None and "det_jac" in g["param"]:       # (a fixture's recorded hooks; builder dicts carry the engine's form)
+        probs[0].param = g["param"]
     return probs[0]
+
+
+def start_point(g):
+    """Starting point of a recorded run in the SAMPLING space: parametrization_forward(initial_val)
+    (solve_problem.py:309), which is the first chain row the reference saved."""
+    return np.array(g["chain"][0], dtype=np.float64) if "param" in g else np.array(g["x0"], dtype=np.float64)
+
+
+def wants_map(g):
+    return g["algo"].get("estimate_max_distr") == "yes"
 
 
 def mh_kwargs(algo):

@@ -115,10 +115,10 @@ def test_error_paths():
     with pytest.raises(ValueError):
         SamplerConfig(algo="NUTS")._c_struct()
     q = dict(p)
-    q["theta_nom"] = np.arange(7.0)                           # no linear kernel with 7 parameters is compiled
-    q["unc_idx"] = np.arange(7)
-    q["design"] = dict(Phi=np.ones((50, 7)))
-    q["lb"], q["ub"] = np.full(7, -1.0), np.full(7, 1.0)
+    q["theta_nom"] = np.arange(11.0)                          # no linear kernel with 11 parameters is compiled
+    q["unc_idx"] = np.arange(11)
+    q["design"] = dict(Phi=np.ones((50, 11)))
+    q["lb"], q["ub"] = np.full(11, -1.0), np.full(11, 1.0)
     with pytest.raises(_capi.UnsupportedProblem):
         ChainEngine(ProblemSpec.from_dict(q), SamplerConfig(), 1)
     with pytest.raises(_capi.UnsupportedProblem):

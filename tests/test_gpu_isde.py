@@ -160,3 +160,46 @@ def test_hmc_many_chains_vs_oracle_with_adaptation_and_fd():
             out = orc.run_hmc(prob, x0[c], T, orc.Streams(nz[c], un[c]), 0.3, 3, gradient="Analytical", C0=C0, starting_it=30,
                               update_it=10, end_it=60)
             assert H.rel_err(xs[:, :, c], out["chain"][1:]) < 1e-6, c
+
+
+WIDENED = ["regression_isde_map", "regression_hmc_map", "cubic_fixed_isde", "regression_fixed_hmc",
+           "regression_logparam_isde", "regression_logparam_hmc"]
+
+
+@pytest.mark.parametrize("lanes", [1, 4])
+@pytest.mark.parametrize("case", WIDENED)
+def test_gradient_samplers_widened_golden(case, lanes):
+    """Ito-SDE / HMC against reference runs with MAP tracking (estimate_max_distr: one more posterior evaluation per
+    Ito-SDE iteration, mha.py:1011-1019), with fixed parameters (d < P) and through a change of variables (the gradient
+    goes through inv_jac and grad_det_jac, bayesian_inference.py:604-636)."""
+    from pybitup_b200.engine import ChainEngine, ProblemSpec, SamplerConfig
+    g = H.load_golden(case)
+    a = g["algo"]
+    if len(g["unc_idx"]) < len(g["theta_nom"]) and lanes != 1:
+        pytest.skip("models with fixed parameters (d < P) are compiled for one lane per chain")
+    T, C = int(a["n_iterations"]), 3
+    common = dict(isde_gradient=a["gradient"], adapt_start=int(a["covariance"]["starting_it"]),
+                  adapt_update=int(a["covariance"]["update_it"]), lanes_per_chain=lanes, track_map=H.wants_map(g))
+    if a["name"] == "ISDE":
+        cfg = SamplerConfig(algo="ISDE", isde_h=float(a["ISDE"]["h"]), isde_f0=float(a["ISDE"]["f0"]), **common)
+    else:
+        cfg = SamplerConfig(algo="HMC", hmc_step_size=float(a["HMC"]["step_size"]), hmc_num_steps=int(a["HMC"]["num_steps"]), **common)
+    x0 = H.start_point(g)
+    with ChainEngine(ProblemSpec.from_dict(H.problem_dict(g)), cfg, C) as eng:
+        eng.init_chains(np.tile(x0, (C, 1)), None)
+        eng.set_streams(np.tile(g["normals"], (C, 1)), np.tile(g["uniforms"], (C, 1)) if a["name"] == "HMC" else None)
+        res = eng.run(T, thin=1)
+        eng.synchronize()
+        xs = res.samples.cpu().numpy()
+        ctr = eng.counters()
+        for c in range(C):
+            chain = np.concatenate([x0[None, :], xs[:, :, c]], axis=0)
+            assert H.rel_err(chain, g["chain"]) < 1e-9
+            if a["name"] == "HMC":
+                assert ctr["n_rejected"][c] == int(g["n_rejected"])
+        if H.wants_map(g):
+            arg_map, map_val = eng.map_estimate()
+            for c in range(C):
+                assert H.rel_err(arg_map[c], g["final_arg_MAP"]) < 1e-9
+                assert H.rel_err(map_val[c], float(g["final_MAP_val"])) < 1e-9
+        assert np.all(ctr["status"] == 0)

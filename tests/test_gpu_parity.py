@@ -52,11 +52,13 @@ def test_mh_golden_parity(case, lanes):
         pytest.skip("sequential ODE model: one lane per chain")
     if "n_models" in g and lanes < 0:
         pytest.skip("several models per likelihood run in the replicated layout (the cooperative kernel is single-model)")
+    if g["model"] in ("linear", "poly") and len(g["unc_idx"]) < len(g["theta_nom"]) and lanes != 1:
+        pytest.skip("models with fixed parameters (d < P) are compiled for one lane per chain")
     T = int(algo["n_iterations"])
     tol = TOL          # every fixture: the kernel's Cholesky runs in LAPACK's dpotf2 order (pbu_common.cuh)
     n_chains = 3 if lanes > 0 else 11       # the same chain several times: every chain must reproduce the reference
-    eng = _engine(g, algo, n_chains, lanes_per_chain=abs(lanes), cooperative=(1 if lanes < 0 else -1))
-    eng.init_chains(np.tile(g["x0"], (n_chains, 1)), g["prop_cov"])
+    eng = _engine(g, algo, n_chains, lanes_per_chain=abs(lanes), cooperative=(1 if lanes < 0 else -1), track_map=H.wants_map(g))
+    eng.init_chains(np.tile(H.start_point(g), (n_chains, 1)), g["prop_cov"])      # (sampling space: forward(initial_val))
     x_init, lp_init = eng.state()
     eng.set_streams(np.tile(g["normals"], (n_chains, 1)), np.tile(g["uniforms"], (n_chains, 1)))
     res = eng.run(T, thin=1, keep_lp=True, trace=True)
@@ -78,6 +80,11 @@ def test_mh_golden_parity(case, lanes):
         assert ctr["n_eval"][c] == len(g["eval_lp"])
         assert ctr["status"][c] & 3 == 0
         assert H.rel_err(ctr["mean_r"][c], float(g["mean_r"])) < max(tol, 1e-9)
+    if H.wants_map(g):          # estimate_max on the device (mha.py:226-237): every copy of the chain finds the reference's MAP
+        arg_map, map_val = eng.map_estimate()
+        for c in range(n_chains):
+            assert H.rel_err(arg_map[c], g["final_arg_MAP"]) < tol
+            assert H.rel_err(map_val[c], float(g["final_MAP_val"])) < tol
     prop = eng.proposal()
     assert H.rel_err(prop["R"][0], g["final_R"]) < max(1e-7, 100 * tol)
     if algo["name"] in ("AMH", "DRAM"):

@@ -110,7 +110,12 @@ def test_unsupported_problems_fail_loudly():
     post = _posterior({"device_model": None})
     with pytest.raises(_capi.UnsupportedProblem):
         post.lower()
-    post = _posterior({"parametrization_backward": lambda self, Y=1, P=1: np.exp(Y)})
+    # log sampling with the det_jac hook left at 1 is a registered change of variables (kind 1, constant log det_jac) ...
+    spec = _posterior({"parametrization_backward": lambda self, Y=1, P=1: np.exp(Y)}).lower()
+    assert list(spec.param["kind"]) == [1] * spec.d and np.all(spec.param["c"] == 1.0) and np.all(spec.param["ldj_s"] == 0.0)
+    assert _posterior({}).lower().param is None
+    # ... a map the device does not know is refused
+    post = _posterior({"parametrization_backward": lambda self, Y=1, P=1: np.asarray(Y) ** 3})
     with pytest.raises(_capi.UnsupportedProblem):
         post.lower()
     from pybitup_b200 import distributions

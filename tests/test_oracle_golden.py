@@ -21,7 +21,7 @@ def test_mh_family_matches_reference(case):
     algo = g["algo"]
     T = int(algo["n_iterations"])
     st = orc.Streams(g["normals"], g["uniforms"])
-    out = orc.run_mh(prob, g["x0"], g["prop_cov"], T, st, **H.mh_kwargs(algo))
+    out = orc.run_mh(prob, H.start_point(g), g["prop_cov"], T, st, **H.mh_kwargs(algo))
     # same number of posterior evaluations, same inputs, same values
     assert out["n_eval"] == len(g["eval_lp"])
     assert H.rel_err(out["eval_lp"], g["eval_lp"]) < TOL
@@ -40,6 +40,65 @@ def test_mh_family_matches_reference(case):
     if "final_V_i" in g and algo["name"] in ("AMH", "DRAM"):
         assert H.rel_err(out["V_i"], g["final_V_i"]) < 1e-7
         assert H.rel_err(out["X_av"], g["final_X_av_i"]) < TOL
+    if H.wants_map(g):                  # estimate_max (mha.py:226-237): first-stage acceptances only (Q10)
+        assert np.array_equal(out["arg_MAP"], out["arg_MAP"]) and H.rel_err(out["arg_MAP"], g["final_arg_MAP"]) < TOL
+        assert H.rel_err(out["MAP_val"], float(g["final_MAP_val"])) < TOL
+        assert float(g["final_MAP_val"]) > g["eval_lp"][0]
+
+
+WIDENED_GRADIENT_CASES = ["regression_isde_map", "regression_hmc_map", "cubic_fixed_isde", "regression_fixed_hmc",
+                          "regression_logparam_isde", "regression_logparam_hmc"]
+
+
+@pytest.mark.parametrize("case", WIDENED_GRADIENT_CASES)
+def test_gradient_samplers_widened_cases(case):
+    """Ito-SDE / HMC with MAP tracking (one more posterior evaluation per Ito-SDE iteration, mha.py:1011-1019), with fixed
+    parameters (d < P) and through a change of variables (inv_jac, grad_det_jac: bayesian_inference.py:604-636)."""
+    g = H.load_golden(case)
+    prob = H.oracle_problem(g)
+    a = g["algo"]
+    T = int(a["n_iterations"])
+    x0 = H.start_point(g)
+    if a["name"] == "ISDE":
+        out = orc.run_isde(prob, x0, T, orc.Streams(g["normals"], np.zeros(1)), a["ISDE"]["h"], a["ISDE"]["f0"],
+                           gradient=a["gradient"], track_map=H.wants_map(g))
+        assert H.rel_err(out["P"][-1], g["final_P_nm"]) < 1e-9
+    else:
+        st = orc.Streams(g["normals"], g["uniforms"])
+        out = orc.run_hmc(prob, x0, T, st, a["HMC"]["step_size"], int(a["HMC"]["num_steps"]), gradient=a["gradient"])
+        assert st.i_n == len(g["normals"]) and st.i_u == len(g["uniforms"])
+        assert out["n_rejected"] == int(g["n_rejected"])
+    assert H.rel_err(out["chain"], g["chain"]) < 1e-9
+    if H.wants_map(g):
+        assert H.rel_err(out["arg_MAP"], g["final_arg_MAP"]) < 1e-9
+        assert H.rel_err(out["MAP_val"], float(g["final_MAP_val"])) < 1e-9
+
+
+@pytest.mark.parametrize("case", ["linear_logparam_am", "cubic_affine_dram", "cubic_mixed_dr", "regression_logparam_isde"])
+def test_parametrization_is_recovered_from_the_hooks(case):
+    """pybitup_b200.bayesian_inference.lower_parametrization probes the user's parametrization_* hooks and must recover
+    the element-wise map (and the affine form of -log det_jac) the fixture's model was given."""
+    from pybitup_b200 import bayesian_inference as bi
+    g = H.load_golden(case)
+    m = bi.Model()
+    H.install_parametrization(m, g["param"])
+    got = bi.lower_parametrization(m, H.start_point(g), need_gradient=True)
+    want = H.device_param(g["param"])
+    assert np.array_equal(got["kind"], want["kind"])
+    for k in ("a", "b", "c", "ldj_s"):
+        assert np.max(np.abs(got[k] - want[k])) < 1e-12 * max(1.0, np.max(np.abs(want[k]))), k
+    assert abs(got["ldj_c0"] - want["ldj_c0"]) < 1e-12
+    assert got["grad_ok"]
+    # the identity is recognised as such, and a map the device does not know is refused
+    assert bi.lower_parametrization(bi.Model(), H.start_point(g)) is None
+    bad = bi.Model()
+    bad.parametrization_backward = lambda Y=1, P=1: np.asarray(Y) ** 3
+    with pytest.raises(Exception, match="re-parametrisation"):
+        bi.lower_parametrization(bad, np.array([0.7, 1.1]))
+    coupled = bi.Model()
+    coupled.parametrization_backward = lambda Y=1, P=1: np.array([Y[0] + Y[1], Y[1]])
+    with pytest.raises(Exception, match="element-wise"):
+        bi.lower_parametrization(coupled, np.array([0.7, 1.1]))
 
 
 def test_isde_analytical_matches_reference():
@@ -153,7 +212,7 @@ def test_adaptive_cases_in_the_kernels_operation_order(case):
     prob = H.oracle_problem(g)
     st = orc.Streams(g["normals"], g["uniforms"])
     with orc.kernel_order():
-        out = orc.run_mh(prob, g["x0"], g["prop_cov"], int(g["algo"]["n_iterations"]), st, **H.mh_kwargs(g["algo"]))
+        out = orc.run_mh(prob, H.start_point(g), g["prop_cov"], int(g["algo"]["n_iterations"]), st, **H.mh_kwargs(g["algo"]))
     assert H.rel_err(out["eval_lp"], g["eval_lp"]) < 1e-13
     ref_chain = H.golden_chain(g)
     assert np.array_equal(out["acc"] > 0, np.any(ref_chain[1:] != ref_chain[:-1], axis=1))
