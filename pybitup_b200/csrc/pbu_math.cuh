@@ -111,20 +111,22 @@ PBU_HD double pbu_log(double u) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Table-driven base-2 variants: 2^y in 8 and log2(u) in 7 FP64 instructions (against 17 and 22 above), paid for with
+// Table-driven base-2 variants: 2^y in 7 and log2(u) in 6 FP64 instructions (against 17 and 22 above), paid for with
 // one shared-memory load each.  The FP64 pipe is what bounds the ODE models, the load/store pipe is idle there.  Base 2
 // makes both argument reductions exact and removes the ln2 hi/lo bookkeeping; u^n = 2^(n log2 u) needs nothing else.
-//   pbu_exp2_tab : y = k + j/512 + r, |r| <= 2^-10 (r = y - (512k+j)/512 EXACTLY, one FMA);
-//                  2^y = 2^k T[j] (1 + r (b1 + b2 r + b3 r^2 + b4 r^3)),  T[j] = 2^(j/512),  b_i = ln2^i / i!
-//   pbu_log2_tab : u = 2^e m, m in [1, 2), i = top 8 mantissa bits;  r = m c_i - 1, |r| <= 2^-9 (one FMA);
-//                  log2 u = e + (-log2 c_i + r (a1 + a2 r + .. + a5 r^4)),  a_i = (-1)^(i+1) / (i ln2)
-// Tables: pbu_math_tables.h (generated by tools/gen_math_tables.py), 512 + 2*256 doubles (8 KB).  On the device the kernels
-// stage them in shared memory once per block (Model::block_init), on a 4 KB boundary of the shared window, and pass the
-// pointer; on the host the static copy.
-// Checked against libm in tools/test_math.cu: exp2 <= 1 ulp; log2 <= 1 ulp of max(|log2 u|, 1) -- the error that
+//   pbu_exp2_tab : y = k + j/1024 + r, |r| <= 2^-11 (r = y - (1024k+j)/1024 EXACTLY, one FMA);
+//                  2^y = 2^k T[j] (1 + r (B1 + r (B2 + r B3))),  T[j] = 2^(j/1024)
+//   pbu_log2_tab : u = 2^e m, m in [1, 2), i = top 9 mantissa bits;  r = m c_i - 1 = u (2^-e c_i) - 1, |r| <= 2^-10 (one FMA on
+//                  u itself: the table value is scaled by 2^-e with one integer instruction, u is never taken apart);
+//                  log2 u = e + (-log2 c_i + r (A1 + r (A2 + r (A3 + r A4))))
+// The coefficients are Taylor series whose last term is economised over the reduced range (tools/gen_math_tables.py): a
+// cubic and a quartic where the plain series need one degree more.  Tables: pbu_math_tables.h, 1024 + 2*512 doubles (16 KB).
+// On the device the kernels stage them in shared memory once per block (Model::block_init), on an 8 KB boundary of the
+// shared window, and pass the pointer; on the host the static copy.
+// Checked against libm in tools/test_math.cu: exp2 <= 2 ulp; log2 <= 1 ulp of max(|log2 u|, 1) -- the error that
 // matters for 2^(n log2 u) is the absolute one.
-#define PBU_MATH_TABLE_DOUBLES (512 + 512)
-#define PBU_LOG2_TABLE_OFFSET 512
+#define PBU_MATH_TABLE_DOUBLES (PBU_EXP2_ENTRIES + 2 * PBU_LOG2_ENTRIES)
+#define PBU_LOG2_TABLE_OFFSET PBU_EXP2_ENTRIES
 static const double pbu_math_tables_host[PBU_MATH_TABLE_DOUBLES] = {PBU_EXP2_TABLE, PBU_LOG2_TABLE};
 #ifdef __CUDACC__
 static __device__ const double pbu_math_tables_dev[PBU_MATH_TABLE_DOUBLES] = {PBU_EXP2_TABLE, PBU_LOG2_TABLE};
@@ -135,17 +137,12 @@ static __device__ const double pbu_math_tables_dev[PBU_MATH_TABLE_DOUBLES] = {PB
 // about 30 instruction-issue slots per RK4 step, and on this kernel every issued instruction is a cycle the FP64 pipe
 // idles (an FP64 instruction holds the issue port for 2 cycles, everything else for 1; ncu: issue slots add up to the
 // elapsed cycles).
-#define PBU_K_B4 9.6181291076284772e-03                          // ln2^4/24
-#define PBU_K_B3 5.5504108664821580e-02                          // ln2^3/6
-#define PBU_K_B2 2.4022650695910072e-01                          // ln2^2/2
-#define PBU_K_B1 6.9314718055994531e-01                          // ln2
-#define PBU_K_A5 2.8853900817779266e-01                          // 1/(5 ln2)
-#define PBU_K_A4 -3.6067376022224085e-01                         // -1/(4 ln2)
-#define PBU_K_A3 4.8089834696298783e-01                          // 1/(3 ln2)
-#define PBU_K_A2 -7.2134752044448170e-01                         // -1/(2 ln2)
-#define PBU_K_A1 1.4426950408889634e+00                          // 1/ln2
 #ifdef __CUDACC__
-static __constant__ double pbu_kc[9] = {PBU_K_B4, PBU_K_B3, PBU_K_B2, PBU_K_B1, PBU_K_A5, PBU_K_A4, PBU_K_A3, PBU_K_A2, PBU_K_A1};
+// exp2 coefficients in the scaled variable r' = PBU_EXP2_ENTRIES r (exact power-of-two scalings)
+#define PBU_K_B1S (PBU_K_B1 / PBU_EXP2_ENTRIES)
+#define PBU_K_B2S (PBU_K_B2 / ((double)PBU_EXP2_ENTRIES * PBU_EXP2_ENTRIES))
+#define PBU_K_B3S (PBU_K_B3 / ((double)PBU_EXP2_ENTRIES * PBU_EXP2_ENTRIES * PBU_EXP2_ENTRIES))
+static __constant__ double pbu_kc[8] = {0.0, PBU_K_B1S, PBU_K_B2S, PBU_K_B3S, PBU_K_A1, PBU_K_A2, PBU_K_A3, PBU_K_A4};
 #endif
 #ifdef __CUDA_ARCH__
 #define PBU_KC(i, lit) pbu_kc[i]
@@ -154,7 +151,7 @@ static __constant__ double pbu_kc[9] = {PBU_K_B4, PBU_K_B3, PBU_K_B2, PBU_K_B1, 
 #endif
 
 #ifdef __CUDA_ARCH__
-// 32-bit shared-window address of the tables, which the caller has placed on a 4 KB boundary of that window
+// 32-bit shared-window address of the tables, which the caller has placed on an 8 KB boundary of that window
 // (ArrheniusModel::tables).  The mov hides the known-zero low bits from the front end, which would otherwise turn
 // base | offset back into an add; ptxas folds the mov and merges mask and OR into one LOP3.
 __device__ __forceinline__ uint32_t pbu_tab_base(const double *tab) {
@@ -164,17 +161,27 @@ __device__ __forceinline__ uint32_t pbu_tab_base(const double *tab) {
 }
 #endif
 
-// 2^y, hi word of the result forced to 0 where !keep (the caller's own range test rides on the selection that is
-// already there).  tab: the PBU_MATH_TABLE_DOUBLES doubles above (exp2 table first).  Domain y < 1024; y <= -1022 (and
-// -inf) returns a denormal (< 2.3e-308) instead of the exact tail: the hi word of y is clamped as an unsigned integer
-// (one instruction; negative doubles order by magnitude), which lands in k = -1022 or -1023 and leaves at most the
-// mantissa bits.  The FP64 pipe sees the eight arithmetic instructions only.  NaN with the sign bit clear propagates.
-PBU_HD double pbu_exp2_tab_sel(double y, const double *tab, bool keep) {
-    const uint32_t yh = (uint32_t)hi_word(y);
-    y = with_hi_word(y, (int32_t)(yh < 0xC08FF000u ? yh : 0xC08FF000u));        // y >= -1022.001
+// The first FMA of each polynomial has TWO constant operands and a DFMA reads only one from the constant bank: left to
+// itself ptxas reloads the other into a register inside the caller's loop, every trip (it rematerialises constant-bank
+// loads at will, through inline-asm moves as well).  The caller therefore keeps the two leading coefficients (and its own
+// -1/6) behind the tables in SHARED memory, loads them once per model evaluation and passes them in: a shared-memory
+// load is not something ptxas repeats.
+#define PBU_MATH_EXTRA_DOUBLES 4
+#ifdef __CUDACC__
+static __device__ const double pbu_math_extra_dev[PBU_MATH_EXTRA_DOUBLES] = {PBU_K_A4, PBU_K_B3S, -1.0 / 6.0, 0.0};
+#endif
+
+// 2^y for y < 1024, taking ys = PBU_EXP2_ENTRIES * y (the caller keeps its exponents in that unit: scaling by a power of two is exact,
+// and the reduction becomes three plain additions with immediate operands -- no constant held in a register).  The result is
+// forced to (almost) zero where y <= -1022 or where uh, the HI WORD of the caller's log argument u, is not that of a positive
+// normal number (negative, zero, denormal: pbu_log2_tab returned garbage for it): both tests ride on ONE selection of the
+// table value's hi word, which leaves a tiny denormal instead of the exact tail below 2^-1022 (-inf included).  The scale
+// 2^k goes onto the TABLE value before the last FMA, so the result needs no fix-up.  The FP64 pipe sees the seven arithmetic
+// instructions only.  NaN with the sign bit clear propagates.
+PBU_HD double pbu_exp2_tab_scaled_sel(double ys, const double *tab, int32_t uh, double kB3) {
     const double SHIFT = 6755399441055744.0;                     // 1.5 * 2^52
-    const double t = fma(y, 512.0, SHIFT);
-    const double kf = t - SHIFT;                                 // 512 k + j as a double
+    const double t = ys + SHIFT;
+    const double kf = t - SHIFT;                                 // 1024 k + j as a double
     const int32_t m = (int32_t)(uint32_t)(
 #ifdef __CUDA_ARCH__
         __double2loint(t)
@@ -182,48 +189,59 @@ PBU_HD double pbu_exp2_tab_sel(double y, const double *tab, bool keep) {
         [](double v) { uint64_t b; memcpy(&b, &v, 8); return (int32_t)(uint32_t)b; }(t)
 #endif
     );
-    const double r = fma(kf, -0.001953125, y);                   // exact
-    double p = fma(r, PBU_KC(0, PBU_K_B4), PBU_KC(1, PBU_K_B3));
-    p = fma(p, r, PBU_KC(2, PBU_K_B2));
-    p = fma(p, r, PBU_KC(3, PBU_K_B1));
-    const double v = p * r;                                      // 2^r - 1, remainder (r ln2)^5/120 < 1.3e-18
+    const double r = ys - kf;                                    // exact; |r| <= 1/2, i.e. 2^-11 in units of y
+    double p = fma(r, kB3, PBU_KC(2, PBU_K_B2S));                // kB3 = PBU_K_B3S, held in a register by the caller (see pbu_lead_coefficients)
+    p = fma(p, r, PBU_KC(1, PBU_K_B1S));
+    const double v = p * r;                                      // 2^(r/1024) - 1 (no constant term: 2^0 is exactly 1)
 #ifdef __CUDA_ARCH__
-    double T;                                                    // tab is 4 KB aligned in the shared window: base | offset
-    asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(pbu_tab_base(tab) | (((uint32_t)m << 3) & 0xFF8u)));      // is one LOP3
+    double T;                                                    // tab is 8 KB aligned in the shared window: base | offset
+    asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(pbu_tab_base(tab) | (((uint32_t)m << 3) & (8u * PBU_EXP2_ENTRIES - 8u))));      // is one LOP3
+    // hi word of T 2^k where kept, 0 otherwise: two compares into one predicate, one multiply-add, one select
+    double Ts;
+    asm("{\n\t.reg .pred p, q;\n\t.reg .s32 k, lo, hi;\n\t"
+        "setp.ge.s32 q, %3, 0x00100000;\n\t"                      // u positive and normal
+        "setp.lt.and.u32 p, %2, 0xC12FF000, q;\n\t"               // ys > -1022 * 1024 (negative doubles order by magnitude as unsigned integers)
+        "mov.b64 {lo, hi}, %1;\n\t"
+        "shr.s32 k, %4, 10;\n\t"
+        "mad.lo.s32 hi, k, 1048576, hi;\n\t"
+        "selp.b32 hi, hi, 0, p;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t}"
+        : "=d"(Ts) : "d"(T), "r"(hi_word(ys)), "r"(uh), "r"(m));
 #else
-    const double T = tab[m & 511];
+    const double T = tab[m & (PBU_EXP2_ENTRIES - 1)];
+    const bool keep = (uh >= 0x00100000) && ((uint32_t)hi_word(ys) < 0xC12FF000u);
+    const double Ts = with_hi_word(T, keep ? hi_word(T) + (m >> 10) * 1048576 : 0);
 #endif
-    const double e = fma(T, v, T);
-    int32_t rh;                                                  // * 2^k on the exponent field (k >= -1023 here)
-#ifdef __CUDA_ARCH__
-    asm("{\n\t.reg .s32 k;\n\tshr.s32 k, %1, 9;\n\tmad.lo.s32 %0, k, 1048576, %2;\n\t}" : "=r"(rh) : "r"(m), "r"(hi_word(e)));
-#else
-    rh = hi_word(e) + (m >> 9) * 1048576;
-#endif
-    return with_hi_word(e, keep ? rh : 0);
+    return fma(Ts, v, Ts);
 }
-PBU_HD double pbu_exp2_tab(double y, const double *tab) { return pbu_exp2_tab_sel(y, tab, true); }
+PBU_HD double pbu_exp2_tab(double y, const double *tab) { return pbu_exp2_tab_scaled_sel(y * (double)PBU_EXP2_ENTRIES, tab, 0x3FF00000, PBU_K_B3S); }
 
-// true for positive, normal, finite u: the arguments pbu_log2_tab accepts (an integer test)
-PBU_HD bool pbu_log_arg_ok(double u) { return (uint32_t)(hi_word(u) - 0x00100000) < 0x7FE00000u; }
-
-PBU_HD double pbu_log2_tab(double u, const double *tab) {
+// log2(u) for normal 0 < u < 2^1000 (anything else: finite garbage, to be discarded by the caller -- pbu_exp2_tab_scaled_sel
+// does it from the hi word of u)
+PBU_HD double pbu_log2_tab(double u, const double *tab, double kA4 = PBU_K_A4) {
     const int32_t hi = hi_word(u);
     const int32_t e = (hi >> 20) - 1023;
-    const double m = with_hi_word(u, (hi & 0x000FFFFF) | 0x3FF00000);
 #ifdef __CUDA_ARCH__
-    double c, nlc;                                               // one 16-byte shared-memory load, address as in exp2
-    asm("ld.shared.v2.f64 {%0, %1}, [%2+4096];" : "=d"(c), "=d"(nlc)                 // 4096 = 8 * PBU_LOG2_TABLE_OFFSET
-        : "r"(pbu_tab_base(tab) | (((uint32_t)hi >> 8) & 0xFF0u)));
+    double cs, nlc;                                              // one 16-byte shared-memory load, address as in exp2
+    asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(cs), "=d"(nlc)
+        : "r"(pbu_tab_base(tab) | (((uint32_t)hi >> 7) & (16u * PBU_LOG2_ENTRIES - 16u))), "n"(8 * PBU_LOG2_TABLE_OFFSET));
+    // c 2^-e: the exponent field of u comes off the exponent field of c, in place (one three-input integer add)
+    asm("{\n\t.reg .s32 lo, hi, t;\n\t"
+        "mov.b64 {lo, hi}, %0;\n\t"
+        "and.b32 t, %1, 0x7FF00000;\n\t"
+        "sub.s32 hi, hi, t;\n\t"
+        "add.s32 hi, hi, 0x3FF00000;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t}"
+        : "+d"(cs) : "r"(hi));
 #else
-    const int32_t i = (hi >> 12) & 255;
+    const int32_t i = (hi >> 11) & (PBU_LOG2_ENTRIES - 1);
     const double c = tab[PBU_LOG2_TABLE_OFFSET + 2 * i], nlc = tab[PBU_LOG2_TABLE_OFFSET + 2 * i + 1];
+    const double cs = with_hi_word(c, hi_word(c) - (hi & 0x7FF00000) + 0x3FF00000);
 #endif
-    const double r = fma(m, c, -1.0);
-    double q = fma(r, PBU_KC(4, PBU_K_A5), PBU_KC(5, PBU_K_A4));     // remainder r^6 / (6 ln2) < 1.4e-17
-    q = fma(q, r, PBU_KC(6, PBU_K_A3));
-    q = fma(q, r, PBU_KC(7, PBU_K_A2));
-    q = fma(q, r, PBU_KC(8, PBU_K_A1));
+    const double r = fma(u, cs, -1.0);
+    double q = fma(r, kA4, PBU_KC(6, PBU_K_A3));                 // economised: see the header of this section
+    q = fma(q, r, PBU_KC(5, PBU_K_A2));
+    q = fma(q, r, PBU_KC(4, PBU_K_A1));
     return fma(r, q, nlc) + (double)e;                           // small part first: one rounding at full size
 }
 

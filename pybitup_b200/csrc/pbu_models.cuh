@@ -183,65 +183,70 @@ struct ArrheniusModel {
     static constexpr int MIN_BLOCKS = 2;   // resident blocks per SM the step kernels are compiled for (register cap)
     static constexpr double R_GAS = 8.314462618;
     struct Ctx {
-        double c0, ER, n, F, h, y_start;
+        double c0, ER, n, F, omF, y_start;
+        double kA4, kB3, sixth;     // leading polynomial coefficients of log2 / exp2 and -1/6, pinned in registers (loaded from shared memory, pbu_math.cuh)
     };
     struct Seq {
-        double alpha, y0;
+        double u, y0;          // u = 1 - alpha (the unconverted fraction), y0 = log2 of (rate x step) at the start of the step
     };
     // Everything is kept in base 2: c0 and ER are divided by ln 2 and c0 also carries log2(h), so y(T) = c0 - ER/T is
     // the log2 of the stage rate times the step.  A stage is k = h g(T) u^n = 2^(y + n log2 u): ONE exp2 per stage on the
-    // sum of the two exponents, no exp2 for the rate alone and no product g * u^n (76 FP64 instructions per RK4 step
-    // where exp2(rate) x exp2(n log2 u) took 96).
+    // sum of the two exponents, no exp2 for the rate alone and no product g * u^n.
     __device__ __forceinline__ static void begin(Ctx &c, const double (&theta)[4], const double *consts) {
         const double c0 = 2.302585092994046 * theta[0] - log(consts[2]) + log(consts[1]);   // ln(10)*log10A - ln(beta) + ln(h)
         const double ER = theta[1] / R_GAS;
-        c.c0 = c0 * 1.4426950408889634;
-        c.ER = ER * 1.4426950408889634;
-        c.n = theta[2];
+        // ... and in units of 1/PBU_EXP2_ENTRIES, the index unit of the exp2 table (exact scalings by a power of two)
+        c.c0 = c0 * 1.4426950408889634 * PBU_EXP2_ENTRIES;
+        c.ER = ER * 1.4426950408889634 * PBU_EXP2_ENTRIES;
+        c.n = theta[2] * PBU_EXP2_ENTRIES;
         c.F = theta[3];
-        c.h = consts[1];
+        c.omF = 1.0 - theta[3];
         c.y_start = fma(-c.ER, 1.0 / consts[0], c.c0);
+        const volatile double *extra = tables() + PBU_MATH_TABLE_DOUBLES;      // (every kernel synchronises after block_init)
+        c.kA4 = extra[0];
+        c.kB3 = extra[1];
+        c.sixth = extra[2];
     }
     __device__ __forceinline__ static void seq_init(const Ctx &c, Seq &s, const double *) {
-        s.alpha = 0.0;
+        s.u = 1.0;
         s.y0 = c.y_start;
     }
-    // exp / log lookup tables of pbu_math.cuh, staged once per block (every kernel calls block_init before its first
-    // __syncthreads): 12 KB of static shared memory
-    // The two 4 KB tables start on a 4 KB boundary of the SHARED WINDOW (the 32-bit shared address, whatever offset the
-    // block's static segment has in it), found at run time inside a 12 KB array: a table address is then base | offset,
-    // which folds into the one LOP3 that masks the index (pbu_math.cuh), instead of mask + add.
+    // exp2 / log2 lookup tables of pbu_math.cuh, staged once per block (every kernel calls block_init before its first
+    // __syncthreads).  The 16 KB of tables start on an 8 KB boundary of the SHARED WINDOW (the 32-bit shared address,
+    // whatever offset the block's static segment has in it), found at run time inside a 24 KB array: a table address is
+    // then base | offset, which folds into the one LOP3 that masks the index (pbu_math.cuh), instead of mask + add.
     __device__ __forceinline__ static double *tables() {
-        __shared__ __align__(16) double raw[PBU_MATH_TABLE_DOUBLES + 512];
+        __shared__ __align__(16) double raw[PBU_MATH_TABLE_DOUBLES + PBU_MATH_EXTRA_DOUBLES + 1024];
         const uint32_t a = (uint32_t)__cvta_generic_to_shared(raw);
-        return raw + (((0u - a) & 4095u) >> 3);
+        return raw + (((0u - a) & 8191u) >> 3);
     }
     __device__ __forceinline__ static void block_init() {
         double *t = tables();
         for (int i = threadIdx.x; i < PBU_MATH_TABLE_DOUBLES; i += blockDim.x) t[i] = pbu_math_tables_dev[i];
+        if (threadIdx.x < PBU_MATH_EXTRA_DOUBLES) t[PBU_MATH_TABLE_DOUBLES + threadIdx.x] = pbu_math_extra_dev[threadIdx.x];
     }
     // One stage increment h g(T) u^n = 2^(y + n log2 u) with the table-driven pbu_exp2_tab / pbu_log2_tab (pbu_math.cuh):
-    // relative error below 2e-14 against exp() * pow() (tools/test_math.cu), far inside the 1e-10 parity bar, at 16 FP64
-    // instructions.  u <= 0 (conversion complete, or overshot by a stage), denormal or NaN u: 0 up to a denormal (hi word
-    // cleared).  The log of such an argument is finite garbage, discarded by the selection; no FP64 instruction is spent
-    // on the test.  A sum of exponents below -1022 (u -> 0) gives a denormal as well.
-    __device__ __forceinline__ static double stage(double y, double u, double n) {
-        return pbu_exp2_tab_sel(fma(n, pbu_log2_tab(u, tables()), y), tables(), pbu_log_arg_ok(u));
+    // relative error below 3e-14 against exp() * pow() (tools/test_math.cu), far inside the 1e-10 parity bar, at 14 FP64
+    // instructions.  u <= 0 (conversion complete, or overshot by a stage), denormal u: 0 up to a denormal.  The log of
+    // such an argument is finite garbage, discarded by the selection; no FP64 instruction is spent on the test.  A sum of
+    // exponents below -1022 (u -> 0) gives a denormal as well.
+    __device__ __forceinline__ static double stage(const Ctx &c, double y, double u) {
+        return pbu_exp2_tab_scaled_sel(fma(c.n, pbu_log2_tab(u, tables(), c.kA4), y), tables(), hi_word(u), c.kB3);
     }
-    // One RK4 step of d(alpha)/dT = g(T) (1 - alpha)^n.  Written on u = 1 - alpha for the stage arguments; this differs
-    // from the oracle's 1 - (alpha + k/2) by rounding only (<= 2 ulp of u), far inside the 1e-10 parity bar.
+    // One RK4 step of d(alpha)/dT = g(T) (1 - alpha)^n, carried on u = 1 - alpha (du/dT = -g u^n): this differs from the
+    // oracle's alpha + ... and 1 - (alpha + k/2) by rounding only (a few ulp of u), far inside the 1e-10 parity bar.
+    // Output 1 - F alpha = (1 - F) + F u.
     __device__ __forceinline__ static double step(const Ctx &c, Seq &s, double inv_mid, double inv_end) {
         const double ym = fma(-c.ER, inv_mid, c.c0);
         const double y1 = fma(-c.ER, inv_end, c.c0);
-        const double a = s.alpha;
-        const double u0 = 1.0 - a;
-        const double k1 = stage(s.y0, u0, c.n);
-        const double k2 = stage(ym, fma(-0.5, k1, u0), c.n);
-        const double k3 = stage(ym, fma(-0.5, k2, u0), c.n);
-        const double k4 = stage(y1, u0 - k3, c.n);
-        s.alpha = fma((k1 + k4) + 2.0 * (k2 + k3), 1.0 / 6.0, a);
+        const double u0 = s.u;
+        const double k1 = stage(c, s.y0, u0);
+        const double k2 = stage(c, ym, fma(-0.5, k1, u0));
+        const double k3 = stage(c, ym, fma(-0.5, k2, u0));
+        const double k4 = stage(c, y1, u0 - k3);
+        s.u = fma((k1 + k4) + 2.0 * (k2 + k3), c.sixth, u0);
         s.y0 = y1;
-        return fma(-c.F, s.alpha, 1.0);
+        return fma(c.F, s.u, c.omF);
     }
     template <int U>
     __device__ __forceinline__ static void resid_batch(const Ctx &c, Seq &s, const double (&rec)[U][NC], double (&t)[U]) {

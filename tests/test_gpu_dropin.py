@@ -310,3 +310,71 @@ def test_two_models_in_one_posterior_from_json(tmp_path, monkeypatch):
     assert abs(st["mean"][0] - 6.0) < 0.1 and abs(st["mean"][1] - 1.0e5) < 1500.0, st["mean"]
     # the two heating rates together pin the (log10A, E) ridge tighter than either alone would
     assert np.sqrt(st["cov"][0, 0]) < 0.05
+
+
+def test_reparametrised_model_with_fixed_parameter_and_map_from_json(tmp_path, monkeypatch):
+    """A user model with its own parametrization_* hooks (log sampling, bayesian_inference.py:314-336), one FIXED
+    parameter (d = 3 < P = 4, Model.run_model :351-366), estimate_max_distr and estimate_sigma, through
+    Sampling(json).sample(models): chain files in both spaces, MAP / sigma files (mha.py:332-355, solve_problem.py:90-111),
+    and the posterior of the linear-Gaussian problem in the MODEL space."""
+    from pybitup_b200 import synthetic, bayesian_inference as bi
+    from pybitup_b200.solve_problem import Sampling
+    monkeypatch.chdir(tmp_path)
+    p = synthetic.cubic_problem(n_points=400)
+    pd.DataFrame({"x": p["design"]["x"], "y": p["y"][0], "s": p["std_y"]}).to_csv("cubic.csv", index=False)
+
+    class CubicLog(bi.Model):           # as a user of the reference writes it: sample log(c) for the positive coefficients
+        device_model = "poly"
+
+        def parametrization_forward(self, X=1, P=1):
+            return np.log(X)
+
+        def parametrization_backward(self, Y=1, P=1):
+            return np.exp(Y)
+
+        def parametrization_det_jac(self, X=1):
+            return np.prod(1.0 / np.asarray(X))
+
+    names, vals = ["c0", "c1", "c2", "c3"], [1.0, -2.0, 0.5, 3.0]
+    unc = ["c0", "c2", "c3"]                                     # c1 stays at its nominal value
+    T = 3000
+    cfg = {"Sampling": {"BayesianPosterior": {
+        "Data": [{"Type": "ReadFromFile", "FileName": "cubic", "xField": ["x"], "yField": ["y"], "sigmaField": ["s"]}],
+        "Model": [{"param_names": names, "param_values": vals}],
+        "Prior": {"Distribution": "Mixture", "Param": {n: {"initial_val": vals[names.index(n)], "prior_name": "Uniform",
+                                                           "prior_param": [1e-3, 10]} for n in unc}},
+        "Likelihood": {"function": "Gaussian"}},
+        "Algorithm": {"name": "AMH", "AMH": {"starting_it": 100, "updating_it": 20, "eps_v": 1e-10}, "n_iterations": T,
+                      "n_chains": 128, "seed": 9, "save_eval_freq": 1e9, "save_all_chains": "yes", "estimate_max_distr": "yes",
+                      "estimate_sigma": "yes",
+                      "proposal": {"covariance": {"type": "diag", "value": [2e-5, 2e-4, 2e-5]}}}}}
+    with open("cubic.json", "w") as f:
+        json.dump(cfg, f)
+    job = Sampling("cubic.json")
+    run = job.sample({"cubic": CubicLog()})
+    job.close()
+    assert run.problem.param is not None and list(run.problem.param["kind"]) == [1, 1, 1] and list(run.problem.unc_idx) == [0, 2, 3]
+    X = pd.read_csv("output/mcmc_chain.csv", header=None).values
+    Y = pd.read_csv("output/mcmc_chain_reparam.csv", header=None).values
+    assert X.shape == (T + 1, 3) and np.allclose(X[0], [1.0, 0.5, 3.0]) and np.allclose(X, np.exp(Y), atol=2e-6)
+    # MAP files: arg max in the MODEL space, value = exp(log MAP) (mha.py:352-355)
+    arg_map = np.loadtxt("output/arg_MAP_estimation.csv", delimiter=",")
+    assert np.allclose(arg_map, np.exp(run.arg_MAP), atol=1e-6)
+    assert run.MAP_val >= run.MAP_val_all[0] - 1e-12 and run.arg_MAP_all.shape == (128, 3)
+    assert np.isclose(np.loadtxt("output/MAP_estimation.csv"), np.exp(run.MAP_val), atol=1e-6)
+    sig = pd.read_csv("output/estimated_sigma.csv")
+    assert np.allclose(sig["model_id"].values, 0.1)             # the unchanged std_y (SURVEY Q16)
+    # posterior in the model space: c1 fixed -> least squares of y + 2x on (1, x^2, x^3)
+    x = p["design"]["x"]
+    Phi = np.stack([np.ones_like(x), x ** 2, x ** 3], axis=1)
+    cov = np.linalg.inv(Phi.T @ Phi) * 0.1 ** 2
+    mean = cov @ Phi.T @ (p["y"][0] + 2.0 * x) / 0.1 ** 2
+    allc = np.exp(run.chains_all[T // 2:])                      # [T/2, d, C] in the model space
+    emp_mean = allc.mean(axis=(0, 2))
+    sd = np.sqrt(np.diag(cov))
+    assert np.all(np.abs(emp_mean - mean) < 0.15 * sd), (emp_mean, mean, sd)
+    emp_sd = np.sqrt(np.mean((allc - emp_mean[None, :, None]) ** 2, axis=(0, 2)))
+    assert np.all(np.abs(emp_sd / sd - 1.0) < 0.15), (emp_sd, sd)
+    # the device MAP is where the posterior density in Y peaks: prior(X) |dX/dY| like(X) -> close to the least-squares point
+    best = np.exp(run.arg_MAP_all[np.argmax(run.MAP_val_all)])
+    assert np.all(np.abs(best - mean) < 1.0 * sd)
