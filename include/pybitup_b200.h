@@ -309,6 +309,8 @@ int pbu_propagation_bracket_pass(pbu_propagation *p, const double *brackets_host
 int pbu_propagation_bracket_select_begin(pbu_propagation *p, const int64_t *ranks_in_bracket, const double *brackets_host, int *first_pass);
 /* evaluations of samples [s0, s0+n) on the host, sample-major [n][N] (fun_eval, :571) */
 int pbu_propagation_get_evals(pbu_propagation *p, int64_t s0, int64_t n, double *f_host);
+/* the samples [s0, s0+n) themselves, [n][d] on the host: the rows of eval_host, or those eval_gaussian drew (c_param, :559-565) */
+int pbu_propagation_get_samples(pbu_propagation *p, int64_t s0, int64_t n, double *X_host);
 
 /* ---- measurement helper: achieved FP64 FMA throughput of the device (TFLOP/s, FMA = 2 flops) from a
  *      register-resident DFMA loop; the denominator of the FP64 roofline in bench.py.  reps > 0: best of `reps`

@@ -124,6 +124,7 @@ def _load():
         "pbu_propagation_bracket_pass": (C.c_int, [E, _dp, C.c_int, C.c_int64, _dp, _dp, _dp, _lp, _lp, C.POINTER(C.c_int)]),
         "pbu_propagation_bracket_select_begin": (C.c_int, [E, _lp, _dp, C.POINTER(C.c_int)]),
         "pbu_propagation_get_evals": (C.c_int, [E, C.c_int64, C.c_int64, _dp]),
+        "pbu_propagation_get_samples": (C.c_int, [E, C.c_int64, C.c_int64, _dp]),
         "pbu_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp]),
     }
     for name, (res, args) in sig.items():

@@ -188,6 +188,23 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, double &z0, d
     z1 = (double)(s * __sinf(ang));
 }
 
+// The same from the top 24 bits of each word (exact int -> float conversions, no rounding that would look at the low byte):
+// the low bytes of the four words of one Philox block then make an independent 32-bit uniform (draw_philox for d = 3, 4).
+// The radius uniform has 24 bits: the normals are cut off at sqrt(-2 ln 2^-25) = 5.9 sigma (3.6e-9 of the mass).
+__device__ __forceinline__ void box_muller24(uint32_t a, uint32_t b, double &z0, double &z1) {
+    const float u = (float)(a >> 8) * 5.9604644775390625e-08f + 2.98023223876953125e-08f;    // (k + 1/2) 2^-24 in (0,1)
+    const float ang = (float)((int32_t)b >> 8) * 3.7450702829238284e-07f;                     // 2 pi k / 2^24 in [-pi, pi)
+    const float s = __fsqrt_rn(-1.3862943611198906f * __log2f(u));
+    z0 = (double)(s * __cosf(ang));
+    z1 = (double)(s * __sinf(ang));
+}
+// uniform in (0,1) with 32 random bits: the low bytes of four words
+__device__ __forceinline__ double uniform32_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    const uint32_t lo = __byte_perm(a, b, 0x0040), hi = __byte_perm(c, d, 0x0040);
+    const uint32_t bits = __byte_perm(lo, hi, 0x5410);
+    return fma((double)bits, 2.3283064365386963e-10, 1.1641532182693481e-10);                   // (k + 1/2) 2^-32
+}
+
 // uniform in (0,1) with 53 random bits
 __device__ __forceinline__ double uniform53(uint32_t a, uint32_t b) {
     uint64_t bits = ((uint64_t)a << 21) ^ (uint64_t)(b >> 11);   // 53 bits

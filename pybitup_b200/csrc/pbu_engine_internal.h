@@ -21,7 +21,7 @@ int pbu_fail(int code, const char *fmt, ...);
 
 // static shared memory a kernel may use besides the dynamic record tiles (the Arrhenius model's exp / log lookup
 // tables, pbu_math.cuh: 12,288 B with their alignment slack); taken off the opt-in maximum when the tiles are planned
-#define PBU_STATIC_SMEM_RESERVE 12800
+#define PBU_STATIC_SMEM_RESERVE 25600
 
 // chain slices of the moment reduction (pbu_moments.cu): partial sums [L][slices], added in slice order
 #define PBU_MOMENT_SLICES 64

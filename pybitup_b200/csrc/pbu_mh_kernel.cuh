@@ -366,6 +366,23 @@ __device__ __forceinline__ void log_posterior(const double (&yv)[Q][D], const bo
 // ------------------------------------------------------------------------------------------------
 template <int D>
 __device__ __forceinline__ void draw_philox(uint64_t seed, uint64_t chain, uint64_t it, uint32_t stage, double (&z)[D], double &u) {
+    if constexpr (D == 3 || D == 4) {
+        // ONE Philox4x32-10 block per proposal stage: two Box-Muller pairs from the top 24 bits of the four words, the
+        // acceptance uniform (32 bits) from their low bytes.  (Two blocks were a fifth of the instructions of a chain-step
+        // of the small linear model, BASELINE configuration 1.)
+        const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+        const uint4 ctr = make_uint4((uint32_t)chain, (uint32_t)it, (uint32_t)(it >> 32) ^ ((uint32_t)(chain >> 32) << 8) ^ (stage << 30), 0u);
+        const uint4 r = Philox::round10(ctr, key);
+        double a, b;
+        box_muller24(r.x, r.y, a, b);
+        z[0] = a;
+        z[1] = b;
+        box_muller24(r.z, r.w, a, b);
+        z[2] = a;
+        if constexpr (D == 4) z[3] = b;
+        u = uniform32_low_bytes(r.x, r.y, r.z, r.w);
+        return;
+    }
     constexpr int NPAIR = (D + 1) / 2;
     constexpr int NW = 2 * NPAIR + 2;
     constexpr int NB = (NW + 3) / 4;
@@ -769,19 +786,31 @@ __global__ void __launch_bounds__(256) eval_model_kernel(const __grid_constant__
     int b = 0, next = prob.blk[0].count;          // model blocks are contiguous point ranges: restart at each boundary
     begin_chain_block<M, D>(x, prob, 0, ctx, seq);
     ts.begin_pass(prob.raw, prob.n_points, tile_points);
+    const bool one_model = prob.n_blocks <= 1;      // (uniform) the common case pays nothing for the model boundaries
     for (int tl = 0; tl < n_tl; ++tl) {
         int cnt;
         const double *tile = ts.acquire(prob.n_points, tile_points, tl, cnt);
-        for (int k = 0; k < cnt; ++k) {
-            if (tl * tile_points + k == next) {
-                b += 1;
-                next += prob.blk[b].count;
-                begin_chain_block<M, D>(x, prob, b, ctx, seq);
+        double *out = f_out + (int64_t)(tl * tile_points) * S + t;
+        if (one_model) {
+#pragma unroll 2
+            for (int k = 0; k < cnt; ++k) {
+                double raw[M::NCR];
+                load_record<M::NCR>(tile, k, raw);
+                const double f = M::value(ctx, seq, raw);
+                if (livet) out[(int64_t)k * S] = f;
             }
-            double raw[M::NCR];
-            load_record<M::NCR>(tile, k, raw);
-            const double f = M::value(ctx, seq, raw);
-            if (livet) f_out[(int64_t)(tl * tile_points + k) * S + t] = f;
+        } else {
+            for (int k = 0; k < cnt; ++k) {
+                if (tl * tile_points + k == next) {
+                    b += 1;
+                    next += prob.blk[b].count;
+                    begin_chain_block<M, D>(x, prob, b, ctx, seq);
+                }
+                double raw[M::NCR];
+                load_record<M::NCR>(tile, k, raw);
+                const double f = M::value(ctx, seq, raw);
+                if (livet) out[(int64_t)k * S] = f;
+            }
         }
         ts.release(prob.raw, prob.n_points, tile_points, tl);
     }

@@ -843,3 +843,18 @@ PBU_API int pbu_propagation_get_evals(pbu_propagation *p, int64_t s0, int64_t n,
         for (int k = 0; k < p->N; ++k) f_host[(size_t)s * p->N + k] = pm[(size_t)k * n + s];
     return PBU_OK;
 }
+
+// the samples themselves (the rows handed to eval_host, or drawn on the device by eval_gaussian), [n][d] on the host
+PBU_API int pbu_propagation_get_samples(pbu_propagation *p, int64_t s0, int64_t n, double *X_host) {
+    if (!p || !p->evaluated || s0 < 0 || n < 1 || s0 + n > p->S || !X_host) return fail(PBU_ERR_INVALID, "bad argument");
+    pbu_engine *e = p->e;
+    CUDA_TRY(cudaSetDevice(e->device));
+    const int d = e->d;
+    std::vector<double> pm((size_t)d * n);
+    CUDA_TRY(cudaMemcpy2DAsync(pm.data(), (size_t)n * sizeof(double), p->d_X + s0, (size_t)p->S * sizeof(double), (size_t)n * sizeof(double), d,
+                               cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    for (int64_t s = 0; s < n; ++s)
+        for (int i = 0; i < d; ++i) X_host[(size_t)s * d + i] = pm[(size_t)i * n + s];
+    return PBU_OK;
+}

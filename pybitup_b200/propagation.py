@@ -70,6 +70,14 @@ class DevicePropagation:
         std = np.ascontiguousarray(np.asarray(std, dtype=np.float64))
         capi.check(capi.lib.pbu_propagation_eval_gaussian(self._h, capi.dptr(mean), capi.dptr(std), int(seed), int(sample_offset)))
 
+    def samples(self, first=0, count=None):
+        """Rows [first, first + count) of the samples the evaluations belong to, [count, d] on the host: the rows handed
+        to ``evaluate`` or drawn on the device by ``evaluate_gaussian``."""
+        count = self.n_samples - first if count is None else count
+        out = np.empty((count, self.engine.d))
+        capi.check(capi.lib.pbu_propagation_get_samples(self._h, int(first), int(count), capi.dptr(out)))
+        return out
+
     def evals(self, first=0, count=None):
         count = self.n_samples - first if count is None else count
         out = np.empty((count, self.n_points))

@@ -240,6 +240,11 @@ def test_cfg5_full_size_propagation():
             st = dp.statistics()
             head = dp.evals(0, 20000)
             tail = dp.evals(S - 3, 3)
+            # sample rows against the oracle: the parameters the device drew, pushed through the CPU model
+            for s0 in (0, 4999999, S - 40):
+                Xs = dp.samples(s0, 40)
+                assert np.all(np.abs(Xs / mean - 1.0) < 0.08) and len(np.unique(Xs[:, 0])) == 40
+                assert H.rel_err(dp.evals(s0, 40), orc.propagate(prob, Xs)["fun_eval"]) < 1e-11
         # the same Philox samples in a small object: sample s does not depend on the launch it is drawn in
         with DevicePropagation(eng, 20000) as dp:
             dp.evaluate_gaussian(mean, std, seed=0, sample_offset=0)
