@@ -202,7 +202,8 @@ def cpu_baseline_leg():
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-FP64_INST_RK4 = 77           # FP64 instructions of one RK4 step of the Arrhenius kernels (cuobjdump -sass)
+FP64_INST_RK4 = 68.5         # FP64 instructions of one RK4 step of the Arrhenius kernels (137 per two steps, cuobjdump -sass)
+OTHER_INST_RK4 = 66.5        # the other instructions of that step: an FP64 instruction holds the issue port for two cycles, these for one
 
 
 def _finite(o):
@@ -290,8 +291,12 @@ def measure_configs(rank, local_rank, world, red, fp64_peak, hbm_peak, barrier, 
                     "roofline": {"bound": "fp64", "achieved": tf_alg, "peak": fp64_peak, "unit": "TFLOP/s", "frac": frac(tf_alg),
                                  "flops_per_evaluation": 2.17e4,
                                  "fp64_issue": {"achieved": tf_issue, "frac": frac(tf_issue), "fp64_inst_per_rk4_step": FP64_INST_RK4,
+                                                "other_inst_per_rk4_step": OTHER_INST_RK4,
+                                                "issue_slot_bound_frac": 2 * FP64_INST_RK4 / (2 * FP64_INST_RK4 + OTHER_INST_RK4),
                                                 "note": "FP64 instructions the kernel issues, each counted as an FMA (2 flops): what the pipe "
-                                                        "is busy with; the algorithmic count takes exp / pow as 1 flop each"}}}
+                                                        "is busy with; the algorithmic count takes exp / pow as 1 flop each.  "
+                                                        "issue_slot_bound_frac is the most this instruction mix can reach "
+                                                        "(2 issue cycles per FP64 instruction, 1 per other)"}}}
     if "4" in which:
         p = synthetic.regression_problem()
         C, T = 131072, 4

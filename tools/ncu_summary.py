@@ -16,6 +16,8 @@ KEYS = [
     "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum", "sm__cycles_elapsed.max", "sm__cycles_active.avg",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__cycles_active.avg",
     "smsp__average_warp_latency_per_inst_issued.ratio", "smsp__average_warps_issue_stalled",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared", "smsp__inst_executed_op_shared_ld.sum", "sm__inst_executed_pipe_xu",
+    "sm__inst_executed_pipe_alu", "sm__inst_executed_pipe_fma", "smsp__inst_executed_pipe_fp64", "sm__inst_executed.avg.per_cycle_elapsed",
 ]
 
 
