@@ -282,12 +282,16 @@ def measure_configs(rank, local_rank, world, red, fp64_peak, hbm_peak, barrier, 
                 eng.run(T, thin=T, keep_samples=False)
                 ms = _timed(lambda: eng.run(T, thin=T, keep_samples=False), 3, barrier, max_over_ranks, flush)
                 ev = float(eng.read_state()["n_eval"].mean()) / eng.iteration
+                # speculative delayed rejection (two lanes per chain): both stages are evaluated every step, the second one
+                # for nothing when the first proposal is accepted; n_eval counts what the reference would have evaluated
+                ev_run = 2.0 if eng.launch_geometry()["lanes"] == 2 else ev
                 r = world * C * T / (ms * 1e-3)
                 tf_alg = r / world * ev * 2.17e4 / 1e12
-                tf_issue = r / world * ev * 500 * FP64_INST_RK4 * 2 / 1e12
+                tf_issue = r / world * ev_run * 500 * FP64_INST_RK4 * 2 / 1e12
                 out["cfg3" if mode == "weak" else "cfg3_strong"] = {
                     "workload": "Arrhenius pyrolysis ODE (RK4 x 500), d=4, DRAM, %d chains per GPU (%d in all) x %d iterations" % (C, world * C, T),
-                    "scaling": mode, "ms": ms, "chain_steps_per_s": r, "evals_per_chain_step": ev, "launch": eng.launch_geometry(),
+                    "scaling": mode, "ms": ms, "chain_steps_per_s": r, "evals_per_chain_step": ev, "evals_executed_per_chain_step": ev_run,
+                    "launch": eng.launch_geometry(),
                     "roofline": {"bound": "fp64", "achieved": tf_alg, "peak": fp64_peak, "unit": "TFLOP/s", "frac": frac(tf_alg),
                                  "flops_per_evaluation": 2.17e4,
                                  "fp64_issue": {"achieved": tf_issue, "frac": frac(tf_issue), "fp64_inst_per_rk4_step": FP64_INST_RK4,

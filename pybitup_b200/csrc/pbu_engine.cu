@@ -241,7 +241,10 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
         if (coop && e->prob.n_blocks > 1) continue;          // the cooperative kernel evaluates one model
         if (want_lanes > 0 && g != want_lanes) continue;
         if (want_q > 0 && q != want_q) continue;
-        if (sequential && g != 1) continue;
+        // sequential (ODE) models: one lane per chain -- or, for delayed rejection, a pair of lanes that evaluates both
+        // proposal stages at once (speculative delayed rejection, pbu_mh_kernel.cuh)
+        const bool delayed = algo == PBU_ALGO_DR || algo == PBU_ALGO_DRAM;
+        if (sequential && !(g == 1 || (g == 2 && q == 1 && delayed && !mixed && !coop))) continue;
         if (mixed && (isde || streamed || (!force && (want_block > 0 || want_lanes > 0)))) continue;
         // delayed rejection: the second stage runs for a thread when ANY of its chains was rejected, so pairing
         // chains wastes evaluations; one chain per thread unless asked otherwise
@@ -275,7 +278,12 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
         const double conflict = (g >= 8 && (e->ev->nc / 2) % 2 == 0) ? 1.1 : 1.0;
         // per thread of a warp: every lane evaluates q chains on its share of the points; the scalar part is done for q chains
         // per lane in the replicated layout and for one chain per lane in the cooperative one
-        const double work = q * (sequential ? N : std::ceil(N / g)) * ops * conflict + (coop ? 1.0 : (double)q) * S0;
+        // passes of a sequential model over its points per delayed-rejection step: with one lane per chain a warp walks the
+        // points a second time as soon as ONE of its 32 chains was rejected at the first stage (practically always); the
+        // speculative pair does one pass for its 16 chains.  Equal work per chain at full occupancy -- measured 5 % in favour
+        // of the pair at 262,144 chains (tools/exp_block.py), 1.7x at 32,768 -- so the pair is preferred throughout.
+        const double evals = (sequential && delayed) ? ((g == 2) ? 0.95 : 2.0) : 1.0;
+        const double work = q * (sequential ? N : std::ceil(N / g)) * ops * conflict * evals + (coop ? 1.0 : (double)q) * S0;
         for (int B = MH_MAX_BLOCK; B >= 32; B -= 32) {
             if (want_block > 0 && B != want_block) continue;
             // cooperative kernels park the own chain's state (x, y, lp, mean_r, u: 2d + 3 doubles per thread, component stride

@@ -25,6 +25,10 @@
         PBU_MH_ALGOS(MODEL, P, D, 8, 1, 1), PBU_MH_MIXED(MODEL, P, D, 2, 2, 0), PBU_MH_MIXED(MODEL, P, D, 2, 2, 1),     \
         PBU_MH_COOP_ALGOS(MODEL, P, D, 4, 0), PBU_MH_COOP_ALGOS(MODEL, P, D, 4, 1)
 #define PBU_MH_SEQ(MODEL, P, D) PBU_MH_ALGOS(MODEL, P, D, 1, 1, 0), PBU_MH_ALGOS(MODEL, P, D, 1, 1, 1)
+// sequential (ODE) models, delayed rejection: pairs of lanes evaluate both proposal stages of a chain at once
+// (speculative delayed rejection, pbu_mh_kernel.cuh)
+#define PBU_MH_SEQ_SPEC(MODEL, P, D) \
+    PBU_MH(MODEL, P, D, 2, 1, 2, 0), PBU_MH(MODEL, P, D, 2, 1, 3, 0), PBU_MH(MODEL, P, D, 2, 1, 2, 1), PBU_MH(MODEL, P, D, 2, 1, 3, 1)
 // Ito-SDE step kernel variants (lanes per chain, chains per thread, streamed)
 #define PBU_ISDE(MODEL, P, D, G, Q, S) \
     { MODEL::ID, P, D, G, Q, MODEL::HAS_GRAD ? 1 : 0, S, (const void *)&pbu::isde_step_kernel<MODEL, D, G, Q, (S != 0)> }

@@ -442,6 +442,29 @@ __device__ __forceinline__ bool draw_injected(const StreamsDev &s, int64_t c, bo
     return ok;
 }
 
+// The same without advancing the cursors, `ahead` proposal stages past them (speculative delayed rejection: both stages'
+// draws are looked at before it is known whether the second is consumed; advance_injected then moves the cursors by the
+// number of stages the reference would have drawn).
+template <int D>
+__device__ __forceinline__ bool peek_injected(const StreamsDev &s, int64_t c, bool live, int ahead, double (&z)[D], double &u) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) z[i] = 0.0;
+    u = 1.0;
+    if (!live) return true;
+    const int64_t cn = s.cur_n[c] + (int64_t)ahead * D, cu = s.cur_u[c] + ahead;
+    if (cn + D > s.n_normals || cu + 1 > s.n_uniforms) return false;
+    const double *zn = s.normals + c * s.n_normals + cn;
+#pragma unroll
+    for (int i = 0; i < D; ++i) z[i] = zn[i];
+    u = s.uniforms[c * s.n_uniforms + cu];
+    return true;
+}
+template <int D>
+__device__ __forceinline__ void advance_injected(const StreamsDev &s, int64_t c, int stages) {
+    s.cur_n[c] += (int64_t)stages * D;
+    s.cur_u[c] += stages;
+}
+
 // ------------------------------------------------------------------------------------------------
 // The kernel.  ALGO = pbu_algo_id of the MH family: bit 0 adaptive (AM, DRAM), bit 1 delayed
 // rejection (DR, DRAM).  Q = chains per thread; thread group g owns chains g, g + n_groups, ...
@@ -450,6 +473,14 @@ template <class M, int D, int G, int ALGO, int Q, bool STREAM>
 __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::NC> &ts, const int64_t group, const int sub) {
     constexpr bool ADAPT = (ALGO & 1) != 0;
     constexpr bool DELAYED = (ALGO & 2) != 0;
+    // SPECULATIVE DELAYED REJECTION (sequential models, two lanes per chain).  The points of an ODE model cannot be split
+    // over lanes, so few chains leave the GPU latency-bound (one serial RK4 recurrence per thread).  But the second-stage
+    // proposal x + gamma R z2 (mha.py:543) does not depend on the OUTCOME of the first stage: lane 0 of a chain's pair
+    // evaluates the first proposal while lane 1 evaluates the second, in the same pass over the points; the acceptance
+    // logic then runs as written, on values that are already there.  Philox draws are keyed by (chain, iteration, stage)
+    // and injected draws are consumed as the reference consumes them, so the chains are those of the one-lane kernel: the
+    // second evaluation is wasted when the first proposal is accepted, and a chain-step costs ONE evaluation time, not 1.9.
+    constexpr bool SPEC = M::SEQUENTIAL && DELAYED && (G == 2);
     constexpr int NT = tri_size(D);
     const int64_t C = p.st.n_chains;
     const int lane = threadIdx.x & 31;
@@ -503,12 +534,59 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
             alpha[q] = 0.0;
             u[q] = 1.0;
         }
+        double ysp[SPEC ? 2 : 1][SPEC ? Q : 1][SPEC ? D : 1], usp[SPEC ? 2 : 1][SPEC ? Q : 1], lpsp[SPEC ? 2 : 1][SPEC ? Q : 1];
+        if constexpr (SPEC) {
+            double ysel[Q][D], lps[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+#pragma unroll
+                for (int st = 0; st < 2; ++st) {
+                    double z[D];
+                    usp[st][q] = 1.0;
+                    if (injected) {
+                        // the second stage's draws may lie past the end of the streams when the first stage accepts: only an
+                        // exhausted stage that is actually consumed counts (flagged below)
+                        if (!peek_injected<D>(p.streams, c[q], live[q], st, z, usp[st][q])) usp[st][q] = -1.0;
+                    } else {
+                        draw_philox<D>(p.seed, p.chain_offset + (uint64_t)c[q], (uint64_t)it, (uint32_t)st, z, usp[st][q]);
+                    }
+                    double sj[D];
+                    upper_matvec<D>([&](int i, int j) { return ADAPT ? p.st.R[(int64_t)tri_idx(D, i, j) * C + c[q]] : p.R0[tri_idx(D, i, j)]; }, z, sj);
+                    const double scale = (st == 0) ? 1.0 : p.gamma_dr;
+#pragma unroll
+                    for (int i = 0; i < D; ++i) ysp[st][q][i] = __dadd_rn(x[q][i], __dmul_rn(scale, sj[i]));
+                }
+#pragma unroll
+                for (int i = 0; i < D; ++i) ysel[q][i] = (sub == 0) ? ysp[0][q][i] : ysp[1][q][i];
+            }
+            __syncwarp(group_mask);       // both lanes have read the stream cursors before the writer lane moves them
+            // each lane evaluates ITS proposal over all points (no lane splitting: lanes-per-chain 1 inside the evaluation)
+            log_posterior<M, D, 1, Q, STREAM>(ysel, want, p.prob, ts, p.tile_points, 0, 1u << lane, lps);
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                lpsp[0][q] = __shfl_sync(group_mask, lps[q], lane_chain<G>(lane));
+                lpsp[1][q] = __shfl_sync(group_mask, lps[q], lane_chain<G>(lane) + 32 / G);
+            }
+        }
 #pragma unroll 1
         for (int stage = 0; stage < (DELAYED ? 2 : 1); ++stage) {
             const double scale = (stage == 0) ? 1.0 : p.gamma_dr;
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 if (!want[q]) continue;
+                if constexpr (SPEC) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) y[q][i] = (stage == 0) ? ysp[0][SPEC ? q : 0][SPEC ? i : 0] : ysp[SPEC ? 1 : 0][SPEC ? q : 0][SPEC ? i : 0];
+                    u[q] = (stage == 0) ? usp[0][SPEC ? q : 0] : usp[SPEC ? 1 : 0][SPEC ? q : 0];
+                    if (u[q] < 0.0) {             // the injected streams ended before this stage
+                        status[q] |= ST_STREAM_EXHAUSTED;
+#pragma unroll
+                        for (int i = 0; i < D; ++i) y[q][i] = x[q][i];
+                        u[q] = 1.0;
+                    }
+                    n_eval[q] += 1;
+                    continue;
+                }
                 double z[D];
                 if (injected) {
                     if (!draw_injected<D>(p.streams, c[q], live[q], live[q] && sub == 0, group_mask, z, u[q])) status[q] |= ST_STREAM_EXHAUSTED;
@@ -522,7 +600,12 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
                 for (int i = 0; i < D; ++i) y[q][i] = __dadd_rn(x[q][i], __dmul_rn(scale, sj[i]));
                 n_eval[q] += 1;
             }
-            log_posterior<M, D, G, Q, STREAM>(y, want, p.prob, ts, p.tile_points, sub, group_mask, lpy);
+            if constexpr (SPEC) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q) lpy[q] = (stage == 0) ? lpsp[0][SPEC ? q : 0] : lpsp[SPEC ? 1 : 0][SPEC ? q : 0];
+            } else {
+                log_posterior<M, D, G, Q, STREAM>(y, want, p.prob, ts, p.tile_points, sub, group_mask, lpy);
+            }
             bool again = false;
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
@@ -576,8 +659,17 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
                     want[q] = false;
                 }
             }
-            if (STREAM) again = __syncthreads_or(again) != 0;     // streaming: the block walks the tiles together
+            if (STREAM && !SPEC) again = __syncthreads_or(again) != 0;     // streaming: the block walks the tiles together
             if (!again) break;
+        }
+        if constexpr (SPEC) {
+            // injected streams: the reference drew for one stage, or for two when the first proposal was rejected
+            if (injected) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q)
+                    if (live[q] && sub == 0) advance_injected<D>(p.streams, c[q], acc[q] == 1 ? 1 : 2);
+                __syncwarp(group_mask);
+            }
         }
 
         const bool refresh = ADAPT && (--to_refresh == 0);          // it % updating_it == 0  (:470)

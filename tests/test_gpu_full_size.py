@@ -175,6 +175,20 @@ def test_cfg3_full_size_arrhenius_dram():
         eng.init_chains(x0[first:first + 96], p["prop_cov"])
         eng.run(T, keep_samples=False)
         assert H.rel_err(eng.state()[0], whole[first:first + 96]) < 1e-9
+    # speculative delayed rejection (a pair of lanes per chain evaluates both stages at once; what the planner picks for a
+    # latency-bound share such as 32,768 chains per GPU): the SAME chains as the one-lane kernel, Philox being keyed by
+    # (chain, iteration, stage), and the same evaluation counts as the reference would report
+    Cs = 32768
+    with _mk(p, "DRAM", Cs, seed=5, chain_offset=first, **kw) as eng:
+        assert eng.launch_geometry()["lanes"] == 2
+        eng.init_chains(x0[first:first + Cs], p["prop_cov"])
+        eng.run(T, keep_samples=False)
+        assert H.rel_err(eng.state()[0], whole[first:first + Cs]) < 1e-9
+        ev2 = eng.counters()["n_eval"]
+    with _mk(p, "DRAM", Cs, seed=5, chain_offset=first, lanes_per_chain=1, **kw) as eng:
+        eng.init_chains(x0[first:first + Cs], p["prop_cov"])
+        eng.run(T, keep_samples=False)
+        assert np.array_equal(eng.counters()["n_eval"], ev2)
 
 
 # ------------------------------------------------------------------------------------------------ cfg 4

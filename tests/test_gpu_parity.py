@@ -48,8 +48,8 @@ def test_mh_golden_parity(case, lanes):
     """CUDA engine vs the recorded reference run, fed the same streams.  lanes < 0: cooperative teams of -lanes lanes."""
     g = H.load_golden(case)
     algo = g["algo"]
-    if g["model"] == "arrhenius" and lanes != 1:
-        pytest.skip("sequential ODE model: one lane per chain")
+    if g["model"] == "arrhenius" and not (lanes == 1 or (lanes == 2 and algo["name"] in ("DR", "DRAM"))):
+        pytest.skip("sequential ODE model: one lane per chain (or the speculative pair of delayed rejection)")
     if "n_models" in g and lanes < 0:
         pytest.skip("several models per likelihood run in the replicated layout (the cooperative kernel is single-model)")
     if g["model"] in ("linear", "poly") and len(g["unc_idx"]) < len(g["theta_nom"]) and lanes != 1:
@@ -99,10 +99,13 @@ def test_mh_golden_parity(case, lanes):
 @pytest.mark.parametrize("algo_name", ["RWMH", "AMH", "DR", "DRAM"])
 @pytest.mark.parametrize("builder,lanes", [("linear_problem", 1), ("linear_problem", 8), ("cubic_problem", 2),
                                            ("heat_problem", 1), ("arrhenius_problem", 1), ("cubic_problem", -4),
-                                           ("linear_problem", -4), ("heat_problem", -4)])
+                                           ("linear_problem", -4), ("heat_problem", -4), ("arrhenius_problem", 2)])
 def test_many_chains_vs_oracle(builder, lanes, algo_name):
-    """64 different chains (own start, own streams) against the CPU oracle, chain by chain."""
+    """64 different chains (own start, own streams) against the CPU oracle, chain by chain.  (arrhenius, 2): speculative
+    delayed rejection -- a pair of lanes evaluates both proposal stages of a chain at once."""
     from pybitup_b200 import synthetic
+    if builder == "arrhenius_problem" and lanes == 2 and algo_name not in ("DR", "DRAM"):
+        pytest.skip("the two-lane layout of a sequential model is the speculative delayed rejection")
     kwargs = {"linear_problem": {}, "cubic_problem": {"n_points": 257}, "heat_problem": {},
               "arrhenius_problem": {"n_steps": 40, "dT": 15.0}}[builder]
     p = getattr(synthetic, builder)(**kwargs)
