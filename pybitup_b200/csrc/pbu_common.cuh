@@ -117,6 +117,9 @@ struct MhParams {
     int32_t state_smem_off;   // cooperative adaptive kernels: byte offset of the per-thread (V_i, X_av, R) block in shared
                               // memory, 0 = the adaptive state stays in global memory
     int32_t groups_per_block; // mixed kernels: chain groups per block
+    int32_t stagger_cycles;   // > 0: the warps that share a scheduler start this many cycles apart (pbu_mh_coop.cuh), so that the
+                              // scalar phase of one overlaps the data loops of the others instead of all four idling the pipe together
+    int32_t pad_stagger;
     double R0[PBU_MAX_DIM * (PBU_MAX_DIM + 1) / 2];   // packed upper Cholesky factor shared by all chains (non-adaptive samplers)
 };
 

@@ -328,6 +328,10 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
                     e->grid = (int)blocks;
                     e->n_full_warps = mixed ? nfull : 0;
                     e->groups_per_block = gpb;
+                    // a warp's own FP64 pipe time per iteration (two cycles per DFMA-equivalent) = a quarter of the iteration of
+                    // four warps sharing a scheduler: the start offset that spreads their scalar phases evenly
+                    e->stagger_cycles = (coop && W >= 8 && !tiny) ? (int)std::min(2.0 * work, 1.0e6) : 0;
+                    if (const char *sv = getenv("PBU_STAGGER")) e->stagger_cycles = coop ? atoi(sv) : 0;      // diagnostics
                     e->state_smem_off = state_off;
                     e->launch_smem = smem_launch;
                     found = true;
@@ -854,6 +858,7 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine 
     p.n_groups = (int64_t)e->grid * e->groups_per_block;
     p.n_full_warps = e->n_full_warps;
     p.groups_per_block = e->groups_per_block;
+    p.stagger_cycles = e->stagger_cycles;
     p.state_smem_off = e->state_smem_off;
     for (size_t i = 0; i < e->R0.size(); ++i) p.R0[i] = e->R0[i];
     void *args[] = {(void *)&p};

@@ -46,6 +46,7 @@ struct pbu_engine {
     int q = 1;                    // chains per thread
     int n_full_warps = 0;         // mixed kernels: warps per block with `lanes` lanes per chain, the rest use 2 * lanes
     int groups_per_block = 0;     // chain groups (G-lane teams) per block
+    int stagger_cycles = 0;       // cooperative kernels: start offset between the warps of one scheduler (a quarter iteration)
     int state_smem_off = 0;       // cooperative adaptive kernels: offset of the per-thread adaptive state in shared memory
     size_t launch_smem = 0;       // dynamic shared memory of the planned step kernel (records + staged state)
     int block = 128;

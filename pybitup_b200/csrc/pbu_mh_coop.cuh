@@ -336,6 +336,17 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, M::MIN_BLOCKS) mh_coop_kernel(co
     ts.init(p.prob.records, p.prob.n_points, p.tile_points);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    // Phase stagger.  Every warp alternates a long data loop (the FP64 pipe at its throttle) with a scalar phase of ~1,200
+    // mostly dependent instructions (draws, exp, adaptation, global loads) during which it issues almost no DFMA.  Warps of a
+    // block start together and take equally long per iteration, so the four warps a scheduler holds would go through their
+    // scalar phases TOGETHER and leave the pipe idle; started a quarter of an iteration apart they stay that way for the
+    // whole launch, and one warp's scalar phase hides behind the other three's loops.
+    if (p.stagger_cycles > 0) {
+        const long long wait = (long long)((warp >> 2) & 3) * p.stagger_cycles;      // warps w, w+4, w+8, w+12 share a scheduler
+        const long long t0 = clock64();
+        while (clock64() - t0 < wait) {
+        }
+    }
     if constexpr (!MIXED) {
         const int64_t warp_g = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
         mh_coop_loop<M, D, G, G, ALGO, STREAM>(p, ts, warp_g * (32 / G) + lane_chain<G>(lane), lane_sub<G>(lane));
