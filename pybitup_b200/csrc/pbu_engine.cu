@@ -250,7 +250,10 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
         // chains wastes evaluations; one chain per thread unless asked otherwise
         if ((algo == PBU_ALGO_DR || algo == PBU_ALGO_DRAM) && q != 1 && !coop && want_q <= 0 && want_lanes <= 0) continue;
         // wide states spill heavily with two chains per thread
-        if (e->d > 6 && q != 1 && ((coop && want_coop <= 0) || (!coop && want_q <= 0 && want_lanes <= 0))) continue;
+        // (the streamed Ito-SDE / HMC pass with one lane per chain is the exception: its loop waits on the record loads, which
+        // two chains per thread halve per FMA -- 9.8 against 10.5 ms at BASELINE configuration 4, spills and all)
+        if (e->d > 6 && q != 1 && !(isde && streamed && g == 1) &&
+            ((coop && want_coop <= 0) || (!coop && want_q <= 0 && want_lanes <= 0))) continue;
         const void *fn = nullptr;
         const MhKernelEntry *km = nullptr;
         const IsdeKernelEntry *ki = nullptr;

@@ -29,12 +29,14 @@
 // (speculative delayed rejection, pbu_mh_kernel.cuh)
 #define PBU_MH_SEQ_SPEC(MODEL, P, D) \
     PBU_MH(MODEL, P, D, 2, 1, 2, 0), PBU_MH(MODEL, P, D, 2, 1, 3, 0), PBU_MH(MODEL, P, D, 2, 1, 2, 1), PBU_MH(MODEL, P, D, 2, 1, 3, 1)
-// Ito-SDE step kernel variants (lanes per chain, chains per thread, streamed)
+// Ito-SDE step kernel variants (lanes per chain, chains per thread, streamed).  (1, 2, streamed): every record read from the
+// tile ring feeds two chains -- the layout of BASELINE configuration 4 when there are enough chains to fill the GPU
 #define PBU_ISDE(MODEL, P, D, G, Q, S) \
     { MODEL::ID, P, D, G, Q, MODEL::HAS_GRAD ? 1 : 0, S, (const void *)&pbu::isde_step_kernel<MODEL, D, G, Q, (S != 0)> }
 #define PBU_ISDE_ALL(MODEL, P, D)                                                                                   \
     PBU_ISDE(MODEL, P, D, 1, 1, 0), PBU_ISDE(MODEL, P, D, 1, 2, 0), PBU_ISDE(MODEL, P, D, 2, 2, 0), PBU_ISDE(MODEL, P, D, 4, 1, 0), \
-        PBU_ISDE(MODEL, P, D, 8, 1, 0), PBU_ISDE(MODEL, P, D, 1, 1, 1), PBU_ISDE(MODEL, P, D, 4, 1, 1), PBU_ISDE(MODEL, P, D, 8, 1, 1)
+        PBU_ISDE(MODEL, P, D, 8, 1, 0), PBU_ISDE(MODEL, P, D, 1, 1, 1), PBU_ISDE(MODEL, P, D, 4, 1, 1), PBU_ISDE(MODEL, P, D, 8, 1, 1), \
+        PBU_ISDE(MODEL, P, D, 1, 2, 1)
 #define PBU_ISDE_SEQ(MODEL, P, D) PBU_ISDE(MODEL, P, D, 1, 1, 0), PBU_ISDE(MODEL, P, D, 1, 1, 1)
 // Hamiltonian Monte Carlo step kernel variants (same table type as ISDE; `kind` 1)
 #define PBU_HMC(MODEL, P, D, G, Q, S) \
