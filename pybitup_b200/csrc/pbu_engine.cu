@@ -101,12 +101,12 @@ static const MhKernelEntry *find_mh(int model, int P, int d, int lanes, int q, i
             return &t[i];
     return nullptr;
 }
-static const IsdeKernelEntry *find_isde(int model, int P, int d, int lanes, int q, int streamed) {
+static const IsdeKernelEntry *find_isde(int model, int P, int d, int lanes, int q, int streamed, int mixed = 0) {
     int n = 0;
     const IsdeKernelEntry *t = pbu_isde_kernels(&n);
     for (int i = 0; i < n; ++i)
         if (t[i].model == model && t[i].n_param == P && t[i].n_unc == d && t[i].lanes == lanes && t[i].chains_per_thread == q &&
-            t[i].streamed == streamed)
+            t[i].streamed == streamed && t[i].mixed == mixed)
             return &t[i];
     return nullptr;
 }
@@ -216,8 +216,8 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
     const double S0 = 60.0 + 15.0 * e->d;           // per-iteration scalar part (RNG, proposal, accept, adaptation), in DFMA-equivalents
     // (lanes, chains per thread or per team, mixed, coop): mixed = the last warps of a block use twice the lanes;
     // coop = teams of `lanes` lanes own `lanes` chains (pbu_mh_coop.cuh)
-    const int cand[10][4] = {{1, 1, 0, 0}, {1, 2, 0, 0}, {2, 2, 0, 0}, {2, 2, 1, 0}, {4, 2, 0, 0}, {2, 1, 0, 0}, {4, 1, 0, 0}, {8, 1, 0, 0},
-                             {4, 4, 0, 1}, {4, 4, 1, 1}};
+    const int cand[11][4] = {{1, 1, 0, 0}, {1, 2, 0, 0}, {2, 2, 0, 0}, {2, 2, 1, 0}, {4, 2, 0, 0}, {2, 1, 0, 0}, {4, 1, 0, 0}, {8, 1, 0, 0},
+                             {4, 4, 0, 1}, {4, 4, 1, 1}, {1, 2, 1, 0}};
     const char *force = getenv("PBU_FORCE_VARIANT");      // "lanes,q,mixed,coop": diagnostics
     const bool hmc = algo == PBU_ALGO_HMC;
     const bool isde = algo == PBU_ALGO_ISDE || hmc;
@@ -245,20 +245,21 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
         // proposal stages at once (speculative delayed rejection, pbu_mh_kernel.cuh)
         const bool delayed = algo == PBU_ALGO_DR || algo == PBU_ALGO_DRAM;
         if (sequential && !(g == 1 || (g == 2 && q == 1 && delayed && !mixed && !coop))) continue;
-        if (mixed && (isde || streamed || (!force && (want_block > 0 || want_lanes > 0)))) continue;
+        // mixed warp widths: the resident replicated / cooperative MH kernels, and the streamed Ito-SDE pass (not HMC)
+        if (mixed && ((isde && (hmc || !streamed)) || (!isde && streamed) || (!force && (want_block > 0 || want_lanes > 0)))) continue;
         // delayed rejection: the second stage runs for a thread when ANY of its chains was rejected, so pairing
         // chains wastes evaluations; one chain per thread unless asked otherwise
         if ((algo == PBU_ALGO_DR || algo == PBU_ALGO_DRAM) && q != 1 && !coop && want_q <= 0 && want_lanes <= 0) continue;
         // wide states spill heavily with two chains per thread
         // (the streamed Ito-SDE / HMC pass with one lane per chain is the exception: its loop waits on the record loads, which
         // two chains per thread halve per FMA -- 9.8 against 10.5 ms at BASELINE configuration 4, spills and all)
-        if (e->d > 6 && q != 1 && !(isde && streamed && g == 1) &&
+        if (e->d > 6 && q != 1 && !(isde && streamed && g == 1) && !(force != nullptr) &&
             ((coop && want_coop <= 0) || (!coop && want_q <= 0 && want_lanes <= 0))) continue;
         const void *fn = nullptr;
         const MhKernelEntry *km = nullptr;
         const IsdeKernelEntry *ki = nullptr;
         if (isde) {
-            ki = hmc ? find_hmc(model, e->P, e->d, g, q, streamed) : find_isde(model, e->P, e->d, g, q, streamed);
+            ki = hmc ? find_hmc(model, e->P, e->d, g, q, streamed) : find_isde(model, e->P, e->d, g, q, streamed, mixed);
             if (ki) fn = ki->fn;
         } else {
             km = find_mh(model, e->P, e->d, g, q, algo, streamed, mixed, coop);
@@ -827,6 +828,8 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine 
         q.end_it = e->cfg.adapt_end > 0 ? e->cfg.adapt_end : INT64_MAX / 4;
         q.tile_points = e->tile_points;
         q.fd_gradient = e->cfg.isde_gradient != 0;
+        q.n_full_warps = e->n_full_warps;
+        q.groups_per_block = e->groups_per_block;
         void *iargs[] = {(void *)&q};
         CUDA_TRY(cudaLaunchKernel(e->step_fn, dim3((unsigned)e->grid), dim3(e->block), iargs, e->launch_smem, e->stream));
         e->iteration += n_steps;

@@ -32,7 +32,10 @@
 // Ito-SDE step kernel variants (lanes per chain, chains per thread, streamed).  (1, 2, streamed): every record read from the
 // tile ring feeds two chains -- the layout of BASELINE configuration 4 when there are enough chains to fill the GPU
 #define PBU_ISDE(MODEL, P, D, G, Q, S) \
-    { MODEL::ID, P, D, G, Q, MODEL::HAS_GRAD ? 1 : 0, S, (const void *)&pbu::isde_step_kernel<MODEL, D, G, Q, (S != 0)> }
+    { MODEL::ID, P, D, G, Q, MODEL::HAS_GRAD ? 1 : 0, S, 0, (const void *)&pbu::isde_step_kernel<MODEL, D, G, Q, (S != 0), false> }
+// streamed records, mixed warp widths (wide state vectors: the layout of BASELINE configuration 4)
+#define PBU_ISDE_MIXED(MODEL, P, D, G, Q) \
+    { MODEL::ID, P, D, G, Q, MODEL::HAS_GRAD ? 1 : 0, 1, 1, (const void *)&pbu::isde_step_kernel<MODEL, D, G, Q, true, true> }
 #define PBU_ISDE_ALL(MODEL, P, D)                                                                                   \
     PBU_ISDE(MODEL, P, D, 1, 1, 0), PBU_ISDE(MODEL, P, D, 1, 2, 0), PBU_ISDE(MODEL, P, D, 2, 2, 0), PBU_ISDE(MODEL, P, D, 4, 1, 0), \
         PBU_ISDE(MODEL, P, D, 8, 1, 0), PBU_ISDE(MODEL, P, D, 1, 1, 1), PBU_ISDE(MODEL, P, D, 4, 1, 1), PBU_ISDE(MODEL, P, D, 8, 1, 1), \
@@ -40,7 +43,7 @@
 #define PBU_ISDE_SEQ(MODEL, P, D) PBU_ISDE(MODEL, P, D, 1, 1, 0), PBU_ISDE(MODEL, P, D, 1, 1, 1)
 // Hamiltonian Monte Carlo step kernel variants (same table type as ISDE; `kind` 1)
 #define PBU_HMC(MODEL, P, D, G, Q, S) \
-    { MODEL::ID, P, D, G, Q, MODEL::HAS_GRAD ? 1 : 0, S, (const void *)&pbu::hmc_step_kernel<MODEL, D, G, Q, (S != 0)> }
+    { MODEL::ID, P, D, G, Q, MODEL::HAS_GRAD ? 1 : 0, S, 0, (const void *)&pbu::hmc_step_kernel<MODEL, D, G, Q, (S != 0)> }
 #define PBU_HMC_ALL(MODEL, P, D) PBU_HMC(MODEL, P, D, 1, 1, 0), PBU_HMC(MODEL, P, D, 4, 1, 0), PBU_HMC(MODEL, P, D, 8, 1, 0), PBU_HMC(MODEL, P, D, 1, 1, 1)
 #define PBU_HMC_SEQ(MODEL, P, D) PBU_HMC(MODEL, P, D, 1, 1, 0), PBU_HMC(MODEL, P, D, 1, 1, 1)
 #define PBU_EVAL(MODEL, P, D)                                                                 \

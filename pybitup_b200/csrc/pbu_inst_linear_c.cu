@@ -3,6 +3,6 @@
 using namespace pbu;
 #define MH_LIST PBU_MH_ALL(LinearModel<8>, 8, 8)
 #define EV_LIST PBU_EVAL(LinearModel<8>, 8, 8)
-#define ISDE_LIST PBU_ISDE_ALL(LinearModel<8>, 8, 8)
+#define ISDE_LIST PBU_ISDE_ALL(LinearModel<8>, 8, 8), PBU_ISDE_MIXED(LinearModel<8>, 8, 8, 1, 2)
 #define HMC_LIST PBU_HMC_ALL(LinearModel<8>, 8, 8)
 PBU_DEFINE_SLICE(linear_c, MH_LIST, EV_LIST, ISDE_LIST, HMC_LIST)

@@ -37,6 +37,8 @@ struct IsdeParams {
     int32_t fd_gradient;      // 1: forward differences with relative step 1e-10 (mha.py:726, :1069-1088)
     int32_t hmc_steps;        // HMC: leapfrog steps L (mha.py:819); the step size epsilon travels in h
     int32_t pad0;
+    int32_t n_full_warps;     // mixed Ito-SDE kernels: warps of a block with G lanes per chain (the rest use 2G)
+    int32_t groups_per_block; // mixed Ito-SDE kernels: chain groups per block
 };
 
 // symmetric packed matrix (upper triangle stored) times vector, reading the matrix from global memory
@@ -225,16 +227,10 @@ __device__ __forceinline__ void grad_log_like(const double (&yv)[Q][D], const Pr
 }
 
 template <class M, int D, int G, int Q, bool STREAM>
-__global__ void __launch_bounds__(MH_MAX_BLOCK, M::MIN_BLOCKS) isde_step_kernel(const __grid_constant__ IsdeParams p) {
+__device__ __forceinline__ void isde_chain_loop(const IsdeParams &p, TileStream<M::NC> &ts, const int64_t group, const int sub) {
     constexpr int NT = tri_size(D);
-    TileStream<M::NC> ts;
-    M::block_init();
-    ts.init(p.prob.records, p.prob.n_points, p.tile_points);
-
     const int64_t C = p.st.n_chains;
     const int lane = threadIdx.x & 31;
-    const int sub = lane_sub<G>(lane);
-    const int64_t group = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32 / G) + lane_chain<G>(lane);
     const unsigned group_mask = lane_group_mask<G>(lane);
     const bool injected = p.streams.normals != nullptr;
 
@@ -436,6 +432,32 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, M::MIN_BLOCKS) isde_step_kernel(
             p.st.lp[cq] = lp[q];
             p.st.n_eval[cq] += n_eval[q];
             p.st.status[cq] = status[q];
+        }
+    }
+}
+
+// The kernel proper.  MIXED: the last warps of every block (from warp index p.n_full_warps on) give each chain 2G lanes
+// instead of G, i.e. carry half as many chains -- half a unit of work, as in mh_step_kernel.  With equal warps the 2,048
+// warps of 131,072 chains (G = 1, Q = 2) fill 128 blocks of 16 warps and leave 20 of the 148 SMs idle; three full warps and
+// one half warp per scheduler (896 chains per block, 147 blocks) use them all.  Streamed records: every warp of either
+// width walks the same tiles, the wide ones split each tile's points over their two lanes.
+template <class M, int D, int G, int Q, bool STREAM, bool MIXED>
+__global__ void __launch_bounds__(MH_MAX_BLOCK, M::MIN_BLOCKS) isde_step_kernel(const __grid_constant__ IsdeParams p) {
+    TileStream<M::NC> ts;
+    M::block_init();
+    ts.init(p.prob.records, p.prob.n_points, p.tile_points);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    if constexpr (!MIXED) {
+        const int64_t warp_g = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+        isde_chain_loop<M, D, G, Q, STREAM>(p, ts, warp_g * (32 / G) + lane_chain<G>(lane), lane_sub<G>(lane));
+    } else {
+        const int64_t base = (int64_t)blockIdx.x * p.groups_per_block;
+        if (warp < p.n_full_warps) {
+            isde_chain_loop<M, D, G, Q, STREAM>(p, ts, base + warp * (32 / G) + lane_chain<G>(lane), lane_sub<G>(lane));
+        } else {
+            isde_chain_loop<M, D, 2 * G, Q, STREAM>(p, ts, base + p.n_full_warps * (32 / G) + (warp - p.n_full_warps) * (16 / G) + lane_chain<2 * G>(lane),
+                                                   lane_sub<2 * G>(lane));
         }
     }
 }

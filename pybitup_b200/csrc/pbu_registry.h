@@ -13,6 +13,7 @@ struct MhKernelEntry {
 };
 struct IsdeKernelEntry {
     int model, n_param, n_unc, lanes, chains_per_thread, has_grad, streamed;
+    int mixed;                // 1: the last warps of a block use 2 * lanes per chain (Ito-SDE only)
     const void *fn;   // __global__ void (*)(const IsdeParams)
 };
 struct EvalKernelEntry {
