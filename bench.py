@@ -550,7 +550,9 @@ def run_gpu_arm(args):
             "ess": ess,
             "configs": configs,
         }
-        prof = os.path.join(ROOT, "profiles", "traffic_r1.json")
+        prof = os.path.join(ROOT, "profiles", "traffic_r2.json")
+        if not os.path.exists(prof):
+            prof = os.path.join(ROOT, "profiles", "traffic_r1.json")
         if os.path.exists(prof):
             try:
                 with open(prof) as f:
