@@ -204,6 +204,8 @@ def cpu_baseline_leg():
 # ------------------------------------------------------------------------------------------------ GPU arm
 FP64_INST_RK4 = 68.5         # FP64 instructions of one RK4 step of the Arrhenius kernels (137 per two steps, cuobjdump -sass)
 OTHER_INST_RK4 = 66.5        # the other instructions of that step: an FP64 instruction holds the issue port for two cycles, these for one
+FP64_INST_RK4_EVAL = 66.5    # the evaluation kernel of the propagation (no residual, no sum of squares): 133 FP64 + 136 other per two steps
+OTHER_INST_RK4_EVAL = 68.0
 
 
 def _finite(o):
@@ -339,7 +341,7 @@ def measure_configs(rank, local_rank, world, red, fp64_peak, hbm_peak, barrier, 
                 st = dp.statistics(reduce=rd, n_total=world * S)
                 torch.cuda.synchronize()
                 ms_stat = max_over_ranks((time.perf_counter() - t0) * 1e3)
-                tf_issue = S * 500 * FP64_INST_RK4 * 2 / (ms_eval * 1e-3) / 1e12
+                tf_issue = S * 500 * FP64_INST_RK4_EVAL * 2 / (ms_eval * 1e-3) / 1e12
                 out["cfg5"] = {"workload": "Monte-Carlo propagation through the pyrolysis ODE, 1.25e7 samples per GPU (%.3g in all) x 500 "
                                            "points, evaluations materialised in HBM (50 GB per GPU)" % (world * S), "scaling": "weak",
                                "eval_ms": ms_eval, "statistics_ms": ms_stat, "statistics_select": dp.last_select,
@@ -348,7 +350,10 @@ def measure_configs(rank, local_rank, world, red, fp64_peak, hbm_peak, barrier, 
                                "ci_last_point": [float(st["ci_lb"][-1]), float(st["ci_ub"][-1])],
                                "roofline": {"bound": "fp64", "achieved": S * 2.15e4 / (ms_eval * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                                             "frac": frac(S * 2.15e4 / (ms_eval * 1e-3) / 1e12), "flops_per_sample": 2.15e4,
-                                            "fp64_issue": {"achieved": tf_issue, "frac": frac(tf_issue), "fp64_inst_per_rk4_step": FP64_INST_RK4},
+                                            "fp64_issue": {"achieved": tf_issue, "frac": frac(tf_issue), "fp64_inst_per_rk4_step": FP64_INST_RK4_EVAL,
+                                                           "other_inst_per_rk4_step": OTHER_INST_RK4_EVAL,
+                                                           "kernel": "eval_model_rep_kernel<ArrheniusModel>: conflict-free replicated exp2 / log2 "
+                                                                     "tables (192 KB of shared memory), 1024-thread persistent blocks"},
                                             "hbm_write": {"achieved": S * 4000 / (ms_eval * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                                           "frac": S * 4000 / (ms_eval * 1e-3) / 1e9 / hbm_peak}}}
     return out

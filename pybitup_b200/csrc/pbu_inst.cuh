@@ -48,7 +48,7 @@
 #define PBU_HMC_SEQ(MODEL, P, D) PBU_HMC(MODEL, P, D, 1, 1, 0), PBU_HMC(MODEL, P, D, 1, 1, 1)
 #define PBU_EVAL(MODEL, P, D)                                                                 \
     { MODEL::ID, P, D, MODEL::SEQUENTIAL ? 1 : 0, MODEL::NC, MODEL::NCR, MODEL::OPS, MODEL::WF, (const void *)&pbu::eval_logpost_kernel<MODEL, D>, \
-      (const void *)&pbu::eval_model_kernel<MODEL, D>, (const void *)&pbu::eval_grad_kernel<MODEL, D> }
+      (const void *)&pbu::eval_model_kernel<MODEL, D>, (const void *)&pbu::eval_grad_kernel<MODEL, D>, pbu::RepEval<MODEL, D>::fn() }
 
 #define PBU_DEFINE_SLICE(name, MH_LIST, EVAL_LIST, ISDE_LIST, HMC_LIST)              \
     static const pbu::IsdeKernelEntry hmc_tab_##name[] = {HMC_LIST};                 \

@@ -125,6 +125,18 @@ PBU_HD double pbu_log(double u) {
 // shared window, and pass the pointer; on the host the static copy.
 // Checked against libm in tools/test_math.cu: exp2 <= 2 ulp; log2 <= 1 ulp of max(|log2 u|, 1) -- the error that
 // matters for 2^(n log2 u) is the absolute one.
+//
+// Conflict-free replicas (the evaluation kernel of the propagation, where every lane of a warp looks up a different entry:
+// ncu showed the shared-memory pipe at 95 % of its wavefront rate, 60 % of the wavefronts bank conflicts).  An 8-byte load
+// is served per half warp, a 16-byte load per quarter warp, 128 bytes at a time: with 16 interleaved copies of the exp2
+// table (entry j of copy r at byte 128 j + 8 r, lane l reads copy l mod 16) and 8 copies of the log2 table (entry i of
+// copy r at 128 i + 16 r, copy l mod 8) the lanes served together always sit in different banks, whatever their indices.
+// 128 KB + 64 KB of shared memory: one block of 1024 threads per SM (the kernel needs fewer than 64 registers).
+#define PBU_EXP2_REPLICAS 16
+#define PBU_LOG2_REPLICAS 8
+#define PBU_REP_EXP2_BYTES (8 * PBU_EXP2_ENTRIES * PBU_EXP2_REPLICAS)
+#define PBU_REP_LOG2_BYTES (16 * PBU_LOG2_ENTRIES * PBU_LOG2_REPLICAS)
+#define PBU_REP_TABLE_BYTES (PBU_REP_EXP2_BYTES + PBU_REP_LOG2_BYTES + 128)      // + the leading coefficients (PBU_MATH_EXTRA_DOUBLES)
 #define PBU_MATH_TABLE_DOUBLES (PBU_EXP2_ENTRIES + 2 * PBU_LOG2_ENTRIES)
 #define PBU_LOG2_TABLE_OFFSET PBU_EXP2_ENTRIES
 static const double pbu_math_tables_host[PBU_MATH_TABLE_DOUBLES] = {PBU_EXP2_TABLE, PBU_LOG2_TABLE};
@@ -178,7 +190,10 @@ static __device__ const double pbu_math_extra_dev[PBU_MATH_EXTRA_DOUBLES] = {PBU
 // table value's hi word, which leaves a tiny denormal instead of the exact tail below 2^-1022 (-inf included).  The scale
 // 2^k goes onto the TABLE value before the last FMA, so the result needs no fix-up.  The FP64 pipe sees the seven arithmetic
 // instructions only.  NaN with the sign bit clear propagates.
-PBU_HD double pbu_exp2_tab_scaled_sel(double ys, const double *tab, int32_t uh, double kB3) {
+// REP: `rep_addr` is the 32-bit shared-window address of THIS LANE's copy of entry 0 in the replicated table (see
+// "Conflict-free replicas" below); `tab` is unused.
+template <bool REP>
+PBU_HD double pbu_exp2_tab_scaled_sel_t(double ys, const double *tab, uint32_t rep_addr, int32_t uh, double kB3) {
     const double SHIFT = 6755399441055744.0;                     // 1.5 * 2^52
     const double t = ys + SHIFT;
     const double kf = t - SHIFT;                                 // 1024 k + j as a double
@@ -194,8 +209,16 @@ PBU_HD double pbu_exp2_tab_scaled_sel(double ys, const double *tab, int32_t uh, 
     p = fma(p, r, PBU_KC(1, PBU_K_B1S));
     const double v = p * r;                                      // 2^(r/1024) - 1 (no constant term: 2^0 is exactly 1)
 #ifdef __CUDA_ARCH__
-    double T;                                                    // tab is 8 KB aligned in the shared window: base | offset
-    asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(pbu_tab_base(tab) | (((uint32_t)m << 3) & (8u * PBU_EXP2_ENTRIES - 8u))));      // is one LOP3
+    double T;
+    if constexpr (REP) {                                         // entry j of the lane's replica: rep_addr + 128 j (mask, then one multiply-add)
+        asm("{\n\t.reg .u32 j, a;\n\t"
+            "and.b32 j, %1, %3;\n\t"
+            "mad.lo.u32 a, j, %4, %2;\n\t"
+            "ld.shared.f64 %0, [a];\n\t}"
+            : "=d"(T) : "r"(m), "r"(rep_addr), "n"(PBU_EXP2_ENTRIES - 1), "n"(8 * PBU_EXP2_REPLICAS));
+    } else {                                                     // tab is 8 KB aligned in the shared window: base | offset
+        asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(pbu_tab_base(tab) | (((uint32_t)m << 3) & (8u * PBU_EXP2_ENTRIES - 8u))));      // is one LOP3
+    }
     // hi word of T 2^k where kept, 0 otherwise: two compares into one predicate, one multiply-add, one select
     double Ts;
     asm("{\n\t.reg .pred p, q;\n\t.reg .s32 k, lo, hi;\n\t"
@@ -214,17 +237,29 @@ PBU_HD double pbu_exp2_tab_scaled_sel(double ys, const double *tab, int32_t uh, 
 #endif
     return fma(Ts, v, Ts);
 }
+PBU_HD double pbu_exp2_tab_scaled_sel(double ys, const double *tab, int32_t uh, double kB3) {
+    return pbu_exp2_tab_scaled_sel_t<false>(ys, tab, 0u, uh, kB3);
+}
 PBU_HD double pbu_exp2_tab(double y, const double *tab) { return pbu_exp2_tab_scaled_sel(y * (double)PBU_EXP2_ENTRIES, tab, 0x3FF00000, PBU_K_B3S); }
 
 // log2(u) for normal 0 < u < 2^1000 (anything else: finite garbage, to be discarded by the caller -- pbu_exp2_tab_scaled_sel
 // does it from the hi word of u)
-PBU_HD double pbu_log2_tab(double u, const double *tab, double kA4 = PBU_K_A4) {
+template <bool REP>
+PBU_HD double pbu_log2_tab_t(double u, const double *tab, uint32_t rep_addr, double kA4) {
     const int32_t hi = hi_word(u);
     const int32_t e = (hi >> 20) - 1023;
 #ifdef __CUDA_ARCH__
     double cs, nlc;                                              // one 16-byte shared-memory load, address as in exp2
-    asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(cs), "=d"(nlc)
-        : "r"(pbu_tab_base(tab) | (((uint32_t)hi >> 7) & (16u * PBU_LOG2_ENTRIES - 16u))), "n"(8 * PBU_LOG2_TABLE_OFFSET));
+    if constexpr (REP) {                                         // rep_addr + 128 i, i = the top 9 mantissa bits: mask in place, then hi(x 2^28) = x >> 4 with the add
+        asm("{\n\t.reg .u32 i, a;\n\t"
+            "and.b32 i, %2, %4;\n\t"
+            "mad.hi.u32 a, i, %5, %3;\n\t"
+            "ld.shared.v2.f64 {%0, %1}, [a];\n\t}"
+            : "=d"(cs), "=d"(nlc) : "r"(hi), "r"(rep_addr), "n"((PBU_LOG2_ENTRIES - 1) << 11), "n"((16 * PBU_LOG2_REPLICAS) << 21));
+    } else {
+        asm("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(cs), "=d"(nlc)
+            : "r"(pbu_tab_base(tab) | (((uint32_t)hi >> 7) & (16u * PBU_LOG2_ENTRIES - 16u))), "n"(8 * PBU_LOG2_TABLE_OFFSET));
+    }
     // c 2^-e: the exponent field of u comes off the exponent field of c, in place (one three-input integer add)
     asm("{\n\t.reg .s32 lo, hi, t;\n\t"
         "mov.b64 {lo, hi}, %0;\n\t"
@@ -244,5 +279,6 @@ PBU_HD double pbu_log2_tab(double u, const double *tab, double kA4 = PBU_K_A4) {
     q = fma(q, r, PBU_KC(4, PBU_K_A1));
     return fma(r, q, nlc) + (double)e;                           // small part first: one rounding at full size
 }
+PBU_HD double pbu_log2_tab(double u, const double *tab, double kA4 = PBU_K_A4) { return pbu_log2_tab_t<false>(u, tab, 0u, kA4); }
 
 }  // namespace pbu

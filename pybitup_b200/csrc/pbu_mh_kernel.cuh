@@ -22,6 +22,7 @@
 // under 128 registers so that one block of up to 512 threads (16 warps) fills an SM, and lets the
 // host pick a block size that spreads the chains evenly over the 148 SMs (pbu_engine.cu::plan_launch).
 #pragma once
+#include <type_traits>
 #include "pbu_common.cuh"
 #include "pbu_models.cuh"
 
@@ -907,5 +908,43 @@ __global__ void __launch_bounds__(256) eval_model_kernel(const __grid_constant__
         ts.release(prob.raw, prob.n_points, tile_points, tl);
     }
 }
+
+// The same for a model with conflict-free replicated lookup tables (M = Model::Rep, pbu_math.cuh): one block of 1024
+// threads per SM (the replicas take 192 KB of its shared memory), persistent -- the tables are staged once and the block
+// strides over the samples.  One model block, records resident (the host checks both before choosing this kernel).
+template <class M, int D>
+__global__ void __launch_bounds__(1024, 1) eval_model_rep_kernel(const __grid_constant__ ProblemDev prob, const double *X /*[d][S]*/, int64_t S,
+                                                                 double *f_out, int tile_points) {
+    TileStream<M::NCR> ts;
+    M::block_init();
+    ts.init(prob.raw, prob.n_points, tile_points);        // (synchronises the block: the tables are in place)
+    int cnt;
+    const double *tile = ts.acquire(prob.n_points, tile_points, 0, cnt);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < S; t += (int64_t)gridDim.x * blockDim.x) {
+        double x[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) x[i] = X[i * S + t];
+        typename M::Ctx ctx;
+        typename M::Seq seq;
+        begin_chain_block<M, D>(x, prob, 0, ctx, seq);
+        double *out = f_out + t;
+#pragma unroll 2
+        for (int k = 0; k < cnt; ++k) {
+            double raw[M::NCR];
+            load_record<M::NCR>(tile, k, raw);
+            out[(int64_t)k * S] = M::value(ctx, seq, raw);
+        }
+    }
+}
+
+// nullptr for models without replicated tables
+template <class M, int D, class = void>
+struct RepEval {
+    static const void *fn() { return nullptr; }
+};
+template <class M, int D>
+struct RepEval<M, D, std::void_t<typename M::Rep>> {
+    static const void *fn() { return (const void *)&eval_model_rep_kernel<typename M::Rep, D>; }
+};
 
 }  // namespace pbu

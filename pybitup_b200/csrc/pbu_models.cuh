@@ -169,7 +169,12 @@ struct PolyModel {
 //   likelihood record [1/T_mid | 1/T_end | w | w*y];  raw record [1/T_mid | 1/T_end]
 // The rate at the start of a step is the rate at the end of the previous one, so each step costs two
 // exp and four pow.
-struct ArrheniusModel {
+// REP: the lookup tables are the conflict-free replicas of pbu_math.cuh in DYNAMIC shared memory (the last
+// PBU_REP_TABLE_BYTES of it, 128-byte aligned); used by the evaluation kernel of the propagation only.
+template <bool REP>
+struct ArrheniusModelT {
+    using Rep = ArrheniusModelT<true>;
+    static constexpr bool HAS_REP = !REP;
     static constexpr bool HAS_MULTI = false;
     static constexpr int NPARAM = 4;
     static constexpr int NC = 4;
@@ -185,6 +190,7 @@ struct ArrheniusModel {
     struct Ctx {
         double c0, ER, n, F, omF, y_start;
         double kA4, kB3, sixth;     // leading polynomial coefficients of log2 / exp2 and -1/6, pinned in registers (loaded from shared memory, pbu_math.cuh)
+        uint32_t cexp, clog;        // REP: shared-window address of this lane's copy of entry 0 of the exp2 / log2 table
     };
     struct Seq {
         double u, y0;          // u = 1 - alpha (the unconverted fraction), y0 = log2 of (rate x step) at the start of the step
@@ -202,7 +208,16 @@ struct ArrheniusModel {
         c.F = theta[3];
         c.omF = 1.0 - theta[3];
         c.y_start = fma(-c.ER, 1.0 / consts[0], c.c0);
-        const volatile double *extra = tables() + PBU_MATH_TABLE_DOUBLES;      // (every kernel synchronises after block_init)
+        const volatile double *extra;                                          // (every kernel synchronises after block_init)
+        if constexpr (REP) {
+            const uint32_t lane = threadIdx.x & 31u;
+            c.cexp = rep_base() + 8u * (lane & (PBU_EXP2_REPLICAS - 1));
+            c.clog = rep_base() + PBU_REP_EXP2_BYTES + 16u * (lane & (PBU_LOG2_REPLICAS - 1));
+            extra = rep_ptr() + (PBU_REP_EXP2_BYTES + PBU_REP_LOG2_BYTES) / 8;
+        } else {
+            c.cexp = c.clog = 0u;
+            extra = tables() + PBU_MATH_TABLE_DOUBLES;
+        }
         c.kA4 = extra[0];
         c.kB3 = extra[1];
         c.sixth = extra[2];
@@ -220,10 +235,34 @@ struct ArrheniusModel {
         const uint32_t a = (uint32_t)__cvta_generic_to_shared(raw);
         return raw + (((0u - a) & 8191u) >> 3);
     }
+    // REP: the replicas occupy the END of the dynamic shared memory the host asked for (PBU_REP_TABLE_BYTES + 128 more than
+    // the kernel's own layout needs), from a 128-byte boundary of the shared window
+    __device__ __forceinline__ static uint32_t rep_base() {
+        extern __shared__ __align__(128) unsigned char pbu_smem[];
+        uint32_t dyn;
+        asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+        return ((uint32_t)__cvta_generic_to_shared(pbu_smem) + dyn - (uint32_t)PBU_REP_TABLE_BYTES) & ~127u;
+    }
+    __device__ __forceinline__ static double *rep_ptr() {
+        extern __shared__ __align__(128) unsigned char pbu_smem[];
+        return reinterpret_cast<double *>(pbu_smem + (rep_base() - (uint32_t)__cvta_generic_to_shared(pbu_smem)));
+    }
     __device__ __forceinline__ static void block_init() {
-        double *t = tables();
-        for (int i = threadIdx.x; i < PBU_MATH_TABLE_DOUBLES; i += blockDim.x) t[i] = pbu_math_tables_dev[i];
-        if (threadIdx.x < PBU_MATH_EXTRA_DOUBLES) t[PBU_MATH_TABLE_DOUBLES + threadIdx.x] = pbu_math_extra_dev[threadIdx.x];
+        if constexpr (REP) {
+            double *t = rep_ptr();
+            for (int i = threadIdx.x; i < PBU_EXP2_ENTRIES * PBU_EXP2_REPLICAS; i += blockDim.x) t[i] = pbu_math_tables_dev[i / PBU_EXP2_REPLICAS];
+            double2 *t2 = reinterpret_cast<double2 *>(t + PBU_EXP2_ENTRIES * PBU_EXP2_REPLICAS);
+            for (int i = threadIdx.x; i < PBU_LOG2_ENTRIES * PBU_LOG2_REPLICAS; i += blockDim.x) {
+                const int j = i / PBU_LOG2_REPLICAS;
+                t2[i] = make_double2(pbu_math_tables_dev[PBU_LOG2_TABLE_OFFSET + 2 * j], pbu_math_tables_dev[PBU_LOG2_TABLE_OFFSET + 2 * j + 1]);
+            }
+            double *ex = t + (PBU_REP_EXP2_BYTES + PBU_REP_LOG2_BYTES) / 8;
+            if (threadIdx.x < PBU_MATH_EXTRA_DOUBLES) ex[threadIdx.x] = pbu_math_extra_dev[threadIdx.x];
+        } else {
+            double *t = tables();
+            for (int i = threadIdx.x; i < PBU_MATH_TABLE_DOUBLES; i += blockDim.x) t[i] = pbu_math_tables_dev[i];
+            if (threadIdx.x < PBU_MATH_EXTRA_DOUBLES) t[PBU_MATH_TABLE_DOUBLES + threadIdx.x] = pbu_math_extra_dev[threadIdx.x];
+        }
     }
     // One stage increment h g(T) u^n = 2^(y + n log2 u) with the table-driven pbu_exp2_tab / pbu_log2_tab (pbu_math.cuh):
     // relative error below 3e-14 against exp() * pow() (tools/test_math.cu), far inside the 1e-10 parity bar, at 14 FP64
@@ -231,7 +270,10 @@ struct ArrheniusModel {
     // such an argument is finite garbage, discarded by the selection; no FP64 instruction is spent on the test.  A sum of
     // exponents below -1022 (u -> 0) gives a denormal as well.
     __device__ __forceinline__ static double stage(const Ctx &c, double y, double u) {
-        return pbu_exp2_tab_scaled_sel(fma(c.n, pbu_log2_tab(u, tables(), c.kA4), y), tables(), hi_word(u), c.kB3);
+        if constexpr (REP)
+            return pbu_exp2_tab_scaled_sel_t<true>(fma(c.n, pbu_log2_tab_t<true>(u, nullptr, c.clog, c.kA4), y), nullptr, c.cexp, hi_word(u), c.kB3);
+        else
+            return pbu_exp2_tab_scaled_sel(fma(c.n, pbu_log2_tab(u, tables(), c.kA4), y), tables(), hi_word(u), c.kB3);
     }
     // One RK4 step of d(alpha)/dT = g(T) (1 - alpha)^n, carried on u = 1 - alpha (du/dT = -g u^n): this differs from the
     // oracle's alpha + ... and 1 - (alpha + k/2) by rounding only (a few ulp of u), far inside the 1e-10 parity bar.
@@ -256,6 +298,7 @@ struct ArrheniusModel {
     __device__ __forceinline__ static double value(const Ctx &c, Seq &s, const double *raw) { return step(c, s, raw[0], raw[1]); }
     __device__ __forceinline__ static void grad_acc(const Ctx &, const double (&)[NC], double, double (&)[4]) {}
 };
+using ArrheniusModel = ArrheniusModelT<false>;
 
 // ------------------------------------------------------------------------------------------------
 // HEAT: steady fin temperature, the reference's own test model

@@ -480,6 +480,25 @@ PBU_API int pbu_propagation_destroy(pbu_propagation *p) {
 
 static int run_model_eval(pbu_propagation *p) {
     pbu_engine *e = p->e;
+    // Models with lookup tables (Arrhenius): conflict-free replicated tables in 1024-thread persistent blocks, one per SM,
+    // once there are samples for two rounds of them (PBU_REP_TABLES=0 / 1 overrides: diagnostics)
+    if (e->ev->eval_model_rep && e->prob.n_blocks <= 1 && e->tile_points_raw >= e->prob.n_points) {
+        int n_sm = 0, max_smem = 0;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, e->device);
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device);
+        const size_t smem = e->smem_raw_bytes + 128 + PBU_REP_TABLE_BYTES;
+        bool use = p->S >= (int64_t)2 * 1024 * n_sm;
+        if (const char *f = getenv("PBU_REP_TABLES")) use = atoi(f) != 0;
+        if (use && smem <= (size_t)max_smem) {
+            CUDA_TRY(cudaFuncSetAttribute(e->ev->eval_model_rep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int64_t need = (p->S + 1023) / 1024;
+            const unsigned grid = (unsigned)std::min<int64_t>(need, n_sm);
+            void *args[] = {(void *)&e->prob, (void *)&p->d_X, (void *)&p->S, (void *)&p->d_f, (void *)&e->tile_points_raw};
+            CUDA_TRY(cudaLaunchKernel(e->ev->eval_model_rep, dim3(grid), dim3(1024), args, smem, e->stream));
+            p->evaluated = true;
+            return PBU_OK;
+        }
+    }
     CUDA_TRY(cudaFuncSetAttribute(e->ev->eval_model, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_raw_bytes));
     const int block = 128;
     const unsigned grid = (unsigned)((p->S + block - 1) / block);

@@ -23,6 +23,7 @@ struct EvalKernelEntry {
     const void *eval_lp;      // __global__ void (*)(const ProblemDev, const double*, int64_t, double*)
     const void *eval_model;   // same signature
     const void *eval_grad;    // __global__ void (*)(const ProblemDev, const double*, int64_t, double*, int, int)
+    const void *eval_model_rep;   // eval_model with conflict-free replicated lookup tables (1024-thread persistent blocks), or nullptr
 };
 
 }  // namespace pbu

@@ -33,6 +33,34 @@ def test_propagation_statistics_match_oracle(builder, kwargs, S):
     assert H.rel_err(out["ci_lb"], ref["ci_lb"]) < 1e-10 and H.rel_err(out["ci_ub"], ref["ci_ub"]) < 1e-10
 
 
+@pytest.mark.parametrize("d", [4, 2])
+def test_replicated_table_kernel_is_bit_identical(d, monkeypatch):
+    """Arrhenius evaluations with the conflict-free replicated lookup tables (1024-thread persistent blocks, what cfg 5
+    runs) against the plain-table kernel: the same table values, the same arithmetic -> identical bits; and against
+    the oracle.  S is not a multiple of the block, several grid strides per block."""
+    from pybitup_b200 import synthetic
+    from pybitup_b200.engine import ChainEngine, ProblemSpec, SamplerConfig
+    from pybitup_b200.propagation import DevicePropagation
+    p = synthetic.arrhenius_problem(n_steps=50, dT=12.0)
+    if d < 4:                        # E and F fixed at their nominal values: the d = 2 of 4 instantiation
+        idx = np.array([0, 2])
+        p.update(unc_idx=idx, lb=p["lb"][idx], ub=p["ub"][idx], x0=p["x0"][idx])
+    S = 2 * 148 * 1024 + 1234
+    mean, std = p["x0"], 0.03 * np.abs(p["x0"])
+    out = {}
+    with ChainEngine(ProblemSpec.from_dict(p), SamplerConfig(algo="RWMH"), 1) as eng:
+        for rep in ("0", "1"):
+            monkeypatch.setenv("PBU_REP_TABLES", rep)
+            with DevicePropagation(eng, S) as dp:
+                dp.evaluate_gaussian(mean, std, seed=3, sample_offset=0)
+                out[rep] = dp.evals()
+                if rep == "1":
+                    X = dp.samples()[:300]
+    assert np.array_equal(out["0"], out["1"])
+    ref = orc.propagate(H.oracle_problem(p), X)
+    assert H.rel_err(out["1"][:300], ref["fun_eval"]) < 1e-11
+
+
 def test_propagation_gaussian_samples_and_sharding():
     """Samples drawn on the device: sharding them over two engines (as two GPUs would) and summing the moment /
     histogram arrays gives the statistics of the unsharded run, bit for bit on the order statistics."""
