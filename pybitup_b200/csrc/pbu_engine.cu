@@ -92,12 +92,12 @@ extern "C" __attribute__((visibility("default"))) int pbu_list_kernels(char *buf
     return total;
 }
 
-static const MhKernelEntry *find_mh(int model, int P, int d, int lanes, int q, int algo, int streamed, int mixed = 0, int coop = 0) {
+static const MhKernelEntry *find_mh(int model, int P, int d, int lanes, int q, int algo, int streamed, int mixed = 0, int coop = 0, int rep = 0) {
     int n = 0;
     const MhKernelEntry *t = pbu_mh_kernels(&n);
     for (int i = 0; i < n; ++i)
         if (t[i].model == model && t[i].n_param == P && t[i].n_unc == d && t[i].lanes == lanes && t[i].chains_per_thread == q &&
-            t[i].algo == algo && t[i].streamed == streamed && t[i].mixed == mixed && t[i].coop == coop)
+            t[i].algo == algo && t[i].streamed == streamed && t[i].mixed == mixed && t[i].coop == coop && t[i].rep == rep)
             return &t[i];
     return nullptr;
 }
@@ -216,9 +216,11 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
     const double S0 = 60.0 + 15.0 * e->d;           // per-iteration scalar part (RNG, proposal, accept, adaptation), in DFMA-equivalents
     // (lanes, chains per thread or per team, mixed, coop): mixed = the last warps of a block use twice the lanes;
     // coop = teams of `lanes` lanes own `lanes` chains (pbu_mh_coop.cuh)
-    const int cand[11][4] = {{1, 1, 0, 0}, {1, 2, 0, 0}, {2, 2, 0, 0}, {2, 2, 1, 0}, {4, 2, 0, 0}, {2, 1, 0, 0}, {4, 1, 0, 0}, {8, 1, 0, 0},
-                             {4, 4, 0, 1}, {4, 4, 1, 1}, {1, 2, 1, 0}};
-    const char *force = getenv("PBU_FORCE_VARIANT");      // "lanes,q,mixed,coop": diagnostics
+    // rep = the model's lookup tables as conflict-free replicas (192 KB of shared memory, one block of up to 1024 threads per SM)
+    const int cand[13][5] = {{1, 1, 0, 0, 0}, {1, 2, 0, 0, 0}, {2, 2, 0, 0, 0}, {2, 2, 1, 0, 0}, {4, 2, 0, 0, 0}, {2, 1, 0, 0, 0}, {4, 1, 0, 0, 0},
+                             {8, 1, 0, 0, 0}, {4, 4, 0, 1, 0}, {4, 4, 1, 1, 0}, {1, 2, 1, 0, 0}, {1, 1, 0, 0, 1}, {2, 1, 0, 0, 1}};
+    const char *force = getenv("PBU_FORCE_VARIANT");      // "lanes,q,mixed,coop[,rep]": diagnostics
+    const char *rep_env = getenv("PBU_REP_TABLES");       // 0: never the replicated tables (diagnostics)
     const bool hmc = algo == PBU_ALGO_HMC;
     const bool isde = algo == PBU_ALGO_ISDE || hmc;
     const int streamed = e->tile_points < e->prob.n_points ? 1 : 0;
@@ -226,11 +228,12 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
     double best = 1e300;
     bool found = false;
     for (const auto &gq : cand) {
-        const int g = gq[0], q = gq[1], mixed = gq[2], coop = gq[3];
+        const int g = gq[0], q = gq[1], mixed = gq[2], coop = gq[3], rep = gq[4];
+        if (rep && (isde || streamed || e->prob.n_blocks > 1 || (rep_env && atoi(rep_env) == 0))) continue;
         if (force) {
-            int f[4] = {0, 0, 0, 0};
-            sscanf(force, "%d,%d,%d,%d", &f[0], &f[1], &f[2], &f[3]);
-            if (f[0] != g || f[1] != q || f[2] != mixed || f[3] != coop) continue;
+            int f[5] = {0, 0, 0, 0, 0};
+            sscanf(force, "%d,%d,%d,%d,%d", &f[0], &f[1], &f[2], &f[3], &f[4]);
+            if (f[0] != g || f[1] != q || f[2] != mixed || f[3] != coop || f[4] != rep) continue;
         } else {
             if (want_coop > 0 && !coop) continue;
             if (want_coop < 0 && coop) continue;
@@ -262,7 +265,7 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
             ki = hmc ? find_hmc(model, e->P, e->d, g, q, streamed) : find_isde(model, e->P, e->d, g, q, streamed, mixed);
             if (ki) fn = ki->fn;
         } else {
-            km = find_mh(model, e->P, e->d, g, q, algo, streamed, mixed, coop);
+            km = find_mh(model, e->P, e->d, g, q, algo, streamed, mixed, coop, rep);
             if (km) fn = km->fn;
         }
         if (!fn) continue;
@@ -272,7 +275,7 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
         CUDA_TRY(cudaFuncGetAttributes(&fattr, fn));
         if ((int)fattr.sharedSizeBytes > PBU_STATIC_SMEM_RESERVE)
             return fail(PBU_ERR_UNSUPPORTED, "a step kernel uses %zu B of static shared memory, more than the %d B reserved", fattr.sharedSizeBytes, PBU_STATIC_SMEM_RESERVE);
-        max_smem -= PBU_STATIC_SMEM_RESERVE;
+        max_smem -= rep ? (int)fattr.sharedSizeBytes : PBU_STATIC_SMEM_RESERVE;      // (replicas: no tables in static shared memory)
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         const size_t rec_aligned = (e->smem_bytes + 127) & ~(size_t)127;
         // replicated layout: a group of g lanes carries q chains per lane-set; cooperative: a team of g lanes owns q = g chains
@@ -287,13 +290,20 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
         // speculative pair does one pass for its 16 chains.  Equal work per chain at full occupancy -- measured 5 % in favour
         // of the pair at 262,144 chains (tools/exp_block.py), 1.7x at 32,768 -- so the pair is preferred throughout.
         const double evals = (sequential && delayed) ? ((g == 2) ? 0.95 : 2.0) : 1.0;
-        const double work = q * (sequential ? N : std::ceil(N / g)) * ops * conflict * evals + (coop ? 1.0 : (double)q) * S0;
-        for (int B = MH_MAX_BLOCK; B >= 32; B -= 32) {
+        // replicated tables: no bank conflicts among the 32 independent table indices of a warp (PBU_REP_GAIN: diagnostics)
+        double rep_gain = 0.9;
+        if (const char *rg = getenv("PBU_REP_GAIN")) rep_gain = atof(rg);
+        const double work = q * (sequential ? N : std::ceil(N / g)) * ops * conflict * evals * (rep ? rep_gain : 1.0) + (coop ? 1.0 : (double)q) * S0;
+        for (int B = (rep ? 1024 : MH_MAX_BLOCK); B >= 32; B -= 32) {
             if (want_block > 0 && B != want_block) continue;
             // cooperative kernels park the own chain's state (x, y, lp, mean_r, u: 2d + 3 doubles per thread, component stride
             // MH_MAX_BLOCK) behind the records for the duration of the data loop (pbu_mh_coop.cuh)
             size_t smem_launch = e->smem_bytes;
             int state_off = 0;
+            if (rep) {
+                smem_launch = rec_aligned + 128 + PBU_REP_TABLE_BYTES;
+                if (smem_launch > (size_t)max_smem) continue;
+            }
             if (coop) {
                 const size_t state = (size_t)(2 * e->d + 3) * sizeof(double) * MH_MAX_BLOCK;
                 if (rec_aligned + state > (size_t)max_smem) continue;
@@ -417,9 +427,9 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
     e->nt = tri_size(e->d);
     e->ev = ev;
 
-    if (cfg->block_threads != 0 && (cfg->block_threads % 32 != 0 || cfg->block_threads < 32 || cfg->block_threads > MH_MAX_BLOCK)) {
+    if (cfg->block_threads != 0 && (cfg->block_threads % 32 != 0 || cfg->block_threads < 32 || cfg->block_threads > 1024)) {
         delete e;
-        return fail(PBU_ERR_INVALID, "block_threads must be a multiple of 32 in [32, %d]", MH_MAX_BLOCK);
+        return fail(PBU_ERR_INVALID, "block_threads must be a multiple of 32 in [32, %d]", 1024);
     }
     if (cfg->algo == PBU_ALGO_HMC && (!(cfg->hmc_step_size > 0.0) || cfg->hmc_num_steps < 1)) {
         delete e;

@@ -32,6 +32,16 @@ namespace pbu {
 #define PBU_MAX_BLOCK 512
 #endif
 constexpr int MH_MAX_BLOCK = PBU_MAX_BLOCK;
+// models whose lookup tables are the conflict-free replicas (Model::Rep, 192 KB of shared memory): ONE block of up to 1024
+// threads per SM
+template <class M, class = void>
+struct StepBounds {
+    static constexpr int MAX_BLOCK = MH_MAX_BLOCK, MIN_BLOCKS = M::MIN_BLOCKS;
+};
+template <class M>
+struct StepBounds<M, std::enable_if_t<M::IS_REP>> {
+    static constexpr int MAX_BLOCK = 1024, MIN_BLOCKS = 1;
+};
 
 // ------------------------------------------------------------------------------------------------
 // Shared-memory staging of the point records with bulk TMA copies (cp.async.bulk + mbarrier).
@@ -816,7 +826,7 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
 // be spread evenly over the 592 warp schedulers of a B200 (3.46 each: the schedulers holding four set the pace);
 // three full warps and one half warp per scheduler can (3.5 units each).
 template <class M, int D, int G, int ALGO, int Q, bool STREAM, bool MIXED>
-__global__ void __launch_bounds__(MH_MAX_BLOCK, M::MIN_BLOCKS) mh_step_kernel(const __grid_constant__ MhParams p) {
+__global__ void __launch_bounds__(StepBounds<M>::MAX_BLOCK, StepBounds<M>::MIN_BLOCKS) mh_step_kernel(const __grid_constant__ MhParams p) {
     TileStream<M::NC> ts;
     M::block_init();
     ts.init(p.prob.records, p.prob.n_points, p.tile_points);

@@ -174,7 +174,7 @@ struct PolyModel {
 template <bool REP>
 struct ArrheniusModelT {
     using Rep = ArrheniusModelT<true>;
-    static constexpr bool HAS_REP = !REP;
+    static constexpr bool IS_REP = REP;
     static constexpr bool HAS_MULTI = false;
     static constexpr int NPARAM = 4;
     static constexpr int NC = 4;

@@ -9,6 +9,7 @@ struct MhKernelEntry {
     int streamed;             // 0: records resident in shared memory, 1: streamed in tiles
     int mixed;                // 1: the last warps of a block use 2 * lanes per chain
     int coop;                 // 1: cooperative teams (pbu_mh_coop.cuh): `lanes` lanes own `chains_per_thread` (= lanes) chains
+    int rep;                  // 1: the model's lookup tables are conflict-free replicas in dynamic shared memory (Model::Rep): blocks of up to 1024 threads, one per SM
     const void *fn;   // __global__ void (*)(const MhParams)
 };
 struct IsdeKernelEntry {

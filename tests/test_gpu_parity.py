@@ -103,9 +103,23 @@ def test_mh_golden_parity(case, lanes):
 def test_many_chains_vs_oracle(builder, lanes, algo_name):
     """64 different chains (own start, own streams) against the CPU oracle, chain by chain.  (arrhenius, 2): speculative
     delayed rejection -- a pair of lanes evaluates both proposal stages of a chain at once."""
-    from pybitup_b200 import synthetic
     if builder == "arrhenius_problem" and lanes == 2 and algo_name not in ("DR", "DRAM"):
         pytest.skip("the two-lane layout of a sequential model is the speculative delayed rejection")
+    _many_chains(builder, lanes, algo_name)
+
+
+@pytest.mark.parametrize("algo_name", ["RWMH", "AMH", "DR", "DRAM"])
+def test_replicated_tables_step_kernel_vs_oracle(algo_name, monkeypatch):
+    """The Arrhenius step kernels with the conflict-free replicated exp2 / log2 tables (192 KB of shared memory, what the
+    planner picks when the chains fill the GPU), forced here for 64 chains: same chains as the oracle's."""
+    lanes = 2 if algo_name in ("DR", "DRAM") else 1
+    monkeypatch.setenv("PBU_FORCE_VARIANT", "%d,1,0,0,1" % lanes)
+    geo = _many_chains("arrhenius_problem", lanes, algo_name)
+    assert geo["smem_bytes"] > 190000 and geo["lanes"] == lanes
+
+
+def _many_chains(builder, lanes, algo_name):
+    from pybitup_b200 import synthetic
     kwargs = {"linear_problem": {}, "cubic_problem": {"n_points": 257}, "heat_problem": {},
               "arrhenius_problem": {"n_steps": 40, "dT": 15.0}}[builder]
     p = getattr(synthetic, builder)(**kwargs)
@@ -120,6 +134,7 @@ def test_many_chains_vs_oracle(builder, lanes, algo_name):
     algo = {"name": algo_name, "AMH": {"updating_it": 7, "eps_v": 1e-10}, "DR": {"gamma": 0.3},
             "DRAM": {"updating_it": 7, "eps_v": 1e-10, "gamma": 0.3}}
     eng = _engine(p, algo, n_chains, lanes_per_chain=abs(lanes), cooperative=(1 if lanes < 0 else -1))
+    geo = eng.launch_geometry()
     eng.init_chains(x0, p["prop_cov"])
     _, lp_init = eng.state()
     eng.set_streams(normals, uniforms)
@@ -139,6 +154,7 @@ def test_many_chains_vs_oracle(builder, lanes, algo_name):
         assert H.rel_err(lp_fin[c], out["lp"][-1]) < tol
         assert H.rel_err(lp_init[c], out["lp"][0]) < 1e-12
     eng.close()
+    return geo
 
 
 @pytest.mark.parametrize("algo_name", ["AMH", "DRAM"])

@@ -4,6 +4,8 @@
               chains (every lane reads the same table entry: a broadcast) against dispersed ones.
   lanes       cfg 3 (Arrhenius DRAM): one lane per chain against the speculative pair (both delayed-rejection stages
               evaluated at once), over chain counts and block sizes.
+  rep         cfg 3: plain lookup tables against the conflict-free replicas (192 KB of shared memory, one block per SM), over
+              chain counts and block sizes.
 """
 import os
 import sys
@@ -64,5 +66,22 @@ def lanes():
                     print("C=%d lanes=%d block=%d %s: %.2f ms  %.4e chain-steps/s" % (C, L, B, eng.launch_geometry(), ms, C * T / ms * 1e3), flush=True)
 
 
+def rep():
+    p = synthetic.arrhenius_problem()
+    T = 20
+    for C in (262144, 131072, 65536, 32768, 8192):
+        for force, B in (("2,1,0,0,0", 0), ("2,1,0,0,1", 0), ("2,1,0,0,1", 1024), ("2,1,0,0,1", 896), ("2,1,0,0,1", 768), ("2,1,0,0,1", 512), ("", 0)):
+            if force:
+                os.environ["PBU_FORCE_VARIANT"] = force
+            else:
+                os.environ.pop("PBU_FORCE_VARIANT", None)
+            cfg = SamplerConfig(algo="DRAM", seed=1, updating_it=10, eps_v=1e-10, gamma_dr=0.2, block_threads=B)
+            with ChainEngine(ProblemSpec.from_dict(p), cfg, C) as eng:
+                eng.init_chains(synthetic.chain_starts(p["x0"], C, jitter=1e-3, seed=0), p["prop_cov"])
+                eng.run(T, thin=T, keep_samples=False)
+                ms = timed(lambda: eng.run(T, thin=T, keep_samples=False))
+                print("C=%d force=[%s] block=%d %s: %.2f ms  %.4e chain-steps/s" % (C, force, B, eng.launch_geometry(), ms, C * T / ms * 1e3), flush=True)
+
+
 if __name__ == "__main__":
-    {"conflicts": conflicts, "lanes": lanes}[sys.argv[1]]()
+    {"conflicts": conflicts, "lanes": lanes, "rep": rep}[sys.argv[1]]()
