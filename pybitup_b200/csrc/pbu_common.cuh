@@ -183,10 +183,20 @@ struct Philox {
 // function unit does the transcendental work (lg2.approx, sin/cos.approx on an argument reduced to [-pi, pi), sqrt
 // .approx): absolute error ~2^-21 on the uniform scale, i.e. the proposal draws are float-accurate normals, at a
 // quarter of the instructions of logf / sincospif.  (Parity runs inject their draws and never come here.)
+// sqrt(-2 ln u) for u in [2^-33, 1]: lg2.approx and sqrt.approx straight on the special function unit (one MUFU each).
+// __log2f / __fsqrt_rn wrap them in a denormal rescue and a Newton step with a slow-path branch: 14 instructions more
+// per pair, for digits a float-accurate normal does not have.  u is never denormal and the argument of the square root
+// is 0 or at least 2^-23, so the .ftz forms lose nothing.
+__device__ __forceinline__ float bm_radius(float u) {
+    float l, s;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(-1.3862943611198906f * l));
+    return s;
+}
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, double &z0, double &z1) {
     const float u = (float)a * 2.3283064365386963e-10f + 1.1641532182693481e-10f;   // (0,1]
     const float ang = (float)(int32_t)b * 1.4629180792671596e-09f;                   // 2 pi * b / 2^32 in [-pi, pi)
-    const float s = __fsqrt_rn(-1.3862943611198906f * __log2f(u));                   // sqrt(-2 ln u)
+    const float s = bm_radius(u);                                                    // sqrt(-2 ln u)
     z0 = (double)(s * __cosf(ang));
     z1 = (double)(s * __sinf(ang));
 }
@@ -197,7 +207,7 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, double &z0, d
 __device__ __forceinline__ void box_muller24(uint32_t a, uint32_t b, double &z0, double &z1) {
     const float u = (float)(a >> 8) * 5.9604644775390625e-08f + 2.98023223876953125e-08f;    // (k + 1/2) 2^-24 in (0,1)
     const float ang = (float)((int32_t)b >> 8) * 3.7450702829238284e-07f;                     // 2 pi k / 2^24 in [-pi, pi)
-    const float s = __fsqrt_rn(-1.3862943611198906f * __log2f(u));
+    const float s = bm_radius(u);
     z0 = (double)(s * __cosf(ang));
     z1 = (double)(s * __sinf(ang));
 }

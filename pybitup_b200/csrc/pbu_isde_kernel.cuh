@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(MH_MAX_BLOCK, M::MIN_BLOCKS) hmc_step_kernel(c
             for (int i = 0; i < D; ++i) k = __dadd_rn(k, __dmul_rn(CP[i], pf[i]));
             const double Knew = k / 2.0;
             n_eval[q] += 1;                                // distr_fun(new_val) (:868)
-            double r = exp(__dadd_rn(__dadd_rn(__dadd_rn(-lp[q], lpn[q]), Kcur[q]), -Knew));                    // :879
+            double r = pbu_exp_full(__dadd_rn(__dadd_rn(__dadd_rn(-lp[q], lpn[q]), Kcur[q]), -Knew));                    // :879
             if (r != r) {
                 status[q] |= ST_NAN_RATIO;
                 r = 0.0;

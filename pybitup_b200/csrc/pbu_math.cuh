@@ -71,6 +71,51 @@ PBU_HD double pbu_exp(double x) {
     return tiny ? 0.0 : res;
 }
 
+// exp(x) over the whole domain, for the acceptance ratios (mha.py:200-207, :547-556): +inf from 708 (numpy overflows to
+// inf from 709.78: alpha = 1 either way), 0 below -708 (numpy: 3e-308 and denormals -- below any uniform and
+// invisible in a sum), NaN for NaN.  The degree-10 polynomial of pbu_exp with its coefficients read by the FMAs from the constant bank: CUDA's
+// exp() builds each of its constants with two UMOVs inside the caller's loop, 22 instruction-issue slots per call.
+#ifdef __CUDACC__
+static __constant__ double pbu_exp_kc[14] = {1.4426950408889634, -0.6931471803691238, -1.9082149292705877e-10, 2.5100375832561234e-08,
+                                              2.7620075879983367e-07, 2.7557268480310024e-06, 2.4801521322368692e-05, 0.00019841269863040545,
+                                              0.0013888888917196719, 0.008333333333330065, 0.041666666666624164, 0.16666666666666669,
+                                              0.5000000000000001, 0.0};
+#endif
+#ifdef __CUDA_ARCH__
+#define PBU_EXP_KC(i, lit) pbu_exp_kc[i]
+#else
+#define PBU_EXP_KC(i, lit) (lit)
+#endif
+PBU_HD double pbu_exp_full(double x) {
+    const double SHIFT = 6755399441055744.0;                     // 1.5 * 2^52
+    const double t = fma(x, PBU_EXP_KC(0, 1.4426950408889634), SHIFT);
+    const double kf = t - SHIFT;
+    const int32_t k = (int32_t)(uint32_t)(
+#ifdef __CUDA_ARCH__
+        __double2loint(t)
+#else
+        [](double v) { uint64_t b; memcpy(&b, &v, 8); return (int32_t)(uint32_t)b; }(t)
+#endif
+    );
+    double r = fma(kf, PBU_EXP_KC(1, -0.6931471803691238), x);
+    r = fma(kf, PBU_EXP_KC(2, -1.9082149292705877e-10), r);
+    double p = fma(PBU_EXP_KC(3, 2.5100375832561234e-08), r, PBU_EXP_KC(4, 2.7620075879983367e-07));
+    p = fma(p, r, PBU_EXP_KC(5, 2.7557268480310024e-06));
+    p = fma(p, r, PBU_EXP_KC(6, 2.4801521322368692e-05));
+    p = fma(p, r, PBU_EXP_KC(7, 0.00019841269863040545));
+    p = fma(p, r, PBU_EXP_KC(8, 0.0013888888917196719));
+    p = fma(p, r, PBU_EXP_KC(9, 0.008333333333330065));
+    p = fma(p, r, PBU_EXP_KC(10, 0.041666666666624164));
+    p = fma(p, r, PBU_EXP_KC(11, 0.16666666666666669));
+    p = fma(p, r, PBU_EXP_KC(12, 0.5000000000000001));
+    const double v = 1.0 + fma(r * r, p, r);                     // in [0.70, 1.42]
+    double res = with_hi_word(v, hi_word(v) + (k << 20));        // * 2^k on the exponent field: k in [-1021, 1023] for |x| < 708
+    // |x| >= 708 (one integer compare on the hi word; inf and NaN land here too): the rare path
+    const int32_t hx = hi_word(x);
+    if (((uint32_t)hx & 0x7FFFFFFFu) >= 0x40862000u) res = (x != x) ? x : ((hx < 0) ? 0.0 : (double)INFINITY);
+    return res;
+}
+
 // log(u) for normal u > 0 (no zero / denormal / inf / nan handling)
 PBU_HD double pbu_log(double u) {
     int32_t hi = hi_word(u);

@@ -72,7 +72,7 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
                 double sj[D];                                                   // new = cur + scale * R @ z, R upper (:193, :543)
                 upper_matvec<D>([&](int i, int j) { return ADAPT ? p.st.R[(int64_t)tri_idx(D, i, j) * sS + c] : p.R0[tri_idx(D, i, j)]; }, z, sj);
 #pragma unroll
-                for (int i = 0; i < D; ++i) y[i] = __dadd_rn(x[i], __dmul_rn(scale, sj[i]));
+                for (int i = 0; i < D; ++i) y[i] = __dadd_rn(x[i], (stage == 0) ? sj[i] : __dmul_rn(scale, sj[i]));      // (1.0 * v == v exactly)
                 n_eval += 1;
             }
             double Xown[D], ldj_own;                // X = parametrization_backward(Y) (bayesian_inference.py:50); X = Y when not re-parametrised
@@ -155,7 +155,7 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
                 bool accept;
                 if (stage == 0) {
                     lp1 = lpy;
-                    r = (lp1 == -INFINITY) ? 0.0 : exp(lp1 - lp);                      // :200-205
+                    r = (lp1 == -INFINITY) ? 0.0 : pbu_exp_full(lp1 - lp);                      // :200-205
                     if (r != r) {
                         status |= ST_NAN_RATIO;
                         if (p.nan_rejects) r = 0.0;
@@ -164,7 +164,7 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
                     accept = u < alpha;                                                 // :214
                 } else {
                     lp2 = lpy;
-                    const double a12 = py_min1(exp(lp1 - lp2));                         // :547-548
+                    const double a12 = py_min1(pbu_exp_full(lp1 - lp2));                         // :547-548
                     double M2 = 0.0, M4 = 0.0;                                          // inv_V = diag(1/R_ii^2)
 #pragma unroll
                     for (int i = 0; i < D; ++i) {
@@ -177,7 +177,7 @@ __device__ __forceinline__ void mh_coop_loop(const MhParams &p, TileStream<M::NC
                         M2 += (d1 * iv) * d1;
                         M4 += (d2 * iv) * d2;
                     }
-                    double r2 = exp(lp2 - lp) * (exp(-0.5 * M2) / exp(-0.5 * M4)) * (1.0 - a12) / (1.0 - alpha);     // :555-556
+                    double r2 = pbu_exp_full(lp2 - lp) * (pbu_exp_full(-0.5 * M2) / pbu_exp_full(-0.5 * M4)) * (1.0 - a12) / (1.0 - alpha);     // :555-556
                     if (r2 != r2) {
                         status |= ST_NAN_RATIO;
                         if (p.nan_rejects) r2 = 0.0;

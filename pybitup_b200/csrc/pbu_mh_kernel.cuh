@@ -565,7 +565,7 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
                     upper_matvec<D>([&](int i, int j) { return ADAPT ? p.st.R[(int64_t)tri_idx(D, i, j) * C + c[q]] : p.R0[tri_idx(D, i, j)]; }, z, sj);
                     const double scale = (st == 0) ? 1.0 : p.gamma_dr;
 #pragma unroll
-                    for (int i = 0; i < D; ++i) ysp[st][q][i] = __dadd_rn(x[q][i], __dmul_rn(scale, sj[i]));
+                    for (int i = 0; i < D; ++i) ysp[st][q][i] = __dadd_rn(x[q][i], (st == 0) ? sj[i] : __dmul_rn(scale, sj[i]));      // (1.0 * v == v exactly)
                 }
 #pragma unroll
                 for (int i = 0; i < D; ++i) ysel[q][i] = (sub == 0) ? ysp[0][q][i] : ysp[1][q][i];
@@ -608,7 +608,7 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
                 double sj[D];
                 upper_matvec<D>([&](int i, int j) { return ADAPT ? p.st.R[(int64_t)tri_idx(D, i, j) * C + c[q]] : p.R0[tri_idx(D, i, j)]; }, z, sj);
 #pragma unroll
-                for (int i = 0; i < D; ++i) y[q][i] = __dadd_rn(x[q][i], __dmul_rn(scale, sj[i]));
+                for (int i = 0; i < D; ++i) y[q][i] = __dadd_rn(x[q][i], (stage == 0) ? sj[i] : __dmul_rn(scale, sj[i]));      // (1.0 * v == v exactly)
                 n_eval[q] += 1;
             }
             if constexpr (SPEC) {
@@ -624,7 +624,7 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
                 bool accept;
                 if (stage == 0) {
                     lp1[q] = lpy[q];
-                    r[q] = (lp1[q] == -INFINITY) ? 0.0 : exp(lp1[q] - lp[q]);         // :200-205 (full-domain exp: the difference may be anything)
+                    r[q] = (lp1[q] == -INFINITY) ? 0.0 : pbu_exp_full(lp1[q] - lp[q]);         // :200-205 (full-domain exp: the difference may be anything)
                     if (r[q] != r[q]) {
                         status[q] |= ST_NAN_RATIO;
                         if (p.nan_rejects) r[q] = 0.0;
@@ -633,7 +633,7 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
                     accept = u[q] < alpha[q];                                           // :214
                 } else {
                     lp2[q] = lpy[q];
-                    const double r12 = exp(lp1[q] - lp2[q]);                            // :547
+                    const double r12 = pbu_exp_full(lp1[q] - lp2[q]);                            // :547
                     const double a12 = py_min1(r12);
                     // inv_V = inv_R * inv_R^T ELEMENTWISE = diag(1/R_ii^2)  (:517-518, :594-595)
                     double M2 = 0.0, M4 = 0.0;
@@ -647,7 +647,7 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
                         M2 += (d1 * iv) * d1;
                         M4 += (d2 * iv) * d2;
                     }
-                    double r2 = exp(lp2[q] - lp[q]) * (exp(-0.5 * M2) / exp(-0.5 * M4)) * (1.0 - a12) / (1.0 - alpha[q]);   // :555-556
+                    double r2 = pbu_exp_full(lp2[q] - lp[q]) * (pbu_exp_full(-0.5 * M2) / pbu_exp_full(-0.5 * M4)) * (1.0 - a12) / (1.0 - alpha[q]);   // :555-556
                     if (r2 != r2) {
                         status[q] |= ST_NAN_RATIO;
                         if (p.nan_rejects) r2 = 0.0;

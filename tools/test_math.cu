@@ -15,12 +15,13 @@ static double ulp_err(double got, double ref) {
 int main() {
     std::mt19937_64 rng(1);
     std::uniform_real_distribution<double> ue(-700.0, 700.0), us(-60.0, 20.0), u01(0.0, 1.0);
-    double me = 0, ml = 0, mp = 0, met = 0, mlt = 0, mpt = 0, mst = 0;
+    double mef = 0, me = 0, ml = 0, mp = 0, met = 0, mlt = 0, mpt = 0, mst = 0;
     long bad = 0;
     const double *tab = pbu::pbu_math_tables_host;
     for (long i = 0; i < 20000000; ++i) {
         double x = (i & 1) ? ue(rng) : us(rng);
         me = fmax(me, ulp_err(pbu::pbu_exp(x), exp(x)));
+        mef = fmax(mef, ulp_err(pbu::pbu_exp_full(x), exp(x)));
         double u = (i % 3 == 0) ? u01(rng) : ((i % 3 == 1) ? exp(-40.0 * u01(rng)) : 1.0 - 1e-3 * u01(rng) * u01(rng));
         if (u <= 0.0) continue;
         const double l = pbu::pbu_log(u), lr = log(u);
@@ -51,5 +52,9 @@ int main() {
     printf("edge: exp2_tab(0)=%.17g log2_tab(1)=%.17g log2_tab(1-2^-53)=%.17g (ref %.17g) log2_tab(0.5)=%.17g exp2_tab(-1022.5)=%g\n",
            pbu::pbu_exp2_tab(0.0, tab), pbu::pbu_log2_tab(1.0, tab), pbu::pbu_log2_tab(1.0 - ldexp(1.0, -53), tab),
            log2(1.0 - ldexp(1.0, -53)), pbu::pbu_log2_tab(0.5, tab), pbu::pbu_exp2_tab(-1022.5, tab));
+    printf("pbu_exp_full: max ulp error %.3f; exp(-inf)=%g exp(inf)=%g exp(nan)=%g exp(708.5)=%g exp(-708.5)=%g exp(707.9)=%.17g (ref %.17g) exp(-707.9)=%.17g (ref %.17g) exp(0)=%.17g\n", mef,
+           pbu::pbu_exp_full(-INFINITY), pbu::pbu_exp_full(INFINITY), pbu::pbu_exp_full(NAN), pbu::pbu_exp_full(708.5), pbu::pbu_exp_full(-708.5),
+           pbu::pbu_exp_full(707.9), exp(707.9), pbu::pbu_exp_full(-707.9), exp(-707.9), pbu::pbu_exp_full(0.0));
+    if (!(mef < 2.0 && pbu::pbu_exp_full(-INFINITY) == 0.0 && std::isinf(pbu::pbu_exp_full(INFINITY)) && std::isnan(pbu::pbu_exp_full(NAN)) && pbu::pbu_exp_full(0.0) == 1.0)) return 1;
     return (me < 2.0 && ml < 2.5 && mp < 2e-14 && met < 2.5 && mlt < 2.5 && mpt < 2e-14 && mst < 3e-14) ? 0 : 1;
 }
