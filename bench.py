@@ -414,8 +414,12 @@ def run_gpu_arm(args):
     eng = ChainEngine(spec, cfg, C, device=local_rank)
     eng.init_chains(x0, p["prop_cov"])
     geom = eng.launch_geometry()
-    coop = geom["chains_per_thread"] == geom["lanes"] and geom["lanes"] > 1      # teams of G lanes own G chains
-    kernel_name = "%s<PolyModel<4>,D=4,G=%d,ALGO=AM>" % ("mh_coop_kernel" if coop else "mh_step_kernel", geom["lanes"])
+    coop = bool(geom["cooperative"])                                              # teams of G lanes own G chains
+    # PolyModelU: the uniform-weight form of the polynomial model (one std_y for all points: the weight is folded into the
+    # coefficients once per evaluation, records [x | w*y]; pbu_models.cuh) -- picked by the engine when the data allow it
+    kernel_name = "%s<%s<4>,D=4,G=%d,ALGO=AM%s>" % ("mh_coop_kernel" if coop else "mh_step_kernel",
+                                                     "PolyModelU" if geom["uniform_weight"] else "PolyModel", geom["lanes"],
+                                                     ",MIXED" if geom["mixed"] else "")
     for _ in range(W):
         eng.run(T, thin=T, keep_samples=True)
     barrier()
@@ -545,6 +549,8 @@ def run_gpu_arm(args):
                          "frac": achieved / fp64_peak, "traffic": None,
                          "kernel": kernel_name, "launch": geom,
                          "flops_per_chain_step": FLOPS_PER_CHAIN_STEP,
+                         "fp64_instructions_per_point": "5 = 3 Horner DFMA + 1 residual (DFMA -f*w + w*y; a DADD w*y - (w f) in the uniform-weight "
+                                                        "form) + 1 square-accumulate DFMA: the same count in both forms",
                          "peak_source": "live DFMA micro-benchmark on this GPU, sustained over ~0.7 s of back-to-back launches "
                                         "(pbu_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                          "peak_burst": fp64_burst, "ms_per_launch": {"min": float(min(ms)), "median": float(np.median(ms)),

@@ -219,6 +219,9 @@ int pbu_engine_get_isde_state(pbu_engine *e, double *P_host, double *C_host);
  * chains per thread, blocks, dynamic shared memory bytes per block (diagnostics; no reference counterpart). */
 int pbu_engine_get_launch(const pbu_engine *e, int32_t *lanes, int32_t *chains_per_thread, int32_t *block, int32_t *grid,
                           int64_t *smem_bytes);
+/* which compiled variant of the step kernel that is: mixed warp widths, cooperative teams, replicated lookup tables,
+ * uniform-weight records (0 / 1 each; diagnostics, no reference counterpart). */
+int pbu_engine_get_variant(const pbu_engine *e, int32_t *mixed, int32_t *cooperative, int32_t *replicated_tables, int32_t *uniform_weight);
 
 /* ---- evaluation only: BayesianPosterior.compute_log_value (bayesian_inference.py:44-64) and
  *      Model.run_model (:338-371) for S parameter vectors -------------------------------------- */

@@ -97,6 +97,7 @@ def _load():
         "pbu_engine_iteration": (C.c_int64, [E]),
         "pbu_engine_get_isde_state": (C.c_int, [E, _dp, _dp]),
         "pbu_engine_get_launch": (C.c_int, [E, _ip, _ip, _ip, _ip, _lp]),
+        "pbu_engine_get_variant": (C.c_int, [E, _ip, _ip, _ip, _ip]),
         "pbu_eval_logpost": (C.c_int, [E, _dp, C.c_int64, _dp]),
         "pbu_eval_model": (C.c_int, [E, _dp, C.c_int64, _dp]),
         "pbu_engine_chain_sums_len": (C.c_int, [E]),

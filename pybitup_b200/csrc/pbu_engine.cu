@@ -92,12 +92,12 @@ extern "C" __attribute__((visibility("default"))) int pbu_list_kernels(char *buf
     return total;
 }
 
-static const MhKernelEntry *find_mh(int model, int P, int d, int lanes, int q, int algo, int streamed, int mixed = 0, int coop = 0, int rep = 0) {
+static const MhKernelEntry *find_mh(int model, int P, int d, int lanes, int q, int algo, int streamed, int mixed = 0, int coop = 0, int rep = 0, int uniform_w = 0) {
     int n = 0;
     const MhKernelEntry *t = pbu_mh_kernels(&n);
     for (int i = 0; i < n; ++i)
         if (t[i].model == model && t[i].n_param == P && t[i].n_unc == d && t[i].lanes == lanes && t[i].chains_per_thread == q &&
-            t[i].algo == algo && t[i].streamed == streamed && t[i].mixed == mixed && t[i].coop == coop && t[i].rep == rep)
+            t[i].algo == algo && t[i].streamed == streamed && t[i].mixed == mixed && t[i].coop == coop && t[i].rep == rep && t[i].uniform_w == uniform_w)
             return &t[i];
     return nullptr;
 }
@@ -217,10 +217,13 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
     // (lanes, chains per thread or per team, mixed, coop): mixed = the last warps of a block use twice the lanes;
     // coop = teams of `lanes` lanes own `lanes` chains (pbu_mh_coop.cuh)
     // rep = the model's lookup tables as conflict-free replicas (192 KB of shared memory, one block of up to 1024 threads per SM)
-    const int cand[13][5] = {{1, 1, 0, 0, 0}, {1, 2, 0, 0, 0}, {2, 2, 0, 0, 0}, {2, 2, 1, 0, 0}, {4, 2, 0, 0, 0}, {2, 1, 0, 0, 0}, {4, 1, 0, 0, 0},
-                             {8, 1, 0, 0, 0}, {4, 4, 0, 1, 0}, {4, 4, 1, 1, 0}, {1, 2, 1, 0, 0}, {1, 1, 0, 0, 1}, {2, 1, 0, 0, 1}};
+    // uni = the model's uniform-weight form (records [x | w*y], one shared-memory load per point): cooperative kernels only
+    const int cand[15][6] = {{1, 1, 0, 0, 0, 0}, {1, 2, 0, 0, 0, 0}, {2, 2, 0, 0, 0, 0}, {2, 2, 1, 0, 0, 0}, {4, 2, 0, 0, 0, 0}, {2, 1, 0, 0, 0, 0},
+                             {4, 1, 0, 0, 0, 0}, {8, 1, 0, 0, 0, 0}, {4, 4, 0, 1, 0, 0}, {4, 4, 1, 1, 0, 0}, {1, 2, 1, 0, 0, 0}, {1, 1, 0, 0, 1, 0},
+                             {2, 1, 0, 0, 1, 0}, {4, 4, 0, 1, 0, 1}, {4, 4, 1, 1, 0, 1}};
     const char *force = getenv("PBU_FORCE_VARIANT");      // "lanes,q,mixed,coop[,rep]": diagnostics
     const char *rep_env = getenv("PBU_REP_TABLES");       // 0: never the replicated tables (diagnostics)
+    const char *uni_env = getenv("PBU_UNIFORM_W");        // 0: never the uniform-weight kernels (diagnostics)
     const bool hmc = algo == PBU_ALGO_HMC;
     const bool isde = algo == PBU_ALGO_ISDE || hmc;
     const int streamed = e->tile_points < e->prob.n_points ? 1 : 0;
@@ -228,12 +231,13 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
     double best = 1e300;
     bool found = false;
     for (const auto &gq : cand) {
-        const int g = gq[0], q = gq[1], mixed = gq[2], coop = gq[3], rep = gq[4];
+        const int g = gq[0], q = gq[1], mixed = gq[2], coop = gq[3], rep = gq[4], uni = gq[5];
         if (rep && (isde || streamed || e->prob.n_blocks > 1 || (rep_env && atoi(rep_env) == 0))) continue;
+        if (uni && (!e->d_records_u || (uni_env && atoi(uni_env) == 0))) continue;
         if (force) {
-            int f[5] = {0, 0, 0, 0, 0};
-            sscanf(force, "%d,%d,%d,%d,%d", &f[0], &f[1], &f[2], &f[3], &f[4]);
-            if (f[0] != g || f[1] != q || f[2] != mixed || f[3] != coop || f[4] != rep) continue;
+            int f[6] = {0, 0, 0, 0, 0, 0};
+            sscanf(force, "%d,%d,%d,%d,%d,%d", &f[0], &f[1], &f[2], &f[3], &f[4], &f[5]);
+            if (f[0] != g || f[1] != q || f[2] != mixed || f[3] != coop || f[4] != rep || f[5] != uni) continue;
         } else {
             if (want_coop > 0 && !coop) continue;
             if (want_coop < 0 && coop) continue;
@@ -265,7 +269,7 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
             ki = hmc ? find_hmc(model, e->P, e->d, g, q, streamed) : find_isde(model, e->P, e->d, g, q, streamed, mixed);
             if (ki) fn = ki->fn;
         } else {
-            km = find_mh(model, e->P, e->d, g, q, algo, streamed, mixed, coop, rep);
+            km = find_mh(model, e->P, e->d, g, q, algo, streamed, mixed, coop, rep, uni);
             if (km) fn = km->fn;
         }
         if (!fn) continue;
@@ -277,7 +281,8 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
             return fail(PBU_ERR_UNSUPPORTED, "a step kernel uses %zu B of static shared memory, more than the %d B reserved", fattr.sharedSizeBytes, PBU_STATIC_SMEM_RESERVE);
         max_smem -= rep ? (int)fattr.sharedSizeBytes : PBU_STATIC_SMEM_RESERVE;      // (replicas: no tables in static shared memory)
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        const size_t rec_aligned = (e->smem_bytes + 127) & ~(size_t)127;
+        const size_t rec_bytes_k = uni ? e->smem_bytes_u : e->smem_bytes;
+        const size_t rec_aligned = (rec_bytes_k + 127) & ~(size_t)127;
         // replicated layout: a group of g lanes carries q chains per lane-set; cooperative: a team of g lanes owns q = g chains
         const int64_t groups_needed = (e->C + q - 1) / q;
         // 8 lanes reading 8 consecutive records collide in the shared-memory banks when the record stride is an even
@@ -293,12 +298,13 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
         // replicated tables: no bank conflicts among the 32 independent table indices of a warp (PBU_REP_GAIN: diagnostics)
         double rep_gain = 0.9;
         if (const char *rg = getenv("PBU_REP_GAIN")) rep_gain = atof(rg);
-        const double work = q * (sequential ? N : std::ceil(N / g)) * ops * conflict * evals * (rep ? rep_gain : 1.0) + (coop ? 1.0 : (double)q) * S0;
+        // uniform weight: 8 instead of 14 non-FP64 instructions per four points of the cooperative data loop
+        const double work = q * (sequential ? N : std::ceil(N / g)) * ops * conflict * evals * (rep ? rep_gain : 1.0) * (uni ? 0.97 : 1.0) + (coop ? 1.0 : (double)q) * S0;
         for (int B = (rep ? 1024 : MH_MAX_BLOCK); B >= 32; B -= 32) {
             if (want_block > 0 && B != want_block) continue;
             // cooperative kernels park the own chain's state (x, y, lp, mean_r, u: 2d + 3 doubles per thread, component stride
             // MH_MAX_BLOCK) behind the records for the duration of the data loop (pbu_mh_coop.cuh)
-            size_t smem_launch = e->smem_bytes;
+            size_t smem_launch = rec_bytes_k;
             int state_off = 0;
             if (rep) {
                 smem_launch = rec_aligned + 128 + PBU_REP_TABLE_BYTES;
@@ -348,6 +354,7 @@ static int plan_launch(pbu_engine *e, int model, bool sequential, int algo, int 
                     if (const char *sv = getenv("PBU_STAGGER")) e->stagger_cycles = coop ? atoi(sv) : 0;      // diagnostics
                     e->state_smem_off = state_off;
                     e->launch_smem = smem_launch;
+                    e->uniform_w_kernel = uni != 0;
                     found = true;
                 }
             }
@@ -554,6 +561,24 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_create(const pb
     CUDA_TRY(cudaMemcpyAsync(e->d_raw, raw.data(), raw.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     pd.records = e->d_records;
     pd.raw = e->d_raw;
+    // one weight for all points (and one model, resident records): the uniform-weight form of the records for the kernels of
+    // Model::Uniform (pbu_models.cuh: PolyModelU)
+    if (pr->model == PBU_MODEL_POLY && blocks.size() == 1 && e->tile_points >= pr->n_points) {
+        bool same = true;
+        for (int k = 1; k < pr->n_points && same; ++k) same = rec[(size_t)k * ev->nc + 1] == rec[1];
+        if (same) {
+            std::vector<double> ru((size_t)pr->n_points * 2);
+            for (int k = 0; k < pr->n_points; ++k) {
+                ru[2 * (size_t)k] = rec[(size_t)k * ev->nc];
+                ru[2 * (size_t)k + 1] = rec[(size_t)k * ev->nc + 2];
+            }
+            if ((rc = dev_alloc(e, &e->d_records_u, ru.size())) != PBU_OK) return rc;
+            CUDA_TRY(cudaMemcpyAsync(e->d_records_u, ru.data(), ru.size() * sizeof(double), cudaMemcpyHostToDevice, e->stream));
+            CUDA_TRY(cudaStreamSynchronize(e->stream));          // (ru is a local)
+            e->w_uniform = rec[1];
+            e->smem_bytes_u = 128 + ru.size() * sizeof(double);
+        }
+    }
 
     // ---- launch geometry
     if ((rc = plan_launch(e, pr->model, ev->sequential != 0, cfg->algo, cfg->lanes_per_chain, cfg->chains_per_thread, cfg->block_threads, cfg->cooperative)) != PBU_OK) {
@@ -807,6 +832,16 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_get_launch(cons
     return PBU_OK;
 }
 
+extern "C" __attribute__((visibility("default"))) int pbu_engine_get_variant(const pbu_engine *e, int32_t *mixed, int32_t *cooperative, int32_t *replicated_tables,
+                                                                                   int32_t *uniform_weight) {
+    if (!e) return fail(PBU_ERR_INVALID, "null engine");
+    if (mixed) *mixed = e->mh ? e->mh->mixed : (e->isde ? e->isde->mixed : 0);
+    if (cooperative) *cooperative = e->mh ? e->mh->coop : 0;
+    if (replicated_tables) *replicated_tables = e->mh ? e->mh->rep : 0;
+    if (uniform_weight) *uniform_weight = e->uniform_w_kernel ? 1 : 0;
+    return PBU_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine *e, int64_t n_steps, int64_t thin, const pbu_run_outputs *out) {
     if (!e) return fail(PBU_ERR_INVALID, "null engine");
     if (!e->initialised) return fail(PBU_ERR_INVALID, "pbu_engine_init_chains has not been called");
@@ -877,6 +912,11 @@ extern "C" __attribute__((visibility("default"))) int pbu_engine_run(pbu_engine 
     p.stagger_cycles = e->stagger_cycles;
     p.state_smem_off = e->state_smem_off;
     for (size_t i = 0; i < e->R0.size(); ++i) p.R0[i] = e->R0[i];
+    if (e->uniform_w_kernel) {          // the kernel of Model::Uniform: records [x | w*y], the weight in consts[7]
+        p.prob.records = e->d_records_u;
+        p.prob.ncol = 2;
+        p.prob.consts[7] = p.prob.blk[0].consts[7] = e->w_uniform;
+    }
     void *args[] = {(void *)&p};
     CUDA_TRY(cudaLaunchKernel(e->step_fn, dim3((unsigned)e->grid), dim3(e->block), args, e->launch_smem, e->stream));
     e->iteration += n_steps;

@@ -64,6 +64,12 @@ struct pbu_engine {
     bool r0_pending = false;
     // device allocations
     double *d_records = nullptr;
+    // uniform-weight form of the likelihood records ([x | w*y], Model::Uniform), when every point has the same weight and a
+    // model offers it; the step kernel the planner picked reads it when uniform_w_kernel is set
+    double *d_records_u = nullptr;
+    double w_uniform = 0.0;
+    size_t smem_bytes_u = 0;
+    bool uniform_w_kernel = false;
     double *d_raw = nullptr;
     pbu::ChainState st{};
     pbu::StreamsDev streams{};

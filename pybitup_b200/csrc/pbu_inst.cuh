@@ -6,16 +6,21 @@
 
 // S = 0: records resident in shared memory; S = 1: streamed in tiles (data sets larger than shared memory)
 #define PBU_MH(MODEL, P, D, G, Q, A, S) \
-    { MODEL::ID, P, D, G, Q, A, S, 0, 0, 0, (const void *)&pbu::mh_step_kernel<MODEL, D, G, A, Q, (S != 0), false> }
+    { MODEL::ID, P, D, G, Q, A, S, 0, 0, 0, 0, (const void *)&pbu::mh_step_kernel<MODEL, D, G, A, Q, (S != 0), false> }
 // resident records, replicated lookup tables (MODEL::Rep)
 #define PBU_MH_REP(MODEL, P, D, G, Q, A) \
-    { MODEL::ID, P, D, G, Q, A, 0, 0, 0, 1, (const void *)&pbu::mh_step_kernel<typename MODEL::Rep, D, G, A, Q, false, false> }
+    { MODEL::ID, P, D, G, Q, A, 0, 0, 0, 1, 0, (const void *)&pbu::mh_step_kernel<typename MODEL::Rep, D, G, A, Q, false, false> }
 // mixed: the last warps of each block use 2G lanes per chain (scheduler-level load balance)
 #define PBU_MH_MIXED(MODEL, P, D, G, Q, A) \
-    { MODEL::ID, P, D, G, Q, A, 0, 1, 0, 0, (const void *)&pbu::mh_step_kernel<MODEL, D, G, A, Q, false, true> }
+    { MODEL::ID, P, D, G, Q, A, 0, 1, 0, 0, 0, (const void *)&pbu::mh_step_kernel<MODEL, D, G, A, Q, false, true> }
 // cooperative: teams of G lanes own G chains (pbu_mh_coop.cuh); MX = 1: the last warps of a block use 2G lanes
 #define PBU_MH_COOP(MODEL, P, D, G, A, MX) \
-    { MODEL::ID, P, D, G, G, A, 0, MX, 1, 0, (const void *)&pbu::mh_coop_kernel<MODEL, D, G, A, false, (MX != 0)> }
+    { MODEL::ID, P, D, G, G, A, 0, MX, 1, 0, 0, (const void *)&pbu::mh_coop_kernel<MODEL, D, G, A, false, (MX != 0)> }
+// ... of the model's uniform-weight form (MODEL::Uniform)
+#define PBU_MH_COOP_U(MODEL, P, D, G, A, MX) \
+    { MODEL::ID, P, D, G, G, A, 0, MX, 1, 0, 1, (const void *)&pbu::mh_coop_kernel<typename MODEL::Uniform, D, G, A, false, (MX != 0)> }
+#define PBU_MH_COOP_U_ALGOS(MODEL, P, D, G, MX) \
+    PBU_MH_COOP_U(MODEL, P, D, G, 0, MX), PBU_MH_COOP_U(MODEL, P, D, G, 1, MX), PBU_MH_COOP_U(MODEL, P, D, G, 2, MX), PBU_MH_COOP_U(MODEL, P, D, G, 3, MX)
 #define PBU_MH_COOP_ALGOS(MODEL, P, D, G, MX) \
     PBU_MH_COOP(MODEL, P, D, G, 0, MX), PBU_MH_COOP(MODEL, P, D, G, 1, MX), PBU_MH_COOP(MODEL, P, D, G, 2, MX), PBU_MH_COOP(MODEL, P, D, G, 3, MX)
 #define PBU_MH_ALGOS(MODEL, P, D, G, Q, S) \

@@ -167,17 +167,18 @@ __device__ __forceinline__ void tile_accumulate(const typename M::Ctx (&ctx)[Q],
     } else {
         int k = sub;
         if constexpr (M::HAS_MULTI && !GRAD && (Q > 1)) {
-            // two batches of U points per trip: half the loop bookkeeping per point, the second batch's records in flight
-            // while the first is evaluated
+            // H batches of U points per trip: the loop bookkeeping shared by H * U points, the later batches' records in flight
+            // while the first is evaluated (H = 2; 4 for 16-byte records, which take one load and two registers per point)
+            constexpr int H = (NC <= 2) ? 4 : 2;
 #pragma unroll 1
-            for (; k + (2 * U - 1) * G < n; k += 2 * U * G) {
-                double rec[2][U][NC];
+            for (; k + (H * U - 1) * G < n; k += H * U * G) {
+                double rec[H][U][NC];
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+                for (int h = 0; h < H; ++h)
 #pragma unroll
                     for (int u = 0; u < U; ++u) load_record<NC>(tile, k + (h * U + u) * G, rec[h][u]);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < H; ++h) {
                     double t[Q][U];
                     M::template resid_multi<Q, U>(ctx, rec[h], t);
 #pragma unroll

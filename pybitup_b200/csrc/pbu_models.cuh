@@ -92,7 +92,10 @@ struct LinearModel {
 // POLY: Horner from the top coefficient (oracle/cpu_models.py::poly_horner)
 //   likelihood record [x | w | w*y | pad];  raw record [x | pad]
 template <int P>
+struct PolyModelU;
+template <int P>
 struct PolyModel {
+    using Uniform = PolyModelU<P>;
     static constexpr int NPARAM = P;
     static constexpr int NC = 4;
     static constexpr int NCR = 2;
@@ -155,6 +158,83 @@ struct PolyModel {
     }
     __device__ __forceinline__ static void grad_acc(const Ctx &, const double (&rec)[NC], double t, double (&g)[P]) {
         double s = t * rec[1];          // t_k w_k x^j
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            g[j] += s;
+            s *= rec[0];
+        }
+    }
+};
+
+// POLY with ONE weight for all points (std_y constant, the usual case): the weight goes onto the coefficients once per
+// evaluation -- w f(x) is the Horner polynomial of (w theta) -- and the likelihood record shrinks to [x | w*y], 16 bytes:
+// ONE shared-memory load per point instead of two (the data loop of the cooperative kernel issues 80 DFMAs and 14 other
+// instructions per four points, 10 of them loads).  Residual t = w*y - (w f)(x): the same 5 FP64 instructions per point;
+// rounding differs from PolyModel's fma(-f, w, w*y) by ~1e-16 relative.  consts[7] = w (set by the engine).
+template <int P>
+struct PolyModelU {
+    static constexpr int NPARAM = P;
+    static constexpr int NC = 2;
+    static constexpr int NCR = 2;
+    static constexpr bool SEQUENTIAL = false;
+    static constexpr bool HAS_GRAD = true;
+    static constexpr int ID = PBU_MODEL_POLY;
+    static constexpr int UNROLL = 4;
+    static constexpr int OPS = P + 1;
+    static constexpr int WF = 2;
+    static constexpr int MIN_BLOCKS = 1;
+    struct Ctx {
+        double th[P];      // w * theta
+        double w;
+    };
+    struct Seq {};
+    __device__ __forceinline__ static void begin(Ctx &c, const double (&theta)[P], const double *consts) {
+        c.w = consts[7];
+#pragma unroll
+        for (int j = 0; j < P; ++j) c.th[j] = theta[j] * c.w;
+    }
+    __device__ __forceinline__ static void block_init() {}
+    __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const double *) {}
+    template <int U>
+    __device__ __forceinline__ static void resid_batch(const Ctx &c, Seq &, const double (&rec)[U][NC], double (&t)[U]) {
+        double f[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) f[u] = c.th[P - 1];
+#pragma unroll
+        for (int j = P - 2; j >= 0; --j)
+#pragma unroll
+            for (int u = 0; u < U; ++u) f[u] = fma(f[u], rec[u][0], c.th[j]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) t[u] = rec[u][1] - f[u];
+    }
+    static constexpr bool HAS_MULTI = true;
+    template <int Q, int U>
+    __device__ __forceinline__ static void resid_multi(const Ctx (&c)[Q], const double (&rec)[U][NC], double (&t)[Q][U]) {
+        double f[Q][U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < Q; ++q) f[q][u] = c[q].th[P - 1];
+#pragma unroll
+        for (int j = P - 2; j >= 0; --j)
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int q = 0; q < Q; ++q) f[q][u] = fma(f[q][u], rec[u][0], c[q].th[j]);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < Q; ++q) t[q][u] = rec[u][1] - f[q][u];
+    }
+    __device__ __forceinline__ static double value(const Ctx &c, Seq &, const double *raw) {
+        const double x = raw[0];
+        double f = c.th[P - 1];
+#pragma unroll
+        for (int j = P - 2; j >= 0; --j) f = fma(f, x, c.th[j]);
+        return f / c.w;
+    }
+    __device__ __forceinline__ static void grad_acc(const Ctx &c, const double (&rec)[NC], double t, double (&g)[P]) {
+        double s = t * c.w;             // t_k w x^j
 #pragma unroll
         for (int j = 0; j < P; ++j) {
             g[j] += s;

@@ -28,6 +28,7 @@ const pbu::MhKernelEntry *pbu_mh_kernels(int *n) {
         append(v, pbu_mh_slice_poly_c);
         append(v, pbu_mh_slice_poly_d);
         append(v, pbu_mh_slice_poly_e);
+        append(v, pbu_mh_slice_poly_u);
         return v;
     }();
     *n = (int)all.size();

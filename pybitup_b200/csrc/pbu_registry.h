@@ -10,6 +10,7 @@ struct MhKernelEntry {
     int mixed;                // 1: the last warps of a block use 2 * lanes per chain
     int coop;                 // 1: cooperative teams (pbu_mh_coop.cuh): `lanes` lanes own `chains_per_thread` (= lanes) chains
     int rep;                  // 1: the model's lookup tables are conflict-free replicas in dynamic shared memory (Model::Rep): blocks of up to 1024 threads, one per SM
+    int uniform_w;            // 1: Model::Uniform -- one weight for all points, folded into the coefficients; records [x | w*y] (pbu_models.cuh)
     const void *fn;   // __global__ void (*)(const MhParams)
 };
 struct IsdeKernelEntry {
@@ -56,3 +57,4 @@ PBU_DECLARE_SLICE(linear_h)
 PBU_DECLARE_SLICE(poly_c)
 PBU_DECLARE_SLICE(poly_d)
 PBU_DECLARE_SLICE(poly_e)
+const pbu::MhKernelEntry *pbu_mh_slice_poly_u(int *n);

@@ -314,7 +314,10 @@ class ChainEngine:
         """(lanes per chain, threads per block, blocks, dynamic shared memory bytes) of the step kernel."""
         a, q, b, g, m = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
         capi.check(capi.lib.pbu_engine_get_launch(self._h, C.byref(a), C.byref(q), C.byref(b), C.byref(g), C.byref(m)))
-        return dict(lanes=a.value, chains_per_thread=q.value, block=b.value, grid=g.value, smem_bytes=m.value)
+        mx, co, rp, un = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        capi.check(capi.lib.pbu_engine_get_variant(self._h, C.byref(mx), C.byref(co), C.byref(rp), C.byref(un)))
+        return dict(lanes=a.value, chains_per_thread=q.value, block=b.value, grid=g.value, smem_bytes=m.value,
+                    mixed=mx.value, cooperative=co.value, replicated_tables=rp.value, uniform_weight=un.value)
 
     # -- the hot loop -------------------------------------------------------------------------
     def run(self, n_steps, thin=1, keep_samples=True, keep_lp=False, trace=False, out=None, sample_chains=None,

@@ -118,6 +118,46 @@ def test_replicated_tables_step_kernel_vs_oracle(algo_name, monkeypatch):
     assert geo["smem_bytes"] > 190000 and geo["lanes"] == lanes
 
 
+@pytest.mark.parametrize("algo_name", ["RWMH", "AMH", "DRAM"])
+def test_uniform_weight_kernel(algo_name, monkeypatch):
+    """Polynomial model, one std_y for all points: the engine picks the uniform-weight cooperative kernel (PolyModelU: the
+    weight folded into the coefficients, records [x | w*y]).  Same accept codes and states (rounding apart) as the general
+    kernel and as the oracle; unequal std_y fall back to the general kernel."""
+    from pybitup_b200 import synthetic
+    p = synthetic.cubic_problem(n_points=333)
+    prob = H.oracle_problem(p)
+    n_chains, T, d = 64, 50, prob.d
+    rng = np.random.default_rng(11)
+    x0 = synthetic.chain_starts(p["x0"], n_chains, jitter=1e-3, seed=2)
+    normals, uniforms = rng.standard_normal((n_chains, 2 * T * d)), rng.random((n_chains, 2 * T))
+    algo = {"name": algo_name, "AMH": {"updating_it": 7, "eps_v": 1e-10}, "DRAM": {"updating_it": 7, "eps_v": 1e-10, "gamma": 0.3}}
+    runs = {}
+    for uni in ("1", "0"):
+        monkeypatch.setenv("PBU_UNIFORM_W", uni)
+        eng = _engine(p, algo, n_chains, lanes_per_chain=4, cooperative=1)
+        assert eng.launch_geometry()["uniform_weight"] == int(uni) and eng.launch_geometry()["cooperative"] == 1
+        eng.init_chains(x0, p["prop_cov"])
+        eng.set_streams(normals, uniforms)
+        res = eng.run(T, thin=1, trace=True)
+        eng.synchronize()
+        runs[uni] = (res.samples.cpu().numpy(), res.trace_acc.cpu().numpy(), eng.state()[1])
+        eng.close()
+    assert np.array_equal(runs["1"][1], runs["0"][1])
+    assert H.rel_err(runs["1"][0], runs["0"][0]) < 1e-11 and H.rel_err(runs["1"][2], runs["0"][2]) < 1e-11
+    import tests.helpers as helpers
+    for c in range(0, n_chains, 7):
+        with orc.kernel_order():
+            out = orc.run_mh(prob, x0[c], p["prop_cov"], T, orc.Streams(normals[c], uniforms[c]), **helpers.mh_kwargs(algo))
+        assert np.array_equal(runs["1"][1][:, c], out["acc"])
+        assert H.rel_err(runs["1"][0][:, :, c], out["chain"][1:]) < 1e-9
+    monkeypatch.delenv("PBU_UNIFORM_W")
+    p2 = dict(p)
+    p2["std_y"] = p["std_y"] * (1.0 + 0.5 * rng.random(p["std_y"].shape))
+    eng = _engine(p2, algo, n_chains, lanes_per_chain=4, cooperative=1)
+    assert eng.launch_geometry()["uniform_weight"] == 0
+    eng.close()
+
+
 def _many_chains(builder, lanes, algo_name):
     from pybitup_b200 import synthetic
     kwargs = {"linear_problem": {}, "cubic_problem": {"n_points": 257}, "heat_problem": {},
