@@ -203,9 +203,9 @@ def cpu_baseline_leg():
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 FP64_INST_RK4 = 68.5         # FP64 instructions of one RK4 step of the Arrhenius kernels (137 per two steps, cuobjdump -sass)
-OTHER_INST_RK4 = 66.5        # the other instructions of that step: an FP64 instruction holds the issue port for two cycles, these for one
-FP64_INST_RK4_EVAL = 66.5    # the evaluation kernel of the propagation (no residual, no sum of squares): 133 FP64 + 136 other per two steps
-OTHER_INST_RK4_EVAL = 68.0
+OTHER_INST_RK4 = 62.5        # the other instructions of that step: an FP64 instruction holds the issue port for two cycles, these for one
+FP64_INST_RK4_EVAL = 66.5    # the evaluation kernel of the propagation (no residual, no sum of squares): 133 FP64 + 128 other per two steps
+OTHER_INST_RK4_EVAL = 64.0
 
 
 def _finite(o):

@@ -228,6 +228,16 @@ __device__ __forceinline__ uint32_t pbu_tab_base(const double *tab) {
 static __device__ const double pbu_math_extra_dev[PBU_MATH_EXTRA_DOUBLES] = {PBU_K_A4, PBU_K_B3S, -1.0 / 6.0, 0.0};
 #endif
 
+// The exp2 table as the kernels stage it in shared memory: entry j with j 2^10 taken off its hi word.  The scale 2^k then goes
+// onto the entry with ONE multiply-add on the integer m = 1024 k + j the reduction already has (m 2^10 + hi = k 2^20 + hi(T_j)),
+// instead of a shift and a multiply-add; the entry itself is never used unscaled.
+#ifdef __CUDACC__
+__device__ __forceinline__ double pbu_exp2_staged(int j) {
+    const double T = pbu_math_tables_dev[j];
+    return __hiloint2double(__double2hiint(T) - (j << 10), __double2loint(T));
+}
+#endif
+
 // 2^y for y < 1024, taking ys = PBU_EXP2_ENTRIES * y (the caller keeps its exponents in that unit: scaling by a power of two is exact,
 // and the reduction becomes three plain additions with immediate operands -- no constant held in a register).  The result is
 // forced to (almost) zero where y <= -1022 or where uh, the HI WORD of the caller's log argument u, is not that of a positive
@@ -266,12 +276,11 @@ PBU_HD double pbu_exp2_tab_scaled_sel_t(double ys, const double *tab, uint32_t r
     }
     // hi word of T 2^k where kept, 0 otherwise: two compares into one predicate, one multiply-add, one select
     double Ts;
-    asm("{\n\t.reg .pred p, q;\n\t.reg .s32 k, lo, hi;\n\t"
+    asm("{\n\t.reg .pred p, q;\n\t.reg .s32 lo, hi;\n\t"
         "setp.ge.s32 q, %3, 0x00100000;\n\t"                      // u positive and normal
         "setp.lt.and.u32 p, %2, 0xC12FF000, q;\n\t"               // ys > -1022 * 1024 (negative doubles order by magnitude as unsigned integers)
         "mov.b64 {lo, hi}, %1;\n\t"
-        "shr.s32 k, %4, 10;\n\t"
-        "mad.lo.s32 hi, k, 1048576, hi;\n\t"
+        "mad.lo.s32 hi, %4, 1024, hi;\n\t"                      // (1024 k + j) 2^10 + (hi(T_j) - j 2^10) = k 2^20 + hi(T_j): see pbu_exp2_staged
         "selp.b32 hi, hi, 0, p;\n\t"
         "mov.b64 %0, {lo, hi};\n\t}"
         : "=d"(Ts) : "d"(T), "r"(hi_word(ys)), "r"(uh), "r"(m));

@@ -330,7 +330,7 @@ struct ArrheniusModelT {
     __device__ __forceinline__ static void block_init() {
         if constexpr (REP) {
             double *t = rep_ptr();
-            for (int i = threadIdx.x; i < PBU_EXP2_ENTRIES * PBU_EXP2_REPLICAS; i += blockDim.x) t[i] = pbu_math_tables_dev[i / PBU_EXP2_REPLICAS];
+            for (int i = threadIdx.x; i < PBU_EXP2_ENTRIES * PBU_EXP2_REPLICAS; i += blockDim.x) t[i] = pbu_exp2_staged(i / PBU_EXP2_REPLICAS);
             double2 *t2 = reinterpret_cast<double2 *>(t + PBU_EXP2_ENTRIES * PBU_EXP2_REPLICAS);
             for (int i = threadIdx.x; i < PBU_LOG2_ENTRIES * PBU_LOG2_REPLICAS; i += blockDim.x) {
                 const int j = i / PBU_LOG2_REPLICAS;
@@ -340,7 +340,7 @@ struct ArrheniusModelT {
             if (threadIdx.x < PBU_MATH_EXTRA_DOUBLES) ex[threadIdx.x] = pbu_math_extra_dev[threadIdx.x];
         } else {
             double *t = tables();
-            for (int i = threadIdx.x; i < PBU_MATH_TABLE_DOUBLES; i += blockDim.x) t[i] = pbu_math_tables_dev[i];
+            for (int i = threadIdx.x; i < PBU_MATH_TABLE_DOUBLES; i += blockDim.x) t[i] = (i < PBU_EXP2_ENTRIES) ? pbu_exp2_staged(i) : pbu_math_tables_dev[i];
             if (threadIdx.x < PBU_MATH_EXTRA_DOUBLES) t[PBU_MATH_TABLE_DOUBLES + threadIdx.x] = pbu_math_extra_dev[threadIdx.x];
         }
     }
