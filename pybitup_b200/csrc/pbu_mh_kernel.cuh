@@ -524,7 +524,9 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
     int32_t to_refresh = ADAPT ? (int32_t)(p.updating_it - p.it0 % p.updating_it) : 0;   // iterations until it % updating_it == 0
     int32_t to_keep = (int32_t)(p.thin - p.it0 % p.thin);                                 // iterations until it % thin == 0
     int64_t row = 0;                                                                      // kept rows written by this launch
-    for (int64_t s = 0; s < p.n_steps; ++s) {
+    const bool tracing = p.out.trace_lp1 || p.out.trace_lp2 || p.out.trace_acc;         // (parity runs) tested once per iteration, not per pointer
+    const int32_t n_steps = (int32_t)p.n_steps;      // a launch is at most 2^31 iterations (checked on the host)
+    for (int32_t s = 0; s < n_steps; ++s) {
         const int64_t it = p.it0 + s + 1;
         // Up to two proposal stages share ONE inlined copy of the posterior evaluation (code size):
         // stage 0 = the Metropolis proposal (mha.py:184-224), stage 1 = the delayed-rejection
@@ -769,9 +771,11 @@ __device__ __forceinline__ void mh_chain_loop(const MhParams &p, TileStream<M::N
 
             // ---- outputs
             if (live[q] && sub == 0) {
-                if (p.out.trace_lp1) p.out.trace_lp1[s * C + cq] = lp1[q];
-                if (p.out.trace_lp2) p.out.trace_lp2[s * C + cq] = lp2[q];
-                if (p.out.trace_acc) p.out.trace_acc[s * C + cq] = (uint8_t)acc[q];
+                if (tracing) {
+                    if (p.out.trace_lp1) p.out.trace_lp1[s * C + cq] = lp1[q];
+                    if (p.out.trace_lp2) p.out.trace_lp2[s * C + cq] = lp2[q];
+                    if (p.out.trace_acc) p.out.trace_acc[s * C + cq] = (uint8_t)acc[q];
+                }
                 if (keep) {
                     // running (Welford) moments of the KEPT states, held in global memory so that they cost
                     // no registers in the data loop; input of the moment reduction (K4: pooled covariance, R-hat)
