@@ -1,8 +1,8 @@
 #!/bin/bash
 # one visit: the whole GPU suite, then the bench line (GPU arm only, every configuration)
 TAG=${1:-q}; OUT=gpurun_out; mkdir -p $OUT
-python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/pytest_$TAG.log
-python bench.py --no-cpu > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"
+timeout 240 python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/pytest_$TAG.log
+timeout 240 python bench.py --no-cpu > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"
 python - <<PY
 import json
 d=json.loads(open("$OUT/bench_$TAG.json").read().strip().splitlines()[-1])
