@@ -315,3 +315,20 @@ def test_cfg5_full_size_propagation():
     assert np.all(np.abs(st["mean"] - head.mean(axis=0))[live] < 5.0 * sd[live] / np.sqrt(20000))
     lo, hi = np.percentile(head, 2.5, axis=0), np.percentile(head, 97.5, axis=0)
     assert np.all(np.abs(st["ci_lb"] - lo)[live] < 0.1 * sd[live]) and np.all(np.abs(st["ci_ub"] - hi)[live] < 0.1 * sd[live])
+
+
+def test_planner_picks_the_measured_layouts():
+    """The launch the engine plans for the BASELINE shapes (what bench.py then measures): regression guard for the planner."""
+    from pybitup_b200 import synthetic
+    with _mk(synthetic.cubic_problem(), "AMH", 65536, updating_it=10, eps_v=1e-10) as eng:          # cfg 2
+        g = eng.launch_geometry()
+        assert (g["cooperative"], g["mixed"], g["uniform_weight"], g["lanes"], g["block"], g["grid"]) == (1, 1, 1, 4, 512, 147), g
+    with _mk(synthetic.arrhenius_problem(), "DRAM", 262144, updating_it=10, eps_v=1e-10, gamma_dr=0.2) as eng:      # cfg 3
+        g = eng.launch_geometry()
+        assert (g["replicated_tables"], g["lanes"], g["chains_per_thread"], g["block"]) == (1, 2, 1, 896), g
+    with _mk(synthetic.linear_problem(), "RWMH", 1 << 20) as eng:                                       # cfg 1b
+        g = eng.launch_geometry()
+        assert (g["lanes"], g["chains_per_thread"], g["cooperative"]) == (1, 2, 0), g
+    with _mk(synthetic.regression_problem(), "ISDE", 131072, isde_h=0.05, isde_f0=4.0, isde_gradient="Analytical") as eng:      # cfg 4
+        g = eng.launch_geometry()
+        assert (g["lanes"], g["chains_per_thread"], g["mixed"], g["grid"]) == (1, 2, 1, 147), g
