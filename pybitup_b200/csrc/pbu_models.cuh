@@ -414,7 +414,8 @@ struct HeatModel {
     __device__ __forceinline__ static void seq_init(const Ctx &, Seq &, const double *) {}
     __device__ __forceinline__ static double value(const Ctx &c, Seq &, const double *raw) {
         const double x = raw[0];
-        return c.c1 * exp(-c.gamma * x) + c.c2 * exp(c.gamma * x) + c.T_amb;
+        // (pbu_exp_full: <= 1 ulp, coefficients from the constant bank -- CUDA's exp() rebuilds its constants with 22 UMOVs per call)
+        return c.c1 * pbu_exp_full(-c.gamma * x) + c.c2 * pbu_exp_full(c.gamma * x) + c.T_amb;
     }
     template <int U>
     __device__ __forceinline__ static void resid_batch(const Ctx &c, Seq &s, const double (&rec)[U][NC], double (&t)[U]) {
